@@ -1,0 +1,207 @@
+"""Generate tests/golden/*.npz.  TEST INFRASTRUCTURE ONLY; runs in the build container only.
+
+    python -m oracle.make_golden
+
+Fixtures marked REFERENCE come from the reference's own, unmodified code
+(/root/reference/sim_plain.py, demo_maxcut.py) imported behind oracle/standin.  Fixtures
+marked RESTATEMENT come from oracle/restate.py for code the reference cannot run here
+(diffqc.cc needs Eigen, which is absent; the per-term product form is commented out in the
+reference); restate.py itself is pinned to the REFERENCE fixtures by tests/test_oracle.py.
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(HERE))
+
+from oracle import ref_loader, restate as R  # noqa: E402
+
+OUT = os.path.join(os.path.dirname(HERE), "tests", "golden")
+
+DEMO_GRAPH = [[0, 1], [0, 3], [1, 2], [2, 3]]       # demo_maxcut.py:11
+
+# H2 / STO-3G / Jordan-Wigner, R = 0.7414 A (textbook 4-qubit coefficients; the reference lists
+# the H2 VQE demo as TODO, README.md:27, and ships no Hamiltonian - SURVEY H10).
+H2_TERMS = [
+    ("IIII", -0.81261), ("ZIII", 0.171201), ("IZII", 0.171201), ("IIZI", -0.2227965),
+    ("IIIZ", -0.2227965), ("ZZII", 0.16862325), ("ZIZI", 0.12054625), ("ZIIZ", 0.165868),
+    ("IZZI", 0.165868), ("IZIZ", 0.12054625), ("IIZZ", 0.17434925), ("XXYY", -0.04532175),
+    ("XYYX", 0.04532175), ("YXXY", 0.04532175), ("YYXX", -0.04532175),
+]
+_P = {"I": np.eye(2, dtype=complex), "X": np.array([[0, 1], [1, 0]], dtype=complex),
+      "Y": np.array([[0, -1j], [1j, 0]]), "Z": np.array([[1, 0], [0, -1]], dtype=complex)}
+
+
+def pauli_string(s):
+    return R.multi_kron(*[_P[c] for c in s]).astype(np.complex128)
+
+
+def h2_problem():
+    """Config 2 inputs (builder-supplied): M = H2 Hamiltonian, drift = always-on ZZ chain,
+    controls = X_q and Y_q on each of 4 qubits, psi0 = Hartree-Fock |1100>."""
+    M = sum(c * pauli_string(s) for s, c in H2_TERMS)
+    H0 = 0.5 * sum(pauli_string(s) for s in ("ZZII", "IZZI", "IIZZ"))
+    Hs = []
+    for q in range(4):
+        for p in "XY":
+            Hs.append(pauli_string("".join(p if j == q else "I" for j in range(4))))
+    psi0 = np.zeros(16, dtype=np.complex128)
+    psi0[0b1100] = 1.0
+    omegas = np.full(len(Hs), 2.0)
+    return dict(M=M, H0=H0, Hs=np.array(Hs), psi0=psi0, omegas=omegas, T=1.5)
+
+
+def make_sim(sp, n_basis, basis, T, omegas, n_Hs, coeff, per_step=10):
+    sim = sp.SimulatorPlain(n_basis=n_basis, basis=basis, n_epoch=1, per_step=per_step)
+    sim.T = T
+    sim.omegas = list(omegas)
+    sim.n_Hs = n_Hs
+    sim.spectral_coeff = torch.tensor(coeff, requires_grad=True)
+    return sim
+
+
+def ref_H(sim, qp, H0, Hs, coeff):
+    """H list exactly as train_energy builds it: sim_plain.py:272-274."""
+    H = [qp.Qobj(H0)]
+    for i in range(len(Hs)):
+        H.append([qp.Qobj(Hs[i]), sim.generate_u(i, coeff.copy())])
+    return H
+
+
+def golden_dense_reference(sp, qp, name, H0, Hs, M, psi0, omegas, T, basis, n_basis, seed,
+                           per_step=10, n_samples=6):
+    """REFERENCE: SimulatorPlain.trotter and compute_energy_grad_MC on a dense problem."""
+    rng = np.random.RandomState(seed)
+    coeff = rng.normal(0, 1, [len(Hs), n_basis])
+    sim = make_sim(sp, n_basis, basis, T, omegas, len(Hs), coeff, per_step)
+    H = ref_H(sim, qp, H0, Hs, coeff)
+    q0 = qp.Qobj(psi0)
+    final = sim.trotter(H, q0, 0, T).full().reshape(-1)
+    energy = qp.Qobj(M).matrix_element(qp.Qobj(final), qp.Qobj(final))
+    n_steps, dt, ts = R.step_grid(0, T, per_step)
+    u_tab = np.array([[H[i + 1][1](t, None) for i in range(len(Hs))] for t in ts])
+    s_list, grads, phis = [], [], []
+    for k in range(n_samples):
+        np.random.seed(1000 + k)
+        state = np.random.get_state()
+        g = sim.compute_energy_grad_MC(qp.Qobj(M), H, q0).numpy().copy()
+        np.random.set_state(state)
+        s = np.random.uniform() * T           # sim_plain.py:167, same stream position
+        s_list.append(s)
+        grads.append(g)
+        phis.append(sim.trotter(H, q0, 0, s).full().reshape(-1))
+    np.savez(os.path.join(OUT, name + ".npz"), H0=H0, Hs=np.array(Hs), M=M, psi0=psi0,
+             omegas=np.array(omegas, dtype=float), T=T, n_basis=n_basis, basis=basis,
+             per_step=per_step, coeff=coeff, final=final, energy=energy, ts=ts, dt=dt, u_tab=u_tab,
+             s=np.array(s_list), grads=np.array(grads), phis=np.array(phis),
+             source="REFERENCE sim_plain.py:119-231 run unmodified behind oracle/standin")
+    print(name, "energy", energy.real, "|grad0|", np.linalg.norm(grads[0]))
+
+
+def golden_demo_training(name):
+    """REFERENCE: the shipped demo, demo_maxcut.py, run end to end with np.random.seed(0)."""
+    ns = ref_loader.run_demo_maxcut(seed=0)
+    sim = ns["sim"]
+    np.savez(os.path.join(OUT, name + ".npz"),
+             losses_energy=np.array(sim.losses_energy, dtype=float),
+             final_coeff=sim.spectral_coeff.detach().numpy(),
+             final_state=sim.final_state.full().reshape(-1),
+             cut_state=int(ns["state"]), prob=np.array(ns["prob"]),
+             H0=ns["H0"].full(), H_cost=ns["H_cost"].full(),
+             Hs=np.array([h.full() for h in ns["Hs"]]),
+             psi0=ns["superposition"].full().reshape(-1), T=sim.T, omegas=np.array(sim.omegas),
+             stdout_tail=ns["__stdout__"].strip().splitlines()[-1],
+             source="REFERENCE demo_maxcut.py:1-89, np.random.seed(0), 202 epochs")
+    print(name, ns["__stdout__"].strip().splitlines()[-1], sim.losses_energy[-1])
+
+
+def golden_split(name, n, edges, seed, per_step, n_samples=3):
+    """RESTATEMENT: the disabled per-term product (diffqc.cc:155-164).  For n <= 8 the dense
+    product of matrix exponentials is evaluated literally and stored next to the structured
+    form so tests can pin one against the other."""
+    prob = R.maxcut_structured(n, edges)
+    rng = np.random.RandomState(seed)
+    n_H = len(prob["terms"])
+    coeff = rng.normal(0, 1, [n_H, 6])
+    n_steps, dt, ts = R.step_grid(0, prob["T"], per_step)
+    u = R.coef_table_plain(coeff, prob["omegas"], prob["T"], ts)
+    final = R.evolve_split_structured(prob, u, dt, prob["psi0"])
+    extra = {}
+    if n <= 8:
+        H0, Hs, M = R.maxcut_dense(prob)
+        extra["final_dense_product"] = R.evolve_split_dense(H0, Hs, u, dt, prob["psi0"])
+    s_list = np.random.RandomState(seed + 1).uniform(size=n_samples) * prob["T"]
+    grads, ens = [], []
+    for s in s_list:
+        g, e = R.grad_mc_structured(prob, coeff, float(s), per_step, mode="split",
+                                    return_energies=True)
+        grads.append(g)
+        ens.append(e)
+    np.savez(os.path.join(OUT, name + ".npz"), n=n, edges=np.array(edges), coeff=coeff,
+             per_step=per_step, T=prob["T"], omegas=prob["omegas"], u=u, dt=dt, final=final,
+             energy=R.energy_diag(prob["m_diag"], final), s=s_list, grads=np.array(grads),
+             energies=np.array(ens),
+             source="RESTATEMENT oracle/restate.py evolve_split_structured (diffqc.cc:155-164)",
+             **extra)
+    print(name, "energy", R.energy_diag(prob["m_diag"], final))
+
+
+def golden_diffqc_cc(name):
+    """RESTATEMENT of diffqc.set_H/trotter (diffqc.cc:43-135,173-205); Eigen is absent so the
+    C++ cannot be built here.  Two-level + coupled-qubit style inputs, both basis types."""
+    rng = np.random.RandomState(7)
+    X, Y, Z, I = _P["X"], _P["Y"], _P["Z"], _P["I"]
+    H0 = 0.3 * np.kron(Z, Z) + 0.2 * np.kron(Z, I)
+    Hs = [np.kron(X, I), np.kron(I, X), np.kron(Y, I) + 0.1 * np.kron(I, Y)]
+    # channels[h][c] = [unused, omega, w, idx]   (diffqc.cc:108-111)
+    channels = [[[0.0, 1.5, 0.7, 0.0]],
+                [[0.0, 2.0, 0.0, 1.0], [0.0, 0.5, 1.3, 2.0]],
+                [[0.0, 1.0, 2.1, 2.0]]]
+    n_param, n_basis = 3, 5
+    vv = rng.normal(0, 1, [2, n_param, n_basis])
+    vv[:, 1, :] *= 1e-8          # exercises the |N| < 1e-6 branch (diffqc.cc:128-129)
+    psi0 = rng.normal(size=4) + 1j * rng.normal(size=4)
+    psi0 /= np.linalg.norm(psi0)
+    out = {}
+    for func_type in (0, 1):
+        for (T0, T) in ((0.0, 1.7), (1.2, 0.4)):     # second span is negative: abs() matters
+            key = "f%d_%s" % (func_type, "fwd" if T > T0 else "bwd")
+            out[key] = R.trotter_cc(H0, Hs, channels, 2.0, func_type, psi0, T0, T, 12, vv)
+            n_steps, dt, ts = R.step_grid(T0, T, 12, use_abs=True)
+            out[key + "_u"] = np.array([[R.f_u_cc(h, t, vv, channels, 2.0, func_type)
+                                         for h in range(3)] for t in ts])
+    chan_flat = np.array([c for h in channels for c in h])
+    np.savez(os.path.join(OUT, name + ".npz"), H0=H0, Hs=np.array(Hs), chan_flat=chan_flat,
+             chan_counts=np.array([len(h) for h in channels]), duration=2.0, vv=vv, psi0=psi0,
+             per_step=12, spans=np.array([[0.0, 1.7], [1.2, 0.4]]),
+             source="RESTATEMENT oracle/restate.py trotter_cc (diffqc.cc:43-135,173-205)", **out)
+    print(name, "done")
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    sp = ref_loader.load_sim_plain()
+    qp = ref_loader.load_qutip_standin()
+    demo = R.maxcut_structured(4, DEMO_GRAPH)
+    H0, Hs, M = R.maxcut_dense(demo)
+    golden_dense_reference(sp, qp, "demo_bspline_ref", H0, Hs, M, demo["psi0"], demo["omegas"],
+                           demo["T"], "BSpline", 6, seed=1234)
+    golden_dense_reference(sp, qp, "demo_legendre_ref", H0, Hs, M, demo["psi0"], demo["omegas"],
+                           demo["T"], "Legendre", 5, seed=4321, n_samples=3)
+    h2 = h2_problem()
+    golden_dense_reference(sp, qp, "h2_vqe_ref", h2["H0"], list(h2["Hs"]), h2["M"], h2["psi0"],
+                           h2["omegas"], h2["T"], "BSpline", 6, seed=99, n_samples=4)
+    golden_demo_training("demo_training_ref")
+    golden_split("split_n4_demo", 4, DEMO_GRAPH, seed=11, per_step=10)
+    golden_split("split_n6", 6, R.random_regular_edges(6, seed=1), seed=12, per_step=10)
+    golden_split("split_n8", 8, R.random_regular_edges(8, seed=2), seed=13, per_step=7)
+    golden_split("split_n12", 12, R.random_regular_edges(12, seed=3), seed=14, per_step=3,
+                 n_samples=1)
+    golden_diffqc_cc("diffqc_cc_restated")
+
+
+if __name__ == "__main__":
+    main()
