@@ -1,0 +1,59 @@
+// Structured (Pauli-term) problem handle shared by the generic and fused engines.
+#pragma once
+#include "common.cuh"
+
+struct dq_ising {
+    dq_context* ctx = nullptr;
+    int n = 0;                     // qubits
+    int n_zz = 0;                  // ZZ pairs
+    int row_len = 0;               // 1 + n_zz + n doubles per angle row
+    std::vector<int> qa, qb;       // pair endpoints (qubit ids)
+    int bitpos[40];                // physical bit position of qubit q in the device layout
+    std::vector<int> pa, pb;       // pair endpoints as physical bit positions
+    bool identity_layout = true;   // bitpos[q] == n-1-q for all q
+    dq::DevBuf mdiag;              // double[2^n], physical order
+    dq::DevBuf pairs_dev;          // int2[n_zz] physical bit positions
+
+    int engine = 1;                // 0 generic, 1 fused (n >= 12)
+    int ket_group = 4;             // states per fused launch (L2 residency)
+
+    // work buffers
+    dq::DevBuf states, phi, rows_a, rows_b, trig_a, trig_b, energies, scratch, io, shift_desc;
+
+    // staged gradient batch
+    struct Staged {
+        bool valid = false;
+        int n_samples = 0, n_shift = 0;
+        double r = 0.5;
+        std::vector<int> prefix_steps, suffix_steps, shift_kind, shift_index;
+        std::vector<int64_t> prefix_off, suffix_off;     // row offsets
+        bool uniform_psi0 = true;
+        dq::DevBuf psi0;                                  // physical order, when not uniform
+    } st;
+
+    double stat_steps = 0, stat_launches = 0, stat_alg_bytes = 0;
+
+    size_t dim() const { return (size_t)1 << n; }
+};
+
+namespace dq {
+// one shifted ket of the estimator: exp(sign * i * atan(r) * P), P = Z_b0 Z_b1 (kind 0) or X_b0 (kind 1)
+struct ShiftDesc { int kind; int b0; int b1; double sign; };
+// generic engine (any n >= 1): one kernel per term group, used for small n and as cross-check
+int gen_fill_uniform(dq_ising* p, c128* psi, int batch);
+int gen_permute_in(dq_ising* p, const c128* src_ref_order, c128* dst_phys, int batch);
+int gen_permute_out(dq_ising* p, const c128* src_phys, c128* dst_ref_order, int batch);
+int gen_trig(dq_ising* p, const double* d_rows, int64_t n_rows, double2* d_trig);
+int gen_evolve(dq_ising* p, c128* d_states, int batch, const double* d_rows, const double2* d_trig,
+               int n_steps);
+int gen_fanout(dq_ising* p, const c128* d_phi, c128* d_kets, int n_kets, const ShiftDesc* d_desc,
+               double r);
+int gen_energy(dq_ising* p, const c128* d_states, int batch, double* d_out);
+int gen_build_mdiag(dq_ising* p, const double* m_zz, double m_const);
+
+// fused persistent engine (n >= 12)
+int fused_supported(const dq_ising* p);
+int fused_grad_run(dq_ising* p);
+int fused_evolve(dq_ising* p, c128* d_states, int batch, const double* h_rows, int n_steps,
+                 double* d_energies, bool want_states);
+}  // namespace dq

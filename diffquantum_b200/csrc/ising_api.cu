@@ -1,0 +1,302 @@
+// C-ABI entry points of the structured (Pauli-term) path: problem handle, single/batched
+// evolution and the batched stochastic parameter-shift sample driver (sim_plain.py:186-220).
+#include <string.h>
+#include <math.h>
+#include "ising.cuh"
+
+using dq::c128;
+
+namespace {
+
+int check_rows(const dq_ising* p, const double* rows, int64_t n_rows, const char* what) {
+    DQ_REQUIRE(n_rows == 0 || rows != nullptr, "%s: NULL angle table", what);
+    for (int64_t i = 0; i < n_rows * p->row_len; ++i)
+        DQ_REQUIRE(isfinite(rows[i]), "%s: non-finite angle at flat index %lld", what, (long long)i);
+    return DQ_OK;
+}
+
+bool use_fused(const dq_ising* p) { return p->engine == 1 && dq::fused_supported(p); }
+
+}  // namespace
+
+extern "C" {
+
+int dq_ising_create(dq_context* ctx, int n_qubits, int n_zz, const int32_t* zz_pairs,
+                    const double* m_zz, double m_const, const double* m_diag, dq_ising** out) {
+    DQ_REQUIRE(ctx && out, "dq_ising_create: NULL argument");
+    *out = nullptr;
+    DQ_REQUIRE(n_qubits >= 1 && n_qubits <= 30, "dq_ising_create: n_qubits=%d outside [1,30]", n_qubits);
+    DQ_REQUIRE(n_zz >= 0 && (n_zz == 0 || zz_pairs), "dq_ising_create: bad ZZ pair list");
+    DQ_TRY(ctx->set_device());
+    dq_ising* p = new dq_ising();
+    p->ctx = ctx;
+    p->n = n_qubits;
+    p->n_zz = n_zz;
+    p->row_len = 1 + n_zz + n_qubits;
+    for (int e = 0; e < n_zz; ++e) {
+        int a = zz_pairs[2 * e], b = zz_pairs[2 * e + 1];
+        if (a < 0 || b < 0 || a >= n_qubits || b >= n_qubits || a == b) {
+            dq::set_error("dq_ising_create: pair %d = (%d,%d) invalid for %d qubits", e, a, b, n_qubits);
+            delete p;
+            return DQ_ERR_INVALID;
+        }
+        p->qa.push_back(a);
+        p->qb.push_back(b);
+    }
+    for (int q = 0; q < n_qubits; ++q) p->bitpos[q] = n_qubits - 1 - q;     // reference order
+    p->identity_layout = true;
+    p->pa.resize(n_zz);
+    p->pb.resize(n_zz);
+    std::vector<int2> pr(n_zz);
+    for (int e = 0; e < n_zz; ++e) {
+        p->pa[e] = p->bitpos[p->qa[e]];
+        p->pb[e] = p->bitpos[p->qb[e]];
+        pr[e] = make_int2(p->pa[e], p->pb[e]);
+    }
+    int s = p->pairs_dev.reserve((n_zz ? n_zz : 1) * sizeof(int2));
+    if (s == DQ_OK) s = p->mdiag.reserve(p->dim() * sizeof(double));
+    if (s != DQ_OK) { dq_ising_destroy(p); return s; }
+    if (n_zz) DQ_CUDA(cudaMemcpy(p->pairs_dev.p, pr.data(), n_zz * sizeof(int2), cudaMemcpyHostToDevice));
+    if (m_diag) {
+        // host table in reference order -> physical order (identity layout today)
+        DQ_CUDA(cudaMemcpy(p->mdiag.p, m_diag, p->dim() * sizeof(double), cudaMemcpyHostToDevice));
+    } else {
+        std::vector<double> zero(n_zz ? n_zz : 1, 0.0);
+        s = dq::gen_build_mdiag(p, m_zz ? m_zz : zero.data(), m_const);
+        if (s != DQ_OK) { dq_ising_destroy(p); return s; }
+    }
+    *out = p;
+    return DQ_OK;
+}
+
+int dq_ising_destroy(dq_ising* p) {
+    if (!p) return DQ_OK;
+    cudaSetDevice(p->ctx->device);
+    cudaStreamSynchronize(p->ctx->stream);
+    dq::DevBuf* bufs[] = {&p->mdiag, &p->pairs_dev, &p->states, &p->phi, &p->rows_a, &p->rows_b, &p->trig_a,
+                          &p->trig_b, &p->energies, &p->scratch, &p->io, &p->shift_desc, &p->st.psi0};
+    for (auto* b : bufs) b->release();
+    delete p;
+    return DQ_OK;
+}
+
+int dq_ising_set_option(dq_ising* p, const char* name, int64_t value) {
+    DQ_REQUIRE(p && name, "NULL argument");
+    if (!strcmp(name, "engine")) {
+        DQ_REQUIRE(value == 0 || value == 1, "engine must be 0 (generic) or 1 (fused)");
+        p->engine = (int)value;
+    } else if (!strcmp(name, "ket_group")) {
+        DQ_REQUIRE(value >= 1 && value <= 1024, "ket_group out of range");
+        p->ket_group = (int)value;
+    } else {
+        dq::set_error("dq_ising_set_option: unknown option '%s'", name);
+        return DQ_ERR_INVALID;
+    }
+    return DQ_OK;
+}
+
+int dq_ising_get_info(dq_ising* p, const char* name, int64_t* value) {
+    DQ_REQUIRE(p && name && value, "NULL argument");
+    if (!strcmp(name, "engine")) *value = use_fused(p) ? 1 : 0;
+    else if (!strcmp(name, "ket_group")) *value = p->ket_group;
+    else if (!strcmp(name, "row_len")) *value = p->row_len;
+    else if (!strcmp(name, "n_qubits")) *value = p->n;
+    else { dq::set_error("dq_ising_get_info: unknown name '%s'", name); return DQ_ERR_INVALID; }
+    return DQ_OK;
+}
+
+int dq_ising_last_stat(dq_ising* p, const char* name, double* value) {
+    DQ_REQUIRE(p && name && value, "NULL argument");
+    if (!strcmp(name, "steps")) *value = p->stat_steps;
+    else if (!strcmp(name, "launches")) *value = p->stat_launches;
+    else if (!strcmp(name, "alg_bytes")) *value = p->stat_alg_bytes;
+    else { dq::set_error("dq_ising_last_stat: unknown name '%s'", name); return DQ_ERR_INVALID; }
+    return DQ_OK;
+}
+
+int dq_ising_evolve(dq_ising* p, int batch, int n_steps, const double* angles, const void* psi_in,
+                    void* psi_out, int psi_is_device, double* energies_out) {
+    DQ_REQUIRE(p, "NULL problem");
+    DQ_REQUIRE(batch >= 1 && n_steps >= 0, "dq_ising_evolve: batch=%d n_steps=%d", batch, n_steps);
+    DQ_REQUIRE(psi_out || energies_out, "dq_ising_evolve: nothing requested");
+    DQ_TRY(check_rows(p, angles, n_steps, "dq_ising_evolve"));
+    DQ_TRY(p->ctx->set_device());
+    cudaStream_t st = p->ctx->stream;
+    const size_t N = p->dim(), bytes = N * batch * sizeof(c128);
+    const uint64_t l0 = p->ctx->launches;
+    DQ_TRY(p->states.reserve(bytes));
+    c128* d = p->states.as<c128>();
+    if (!psi_in) {
+        DQ_TRY(dq::gen_fill_uniform(p, d, batch));
+    } else if (p->identity_layout) {
+        DQ_CUDA(cudaMemcpyAsync(d, psi_in, bytes, psi_is_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
+    } else {
+        DQ_TRY(p->io.reserve(bytes));
+        DQ_CUDA(cudaMemcpyAsync(p->io.p, psi_in, bytes, psi_is_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
+        DQ_TRY(dq::gen_permute_in(p, p->io.as<c128>(), d, batch));
+    }
+    DQ_TRY(p->energies.reserve(batch * sizeof(double)));
+    if (use_fused(p)) {
+        DQ_TRY(dq::fused_evolve(p, d, batch, angles, n_steps, energies_out ? p->energies.as<double>() : nullptr,
+                                psi_out != nullptr));
+    } else {
+        if (n_steps) {
+            DQ_TRY(p->rows_a.reserve((size_t)n_steps * p->row_len * sizeof(double)));
+            DQ_TRY(p->trig_a.reserve((size_t)n_steps * p->n * sizeof(double2)));
+            DQ_CUDA(cudaMemcpyAsync(p->rows_a.p, angles, (size_t)n_steps * p->row_len * sizeof(double),
+                                    cudaMemcpyHostToDevice, st));
+            DQ_TRY(dq::gen_trig(p, p->rows_a.as<double>(), n_steps, p->trig_a.as<double2>()));
+            DQ_TRY(dq::gen_evolve(p, d, batch, p->rows_a.as<double>(), p->trig_a.as<double2>(), n_steps));
+        }
+        if (energies_out) DQ_TRY(dq::gen_energy(p, d, batch, p->energies.as<double>()));
+    }
+    if (energies_out)
+        DQ_CUDA(cudaMemcpyAsync(energies_out, p->energies.p, batch * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (psi_out) {
+        const c128* src = d;
+        if (!p->identity_layout) {
+            DQ_TRY(p->io.reserve(bytes));
+            DQ_TRY(dq::gen_permute_out(p, d, p->io.as<c128>(), batch));
+            src = p->io.as<c128>();
+        }
+        DQ_CUDA(cudaMemcpyAsync(psi_out, src, bytes, psi_is_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, st));
+    }
+    DQ_CUDA(cudaStreamSynchronize(st));
+    p->stat_steps = (double)n_steps * batch;
+    p->stat_alg_bytes = p->stat_steps * 2.0 * sizeof(c128) * N;
+    p->stat_launches = (double)(p->ctx->launches - l0);
+    return DQ_OK;
+}
+
+int dq_ising_grad_stage(dq_ising* p, int n_samples, const int32_t* prefix_steps, const double* prefix_angles,
+                        const int32_t* suffix_steps, const double* suffix_angles, int n_shift,
+                        const int32_t* shift_kind, const int32_t* shift_index, double r, const double* psi0) {
+    DQ_REQUIRE(p, "NULL problem");
+    DQ_REQUIRE(n_samples >= 1 && n_shift >= 1, "dq_ising_grad: n_samples=%d n_shift=%d", n_samples, n_shift);
+    DQ_REQUIRE(prefix_steps && suffix_steps && shift_kind && shift_index, "dq_ising_grad: NULL table");
+    DQ_REQUIRE(r > 0 && isfinite(r), "dq_ising_grad: r must be positive");
+    DQ_TRY(p->ctx->set_device());
+    auto& s = p->st;
+    s.valid = false;
+    s.n_samples = n_samples;
+    s.n_shift = n_shift;
+    s.r = r;
+    s.prefix_steps.assign(prefix_steps, prefix_steps + n_samples);
+    s.suffix_steps.assign(suffix_steps, suffix_steps + n_samples);
+    s.shift_kind.assign(shift_kind, shift_kind + n_shift);
+    s.shift_index.assign(shift_index, shift_index + n_shift);
+    s.prefix_off.resize(n_samples + 1);
+    s.suffix_off.resize(n_samples + 1);
+    s.prefix_off[0] = s.suffix_off[0] = 0;
+    for (int b = 0; b < n_samples; ++b) {
+        DQ_REQUIRE(prefix_steps[b] >= 0 && suffix_steps[b] >= 0, "dq_ising_grad: negative step count (sample %d)", b);
+        s.prefix_off[b + 1] = s.prefix_off[b] + prefix_steps[b];
+        s.suffix_off[b + 1] = s.suffix_off[b] + suffix_steps[b];
+    }
+    for (int i = 0; i < n_shift; ++i) {
+        if (shift_kind[i] == 0)
+            DQ_REQUIRE(shift_index[i] >= 0 && shift_index[i] < p->n_zz, "dq_ising_grad: shift %d: ZZ pair %d of %d", i, shift_index[i], p->n_zz);
+        else if (shift_kind[i] == 1)
+            DQ_REQUIRE(shift_index[i] >= 0 && shift_index[i] < p->n, "dq_ising_grad: shift %d: qubit %d of %d", i, shift_index[i], p->n);
+        else
+            DQ_REQUIRE(false, "dq_ising_grad: shift %d: unknown kind %d", i, shift_kind[i]);
+    }
+    const int64_t np = s.prefix_off[n_samples], ns = s.suffix_off[n_samples];
+    DQ_TRY(check_rows(p, prefix_angles, np, "dq_ising_grad(prefix)"));
+    DQ_TRY(check_rows(p, suffix_angles, ns, "dq_ising_grad(suffix)"));
+    cudaStream_t st = p->ctx->stream;
+    const size_t rb = p->row_len * sizeof(double);
+    DQ_TRY(p->rows_a.reserve((np ? np : 1) * rb));
+    DQ_TRY(p->rows_b.reserve((ns ? ns : 1) * rb));
+    if (np) DQ_CUDA(cudaMemcpyAsync(p->rows_a.p, prefix_angles, np * rb, cudaMemcpyHostToDevice, st));
+    if (ns) DQ_CUDA(cudaMemcpyAsync(p->rows_b.p, suffix_angles, ns * rb, cudaMemcpyHostToDevice, st));
+    // shifted-ket descriptors, order [i][+,-]
+    std::vector<dq::ShiftDesc> h(2 * n_shift);
+    for (int i = 0; i < n_shift; ++i)
+        for (int sg = 0; sg < 2; ++sg) {
+            dq::ShiftDesc d;
+            d.kind = shift_kind[i];
+            if (d.kind == 0) { d.b0 = p->pa[shift_index[i]]; d.b1 = p->pb[shift_index[i]]; }
+            else { d.b0 = p->bitpos[shift_index[i]]; d.b1 = 0; }
+            d.sign = sg == 0 ? +1.0 : -1.0;
+            h[2 * i + sg] = d;
+        }
+    DQ_TRY(p->shift_desc.reserve(h.size() * sizeof(dq::ShiftDesc)));
+    DQ_CUDA(cudaMemcpyAsync(p->shift_desc.p, h.data(), h.size() * sizeof(dq::ShiftDesc), cudaMemcpyHostToDevice, st));
+    s.uniform_psi0 = psi0 == nullptr;
+    if (psi0) {
+        DQ_TRY(s.psi0.reserve(p->dim() * sizeof(c128)));
+        if (p->identity_layout) {
+            DQ_CUDA(cudaMemcpyAsync(s.psi0.p, psi0, p->dim() * sizeof(c128), cudaMemcpyHostToDevice, st));
+        } else {
+            DQ_TRY(p->io.reserve(p->dim() * sizeof(c128)));
+            DQ_CUDA(cudaMemcpyAsync(p->io.p, psi0, p->dim() * sizeof(c128), cudaMemcpyHostToDevice, st));
+            DQ_TRY(dq::gen_permute_in(p, p->io.as<c128>(), s.psi0.as<c128>(), 1));
+        }
+    }
+    DQ_TRY(p->energies.reserve((size_t)n_samples * 2 * n_shift * sizeof(double)));
+    if (!use_fused(p)) {
+        DQ_TRY(p->trig_a.reserve((np ? np : 1) * p->n * sizeof(double2)));
+        DQ_TRY(p->trig_b.reserve((ns ? ns : 1) * p->n * sizeof(double2)));
+        DQ_TRY(dq::gen_trig(p, p->rows_a.as<double>(), np, p->trig_a.as<double2>()));
+        DQ_TRY(dq::gen_trig(p, p->rows_b.as<double>(), ns, p->trig_b.as<double2>()));
+    }
+    DQ_CUDA(cudaStreamSynchronize(st));          // host vectors above go out of scope
+    // keep host copies of the rows for the fused engine's table builder
+    s.valid = true;
+    return DQ_OK;
+}
+
+int dq_ising_grad_run_staged(dq_ising* p) {
+    DQ_REQUIRE(p && p->st.valid, "dq_ising_grad_run_staged: nothing staged");
+    DQ_TRY(p->ctx->set_device());
+    auto& s = p->st;
+    const uint64_t l0 = p->ctx->launches;
+    const size_t N = p->dim();
+    const int kets = 2 * s.n_shift;
+    double steps = 0;
+    if (use_fused(p)) {
+        DQ_TRY(dq::fused_grad_run(p));
+    } else {
+        cudaStream_t st = p->ctx->stream;
+        DQ_TRY(p->phi.reserve(N * sizeof(c128)));
+        DQ_TRY(p->states.reserve(N * kets * sizeof(c128)));
+        for (int b = 0; b < s.n_samples; ++b) {
+            c128* phi = p->phi.as<c128>();
+            if (s.uniform_psi0) DQ_TRY(dq::gen_fill_uniform(p, phi, 1));
+            else DQ_CUDA(cudaMemcpyAsync(phi, s.psi0.p, N * sizeof(c128), cudaMemcpyDeviceToDevice, st));
+            DQ_TRY(dq::gen_evolve(p, phi, 1, p->rows_a.as<double>() + s.prefix_off[b] * p->row_len,
+                                  p->trig_a.as<double2>() + s.prefix_off[b] * p->n, s.prefix_steps[b]));
+            DQ_TRY(dq::gen_fanout(p, phi, p->states.as<c128>(), kets, p->shift_desc.as<dq::ShiftDesc>(), s.r));
+            DQ_TRY(dq::gen_evolve(p, p->states.as<c128>(), kets, p->rows_b.as<double>() + s.suffix_off[b] * p->row_len,
+                                  p->trig_b.as<double2>() + s.suffix_off[b] * p->n, s.suffix_steps[b]));
+            DQ_TRY(dq::gen_energy(p, p->states.as<c128>(), kets, p->energies.as<double>() + (size_t)b * kets));
+        }
+    }
+    for (int b = 0; b < s.n_samples; ++b) steps += s.prefix_steps[b] + (double)kets * s.suffix_steps[b];
+    p->stat_steps = steps;
+    p->stat_alg_bytes = steps * 2.0 * sizeof(c128) * N;
+    p->stat_launches = (double)(p->ctx->launches - l0);
+    return DQ_OK;
+}
+
+int dq_ising_grad_fetch(dq_ising* p, double* energies_out) {
+    DQ_REQUIRE(p && p->st.valid && energies_out, "dq_ising_grad_fetch: nothing staged or NULL output");
+    DQ_TRY(p->ctx->set_device());
+    DQ_CUDA(cudaMemcpyAsync(energies_out, p->energies.p, (size_t)p->st.n_samples * 2 * p->st.n_shift * sizeof(double),
+                            cudaMemcpyDeviceToHost, p->ctx->stream));
+    DQ_CUDA(cudaStreamSynchronize(p->ctx->stream));
+    return DQ_OK;
+}
+
+int dq_ising_grad(dq_ising* p, int n_samples, const int32_t* prefix_steps, const double* prefix_angles,
+                  const int32_t* suffix_steps, const double* suffix_angles, int n_shift, const int32_t* shift_kind,
+                  const int32_t* shift_index, double r, const double* psi0, double* energies_out) {
+    DQ_REQUIRE(energies_out, "dq_ising_grad: NULL output");
+    DQ_TRY(dq_ising_grad_stage(p, n_samples, prefix_steps, prefix_angles, suffix_steps, suffix_angles, n_shift,
+                               shift_kind, shift_index, r, psi0));
+    DQ_TRY(dq_ising_grad_run_staged(p));
+    return dq_ising_grad_fetch(p, energies_out);
+}
+
+}  // extern "C"

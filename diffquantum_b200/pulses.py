@@ -1,0 +1,118 @@
+"""Host-side pulse tables and time grids, vectorised over steps and samples.
+
+Mirrors, in the reference's own operation order, the scalar Python code of
+  SimulatorPlain.get_func_bspline  sim_plain.py:52-70   (open-support quadratic bumps)
+  SimulatorPlain.generate_u        sim_plain.py:73-99   (sequential sum over j, sigmoid, omega)
+  the dDdv autograd block          sim_plain.py:169-184 (closed form of the same derivative)
+  the step grid of trotter         sim_plain.py:123,133-134,150 / diffqc.cc:182-184,199
+  diffqc f_u / my_expit / bspline  diffqc.cc:75-135
+The device only ever sees angles; all pulse arithmetic stays here in float64.
+"""
+import math
+
+import numpy as np
+from scipy.special import eval_legendre
+
+
+def step_grid(T0, T, per_step, use_abs=False):
+    """n_steps, dt and the accumulated left-end times (t += dt, not T0 + k*dt)."""
+    span = abs(T - T0) if use_abs else (T - T0)
+    n_steps = int(per_step * (span + 1))
+    if n_steps <= 0:
+        return 0, 0.0, np.zeros(0)
+    dt = (T - T0) / n_steps
+    # np.add.accumulate is a sequential left fold, i.e. exactly the reference's repeated `t += dt`
+    ts = np.add.accumulate(np.concatenate(([float(T0)], np.full(n_steps - 1, dt))))
+    return n_steps, dt, ts
+
+
+def bspline_table(n_basis, x):
+    """phi[b](x) for all b: array [len(x), n_basis] (sim_plain.py:52-70 == diffqc.cc:82-93)."""
+    x = np.asarray(x, dtype=np.float64).reshape(-1)
+    tau = 1. / (n_basis - 2)
+    out = np.zeros((x.size, n_basis))
+    norm_factor = -(1.5 * tau) ** 2
+    for b in range(n_basis):
+        tau_b = tau * (b - 1.5)
+        l = tau_b - 1.5 * tau
+        r = tau_b + 1.5 * tau
+        inside = ~((x >= r) | (x <= l))
+        out[inside, b] = (x[inside] - l) * (x[inside] - r) / norm_factor
+    return out
+
+
+def legendre_table(n_basis, y):
+    y = np.asarray(y, dtype=np.float64).reshape(-1)
+    return np.stack([eval_legendre(j, y) for j in range(n_basis)], axis=1)
+
+
+def basis_table(basis, n_basis, ts, T):
+    ts = np.asarray(ts, dtype=np.float64)
+    if basis == 'BSpline':
+        return bspline_table(n_basis, ts / T)
+    if basis == 'Legendre':
+        return legendre_table(n_basis, 2 * ts / T - 1)
+    raise ValueError("unsupported basis %r (reference hot path ships BSpline and Legendre)" % (basis,))
+
+
+def _sigmoid(a):
+    return 1 / (1 + np.exp(-a))
+
+
+def u_table(coeff, omegas, T, ts, basis='BSpline'):
+    """u[k, i] = omega_i (2 sigma(sum_j c_ij phi_j(t_k)) - 1)   (sim_plain.py:81-98)."""
+    coeff = np.asarray(coeff, dtype=np.float64)
+    phi = basis_table(basis, coeff.shape[1], ts, T)             # [K, n_basis]
+    a = np.zeros((phi.shape[0], coeff.shape[0]))
+    for j in range(coeff.shape[1]):                             # same summation order as the loop at :85
+        a = a + phi[:, j:j + 1] * coeff[None, :, j]
+    return (_sigmoid(a) * 2 - 1) * np.asarray(omegas, dtype=np.float64)[None, :]
+
+
+def dudc_table(coeff, omegas, T, s, basis='BSpline'):
+    """dDdv[i, j] = d u_i(s) / d c_ij = omega_i 2 sigma'(A_i) phi_j(s)  (sim_plain.py:169-184)."""
+    coeff = np.asarray(coeff, dtype=np.float64)
+    phi = basis_table(basis, coeff.shape[1], [s], T)[0]
+    a = np.zeros(coeff.shape[0])
+    for j in range(coeff.shape[1]):
+        a = a + coeff[:, j] * phi[j]
+    sg = _sigmoid(a)
+    return (np.asarray(omegas, dtype=np.float64) * 2.0 * sg * (1.0 - sg))[:, None] * phi[None, :]
+
+
+# ---- native twin (diffqc.cc) -------------------------------------------------------------------
+
+def _expit_cc(x):
+    out = 1 / (1 + np.exp(-np.clip(x, -700, 700)))
+    out = np.where(x > 32., 1., out)           # diffqc.cc:75-80
+    return np.where(x < -32., 0., out)
+
+
+def f_u_table(channels, duration, func_type, vv, ts):
+    """u[k, h] of the native twin (diffqc.cc:95-135).  channels: list (per term) of lists of
+    [_, omega, w, idx]; vv: [2][n_param][n_basis]."""
+    vv = np.asarray(vv, dtype=np.float64)
+    ts = np.asarray(ts, dtype=np.float64)
+    n_basis = vv.shape[2]
+    if func_type == 0:
+        fv = legendre_table(n_basis, 2 * ts / duration - 1)
+    else:
+        fv = bspline_table(n_basis, ts / duration)
+    out = np.zeros((ts.size, len(channels)))
+    for h, chans in enumerate(channels):
+        for chan in chans:
+            omega, w = float(chan[1]), float(chan[2])
+            idx = int(math.floor(abs(chan[3]) + 0.5)) * (1 if chan[3] >= 0 else -1)   # C round()
+            if not 0 <= idx < vv.shape[1]:
+                raise ValueError("channel parameter index %d outside vv (n_param=%d)" % (idx, vv.shape[1]))
+            A = np.zeros(ts.size)
+            B = np.zeros(ts.size)
+            for j in range(n_basis):
+                A = A + vv[0, idx, j] * fv[:, j]
+                B = B + vv[1, idx, j] * fv[:, j]
+            N = np.sqrt(A * A + B * B)
+            small = np.abs(N - 0.0) < 0.000001
+            Ns = np.where(small, 1.0, N)
+            term = omega * (2 * _expit_cc(Ns) - 1) / Ns * (np.cos(w * ts) * A + np.sin(w * ts) * B)
+            out[:, h] += np.where(small, 0.0, term)
+    return out

@@ -1,0 +1,143 @@
+/*
+ * diffqc_b200.h — C ABI of the B200-native replacement for diffquantum's evolution hot path.
+ *
+ * Everything the Python host layer (diffquantum_b200/) binds with ctypes is declared here and
+ * nowhere else.  Plain pointers, sizes and scalars only; no C++ or torch types cross this line.
+ * Complex numbers are interleaved (re, im) IEEE float64 pairs ("c128").  Matrices are row-major.
+ * Every function returns 0 on success and a negative dq_status on failure; the message for the
+ * calling thread's last failure is dq_last_error().  No C++ exception crosses the ABI.
+ *
+ * Which reference interface each entry point replaces (paths relative to the reference tree):
+ *
+ *   dq_dense_set_H      diffqc.set_H            diffqc.cc:43-73    (+ pybind11 list casters, stl.h:129-142)
+ *   dq_dense_trotter    diffqc.trotter + f_u    diffqc.cc:95-135, 173-205
+ *   dq_dense_evolve     SimulatorPlain.trotter  sim_plain.py:119-153   (solver hook, sim_plain.py:43)
+ *   dq_dense_grad       compute_energy_grad_MC  sim_plain.py:186-220   (prefix + 2*n_H shifted suffixes)
+ *   dq_ising_*          the same two paths for Pauli-term (MaxCut/QAOA) Hamiltonians that the dense
+ *                       nested-list API cannot express beyond n~13 (demo_maxcut.py:19-85 builds
+ *                       them with np.kron) — step semantics of diffqc.cc:155-164.
+ *
+ * Qubit/bit convention is the reference's: qubit j of n is bit (n-1-j) of the basis index
+ * (demo_maxcut.py:49-57, sim_plain.py:477-482).
+ */
+#ifndef DIFFQC_B200_H
+#define DIFFQC_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum dq_status {
+    DQ_OK = 0,
+    DQ_ERR_INVALID = -1,   /* bad argument (sizes, indices, NULL) — the reference has UB here */
+    DQ_ERR_CUDA = -2,      /* CUDA runtime failure, message carries cudaGetErrorString */
+    DQ_ERR_STATE = -3,     /* call order (e.g. trotter before set_H, diffqc.cc:21-25 globals) */
+    DQ_ERR_UNSUPPORTED = -4,
+    DQ_ERR_NOMEM = -5
+} dq_status;
+
+typedef struct dq_context dq_context;   /* one per process x device; owns stream + workspaces */
+typedef struct dq_ising dq_ising;       /* a structured (Pauli-term) problem bound to a context */
+
+/* ---- library / context ------------------------------------------------------------------ */
+const char* dq_version(void);                       /* "dev", as diffqc.__version__ (diffqc.cc:227) */
+const char* dq_last_error(void);                    /* thread-local, never NULL */
+int dq_device_count(int* count);
+int dq_context_create(int device, dq_context** out);
+int dq_context_destroy(dq_context* ctx);
+int dq_context_synchronize(dq_context* ctx);
+/* cudaStream_t of the context as an integer, so the host can record torch/CUDA events on it. */
+int dq_context_stream(dq_context* ctx, uint64_t* stream_out);
+/* kernels launched by this context since creation (bench.py's gpu_launches claim). */
+int dq_context_launch_count(dq_context* ctx, uint64_t* count_out);
+
+/* ---- dense path (n <= 10 qubits, D = dim <= 1024): live `exact` step semantics --------------
+ * psi <- expm(-i dt (H0 + sum_h u_h(t_k) H_h)) psi per step  (sim_plain.py:135-150, diffqc.cc:190-200),
+ * evaluated on the device with FP64 tensor-core (DMMA) complex matmuls. */
+
+/* diffqc.set_H: H0 [dim*dim] c128, Hs [n_H*dim*dim] c128; channels flattened:
+ * chan_counts[h] channels for term h, each 4 doubles {unused, omega, w, idx} (diffqc.cc:108-111).
+ * func_type 0 = Legendre, otherwise the B-spline bump basis (diffqc.cc:25,115-125). */
+int dq_dense_set_H(dq_context* ctx, int dim, const double* H0, int n_H, const double* Hs,
+                   const int32_t* chan_counts, const double* channels, double duration,
+                   int func_type);
+
+/* diffqc.trotter: vv [2][n_param][n_basis] (A then B coefficients); psi0/psi_out [dim] c128 on the
+ * HOST.  n_steps = (int)(per_step*(|T-T0|+1)), dt = (T-T0)/n_steps, t accumulated (diffqc.cc:182-199).
+ * u_out, if not NULL, receives the [n_steps][n_H] envelope values f_u (for parity tests). */
+int dq_dense_trotter(dq_context* ctx, const double* psi0, double T0, double T, int per_step,
+                     const double* vv, int n_param, int n_basis, double* psi_out, double* u_out);
+
+/* Solver-hook form: the host has already evaluated u[k][h] (Python closures, sim_plain.py:81-98).
+ * mode 0 = exact (live reference code), 1 = split (per-term product, diffqc.cc:155-164).
+ * psi_in / psi_out: [batch][dim] c128 host buffers; all batch members share H and u. */
+int dq_dense_evolve(dq_context* ctx, int dim, const double* H0, int n_H, const double* Hs,
+                    const double* u, int n_steps, double dt, int mode, int batch,
+                    const double* psi_in, double* psi_out);
+
+/* Batched stochastic parameter-shift samples on a dense problem (sim_plain.py:186-220).
+ * For each sample b: phi = U(prefix_b) psi0; for each term i and sign +/-:
+ * ket = U(suffix_b) (I +/- i r H_i) phi / sqrt(1+r^2); energies[b][i][0|1] = Re <ket|M|ket> (+, -).
+ * u_prefix / u_suffix are packed [sum_b steps_b][n_H] tables with per-sample dt. */
+int dq_dense_grad(dq_context* ctx, int dim, const double* H0, int n_H, const double* Hs,
+                  const double* M, const double* psi0, double r, int n_samples,
+                  const int32_t* prefix_steps, const double* prefix_dt, const double* u_prefix,
+                  const int32_t* suffix_steps, const double* suffix_dt, const double* u_suffix,
+                  int mode, double* energies_out);
+
+/* ---- structured path: H(t) = c0 + sum_e (w_e + u_e(t)) Z_a Z_b + sum_q u_q(t) X_q ------------
+ * One product-formula step = one diagonal phase exp(-i(angle_c + sum_e angle_e z_a z_b)) followed by
+ * exp(-i angle_q X_q) on every qubit (term order of diffqc.cc:155-164: H0, ZZ controls, X controls).
+ * The HOST evaluates pulses and supplies per-step ANGLES (already multiplied by dt):
+ *   row layout  [ angle_c | angle_e for e < n_zz | angle_q for q < n_qubits ]   (1 + n_zz + n doubles)
+ */
+int dq_ising_create(dq_context* ctx, int n_qubits, int n_zz, const int32_t* zz_pairs /*[n_zz][2]*/,
+                    const double* m_zz /*[n_zz] or NULL*/, double m_const,
+                    const double* m_diag /*[2^n] host, overrides m_zz when not NULL*/,
+                    dq_ising** out);
+int dq_ising_destroy(dq_ising* p);
+/* Tunables: "ket_group" (states co-resident in L2 per launch), "engine" (0 generic, 1 fused). */
+int dq_ising_set_option(dq_ising* p, const char* name, int64_t value);
+int dq_ising_get_info(dq_ising* p, const char* name, int64_t* value);
+
+/* Evolve `batch` states through `n_steps` rows of `angles`.  psi is [batch][2^n] c128 in the
+ * REFERENCE index order; psi_is_device selects host or device pointers (device pointers come from
+ * torch.Tensor.data_ptr()).  energies_out (host, [batch]) may be NULL; psi_out may be NULL when only
+ * energies are wanted.  psi_in == NULL means the uniform superposition (demo_maxcut.py:12-17). */
+int dq_ising_evolve(dq_ising* p, int batch, int n_steps, const double* angles,
+                    const void* psi_in, void* psi_out, int psi_is_device, double* energies_out);
+
+/* Batched gradient samples.  For each sample b: prefix rows evolve psi0 to phi_b; then for every
+ * shift term i (kind 0: ZZ pair index, kind 1: X on qubit index) and sign s in (+,-):
+ *   ket = U(suffix rows of b) exp(+/- i atan(r) P_i) phi_b   [== (I +/- i r P_i) phi / sqrt(1+r^2)]
+ *   energies_out[b][i][0|1] = <ket|M|ket>.
+ * prefix_angles / suffix_angles are packed row tables, sample b occupying prefix_steps[b] /
+ * suffix_steps[b] consecutive rows.  psi0 == NULL means the uniform superposition (host c128 otherwise).
+ * All pointers are HOST pointers; copies are part of the call. */
+int dq_ising_grad(dq_ising* p, int n_samples, const int32_t* prefix_steps,
+                  const double* prefix_angles, const int32_t* suffix_steps,
+                  const double* suffix_angles, int n_shift, const int32_t* shift_kind,
+                  const int32_t* shift_index, double r, const double* psi0, double* energies_out);
+
+/* Same work with inputs already staged on the device by dq_ising_grad_stage (bench.py times this
+ * as the HBM-resident `value`; dq_ising_grad is the host-buffer `e2e` path). */
+int dq_ising_grad_stage(dq_ising* p, int n_samples, const int32_t* prefix_steps,
+                        const double* prefix_angles, const int32_t* suffix_steps,
+                        const double* suffix_angles, int n_shift, const int32_t* shift_kind,
+                        const int32_t* shift_index, double r, const double* psi0);
+int dq_ising_grad_run_staged(dq_ising* p);                      /* asynchronous on the ctx stream */
+int dq_ising_grad_fetch(dq_ising* p, double* energies_out);     /* synchronises, copies D2H */
+
+/* Counters of the last run: "steps" (trajectory-steps executed), "launches", "alg_bytes". */
+int dq_ising_last_stat(dq_ising* p, const char* name, double* value);
+
+/* ---- micro-benchmarks used by bench.py/profiles to calibrate the roofline --------------------- */
+/* kind: 0 = device copy GB/s over `bytes`, 1 = FP64 FMA TFLOP/s, 2 = L2-resident read+write GB/s. */
+int dq_microbench(dq_context* ctx, int kind, int64_t bytes, int iters, double* result);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DIFFQC_B200_H */

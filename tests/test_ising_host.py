@@ -1,0 +1,69 @@
+"""Host-side logic of the structured path (no GPU): pulse tables, step grids, angle rows."""
+import numpy as np
+
+from diffquantum_b200 import pulses as P
+from diffquantum_b200.ising import IsingProblem
+from oracle import restate as R
+
+
+def test_step_grid_matches_reference_grid(golden):
+    g = golden("demo_bspline_ref")
+    n, dt, ts = P.step_grid(0, float(g["T"]), int(g["per_step"]))
+    assert n == len(g["ts"]) and dt == float(g["dt"])
+    np.testing.assert_array_equal(ts, g["ts"])
+    for T0, T in ((0.37, 2.0), (0.0, 0.0049), (1.999, 2.0)):
+        a, b = P.step_grid(T0, T, 10), R.step_grid(T0, T, 10)
+        assert a[0] == b[0] and a[1] == b[1]
+        np.testing.assert_array_equal(a[2], b[2])
+    assert P.step_grid(1.2, 0.4, 12, use_abs=True)[0] == 21 and P.step_grid(1.2, 0.4, 12)[0] == 2
+
+
+def test_u_table_matches_reference_closures(golden):
+    for name in ("demo_bspline_ref", "demo_legendre_ref", "h2_vqe_ref"):
+        g = golden(name)
+        u = P.u_table(g["coeff"], g["omegas"], float(g["T"]), g["ts"], str(g["basis"]))
+        np.testing.assert_allclose(u, g["u_tab"], rtol=1e-13, atol=1e-15)
+
+
+def test_dudc_matches_autograd_restatement():
+    rng = np.random.RandomState(3)
+    coeff = rng.normal(0, 1, [5, 6])
+    om = rng.uniform(1, 3, 5)
+    for basis in ("BSpline", "Legendre"):
+        d = P.dudc_table(coeff, om, 1.7, 0.61, basis)
+        ref = np.array([R.dudc_plain(i, 0.61, coeff, om, 1.7, basis) for i in range(5)])
+        np.testing.assert_allclose(d, ref, rtol=1e-14, atol=1e-16)
+
+
+def test_f_u_table_matches_restated_cc(golden):
+    g = golden("diffqc_cc_restated")
+    channels, k = [], 0
+    for c in g["chan_counts"]:
+        channels.append([list(g["chan_flat"][k + i]) for i in range(c)])
+        k += c
+    for func_type in (0, 1):
+        for tag, (T0, T) in zip(("fwd", "bwd"), g["spans"]):
+            n, dt, ts = P.step_grid(float(T0), float(T), int(g["per_step"]), use_abs=True)
+            u = P.f_u_table(channels, float(g["duration"]), func_type, g["vv"], ts)
+            np.testing.assert_allclose(u, g["f%d_%s_u" % (func_type, tag)], rtol=1e-13, atol=1e-15)
+
+
+def test_maxcut_angle_rows_reproduce_oracle_phases():
+    edges = R.random_regular_edges(6, seed=1)
+    prob = IsingProblem.maxcut(6, edges)
+    ref = R.maxcut_structured(6, edges)
+    assert prob.T == ref["T"] and prob.n_zz == len(edges)
+    coeff = np.random.RandomState(0).normal(0, 1, [len(prob.terms), 6])
+    n, dt, ts = P.step_grid(0, prob.T, 10)
+    u = P.u_table(coeff, prob.omegas, prob.T, ts)
+    rows = prob.angle_rows(u, dt)
+    k = 7
+    angle = np.full(64, rows[k, 0])
+    for e, (a, b) in enumerate(prob.zz_pairs):
+        angle += rows[k, 1 + e] * R.z_diag(6, a) * R.z_diag(6, b)
+    want = dt * ref["h0_diag"]
+    for i, t in enumerate(ref["terms"]):
+        if t[0] == "zz":
+            want = want + dt * u[k, i] * R.term_diag(ref, t)
+    np.testing.assert_allclose(angle, want, atol=1e-13)
+    np.testing.assert_allclose(rows[k, 1 + prob.n_zz:], dt * u[k, len(edges):], atol=1e-16)
