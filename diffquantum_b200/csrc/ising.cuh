@@ -28,6 +28,7 @@ struct dq_ising {
         std::vector<int> prefix_steps, suffix_steps, shift_kind, shift_index;
         std::vector<int64_t> prefix_off, suffix_off;     // row offsets
         bool uniform_psi0 = true;
+        bool scaled_ok = true;                            // every |x angle| and atan(r) <= 1 rad
         dq::DevBuf psi0;                                  // physical order, when not uniform
     } st;
 
@@ -53,6 +54,7 @@ int gen_build_mdiag(dq_ising* p, const double* m_zz, double m_const);
 
 // fused persistent engine (n >= 12)
 int fused_supported(const dq_ising* p);
+void fused_release(dq_ising* p);
 int fused_grad_run(dq_ising* p);
 int fused_evolve(dq_ising* p, c128* d_states, int batch, const double* h_rows, int n_steps,
                  double* d_energies, bool want_states);

@@ -73,6 +73,7 @@ int dq_ising_destroy(dq_ising* p) {
     if (!p) return DQ_OK;
     cudaSetDevice(p->ctx->device);
     cudaStreamSynchronize(p->ctx->stream);
+    dq::fused_release(p);
     dq::DevBuf* bufs[] = {&p->mdiag, &p->pairs_dev, &p->states, &p->phi, &p->rows_a, &p->rows_b, &p->trig_a,
                           &p->trig_b, &p->energies, &p->scratch, &p->io, &p->shift_desc, &p->st.psi0};
     for (auto* b : bufs) b->release();
@@ -223,6 +224,15 @@ int dq_ising_grad_stage(dq_ising* p, int n_samples, const int32_t* prefix_steps,
         }
     DQ_TRY(p->shift_desc.reserve(h.size() * sizeof(dq::ShiftDesc)));
     DQ_CUDA(cudaMemcpyAsync(p->shift_desc.p, h.data(), h.size() * sizeof(dq::ShiftDesc), cudaMemcpyHostToDevice, st));
+    {
+        double mx = fabs(atan(r));
+        const int off_x = 1 + p->n_zz;
+        for (int64_t k = 0; k < np; ++k)
+            for (int q = 0; q < p->n; ++q) mx = fmax(mx, fabs(prefix_angles[k * p->row_len + off_x + q]));
+        for (int64_t k = 0; k < ns; ++k)
+            for (int q = 0; q < p->n; ++q) mx = fmax(mx, fabs(suffix_angles[k * p->row_len + off_x + q]));
+        s.scaled_ok = mx <= 1.0;
+    }
     s.uniform_psi0 = psi0 == nullptr;
     if (psi0) {
         DQ_TRY(s.psi0.reserve(p->dim() * sizeof(c128)));

@@ -1,11 +1,897 @@
-// Fused persistent engine (placeholder until the kernels land): reports "unsupported" so the
-// API layer routes to the generic engine.
+// Fused persistent engine for the structured path (n >= 12), sm_100a.
+//
+// One product-formula step (diffqc.cc:155-164) = diagonal phase D(k) then X rotations on every
+// qubit.  Qubits are split into two sets by physical bit position, L = bits [0,10) and
+// H = bits [10,n).  Because the X rotations of one step commute with each other and D is
+// elementwise, the work is regrouped into PASSES that each touch one set only:
+//
+//     pass p :  [ mixer S_p of step p ]  ->  D(p+1)  ->  [ mixer S_p of step p+1 ]        S_p alternates L,H
+//
+// so a trajectory of N steps costs N+1 passes = ONE global read+write of the state per step.
+// Inside a pass a CTA owns a tile of 2^12 amplitudes (64 KiB of shared memory); every thread
+// keeps 32 amplitudes in registers and applies 5 qubits' butterflies per register round:
+//     outer-A (5 "K" bits, straight from global)  -> smem -> inner (5 "J" bits, phase, 5 "J" bits)
+//     -> smem -> outer-B (5 "K" bits) -> global / fused energy reduction.
+// Rotations use the scaled form a' = a - i tan(theta) b (2 FMA per amplitude per qubit); the product
+// of cosines is folded into the phase tables.  The diagonal phase is never computed per amplitude
+// with sincos: per thread it is  TC[column] * TKK[K bits] * prod XK_m  (base phase) and then a
+// product-state doubling over the 5 register bits with per-bit factors F_k (31 + 32 complex
+// multiplies per 32 amplitudes).  Tables are built per (trajectory, pass) by a setup kernel.
+//
+// The kernel is persistent: CTAs pull (pass, ket, tile) items from an atomic counter in pass-major
+// order; an item waits until all tiles of the previous pass of ITS ket are done (per-ket counter,
+// release/acquire through L2).  Several kets per launch keep every SM busy across pass boundaries,
+// and the ket group is sized to stay resident in the 126 MB L2 between passes.
+#include <algorithm>
+#include <math.h>
+#include <string.h>
 #include "ising.cuh"
+
 namespace dq {
-int fused_supported(const dq_ising*) { return 0; }
-int fused_grad_run(dq_ising*) { set_error("fused engine not built"); return DQ_ERR_UNSUPPORTED; }
-int fused_evolve(dq_ising*, c128*, int, const double*, int, double*, bool) {
-    set_error("fused engine not built");
-    return DQ_ERR_UNSUPPORTED;
+namespace fused {
+
+constexpr int kTileBits = 12;
+constexpr int kTile = 1 << kTileBits;      // amplitudes per tile
+constexpr int kThreads = 128;              // kTile / 32
+constexpr int kRegs = 32;                  // amplitudes per thread
+constexpr int kMaxNbr = 3;                 // neighbour bits per register qubit held in tables
+constexpr int kMaxPairs = 128;
+
+enum : int { F_ENERGY = 2, F_STORE = 4 };
+
+struct __align__(16) PassStep {
+    double2 tkk[32];                // base phase over the 5 K bits (includes constant + cos scale)
+    double2 aj[32];                 // J-internal pairs, relative to j = 0
+    double2 xk[5][8];               // K bit m x pattern of its column neighbours
+    double2 fj[5][8];               // J bit k x pattern of its non-J neighbours: exp(+2i w_k)
+    double2 rot[4][5];              // (cos, sin) or (1, tan) per slot {KA, J1, J2, KB} and bit
+    int flags;
+    int type;
+    unsigned long long tc_offset;   // first entry of this pass-step's column table
+};
+
+// Launch-constant geometry of one pass type; lives in kernel parameters (constant bank).
+struct TypeGeom {
+    int a, lowmask;                 // tile bit t -> physical: t < a ? t : 10 + (t - a)   (type H; L is identity)
+    int tid_lo_bits, high_end;
+    int fj_pos[5][kMaxNbr], fj_msk[5][kMaxNbr];
+    int xk_pos[5][kMaxNbr], xk_msk[5][kMaxNbr];
+    int offK[kRegs], offJ[kRegs];   // physical offset (amplitudes) of register j in the outer / inner round
+};
+
+// Host-side plan of a pass type (superset of TypeGeom; the setup kernel reads it from global memory).
+struct TypePlan {
+    TypeGeom g;
+    int k0, j0, start, spare_shift;
+    int jq[5], kq[5];               // x-angle column of the qubit on that register bit, -1 = spectator
+    int fj_pair[5][kMaxNbr], xk_pair[5][kMaxNbr];
+    int n_col_bits;
+    int n_pairs;
+    int has_aj;
+    // pair classes: 0 JJ, 1 KK, 2 JK, 3 JC, 4 KC, 5 CC ; i0/i1 local bit indices
+    signed char cls[kMaxPairs], i0[kMaxPairs], i1[kMaxPairs];
+};
+
+struct KetDesc {
+    const c128* src;                // read by pass 0
+    c128* buf;                      // written by every storing pass, read by passes > 0
+    const PassStep* steps;
+    double* partial;                // [tiles] energy partials of the final pass (may be NULL)
+    double sigma;                   // +1 / -1 : sign of the shift gate
+    double escale;                  // multiplies the energy (1/(1+r^2) for scaled X-shifted kets)
+    int n_pass;
+    int shift_kind;                 // -1 none, 0 ZZ on (sb0, sb1), 1 X on sb0   (physical bits)
+    int sb0, sb1;
+};
+
+struct SetupJob {
+    long long row_pre;              // row index into the angle table, -1 = none
+    long long row_cur;              // -1 = final pass
+    int type;
+    int flags;
+};
+
+struct LaunchArgs {
+    const KetDesc* kets;
+    const double2* tc;
+    const double* mdiag;
+    unsigned* counters;             // [0] next item, [1 + g] tiles done of ket g
+    int n_kets;
+    int max_pass;
+    int tiles_log2;
+    double r, ca, sa, c2a, s2a;     // shift gate: r, cos/sin(atan r), cos/sin(2 atan r)
+    TypeGeom geom[2];
+};
+
+// ------------------------------------------------------------------------------------------
+// device helpers
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ int insert5(int t, int p) { return (t & ((1 << p) - 1)) | ((t >> p) << (p + 5)); }
+__device__ __forceinline__ unsigned ld_acquire(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
 }
+__device__ __forceinline__ int gather3(size_t x, const int* pos, const int* msk) {
+    return (int)(((x >> pos[0]) & msk[0]) | (((x >> pos[1]) & msk[1]) << 1) | (((x >> pos[2]) & msk[2]) << 2));
+}
+
+// exp(-i theta X) on register bit B.  SCALED: rc = (1, tan) -> a' = a - i t b (cos folded elsewhere).
+template <bool SCALED, int B>
+__device__ __forceinline__ void rot_bit(c128 (&v)[kRegs], const double2 rc) {
+#pragma unroll
+    for (int j = 0; j < kRegs; ++j) {
+        if (j & (1 << B)) continue;
+        const c128 a = v[j], b = v[j | (1 << B)];
+        if (SCALED) {
+            v[j] = make_double2(fma(rc.y, b.y, a.x), fma(-rc.y, b.x, a.y));
+            v[j | (1 << B)] = make_double2(fma(rc.y, a.y, b.x), fma(-rc.y, a.x, b.y));
+        } else {
+            v[j] = make_double2(fma(rc.y, b.y, rc.x * a.x), fma(-rc.y, b.x, rc.x * a.y));
+            v[j | (1 << B)] = make_double2(fma(rc.y, a.y, rc.x * b.x), fma(-rc.y, a.x, rc.x * b.y));
+        }
+    }
+}
+
+// Straight-line on purpose: a branch around a butterfly block makes ptxas reconcile the 128
+// amplitude registers at the join with one move per FMA (measured: 2150 IMAD.MOV in v0).
+// An inactive slot holds the identity (1, 0) and costs only its FMAs.
+template <bool SCALED>
+__device__ __forceinline__ void rot_run(c128 (&v)[kRegs], const double2* rc, const int override_bit,
+                                        const double2 override_rc) {
+    double2 r0 = rc[0], r1 = rc[1], r2 = rc[2], r3 = rc[3], r4 = rc[4];
+    if (override_bit == 0) r0 = override_rc;
+    if (override_bit == 1) r1 = override_rc;
+    if (override_bit == 2) r2 = override_rc;
+    if (override_bit == 3) r3 = override_rc;
+    if (override_bit == 4) r4 = override_rc;
+    rot_bit<SCALED, 0>(v, r0);
+    rot_bit<SCALED, 1>(v, r1);
+    rot_bit<SCALED, 2>(v, r2);
+    rot_bit<SCALED, 3>(v, r3);
+    rot_bit<SCALED, 4>(v, r4);
+}
+
+// Geometry of the two pass types, compile-time where it can be.
+//   TYPE 0 (L): tile = physical bits [0,12);  K = tile bits 5..9, J = tile bits 0..4.
+//   TYPE 1 (H): tile = `a` low spectator bits + physical bits [10, 10+12-a);  K = tile bits 2..6, J = 7..11
+//               (J on top so that J_L = bits 0..4 and J_H never share two bits: a ZZ shift gate must find a
+//               pass type in which its pair is not J-J).
+template <int TYPE> struct Geo;
+template <> struct Geo<0> {
+    static constexpr int k0 = 5, j0 = 0, spare_shift = 10;
+    __device__ static __forceinline__ int swz(int i) { return i ^ ((i >> 5) & 7); }
+};
+template <> struct Geo<1> {
+    static constexpr int k0 = 2, j0 = 7, spare_shift = 0;
+    __device__ static __forceinline__ int swz(int i) { return i ^ (((i >> 7) & 1) << 2); }
+};
+
+template <bool SCALED, bool AJ, int TYPE>
+__device__ __forceinline__ void process_tile(const LaunchArgs& A, const KetDesc* __restrict__ kd, const PassStep& P,
+                                             c128* __restrict__ tile, double* __restrict__ s_red, const int p,
+                                             const int t_id) {
+    using G = Geo<TYPE>;
+    const TypeGeom& T = A.geom[TYPE];
+    const int tid = threadIdx.x;
+    const int flags = P.flags;
+
+    // tile geometry
+    size_t tbase, xK, xJ;
+    const int iK = insert5(tid, G::k0);
+    const int iJ = insert5(tid, G::j0);
+    if (TYPE == 0) {
+        tbase = (size_t)t_id << kTileBits;
+        xK = tbase + iK;
+        xJ = tbase + iJ;
+    } else {
+        tbase = ((size_t)(t_id & ((1 << T.tid_lo_bits) - 1)) << T.a) | ((size_t)(t_id >> T.tid_lo_bits) << T.high_end);
+        xK = tbase + ((size_t)(iK & T.lowmask) | ((size_t)(iK >> T.a) << 10));
+        xJ = tbase + ((size_t)(iJ & T.lowmask) | ((size_t)(iJ >> T.a) << 10));
+    }
+
+    // shift gate of the estimator (pass 0 only), expressed as data so the amplitude code stays straight-line
+    const int shift_kind = (p == 0) ? kd->shift_kind : -1;
+    const double sigma = kd->sigma;
+    int ovK = -1, ovJ = -1;
+    int tb0 = -1, tb1 = -1;                  // tile bits of the shift operands
+    if (shift_kind >= 0) {
+        const int s0 = kd->sb0, s1 = kd->sb1;
+        if (TYPE == 0) { tb0 = s0 < kTileBits ? s0 : -1; tb1 = s1 < kTileBits ? s1 : -1; }
+        else {
+            tb0 = s0 < T.a ? s0 : (s0 >= 10 ? s0 - 10 + T.a : -1);
+            tb1 = s1 < T.a ? s1 : (s1 >= 10 ? s1 - 10 + T.a : -1);
+        }
+        if (shift_kind == 1) {
+            if (tb0 >= G::k0 && tb0 < G::k0 + 5) ovK = tb0 - G::k0;
+            if (tb0 >= G::j0 && tb0 < G::j0 + 5) ovJ = tb0 - G::j0;
+        }
+    }
+    // (I + i sigma r X) = exp(-i theta X) / cos(theta) with tan(theta) = -sigma r
+    const double2 shift_rc = SCALED ? make_double2(1.0, -sigma * A.r) : make_double2(A.ca, -sigma * A.sa);
+
+    c128 v[kRegs];
+    // ---- outer-A : global -> registers, K-bit rotations of the previous step ----------------------
+    {
+        const c128* __restrict__ src = (p == 0 ? kd->src : kd->buf) + xK;
+#pragma unroll
+        for (int j = 0; j < kRegs; ++j) v[j] = __ldcg(src + (TYPE == 0 ? (j << G::k0) : T.offK[j]));
+    }
+    rot_run<SCALED>(v, P.rot[0], ovK, shift_rc);
+#pragma unroll
+    for (int j = 0; j < kRegs; ++j) tile[G::swz(iK | (j << G::k0))] = v[j];
+    __syncthreads();
+
+    // ---- inner : J-bit rotations, phase, J-bit rotations ---------------------------------------------
+#pragma unroll
+    for (int j = 0; j < kRegs; ++j) v[j] = tile[G::swz(iJ | (j << G::j0))];
+    rot_run<SCALED>(v, P.rot[1], ovJ, shift_rc);
+    {
+        const int kb = (iJ >> G::k0) & 31;
+        const unsigned col = (unsigned)((iJ >> G::spare_shift) & 3) | ((unsigned)t_id << 2);
+        c128 phi = __ldg(A.tc + P.tc_offset + col);
+        phi = cmul(phi, P.tkk[kb]);
+#pragma unroll
+        for (int m = 0; m < 5; ++m) {
+            if (T.xk_msk[m][0]) {            // launch-uniform
+                c128 w = P.xk[m][gather3(xJ, T.xk_pos[m], T.xk_msk[m])];
+                if ((kb >> m) & 1) w.y = -w.y;
+                phi = cmul(phi, w);
+            }
+        }
+        c128 F[5];
+#pragma unroll
+        for (int k = 0; k < 5; ++k) F[k] = P.fj[k][gather3(xJ, T.fj_pos[k], T.fj_msk[k])];
+        if (shift_kind == 0) {               // ZZ shift gate exp(i sigma alpha z0 z1); never both operands in J
+            const int j0b = (tb0 >= G::j0 && tb0 < G::j0 + 5) ? tb0 - G::j0 : -1;
+            const int j1b = (tb1 >= G::j0 && tb1 < G::j0 + 5) ? tb1 - G::j0 : -1;
+            const double z0 = ((xJ >> kd->sb0) & 1) ? -1.0 : 1.0;
+            const double z1 = ((xJ >> kd->sb1) & 1) ? -1.0 : 1.0;
+            // with the J operand at 0 (z = +1) the factor is exp(i sigma alpha z_other)
+            phi = cmul(phi, make_double2(A.ca, sigma * A.sa * z0 * z1));
+            const int jb = j0b >= 0 ? j0b : j1b;
+            if (jb >= 0) {                   // flipping that J bit multiplies by exp(-2 i sigma alpha z_other)
+                const double zo = j0b >= 0 ? z1 : z0;
+                const c128 f = make_double2(A.c2a, -sigma * A.s2a * zo);
+#pragma unroll
+                for (int k = 0; k < 5; ++k)
+                    if (k == jb) F[k] = cmul(F[k], f);
+            }
+        }
+#pragma unroll
+        for (int b4 = 0; b4 < 2; ++b4) {
+            const c128 p4 = b4 ? cmul(phi, F[4]) : phi;
+#pragma unroll
+            for (int b3 = 0; b3 < 2; ++b3) {
+                const c128 p3 = b3 ? cmul(p4, F[3]) : p4;
+#pragma unroll
+                for (int b2 = 0; b2 < 2; ++b2) {
+                    const c128 p2 = b2 ? cmul(p3, F[2]) : p3;
+#pragma unroll
+                    for (int b1 = 0; b1 < 2; ++b1) {
+                        const c128 p1 = b1 ? cmul(p2, F[1]) : p2;
+                        const int j = (b4 << 4) | (b3 << 3) | (b2 << 2) | (b1 << 1);
+                        v[j] = cmul(v[j], p1);
+                        v[j | 1] = cmul(v[j | 1], cmul(p1, F[0]));
+                    }
+                }
+            }
+        }
+        if (AJ) {
+#pragma unroll
+            for (int j = 0; j < kRegs; ++j) v[j] = cmul(v[j], P.aj[j]);
+        }
+    }
+    rot_run<SCALED>(v, P.rot[2], -1, shift_rc);
+#pragma unroll
+    for (int j = 0; j < kRegs; ++j) tile[G::swz(iJ | (j << G::j0))] = v[j];
+    __syncthreads();
+
+    // ---- outer-B : K-bit rotations of the new step, then store or reduce -----------------------------
+#pragma unroll
+    for (int j = 0; j < kRegs; ++j) v[j] = tile[G::swz(iK | (j << G::k0))];
+    rot_run<SCALED>(v, P.rot[3], -1, shift_rc);
+    if (flags & F_ENERGY) {
+        const double* __restrict__ md = A.mdiag + xK;
+        double e = 0.0;
+#pragma unroll
+        for (int j = 0; j < kRegs; ++j) {
+            const double m = __ldg(md + (TYPE == 0 ? (j << G::k0) : T.offK[j]));
+            e = fma(m, fma(v[j].x, v[j].x, v[j].y * v[j].y), e);
+        }
+        for (int o = 16; o > 0; o >>= 1) e += __shfl_xor_sync(0xffffffffu, e, o);
+        if ((tid & 31) == 0) s_red[tid >> 5] = e;
+        __syncthreads();
+        if (tid == 0) kd->partial[t_id] = (s_red[0] + s_red[1] + s_red[2] + s_red[3]) * kd->escale;
+    }
+    if (flags & F_STORE) {
+        c128* __restrict__ dst = kd->buf + xK;
+#pragma unroll
+        for (int j = 0; j < kRegs; ++j) __stcg(dst + (TYPE == 0 ? (j << G::k0) : T.offK[j]), v[j]);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// the persistent pass kernel
+// ------------------------------------------------------------------------------------------
+template <bool SCALED, bool AJ>
+__global__ void __launch_bounds__(kThreads, 2) k_fused_passes(const __grid_constant__ LaunchArgs A) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    c128* tile = reinterpret_cast<c128*>(smem_raw);
+    PassStep* cache = reinterpret_cast<PassStep*>(smem_raw + sizeof(c128) * kTile);
+    __shared__ unsigned s_item;
+    __shared__ double s_red[kThreads / 32];
+
+    const int tid = threadIdx.x;
+    const int tiles = 1 << A.tiles_log2;
+    const unsigned total = (unsigned)A.max_pass * (unsigned)A.n_kets * (unsigned)tiles;
+    const PassStep* cached_ps = nullptr;
+
+    for (;;) {
+        __syncthreads();                       // tile, cache and s_item are free for reuse
+        if (tid == 0) s_item = atomicAdd(&A.counters[0], 1u);
+        __syncthreads();
+        const unsigned item = s_item;
+        if (item >= total) break;
+        const int t_id = (int)(item & (unsigned)(tiles - 1));
+        const unsigned rest = item >> A.tiles_log2;
+        const int g = (int)(rest % (unsigned)A.n_kets);
+        const int p = (int)(rest / (unsigned)A.n_kets);
+        const KetDesc* __restrict__ kd = A.kets + g;
+        if (p >= kd->n_pass) continue;
+        const PassStep* ps_g = kd->steps + p;
+
+        if (ps_g != cached_ps) {               // refresh the shared-memory copy of the tables
+            const int4* s4 = reinterpret_cast<const int4*>(ps_g);
+            int4* d4 = reinterpret_cast<int4*>(cache);
+            for (int i = tid; i < (int)(sizeof(PassStep) / 16); i += kThreads) d4[i] = __ldg(s4 + i);
+            cached_ps = ps_g;
+        }
+        if (p > 0 && tid == 0) {               // all tiles of this ket's previous pass must be stored
+            const unsigned need = (unsigned)p * (unsigned)tiles;
+            while (ld_acquire(&A.counters[1 + g]) < need) __nanosleep(32);
+        }
+        __syncthreads();
+        if (cache->type == 0) process_tile<SCALED, AJ, 0>(A, kd, *cache, tile, s_red, p, t_id);
+        else process_tile<SCALED, AJ, 1>(A, kd, *cache, tile, s_red, p, t_id);
+        __syncthreads();                         // every thread's stores are issued
+        if (tid == 0) {
+            __threadfence();
+            atomicAdd(&A.counters[1 + g], 1u);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// table setup: one CTA per pass-step (y = column-table chunk)
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ double zsign(int bits, int i) { return ((bits >> i) & 1) ? -1.0 : 1.0; }
+
+__global__ void __launch_bounds__(128) k_setup(const SetupJob* __restrict__ jobs, const double* __restrict__ rows,
+                                               int row_len, int n_zz, const TypePlan* __restrict__ types,
+                                               PassStep* __restrict__ steps, double2* __restrict__ tc,
+                                               int n_col_bits, int scaled) {
+    const SetupJob job = jobs[blockIdx.x];
+    const TypePlan& T = types[job.type];
+    PassStep& P = steps[blockIdx.x];
+    const double* pre = job.row_pre >= 0 ? rows + job.row_pre * row_len : nullptr;
+    const double* cur = job.row_cur >= 0 ? rows + job.row_cur * row_len : nullptr;
+    const int off_x = 1 + n_zz;
+    const unsigned long long tc_off = (unsigned long long)blockIdx.x << n_col_bits;
+    const int tid = threadIdx.x;
+
+    // rotation angles by slot {KA, J1, J2, KB}; the final pass (no `cur`) moves the K rotations of the
+    // last step to slot KB so that the energy is reduced from the coalesced outer layout
+    double ang[4][5];
+    double scale = 1.0;
+#pragma unroll
+    for (int b = 0; b < 5; ++b) {
+        const double ka = (pre && T.kq[b] >= 0) ? pre[off_x + T.kq[b]] : 0.0;
+        const double j1 = (pre && T.jq[b] >= 0) ? pre[off_x + T.jq[b]] : 0.0;
+        const double j2 = (cur && T.jq[b] >= 0) ? cur[off_x + T.jq[b]] : 0.0;
+        const double kbv = (cur && T.kq[b] >= 0) ? cur[off_x + T.kq[b]] : 0.0;
+        ang[0][b] = cur ? ka : 0.0;
+        ang[1][b] = j1;
+        ang[2][b] = j2;
+        ang[3][b] = cur ? kbv : ka;
+    }
+    if (scaled) {
+#pragma unroll
+        for (int s = 0; s < 4; ++s)
+#pragma unroll
+            for (int b = 0; b < 5; ++b) scale *= cos(ang[s][b]);
+    }
+    if (blockIdx.y == 0) {
+        if (tid < 20) {
+            const int s = tid / 5, b = tid % 5;
+            double sn, cs;
+            sincos(ang[s][b], &sn, &cs);
+            P.rot[s][b] = scaled ? make_double2(1.0, sn / cs) : make_double2(cs, sn);
+        }
+        if (tid == 0) {
+            P.flags = job.flags;
+            P.type = job.type;
+            P.tc_offset = tc_off;
+        }
+        // phase tables; the final pass has no phase: every angle is 0 and only the cosine scale remains
+        if (tid < 32) {                         // tkk[kb] and aj[j]
+            double a = cur ? cur[0] : 0.0, aa = 0.0;
+            if (cur)
+                for (int e = 0; e < T.n_pairs; ++e) {
+                    const double g = cur[1 + e];
+                    switch (T.cls[e]) {
+                        case 0: a += g; aa += g * (zsign(tid, T.i0[e]) * zsign(tid, T.i1[e]) - 1.0); break;
+                        case 1: a += g * zsign(tid, T.i0[e]) * zsign(tid, T.i1[e]); break;
+                        case 2: a += g * zsign(tid, T.i1[e]); break;
+                        default: break;
+                    }
+                }
+            double sn, cs;
+            sincos(a, &sn, &cs);
+            P.tkk[tid] = make_double2(scale * cs, -scale * sn);
+            sincos(aa, &sn, &cs);
+            P.aj[tid] = make_double2(cs, -sn);
+        } else if (tid < 32 + 40) {             // xk[m][pat]
+            const int m = (tid - 32) >> 3, pat = (tid - 32) & 7;
+            double a = 0.0;
+            if (cur)
+                for (int t = 0; t < kMaxNbr; ++t)
+                    if (T.g.xk_msk[m][t]) a += cur[1 + T.xk_pair[m][t]] * zsign(pat, t);
+            double sn, cs;
+            sincos(a, &sn, &cs);
+            P.xk[m][pat] = make_double2(cs, -sn);
+        } else if (tid < 32 + 80) {             // fj[k][pat] = exp(+2i w_k)
+            const int k = (tid - 72) >> 3, pat = (tid - 72) & 7;
+            double a = 0.0;
+            if (cur)
+                for (int t = 0; t < kMaxNbr; ++t)
+                    if (T.g.fj_msk[k][t]) a += cur[1 + T.fj_pair[k][t]] * zsign(pat, t);
+            double sn, cs;
+            sincos(2.0 * a, &sn, &cs);
+            P.fj[k][pat] = make_double2(cs, sn);
+        }
+    }
+    // column table: CC pairs + fields from J neighbours
+    const unsigned ncol = 1u << n_col_bits;
+    for (unsigned col = blockIdx.y * blockDim.x + tid; col < ncol; col += gridDim.y * blockDim.x) {
+        double a = 0.0;
+        if (cur)
+            for (int e = 0; e < T.n_pairs; ++e) {
+                const double g = cur[1 + e];
+                if (T.cls[e] == 5) a += g * ((((col >> T.i0[e]) ^ (col >> T.i1[e])) & 1) ? -1.0 : 1.0);
+                else if (T.cls[e] == 3) a += g * (((col >> T.i1[e]) & 1) ? -1.0 : 1.0);
+            }
+        double sn, cs;
+        sincos(a, &sn, &cs);
+        tc[tc_off + col] = make_double2(cs, -sn);
+    }
+}
+
+__global__ void k_sum_partials(const double* __restrict__ partial, int tiles, const int* __restrict__ out_index,
+                               double* __restrict__ out) {
+    double acc = 0.0;
+    for (int i = threadIdx.x; i < tiles; i += 32) acc += partial[(size_t)blockIdx.x * tiles + i];
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (threadIdx.x == 0) out[out_index[blockIdx.x]] = acc;
+}
+
+// ------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------
+struct Plan {
+    bool ok = false;
+    int n = 0, n_col_bits = 0, tiles_log2 = 0;
+    bool has_aj = false;
+    TypePlan types[2];
+    int jphys[2][5];
+    DevBuf d_types, jobs, steps, tc, kets, counters, partials, out_index, work, rows, phi, uniform;
+    size_t smem_bytes = 0;
+    int ctas_per_sm = 0;
+    int counter_slots = 0, counter_cursor = 0;
+};
+
+static std::vector<std::pair<dq_ising*, Plan*>> g_plans;     // one plan per problem
+
+static Plan* find_plan(const dq_ising* p) {
+    for (auto& kv : g_plans)
+        if (kv.first == p) return kv.second;
+    return nullptr;
+}
+
+static bool build_type(const dq_ising* p, int type, TypePlan& T, int* jphys_out) {
+    const int n = p->n;
+    memset(&T, 0, sizeof(T));
+    int a, b;
+    if (type == 0) {            // L: tile = physical bits [0,12), K = bits 5..9, J = bits 0..4
+        a = kTileBits; T.start = kTileBits; b = 0;
+        T.k0 = 5; T.j0 = 0; T.spare_shift = 10;
+    } else {                    // H: tile = low spectators [0,a) + physical bits [10,n); J = top 5 tile bits
+        b = n - 10;
+        a = kTileBits - b; T.start = 10;
+        T.k0 = 2; T.j0 = 7; T.spare_shift = 0;
+    }
+    T.g.a = a;
+    T.g.lowmask = (1 << a) - 1;
+    T.g.tid_lo_bits = T.start - a;
+    T.g.high_end = T.start + b;
+    T.n_col_bits = n - 10;
+    auto phys_of_tile_bit = [&](int t) { return t < a ? t : T.start + (t - a); };
+    auto phys_off = [&](int i) { return (i & T.g.lowmask) | ((i >> a) << T.start); };
+    auto tile_bit_of_phys = [&](int pos) { return pos < a ? pos : (pos >= T.start && pos < T.start + b ? pos - T.start + a : -1); };
+    for (int j = 0; j < kRegs; ++j) {
+        T.g.offK[j] = phys_off(j << T.k0);
+        T.g.offJ[j] = phys_off(j << T.j0);
+    }
+    // which physical bits are rotated by this pass type
+    auto active = [&](int pos) { return type == 0 ? (pos < 10) : (pos >= 10); };
+    int qubit_of_pos[64];
+    for (int q = 0; q < n; ++q) qubit_of_pos[p->bitpos[q]] = q;
+    int jphys[5], kphys[5];
+    for (int i = 0; i < 5; ++i) {
+        jphys[i] = phys_of_tile_bit(T.j0 + i);
+        kphys[i] = phys_of_tile_bit(T.k0 + i);
+        jphys_out[i] = jphys[i];
+        T.jq[i] = active(jphys[i]) ? qubit_of_pos[jphys[i]] : -1;
+        T.kq[i] = active(kphys[i]) ? qubit_of_pos[kphys[i]] : -1;
+    }
+    // column bits: the two spare tile bits, then the tile-id bits in ascending physical order
+    std::vector<int> colphys;
+    colphys.push_back(phys_of_tile_bit(T.spare_shift));
+    colphys.push_back(phys_of_tile_bit(T.spare_shift + 1));
+    for (int pos = 0; pos < n; ++pos)
+        if (tile_bit_of_phys(pos) < 0) colphys.push_back(pos);
+    if ((int)colphys.size() != n - 10) return false;
+    auto local = [&](int pos, int& kind, int& idx) {
+        for (int i = 0; i < 5; ++i) if (jphys[i] == pos) { kind = 0; idx = i; return; }
+        for (int i = 0; i < 5; ++i) if (kphys[i] == pos) { kind = 1; idx = i; return; }
+        for (size_t i = 0; i < colphys.size(); ++i) if (colphys[i] == pos) { kind = 2; idx = (int)i; return; }
+        kind = -1; idx = -1;
+    };
+    if (p->n_zz > kMaxPairs) return false;
+    T.n_pairs = p->n_zz;
+    int fj_cnt[5] = {0, 0, 0, 0, 0}, xk_cnt[5] = {0, 0, 0, 0, 0};
+    for (int e = 0; e < p->n_zz; ++e) {
+        int ka, ia, kb2, ib;
+        local(p->pa[e], ka, ia);
+        local(p->pb[e], kb2, ib);
+        if (ka < 0 || kb2 < 0) return false;
+        if (ka > kb2) { std::swap(ka, kb2); std::swap(ia, ib); }
+        const int posb = (kb2 == 1) ? kphys[ib] : (kb2 == 2 ? colphys[ib] : jphys[ib]);
+        if (ka == 0 && kb2 == 0) { T.cls[e] = 0; T.has_aj = 1; }
+        else if (ka == 1 && kb2 == 1) T.cls[e] = 1;
+        else if (ka == 0 && kb2 == 1) T.cls[e] = 2;
+        else if (ka == 0 && kb2 == 2) T.cls[e] = 3;
+        else if (ka == 1 && kb2 == 2) T.cls[e] = 4;
+        else T.cls[e] = 5;
+        T.i0[e] = (signed char)ia;
+        T.i1[e] = (signed char)ib;
+        if (ka == 0 && kb2 != 0) {              // neighbour of J bit ia outside J
+            if (fj_cnt[ia] >= kMaxNbr) return false;
+            const int t = fj_cnt[ia]++;
+            T.g.fj_pos[ia][t] = posb; T.g.fj_msk[ia][t] = 1; T.fj_pair[ia][t] = e;
+        }
+        if (ka == 1 && kb2 == 2) {              // column neighbour of K bit ia
+            if (xk_cnt[ia] >= kMaxNbr) return false;
+            const int t = xk_cnt[ia]++;
+            T.g.xk_pos[ia][t] = posb; T.g.xk_msk[ia][t] = 1; T.xk_pair[ia][t] = e;
+        }
+    }
+    return true;
+}
+
+template <typename K> static bool prep_kernel(K kern, size_t smem, int* occ) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return false;
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, kern, kThreads, smem) == cudaSuccess && *occ >= 1;
+}
+
+static Plan* get_plan(dq_ising* p) {
+    Plan* pl = find_plan(p);
+    if (pl) return pl;
+    pl = new Plan();
+    g_plans.push_back({p, pl});
+    pl->n = p->n;
+    if (p->ctx->set_device() != DQ_OK) return pl;
+    if (p->n < kTileBits || p->n > 20) return pl;       // two sets cover n <= 20
+    for (int t = 0; t < 2; ++t)
+        if (!build_type(p, t, pl->types[t], pl->jphys[t])) return pl;
+    pl->has_aj = pl->types[0].has_aj || pl->types[1].has_aj;
+    pl->n_col_bits = p->n - 10;
+    pl->tiles_log2 = p->n - kTileBits;
+    pl->smem_bytes = sizeof(c128) * kTile + sizeof(PassStep);
+    if (pl->d_types.reserve(sizeof(TypePlan) * 2) != DQ_OK) return pl;
+    if (cudaMemcpy(pl->d_types.p, pl->types, sizeof(TypePlan) * 2, cudaMemcpyHostToDevice) != cudaSuccess) return pl;
+    int occ = 0, o2 = 0;
+    bool good = pl->has_aj ? (prep_kernel(k_fused_passes<true, true>, pl->smem_bytes, &occ) &&
+                              prep_kernel(k_fused_passes<false, true>, pl->smem_bytes, &o2))
+                           : (prep_kernel(k_fused_passes<true, false>, pl->smem_bytes, &occ) &&
+                              prep_kernel(k_fused_passes<false, false>, pl->smem_bytes, &o2));
+    if (!good) { cudaGetLastError(); return pl; }
+    pl->ctas_per_sm = std::min(occ, o2);
+    pl->counter_slots = 1 << 16;
+    if (pl->counters.reserve(pl->counter_slots * sizeof(unsigned)) != DQ_OK) return pl;
+    pl->ok = true;
+    return pl;
+}
+
+// A trajectory = rows [row0, row0 + n_steps); class c = index of its first pass type.
+struct Traj {
+    long long row0;
+    int n_steps;
+    int cls;
+    bool final_energy;
+    size_t step0;          // first PassStep index (filled by add_traj)
+};
+
+static void add_traj(std::vector<SetupJob>& jobs, Traj& t) {
+    t.step0 = jobs.size();
+    for (int p = 0; p <= t.n_steps; ++p) {
+        SetupJob j;
+        j.row_pre = p >= 1 ? t.row0 + p - 1 : -1;
+        j.row_cur = p < t.n_steps ? t.row0 + p : -1;
+        j.type = (p + t.cls) & 1;
+        j.flags = p < t.n_steps ? F_STORE : (t.final_energy ? F_ENERGY : F_STORE);
+        jobs.push_back(j);
+    }
+}
+
+static int run_setup(dq_ising* p, Plan* pl, const std::vector<SetupJob>& jobs, const double* d_rows, bool scaled) {
+    cudaStream_t st = p->ctx->stream;
+    DQ_TRY(pl->jobs.reserve(jobs.size() * sizeof(SetupJob)));
+    DQ_TRY(pl->steps.reserve(jobs.size() * sizeof(PassStep)));
+    DQ_TRY(pl->tc.reserve((jobs.size() << pl->n_col_bits) * sizeof(double2)));
+    DQ_CUDA(cudaMemcpyAsync(pl->jobs.p, jobs.data(), jobs.size() * sizeof(SetupJob), cudaMemcpyHostToDevice, st));
+    const unsigned ncol = 1u << pl->n_col_bits;
+    dim3 grid((unsigned)jobs.size(), std::max(1u, std::min(8u, ncol / 128)));
+    k_setup<<<grid, 128, 0, st>>>(pl->jobs.as<SetupJob>(), d_rows, p->row_len, p->n_zz, pl->d_types.as<TypePlan>(),
+                                  pl->steps.as<PassStep>(), pl->tc.as<double2>(), pl->n_col_bits, scaled ? 1 : 0);
+    p->ctx->launches++;
+    DQ_CUDA(cudaGetLastError());
+    return DQ_OK;
+}
+
+static int launch_group(dq_ising* p, Plan* pl, const KetDesc* d_kets, int n_kets, int max_pass, bool scaled, double r) {
+    cudaStream_t st = p->ctx->stream;
+    if (pl->counter_cursor + 1 + n_kets > pl->counter_slots) pl->counter_cursor = 0;
+    unsigned* ctr = pl->counters.as<unsigned>() + pl->counter_cursor;
+    pl->counter_cursor += 1 + n_kets;
+    DQ_CUDA(cudaMemsetAsync(ctr, 0, (1 + n_kets) * sizeof(unsigned), st));
+    LaunchArgs A;
+    A.kets = d_kets;
+    A.tc = pl->tc.as<double2>();
+    A.mdiag = p->mdiag.as<double>();
+    A.counters = ctr;
+    A.n_kets = n_kets;
+    A.max_pass = max_pass;
+    A.tiles_log2 = pl->tiles_log2;
+    const double alpha = atan(r);
+    A.r = r; A.ca = cos(alpha); A.sa = sin(alpha); A.c2a = cos(2 * alpha); A.s2a = sin(2 * alpha);
+    A.geom[0] = pl->types[0].g;
+    A.geom[1] = pl->types[1].g;
+    const long long all_items = ((long long)n_kets << pl->tiles_log2) * max_pass;
+    long long grid = (long long)p->ctx->prop.multiProcessorCount * pl->ctas_per_sm;
+    if (grid > all_items) grid = all_items;
+    if (scaled) {
+        if (pl->has_aj) k_fused_passes<true, true><<<(unsigned)grid, kThreads, pl->smem_bytes, st>>>(A);
+        else k_fused_passes<true, false><<<(unsigned)grid, kThreads, pl->smem_bytes, st>>>(A);
+    } else {
+        if (pl->has_aj) k_fused_passes<false, true><<<(unsigned)grid, kThreads, pl->smem_bytes, st>>>(A);
+        else k_fused_passes<false, false><<<(unsigned)grid, kThreads, pl->smem_bytes, st>>>(A);
+    }
+    p->ctx->launches++;
+    DQ_CUDA(cudaGetLastError());
+    return DQ_OK;
+}
+
+static bool rows_allow_scaled(const dq_ising* p, const double* rows, long long n_rows, double r) {
+    double mx = fabs(atan(r));
+    for (long long k = 0; k < n_rows; ++k)
+        for (int q = 0; q < p->n; ++q) mx = std::max(mx, fabs(rows[k * p->row_len + 1 + p->n_zz + q]));
+    return mx <= 1.0;              // |tan| <= 1.56: the scaled butterfly stays well conditioned
+}
+
+static bool in_j(const Plan* pl, int type, int pos) {
+    for (int i = 0; i < 5; ++i)
+        if (pl->jphys[type][i] == pos) return true;
+    return false;
+}
+
+}  // namespace fused
+
+int fused_supported(const dq_ising* p) {
+    fused::Plan* pl = fused::get_plan(const_cast<dq_ising*>(p));
+    return pl->ok ? 1 : 0;
+}
+
+void fused_release(dq_ising* p) {
+    for (size_t i = 0; i < fused::g_plans.size(); ++i)
+        if (fused::g_plans[i].first == p) {
+            fused::Plan* pl = fused::g_plans[i].second;
+            DevBuf* bufs[] = {&pl->d_types, &pl->jobs, &pl->steps, &pl->tc, &pl->kets, &pl->counters, &pl->partials,
+                              &pl->out_index, &pl->work, &pl->rows, &pl->phi, &pl->uniform};
+            for (auto* b : bufs) b->release();
+            delete pl;
+            fused::g_plans.erase(fused::g_plans.begin() + i);
+            return;
+        }
+}
+
+// Evolve `batch` states in place through the same rows (API: dq_ising_evolve).
+int fused_evolve(dq_ising* p, c128* d_states, int batch, const double* h_rows, int n_steps, double* d_energies,
+                 bool want_states) {
+    using namespace fused;
+    Plan* pl = get_plan(p);
+    DQ_REQUIRE(pl->ok, "fused engine unavailable for this problem");
+    cudaStream_t st = p->ctx->stream;
+    const bool scaled = rows_allow_scaled(p, h_rows, n_steps, 0.0);
+    const size_t N = p->dim();
+    const int tiles = 1 << pl->tiles_log2;
+    DQ_TRY(pl->rows.reserve((size_t)std::max(1, n_steps) * p->row_len * sizeof(double)));
+    if (n_steps)
+        DQ_CUDA(cudaMemcpyAsync(pl->rows.p, h_rows, (size_t)n_steps * p->row_len * sizeof(double), cudaMemcpyHostToDevice, st));
+    std::vector<SetupJob> jobs;
+    Traj tr{0, n_steps, 0, !want_states, 0};       // energy-only: the final pass reduces instead of storing
+    add_traj(jobs, tr);
+    DQ_TRY(run_setup(p, pl, jobs, pl->rows.as<double>(), scaled));
+    std::vector<KetDesc> kets(batch);
+    DQ_TRY(pl->partials.reserve((size_t)batch * tiles * sizeof(double)));
+    for (int g = 0; g < batch; ++g) {
+        KetDesc& k = kets[g];
+        k.src = d_states + (size_t)g * N;
+        k.buf = d_states + (size_t)g * N;
+        k.steps = pl->steps.as<PassStep>();
+        k.partial = pl->partials.as<double>() + (size_t)g * tiles;
+        k.sigma = 0.0;
+        k.escale = 1.0;
+        k.n_pass = n_steps + 1;
+        k.shift_kind = -1;
+        k.sb0 = k.sb1 = 0;
+    }
+    DQ_TRY(pl->kets.reserve(kets.size() * sizeof(KetDesc)));
+    DQ_CUDA(cudaMemcpyAsync(pl->kets.p, kets.data(), kets.size() * sizeof(KetDesc), cudaMemcpyHostToDevice, st));
+    const int G = std::max(1, p->ket_group);
+    for (int g0 = 0; g0 < batch; g0 += G)
+        DQ_TRY(launch_group(p, pl, pl->kets.as<KetDesc>() + g0, std::min(G, batch - g0), n_steps + 1, scaled, 0.5));
+    if (d_energies) {
+        if (want_states) {
+            DQ_TRY(gen_energy(p, d_states, batch, d_energies));
+        } else {
+            std::vector<int> idx(batch);
+            for (int g = 0; g < batch; ++g) idx[g] = g;
+            DQ_TRY(pl->out_index.reserve(batch * sizeof(int)));
+            DQ_CUDA(cudaMemcpyAsync(pl->out_index.p, idx.data(), batch * sizeof(int), cudaMemcpyHostToDevice, st));
+            k_sum_partials<<<batch, 32, 0, st>>>(pl->partials.as<double>(), tiles, pl->out_index.as<int>(), d_energies);
+            p->ctx->launches++;
+        }
+    }
+    DQ_CUDA(cudaGetLastError());
+    return DQ_OK;
+}
+
+// Batched gradient samples from the staged tables (API: dq_ising_grad_run_staged).
+int fused_grad_run(dq_ising* p) {
+    using namespace fused;
+    Plan* pl = get_plan(p);
+    DQ_REQUIRE(pl->ok, "fused engine unavailable for this problem");
+    auto& s = p->st;
+    cudaStream_t st = p->ctx->stream;
+    const size_t N = p->dim();
+    const int tiles = 1 << pl->tiles_log2;
+    const int B = s.n_samples, n_shift = s.n_shift, kets_per = 2 * n_shift;
+    const int G = std::max(1, p->ket_group);
+    const bool scaled = s.scaled_ok;
+
+    // ---- tables: rows_a (prefix) and rows_b (suffix) live in one device table ---------------------
+    const long long np = s.prefix_off[B], ns = s.suffix_off[B];
+    DQ_TRY(pl->rows.reserve((size_t)std::max<long long>(1, np + ns) * p->row_len * sizeof(double)));
+    if (np) DQ_CUDA(cudaMemcpyAsync(pl->rows.p, p->rows_a.p, np * p->row_len * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    if (ns) DQ_CUDA(cudaMemcpyAsync(pl->rows.as<double>() + np * p->row_len, p->rows_b.p, ns * p->row_len * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    std::vector<SetupJob> jobs;
+    std::vector<Traj> pre(B), sufL(B), sufH(B);
+    for (int b = 0; b < B; ++b) {
+        pre[b] = Traj{s.prefix_off[b], s.prefix_steps[b], 0, false, 0};
+        sufL[b] = Traj{np + s.suffix_off[b], s.suffix_steps[b], 0, true, 0};
+        sufH[b] = Traj{np + s.suffix_off[b], s.suffix_steps[b], 1, true, 0};
+        add_traj(jobs, pre[b]);
+        add_traj(jobs, sufL[b]);
+        add_traj(jobs, sufH[b]);
+    }
+    DQ_TRY(run_setup(p, pl, jobs, pl->rows.as<double>(), scaled));
+
+    // ---- buffers -------------------------------------------------------------------------------------
+    DQ_TRY(pl->phi.reserve((size_t)B * N * sizeof(c128)));
+    DQ_TRY(pl->work.reserve((size_t)G * N * sizeof(c128)));
+    DQ_TRY(pl->partials.reserve((size_t)B * kets_per * tiles * sizeof(double)));
+    const c128* psi0 = nullptr;
+    if (s.uniform_psi0) {
+        DQ_TRY(pl->uniform.reserve(N * sizeof(c128)));
+        DQ_TRY(gen_fill_uniform(p, pl->uniform.as<c128>(), 1));
+        psi0 = pl->uniform.as<c128>();
+    } else {
+        psi0 = s.psi0.as<c128>();
+    }
+
+    // ---- ket descriptors: B prefix kets, then per sample the shifted kets ordered by class ------------
+    const double esc_x = scaled ? 1.0 / (1.0 + s.r * s.r) : 1.0;
+    std::vector<KetDesc> kets;
+    kets.reserve((size_t)B * (kets_per + 1));
+    for (int b = 0; b < B; ++b) {
+        KetDesc k;
+        k.src = psi0;
+        k.buf = pl->phi.as<c128>() + (size_t)b * N;
+        k.steps = pl->steps.as<PassStep>() + pre[b].step0;
+        k.partial = nullptr;
+        k.sigma = 0.0;
+        k.escale = 1.0;
+        k.n_pass = pre[b].n_steps + 1;
+        k.shift_kind = -1;
+        k.sb0 = k.sb1 = 0;
+        kets.push_back(k);
+    }
+    struct Group { size_t first; int count; int max_pass; };
+    std::vector<Group> groups;
+    for (int g0 = 0; g0 < B; g0 += G) {
+        int cnt = std::min(G, B - g0), mp = 0;
+        for (int g = 0; g < cnt; ++g) mp = std::max(mp, kets[g0 + g].n_pass);
+        groups.push_back({(size_t)g0, cnt, mp});
+    }
+    for (int b = 0; b < B; ++b) {
+        for (int cls = 0; cls < 2; ++cls) {
+            std::vector<KetDesc> mine;
+            for (int i = 0; i < n_shift; ++i) {
+                int kcls = 0, b0 = 0, b1 = 0;
+                if (s.shift_kind[i] == 0) {
+                    // a ZZ shift rides on the phase tables; start with the pass type in which the pair is not J-J
+                    b0 = p->pa[s.shift_index[i]]; b1 = p->pb[s.shift_index[i]];
+                    kcls = (in_j(pl, 0, b0) && in_j(pl, 0, b1)) ? 1 : 0;
+                    if (kcls == 1 && in_j(pl, 1, b0) && in_j(pl, 1, b1)) {
+                        set_error("fused engine: ZZ shift pair (%d,%d) is J-J in both pass types", b0, b1);
+                        return DQ_ERR_UNSUPPORTED;
+                    }
+                } else {
+                    // an X shift is one more butterfly: start with the pass type that rotates that bit
+                    b0 = p->bitpos[s.shift_index[i]];
+                    kcls = b0 >= 10 ? 1 : 0;
+                }
+                if (kcls != cls) continue;
+                for (int sg = 0; sg < 2; ++sg) {
+                    KetDesc k;
+                    k.src = pl->phi.as<c128>() + (size_t)b * N;
+                    k.buf = nullptr;                // slot assigned below
+                    k.steps = pl->steps.as<PassStep>() + (cls == 0 ? sufL[b].step0 : sufH[b].step0);
+                    const size_t kidx = (size_t)b * kets_per + 2 * i + sg;
+                    k.partial = pl->partials.as<double>() + kidx * tiles;
+                    k.sigma = sg == 0 ? +1.0 : -1.0;
+                    k.escale = s.shift_kind[i] == 1 ? esc_x : 1.0;
+                    k.n_pass = s.suffix_steps[b] + 1;
+                    k.shift_kind = s.shift_kind[i];
+                    k.sb0 = b0;
+                    k.sb1 = b1;
+                    mine.push_back(k);
+                }
+            }
+            for (size_t g0 = 0; g0 < mine.size(); g0 += G) {
+                const int cnt = (int)std::min<size_t>(G, mine.size() - g0);
+                for (int g = 0; g < cnt; ++g) mine[g0 + g].buf = pl->work.as<c128>() + (size_t)g * N;
+                groups.push_back({kets.size() + g0, cnt, s.suffix_steps[b] + 1});
+            }
+            kets.insert(kets.end(), mine.begin(), mine.end());
+        }
+    }
+    std::vector<int> out_index((size_t)B * kets_per);
+    for (size_t i = 0; i < out_index.size(); ++i) out_index[i] = (int)i;
+    DQ_TRY(pl->kets.reserve(kets.size() * sizeof(KetDesc)));
+    DQ_CUDA(cudaMemcpyAsync(pl->kets.p, kets.data(), kets.size() * sizeof(KetDesc), cudaMemcpyHostToDevice, st));
+    DQ_TRY(pl->out_index.reserve(out_index.size() * sizeof(int)));
+    DQ_CUDA(cudaMemcpyAsync(pl->out_index.p, out_index.data(), out_index.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+
+    for (const Group& g : groups)
+        DQ_TRY(launch_group(p, pl, pl->kets.as<KetDesc>() + g.first, g.count, g.max_pass, scaled, s.r));
+
+    k_sum_partials<<<B * kets_per, 32, 0, st>>>(pl->partials.as<double>(), tiles, pl->out_index.as<int>(),
+                                                 p->energies.as<double>());
+    p->ctx->launches++;
+    DQ_CUDA(cudaGetLastError());
+    return DQ_OK;
+}
+
 }  // namespace dq
