@@ -16,6 +16,7 @@ struct dq_ising {
 
     int engine = 1;                // 0 generic, 1 fused (n >= 12)
     int ket_group = 4;             // states per fused launch (L2 residency)
+    int grid_per_sm = 0;           // experiment knob: CTAs per SM in the persistent grid (0 = occupancy)
 
     // work buffers
     dq::DevBuf states, phi, rows_a, rows_b, trig_a, trig_b, energies, scratch, io, shift_desc;

@@ -86,6 +86,8 @@ int dq_ising_set_option(dq_ising* p, const char* name, int64_t value) {
     if (!strcmp(name, "engine")) {
         DQ_REQUIRE(value == 0 || value == 1, "engine must be 0 (generic) or 1 (fused)");
         p->engine = (int)value;
+    } else if (!strcmp(name, "grid_per_sm")) {
+        p->grid_per_sm = (int)value;
     } else if (!strcmp(name, "ket_group")) {
         DQ_REQUIRE(value >= 1 && value <= 1024, "ket_group out of range");
         p->ket_group = (int)value;

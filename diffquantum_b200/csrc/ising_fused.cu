@@ -36,6 +36,15 @@ constexpr int kThreads = 128;              // kTile / 32
 constexpr int kRegs = 32;                  // amplitudes per thread
 constexpr int kMaxNbr = 3;                 // neighbour bits per register qubit held in tables
 constexpr int kMaxPairs = 128;
+#ifndef DQ_EXP
+#define DQ_EXP 0      // timing experiments only: 1 no FP64 math, 2 no smem exchange, 4 no global traffic
+#endif
+#ifndef DQ_TRACE
+#define DQ_TRACE 0    // 1: lane 0 of every warp records clock64() at phase boundaries of each item (debug)
+#endif
+#ifndef DQ_CTAS_PER_SM
+#define DQ_CTAS_PER_SM 2
+#endif
 
 enum : int { F_ENERGY = 2, F_STORE = 4 };
 
@@ -82,6 +91,8 @@ struct KetDesc {
     int n_pass;
     int shift_kind;                 // -1 none, 0 ZZ on (sb0, sb1), 1 X on sb0   (physical bits)
     int sb0, sb1;
+    int cls;                        // pass type of its pass 0 (0 = L first, 1 = H first)
+    int pad_;
 };
 
 struct SetupJob {
@@ -92,6 +103,7 @@ struct SetupJob {
 };
 
 struct LaunchArgs {
+    long long* trace;               // DQ_TRACE only: [item][warp][8] timestamps
     const KetDesc* kets;
     const double2* tc;
     const double* mdiag;
@@ -119,6 +131,7 @@ __device__ __forceinline__ int gather3(size_t x, const int* pos, const int* msk)
 // exp(-i theta X) on register bit B.  SCALED: rc = (1, tan) -> a' = a - i t b (cos folded elsewhere).
 template <bool SCALED, int B>
 __device__ __forceinline__ void rot_bit(c128 (&v)[kRegs], const double2 rc) {
+    if (DQ_EXP & 1) return;
 #pragma unroll
     for (int j = 0; j < kRegs; ++j) {
         if (j & (1 << B)) continue;
@@ -167,10 +180,96 @@ template <> struct Geo<1> {
     __device__ static __forceinline__ int swz(int i) { return i ^ (((i >> 7) & 1) << 2); }
 };
 
+#if DQ_TRACE
+#define TRACE(A, item, slot) do { if ((threadIdx.x & 31) == 0 && (A).trace) (A).trace[((size_t)(item) * 4 + (threadIdx.x >> 5)) * 8 + (slot)] = clock64(); } while (0)
+#else
+#define TRACE(A, item, slot) do { } while (0)
+#endif
+
+// ---- asynchronous global -> shared copies (LDGSTS) ---------------------------------------------------
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+    if (DQ_EXP & 4) return;
+    const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+// One work item = (pass p, ket g, tile t_id); written to shared memory by thread 0.
+struct ItemInfo {
+    unsigned item;
+    int p, g, t_id;
+    int valid;                      // p < n_pass of that ket
+    int ready;                      // its dependency was already satisfied when thread 0 polled
+};
+
+__device__ __forceinline__ void decode_item(const LaunchArgs& A, unsigned item, ItemInfo& I) {
+    I.item = item;
+    I.t_id = (int)(item & ((1u << A.tiles_log2) - 1u));
+    const unsigned rest = item >> A.tiles_log2;
+    I.g = (int)(rest % (unsigned)A.n_kets);
+    I.p = (int)(rest / (unsigned)A.n_kets);
+}
+
+// Each thread copies exactly the 32 amplitudes it will read back in the outer-A round, into exactly
+// the shared-memory slots it reads them from: no barrier is needed between this prefetch and outer-A.
+__device__ __forceinline__ void prefetch_tile(const LaunchArgs& A, const KetDesc* __restrict__ kd, const int type,
+                                              const int p, const int t_id, c128* __restrict__ tile) {
+    const int tid = threadIdx.x;
+    const c128* __restrict__ src = (p == 0 ? kd->src : kd->buf);
+    if (type == 0) {
+        const int iK = insert5(tid, Geo<0>::k0);
+        src += ((size_t)t_id << kTileBits) + iK;
+#pragma unroll
+        for (int j = 0; j < kRegs; ++j) cp_async16(tile + Geo<0>::swz(iK | (j << Geo<0>::k0)), src + (j << Geo<0>::k0));
+    } else {
+        const TypeGeom& T = A.geom[1];
+        const int iK = insert5(tid, Geo<1>::k0);
+        src += (((size_t)(t_id & ((1 << T.tid_lo_bits) - 1)) << T.a) | ((size_t)(t_id >> T.tid_lo_bits) << T.high_end)) +
+               ((size_t)(iK & T.lowmask) | ((size_t)(iK >> T.a) << 10));
+#pragma unroll
+        for (int j = 0; j < kRegs; ++j) cp_async16(tile + Geo<1>::swz(iK | (j << Geo<1>::k0)), src + T.offK[j]);
+    }
+}
+
+__device__ __forceinline__ void prefetch_tables(const PassStep* __restrict__ ps, PassStep* __restrict__ slot) {
+    const char* s = reinterpret_cast<const char*>(ps);
+    char* d = reinterpret_cast<char*>(slot);
+    for (int i = threadIdx.x; i < (int)(sizeof(PassStep) / 16); i += kThreads) cp_async16(d + 16 * i, s + 16 * i);
+}
+
+struct Shared {
+    ItemInfo info[2];
+    double red[2][kThreads / 32];   // energy partials of the item in slot `cur` (consumed one item later)
+};
+
+// Completion of an item is published one half-item late: thread 0 keeps the record here and releases it
+// right after the next item's mid-tile barrier, when the stores it covers were issued thousands of cycles
+// ago and the fence returns at once.  (Measured: a fence directly after the stores cost ~25% of the kernel.)
+struct Pending {
+    double* partial;                // where to write the energy partial (NULL = none)
+    double escale;
+    int g;                          // ket whose counter is bumped, -1 = nothing pending
+    int slot;                       // sh.red slot
+};
+
+__device__ __forceinline__ void flush_pending(const LaunchArgs& A, Shared& sh, Pending& pd) {
+    if (pd.g < 0) return;
+    if (pd.partial) *pd.partial = (sh.red[pd.slot][0] + sh.red[pd.slot][1] + sh.red[pd.slot][2] + sh.red[pd.slot][3]) * pd.escale;
+    asm volatile("fence.acq_rel.gpu;" ::: "memory");
+    atomicAdd(&A.counters[1 + pd.g], 1u);
+    pd.g = -1;
+}
+
+// Everything between "the tile is in shared memory" and "the tile is stored / reduced" for one pass type.
+// `nxt_raw` is the raw index of the following item (valid in thread 0 only); thread 0 turns it into
+// sh.info[nb] half-way through so that every thread can start prefetching that tile in outer-B.
 template <bool SCALED, bool AJ, int TYPE>
 __device__ __forceinline__ void process_tile(const LaunchArgs& A, const KetDesc* __restrict__ kd, const PassStep& P,
-                                             c128* __restrict__ tile, double* __restrict__ s_red, const int p,
-                                             const int t_id) {
+                                             c128* __restrict__ tile, Shared& sh, const int p, const int t_id,
+                                             const unsigned nxt_raw, const int nb, const unsigned total,
+                                             PassStep* __restrict__ cache, const PassStep* (&cached_ps)[2],
+                                             const int cb, int& next_cb, bool& next_tables_new, Pending& pd) {
     using G = Geo<TYPE>;
     const TypeGeom& T = A.geom[TYPE];
     const int tid = threadIdx.x;
@@ -210,27 +309,40 @@ __device__ __forceinline__ void process_tile(const LaunchArgs& A, const KetDesc*
     // (I + i sigma r X) = exp(-i theta X) / cos(theta) with tan(theta) = -sigma r
     const double2 shift_rc = SCALED ? make_double2(1.0, -sigma * A.r) : make_double2(A.ca, -sigma * A.sa);
 
+    // base-phase column entry: an L2 round trip, issued now and consumed after the J1 rotations
+    const c128 phi_tc = __ldg(A.tc + P.tc_offset + ((unsigned)((iJ >> G::spare_shift) & 3) | ((unsigned)t_id << 2)));
+    const unsigned trace_item = sh.info[nb ^ 1].item;
+    (void)trace_item;
+    TRACE(A, trace_item, 1);
     c128 v[kRegs];
-    // ---- outer-A : global -> registers, K-bit rotations of the previous step ----------------------
-    {
-        const c128* __restrict__ src = (p == 0 ? kd->src : kd->buf) + xK;
+    // ---- outer-A : own slots -> registers, K-bit rotations of the previous step -----------------------
 #pragma unroll
-        for (int j = 0; j < kRegs; ++j) v[j] = __ldcg(src + (TYPE == 0 ? (j << G::k0) : T.offK[j]));
-    }
+    for (int j = 0; j < kRegs; ++j) v[j] = tile[G::swz(iK | (j << G::k0))];
     rot_run<SCALED>(v, P.rot[0], ovK, shift_rc);
 #pragma unroll
-    for (int j = 0; j < kRegs; ++j) tile[G::swz(iK | (j << G::k0))] = v[j];
-    __syncthreads();
+    for (int j = 0; j < kRegs; ++j) if (!(DQ_EXP & 2)) tile[G::swz(iK | (j << G::k0))] = v[j];
+    // thread 0: the following item's dependency counter, polled now and consumed after the phase
+    unsigned polled = 0;
+    ItemInfo nI;
+    nI.valid = 0;
+    nI.ready = 0;
+    if (tid == 0) {
+        decode_item(A, nxt_raw, nI);
+        if (nxt_raw < total) {
+            nI.valid = nI.p < A.kets[nI.g].n_pass;
+            polled = nI.p > 0 ? ld_acquire(&A.counters[1 + nI.g]) : 0u;
+        }
+    }
+    TRACE(A, trace_item, 2);
+    if (TYPE == 0) __syncwarp(); else __syncthreads();    // L: the exchange never leaves the warp's 1024 amplitudes
 
     // ---- inner : J-bit rotations, phase, J-bit rotations ---------------------------------------------
 #pragma unroll
-    for (int j = 0; j < kRegs; ++j) v[j] = tile[G::swz(iJ | (j << G::j0))];
+    for (int j = 0; j < kRegs; ++j) if (!(DQ_EXP & 2)) v[j] = tile[G::swz(iJ | (j << G::j0))];
     rot_run<SCALED>(v, P.rot[1], ovJ, shift_rc);
     {
         const int kb = (iJ >> G::k0) & 31;
-        const unsigned col = (unsigned)((iJ >> G::spare_shift) & 3) | ((unsigned)t_id << 2);
-        c128 phi = __ldg(A.tc + P.tc_offset + col);
-        phi = cmul(phi, P.tkk[kb]);
+        c128 phi = cmul(phi_tc, P.tkk[kb]);
 #pragma unroll
         for (int m = 0; m < 5; ++m) {
             if (T.xk_msk[m][0]) {            // launch-uniform
@@ -258,6 +370,7 @@ __device__ __forceinline__ void process_tile(const LaunchArgs& A, const KetDesc*
                     if (k == jb) F[k] = cmul(F[k], f);
             }
         }
+        if (!(DQ_EXP & 1))
 #pragma unroll
         for (int b4 = 0; b4 < 2; ++b4) {
             const c128 p4 = b4 ? cmul(phi, F[4]) : phi;
@@ -277,37 +390,87 @@ __device__ __forceinline__ void process_tile(const LaunchArgs& A, const KetDesc*
                 }
             }
         }
-        if (AJ) {
+        if (DQ_EXP & 1) v[0] = cmul(v[0], cmul(phi, cmul(F[0], cmul(F[1], cmul(F[2], cmul(F[3], F[4]))))));
+        if (AJ && !(DQ_EXP & 1)) {
 #pragma unroll
             for (int j = 0; j < kRegs; ++j) v[j] = cmul(v[j], P.aj[j]);
         }
     }
     rot_run<SCALED>(v, P.rot[2], -1, shift_rc);
 #pragma unroll
-    for (int j = 0; j < kRegs; ++j) tile[G::swz(iJ | (j << G::j0))] = v[j];
+    for (int j = 0; j < kRegs; ++j) if (!(DQ_EXP & 2)) tile[G::swz(iJ | (j << G::j0))] = v[j];
+    if (tid == 0) {                          // publish the following item
+        nI.ready = nI.valid && (nI.p == 0 || polled >= (unsigned)nI.p << A.tiles_log2);
+        sh.info[nb] = nI;
+    }
+    TRACE(A, trace_item, 3);
     __syncthreads();
+    TRACE(A, trace_item, 4);
+    if (tid == 0) flush_pending(A, sh, pd);  // previous item: all of its stores were ordered by this barrier
 
-    // ---- outer-B : K-bit rotations of the new step, then store or reduce -----------------------------
+    // ---- outer-B : K-bit rotations of the new step; prefetch of the next tile; store or reduce --------
 #pragma unroll
-    for (int j = 0; j < kRegs; ++j) v[j] = tile[G::swz(iK | (j << G::k0))];
-    rot_run<SCALED>(v, P.rot[3], -1, shift_rc);
-    if (flags & F_ENERGY) {
+    for (int j = 0; j < kRegs; ++j) if (!(DQ_EXP & 2)) v[j] = tile[G::swz(iK | (j << G::k0))];
+    rot_bit<SCALED, 0>(v, P.rot[3][0]);      // every slot of this thread has now been consumed ...
+    {
+        const ItemInfo& N = sh.info[nb];
+        next_cb = cb;
+        next_tables_new = false;
+        if (N.ready) {                       // ... so the next tile may land in them while we finish this one
+            const KetDesc* __restrict__ nkd = A.kets + N.g;
+            const PassStep* nps = nkd->steps + N.p;
+            if (nps != cached_ps[cb]) {
+                next_cb = cb ^ 1;
+                if (nps != cached_ps[next_cb]) {
+                    prefetch_tables(nps, cache + next_cb);
+                    cached_ps[next_cb] = nps;
+                    next_tables_new = true;
+                }
+            }
+            prefetch_tile(A, nkd, (N.p + nkd->cls) & 1, N.p, N.t_id, tile);
+            cp_async_commit();
+        }
+    }
+    TRACE(A, trace_item, 5);
+    rot_bit<SCALED, 1>(v, P.rot[3][1]);
+    rot_bit<SCALED, 2>(v, P.rot[3][2]);
+    rot_bit<SCALED, 3>(v, P.rot[3][3]);
+    TRACE(A, trace_item, 6);
+    // last level pair by pair: a pair is final as soon as it is rotated, so its two stores (or its two
+    // energy terms) are issued between the FMAs of the following pairs instead of in one blocking burst
+    {
+        const double2 rc = P.rot[3][4];
+        const bool do_store = (flags & F_STORE) != 0, do_energy = (flags & F_ENERGY) != 0;
+        c128* __restrict__ dst = kd->buf + xK;
         const double* __restrict__ md = A.mdiag + xK;
         double e = 0.0;
 #pragma unroll
-        for (int j = 0; j < kRegs; ++j) {
-            const double m = __ldg(md + (TYPE == 0 ? (j << G::k0) : T.offK[j]));
-            e = fma(m, fma(v[j].x, v[j].x, v[j].y * v[j].y), e);
+        for (int j = 0; j < 16; ++j) {
+            const c128 a = v[j], b = v[j + 16];
+            c128 na, nbv;
+            if (DQ_EXP & 1) { na = a; nbv = b; }
+            else if (SCALED) {
+                na = make_double2(fma(rc.y, b.y, a.x), fma(-rc.y, b.x, a.y));
+                nbv = make_double2(fma(rc.y, a.y, b.x), fma(-rc.y, a.x, b.y));
+            } else {
+                na = make_double2(fma(rc.y, b.y, rc.x * a.x), fma(-rc.y, b.x, rc.x * a.y));
+                nbv = make_double2(fma(rc.y, a.y, rc.x * b.x), fma(-rc.y, a.x, rc.x * b.y));
+            }
+            const size_t o0 = TYPE == 0 ? (size_t)(j << G::k0) : (size_t)T.offK[j];
+            const size_t o1 = TYPE == 0 ? (size_t)((j + 16) << G::k0) : (size_t)T.offK[j + 16];
+            if (do_store) {
+                if (DQ_EXP & 4) { if (na.x == 1.2345e-300) __stcg(dst + j, na); }
+                else { __stcg(dst + o0, na); __stcg(dst + o1, nbv); }
+            }
+            if (do_energy) {
+                e = fma(__ldg(md + o0), fma(na.x, na.x, na.y * na.y), e);
+                e = fma(__ldg(md + o1), fma(nbv.x, nbv.x, nbv.y * nbv.y), e);
+            }
         }
-        for (int o = 16; o > 0; o >>= 1) e += __shfl_xor_sync(0xffffffffu, e, o);
-        if ((tid & 31) == 0) s_red[tid >> 5] = e;
-        __syncthreads();
-        if (tid == 0) kd->partial[t_id] = (s_red[0] + s_red[1] + s_red[2] + s_red[3]) * kd->escale;
-    }
-    if (flags & F_STORE) {
-        c128* __restrict__ dst = kd->buf + xK;
-#pragma unroll
-        for (int j = 0; j < kRegs; ++j) __stcg(dst + (TYPE == 0 ? (j << G::k0) : T.offK[j]), v[j]);
+        if (do_energy) {
+            for (int o = 16; o > 0; o >>= 1) e += __shfl_xor_sync(0xffffffffu, e, o);
+            if ((tid & 31) == 0) sh.red[nb ^ 1][tid >> 5] = e;
+        }
     }
 }
 
@@ -315,51 +478,104 @@ __device__ __forceinline__ void process_tile(const LaunchArgs& A, const KetDesc*
 // the persistent pass kernel
 // ------------------------------------------------------------------------------------------
 template <bool SCALED, bool AJ>
-__global__ void __launch_bounds__(kThreads, 2) k_fused_passes(const __grid_constant__ LaunchArgs A) {
+__global__ void __launch_bounds__(kThreads, DQ_CTAS_PER_SM) k_fused_passes(const __grid_constant__ LaunchArgs A) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     c128* tile = reinterpret_cast<c128*>(smem_raw);
-    PassStep* cache = reinterpret_cast<PassStep*>(smem_raw + sizeof(c128) * kTile);
-    __shared__ unsigned s_item;
-    __shared__ double s_red[kThreads / 32];
+    PassStep* cache = reinterpret_cast<PassStep*>(smem_raw + sizeof(c128) * kTile);     // two slots
+    __shared__ Shared sh;
 
     const int tid = threadIdx.x;
-    const int tiles = 1 << A.tiles_log2;
-    const unsigned total = (unsigned)A.max_pass * (unsigned)A.n_kets * (unsigned)tiles;
-    const PassStep* cached_ps = nullptr;
+    const unsigned total = ((unsigned)A.max_pass * (unsigned)A.n_kets) << A.tiles_log2;
+    const PassStep* cached_ps[2] = {nullptr, nullptr};
+    int cur = 0, cb = 0;
+    bool prefetched = false, tables_new = false;
+    Pending pd;
+    pd.g = -1;
+    pd.partial = nullptr;
+    pd.escale = 0.0;
+    pd.slot = 0;
+
+    if (tid == 0) {
+        ItemInfo I;
+        decode_item(A, atomicAdd(&A.counters[0], 1u), I);
+        I.valid = I.item < total && I.p < A.kets[I.g].n_pass;
+        I.ready = 0;
+        sh.info[0] = I;
+    }
+    __syncthreads();
 
     for (;;) {
-        __syncthreads();                       // tile, cache and s_item are free for reuse
-        if (tid == 0) s_item = atomicAdd(&A.counters[0], 1u);
-        __syncthreads();
-        const unsigned item = s_item;
-        if (item >= total) break;
-        const int t_id = (int)(item & (unsigned)(tiles - 1));
-        const unsigned rest = item >> A.tiles_log2;
-        const int g = (int)(rest % (unsigned)A.n_kets);
-        const int p = (int)(rest / (unsigned)A.n_kets);
-        const KetDesc* __restrict__ kd = A.kets + g;
-        if (p >= kd->n_pass) continue;
-        const PassStep* ps_g = kd->steps + p;
-
-        if (ps_g != cached_ps) {               // refresh the shared-memory copy of the tables
-            const int4* s4 = reinterpret_cast<const int4*>(ps_g);
-            int4* d4 = reinterpret_cast<int4*>(cache);
-            for (int i = tid; i < (int)(sizeof(PassStep) / 16); i += kThreads) d4[i] = __ldg(s4 + i);
-            cached_ps = ps_g;
+        const ItemInfo I = sh.info[cur];
+        if (I.item >= total) break;
+        if (!I.valid) {                        // ragged group: this ket has no such pass; fetch another item
+            __syncthreads();
+            if (tid == 0) {
+                flush_pending(A, sh, pd);
+                ItemInfo N;
+                decode_item(A, atomicAdd(&A.counters[0], 1u), N);
+                N.valid = N.item < total && N.p < A.kets[N.g].n_pass;
+                N.ready = 0;
+                sh.info[cur ^ 1] = N;
+            }
+            __syncthreads();
+            cur ^= 1;
+            prefetched = false;
+            continue;
         }
-        if (p > 0 && tid == 0) {               // all tiles of this ket's previous pass must be stored
-            const unsigned need = (unsigned)p * (unsigned)tiles;
-            while (ld_acquire(&A.counters[1 + g]) < need) __nanosleep(32);
+        const KetDesc* __restrict__ kd = A.kets + I.g;
+        if (!prefetched) {                     // cold path: wait for the dependency, then fetch tile and tables
+            __syncthreads();                   // previous item's stores are issued: its release may go out
+            if (tid == 0) {
+                flush_pending(A, sh, pd);      // always before spinning: the dependency may be our own tile
+                if (I.p > 0) {
+                    const unsigned need = (unsigned)I.p << A.tiles_log2;
+                    while (ld_acquire(&A.counters[1 + I.g]) < need) __nanosleep(32);
+                }
+            }
+            __syncthreads();
+            const PassStep* ps = kd->steps + I.p;
+            tables_new = false;
+            if (ps != cached_ps[cb]) {
+                cb ^= 1;
+                if (ps != cached_ps[cb]) {
+                    prefetch_tables(ps, cache + cb);
+                    cached_ps[cb] = ps;
+                    tables_new = true;
+                }
+            }
+            prefetch_tile(A, kd, (I.p + kd->cls) & 1, I.p, I.t_id, tile);
+            cp_async_commit();
         }
-        __syncthreads();
-        if (cache->type == 0) process_tile<SCALED, AJ, 0>(A, kd, *cache, tile, s_red, p, t_id);
-        else process_tile<SCALED, AJ, 1>(A, kd, *cache, tile, s_red, p, t_id);
-        __syncthreads();                         // every thread's stores are issued
-        if (tid == 0) {
-            __threadfence();
-            atomicAdd(&A.counters[1 + g], 1u);
+        unsigned nxt_raw = 0;
+        if (tid == 0) nxt_raw = atomicAdd(&A.counters[0], 1u);      // consumed inside process_tile
+        TRACE(A, I.item, 0);
+        cp_async_wait_all();                   // this thread's own slots (and its share of the tables) landed
+        if (tables_new) __syncthreads();       // tables in cache[cb] become visible to every thread
+        int next_cb = cb;
+        bool next_tables_new = false;
+        const PassStep& P = cache[cb];
+        const int flags = P.flags;
+        if (P.type == 0)
+            process_tile<SCALED, AJ, 0>(A, kd, P, tile, sh, I.p, I.t_id, nxt_raw, cur ^ 1, total, cache, cached_ps, cb,
+                                        next_cb, next_tables_new, pd);
+        else
+            process_tile<SCALED, AJ, 1>(A, kd, P, tile, sh, I.p, I.t_id, nxt_raw, cur ^ 1, total, cache, cached_ps, cb,
+                                        next_cb, next_tables_new, pd);
+        TRACE(A, I.item, 7);
+        if (tid == 0) {                        // published after the next item's mid-tile barrier
+            pd.g = I.g;
+            pd.partial = (flags & F_ENERGY) ? kd->partial + I.t_id : nullptr;
+            pd.escale = kd->escale;
+            pd.slot = cur;
         }
+        prefetched = sh.info[cur ^ 1].ready != 0;
+        cur ^= 1;
+        cb = next_cb;
+        tables_new = next_tables_new;
     }
+    cp_async_wait_all();
+    __syncthreads();
+    if (tid == 0) flush_pending(A, sh, pd);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -484,7 +700,8 @@ struct Plan {
     bool has_aj = false;
     TypePlan types[2];
     int jphys[2][5];
-    DevBuf d_types, jobs, steps, tc, kets, counters, partials, out_index, work, rows, phi, uniform;
+    DevBuf d_types, jobs, steps, tc, kets, counters, partials, out_index, work, rows, phi, uniform, trace;
+    long long trace_items = 0;
     size_t smem_bytes = 0;
     int ctas_per_sm = 0;
     int counter_slots = 0, counter_cursor = 0;
@@ -597,7 +814,7 @@ static Plan* get_plan(dq_ising* p) {
     pl->has_aj = pl->types[0].has_aj || pl->types[1].has_aj;
     pl->n_col_bits = p->n - 10;
     pl->tiles_log2 = p->n - kTileBits;
-    pl->smem_bytes = sizeof(c128) * kTile + sizeof(PassStep);
+    pl->smem_bytes = sizeof(c128) * kTile + 2 * sizeof(PassStep);
     if (pl->d_types.reserve(sizeof(TypePlan) * 2) != DQ_OK) return pl;
     if (cudaMemcpy(pl->d_types.p, pl->types, sizeof(TypePlan) * 2, cudaMemcpyHostToDevice) != cudaSuccess) return pl;
     int occ = 0, o2 = 0;
@@ -649,6 +866,8 @@ static int run_setup(dq_ising* p, Plan* pl, const std::vector<SetupJob>& jobs, c
     return DQ_OK;
 }
 
+static long long all_items_for_trace(int n_kets, int tiles_log2, int max_pass) { return ((long long)n_kets << tiles_log2) * max_pass; }
+
 static int launch_group(dq_ising* p, Plan* pl, const KetDesc* d_kets, int n_kets, int max_pass, bool scaled, double r) {
     cudaStream_t st = p->ctx->stream;
     if (pl->counter_cursor + 1 + n_kets > pl->counter_slots) pl->counter_cursor = 0;
@@ -656,6 +875,13 @@ static int launch_group(dq_ising* p, Plan* pl, const KetDesc* d_kets, int n_kets
     pl->counter_cursor += 1 + n_kets;
     DQ_CUDA(cudaMemsetAsync(ctr, 0, (1 + n_kets) * sizeof(unsigned), st));
     LaunchArgs A;
+    A.trace = nullptr;
+#if DQ_TRACE
+    {
+        const size_t need = (size_t)all_items_for_trace(n_kets, pl->tiles_log2, max_pass) * 32 * sizeof(long long);
+        if (pl->trace.reserve(need) == DQ_OK) { cudaMemsetAsync(pl->trace.p, 0, need, st); A.trace = pl->trace.as<long long>(); pl->trace_items = all_items_for_trace(n_kets, pl->tiles_log2, max_pass); }
+    }
+#endif
     A.kets = d_kets;
     A.tc = pl->tc.as<double2>();
     A.mdiag = p->mdiag.as<double>();
@@ -668,7 +894,7 @@ static int launch_group(dq_ising* p, Plan* pl, const KetDesc* d_kets, int n_kets
     A.geom[0] = pl->types[0].g;
     A.geom[1] = pl->types[1].g;
     const long long all_items = ((long long)n_kets << pl->tiles_log2) * max_pass;
-    long long grid = (long long)p->ctx->prop.multiProcessorCount * pl->ctas_per_sm;
+    long long grid = (long long)p->ctx->prop.multiProcessorCount * (p->grid_per_sm > 0 ? std::min(p->grid_per_sm, pl->ctas_per_sm) : pl->ctas_per_sm);
     if (grid > all_items) grid = all_items;
     if (scaled) {
         if (pl->has_aj) k_fused_passes<true, true><<<(unsigned)grid, kThreads, pl->smem_bytes, st>>>(A);
@@ -696,6 +922,16 @@ static bool in_j(const Plan* pl, int type, int pos) {
 }
 
 }  // namespace fused
+
+// debug: copy the last launch's phase timestamps to the host (DQ_TRACE builds only)
+extern "C" long long dq_debug_trace(dq_ising* p, long long* out, long long max_items) {
+    fused::Plan* pl = fused::find_plan(p);
+    if (!pl || !pl->trace.p) return 0;
+    cudaStreamSynchronize(p->ctx->stream);
+    long long n = std::min(max_items, pl->trace_items);
+    cudaMemcpy(out, pl->trace.p, (size_t)n * 32 * sizeof(long long), cudaMemcpyDeviceToHost);
+    return n;
+}
 
 int fused_supported(const dq_ising* p) {
     fused::Plan* pl = fused::get_plan(const_cast<dq_ising*>(p));
@@ -745,6 +981,8 @@ int fused_evolve(dq_ising* p, c128* d_states, int batch, const double* h_rows, i
         k.n_pass = n_steps + 1;
         k.shift_kind = -1;
         k.sb0 = k.sb1 = 0;
+        k.cls = 0;
+        k.pad_ = 0;
     }
     DQ_TRY(pl->kets.reserve(kets.size() * sizeof(KetDesc)));
     DQ_CUDA(cudaMemcpyAsync(pl->kets.p, kets.data(), kets.size() * sizeof(KetDesc), cudaMemcpyHostToDevice, st));
@@ -825,6 +1063,8 @@ int fused_grad_run(dq_ising* p) {
         k.n_pass = pre[b].n_steps + 1;
         k.shift_kind = -1;
         k.sb0 = k.sb1 = 0;
+        k.cls = 0;
+        k.pad_ = 0;
         kets.push_back(k);
     }
     struct Group { size_t first; int count; int max_pass; };
@@ -866,6 +1106,8 @@ int fused_grad_run(dq_ising* p) {
                     k.shift_kind = s.shift_kind[i];
                     k.sb0 = b0;
                     k.sb1 = b1;
+                    k.cls = cls;
+                    k.pad_ = 0;
                     mine.push_back(k);
                 }
             }
