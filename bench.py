@@ -1,0 +1,386 @@
+#!/usr/bin/env python
+"""bench.py — gradient samples/s of the stochastic parameter-shift estimator at n=20 MaxCut
+(BASELINE.json configs[3]: random 3-regular MaxCut, n=20, per_step=10 as shipped, T=2, B-spline
+basis with 6 coefficients per control, 50 controls -> 1 + 100 trajectories per sample).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]            our arm (CUDA, sm_100a)
+  python bench.py --impl reference [...]                          reference arm (CPU, host cores)
+
+A "step" is one batch of --samples-per-step gradient samples PER GPU (weak scaling): the sample
+times of step i are the reference's own stream, np.random.seed(i); np.random.uniform(size=B*N)*T
+(sim_plain.py:167), split contiguously over the N ranks.  No rank talks to another until the
+[n_Hs, n_basis] gradient sum is all-reduced once per step (NCCL).
+
+value  : samples/s with the angle tables already staged in HBM; device time from CUDA events on the
+         library's stream, summed over the K steps, max over ranks; L2 flushed between steps.
+e2e    : the same K steps through the public API (IsingSimulator.grad_samples + the sharded
+         reduce) with host buffers: host pulse-table evaluation, H2D of the tables, kernels, D2H of
+         the shifted energies, gradient assembly and the all-reduce are all inside the timed region.
+roofline: the fused pass kernel (k_fused_passes), algorithmic bytes = trajectory-steps x 2 x 16 B x 2^n
+         per launch over its CUDA-event-timed launch durations in the same timed region.
+cpu_baseline / --impl reference: the reference's step (diffqc.cc:155-164) and estimator
+         (sim_plain.py:186-230) as the plain-C OpenMP port in oracle/c on all host cores, on a bounded
+         sample (the reference's own dense code cannot represent n=20: SURVEY F3).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "gradient samples/s at n=20 MaxCut"
+UNIT = "samples/s"
+FALLBACK_HBM_GBS = 6650.0          # /opt/skills/guides/B200_PROFILING.md, used only without MEASURED_PEAKS.json
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--n", type=int, default=20)
+    ap.add_argument("--per-step", type=int, default=10)
+    ap.add_argument("--samples-per-step", type=int, default=8, help="gradient samples per GPU per step")
+    ap.add_argument("--cpu-terms", type=int, default=6,
+                    help="controls whose +/- trajectories the bounded CPU sample runs (of n_Hs)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ket-group", type=int, default=0)
+    return ap.parse_args()
+
+
+# ---------------------------------------------------------------------------------------------
+# workload
+# ---------------------------------------------------------------------------------------------
+def workload(n):
+    import networkx as nx
+    g = nx.random_regular_graph(3, n, seed=0)
+    edges = sorted(tuple(sorted(e)) for e in g.edges())
+    n_H = len(edges) + n
+    coeff = np.random.default_rng(0).normal(0, 1, [n_H, 6])
+    return edges, coeff
+
+
+def step_samples(step, per_gpu, world, T):
+    np.random.seed(step)
+    return np.random.uniform(size=per_gpu * world) * T
+
+
+def steps_of_sample(s, T, per_step, n_H):
+    return int(per_step * (s + 1)), int(per_step * (T - s + 1)), \
+        int(per_step * (s + 1)) + 2 * n_H * int(per_step * (T - s + 1))
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(p):
+        try:
+            d = json.load(open(p))
+            for k in ("hbm_gbs", "hbm_copy_gbs", "hbm_GBs"):
+                if k in d:
+                    return float(d[k]), "measured (MEASURED_PEAKS.json %s)" % k
+        except Exception:
+            pass
+    return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md, MEASURED_PEAKS.json absent)"
+
+
+class ClockSampler(object):
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            pass
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+            out, _ = self.proc.communicate()
+        sm, mx, pw, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in out.strip().splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1])); pw.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        busy = [c for c, p in zip(sm, pw) if p > 0.5 * max(pw)] or sm      # samples taken under load
+        return {"sm_mhz": float(np.median(busy)), "sm_max_mhz": float(max(mx)), "power_w_max": float(max(pw)),
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ---------------------------------------------------------------------------------------------
+# CPU arm: plain-C OpenMP port of the reference step + estimator (oracle/c), bounded sample
+# ---------------------------------------------------------------------------------------------
+def cpu_bounded_sample(n, per_step, coeff, edges, s, n_terms):
+    from oracle import c_port as C, restate as R
+    if not C.available():
+        raise RuntimeError("oracle/c/liboracle_c.so missing: run __graft_entry__.build()")
+    prob = R.maxcut_structured(n, edges)
+    cp = C.CProblem(prob)
+    n_H = len(prob["terms"])
+    # one ZZ control and one X control first, then alternate, so the sample sees both gate kinds
+    order = []
+    zz = [i for i, t in enumerate(prob["terms"]) if t[0] == "zz"]
+    xx = [i for i, t in enumerate(prob["terms"]) if t[0] == "x"]
+    while len(order) < n_terms and (zz or xx):
+        if zz:
+            order.append(zz.pop(0))
+        if xx and len(order) < n_terms:
+            order.append(xx.pop(0))
+    t0 = time.perf_counter()
+    _, _, steps = C.grad_mc(cp, coeff, float(s), per_step, terms=order, return_energies=True)
+    dt = time.perf_counter() - t0
+    full = steps_of_sample(s, prob["T"], per_step, n_H)[2]
+    return dict(seconds=dt, steps=steps, full_steps=full, samples_per_s=(steps / dt) / full,
+                cores=C.num_threads(), n_terms=len(order), n_H=n_H)
+
+
+def run_reference_arm(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    edges, coeff = workload(a.n)
+    T = 2.0
+    vals, last = [], None
+    for i in range(a.warmup + a.steps):
+        # warm-up steps use a reduced sample (page-in, OpenMP pool start-up); timed ones the bounded sample
+        s = step_samples(i, a.samples_per_step, 1, T)[0]
+        r = cpu_bounded_sample(a.n, a.per_step, coeff, edges, s, 1 if i < a.warmup else a.cpu_terms)
+        if i >= a.warmup:
+            vals.append(r)
+            last = r
+    tot_steps = sum(r["steps"] for r in vals)
+    tot_sec = sum(r["seconds"] for r in vals)
+    mean_full = float(np.mean([r["full_steps"] for r in vals]))
+    v = (tot_steps / tot_sec) / mean_full
+    sample = ("per step: 1 prefix + the +/- trajectories of %d of %d controls of one sample (%d of ~%d "
+              "trajectory-steps), scaled by steps" % (last["n_terms"], last["n_H"], last["steps"], last["full_steps"]))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
+        "warmup": a.warmup, "ms_per_step": 1e3 * tot_sec / a.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(a, 1),
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": last["cores"], "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+        "note": "reference's own dense code cannot build n=20 operators (SURVEY F3); this is the plain-C OpenMP port "
+                "of its per-term product step (diffqc.cc:155-164) and estimator (sim_plain.py:186-230)",
+    }
+    print(json.dumps(line))
+    return 0
+
+
+def workload_config(a, world):
+    return {"workload": "configs[3]: random 3-regular MaxCut n=%d (networkx seed 0), per_step=%d, T=2.0, "
+                        "n_basis=6 BSpline, 1+2*n_Hs trajectories per sample" % (a.n, a.per_step),
+            "samples_per_step_per_gpu": a.samples_per_step, "global_samples_per_step": a.samples_per_step * world,
+            "parallelism": "sample-sharded x%d, one all-reduce of the gradient per step" % world,
+            "l2": "L2 flushed (512 MiB write) between timed steps"}
+
+
+# ---------------------------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------------------------
+def run_b200_arm(a):
+    import torch
+    import diffquantum_b200 as dq
+    from diffquantum_b200 import sharding
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py: no CUDA device (there is no CPU fallback; use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+
+    def barrier():
+        if world > 1:
+            import torch.distributed as dist
+            dist.barrier(device_ids=[local])
+        torch.cuda.synchronize(dev)
+
+    def max_over_ranks(x):
+        if world == 1:
+            return float(x)
+        import torch.distributed as dist
+        t = torch.tensor([float(x)], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(x):
+        if world == 1:
+            return float(x)
+        import torch.distributed as dist
+        t = torch.tensor([float(x)], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    edges, coeff = workload(a.n)
+    prob = dq.IsingProblem.maxcut(a.n, edges)
+    sim = dq.IsingSimulator(prob, device=local, per_step=a.per_step, engine=1)
+    if a.ket_group:
+        sim.set_option("ket_group", a.ket_group)
+    if sim.info("engine") != 1:
+        raise RuntimeError("fused engine not available for n=%d" % a.n)
+    n_H = len(prob.terms)
+    stream = torch.cuda.ExternalStream(sim.ctx.stream, device=dev)
+    flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
+    est = sharding.ShardedEstimator(lambda c, s: sim.grad_samples(c, s), device=dev)
+
+    def my_samples(i):
+        return sharding.shard(step_samples(i, a.samples_per_step, world, prob.T), rank, world)
+
+    # ---- value: tables staged in HBM, device-timed ----------------------------------------------
+    sim.set_option("time_launches", 1)
+    dev_ms, alg_bytes, traj_steps, kern_ms, kern_launches = [], 0.0, 0.0, 0.0, 0.0
+    clocks = None
+    launches0 = None
+    for i in range(a.warmup + a.steps):
+        timed = i >= a.warmup
+        if i == a.warmup:
+            barrier()
+            clocks = ClockSampler(local)
+            launches0 = sim.ctx.launch_count
+        sim.stage(coeff, my_samples(i))              # H2D of the angle tables: outside the timed region
+        flush.zero_()
+        torch.cuda.synchronize(dev)
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1 = torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        sim.run_staged()
+        e1.record(stream)
+        e1.synchronize()
+        en = sim.fetch()
+        if timed:
+            dev_ms.append(e0.elapsed_time(e1))
+            alg_bytes += sim.stat("alg_bytes")
+            traj_steps += sim.stat("steps")
+            kern_ms += sim.stat("pass_kernel_ms")
+            kern_launches += sim.stat("pass_kernel_launches")
+    barrier()
+    gpu_launches = sim.ctx.launch_count - launches0
+    clk = clocks.stop()
+    t_value = max_over_ranks(sum(dev_ms) * 1e-3)
+    total_samples = a.samples_per_step * world * a.steps
+    value = total_samples / t_value
+    sim.set_option("time_launches", 0)
+    last_energies = en
+
+    # ---- e2e: public API, host buffers, reduce included ----------------------------------------------
+    h2d = d2h = 0
+    e2e_s = []
+    for i in range(a.warmup + a.steps):
+        timed = i >= a.warmup
+        s_all = step_samples(i, a.samples_per_step, world, prob.T)
+        flush.zero_()
+        barrier()
+        t0 = time.perf_counter()
+        gmean = est.mean_gradient(coeff, s_all)
+        torch.cuda.synchronize(dev)
+        dt = time.perf_counter() - t0
+        if timed:
+            e2e_s.append(dt)
+            tabs = sim.sample_tables(coeff, sharding.shard(s_all, rank, world))     # recount the bytes copied
+            h2d = sum(t.nbytes for t in tabs) + prob.term_kind.nbytes + prob.term_index.nbytes
+            d2h = len(sharding.shard(s_all, rank, world)) * n_H * 2 * 8
+    t_e2e = max_over_ranks(sum(e2e_s))
+    e2e_value = total_samples / t_e2e
+    assert np.all(np.isfinite(gmean)) and np.all(np.isfinite(last_energies))
+
+    # ---- roofline of the dominant kernel ---------------------------------------------------------
+    peak, peak_src = measured_peak()
+    achieved = alg_bytes / (kern_ms * 1e-3) / 1e9 if kern_ms > 0 else None
+    traffic = None
+    tnote = None
+    tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    if os.path.isfile(tp) and kern_launches:
+        try:
+            tj = json.load(open(tp))
+            ratio = float(tj["dram_bytes_per_launch"]) / float(tj["alg_bytes_per_launch"])
+            traffic = ratio * alg_bytes / kern_launches
+            tnote = "ncu dram bytes / algorithmic bytes = %.3f for %s (%s), applied to this run's bytes per launch" % (
+                ratio, tj.get("kernel", "k_fused_passes"), tj.get("source", "profiles/"))
+        except Exception:
+            traffic = None
+    roofline = {"bound": "hbm", "kernel": "k_fused_passes", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": (achieved / peak) if achieved else None, "peak_source": peak_src, "traffic": traffic,
+                "traffic_note": tnote,
+                "alg_bytes_per_launch": alg_bytes / kern_launches if kern_launches else None,
+                "avg_launch_ms": kern_ms / kern_launches if kern_launches else None,
+                "launches_timed": kern_launches, "kernel_share_of_step": kern_ms / sum(dev_ms) if dev_ms else None,
+                "note": "kets of a launch group stay in the 126 MB L2 between passes by design, so algorithmic GB/s can "
+                        "exceed DRAM GB/s; `traffic` is the ncu DRAM figure"}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+        "ms_per_step": 1e3 * t_value / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic", "config": workload_config(a, world),
+        "trajectory_steps_per_s": sum_over_ranks(traj_steps) / t_value,
+        "alg_GBs_whole_job": sum_over_ranks(alg_bytes) / t_value / 1e9,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                "ms_per_step": 1e3 * t_e2e / a.steps,
+                "note": "host pulse tables + H2D (cudaMemcpyAsync from the caller's numpy buffers) + kernels + D2H "
+                        "energies + gradient assembly + all-reduce"},
+        "gpu_launches": int(gpu_launches), "roofline": roofline, "clocks": clk,
+    }
+    if rank == 0 and world == 1 and not a.no_cpu_baseline:
+        try:
+            s0 = step_samples(a.warmup, a.samples_per_step, 1, prob.T)[0]
+            cpu_bounded_sample(a.n, a.per_step, coeff, edges, s0, 1)            # warm the OpenMP pool / page in
+            r = cpu_bounded_sample(a.n, a.per_step, coeff, edges, s0, a.cpu_terms)
+            line["cpu_baseline"] = {
+                "value": r["samples_per_s"], "unit": UNIT, "cores": r["cores"], "kind": "port",
+                "sample": "1 prefix + the +/- trajectories of %d of %d controls of one sample at s=%.4f (%d of %d "
+                          "trajectory-steps, %.1f s), scaled by steps" % (r["n_terms"], r["n_H"], s0, r["steps"],
+                                                                         r["full_steps"], r["seconds"])}
+        except Exception as e:            # the baseline is a report, never a reason to lose the GPU number
+            line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": "failed: %s" % e}
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        import torch.distributed as dist
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    a = parse_args()
+    if a.impl == "reference":
+        return run_reference_arm(a)
+    return run_b200_arm(a)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

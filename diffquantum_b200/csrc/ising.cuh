@@ -17,6 +17,7 @@ struct dq_ising {
     int engine = 1;                // 0 generic, 1 fused (n >= 12)
     int ket_group = 4;             // states per fused launch (L2 residency)
     int grid_per_sm = 0;           // experiment knob: CTAs per SM in the persistent grid (0 = occupancy)
+    int time_launches = 0;         // 1: CUDA-event pairs around every pass-kernel launch (bench.py's roofline)
 
     // work buffers
     dq::DevBuf states, phi, rows_a, rows_b, trig_a, trig_b, energies, scratch, io, shift_desc;
@@ -56,6 +57,7 @@ int gen_build_mdiag(dq_ising* p, const double* m_zz, double m_const);
 // fused persistent engine (n >= 12)
 int fused_supported(const dq_ising* p);
 void fused_release(dq_ising* p);
+int fused_launch_times(dq_ising* p, double* total_ms, double* n_launches);
 int fused_grad_run(dq_ising* p);
 int fused_evolve(dq_ising* p, c128* d_states, int batch, const double* h_rows, int n_steps,
                  double* d_energies, bool want_states);

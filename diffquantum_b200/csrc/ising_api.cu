@@ -88,6 +88,8 @@ int dq_ising_set_option(dq_ising* p, const char* name, int64_t value) {
         p->engine = (int)value;
     } else if (!strcmp(name, "grid_per_sm")) {
         p->grid_per_sm = (int)value;
+    } else if (!strcmp(name, "time_launches")) {
+        p->time_launches = value != 0;
     } else if (!strcmp(name, "ket_group")) {
         DQ_REQUIRE(value >= 1 && value <= 1024, "ket_group out of range");
         p->ket_group = (int)value;
@@ -113,6 +115,11 @@ int dq_ising_last_stat(dq_ising* p, const char* name, double* value) {
     if (!strcmp(name, "steps")) *value = p->stat_steps;
     else if (!strcmp(name, "launches")) *value = p->stat_launches;
     else if (!strcmp(name, "alg_bytes")) *value = p->stat_alg_bytes;
+    else if (!strcmp(name, "pass_kernel_ms") || !strcmp(name, "pass_kernel_launches")) {
+        double ms = 0, nl = 0;
+        DQ_TRY(dq::fused_launch_times(p, &ms, &nl));
+        *value = !strcmp(name, "pass_kernel_ms") ? ms : nl;
+    }
     else { dq::set_error("dq_ising_last_stat: unknown name '%s'", name); return DQ_ERR_INVALID; }
     return DQ_OK;
 }

@@ -705,6 +705,8 @@ struct Plan {
     size_t smem_bytes = 0;
     int ctas_per_sm = 0;
     int counter_slots = 0, counter_cursor = 0;
+    std::vector<cudaEvent_t> ev;    // option time_launches: event pairs around every pass-kernel launch of the last run
+    int ev_used = 0;
 };
 
 static std::vector<std::pair<dq_ising*, Plan*>> g_plans;     // one plan per problem
@@ -896,6 +898,15 @@ static int launch_group(dq_ising* p, Plan* pl, const KetDesc* d_kets, int n_kets
     const long long all_items = ((long long)n_kets << pl->tiles_log2) * max_pass;
     long long grid = (long long)p->ctx->prop.multiProcessorCount * (p->grid_per_sm > 0 ? std::min(p->grid_per_sm, pl->ctas_per_sm) : pl->ctas_per_sm);
     if (grid > all_items) grid = all_items;
+    const bool timed = p->time_launches != 0;
+    if (timed) {
+        while ((int)pl->ev.size() < pl->ev_used + 2) {
+            cudaEvent_t e;
+            DQ_CUDA(cudaEventCreate(&e));
+            pl->ev.push_back(e);
+        }
+        DQ_CUDA(cudaEventRecord(pl->ev[pl->ev_used], st));
+    }
     if (scaled) {
         if (pl->has_aj) k_fused_passes<true, true><<<(unsigned)grid, kThreads, pl->smem_bytes, st>>>(A);
         else k_fused_passes<true, false><<<(unsigned)grid, kThreads, pl->smem_bytes, st>>>(A);
@@ -904,6 +915,10 @@ static int launch_group(dq_ising* p, Plan* pl, const KetDesc* d_kets, int n_kets
         else k_fused_passes<false, false><<<(unsigned)grid, kThreads, pl->smem_bytes, st>>>(A);
     }
     p->ctx->launches++;
+    if (timed) {
+        DQ_CUDA(cudaEventRecord(pl->ev[pl->ev_used + 1], st));
+        pl->ev_used += 2;
+    }
     DQ_CUDA(cudaGetLastError());
     return DQ_OK;
 }
@@ -933,6 +948,22 @@ extern "C" long long dq_debug_trace(dq_ising* p, long long* out, long long max_i
     return n;
 }
 
+// Sum of the event-timed durations of the pass-kernel launches of the last run (option time_launches).
+int fused_launch_times(dq_ising* p, double* total_ms, double* n_launches) {
+    fused::Plan* pl = fused::find_plan(p);
+    *total_ms = 0.0;
+    *n_launches = 0.0;
+    if (!pl || pl->ev_used == 0) return DQ_OK;
+    DQ_CUDA(cudaStreamSynchronize(p->ctx->stream));
+    for (int i = 0; i + 1 < pl->ev_used; i += 2) {
+        float ms = 0.f;
+        DQ_CUDA(cudaEventElapsedTime(&ms, pl->ev[i], pl->ev[i + 1]));
+        *total_ms += ms;
+        *n_launches += 1.0;
+    }
+    return DQ_OK;
+}
+
 int fused_supported(const dq_ising* p) {
     fused::Plan* pl = fused::get_plan(const_cast<dq_ising*>(p));
     return pl->ok ? 1 : 0;
@@ -945,6 +976,7 @@ void fused_release(dq_ising* p) {
             DevBuf* bufs[] = {&pl->d_types, &pl->jobs, &pl->steps, &pl->tc, &pl->kets, &pl->counters, &pl->partials,
                               &pl->out_index, &pl->work, &pl->rows, &pl->phi, &pl->uniform};
             for (auto* b : bufs) b->release();
+            for (cudaEvent_t e : pl->ev) cudaEventDestroy(e);
             delete pl;
             fused::g_plans.erase(fused::g_plans.begin() + i);
             return;
@@ -957,6 +989,7 @@ int fused_evolve(dq_ising* p, c128* d_states, int batch, const double* h_rows, i
     using namespace fused;
     Plan* pl = get_plan(p);
     DQ_REQUIRE(pl->ok, "fused engine unavailable for this problem");
+    pl->ev_used = 0;
     cudaStream_t st = p->ctx->stream;
     const bool scaled = rows_allow_scaled(p, h_rows, n_steps, 0.0);
     const size_t N = p->dim();
@@ -1010,6 +1043,7 @@ int fused_grad_run(dq_ising* p) {
     using namespace fused;
     Plan* pl = get_plan(p);
     DQ_REQUIRE(pl->ok, "fused engine unavailable for this problem");
+    pl->ev_used = 0;
     auto& s = p->st;
     cudaStream_t st = p->ctx->stream;
     const size_t N = p->dim();

@@ -98,7 +98,8 @@ int dq_ising_create(dq_context* ctx, int n_qubits, int n_zz, const int32_t* zz_p
                     const double* m_diag /*[2^n] host, overrides m_zz when not NULL*/,
                     dq_ising** out);
 int dq_ising_destroy(dq_ising* p);
-/* Tunables: "ket_group" (states co-resident in L2 per launch), "engine" (0 generic, 1 fused). */
+/* Tunables: "ket_group" (states co-resident in L2 per launch), "engine" (0 generic, 1 fused),
+ * "time_launches" (1: bracket every pass-kernel launch with CUDA events, read back via dq_ising_last_stat). */
 int dq_ising_set_option(dq_ising* p, const char* name, int64_t value);
 int dq_ising_get_info(dq_ising* p, const char* name, int64_t* value);
 
@@ -130,7 +131,8 @@ int dq_ising_grad_stage(dq_ising* p, int n_samples, const int32_t* prefix_steps,
 int dq_ising_grad_run_staged(dq_ising* p);                      /* asynchronous on the ctx stream */
 int dq_ising_grad_fetch(dq_ising* p, double* energies_out);     /* synchronises, copies D2H */
 
-/* Counters of the last run: "steps" (trajectory-steps executed), "launches", "alg_bytes". */
+/* Counters of the last run: "steps" (trajectory-steps executed), "launches", "alg_bytes",
+ * "pass_kernel_ms" / "pass_kernel_launches" (event-timed fused pass kernel; needs time_launches=1). */
 int dq_ising_last_stat(dq_ising* p, const char* name, double* value);
 
 /* ---- micro-benchmarks used by bench.py/profiles to calibrate the roofline --------------------- */
