@@ -25,7 +25,12 @@ for k, v in sorted(st, key=lambda kv: -kv[1])[:12]:
     print("  %-24s %.3f" % (k, v))
 src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(src)))
-hdr = rows[1]; ix = {h: i for i, h in enumerate(hdr)}; data = rows[2:]
+hdr = rows[1]; ix = {h: i for i, h in enumerate(hdr)}
+data = []
+for x in rows[2:]:
+    if len(x) < len(hdr) or x[0] == 'Address':      # next kernel's block starts
+        break
+    data.append(x)
 nlaunch = 1
 tot = sum(int(x[ix["# Samples"]]) for x in data)
 c = Counter()
