@@ -7,5 +7,7 @@ library and a B200 raises."""
 from . import pulses  # noqa: F401
 from ._lib import Context, DiffqcError, load  # noqa: F401
 from .ising import IsingProblem, IsingSimulator  # noqa: F401
+from .dense import DenseSimulator, dense_evolve, estimator_for, solver_for  # noqa: F401
+from . import diffqc, sharding  # noqa: F401
 
 __version__ = "dev"

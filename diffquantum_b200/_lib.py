@@ -7,7 +7,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libdiffqc_b200.so")
+LIB_PATH = os.environ.get("DIFFQC_B200_LIB") or os.path.join(_HERE, "libdiffqc_b200.so")   # override: kernel experiments
 
 c_double_p = ctypes.POINTER(ctypes.c_double)
 c_int32_p = ctypes.POINTER(ctypes.c_int32)
@@ -31,6 +31,8 @@ SIGNATURES = {
                                        ctypes.c_double, ctypes.c_int, ctypes.c_int, _VP, _VP]),
     "dq_dense_grad": (ctypes.c_int, [_VP, ctypes.c_int, _VP, ctypes.c_int, _VP, _VP, _VP, ctypes.c_double,
                                      ctypes.c_int, _VP, _VP, _VP, _VP, _VP, _VP, ctypes.c_int, _VP]),
+    "dq_dense_last_stat": (ctypes.c_int, [_VP, ctypes.c_char_p, ctypes.POINTER(ctypes.c_double)]),
+    "dq_dense_set_option": (ctypes.c_int, [_VP, ctypes.c_char_p, ctypes.c_int64]),
     "dq_ising_create": (ctypes.c_int, [_VP, ctypes.c_int, ctypes.c_int, _VP, _VP, ctypes.c_double, _VP,
                                        ctypes.POINTER(_VP)]),
     "dq_ising_destroy": (ctypes.c_int, [_VP]),

@@ -1,6 +1,7 @@
 // Context, error reporting and calibration micro-benchmarks.
 #include <stdarg.h>
 #include "common.cuh"
+#include "dense.cuh"
 
 namespace dq {
 static thread_local char g_err[1024] = "";
@@ -58,6 +59,8 @@ int dq_context_create(int device, dq_context** out) {
 int dq_context_destroy(dq_context* ctx) {
     if (!ctx) return DQ_OK;
     cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    dq::dense::release(ctx);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
     return DQ_OK;

@@ -1,0 +1,60 @@
+// Dense path (n <= 10 qubits, dim <= 1024): live `exact` step semantics of the reference,
+//   psi <- expm(-i dt (H0 + sum_h u_h(t_k) H_h)) psi      (sim_plain.py:135-150, diffqc.cc:190-200)
+// and the disabled per-term product (diffqc.cc:155-164) as mode 1.
+//
+// Device layout: every complex matrix / ket block is PLANAR float64 — a real plane followed by an
+// imaginary plane — row-major with leading dimension Dp (dim padded to a multiple of 8) or Ncp
+// (ket count padded to a multiple of 8).  Planar is what the FP64 tensor-core fragments want:
+// a complex product is four real DMMA (mma.sync.m8n8k4.f64) accumulations.
+#pragma once
+#include <array>
+#include "common.cuh"
+
+namespace dq {
+namespace dense {
+
+struct Problem {
+    int dim = 0, Dp = 0, n_H = 0;
+    DevBuf H;                          // [(1 + n_H)][2][Dp*Dp]
+    DevBuf M;                          // [2][Dp*Dp] observable (gradient entry point only)
+    std::vector<double> norm1;         // induced 1-norms of H0, H_1..H_nH (scaling choice)
+    std::vector<double> host_copy;     // last uploaded H0|Hs (interleaved c128), to skip identical uploads
+    // diffqc.set_H pulse model (diffqc.cc:21-25 globals)
+    std::vector<std::vector<std::array<double, 4>>> channels;
+    double duration = 1.0;
+    int func_type = 0;
+    bool is_set = false;
+    size_t plane() const { return (size_t)Dp * Dp; }
+};
+
+struct State {                         // per context
+    Problem global_H;                  // what dq_dense_set_H stored
+    Problem scratch_H;                 // what dq_dense_evolve / dq_dense_grad were last called with
+    DevBuf A, P0, P1, U, K0, K1, K2, u_dev, meta, phi, out;
+    double last_gemm_flops = 0;        // real flops issued to the DMMA GEMM in the last call
+    int last_strategy = 0;             // 0 block-Taylor, 1 per-step propagator, 2 chained propagator
+    int last_squarings = 0, last_degree = 0;
+};
+
+struct Gemm {                          // C[z] = alpha * A[z] B[z] (+ Add[z]) (+ I),  z < batch
+    const double* A; long long strideA, planeA; int lda;
+    const double* B; long long strideB, planeB; int ldb;
+    double* C; long long strideC, planeC; int ldc;
+    const double* Add;                 // same geometry as C, may be NULL
+    int M, N, K, batch;
+    double alpha;
+    int add_identity;
+};
+
+int zgemm(dq_context* ctx, const Gemm& g);
+int build_generator(dq_context* ctx, const Problem& P, int nb, const double* d_u, const long long* d_rows,
+                    const double* d_scale, int k, int term, double* d_A, double* d_P, double inv_m);
+int gather_blocks(dq_context* ctx, const double* src, double* dst, const int* d_order, int nb, size_t block_doubles,
+                  int scatter);
+int fanout(dq_context* ctx, const Problem& P, int B, const double* d_phi, int ncp_phi, double* d_K, int ncp, double r);
+int energies(dq_context* ctx, const Problem& P, int B, const double* d_K, int ncp, int n_cols, double* d_out);
+State* state_of(dq_context* ctx);
+void release(dq_context* ctx);
+
+}  // namespace dense
+}  // namespace dq

@@ -1,15 +1,484 @@
-// Dense path entry points (placeholder until the DMMA kernels land).
-#include "common.cuh"
-extern "C" {
-int dq_dense_set_H(dq_context*, int, const double*, int, const double*, const int32_t*, const double*, double, int) {
-    dq::set_error("dense path not built yet"); return DQ_ERR_UNSUPPORTED; }
-int dq_dense_trotter(dq_context*, const double*, double, double, int, const double*, int, int, double*, double*) {
-    dq::set_error("dense path not built yet"); return DQ_ERR_UNSUPPORTED; }
-int dq_dense_evolve(dq_context*, int, const double*, int, const double*, const double*, int, double, int, int,
-                    const double*, double*) {
-    dq::set_error("dense path not built yet"); return DQ_ERR_UNSUPPORTED; }
-int dq_dense_grad(dq_context*, int, const double*, int, const double*, const double*, const double*, double, int,
-                  const int32_t*, const double*, const double*, const int32_t*, const double*, const double*, int,
-                  double*) {
-    dq::set_error("dense path not built yet"); return DQ_ERR_UNSUPPORTED; }
+// C-ABI entry points and host orchestration of the dense path (dq_dense_*).
+//
+// exp(A) K for A = -i dt H(t_k), K a block of kets, is evaluated one of three ways, chosen per call
+// from the flop counts (all three are sequences of the same batched DMMA complex GEMM):
+//   0  block-Taylor : K <- T_m(A/2^s) applied 2^s times to the block          (2^s m GEMMs  Dp x Dp x Ncp)
+//   1  propagator   : P = T_m(A/2^s), s squarings, K <- P K                   (m-1+s GEMMs  Dp^3, one Dp x Dp x Ncp)
+//   2  chained      : as 1 but U <- P U per step and one K <- U K at the end  (more kets than dim)
+// The polynomial is evaluated in Horner form P <- I + (A/j) P, so every term is one GEMM with a fused
+// "+ I" / "+ K" epilogue.  A is skew-Hermitian, so squaring is norm-preserving and well conditioned.
+#include <algorithm>
+#include <cmath>
+#include <numeric>
+#include <string.h>
+#include "dense.cuh"
+
+namespace dq {
+namespace dense {
+
+State* state_of(dq_context* ctx) {
+    if (!ctx->dense) ctx->dense = new State();
+    return ctx->dense;
 }
+
+void release(dq_context* ctx) {
+    State* S = ctx->dense;
+    if (!S) return;
+    DevBuf* bufs[] = {&S->global_H.H, &S->global_H.M, &S->scratch_H.H, &S->scratch_H.M, &S->A, &S->P0, &S->P1, &S->U,
+                      &S->K0, &S->K1, &S->K2, &S->u_dev, &S->meta, &S->phi, &S->out};
+    for (auto* b : bufs) b->release();
+    delete S;
+    ctx->dense = nullptr;
+}
+
+namespace {
+
+inline int round8(int x) { return (x + 7) & ~7; }
+
+// interleaved c128 [dim][dim] -> planar zero-padded [2][Dp*Dp]
+void to_planar(const double* src, int dim, int Dp, double* dst) {
+    const size_t plane = (size_t)Dp * Dp;
+    for (int i = 0; i < dim; ++i)
+        for (int j = 0; j < dim; ++j) {
+            dst[(size_t)i * Dp + j] = src[2 * ((size_t)i * dim + j)];
+            dst[plane + (size_t)i * Dp + j] = src[2 * ((size_t)i * dim + j) + 1];
+        }
+}
+
+double norm1_of(const double* src, int dim) {
+    double best = 0.0;
+    for (int j = 0; j < dim; ++j) {
+        double s = 0.0;
+        for (int i = 0; i < dim; ++i) s += hypot(src[2 * ((size_t)i * dim + j)], src[2 * ((size_t)i * dim + j) + 1]);
+        best = std::max(best, s);
+    }
+    return best;
+}
+
+int upload_problem(dq_context* ctx, Problem& P, int dim, const double* H0, int n_H, const double* Hs) {
+    DQ_REQUIRE(dim >= 1 && dim <= 1024, "dense path: dim=%d outside [1,1024]", dim);
+    DQ_REQUIRE(n_H >= 0 && H0 && (n_H == 0 || Hs), "dense path: NULL Hamiltonian");
+    const size_t per = (size_t)dim * dim * 2;
+    const size_t total = per * (1 + n_H);
+    for (size_t i = 0; i < per; ++i) DQ_REQUIRE(std::isfinite(H0[i]), "dense path: non-finite H0 entry");
+    for (size_t i = 0; i < per * n_H; ++i) DQ_REQUIRE(std::isfinite(Hs[i]), "dense path: non-finite Hs entry");
+    if (P.dim == dim && P.n_H == n_H && P.host_copy.size() == total &&
+        !memcmp(P.host_copy.data(), H0, per * sizeof(double)) &&
+        (n_H == 0 || !memcmp(P.host_copy.data() + per, Hs, per * n_H * sizeof(double))))
+        return DQ_OK;                                   // same operators as last time: keep the device copy
+    P.dim = dim;
+    P.Dp = round8(dim);
+    P.n_H = n_H;
+    P.host_copy.assign(total, 0.0);
+    memcpy(P.host_copy.data(), H0, per * sizeof(double));
+    if (n_H) memcpy(P.host_copy.data() + per, Hs, per * n_H * sizeof(double));
+    const size_t plane = P.plane();
+    std::vector<double> planar((size_t)(1 + n_H) * 2 * plane, 0.0);
+    P.norm1.assign(1 + n_H, 0.0);
+    for (int h = 0; h <= n_H; ++h) {
+        const double* src = P.host_copy.data() + per * h;
+        to_planar(src, dim, P.Dp, planar.data() + (size_t)h * 2 * plane);
+        P.norm1[h] = norm1_of(src, dim);
+    }
+    DQ_TRY(P.H.reserve(planar.size() * sizeof(double)));
+    DQ_CUDA(cudaMemcpyAsync(P.H.p, planar.data(), planar.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    DQ_CUDA(cudaStreamSynchronize(ctx->stream));
+    return DQ_OK;
+}
+
+int upload_observable(dq_context* ctx, Problem& P, const double* M) {
+    const size_t per = (size_t)P.dim * P.dim * 2;
+    for (size_t i = 0; i < per; ++i) DQ_REQUIRE(std::isfinite(M[i]), "dense path: non-finite M entry");
+    std::vector<double> planar(2 * P.plane(), 0.0);
+    to_planar(M, P.dim, P.Dp, planar.data());
+    DQ_TRY(P.M.reserve(planar.size() * sizeof(double)));
+    DQ_CUDA(cudaMemcpyAsync(P.M.p, planar.data(), planar.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    DQ_CUDA(cudaStreamSynchronize(ctx->stream));
+    return DQ_OK;
+}
+
+inline int log2_ceil_ratio(double x, double theta) {
+    if (!(x > theta)) return 0;
+    return (int)std::ceil(std::log2(x / theta));
+}
+
+// Evolve B ket blocks (sample order, planar [B][2][Dp*Ncp], in place in d_K) through their own step lists.
+// steps/dts/row_off are per sample; h_u is the packed host table [total_rows][n_H].
+int evolve_blocks(dq_context* ctx, Problem& P, int mode, int B, int Ncp, const int* steps, const double* dts,
+                  const long long* row_off, const double* h_u, long long total_rows, double* d_K) {
+    State* S = state_of(ctx);
+    cudaStream_t st = ctx->stream;
+    const int Dp = P.Dp, n_H = P.n_H;
+    const size_t plane = P.plane(), mat = 2 * plane, blk = (size_t)2 * Dp * Ncp;
+    std::vector<int> order(B);
+    std::iota(order.begin(), order.end(), 0);
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return steps[a] > steps[b]; });
+    const int max_steps = steps[order[0]];
+    if (max_steps <= 0) return DQ_OK;
+
+    // ---- norm bound -> scaling -------------------------------------------------------------------
+    double bound = 0.0;
+    for (int b = 0; b < B; ++b)
+        for (int k = 0; k < steps[b]; ++k) {
+            const double* row = h_u + (row_off[b] + k) * n_H;
+            double nb = mode == 0 ? P.norm1[0] : 0.0;
+            for (int h = 0; h < n_H; ++h) {
+                DQ_REQUIRE(std::isfinite(row[h]), "dense path: non-finite pulse value (sample %d step %d term %d)", b, k, h);
+                if (mode == 0) nb += fabs(row[h]) * P.norm1[h + 1];
+                else nb = std::max(nb, fabs(row[h]) * P.norm1[h + 1]);
+            }
+            if (mode != 0) nb = std::max(nb, P.norm1[0]);
+            bound = std::max(bound, fabs(dts[b]) * nb);
+        }
+    const int m_blk = 18, m_mat = 9;
+    const int s_blk = log2_ceil_ratio(bound, 1.0), s_mat = log2_ceil_ratio(bound, 0.125);
+    DQ_REQUIRE(s_blk <= 20, "dense path: ||dt H|| = %g is too large", bound);
+    const double d3 = (double)Dp * Dp * Dp, d2n = (double)Dp * Dp * Ncp;
+    const double cost_blk = std::ldexp((double)m_blk, s_blk) * d2n;
+    const double cost_mat = (m_mat - 1 + s_mat) * d3 + d2n;
+    int strategy = cost_blk <= cost_mat ? 0 : 1;
+    if (strategy == 1 && mode == 0 && Ncp > Dp) strategy = 2;
+    if (ctx->dense_force_strategy >= 0 && (ctx->dense_force_strategy < 2 || mode == 0)) strategy = ctx->dense_force_strategy;
+    const int s = strategy == 0 ? s_blk : s_mat, m = strategy == 0 ? m_blk : m_mat;
+    S->last_strategy = strategy;
+    S->last_squarings = s;
+    S->last_degree = m;
+
+    // ---- device tables -----------------------------------------------------------------------------
+    DQ_TRY(S->u_dev.reserve(std::max<size_t>(1, (size_t)total_rows * n_H) * sizeof(double)));
+    if (total_rows * n_H)
+        DQ_CUDA(cudaMemcpyAsync(S->u_dev.p, h_u, (size_t)total_rows * n_H * sizeof(double), cudaMemcpyHostToDevice, st));
+    std::vector<long long> rows(B);
+    std::vector<double> scale(B);
+    for (int z = 0; z < B; ++z) {
+        rows[z] = row_off[order[z]];
+        scale[z] = std::ldexp(dts[order[z]], -s);
+    }
+    const size_t off_scale = (size_t)B * sizeof(long long), off_order = off_scale + (size_t)B * sizeof(double);
+    DQ_TRY(S->meta.reserve(off_order + (size_t)B * sizeof(int)));
+    char* meta = S->meta.as<char>();
+    DQ_CUDA(cudaMemcpyAsync(meta, rows.data(), B * sizeof(long long), cudaMemcpyHostToDevice, st));
+    DQ_CUDA(cudaMemcpyAsync(meta + off_scale, scale.data(), B * sizeof(double), cudaMemcpyHostToDevice, st));
+    DQ_CUDA(cudaMemcpyAsync(meta + off_order, order.data(), B * sizeof(int), cudaMemcpyHostToDevice, st));
+    const long long* d_rows = reinterpret_cast<const long long*>(meta);
+    const double* d_scale = reinterpret_cast<const double*>(meta + off_scale);
+    const int* d_order = reinterpret_cast<const int*>(meta + off_order);
+
+    DQ_TRY(S->A.reserve((size_t)B * mat * sizeof(double)));
+    DQ_TRY(S->K0.reserve((size_t)B * blk * sizeof(double)));
+    DQ_TRY(S->K1.reserve((size_t)B * blk * sizeof(double)));
+    if (strategy == 0) DQ_TRY(S->K2.reserve((size_t)B * blk * sizeof(double)));
+    else {
+        DQ_TRY(S->P0.reserve((size_t)B * mat * sizeof(double)));
+        DQ_TRY(S->P1.reserve((size_t)B * mat * sizeof(double)));
+    }
+    if (strategy == 2) DQ_TRY(S->U.reserve((size_t)B * mat * sizeof(double)));
+    double* A = S->A.as<double>();
+    double *cur = S->K0.as<double>(), *ya = S->K1.as<double>(), *yb = S->K2.as<double>();
+    double *p0 = S->P0.as<double>(), *p1 = S->P1.as<double>(), *U = S->U.as<double>();
+    DQ_TRY(gather_blocks(ctx, d_K, cur, d_order, B, blk, 0));
+    double flops = 0.0;
+
+    auto gemm_mat = [&](const double* a, const double* b, double* c, int nb, double alpha, int ident) {
+        Gemm g{a, (long long)mat, (long long)plane, Dp, b, (long long)mat, (long long)plane, Dp,
+               c, (long long)mat, (long long)plane, Dp, nullptr, Dp, Dp, Dp, nb, alpha, ident};
+        flops += 8.0 * d3 * nb;
+        return zgemm(ctx, g);
+    };
+    auto gemm_blk = [&](const double* a, const double* b, double* c, const double* add, int nb, double alpha) {
+        Gemm g{a, (long long)mat, (long long)plane, Dp, b, (long long)blk, (long long)Dp * Ncp, Ncp,
+               c, (long long)blk, (long long)Dp * Ncp, Ncp, add, Dp, Ncp, Dp, nb, alpha, 0};
+        flops += 8.0 * d2n * nb;
+        return zgemm(ctx, g);
+    };
+
+    if (strategy == 2) {                                               // U = 0 * (0 0) + I
+        DQ_CUDA(cudaMemsetAsync(A, 0, (size_t)B * mat * sizeof(double), st));
+        DQ_TRY(gemm_mat(A, A, U, B, 0.0, 1));
+        flops -= 8.0 * d3 * B;
+    }
+
+    int nb = B;
+    for (int k = 0; k < max_steps; ++k) {
+        while (nb > 0 && steps[order[nb - 1]] <= k) --nb;
+        int nb_next = nb;
+        while (nb_next > 0 && steps[order[nb_next - 1]] <= k + 1) --nb_next;
+        const int t_lo = mode == 0 ? -1 : 0, t_hi = mode == 0 ? -1 : n_H;
+        for (int term = t_lo; term <= t_hi; ++term) {
+            if (strategy == 0) {
+                DQ_TRY(build_generator(ctx, P, nb, S->u_dev.as<double>(), d_rows, d_scale, k, term, A, nullptr, 0.0));
+                for (long long rep = 0; rep < (1LL << s); ++rep) {
+                    DQ_TRY(gemm_blk(A, cur, ya, cur, nb, 1.0 / m));
+                    for (int j = m - 1; j >= 1; --j) {
+                        DQ_TRY(gemm_blk(A, ya, yb, cur, nb, 1.0 / j));
+                        std::swap(ya, yb);
+                    }
+                    std::swap(cur, ya);          // finished slots keep their data: they were scattered out already
+                }
+            } else {
+                DQ_TRY(build_generator(ctx, P, nb, S->u_dev.as<double>(), d_rows, d_scale, k, term, A, p0, 1.0 / m));
+                for (int j = m - 1; j >= 1; --j) {
+                    DQ_TRY(gemm_mat(A, p0, p1, nb, 1.0 / j, 1));
+                    std::swap(p0, p1);
+                }
+                for (int q = 0; q < s; ++q) {
+                    DQ_TRY(gemm_mat(p0, p0, p1, nb, 1.0, 0));
+                    std::swap(p0, p1);
+                }
+                if (strategy == 1) {
+                    DQ_TRY(gemm_blk(p0, cur, ya, nullptr, nb, 1.0));
+                    std::swap(cur, ya);
+                } else {
+                    DQ_TRY(gemm_mat(p0, U, p1, nb, 1.0, 0));            // U <- P U, result lands in p1
+                    std::swap(U, p1);
+                }
+            }
+        }
+        if (nb_next < nb) {                      // slots [nb_next, nb) took their last step
+            const int cnt = nb - nb_next;
+            if (strategy == 2) {
+                Gemm g{U + (size_t)nb_next * mat, (long long)mat, (long long)plane, Dp,
+                       cur + (size_t)nb_next * blk, (long long)blk, (long long)Dp * Ncp, Ncp,
+                       ya + (size_t)nb_next * blk, (long long)blk, (long long)Dp * Ncp, Ncp, nullptr, Dp, Ncp, Dp, cnt, 1.0, 0};
+                flops += 8.0 * d2n * cnt;
+                DQ_TRY(zgemm(ctx, g));
+                DQ_TRY(gather_blocks(ctx, ya + (size_t)nb_next * blk, d_K, d_order + nb_next, cnt, blk, 1));
+            } else {
+                DQ_TRY(gather_blocks(ctx, cur + (size_t)nb_next * blk, d_K, d_order + nb_next, cnt, blk, 1));
+            }
+        }
+    }
+    // the buffer pointers were rotated locally; the DevBufs still own the same three allocations
+    S->last_gemm_flops += flops;
+    return DQ_OK;
+}
+
+// host block helpers: interleaved c128 kets <-> planar block columns
+void put_column(std::vector<double>& blk, int Dp, int Ncp, int dim, int col, const double* psi) {
+    for (int x = 0; x < dim; ++x) {
+        blk[(size_t)x * Ncp + col] = psi[2 * x];
+        blk[(size_t)Dp * Ncp + (size_t)x * Ncp + col] = psi[2 * x + 1];
+    }
+}
+void get_column(const std::vector<double>& blk, int Dp, int Ncp, int dim, int col, double* psi) {
+    for (int x = 0; x < dim; ++x) {
+        psi[2 * x] = blk[(size_t)x * Ncp + col];
+        psi[2 * x + 1] = blk[(size_t)Dp * Ncp + (size_t)x * Ncp + col];
+    }
+}
+
+// ---- diffqc pulse model on the host (diffqc.cc:75-135) ------------------------------------------------
+double expit_cc(double x) {
+    if (x > 32.) return 1.;
+    if (x < -32.) return 0.;
+    return 1 / (1 + std::exp(-x));
+}
+double bump(int b, int n_basis, double t) {
+    const double tau = 1. / (n_basis - 2.);
+    const double tau_b = tau * (b - 1.5);
+    const double l = tau_b - 1.5 * tau, r = tau_b + 1.5 * tau;
+    if (t < r && t > l) return (t - l) * (t - r) / (-(1.5 * tau) * (1.5 * tau));
+    return 0.;
+}
+int f_u(const Problem& P, int h, double t, const double* vv, int n_param, int n_basis, double* out) {
+    double ans = 0;
+    for (const auto& chan : P.channels[h]) {
+        const double omega = chan[1], w = chan[2];
+        const int idx = (int)std::round(chan[3]);
+        DQ_REQUIRE(idx >= 0 && idx < n_param, "dq_dense_trotter: channel parameter index %d outside vv (n_param=%d)", idx, n_param);
+        double A = 0, B = 0;
+        for (int j = 0; j < n_basis; ++j) {
+            const double fv = P.func_type == 0 ? std::legendre((unsigned)j, 2 * t / P.duration - 1)
+                                               : bump(j, n_basis, t / P.duration);
+            A += vv[((size_t)0 * n_param + idx) * n_basis + j] * fv;
+            B += vv[((size_t)1 * n_param + idx) * n_basis + j] * fv;
+        }
+        const double N = std::sqrt(A * A + B * B);
+        if (std::fabs(N - 0.0) < 0.000001) ans += 0.0;
+        else ans += omega * (2 * expit_cc(N) - 1) / N * (std::cos(w * t) * A + std::sin(w * t) * B);
+    }
+    *out = ans;
+    return DQ_OK;
+}
+
+}  // namespace
+}  // namespace dense
+}  // namespace dq
+
+using namespace dq::dense;
+
+extern "C" {
+
+int dq_dense_set_H(dq_context* ctx, int dim, const double* H0, int n_H, const double* Hs, const int32_t* chan_counts,
+                   const double* channels, double duration, int func_type) {
+    DQ_REQUIRE(ctx, "NULL context");
+    DQ_REQUIRE(n_H == 0 || chan_counts, "dq_dense_set_H: NULL channel counts");
+    DQ_REQUIRE(std::isfinite(duration) && duration != 0.0, "dq_dense_set_H: duration must be finite and non-zero");
+    DQ_TRY(ctx->set_device());
+    Problem& P = state_of(ctx)->global_H;
+    P.is_set = false;
+    DQ_TRY(upload_problem(ctx, P, dim, H0, n_H, Hs));
+    P.channels.assign(n_H, {});
+    size_t k = 0;
+    for (int h = 0; h < n_H; ++h) {
+        DQ_REQUIRE(chan_counts[h] >= 0, "dq_dense_set_H: negative channel count for term %d", h);
+        DQ_REQUIRE(chan_counts[h] == 0 || channels, "dq_dense_set_H: NULL channel table");
+        for (int c = 0; c < chan_counts[h]; ++c, ++k) {
+            std::array<double, 4> ch = {channels[4 * k], channels[4 * k + 1], channels[4 * k + 2], channels[4 * k + 3]};
+            for (double v : ch) DQ_REQUIRE(std::isfinite(v), "dq_dense_set_H: non-finite channel entry (term %d)", h);
+            P.channels[h].push_back(ch);
+        }
+    }
+    P.duration = duration;
+    P.func_type = func_type;
+    P.is_set = true;
+    return DQ_OK;
+}
+
+int dq_dense_trotter(dq_context* ctx, const double* psi0, double T0, double T, int per_step, const double* vv,
+                     int n_param, int n_basis, double* psi_out, double* u_out) {
+    DQ_REQUIRE(ctx && psi0 && psi_out && vv, "dq_dense_trotter: NULL argument");
+    DQ_TRY(ctx->set_device());
+    State* S = state_of(ctx);
+    Problem& P = S->global_H;
+    if (!P.is_set) {
+        dq::set_error("dq_dense_trotter: set_H has not been called (diffqc.cc:21-25 globals are empty)");
+        return DQ_ERR_STATE;
+    }
+    DQ_REQUIRE(n_param >= 1 && n_basis >= 1, "dq_dense_trotter: vv must be [2][n_param>=1][n_basis>=1]");
+    DQ_REQUIRE(P.func_type == 0 || n_basis != 2, "dq_dense_trotter: the bump basis needs n_basis != 2 (tau = 1/(n_basis-2))");
+    DQ_REQUIRE(std::isfinite(T0) && std::isfinite(T), "dq_dense_trotter: non-finite time span");
+    for (size_t i = 0; i < (size_t)2 * n_param * n_basis; ++i) DQ_REQUIRE(std::isfinite(vv[i]), "dq_dense_trotter: non-finite vv entry");
+    for (int i = 0; i < 2 * P.dim; ++i) DQ_REQUIRE(std::isfinite(psi0[i]), "dq_dense_trotter: non-finite psi0 entry");
+    // diffqc.cc:182-184: n_steps = (int)(per_step * (|T - T0| + 1)), dt = (T - T0) / n_steps, t accumulates
+    const int n_steps = (int)(per_step * (std::fabs(T - T0) + 1));
+    DQ_REQUIRE(n_steps >= 1, "dq_dense_trotter: per_step=%d gives %d steps (the reference divides by zero here)", per_step, n_steps);
+    const double dt = (T - T0) / n_steps;
+    std::vector<double> u((size_t)n_steps * std::max(1, P.n_H));
+    double t = T0;
+    for (int k = 0; k < n_steps; ++k) {
+        for (int h = 0; h < P.n_H; ++h) DQ_TRY(f_u(P, h, t, vv, n_param, n_basis, &u[(size_t)k * P.n_H + h]));
+        t += dt;
+    }
+    if (u_out) memcpy(u_out, u.data(), (size_t)n_steps * P.n_H * sizeof(double));
+    const int Ncp = 8;
+    std::vector<double> blk((size_t)2 * P.Dp * Ncp, 0.0);
+    put_column(blk, P.Dp, Ncp, P.dim, 0, psi0);
+    DQ_TRY(S->phi.reserve(blk.size() * sizeof(double)));
+    DQ_CUDA(cudaMemcpyAsync(S->phi.p, blk.data(), blk.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    const long long off = 0;
+    S->last_gemm_flops = 0;
+    DQ_TRY(evolve_blocks(ctx, P, 0, 1, Ncp, &n_steps, &dt, &off, u.data(), n_steps, S->phi.as<double>()));
+    DQ_CUDA(cudaMemcpyAsync(blk.data(), S->phi.p, blk.size() * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    DQ_CUDA(cudaStreamSynchronize(ctx->stream));
+    get_column(blk, P.Dp, Ncp, P.dim, 0, psi_out);
+    return DQ_OK;
+}
+
+int dq_dense_evolve(dq_context* ctx, int dim, const double* H0, int n_H, const double* Hs, const double* u, int n_steps,
+                    double dt, int mode, int batch, const double* psi_in, double* psi_out) {
+    DQ_REQUIRE(ctx && psi_in && psi_out, "dq_dense_evolve: NULL argument");
+    DQ_REQUIRE(mode == 0 || mode == 1, "dq_dense_evolve: mode must be 0 (exact) or 1 (split)");
+    DQ_REQUIRE(batch >= 1 && n_steps >= 0, "dq_dense_evolve: batch=%d n_steps=%d", batch, n_steps);
+    DQ_REQUIRE(n_steps == 0 || n_H == 0 || u, "dq_dense_evolve: NULL pulse table");
+    DQ_REQUIRE(std::isfinite(dt), "dq_dense_evolve: non-finite dt");
+    DQ_TRY(ctx->set_device());
+    State* S = state_of(ctx);
+    Problem& P = S->scratch_H;
+    DQ_TRY(upload_problem(ctx, P, dim, H0, n_H, Hs));
+    for (size_t i = 0; i < (size_t)2 * dim * batch; ++i) DQ_REQUIRE(std::isfinite(psi_in[i]), "dq_dense_evolve: non-finite psi entry");
+    const int Ncp = round8(batch);
+    std::vector<double> blk((size_t)2 * P.Dp * Ncp, 0.0);
+    for (int c = 0; c < batch; ++c) put_column(blk, P.Dp, Ncp, dim, c, psi_in + (size_t)2 * dim * c);
+    DQ_TRY(S->phi.reserve(blk.size() * sizeof(double)));
+    DQ_CUDA(cudaMemcpyAsync(S->phi.p, blk.data(), blk.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    const long long off = 0;
+    S->last_gemm_flops = 0;
+    static const double no_u = 0.0;
+    DQ_TRY(evolve_blocks(ctx, P, mode, 1, Ncp, &n_steps, &dt, &off, u ? u : &no_u, n_steps, S->phi.as<double>()));
+    DQ_CUDA(cudaMemcpyAsync(blk.data(), S->phi.p, blk.size() * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    DQ_CUDA(cudaStreamSynchronize(ctx->stream));
+    for (int c = 0; c < batch; ++c) get_column(blk, P.Dp, Ncp, dim, c, psi_out + (size_t)2 * dim * c);
+    return DQ_OK;
+}
+
+int dq_dense_grad(dq_context* ctx, int dim, const double* H0, int n_H, const double* Hs, const double* M,
+                  const double* psi0, double r, int n_samples, const int32_t* prefix_steps, const double* prefix_dt,
+                  const double* u_prefix, const int32_t* suffix_steps, const double* suffix_dt, const double* u_suffix,
+                  int mode, double* energies_out) {
+    DQ_REQUIRE(ctx && M && psi0 && energies_out, "dq_dense_grad: NULL argument");
+    DQ_REQUIRE(prefix_steps && prefix_dt && suffix_steps && suffix_dt, "dq_dense_grad: NULL step table");
+    DQ_REQUIRE(mode == 0 || mode == 1, "dq_dense_grad: mode must be 0 (exact) or 1 (split)");
+    DQ_REQUIRE(n_samples >= 1 && n_H >= 1, "dq_dense_grad: n_samples=%d n_H=%d", n_samples, n_H);
+    DQ_REQUIRE(r > 0 && std::isfinite(r), "dq_dense_grad: r must be positive");
+    DQ_TRY(ctx->set_device());
+    State* S = state_of(ctx);
+    Problem& P = S->scratch_H;
+    DQ_TRY(upload_problem(ctx, P, dim, H0, n_H, Hs));
+    DQ_TRY(upload_observable(ctx, P, M));
+    for (int i = 0; i < 2 * dim; ++i) DQ_REQUIRE(std::isfinite(psi0[i]), "dq_dense_grad: non-finite psi0 entry");
+    std::vector<long long> pre_off(n_samples + 1, 0), suf_off(n_samples + 1, 0);
+    for (int b = 0; b < n_samples; ++b) {
+        DQ_REQUIRE(prefix_steps[b] >= 0 && suffix_steps[b] >= 0, "dq_dense_grad: negative step count (sample %d)", b);
+        DQ_REQUIRE(std::isfinite(prefix_dt[b]) && std::isfinite(suffix_dt[b]), "dq_dense_grad: non-finite dt (sample %d)", b);
+        pre_off[b + 1] = pre_off[b] + prefix_steps[b];
+        suf_off[b + 1] = suf_off[b] + suffix_steps[b];
+    }
+    DQ_REQUIRE((pre_off[n_samples] == 0 || u_prefix) && (suf_off[n_samples] == 0 || u_suffix), "dq_dense_grad: NULL pulse table");
+    const int Ncp = round8(2 * n_H), Dp = P.Dp;
+    const size_t mat_bytes = 2 * P.plane() * sizeof(double);
+    // samples per chunk: three Dp x Dp work matrices and three ket blocks per sample within ~4 GiB
+    const size_t per_sample = 4 * mat_bytes + 4 * (size_t)2 * Dp * Ncp * sizeof(double);
+    const int chunk = (int)std::max<size_t>(1, std::min<size_t>((size_t)n_samples, ((size_t)4 << 30) / per_sample));
+    std::vector<double> phi_blk((size_t)2 * Dp * 8, 0.0);
+    put_column(phi_blk, Dp, 8, dim, 0, psi0);
+    S->last_gemm_flops = 0;
+    static const double no_u = 0.0;
+    for (int b0 = 0; b0 < n_samples; b0 += chunk) {
+        const int nb = std::min(chunk, n_samples - b0);
+        DQ_TRY(S->phi.reserve((size_t)nb * phi_blk.size() * sizeof(double)));
+        DQ_TRY(S->out.reserve(((size_t)nb * 2 * Dp * Ncp + (size_t)nb * 2 * n_H) * sizeof(double)));
+        for (int b = 0; b < nb; ++b)
+            DQ_CUDA(cudaMemcpyAsync(S->phi.as<double>() + (size_t)b * phi_blk.size(), b == 0 ? (const void*)phi_blk.data() : S->phi.p,
+                                    phi_blk.size() * sizeof(double), b == 0 ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice,
+                                    ctx->stream));
+        std::vector<long long> po(nb), so(nb);
+        for (int b = 0; b < nb; ++b) { po[b] = pre_off[b0 + b] - pre_off[b0]; so[b] = suf_off[b0 + b] - suf_off[b0]; }
+        const long long n_pre = pre_off[b0 + nb] - pre_off[b0], n_suf = suf_off[b0 + nb] - suf_off[b0];
+        DQ_TRY(evolve_blocks(ctx, P, mode, nb, 8, prefix_steps + b0, prefix_dt + b0, po.data(),
+                             u_prefix ? u_prefix + pre_off[b0] * n_H : &no_u, n_pre, S->phi.as<double>()));
+        double* K = S->out.as<double>();
+        double* E = K + (size_t)nb * 2 * Dp * Ncp;
+        DQ_CUDA(cudaMemsetAsync(K, 0, (size_t)nb * 2 * Dp * Ncp * sizeof(double), ctx->stream));
+        DQ_TRY(fanout(ctx, P, nb, S->phi.as<double>(), 8, K, Ncp, r));
+        DQ_TRY(evolve_blocks(ctx, P, mode, nb, Ncp, suffix_steps + b0, suffix_dt + b0, so.data(),
+                             u_suffix ? u_suffix + suf_off[b0] * n_H : &no_u, n_suf, K));
+        DQ_TRY(energies(ctx, P, nb, K, Ncp, 2 * n_H, E));
+        DQ_CUDA(cudaMemcpyAsync(energies_out + (size_t)b0 * 2 * n_H, E, (size_t)nb * 2 * n_H * sizeof(double),
+                                cudaMemcpyDeviceToHost, ctx->stream));
+        DQ_CUDA(cudaStreamSynchronize(ctx->stream));
+    }
+    return DQ_OK;
+}
+
+int dq_dense_last_stat(dq_context* ctx, const char* name, double* value) {
+    DQ_REQUIRE(ctx && name && value, "NULL argument");
+    State* S = state_of(ctx);
+    if (!strcmp(name, "gemm_flops")) *value = S->last_gemm_flops;
+    else if (!strcmp(name, "strategy")) *value = S->last_strategy;
+    else if (!strcmp(name, "squarings")) *value = S->last_squarings;
+    else if (!strcmp(name, "degree")) *value = S->last_degree;
+    else { dq::set_error("dq_dense_last_stat: unknown name '%s'", name); return DQ_ERR_INVALID; }
+    return DQ_OK;
+}
+
+int dq_dense_set_option(dq_context* ctx, const char* name, int64_t value) {
+    DQ_REQUIRE(ctx && name, "NULL argument");
+    if (!strcmp(name, "strategy")) {
+        DQ_REQUIRE(value >= -1 && value <= 2, "strategy must be -1 (auto), 0, 1 or 2");
+        ctx->dense_force_strategy = (int)value;
+    } else { dq::set_error("dq_dense_set_option: unknown option '%s'", name); return DQ_ERR_INVALID; }
+    return DQ_OK;
+}
+
+}  // extern "C"

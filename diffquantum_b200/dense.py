@@ -1,0 +1,191 @@
+"""Dense path (dim <= 1024) behind the reference's Python-facing interfaces.
+
+  DenseSimulator        explicit arrays: evolve / grad_samples with the live `exact` step
+                        psi <- expm(-i dt (H0 + sum_i u_i(t_k) H_i)) psi  (sim_plain.py:135-150), or the
+                        disabled per-term product (`split`, diffqc.cc:155-164).
+  solver_for(sim)       a drop-in for SimulatorPlain.my_solver (sim_plain.py:43): same signature
+                        solver(H_list, psi0, T0, T) -> Qobj, evaluates the reference's own pulse
+                        closures on the reference's own step grid and runs the steps on the GPU.
+  estimator_for(sim)    compute_energy_grad_MC (sim_plain.py:156-231) with the 1 + 2*n_Hs evolutions
+                        batched into one device call; consumes np.random exactly like the reference.
+
+All device work goes through the C ABI (include/diffqc_b200.h, dq_dense_*); there is no CPU path.
+"""
+import ctypes
+
+import numpy as np
+
+from . import _lib
+from . import pulses
+
+MODES = {"exact": 0, "split": 1}
+
+
+def _c128(a, shape=None):
+    a = np.ascontiguousarray(np.asarray(a, dtype=np.complex128))
+    if shape is not None:
+        a = a.reshape(shape)
+    return a
+
+
+def _full(q):
+    """ndarray of a qutip-like object (has .full()) or of anything array-like."""
+    return np.asarray(q.full() if hasattr(q, "full") else q, dtype=np.complex128)
+
+
+def dense_evolve(ctx, H0, Hs, u, dt, psi, mode="exact"):
+    """psi: [batch, dim] (or [dim]); u: [n_steps, n_H] host-evaluated pulse values."""
+    H0 = _c128(H0)
+    dim = H0.shape[0]
+    Hs = _c128(Hs, (-1, dim, dim))
+    u = np.asarray(u, dtype=np.float64)
+    n_steps = u.shape[0] if u.ndim == 2 else u.size // max(1, Hs.shape[0])
+    u = np.ascontiguousarray(u.reshape(n_steps, Hs.shape[0]))
+    psi = _c128(psi)
+    single = psi.ndim == 1
+    psi = psi.reshape(-1, dim)
+    out = np.empty_like(psi)
+    _lib.check(_lib.load().dq_dense_evolve(ctx.handle, dim, _lib.ptr(H0), Hs.shape[0], _lib.ptr(Hs), _lib.ptr(u),
+                                           n_steps, float(dt), MODES[mode], psi.shape[0], _lib.ptr(psi),
+                                           _lib.ptr(out)))
+    return out[0] if single else out
+
+
+class DenseSimulator(object):
+    """H(t) = H0 + sum_i u_i(t) H_i on explicit dense matrices, pulses u_i as SimulatorPlain.generate_u
+    builds them (sim_plain.py:73-99): u_i(t) = omega_i (2 sigma(sum_j c_ij phi_j(t/T)) - 1)."""
+
+    def __init__(self, H0, Hs, omegas, T, M=None, psi0=None, per_step=10, basis="BSpline", device=0, mode="exact"):
+        self.H0 = _c128(H0)
+        self.dim = self.H0.shape[0]
+        self.Hs = _c128(Hs, (-1, self.dim, self.dim))
+        self.n_H = self.Hs.shape[0]
+        self.omegas = np.asarray(omegas, dtype=np.float64)
+        if len(self.omegas) != self.n_H:
+            raise ValueError("one omega per control term is required")
+        self.T = float(T)
+        self.M = None if M is None else _c128(M, (self.dim, self.dim))
+        self.psi0 = None if psi0 is None else _c128(psi0, (self.dim,))
+        self.per_step = per_step
+        self.basis = basis
+        self.mode = mode
+        self.ctx = _lib.Context.get(device)
+
+    def stat(self, name):
+        v = ctypes.c_double()
+        _lib.check(_lib.load().dq_dense_last_stat(self.ctx.handle, name.encode(), ctypes.byref(v)))
+        return v.value
+
+    def set_option(self, name, value):
+        _lib.check(_lib.load().dq_dense_set_option(self.ctx.handle, name.encode(), int(value)))
+
+    def evolve(self, coeff, T0, T1, psi0=None, mode=None):
+        """SimulatorPlain.trotter (sim_plain.py:119-153) on the reference's step grid."""
+        n_steps, dt, ts = pulses.step_grid(T0, T1, self.per_step)
+        psi = self.psi0 if psi0 is None else psi0
+        if n_steps == 0:
+            return _c128(psi).copy()
+        u = pulses.u_table(coeff, self.omegas, self.T, ts, self.basis)
+        return dense_evolve(self.ctx, self.H0, self.Hs, u, dt, psi, mode or self.mode)
+
+    def energy(self, psi):
+        psi = _c128(psi, (self.dim,))
+        return (psi.conj() @ self.M @ psi).real
+
+    def shifted_energies(self, coeff, s_list, r=0.5, mode=None):
+        """energies[b, i, 0|1] = <M> of the (+, -) shifted trajectories (ps_p, ps_m: sim_plain.py:205,215)."""
+        if self.M is None or self.psi0 is None:
+            raise ValueError("shifted_energies needs M and psi0")
+        s_list = np.asarray(s_list, dtype=np.float64).reshape(-1)
+        pre_n, pre_dt, pre_u, suf_n, suf_dt, suf_u = [], [], [], [], [], []
+        for s in s_list:
+            n, dt, ts = pulses.step_grid(0, s, self.per_step)
+            pre_n.append(n); pre_dt.append(dt)
+            pre_u.append(pulses.u_table(coeff, self.omegas, self.T, ts, self.basis).reshape(n, self.n_H))
+            n, dt, ts = pulses.step_grid(s, self.T, self.per_step)
+            suf_n.append(n); suf_dt.append(dt)
+            suf_u.append(pulses.u_table(coeff, self.omegas, self.T, ts, self.basis).reshape(n, self.n_H))
+        cat = lambda xs: np.ascontiguousarray(np.concatenate(xs, axis=0)) if xs else np.zeros((0, self.n_H))
+        pre_n = np.array(pre_n, dtype=np.int32); suf_n = np.array(suf_n, dtype=np.int32)
+        pre_dt = np.array(pre_dt, dtype=np.float64); suf_dt = np.array(suf_dt, dtype=np.float64)
+        pre_u = cat(pre_u); suf_u = cat(suf_u)
+        out = np.empty((len(s_list), self.n_H, 2))
+        _lib.check(_lib.load().dq_dense_grad(
+            self.ctx.handle, self.dim, _lib.ptr(self.H0), self.n_H, _lib.ptr(self.Hs), _lib.ptr(self.M),
+            _lib.ptr(self.psi0), float(r), len(s_list), _lib.ptr(pre_n), _lib.ptr(pre_dt), _lib.ptr(pre_u),
+            _lib.ptr(suf_n), _lib.ptr(suf_dt), _lib.ptr(suf_u), MODES[mode or self.mode], _lib.ptr(out)))
+        return out
+
+    def grad_samples(self, coeff, s_list, r=0.5, coeff_sign=1.0, return_energies=False, mode=None):
+        """Per-sample gradients of compute_energy_grad_MC (sim_plain.py:156-231) at explicit times."""
+        s_list = np.asarray(s_list, dtype=np.float64).reshape(-1)
+        en = self.shifted_energies(coeff, s_list, r, mode)
+        grads = np.empty((len(s_list),) + np.asarray(coeff).shape)
+        for b, s in enumerate(s_list):
+            ps = coeff_sign * ((1 + r ** 2) / 2 / r * (en[b, :, 1] - en[b, :, 0]))
+            grads[b] = ps[:, None] * pulses.dudc_table(coeff, self.omegas, self.T, s, self.basis)
+        return (grads, en) if return_energies else grads
+
+
+# ---- drop-ins for SimulatorPlain --------------------------------------------------------------------
+
+def _split_H(H_):
+    """[H0, [H_1, u_1], ...] as train_energy builds it (sim_plain.py:272-274) -> arrays + closures."""
+    H0 = _full(H_[0])
+    Hs = np.array([_full(h[0]) for h in H_[1:]], dtype=np.complex128).reshape(-1, H0.shape[0], H0.shape[0])
+    fs = [h[1] for h in H_[1:]]
+    return H0, Hs, fs
+
+
+def solver_for(sim, device=0, mode="exact"):
+    """GPU-backed replacement for SimulatorPlain.trotter; assign it to `sim.my_solver`.
+    Step grid and pulse sampling follow sim_plain.py:123,133-150 literally: n_steps by int truncation
+    without abs, left-end sampling, t accumulated by `t += dt`, closures called as u(t, None)."""
+    ctx = _lib.Context.get(device)
+
+    def solver(H_, psi0_, T0, T):
+        H0, Hs, fs = _split_H(H_)
+        n_steps, dt, ts = pulses.step_grid(T0, T, sim.per_step)
+        psi0 = _full(psi0_).reshape(-1)
+        if n_steps <= 0:
+            raise ZeroDivisionError("float division by zero")       # sim_plain.py:133 with n_steps == 0
+        u = np.array([[f(t, None) for f in fs] for t in ts], dtype=np.float64).reshape(n_steps, len(fs))
+        out = dense_evolve(ctx, H0, Hs, u, dt, psi0, mode)
+        return type(psi0_)(out) if hasattr(psi0_, "full") else out
+
+    return solver
+
+
+def estimator_for(sim, device=0, mode="exact"):
+    """Batched replacement for SimulatorPlain.compute_energy_grad_MC (sim_plain.py:156-231).
+    Same signature and return type (torch.float64 [n_Hs, n_basis]); draws s = np.random.uniform() * T
+    exactly where the reference does (:167) unless `s` is passed."""
+    ctx = _lib.Context.get(device)
+
+    def compute_energy_grad_MC(M, H_, psi0_, coeff=1.0, s=None):
+        import torch
+        H0, Hs, fs = _split_H(H_)
+        if s is None:
+            s = np.random.uniform() * sim.T
+        c = sim.spectral_coeff.detach().cpu().numpy()
+        ds = DenseSimulator(H0, Hs, sim.omegas, sim.T, M=_full(M), psi0=_full(psi0_).reshape(-1),
+                            per_step=sim.per_step, basis=sim.basis, device=device, mode=mode)
+        ds.ctx = ctx
+        # pulse values come from the closures the caller built (they may differ from sim.spectral_coeff)
+        def table(T0, T1):
+            n, dt, ts = pulses.step_grid(T0, T1, sim.per_step)
+            return n, dt, np.array([[f(t, None) for f in fs] for t in ts], dtype=np.float64).reshape(n, len(fs))
+        pn, pdt, pu = table(0, s)
+        sn, sdt, su = table(s, sim.T)
+        en = np.empty((1, len(fs), 2))
+        r = 1 / 2
+        _lib.check(_lib.load().dq_dense_grad(
+            ctx.handle, ds.dim, _lib.ptr(ds.H0), ds.n_H, _lib.ptr(ds.Hs), _lib.ptr(ds.M), _lib.ptr(ds.psi0), r, 1,
+            _lib.ptr(np.array([pn], dtype=np.int32)), _lib.ptr(np.array([pdt])), _lib.ptr(np.ascontiguousarray(pu)),
+            _lib.ptr(np.array([sn], dtype=np.int32)), _lib.ptr(np.array([sdt])), _lib.ptr(np.ascontiguousarray(su)),
+            MODES[mode], _lib.ptr(en)))
+        ps = coeff * ((1 + r ** 2) / 2 / r * (en[0, :, 1] - en[0, :, 0]))
+        grad = ps[:, None] * pulses.dudc_table(c, sim.omegas, sim.T, s, sim.basis)
+        return torch.from_numpy(grad)
+
+    return compute_energy_grad_MC

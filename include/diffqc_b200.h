@@ -87,6 +87,12 @@ int dq_dense_grad(dq_context* ctx, int dim, const double* H0, int n_H, const dou
                   const int32_t* suffix_steps, const double* suffix_dt, const double* u_suffix,
                   int mode, double* energies_out);
 
+/* Counters of the last dense call: "gemm_flops" (real flops issued to the DMMA GEMM), "strategy"
+ * (0 block-Taylor, 1 per-step propagator, 2 chained propagator), "squarings", "degree". */
+int dq_dense_last_stat(dq_context* ctx, const char* name, double* value);
+/* "strategy": -1 automatic (flop count), or force 0/1/2 (parity tests cover all three). */
+int dq_dense_set_option(dq_context* ctx, const char* name, int64_t value);
+
 /* ---- structured path: H(t) = c0 + sum_e (w_e + u_e(t)) Z_a Z_b + sum_q u_q(t) X_q ------------
  * One product-formula step = one diagonal phase exp(-i(angle_c + sum_e angle_e z_a z_b)) followed by
  * exp(-i angle_q X_q) on every qubit (term order of diffqc.cc:155-164: H0, ZZ controls, X controls).

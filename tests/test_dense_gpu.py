@@ -1,0 +1,184 @@
+"""GPU parity tests of the dense path through the C ABI (dq_dense_*), against
+  * fixtures produced by the reference's own code (tests/golden/*_ref.npz: SimulatorPlain.trotter and
+    compute_energy_grad_MC run unmodified — oracle/make_golden.py), and
+  * the NumPy restatement (oracle/restate.py) on live seeded inputs.
+Tolerance 1e-10 relative on amplitudes, energies and per-sample gradients (BASELINE north_star)."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+import diffquantum_b200 as dq
+from oracle import restate as R
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-10
+DENSE_REF = ["demo_bspline_ref", "demo_legendre_ref", "h2_vqe_ref"]
+
+
+def rel(a, b):
+    return np.abs(np.asarray(a) - np.asarray(b)).max() / max(np.abs(np.asarray(b)).max(), 1e-300)
+
+
+def sim_from(g, **kw):
+    return dq.DenseSimulator(g["H0"], g["Hs"], g["omegas"], float(g["T"]), M=g["M"], psi0=g["psi0"],
+                             per_step=int(g["per_step"]), basis=str(g["basis"]), **kw)
+
+
+@pytest.mark.parametrize("name", DENSE_REF)
+@pytest.mark.parametrize("strategy", [-1, 0, 1, 2])
+def test_exact_evolution_matches_reference_fixture(golden, name, strategy):
+    g = golden(name)
+    sim = sim_from(g)
+    sim.set_option("strategy", strategy)
+    try:
+        final = sim.evolve(g["coeff"], 0, float(g["T"]))
+        assert rel(final, g["final"]) < TOL
+        assert abs(sim.energy(final) - complex(g["energy"]).real) < TOL * max(1.0, abs(complex(g["energy"])))
+        if strategy >= 0:
+            assert sim.stat("strategy") == strategy
+        for k, s in enumerate(g["s"]):                 # prefix states phi(s) of the estimator
+            assert rel(sim.evolve(g["coeff"], 0, float(s)), g["phis"][k]) < TOL
+    finally:
+        sim.set_option("strategy", -1)
+
+
+@pytest.mark.parametrize("name", DENSE_REF)
+@pytest.mark.parametrize("strategy", [-1, 0, 2])
+def test_gradient_samples_match_reference_fixture(golden, name, strategy):
+    g = golden(name)
+    sim = sim_from(g)
+    sim.set_option("strategy", strategy)
+    try:
+        grads = sim.grad_samples(g["coeff"], g["s"])
+        assert rel(grads, g["grads"]) < TOL
+    finally:
+        sim.set_option("strategy", -1)
+
+
+def test_diffqc_module_matches_restated_cc(golden):
+    import diffqc
+    g = golden("diffqc_cc_restated")
+    channels, k = [], 0
+    for c in g["chan_counts"]:
+        channels.append([list(g["chan_flat"][k + i]) for i in range(c)])
+        k += c
+    for func_type in (0, 1):
+        diffqc.set_H(g["H0"].tolist(), g["Hs"].tolist(), channels, float(g["duration"]), func_type)
+        for tag, (T0, T) in zip(("fwd", "bwd"), g["spans"]):
+            out = diffqc.trotter(g["psi0"].tolist(), float(T0), float(T), int(g["per_step"]), g["vv"].tolist())
+            assert isinstance(out, list) and isinstance(out[0], complex)
+            assert rel(out, g["f%d_%s" % (func_type, tag)]) < TOL
+            u = dq.diffqc._pulse_table(float(T0), float(T), int(g["per_step"]), g["vv"])
+            np.testing.assert_allclose(u, g["f%d_%s_u" % (func_type, tag)], rtol=1e-12, atol=1e-14)
+    # ndarray arguments are accepted like lists (pybind11 sequence caster)
+    diffqc.set_H(g["H0"], g["Hs"], channels, float(g["duration"]), 1)
+    out = diffqc.trotter(g["psi0"], 0.0, 1.7, 12, g["vv"])
+    assert rel(out, g["f1_fwd"]) < TOL
+    with pytest.raises(ValueError):
+        diffqc.trotter(g["psi0"][:3], 0.0, 1.7, 12, g["vv"])
+    with pytest.raises(ValueError):                      # parameter index outside vv: UB in the reference
+        diffqc.trotter(g["psi0"], 0.0, 1.7, 12, g["vv"][:, :2, :])
+    with pytest.raises(TypeError):
+        diffqc.trotter(g["psi0"], 0.0, 1.7, 12.0, g["vv"])
+
+
+@pytest.mark.parametrize("name", ["split_n4_demo", "split_n6"])
+def test_split_mode_matches_dense_term_product(golden, name):
+    g = golden(name)
+    prob = R.maxcut_structured(int(g["n"]), g["edges"].tolist())
+    H0, Hs, M = R.maxcut_dense(prob)
+    sim = dq.DenseSimulator(H0, Hs, prob["omegas"], prob["T"], M=M, psi0=prob["psi0"], per_step=int(g["per_step"]),
+                            mode="split")
+    final = sim.evolve(g["coeff"], 0, prob["T"])
+    assert rel(final, g["final_dense_product"]) < TOL
+    grads, en = sim.grad_samples(g["coeff"], g["s"][:2], return_energies=True)
+    assert rel(en, g["energies"][:2]) < TOL
+    assert rel(grads, g["grads"][:2]) < TOL
+
+
+@pytest.mark.parametrize("dim,n_H,steps", [(1, 1, 3), (3, 2, 5), (9, 3, 4), (64, 4, 3), (100, 3, 2), (256, 2, 2)])
+def test_random_hermitian_any_dimension(dim, n_H, steps):
+    """dims that are not powers of two (qutrits: 3, 9; padded 100) and larger tiles."""
+    rng = np.random.RandomState(dim)
+
+    def herm():
+        a = rng.normal(size=(dim, dim)) + 1j * rng.normal(size=(dim, dim))
+        return (a + a.conj().T) / (2 * np.sqrt(dim))
+    H0 = herm()
+    Hs = [herm() for _ in range(n_H)]
+    u = rng.uniform(-2, 2, size=(steps, n_H))
+    psi = rng.normal(size=(3, dim)) + 1j * rng.normal(size=(3, dim))
+    psi /= np.linalg.norm(psi, axis=1, keepdims=True)
+    ctx = dq.Context.get(0)
+    for mode, f in (("exact", R.evolve_exact_dense), ("split", R.evolve_split_dense)):
+        out = dq.dense_evolve(ctx, H0, Hs, u, 0.21, psi, mode)
+        for b in range(3):
+            assert rel(out[b], f(H0, Hs, u, 0.21, psi[b])) < TOL
+        assert np.abs(np.linalg.norm(out, axis=1) - 1).max() < 1e-12
+
+
+def test_large_norm_needs_squaring_and_dim_1024_single_step():
+    rng = np.random.RandomState(5)
+    dim = 16
+    a = rng.normal(size=(dim, dim)) + 1j * rng.normal(size=(dim, dim))
+    H0 = (a + a.conj().T) * 3.0
+    psi = np.zeros(dim, dtype=complex); psi[0] = 1
+    ctx = dq.Context.get(0)
+    out = dq.dense_evolve(ctx, H0, np.zeros((0, dim, dim)), np.zeros((2, 0)), 1.0, psi, "exact")
+    assert rel(out, R.evolve_exact_dense(H0, [], np.zeros((2, 0)), 1.0, psi)) < 1e-9     # ||A|| ~ 100
+    dim = 1024
+    d = rng.normal(size=dim)
+    X = np.zeros((dim, dim)); X[np.arange(dim), np.arange(dim) ^ 1] = 1.0
+    psi = rng.normal(size=dim) + 1j * rng.normal(size=dim)
+    psi /= np.linalg.norm(psi)
+    out = dq.dense_evolve(ctx, np.diag(d), [X], np.array([[0.7]]), 0.3, psi, "exact")
+    want = psi.copy().reshape(-1, 2)                      # 2x2 blocks: diag(d0, d1) + 0.7 X, closed form via scipy
+    import scipy.linalg
+    blocks = np.array([scipy.linalg.expm(-0.3j * (np.diag(d[2 * i:2 * i + 2]) + 0.7 * np.array([[0, 1], [1, 0]])))
+                       for i in range(dim // 2)])
+    want = np.einsum("bij,bj->bi", blocks, want).reshape(-1)
+    assert rel(out, want) < TOL
+
+
+class _FakeSim(object):
+    """The attributes of SimulatorPlain that the drop-ins read (sim_plain.py:20-46)."""
+    def __init__(self, g):
+        import torch
+        self.per_step = int(g["per_step"]); self.T = float(g["T"]); self.omegas = list(g["omegas"])
+        self.basis = str(g["basis"]); self.n_basis = int(g["n_basis"]); self.n_Hs = len(g["Hs"])
+        self.spectral_coeff = torch.tensor(g["coeff"], requires_grad=True)
+
+
+def test_solver_hook_and_estimator_dropins(golden):
+    here = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "oracle", "standin")
+    sys.path.insert(0, here)
+    try:
+        import qutip as qp                                  # the stand-in container type (test infrastructure)
+    finally:
+        sys.path.remove(here)
+    g = golden("demo_bspline_ref")
+    sim = _FakeSim(g)
+    H = [qp.Qobj(g["H0"])] + [[qp.Qobj(g["Hs"][i]),
+                               (lambda i: lambda t, args: R.u_plain(i, t, g["coeff"], g["omegas"], sim.T))(i)]
+                              for i in range(sim.n_Hs)]
+    solver = dq.solver_for(sim)
+    out = solver(H, qp.Qobj(g["psi0"]), 0, sim.T)
+    assert isinstance(out, qp.Qobj) and out.shape == (16, 1)
+    assert rel(out.full().reshape(-1), g["final"]) < TOL
+    est = dq.estimator_for(sim)
+    for k in range(2):
+        np.random.seed(1000 + k)                             # the stream position make_golden used
+        grad = est(qp.Qobj(g["M"]), H, qp.Qobj(g["psi0"]))
+        assert str(grad.dtype) == "torch.float64" and tuple(grad.shape) == g["coeff"].shape
+        assert rel(grad.numpy(), g["grads"][k]) < TOL
+
+
+def test_dense_errors_are_python_exceptions():
+    ctx = dq.Context.get(0)
+    H0 = np.eye(4)
+    with pytest.raises(ValueError):
+        dq.dense_evolve(ctx, H0, [np.eye(4)], np.array([[np.nan]]), 0.1, np.ones(4) / 2, "exact")
+    with pytest.raises(ValueError):
+        dq.dense_evolve(ctx, np.eye(2000), [], np.zeros((1, 0)), 0.1, np.ones(2000), "exact")
