@@ -9,5 +9,6 @@ from ._lib import Context, DiffqcError, load  # noqa: F401
 from .ising import IsingProblem, IsingSimulator  # noqa: F401
 from .dense import DenseSimulator, dense_evolve, estimator_for, solver_for  # noqa: F401
 from . import diffqc, sharding  # noqa: F401
+from .training import EnergyTrainer  # noqa: F401
 
 __version__ = "dev"

@@ -46,6 +46,11 @@ SIGNATURES = {
     "dq_ising_grad_run_staged": (ctypes.c_int, [_VP]),
     "dq_ising_grad_fetch": (ctypes.c_int, [_VP, _VP]),
     "dq_ising_last_stat": (ctypes.c_int, [_VP, ctypes.c_char_p, ctypes.POINTER(ctypes.c_double)]),
+    "dq_slice_fill_uniform": (ctypes.c_int, [_VP, _VP, ctypes.c_int, ctypes.c_int]),
+    "dq_slice_phase": (ctypes.c_int, [_VP, _VP, ctypes.c_int, ctypes.c_uint64, ctypes.c_int, ctypes.c_int, _VP, _VP]),
+    "dq_slice_rx": (ctypes.c_int, [_VP, _VP, ctypes.c_int, ctypes.c_int, ctypes.c_double]),
+    "dq_slice_energy": (ctypes.c_int, [_VP, _VP, ctypes.c_int, ctypes.c_uint64, ctypes.c_int, ctypes.c_int, _VP, _VP,
+                                       ctypes.c_double, ctypes.POINTER(ctypes.c_double)]),
     "dq_microbench": (ctypes.c_int, [_VP, ctypes.c_int, ctypes.c_int64, ctypes.c_int,
                                      ctypes.POINTER(ctypes.c_double)]),
 }

@@ -74,6 +74,8 @@ namespace dq { namespace dense { struct State; } }
 struct dq_context {
     dq::dense::State* dense = nullptr;     // dense-path state (diffqc.set_H globals + workspaces), lazily created
     int dense_force_strategy = -1;         // tests: -1 auto, 0 block-Taylor, 1 per-step propagator, 2 chained
+    void* slice_ring = nullptr;            // slice.cu: ring of small device argument tables
+    unsigned slice_cursor = 0;
     int device = 0;
     cudaStream_t stream = nullptr;
     cudaDeviceProp prop;

@@ -61,6 +61,7 @@ int dq_context_destroy(dq_context* ctx) {
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     dq::dense::release(ctx);
+    if (ctx->slice_ring) cudaFree(ctx->slice_ring);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
     return DQ_OK;

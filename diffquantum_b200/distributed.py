@@ -1,0 +1,185 @@
+"""One state vector distributed over the GPUs of a box on its high-order qubits (BASELINE
+configs[4]: n = 32 is 64 GiB of complex128 — 8 GiB per B200 at 8 ranks).
+
+Layout.  World size W = 2^g; rank r owns the 2^L amplitudes (L = n - g) whose global basis index has
+top g bits equal to r.  In the reference order qubit q sits on index bit n-1-q (demo_maxcut.py:49-57),
+so qubits 0..g-1 start out "global".  `pos[q]` tracks the current physical bit of every qubit.
+
+Step (per-term product, diffqc.cc:155-164).  The diagonal phase is local in any layout (the kernel is
+told where each ZZ endpoint currently sits).  X rotations commute, so a step rotates every qubit that
+is local, then ONE all-to-all swaps index bits [L-g, L) with the rank bits — because those are the top
+local bits, every rank's send chunks are contiguous and `all_to_all_single` needs no packing — and the
+g qubits that just became local are rotated.  The next step starts from the swapped layout and swaps
+back: one exchange of (W-1)/W of the slice per step, no other traffic.  Energies are reduced with one
+all-reduce of a scalar.
+
+The device work is the C ABI's dq_slice_* kernels; `ops` exists so that the CPU tests can drive the same
+bookkeeping over gloo with a NumPy stand-in for the kernels (tests/test_distributed_state.py).
+"""
+import ctypes
+
+import numpy as np
+
+from . import _lib
+from .sharding import dist_info
+
+
+class CudaSliceOps(object):
+    """Slice kernels through the C ABI; buffers are torch CUDA tensors (device memory + NCCL only)."""
+
+    def __init__(self, device=0):
+        import torch
+        self.torch = torch
+        self.device = torch.device("cuda", device)
+        self.ctx = _lib.Context.get(device)
+        self.lib = _lib.load()
+
+    def alloc(self, n_amps):
+        return self.torch.empty(n_amps, dtype=self.torch.complex128, device=self.device)
+
+    def _p(self, t):
+        return ctypes.c_void_p(t.data_ptr())
+
+    def fill_uniform(self, psi, L, n):
+        _lib.check(self.lib.dq_slice_fill_uniform(self.ctx.handle, self._p(psi), L, n))
+
+    def phase(self, psi, L, high, n, pair_bits, angles):
+        pair_bits = np.ascontiguousarray(pair_bits, dtype=np.int32)
+        angles = np.ascontiguousarray(angles, dtype=np.float64)
+        _lib.check(self.lib.dq_slice_phase(self.ctx.handle, self._p(psi), L, high, n, len(pair_bits), _lib.ptr(pair_bits),
+                                           _lib.ptr(angles)))
+
+    def rx(self, psi, L, bit, theta):
+        _lib.check(self.lib.dq_slice_rx(self.ctx.handle, self._p(psi), L, int(bit), float(theta)))
+
+    def energy(self, psi, L, high, n, pair_bits, m_zz, m_const):
+        pair_bits = np.ascontiguousarray(pair_bits, dtype=np.int32)
+        m_zz = np.ascontiguousarray(m_zz, dtype=np.float64)
+        v = ctypes.c_double()
+        _lib.check(self.lib.dq_slice_energy(self.ctx.handle, self._p(psi), L, high, n, len(pair_bits), _lib.ptr(pair_bits),
+                                            _lib.ptr(m_zz), float(m_const), ctypes.byref(v)))
+        return v.value
+
+    def all_to_all(self, recv, send):
+        import torch.distributed as dist
+        self.ctx.synchronize()                      # kernels run on the library's stream, NCCL on torch's
+        dist.all_to_all_single(self.torch.view_as_real(recv), self.torch.view_as_real(send))
+        self.torch.cuda.current_stream(self.device).synchronize()
+
+    def all_reduce_scalar(self, x):
+        import torch.distributed as dist
+        t = self.torch.tensor([x], dtype=self.torch.float64, device=self.device)
+        dist.all_reduce(t)
+        return float(t.item())
+
+    def to_host(self, psi):
+        self.ctx.synchronize()
+        return psi.cpu().numpy()
+
+    def from_host(self, psi, array):
+        self.ctx.synchronize()
+        psi.copy_(self.torch.from_numpy(np.ascontiguousarray(array, dtype=np.complex128)))
+        self.torch.cuda.current_stream(self.device).synchronize()
+
+
+class DistributedState(object):
+    """The slice of one n-qubit state owned by this rank, plus the qubit -> physical-bit map."""
+
+    def __init__(self, problem, device=0, per_step=10, basis="BSpline", ops=None):
+        self.problem = problem
+        self.per_step = per_step
+        self.basis = basis
+        self.rank, self.world, _ = dist_info()
+        g = self.world.bit_length() - 1
+        if (1 << g) != self.world:
+            raise ValueError("world size %d is not a power of two" % self.world)
+        self.g = g
+        self.n = problem.n
+        self.L = self.n - g
+        if self.L < max(1, g):
+            raise ValueError("%d qubits cannot be split over %d ranks" % (self.n, self.world))
+        self.ops = ops if ops is not None else CudaSliceOps(device)
+        self.psi = self.ops.alloc(1 << self.L)
+        self.recv = self.ops.alloc(1 << self.L) if g else None
+        self.pos = [self.n - 1 - q for q in range(self.n)]
+        self.exchanges = 0
+        self.exchanged_bytes = 0
+
+    # -- layout ------------------------------------------------------------------------------------
+    def pair_bits(self):
+        return np.array([[self.pos[a], self.pos[b]] for a, b in self.problem.zz_pairs], dtype=np.int32).reshape(-1, 2)
+
+    def global_qubits(self):
+        return [q for q in range(self.n) if self.pos[q] >= self.L]
+
+    def swap_global_local(self):
+        """All-to-all that exchanges index bits [L-g, L) with the rank bits [L, n)."""
+        if self.g == 0:
+            return
+        self.ops.all_to_all(self.recv, self.psi)
+        self.psi, self.recv = self.recv, self.psi
+        L, g = self.L, self.g
+        for q in range(self.n):
+            if L - g <= self.pos[q] < L:
+                self.pos[q] += g
+            elif self.pos[q] >= L:
+                self.pos[q] -= g
+        self.exchanges += 1
+        self.exchanged_bytes += 16 * (1 << L) * (self.world - 1) // self.world
+
+    def restore_layout(self):
+        if self.pos != [self.n - 1 - q for q in range(self.n)]:
+            self.swap_global_local()
+
+    # -- evolution -----------------------------------------------------------------------------------
+    def fill_uniform(self):
+        """The demo's start state (demo_maxcut.py:12-17)."""
+        self.restore_layout()
+        self.ops.fill_uniform(self.psi, self.L, self.n)
+
+    def set_state(self, full_state):
+        """Tests: load this rank's slice of a host state given in the reference order."""
+        self.restore_layout()
+        N = 1 << self.L
+        self.ops.from_host(self.psi, np.asarray(full_state).reshape(-1)[self.rank * N:(self.rank + 1) * N])
+
+    def step(self, row):
+        """One product-formula step from an angle row [c | zz angles | x angle per qubit] (already x dt)."""
+        p = self.problem
+        row = np.asarray(row, dtype=np.float64)
+        x = row[1 + p.n_zz:]
+        self.ops.phase(self.psi, self.L, self.rank, self.n, self.pair_bits(), row[:1 + p.n_zz])
+        was_global = self.global_qubits()
+        for q in range(self.n):
+            if self.pos[q] < self.L:
+                self.ops.rx(self.psi, self.L, self.pos[q], x[q])
+        if was_global:
+            self.swap_global_local()
+            for q in was_global:
+                self.ops.rx(self.psi, self.L, self.pos[q], x[q])
+
+    def evolve_rows(self, rows):
+        for row in np.asarray(rows, dtype=np.float64).reshape(-1, self.problem.row_len):
+            self.step(row)
+
+    def evolve(self, coeff, T0, T1):
+        """SimulatorPlain.trotter's step grid (sim_plain.py:123-150) with the product-formula step."""
+        self.evolve_rows(self.problem.trajectory_rows(coeff, T0, T1, self.per_step, self.basis))
+
+    def energy(self):
+        """<psi|M|psi> for the problem's diagonal observable, summed over ranks."""
+        p = self.problem
+        if p.m_diag is not None:
+            raise NotImplementedError("distributed energies need the observable in ZZ form (m_zz, m_const)")
+        part = self.ops.energy(self.psi, self.L, self.rank, self.n, self.pair_bits(), p.m_zz, p.m_const)
+        return self.ops.all_reduce_scalar(part) if self.world > 1 else part
+
+    def norm2(self):
+        zero = np.zeros(self.problem.n_zz)
+        part = self.ops.energy(self.psi, self.L, self.rank, self.n, self.pair_bits(), zero, 1.0)
+        return self.ops.all_reduce_scalar(part) if self.world > 1 else part
+
+    def local_slice(self):
+        """This rank's amplitudes in the reference order (restores the layout first)."""
+        self.restore_layout()
+        return self.ops.to_host(self.psi)

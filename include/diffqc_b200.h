@@ -141,6 +141,22 @@ int dq_ising_grad_fetch(dq_ising* p, double* energies_out);     /* synchronises,
  * "pass_kernel_ms" / "pass_kernel_launches" (event-timed fused pass kernel; needs time_launches=1). */
 int dq_ising_last_stat(dq_ising* p, const char* name, double* value);
 
+/* ---- one state distributed over ranks on its high-order index bits (BASELINE configs[4]) -------------
+ * A rank owns 2^L consecutive amplitudes (device pointer, interleaved c128); the global basis index of
+ * local x is (high_bits << L) | x.  pair_bits are the CURRENT physical bit positions (0 = least
+ * significant bit of the global index) of each ZZ pair; the host tracks them across the global<->local
+ * qubit swaps it performs with an NCCL all-to-all (diffquantum_b200/distributed.py).  Asynchronous on
+ * the context stream except dq_slice_energy.  Step semantics: diffqc.cc:155-164. */
+int dq_slice_fill_uniform(dq_context* ctx, void* psi_dev, int L, int n_total);
+/* psi[x] *= exp(-i (angles[0] + sum_e angles[1+e] z_a z_b)) */
+int dq_slice_phase(dq_context* ctx, void* psi_dev, int L, uint64_t high_bits, int n_total, int n_zz,
+                   const int32_t* pair_bits, const double* angles);
+/* exp(-i theta X) on local bit `bit` < L */
+int dq_slice_rx(dq_context* ctx, void* psi_dev, int L, int bit, double theta);
+/* this rank's part of <psi| m_const + sum_e m_zz[e] Z_a Z_b |psi> (sim_plain.py:205,215,281) */
+int dq_slice_energy(dq_context* ctx, const void* psi_dev, int L, uint64_t high_bits, int n_total, int n_zz,
+                    const int32_t* pair_bits, const double* m_zz, double m_const, double* partial_out);
+
 /* ---- micro-benchmarks used by bench.py/profiles to calibrate the roofline --------------------- */
 /* kind: 0 = device copy GB/s over `bytes`, 1 = FP64 FMA TFLOP/s, 2 = L2-resident read+write GB/s. */
 int dq_microbench(dq_context* ctx, int kind, int64_t bytes, int iters, double* result);

@@ -182,3 +182,30 @@ def test_dense_errors_are_python_exceptions():
         dq.dense_evolve(ctx, H0, [np.eye(4)], np.array([[np.nan]]), 0.1, np.ones(4) / 2, "exact")
     with pytest.raises(ValueError):
         dq.dense_evolve(ctx, np.eye(2000), [], np.zeros((1, 0)), 0.1, np.ones(2000), "exact")
+
+
+def test_demo_maxcut_training_follows_the_reference_run(golden):
+    """configs[0]: demo_maxcut.py as shipped (202 epochs, np.random.seed(0)).  The fixture holds the
+    reference's own loss trajectory, final coefficients and printed cut (oracle/make_golden.py)."""
+    g = golden("demo_training_ref")
+    sim = dq.DenseSimulator(g["H0"], g["Hs"], g["omegas"], float(g["T"]), M=g["H_cost"], psi0=g["psi0"], per_step=10)
+    tr = dq.EnergyTrainer(sim, n_basis=6, n_epoch=202, lr=2e-2)
+    np.random.seed(0)
+    coeff = tr.train_energy().detach().numpy()
+    losses = np.array(tr.losses_energy)
+    assert np.abs(losses - g["losses_energy"]).max() < 1e-8          # 202 Adam steps amplify 1e-14 differences
+    assert rel(coeff, g["final_coeff"]) < 1e-8
+    state, prob = tr.find_state()
+    assert state == int(g["cut_state"]) and bin(state)[2:] == str(g["stdout_tail"]).split()[-1]
+    np.testing.assert_allclose(prob, g["prob"], atol=1e-8)
+
+
+def test_structured_training_reaches_a_maximum_cut():
+    """Same demo through the product-formula engine (sanity, not parity: split != exact at O(dt))."""
+    prob = dq.IsingProblem.maxcut(4, [[0, 1], [0, 3], [1, 2], [2, 3]])
+    sim = dq.IsingSimulator(prob, per_step=10)
+    tr = dq.EnergyTrainer(sim, n_basis=6, n_epoch=202, lr=2e-2, ground_energy=-4.0)
+    np.random.seed(0)
+    tr.train_energy()
+    state, _ = tr.find_state()
+    assert state in (0b0101, 0b1010) and tr.losses_energy[-1] < 0.05
