@@ -292,6 +292,14 @@ def run_b200_arm(a):
     barrier()
     gpu_launches = sim.ctx.launch_count - launches0
     clk = clocks.stop()
+    per_rank = None
+    if world > 1:
+        import torch.distributed as dist
+        mine = torch.tensor([sum(dev_ms), kern_ms, traj_steps, float(gpu_launches)], dtype=torch.float64, device=dev)
+        allr = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(allr, mine)
+        per_rank = [{"rank": r, "device_ms": float(t[0]), "pass_kernel_ms": float(t[1]), "trajectory_steps": float(t[2]),
+                     "launches": int(t[3])} for r, t in enumerate(allr)]
     t_value = max_over_ranks(sum(dev_ms) * 1e-3)
     total_samples = a.samples_per_step * world * a.steps
     value = total_samples / t_value
@@ -355,6 +363,8 @@ def run_b200_arm(a):
                         "energies + gradient assembly + all-reduce"},
         "gpu_launches": int(gpu_launches), "roofline": roofline, "clocks": clk,
     }
+    if per_rank:
+        line["per_rank"] = per_rank
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
         try:
             s0 = step_samples(a.warmup, a.samples_per_step, 1, prob.T)[0]
