@@ -53,6 +53,7 @@ def parse_args():
                     help="controls whose +/- trajectories the bounded CPU sample runs (of n_Hs)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--ket-group", type=int, default=0)
+    ap.add_argument("--engine", type=int, default=1, help="1 fused v2 (32 amps/thread), 2 fused v3 (16 amps/thread)")
     return ap.parse_args()
 
 
@@ -249,11 +250,12 @@ def run_b200_arm(a):
 
     edges, coeff = workload(a.n)
     prob = dq.IsingProblem.maxcut(a.n, edges)
-    sim = dq.IsingSimulator(prob, device=local, per_step=a.per_step, engine=1)
+    sim = dq.IsingSimulator(prob, device=local, per_step=a.per_step, engine=a.engine)
     if a.ket_group:
         sim.set_option("ket_group", a.ket_group)
-    if sim.info("engine") != 1:
-        raise RuntimeError("fused engine not available for n=%d" % a.n)
+    if sim.info("engine") != a.engine:
+        raise RuntimeError("fused engine %d not available for n=%d" % (a.engine, a.n))
+    kernel_name = "k_f16_passes" if a.engine == 2 else "k_fused_passes"
     n_H = len(prob.terms)
     stream = torch.cuda.ExternalStream(sim.ctx.stream, device=dev)
     flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
@@ -342,7 +344,7 @@ def run_b200_arm(a):
                 ratio, tj.get("kernel", "k_fused_passes"), tj.get("source", "profiles/"))
         except Exception:
             traffic = None
-    roofline = {"bound": "hbm", "kernel": "k_fused_passes", "achieved": achieved, "peak": peak, "unit": "GB/s",
+    roofline = {"bound": "hbm", "kernel": kernel_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": (achieved / peak) if achieved else None, "peak_source": peak_src, "traffic": traffic,
                 "traffic_note": tnote,
                 "alg_bytes_per_launch": alg_bytes / kern_launches if kern_launches else None,

@@ -14,8 +14,8 @@ struct dq_ising {
     dq::DevBuf mdiag;              // double[2^n], physical order
     dq::DevBuf pairs_dev;          // int2[n_zz] physical bit positions
 
-    int engine = 1;                // 0 generic, 1 fused (n >= 12)
-    int ket_group = 4;             // states per fused launch (L2 residency)
+    int engine = 1;                // 0 generic, 1 fused v2 (32 amplitudes/thread, default), 2 fused v3 (16 amplitudes/thread); 12 <= n <= 20
+    int ket_group = 5;             // states per fused launch (L2 residency; 5 x 16 MiB measured best at n = 20)
     int grid_per_sm = 0;           // experiment knob: CTAs per SM in the persistent grid (0 = occupancy)
     int time_launches = 0;         // 1: CUDA-event pairs around every pass-kernel launch (bench.py's roofline)
 
@@ -61,4 +61,12 @@ int fused_launch_times(dq_ising* p, double* total_ms, double* n_launches);
 int fused_grad_run(dq_ising* p);
 int fused_evolve(dq_ising* p, c128* d_states, int batch, const double* h_rows, int n_steps,
                  double* d_energies, bool want_states);
+
+// fused persistent engine v3 (ising_f16.cu): 16 amplitudes per thread, 16 warps per SM
+int f16_supported(const dq_ising* p);
+void f16_release(dq_ising* p);
+int f16_launch_times(dq_ising* p, double* total_ms, double* n_launches);
+int f16_grad_run(dq_ising* p);
+int f16_evolve(dq_ising* p, c128* d_states, int batch, const double* h_rows, int n_steps,
+               double* d_energies, bool want_states);
 }  // namespace dq

@@ -27,12 +27,13 @@ def rel(a, b):
 
 
 @pytest.mark.parametrize("name", ["split_n4_demo", "split_n6", "split_n8", "split_n12"])
-@pytest.mark.parametrize("engine", [0, 1])
+@pytest.mark.parametrize("engine", [0, 1, 2])
 def test_split_golden_fixture(golden, name, engine):
     g = golden(name)
     n = int(g["n"])
     prob = dq.IsingProblem.maxcut(n, g["edges"].tolist())
     sim = dq.IsingSimulator(prob, per_step=int(g["per_step"]), engine=engine)
+    assert sim.info("engine") == (engine if n >= 12 else 0)        # the fused engines need a 2^12 tile
     psi, en = sim.evolve(g["coeff"], 0, prob.T)
     assert rel(psi[0], g["final"]) < TOL
     assert abs(en[0] - float(g["energy"])) < TOL * abs(float(g["energy"]))
@@ -42,7 +43,9 @@ def test_split_golden_fixture(golden, name, engine):
 
 
 @pytest.mark.parametrize("n,per_step,engine", [(1, 5, 0), (2, 5, 0), (3, 4, 0), (10, 3, 0), (13, 3, 1),
-                                               (14, 2, 1), (16, 1, 1), (16, 1, 0)])
+                                               (14, 2, 1), (16, 1, 1), (16, 1, 0), (20, 1, 1), (19, 1, 1), (12, 3, 2), (13, 3, 2),
+                                               (14, 2, 2), (15, 2, 2), (16, 1, 2), (17, 1, 2), (18, 1, 2),
+                                               (19, 1, 2), (20, 1, 2)])
 def test_evolve_vs_oracle_live(n, per_step, engine):
     edges = graph_for(n)
     prob = dq.IsingProblem.maxcut(n, edges)
@@ -120,3 +123,23 @@ def test_norm_is_preserved_and_errors_are_python_exceptions():
         sim.evolve_rows(rows)
     with pytest.raises(ValueError):
         dq.IsingProblem(3, [("zz", 0, 3)], [1.0], 1.0)
+
+
+@pytest.mark.parametrize("n,engine", [(12, 2), (15, 2), (17, 2), (20, 2), (16, 1)])
+def test_fused_gradients_agree_with_generic_engine(n, engine):
+    """Every shifted ket (each ZZ pair and each X qubit, both signs) through the fused passes vs the
+    one-kernel-per-term engine on the same device; the generic engine is pinned to the oracle above."""
+    edges = graph_for(n)
+    prob = dq.IsingProblem.maxcut(n, edges)
+    coeff = np.random.RandomState(100 + n).normal(0, 1, [len(prob.terms), 6])
+    s_list = [0.41, 1.63]
+    ref = dq.IsingSimulator(prob, per_step=2, engine=0).shifted_energies(coeff, s_list)
+    sim = dq.IsingSimulator(prob, per_step=2, engine=engine)
+    assert sim.info("engine") == engine
+    got = sim.shifted_energies(coeff, s_list)
+    assert rel(got, ref) < TOL
+    # large angles force the unscaled (cos, sin) butterflies
+    big = coeff * 6.0
+    sim2 = dq.IsingSimulator(prob, per_step=1, engine=engine)
+    ref2 = dq.IsingSimulator(prob, per_step=1, engine=0).shifted_energies(big, s_list[:1])
+    assert rel(sim2.shifted_energies(big, s_list[:1]), ref2) < TOL

@@ -14,7 +14,7 @@ np.random.seed(1)
 s_list = np.random.uniform(size=B) * prob.T
 res = []
 base = None
-for engine, G in [(0, 1)] + [(1, g) for g in (1, 2, 3, 4, 5, 6, 8, 12)]:
+for engine, G in [(0, 1)] + [(e, g) for e in (1, 2) for g in (2, 3, 4, 5, 6, 8)]:
     if engine == 0 and os.environ.get("SKIP_GENERIC"):
         continue
     sim = dq.IsingSimulator(prob, per_step=10, engine=engine, ket_group=G)
