@@ -265,35 +265,45 @@ def run_b200_arm(a):
         return sharding.shard(step_samples(i, a.samples_per_step, world, prob.T), rank, world)
 
     # ---- value: tables staged in HBM, device-timed ----------------------------------------------
-    sim.set_option("time_launches", 1)
-    dev_ms, alg_bytes, traj_steps, kern_ms, kern_launches = [], 0.0, 0.0, 0.0, 0.0
-    clocks = None
-    launches0 = None
-    for i in range(a.warmup + a.steps):
-        timed = i >= a.warmup
-        if i == a.warmup:
-            barrier()
-            clocks = ClockSampler(local)
-            launches0 = sim.ctx.launch_count
-        sim.stage(coeff, my_samples(i))              # H2D of the angle tables: outside the timed region
-        flush.zero_()
-        torch.cuda.synchronize(dev)
-        e0 = torch.cuda.Event(enable_timing=True)
-        e1 = torch.cuda.Event(enable_timing=True)
-        e0.record(stream)
-        sim.run_staged()
-        e1.record(stream)
-        e1.synchronize()
-        en = sim.fetch()
-        if timed:
-            dev_ms.append(e0.elapsed_time(e1))
-            alg_bytes += sim.stat("alg_bytes")
-            traj_steps += sim.stat("steps")
-            kern_ms += sim.stat("pass_kernel_ms")
-            kern_launches += sim.stat("pass_kernel_launches")
-    barrier()
-    gpu_launches = sim.ctx.launch_count - launches0
-    clk = clocks.stop()
+    def staged_loop(linear):
+        """K timed steps of run_staged (W untimed before); returns device ms per step, counters, clocks."""
+        sim.set_option("linear", 1 if linear else 0)
+        sim.set_option("time_launches", 1)
+        r = dict(dev_ms=[], alg_bytes=0.0, traj_steps=0.0, kern_ms=0.0, kern_launches=0.0, clocks=None, launches=0, en=None)
+        sampler = None
+        l0 = 0
+        for i in range(a.warmup + a.steps):
+            timed = i >= a.warmup
+            if i == a.warmup:
+                barrier()
+                sampler = ClockSampler(local)
+                l0 = sim.ctx.launch_count
+            sim.stage(coeff, my_samples(i))              # H2D of the angle tables: outside the timed region
+            flush.zero_()
+            torch.cuda.synchronize(dev)
+            e0 = torch.cuda.Event(enable_timing=True)
+            e1 = torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            sim.run_staged()
+            e1.record(stream)
+            e1.synchronize()
+            r["en"] = sim.fetch()
+            if timed:
+                r["dev_ms"].append(e0.elapsed_time(e1))
+                r["alg_bytes"] += sim.stat("alg_bytes")
+                r["traj_steps"] += sim.stat("steps")
+                r["kern_ms"] += sim.stat("pass_kernel_ms")
+                r["kern_launches"] += sim.stat("pass_kernel_launches")
+        barrier()
+        r["launches"] = sim.ctx.launch_count - l0
+        r["clocks"] = sampler.stop()
+        sim.set_option("time_launches", 0)
+        sim.set_option("linear", 0)
+        return r
+
+    lit = staged_loop(False)
+    dev_ms, alg_bytes, traj_steps = lit["dev_ms"], lit["alg_bytes"], lit["traj_steps"]
+    kern_ms, kern_launches, gpu_launches, clk, en = lit["kern_ms"], lit["kern_launches"], lit["launches"], lit["clocks"], lit["en"]
     per_rank = None
     if world > 1:
         import torch.distributed as dist
@@ -305,6 +315,18 @@ def run_b200_arm(a):
     t_value = max_over_ranks(sum(dev_ms) * 1e-3)
     total_samples = a.samples_per_step * world * a.steps
     value = total_samples / t_value
+    linear_leg = None
+    if a.engine == 1:
+        lin = staged_loop(True)
+        t_lin = max_over_ranks(sum(lin["dev_ms"]) * 1e-3)
+        dmax = float(np.abs(lin["en"] - en).max() / np.abs(en).max())
+        linear_leg = {"value": total_samples / t_lin, "unit": UNIT, "ms_per_step": 1e3 * t_lin / a.steps,
+                      "trajectory_steps_per_s": sum_over_ranks(lin["traj_steps"]) / t_lin,
+                      "pass_kernel_GBs": lin["alg_bytes"] / (lin["kern_ms"] * 1e-3) / 1e9 if lin["kern_ms"] else None,
+                      "max_rel_diff_of_shifted_energies_vs_literal": dmax,
+                      "note": "NOT the headline: same per-sample outputs from n_Hs+1 suffix trajectories instead of 2*n_Hs "
+                              "(ket- = 2 U phi/sqrt(1+r^2) - ket+ by linearity of the evolution); `value` above evolves "
+                              "both shifted kets of every control literally as sim_plain.py:196-215 does"}
     sim.set_option("time_launches", 0)
     last_energies = en
 
@@ -367,6 +389,8 @@ def run_b200_arm(a):
     }
     if per_rank:
         line["per_rank"] = per_rank
+    if linear_leg:
+        line["linear_estimator"] = linear_leg
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
         try:
             s0 = step_samples(a.warmup, a.samples_per_step, 1, prob.T)[0]

@@ -17,6 +17,7 @@ struct dq_ising {
     int engine = 1;                // 0 generic, 1 fused v2 (32 amplitudes/thread, default), 2 fused v3 (16 amplitudes/thread); 12 <= n <= 20
     int ket_group = 5;             // states per fused launch (L2 residency; 5 x 16 MiB measured best at n = 20)
     int grid_per_sm = 0;           // experiment knob: CTAs per SM in the persistent grid (0 = occupancy)
+    int linear = 0;                // 1: estimator by linearity (n_H + 1 suffix trajectories per sample instead of 2 n_H)
     int time_launches = 0;         // 1: CUDA-event pairs around every pass-kernel launch (bench.py's roofline)
 
     // work buffers

@@ -90,6 +90,8 @@ int dq_ising_set_option(dq_ising* p, const char* name, int64_t value) {
         p->engine = (int)value;
     } else if (!strcmp(name, "grid_per_sm")) {
         p->grid_per_sm = (int)value;
+    } else if (!strcmp(name, "linear")) {
+        p->linear = value != 0;
     } else if (!strcmp(name, "time_launches")) {
         p->time_launches = value != 0;
     } else if (!strcmp(name, "ket_group")) {
@@ -300,7 +302,9 @@ int dq_ising_grad_run_staged(dq_ising* p) {
             DQ_TRY(dq::gen_energy(p, p->states.as<c128>(), kets, p->energies.as<double>() + (size_t)b * kets));
         }
     }
-    for (int b = 0; b < s.n_samples; ++b) steps += s.prefix_steps[b] + (double)kets * s.suffix_steps[b];
+    const bool lin = p->linear && use_fused(p);
+    for (int b = 0; b < s.n_samples; ++b)
+        steps += s.prefix_steps[b] + (double)(lin ? s.n_shift + 1 : kets) * s.suffix_steps[b];
     p->stat_steps = steps;
     p->stat_alg_bytes = steps * 2.0 * sizeof(c128) * N;
     p->stat_launches = (double)(p->ctx->launches - l0);

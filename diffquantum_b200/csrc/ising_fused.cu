@@ -93,6 +93,10 @@ struct KetDesc {
     int sb0, sb1;
     int cls;                        // pass type of its pass 0 (0 = L first, 1 = H first)
     int pad_;
+    const c128* cross;              // linear mode: final state a = U phi; the energy pass also reduces Re <a|M|ket>
+    double* partial2;               // [tiles] partials of that cross term
+    double escale2;
+    double pad2_;
 };
 
 struct SetupJob {
@@ -241,6 +245,7 @@ __device__ __forceinline__ void prefetch_tables(const PassStep* __restrict__ ps,
 struct Shared {
     ItemInfo info[2];
     double red[2][kThreads / 32];   // energy partials of the item in slot `cur` (consumed one item later)
+    double red2[2][kThreads / 32];  // cross-term partials (linear mode)
 };
 
 // Completion of an item is published one half-item late: thread 0 keeps the record here and releases it
@@ -248,7 +253,8 @@ struct Shared {
 // ago and the fence returns at once.  (Measured: a fence directly after the stores cost ~25% of the kernel.)
 struct Pending {
     double* partial;                // where to write the energy partial (NULL = none)
-    double escale;
+    double* partial2;               // cross-term partial (NULL = none)
+    double escale, escale2;
     int g;                          // ket whose counter is bumped, -1 = nothing pending
     int slot;                       // sh.red slot
 };
@@ -256,6 +262,7 @@ struct Pending {
 __device__ __forceinline__ void flush_pending(const LaunchArgs& A, Shared& sh, Pending& pd) {
     if (pd.g < 0) return;
     if (pd.partial) *pd.partial = (sh.red[pd.slot][0] + sh.red[pd.slot][1] + sh.red[pd.slot][2] + sh.red[pd.slot][3]) * pd.escale;
+    if (pd.partial2) *pd.partial2 = (sh.red2[pd.slot][0] + sh.red2[pd.slot][1] + sh.red2[pd.slot][2] + sh.red2[pd.slot][3]) * pd.escale2;
     asm volatile("fence.acq_rel.gpu;" ::: "memory");
     atomicAdd(&A.counters[1 + pd.g], 1u);
     pd.g = -1;
@@ -264,7 +271,7 @@ __device__ __forceinline__ void flush_pending(const LaunchArgs& A, Shared& sh, P
 // Everything between "the tile is in shared memory" and "the tile is stored / reduced" for one pass type.
 // `nxt_raw` is the raw index of the following item (valid in thread 0 only); thread 0 turns it into
 // sh.info[nb] half-way through so that every thread can start prefetching that tile in outer-B.
-template <bool SCALED, bool AJ, int TYPE>
+template <bool SCALED, bool AJ, bool CROSS, int TYPE>
 __device__ __forceinline__ void process_tile(const LaunchArgs& A, const KetDesc* __restrict__ kd, const PassStep& P,
                                              c128* __restrict__ tile, Shared& sh, const int p, const int t_id,
                                              const unsigned nxt_raw, const int nb, const unsigned total,
@@ -411,6 +418,15 @@ __device__ __forceinline__ void process_tile(const LaunchArgs& A, const KetDesc*
     // ---- outer-B : K-bit rotations of the new step; prefetch of the next tile; store or reduce --------
 #pragma unroll
     for (int j = 0; j < kRegs; ++j) if (!(DQ_EXP & 2)) v[j] = tile[G::swz(iK | (j << G::k0))];
+    if (flags & F_ENERGY) {                  // energy pass: pull the observable (and the cross state) towards L1 now
+        const double* __restrict__ mdp = A.mdiag + xK;
+#pragma unroll
+        for (int j = 0; j < kRegs; ++j) {
+            const size_t o = TYPE == 0 ? (size_t)(j << G::k0) : (size_t)T.offK[j];
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(mdp + o));
+            if (CROSS && kd->cross) asm volatile("prefetch.global.L2 [%0];" ::"l"(kd->cross + xK + o));
+        }
+    }
     rot_bit<SCALED, 0>(v, P.rot[3][0]);      // every slot of this thread has now been consumed ...
     {
         const ItemInfo& N = sh.info[nb];
@@ -443,7 +459,8 @@ __device__ __forceinline__ void process_tile(const LaunchArgs& A, const KetDesc*
         const bool do_store = (flags & F_STORE) != 0, do_energy = (flags & F_ENERGY) != 0;
         c128* __restrict__ dst = kd->buf + xK;
         const double* __restrict__ md = A.mdiag + xK;
-        double e = 0.0;
+        const c128* __restrict__ cr = (CROSS && do_energy && kd->cross) ? kd->cross + xK : nullptr;
+        double e = 0.0, e2 = 0.0;
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
             const c128 a = v[j], b = v[j + 16];
@@ -463,13 +480,23 @@ __device__ __forceinline__ void process_tile(const LaunchArgs& A, const KetDesc*
                 else { __stcg(dst + o0, na); __stcg(dst + o1, nbv); }
             }
             if (do_energy) {
-                e = fma(__ldg(md + o0), fma(na.x, na.x, na.y * na.y), e);
-                e = fma(__ldg(md + o1), fma(nbv.x, nbv.x, nbv.y * nbv.y), e);
+                const double m0 = __ldg(md + o0), m1 = __ldg(md + o1);
+                e = fma(m0, fma(na.x, na.x, na.y * na.y), e);
+                e = fma(m1, fma(nbv.x, nbv.x, nbv.y * nbv.y), e);
+                if (CROSS && cr) {               // Re conj(a) ket
+                    const c128 a0 = __ldcg(cr + o0), a1 = __ldcg(cr + o1);
+                    e2 = fma(m0, fma(a0.x, na.x, a0.y * na.y), e2);
+                    e2 = fma(m1, fma(a1.x, nbv.x, a1.y * nbv.y), e2);
+                }
             }
         }
         if (do_energy) {
             for (int o = 16; o > 0; o >>= 1) e += __shfl_xor_sync(0xffffffffu, e, o);
             if ((tid & 31) == 0) sh.red[nb ^ 1][tid >> 5] = e;
+            if (CROSS && cr) {
+                for (int o = 16; o > 0; o >>= 1) e2 += __shfl_xor_sync(0xffffffffu, e2, o);
+                if ((tid & 31) == 0) sh.red2[nb ^ 1][tid >> 5] = e2;
+            }
         }
     }
 }
@@ -477,7 +504,7 @@ __device__ __forceinline__ void process_tile(const LaunchArgs& A, const KetDesc*
 // ------------------------------------------------------------------------------------------
 // the persistent pass kernel
 // ------------------------------------------------------------------------------------------
-template <bool SCALED, bool AJ>
+template <bool SCALED, bool AJ, bool CROSS>
 __global__ void __launch_bounds__(kThreads, DQ_CTAS_PER_SM) k_fused_passes(const __grid_constant__ LaunchArgs A) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     c128* tile = reinterpret_cast<c128*>(smem_raw);
@@ -492,7 +519,9 @@ __global__ void __launch_bounds__(kThreads, DQ_CTAS_PER_SM) k_fused_passes(const
     Pending pd;
     pd.g = -1;
     pd.partial = nullptr;
+    pd.partial2 = nullptr;
     pd.escale = 0.0;
+    pd.escale2 = 0.0;
     pd.slot = 0;
 
     if (tid == 0) {
@@ -556,16 +585,18 @@ __global__ void __launch_bounds__(kThreads, DQ_CTAS_PER_SM) k_fused_passes(const
         const PassStep& P = cache[cb];
         const int flags = P.flags;
         if (P.type == 0)
-            process_tile<SCALED, AJ, 0>(A, kd, P, tile, sh, I.p, I.t_id, nxt_raw, cur ^ 1, total, cache, cached_ps, cb,
+            process_tile<SCALED, AJ, CROSS, 0>(A, kd, P, tile, sh, I.p, I.t_id, nxt_raw, cur ^ 1, total, cache, cached_ps, cb,
                                         next_cb, next_tables_new, pd);
         else
-            process_tile<SCALED, AJ, 1>(A, kd, P, tile, sh, I.p, I.t_id, nxt_raw, cur ^ 1, total, cache, cached_ps, cb,
+            process_tile<SCALED, AJ, CROSS, 1>(A, kd, P, tile, sh, I.p, I.t_id, nxt_raw, cur ^ 1, total, cache, cached_ps, cb,
                                         next_cb, next_tables_new, pd);
         TRACE(A, I.item, 7);
         if (tid == 0) {                        // published after the next item's mid-tile barrier
             pd.g = I.g;
-            pd.partial = (flags & F_ENERGY) ? kd->partial + I.t_id : nullptr;
+            pd.partial = ((flags & F_ENERGY) && kd->partial) ? kd->partial + I.t_id : nullptr;
+            pd.partial2 = (CROSS && (flags & F_ENERGY) && kd->cross) ? kd->partial2 + I.t_id : nullptr;
             pd.escale = kd->escale;
+            pd.escale2 = kd->escale2;
             pd.slot = cur;
         }
         prefetched = sh.info[cur ^ 1].ready != 0;
@@ -691,6 +722,16 @@ __global__ void k_sum_partials(const double* __restrict__ partial, int tiles, co
     if (threadIdx.x == 0) out[out_index[blockIdx.x]] = acc;
 }
 
+// linear mode: out[b][2i] holds E+ and out[b][2i+1] the cross term C = Re <a|M|ket+>; ket- = 2a/sqrt(1+r^2) - ket+
+// gives E- = 4 Ea/(1+r^2) + E+ - 4 C/sqrt(1+r^2)   (sim_plain.py:197-220 by linearity of the suffix evolution)
+__global__ void k_linear_fix(double* __restrict__ out, const double* __restrict__ ea, int kets_per, int total, double r) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total || (i & 1) == 0) return;
+    const int b = i / kets_per;
+    const double inv = 1.0 / (1.0 + r * r);
+    out[i] = 4.0 * ea[b] * inv + out[i - 1] - 4.0 * out[i] * sqrt(inv);
+}
+
 // ------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------
@@ -700,7 +741,7 @@ struct Plan {
     bool has_aj = false;
     TypePlan types[2];
     int jphys[2][5];
-    DevBuf d_types, jobs, steps, tc, kets, counters, partials, out_index, work, rows, phi, uniform, trace;
+    DevBuf d_types, jobs, steps, tc, kets, counters, partials, out_index, work, rows, phi, uniform, trace, afin, ea, ea_index;
     long long trace_items = 0;
     size_t smem_bytes = 0;
     int ctas_per_sm = 0;
@@ -820,10 +861,16 @@ static Plan* get_plan(dq_ising* p) {
     if (pl->d_types.reserve(sizeof(TypePlan) * 2) != DQ_OK) return pl;
     if (cudaMemcpy(pl->d_types.p, pl->types, sizeof(TypePlan) * 2, cudaMemcpyHostToDevice) != cudaSuccess) return pl;
     int occ = 0, o2 = 0;
-    bool good = pl->has_aj ? (prep_kernel(k_fused_passes<true, true>, pl->smem_bytes, &occ) &&
-                              prep_kernel(k_fused_passes<false, true>, pl->smem_bytes, &o2))
-                           : (prep_kernel(k_fused_passes<true, false>, pl->smem_bytes, &occ) &&
-                              prep_kernel(k_fused_passes<false, false>, pl->smem_bytes, &o2));
+    int o3 = 0, o4 = 0;
+    bool good = pl->has_aj ? (prep_kernel(k_fused_passes<true, true, false>, pl->smem_bytes, &occ) &&
+                              prep_kernel(k_fused_passes<false, true, false>, pl->smem_bytes, &o2) &&
+                              prep_kernel(k_fused_passes<true, true, true>, pl->smem_bytes, &o3) &&
+                              prep_kernel(k_fused_passes<false, true, true>, pl->smem_bytes, &o4))
+                           : (prep_kernel(k_fused_passes<true, false, false>, pl->smem_bytes, &occ) &&
+                              prep_kernel(k_fused_passes<false, false, false>, pl->smem_bytes, &o2) &&
+                              prep_kernel(k_fused_passes<true, false, true>, pl->smem_bytes, &o3) &&
+                              prep_kernel(k_fused_passes<false, false, true>, pl->smem_bytes, &o4));
+    o2 = std::min(o2, std::min(o3, o4));
     if (!good) { cudaGetLastError(); return pl; }
     pl->ctas_per_sm = std::min(occ, o2);
     pl->counter_slots = 1 << 16;
@@ -839,6 +886,7 @@ struct Traj {
     int cls;
     bool final_energy;
     size_t step0;          // first PassStep index (filled by add_traj)
+    bool final_both = false;   // final pass stores AND reduces (the unshifted trajectory of the linear mode)
 };
 
 static void add_traj(std::vector<SetupJob>& jobs, Traj& t) {
@@ -848,7 +896,7 @@ static void add_traj(std::vector<SetupJob>& jobs, Traj& t) {
         j.row_pre = p >= 1 ? t.row0 + p - 1 : -1;
         j.row_cur = p < t.n_steps ? t.row0 + p : -1;
         j.type = (p + t.cls) & 1;
-        j.flags = p < t.n_steps ? F_STORE : (t.final_energy ? F_ENERGY : F_STORE);
+        j.flags = p < t.n_steps ? F_STORE : (t.final_both ? (F_ENERGY | F_STORE) : (t.final_energy ? F_ENERGY : F_STORE));
         jobs.push_back(j);
     }
 }
@@ -907,13 +955,16 @@ static int launch_group(dq_ising* p, Plan* pl, const KetDesc* d_kets, int n_kets
         }
         DQ_CUDA(cudaEventRecord(pl->ev[pl->ev_used], st));
     }
+#define DQ_LAUNCH(S, J, C) k_fused_passes<S, J, C><<<(unsigned)grid, kThreads, pl->smem_bytes, st>>>(A)
+    const bool cross = p->linear != 0;
     if (scaled) {
-        if (pl->has_aj) k_fused_passes<true, true><<<(unsigned)grid, kThreads, pl->smem_bytes, st>>>(A);
-        else k_fused_passes<true, false><<<(unsigned)grid, kThreads, pl->smem_bytes, st>>>(A);
+        if (pl->has_aj) { if (cross) DQ_LAUNCH(true, true, true); else DQ_LAUNCH(true, true, false); }
+        else { if (cross) DQ_LAUNCH(true, false, true); else DQ_LAUNCH(true, false, false); }
     } else {
-        if (pl->has_aj) k_fused_passes<false, true><<<(unsigned)grid, kThreads, pl->smem_bytes, st>>>(A);
-        else k_fused_passes<false, false><<<(unsigned)grid, kThreads, pl->smem_bytes, st>>>(A);
+        if (pl->has_aj) { if (cross) DQ_LAUNCH(false, true, true); else DQ_LAUNCH(false, true, false); }
+        else { if (cross) DQ_LAUNCH(false, false, true); else DQ_LAUNCH(false, false, false); }
     }
+#undef DQ_LAUNCH
     p->ctx->launches++;
     if (timed) {
         DQ_CUDA(cudaEventRecord(pl->ev[pl->ev_used + 1], st));
@@ -974,7 +1025,7 @@ void fused_release(dq_ising* p) {
         if (fused::g_plans[i].first == p) {
             fused::Plan* pl = fused::g_plans[i].second;
             DevBuf* bufs[] = {&pl->d_types, &pl->jobs, &pl->steps, &pl->tc, &pl->kets, &pl->counters, &pl->partials,
-                              &pl->out_index, &pl->work, &pl->rows, &pl->phi, &pl->uniform};
+                              &pl->out_index, &pl->work, &pl->rows, &pl->phi, &pl->uniform, &pl->afin, &pl->ea, &pl->ea_index};
             for (auto* b : bufs) b->release();
             for (cudaEvent_t e : pl->ev) cudaEventDestroy(e);
             delete pl;
@@ -1016,6 +1067,10 @@ int fused_evolve(dq_ising* p, c128* d_states, int batch, const double* h_rows, i
         k.sb0 = k.sb1 = 0;
         k.cls = 0;
         k.pad_ = 0;
+        k.cross = nullptr;
+        k.partial2 = nullptr;
+        k.escale2 = 0.0;
+        k.pad2_ = 0.0;
     }
     DQ_TRY(pl->kets.reserve(kets.size() * sizeof(KetDesc)));
     DQ_CUDA(cudaMemcpyAsync(pl->kets.p, kets.data(), kets.size() * sizeof(KetDesc), cudaMemcpyHostToDevice, st));
@@ -1051,6 +1106,7 @@ int fused_grad_run(dq_ising* p) {
     const int B = s.n_samples, n_shift = s.n_shift, kets_per = 2 * n_shift;
     const int G = std::max(1, p->ket_group);
     const bool scaled = s.scaled_ok;
+    const bool linear = p->linear != 0;   // one shifted ket per term + the unshifted suffix state (see k_linear_fix)
 
     // ---- tables: rows_a (prefix) and rows_b (suffix) live in one device table ---------------------
     const long long np = s.prefix_off[B], ns = s.suffix_off[B];
@@ -1058,7 +1114,7 @@ int fused_grad_run(dq_ising* p) {
     if (np) DQ_CUDA(cudaMemcpyAsync(pl->rows.p, p->rows_a.p, np * p->row_len * sizeof(double), cudaMemcpyDeviceToDevice, st));
     if (ns) DQ_CUDA(cudaMemcpyAsync(pl->rows.as<double>() + np * p->row_len, p->rows_b.p, ns * p->row_len * sizeof(double), cudaMemcpyDeviceToDevice, st));
     std::vector<SetupJob> jobs;
-    std::vector<Traj> pre(B), sufL(B), sufH(B);
+    std::vector<Traj> pre(B), sufL(B), sufH(B), sufA(B);
     for (int b = 0; b < B; ++b) {
         pre[b] = Traj{s.prefix_off[b], s.prefix_steps[b], 0, false, 0};
         sufL[b] = Traj{np + s.suffix_off[b], s.suffix_steps[b], 0, true, 0};
@@ -1066,6 +1122,10 @@ int fused_grad_run(dq_ising* p) {
         add_traj(jobs, pre[b]);
         add_traj(jobs, sufL[b]);
         add_traj(jobs, sufH[b]);
+        if (linear) {
+            sufA[b] = Traj{np + s.suffix_off[b], s.suffix_steps[b], 0, true, 0, true};
+            add_traj(jobs, sufA[b]);
+        }
     }
     DQ_TRY(run_setup(p, pl, jobs, pl->rows.as<double>(), scaled));
 
@@ -1073,6 +1133,10 @@ int fused_grad_run(dq_ising* p) {
     DQ_TRY(pl->phi.reserve((size_t)B * N * sizeof(c128)));
     DQ_TRY(pl->work.reserve((size_t)G * N * sizeof(c128)));
     DQ_TRY(pl->partials.reserve((size_t)B * kets_per * tiles * sizeof(double)));
+    if (linear) {
+        DQ_TRY(pl->afin.reserve((size_t)B * N * sizeof(c128)));
+        DQ_TRY(pl->ea.reserve(((size_t)B * tiles + B) * sizeof(double)));
+    }
     const c128* psi0 = nullptr;
     if (s.uniform_psi0) {
         DQ_TRY(pl->uniform.reserve(N * sizeof(c128)));
@@ -1099,6 +1163,10 @@ int fused_grad_run(dq_ising* p) {
         k.sb0 = k.sb1 = 0;
         k.cls = 0;
         k.pad_ = 0;
+        k.cross = nullptr;
+        k.partial2 = nullptr;
+        k.escale2 = 0.0;
+        k.pad2_ = 0.0;
         kets.push_back(k);
     }
     struct Group { size_t first; int count; int max_pass; };
@@ -1107,6 +1175,22 @@ int fused_grad_run(dq_ising* p) {
         int cnt = std::min(G, B - g0), mp = 0;
         for (int g = 0; g < cnt; ++g) mp = std::max(mp, kets[g0 + g].n_pass);
         groups.push_back({(size_t)g0, cnt, mp});
+    }
+    if (linear) {                       // a_b = U(suffix of b) phi_b : stored (cross terms) and reduced (Ea)
+        for (int b = 0; b < B; ++b) {
+            KetDesc k = kets[b];
+            k.src = pl->phi.as<c128>() + (size_t)b * N;
+            k.buf = pl->afin.as<c128>() + (size_t)b * N;
+            k.steps = pl->steps.as<PassStep>() + sufA[b].step0;
+            k.partial = pl->ea.as<double>() + (size_t)b * tiles;
+            k.n_pass = s.suffix_steps[b] + 1;
+            kets.push_back(k);
+        }
+        for (int g0 = 0; g0 < B; g0 += G) {
+            int cnt = std::min(G, B - g0), mp = 0;
+            for (int g = 0; g < cnt; ++g) mp = std::max(mp, kets[B + g0 + g].n_pass);
+            groups.push_back({(size_t)(B + g0), cnt, mp});
+        }
     }
     for (int b = 0; b < B; ++b) {
         for (int cls = 0; cls < 2; ++cls) {
@@ -1127,8 +1211,12 @@ int fused_grad_run(dq_ising* p) {
                     kcls = b0 >= 10 ? 1 : 0;
                 }
                 if (kcls != cls) continue;
-                for (int sg = 0; sg < 2; ++sg) {
+                for (int sg = 0; sg < (linear ? 1 : 2); ++sg) {
                     KetDesc k;
+                    k.cross = linear ? pl->afin.as<c128>() + (size_t)b * N : nullptr;
+                    k.partial2 = linear ? pl->partials.as<double>() + ((size_t)b * kets_per + 2 * i + 1) * tiles : nullptr;
+                    k.escale2 = s.shift_kind[i] == 1 ? sqrt(esc_x) : 1.0;
+                    k.pad2_ = 0.0;
                     k.src = pl->phi.as<c128>() + (size_t)b * N;
                     k.buf = nullptr;                // slot assigned below
                     k.steps = pl->steps.as<PassStep>() + (cls == 0 ? sufL[b].step0 : sufH[b].step0);
@@ -1166,6 +1254,13 @@ int fused_grad_run(dq_ising* p) {
     k_sum_partials<<<B * kets_per, 32, 0, st>>>(pl->partials.as<double>(), tiles, pl->out_index.as<int>(),
                                                  p->energies.as<double>());
     p->ctx->launches++;
+    if (linear) {
+        double* ea_out = pl->ea.as<double>() + (size_t)B * tiles;
+        k_sum_partials<<<B, 32, 0, st>>>(pl->ea.as<double>(), tiles, pl->out_index.as<int>(), ea_out);
+        const int total = B * kets_per;
+        k_linear_fix<<<(total + 255) / 256, 256, 0, st>>>(p->energies.as<double>(), ea_out, kets_per, total, s.r);
+        p->ctx->launches += 2;
+    }
     DQ_CUDA(cudaGetLastError());
     return DQ_OK;
 }

@@ -105,6 +105,8 @@ int dq_ising_create(dq_context* ctx, int n_qubits, int n_zz, const int32_t* zz_p
                     dq_ising** out);
 int dq_ising_destroy(dq_ising* p);
 /* Tunables: "ket_group" (states co-resident in L2 per launch), "engine" (0 generic, 1 fused v2 = default when 12 <= n <= 20, 2 fused v3),
+ * "linear" (1, fused v2 only: evolve one shifted ket per term plus the unshifted suffix state and obtain the
+ * other sign from ket- = 2 a/sqrt(1+r^2) - ket+; same outputs to rounding, about half the trajectory-steps),
  * "time_launches" (1: bracket every pass-kernel launch with CUDA events, read back via dq_ising_last_stat). */
 int dq_ising_set_option(dq_ising* p, const char* name, int64_t value);
 int dq_ising_get_info(dq_ising* p, const char* name, int64_t* value);

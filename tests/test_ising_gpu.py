@@ -125,7 +125,7 @@ def test_norm_is_preserved_and_errors_are_python_exceptions():
         dq.IsingProblem(3, [("zz", 0, 3)], [1.0], 1.0)
 
 
-@pytest.mark.parametrize("n,engine", [(12, 2), (15, 2), (17, 2), (20, 2), (16, 1)])
+@pytest.mark.parametrize("n,engine", [(12, 2), (15, 2), (17, 2), (20, 2), (16, 1), (12, 1), (20, 1)])
 def test_fused_gradients_agree_with_generic_engine(n, engine):
     """Every shifted ket (each ZZ pair and each X qubit, both signs) through the fused passes vs the
     one-kernel-per-term engine on the same device; the generic engine is pinned to the oracle above."""
@@ -138,8 +138,20 @@ def test_fused_gradients_agree_with_generic_engine(n, engine):
     assert sim.info("engine") == engine
     got = sim.shifted_energies(coeff, s_list)
     assert rel(got, ref) < TOL
+    if engine == 1:                      # estimator by linearity: n_H + 1 suffix trajectories, same outputs
+        sim.set_option("linear", 1)
+        lin = sim.shifted_energies(coeff, s_list)
+        assert sim.stat("steps") < 0.6 * 2 * len(prob.terms) * 3 * len(s_list) + 50
+        sim.set_option("linear", 0)
+        assert rel(lin, ref) < TOL
+        g_lin = sim.assemble_gradients(coeff, s_list, lin)
+        g_ref = sim.assemble_gradients(coeff, s_list, ref)
+        assert rel(g_lin, g_ref) < TOL
     # large angles force the unscaled (cos, sin) butterflies
     big = coeff * 6.0
     sim2 = dq.IsingSimulator(prob, per_step=1, engine=engine)
     ref2 = dq.IsingSimulator(prob, per_step=1, engine=0).shifted_energies(big, s_list[:1])
     assert rel(sim2.shifted_energies(big, s_list[:1]), ref2) < TOL
+    if engine == 1:
+        sim2.set_option("linear", 1)
+        assert rel(sim2.shifted_energies(big, s_list[:1]), ref2) < TOL
