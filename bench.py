@@ -93,46 +93,61 @@ def measured_peak():
 
 
 class ClockSampler(object):
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+    """nvidia-smi polled in the background for the whole run (its start-up enumerates every GPU and can
+    stall launches for hundreds of ms, so it is started BEFORE the warm-up steps, never inside a timed
+    region); `window(t0, t1)` summarises the samples whose timestamps fall inside a timed region."""
+    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
         self.proc = None
+        self.rows = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            import select
+            ready, _, _ = select.select([self.proc.stdout], [], [], 10.0)      # first sample = start-up is over
+            self.first = self.proc.stdout.readline() if ready else ""
         except OSError:
-            pass
+            self.proc = None
 
     def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        if self.proc is None or self.rows is not None:
+            return
         self.proc.terminate()
         try:
             out, _ = self.proc.communicate(timeout=5)
         except subprocess.TimeoutExpired:
             self.proc.kill()
             out, _ = self.proc.communicate()
-        sm, mx, pw, reasons = [], [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        out = self.first + out
+        import datetime
+        self.rows = []
         for line in out.strip().splitlines():
             f = [x.strip() for x in line.split(",")]
-            if len(f) < 7:
+            if len(f) < 8:
                 continue
             try:
-                sm.append(float(f[0])); mx.append(float(f[1])); pw.append(float(f[2]))
+                ts = datetime.datetime.strptime(f[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                self.rows.append((ts, float(f[1]), float(f[2]), float(f[3]), f[4:8]))
             except ValueError:
                 continue
-            for nm, v in zip(names, f[3:7]):
+
+    def window(self, t0, t1):
+        self.stop()
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        sel = [r for r in self.rows if t0 - 0.05 <= r[0] <= t1 + 0.05] or self.rows
+        reasons = set()
+        for r in sel:
+            for nm, v in zip(names, r[4]):
                 if v.lower().startswith("active"):
                     reasons.add(nm)
-        if not sm:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
-        busy = [c for c, p in zip(sm, pw) if p > 0.5 * max(pw)] or sm      # samples taken under load
-        return {"sm_mhz": float(np.median(busy)), "sm_max_mhz": float(max(mx)), "power_w_max": float(max(pw)),
-                "samples": len(sm), "reasons": sorted(reasons)}
+        return {"sm_mhz": float(np.median([r[1] for r in sel])), "sm_max_mhz": float(max(r[2] for r in sel)),
+                "power_w_max": float(max(r[3] for r in sel)), "samples": len(sel), "reasons": sorted(reasons)}
 
 
 # ---------------------------------------------------------------------------------------------
@@ -201,7 +216,7 @@ def workload_config(a, world):
     return {"workload": "configs[3]: random 3-regular MaxCut n=%d (networkx seed 0), per_step=%d, T=2.0, "
                         "n_basis=6 BSpline, 1+2*n_Hs trajectories per sample" % (a.n, a.per_step),
             "samples_per_step_per_gpu": a.samples_per_step, "global_samples_per_step": a.samples_per_step * world,
-            "parallelism": "sample-sharded x%d, one all-reduce of the gradient per step" % world,
+            "parallelism": "sample-sharded x%d (cost-balanced shards), one all-reduce of the gradient per step" % world,
             "l2": "L2 flushed (512 MiB write) between timed steps"}
 
 
@@ -259,10 +274,11 @@ def run_b200_arm(a):
     n_H = len(prob.terms)
     stream = torch.cuda.ExternalStream(sim.ctx.stream, device=dev)
     flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
-    est = sharding.ShardedEstimator(lambda c, s: sim.grad_samples(c, s), device=dev)
+    cost = lambda s: steps_of_sample(s, prob.T, a.per_step, n_H)[2]
+    est = sharding.ShardedEstimator(lambda c, s: sim.grad_samples(c, s), device=dev, cost=cost)
 
     def my_samples(i):
-        return sharding.shard(step_samples(i, a.samples_per_step, world, prob.T), rank, world)
+        return est.my_samples(step_samples(i, a.samples_per_step, world, prob.T))
 
     # ---- value: tables staged in HBM, device-timed ----------------------------------------------
     def staged_loop(linear):
@@ -270,13 +286,13 @@ def run_b200_arm(a):
         sim.set_option("linear", 1 if linear else 0)
         sim.set_option("time_launches", 1)
         r = dict(dev_ms=[], alg_bytes=0.0, traj_steps=0.0, kern_ms=0.0, kern_launches=0.0, clocks=None, launches=0, en=None)
-        sampler = None
         l0 = 0
+        t_start = time.time()
         for i in range(a.warmup + a.steps):
             timed = i >= a.warmup
             if i == a.warmup:
                 barrier()
-                sampler = ClockSampler(local)
+                t_start = time.time()
                 l0 = sim.ctx.launch_count
             sim.stage(coeff, my_samples(i))              # H2D of the angle tables: outside the timed region
             flush.zero_()
@@ -296,14 +312,15 @@ def run_b200_arm(a):
                 r["kern_launches"] += sim.stat("pass_kernel_launches")
         barrier()
         r["launches"] = sim.ctx.launch_count - l0
-        r["clocks"] = sampler.stop()
+        r["window"] = (t_start, time.time())
         sim.set_option("time_launches", 0)
         sim.set_option("linear", 0)
         return r
 
+    sampler = ClockSampler(local)            # starts (and finishes its start-up) during the warm-up steps
     lit = staged_loop(False)
     dev_ms, alg_bytes, traj_steps = lit["dev_ms"], lit["alg_bytes"], lit["traj_steps"]
-    kern_ms, kern_launches, gpu_launches, clk, en = lit["kern_ms"], lit["kern_launches"], lit["launches"], lit["clocks"], lit["en"]
+    kern_ms, kern_launches, gpu_launches, en = lit["kern_ms"], lit["kern_launches"], lit["launches"], lit["en"]
     per_rank = None
     if world > 1:
         import torch.distributed as dist
@@ -344,12 +361,14 @@ def run_b200_arm(a):
         dt = time.perf_counter() - t0
         if timed:
             e2e_s.append(dt)
-            tabs = sim.sample_tables(coeff, sharding.shard(s_all, rank, world))     # recount the bytes copied
+            tabs = sim.sample_tables(coeff, est.my_samples(s_all))                  # recount the bytes copied
             h2d = sum(t.nbytes for t in tabs) + prob.term_kind.nbytes + prob.term_index.nbytes
-            d2h = len(sharding.shard(s_all, rank, world)) * n_H * 2 * 8
+            d2h = len(est.my_samples(s_all)) * n_H * 2 * 8
     t_e2e = max_over_ranks(sum(e2e_s))
     e2e_value = total_samples / t_e2e
     assert np.all(np.isfinite(gmean)) and np.all(np.isfinite(last_energies))
+
+    clk = sampler.window(*lit["window"])
 
     # ---- roofline of the dominant kernel ---------------------------------------------------------
     peak, peak_src = measured_peak()

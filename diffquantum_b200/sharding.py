@@ -23,6 +23,23 @@ def shard(items, rank, world_size):
     return items[lo:hi]
 
 
+def balanced_assignment(costs, world_size):
+    """Cost-balanced split of independent items (longest-processing-time greedy, deterministic):
+    returns one sorted index array per rank.  Sample cost is known up front — a sample at time s runs
+    int(per_step (s+1)) + 2 n_Hs int(per_step (T-s+1)) trajectory-steps (sim_plain.py:123,190-215) and
+    varies 3x with s — so balancing by cost instead of by count removes most of the idle tail of the
+    slowest rank."""
+    costs = np.asarray(costs, dtype=np.float64).reshape(-1)
+    order = np.argsort(-costs, kind="stable")
+    load = np.zeros(world_size)
+    out = [[] for _ in range(world_size)]
+    for i in order:
+        r = int(np.argmin(load))             # first minimum: deterministic on every rank
+        out[r].append(int(i))
+        load[r] += costs[i]
+    return [np.array(sorted(x), dtype=np.int64) for x in out]
+
+
 def dist_info():
     """(rank, world_size, initialised) of the default process group; (0, 1, False) without one."""
     try:
@@ -79,14 +96,22 @@ class ShardedEstimator(object):
     returning per-sample gradients [len(s_shard), n_Hs, n_basis] — normally
     IsingSimulator.grad_samples bound to this rank's GPU."""
 
-    def __init__(self, local_grads, device=None):
+    def __init__(self, local_grads, device=None, cost=None):
         self.local_grads = local_grads
         self.device = device
+        self.cost = cost                # optional: callable s -> relative cost, enables cost-balanced shards
+
+    def my_samples(self, s_list):
+        rank, world, _ = dist_info()
+        s_list = np.asarray(s_list, dtype=np.float64).reshape(-1)
+        if self.cost is None or world == 1:
+            return shard(s_list, rank, world)
+        return s_list[balanced_assignment([self.cost(s) for s in s_list], world)[rank]]
 
     def mean_gradient(self, coeff, s_list):
         rank, world, _ = dist_info()
         s_list = np.asarray(s_list, dtype=np.float64).reshape(-1)
-        mine = shard(s_list, rank, world)
+        mine = self.my_samples(s_list)
         shape = np.asarray(coeff).shape
         local = np.zeros(shape)
         if len(mine):

@@ -27,6 +27,17 @@ def test_shard_bounds_cover_everything_once():
         sharding.shard_bounds(4, 2, 2)
 
 
+def test_balanced_assignment_is_a_partition_and_balances():
+    rng = np.random.RandomState(0)
+    costs = rng.uniform(1000, 3000, size=64)
+    for w in (1, 2, 4, 8):
+        parts = sharding.balanced_assignment(costs, w)
+        assert sorted(np.concatenate(parts).tolist()) == list(range(64))
+        loads = [costs[p].sum() for p in parts]
+        assert max(loads) - min(loads) <= costs.max()
+        assert max(loads) / (costs.sum() / w) < 1.03 or w == 1
+
+
 def test_single_process_estimator_is_plain_mean():
     fake = lambda coeff, s: np.stack([np.full(coeff.shape, float(x)) for x in s])
     est = sharding.ShardedEstimator(fake)
@@ -49,6 +60,9 @@ def _worker(rank, world, port, out):
         coeff = np.zeros((3, 2))
         s = np.random.RandomState(0).uniform(size=7) * 2.0
         mean = est.mean_gradient(coeff, s)
+        bal = sharding.ShardedEstimator(fake, cost=lambda x: 3.0 - x)      # cost-balanced shards: same mean
+        np.testing.assert_allclose(bal.mean_gradient(coeff, s), mean, rtol=1e-14)
+        assert len(bal.my_samples(s)) in (3, 4)
         every = est.per_sample_gradients(coeff, s)
         want = fake(coeff, s)
         np.testing.assert_allclose(mean, want.mean(axis=0), rtol=1e-14)
