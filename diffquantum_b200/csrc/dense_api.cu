@@ -134,8 +134,12 @@ int evolve_blocks(dq_context* ctx, Problem& P, int mode, int B, int Ncp, const i
     const int s_blk = log2_ceil_ratio(bound, 1.0), s_mat = log2_ceil_ratio(bound, 0.125);
     DQ_REQUIRE(s_blk <= 20, "dense path: ||dt H|| = %g is too large", bound);
     const double d3 = (double)Dp * Dp * Dp, d2n = (double)Dp * Dp * Ncp;
-    const double cost_blk = std::ldexp((double)m_blk, s_blk) * d2n;
-    const double cost_mat = (m_mat - 1 + s_mat) * d3 + d2n;
+    // time model per launch: ~4 us of launch latency + tensor-pipe time (DMMA GEMM at ~12 TFLOP/s) or, for the
+    // skinny mat-vec kernel, the time to stream A (16 Dp^2 bytes per batch member at ~3 TB/s)
+    const double n_blk = std::ldexp((double)m_blk, s_blk), n_mat = m_mat - 1 + s_mat;
+    const double per_blk = (Ncp == 8 && Dp >= 64) ? 16.0 * Dp * Dp / 3e12 : 8.0 * d2n / 4e12;
+    const double cost_blk = n_blk * (4e-6 + B * per_blk);
+    const double cost_mat = n_mat * (4e-6 + B * 8.0 * d3 / 12e12) + (4e-6 + B * 8.0 * d2n / 4e12);
     int strategy = cost_blk <= cost_mat ? 0 : 1;
     if (strategy == 1 && mode == 0 && Ncp > Dp) strategy = 2;
     if (ctx->dense_force_strategy >= 0 && (ctx->dense_force_strategy < 2 || mode == 0)) strategy = ctx->dense_force_strategy;

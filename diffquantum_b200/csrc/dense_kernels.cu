@@ -109,6 +109,55 @@ __global__ void __launch_bounds__(WM * WN * 32) k_zgemm(const Gemm g) {
         }
 }
 
+// Skinny case (N == 8, i.e. a block of <= 8 kets: diffqc.trotter, the solver hook, the estimator's prefix): the product
+// is a batched mat-vec, bound by streaming A once, so tensor-core tiles only waste parallelism (a 64-row tile leaves
+// 16 CTAs at dim 1024).  One warp per row: lanes stride over k with coalesced loads of A, the 8 ket columns of B come
+// from L1, 16 accumulators per lane, butterfly reduction, fused "+ Add" epilogue.
+__global__ void __launch_bounds__(256) k_zgemm_skinny(const Gemm g) {
+    const int z = blockIdx.y;
+    const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (row >= g.M) return;
+    const double* __restrict__ Ar = g.A + (long long)z * g.strideA + (long long)row * g.lda;
+    const double* __restrict__ Ai = Ar + g.planeA;
+    const double* __restrict__ Br = g.B + (long long)z * g.strideB;
+    const double* __restrict__ Bi = Br + g.planeB;
+    double cr[8], ci[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) cr[c] = ci[c] = 0.0;
+    for (int k = lane; k < g.K; k += 32) {
+        const double ar = Ar[k], ai = Ai[k];
+        const double2* br = reinterpret_cast<const double2*>(Br + (long long)k * g.ldb);
+        const double2* bi = reinterpret_cast<const double2*>(Bi + (long long)k * g.ldb);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const double2 xr = __ldg(br + c), xi = __ldg(bi + c);
+            cr[2 * c] = fma(ar, xr.x, fma(-ai, xi.x, cr[2 * c]));
+            ci[2 * c] = fma(ar, xi.x, fma(ai, xr.x, ci[2 * c]));
+            cr[2 * c + 1] = fma(ar, xr.y, fma(-ai, xi.y, cr[2 * c + 1]));
+            ci[2 * c + 1] = fma(ar, xi.y, fma(ai, xr.y, ci[2 * c + 1]));
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < 8; ++c)
+        for (int o = 16; o > 0; o >>= 1) {
+            cr[c] += __shfl_xor_sync(0xffffffffu, cr[c], o);
+            ci[c] += __shfl_xor_sync(0xffffffffu, ci[c], o);
+        }
+    if (lane < 8) {
+        double vr = 0.0, vi = 0.0;
+#pragma unroll
+        for (int c = 0; c < 8; ++c)
+            if (c == lane) { vr = cr[c]; vi = ci[c]; }
+        const long long o = (long long)z * g.strideC + (long long)row * g.ldc + lane;
+        vr *= g.alpha;
+        vi *= g.alpha;
+        if (g.Add) { vr += g.Add[o]; vi += g.Add[o + g.planeC]; }
+        if (g.add_identity && row == lane) vr += 1.0;
+        g.C[o] = vr;
+        g.C[o + g.planeC] = vi;
+    }
+}
+
 template <int BM, int BN, int WM, int WN>
 int launch_zgemm(dq_context* ctx, const Gemm& g) {
     dim3 grid((g.N + BN - 1) / BN, (g.M + BM - 1) / BM, g.batch);
@@ -226,6 +275,13 @@ __global__ void k_energy(const double* __restrict__ M, int Dp, int dim, const do
 
 int zgemm(dq_context* ctx, const Gemm& g) {
     DQ_REQUIRE(g.M % 8 == 0 && g.N % 8 == 0 && g.K % 8 == 0 && g.batch >= 1, "zgemm: dims must be multiples of 8");
+    if (g.N == 8 && g.M >= 64) {
+        dim3 grid(g.M / 8, g.batch);
+        k_zgemm_skinny<<<grid, 256, 0, ctx->stream>>>(g);
+        ctx->launches++;
+        DQ_CUDA(cudaGetLastError());
+        return DQ_OK;
+    }
     if (g.M >= 64) {
         if (g.N >= 64) return launch_zgemm<64, 64, 2, 2>(ctx, g);
         if (g.N >= 16) return launch_zgemm<64, 16, 4, 1>(ctx, g);

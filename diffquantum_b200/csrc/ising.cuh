@@ -15,13 +15,16 @@ struct dq_ising {
     dq::DevBuf pairs_dev;          // int2[n_zz] physical bit positions
 
     int engine = 1;                // 0 generic, 1 fused v2 (32 amplitudes/thread, default), 2 fused v3 (16 amplitudes/thread); 12 <= n <= 20
-    int ket_group = 5;             // states per fused launch (L2 residency; 5 x 16 MiB measured best at n = 20)
+    int ket_group = 0;             // states per fused launch; 0 = automatic (auto_ket_group below)
     int grid_per_sm = 0;           // experiment knob: CTAs per SM in the persistent grid (0 = occupancy)
     int linear = 0;                // 1: estimator by linearity (n_H + 1 suffix trajectories per sample instead of 2 n_H)
     int time_launches = 0;         // 1: CUDA-event pairs around every pass-kernel launch (bench.py's roofline)
 
     // work buffers
     dq::DevBuf states, phi, rows_a, rows_b, trig_a, trig_b, energies, scratch, io, shift_desc;
+    dq::DevBuf exact_diag, exact_t0, exact_t1;     // exact-step workspaces (generic engine)
+    int step_mode = 0;             // 0 split (per-term product, diffqc.cc:155-164), 1 exact (live semantics, sim_plain.py:135-150)
+    std::vector<double> host_rows_a, host_rows_b;  // exact step: host copy of the staged rows (norm bound per step)
 
     // staged gradient batch
     struct Staged {
@@ -41,6 +44,14 @@ struct dq_ising {
 };
 
 namespace dq {
+// States co-resident per fused launch: as many as keep the work ring inside ~80 MiB of the 126 MB L2
+// (5 x 16 MiB measured best at n = 20), at least 5, at most 96 (small states need many kets to fill 148 SMs).
+inline int auto_ket_group(const dq_ising* p) {
+    if (p->ket_group > 0) return p->ket_group;
+    const size_t state_bytes = sizeof(double2) << p->n;
+    const size_t g = ((size_t)80 << 20) / state_bytes;
+    return (int)(g < 5 ? 5 : (g > 96 ? 96 : g));
+}
 // one shifted ket of the estimator: exp(sign * i * atan(r) * P), P = Z_b0 Z_b1 (kind 0) or X_b0 (kind 1)
 struct ShiftDesc { int kind; int b0; int b1; double sign; };
 // generic engine (any n >= 1): one kernel per term group, used for small n and as cross-check
@@ -50,6 +61,7 @@ int gen_permute_out(dq_ising* p, const c128* src_phys, c128* dst_ref_order, int 
 int gen_trig(dq_ising* p, const double* d_rows, int64_t n_rows, double2* d_trig);
 int gen_evolve(dq_ising* p, c128* d_states, int batch, const double* d_rows, const double2* d_trig,
                int n_steps);
+int gen_evolve_exact(dq_ising* p, c128* d_states, int batch, const double* d_rows, const double* h_rows, int n_steps);
 int gen_fanout(dq_ising* p, const c128* d_phi, c128* d_kets, int n_kets, const ShiftDesc* d_desc,
                double r);
 int gen_energy(dq_ising* p, const c128* d_states, int batch, double* d_out);

@@ -15,8 +15,9 @@ int check_rows(const dq_ising* p, const double* rows, int64_t n_rows, const char
     return DQ_OK;
 }
 
-bool use_f16(const dq_ising* p) { return p->engine == 2 && dq::f16_supported(p); }
-bool use_fused(const dq_ising* p) { return p->engine >= 1 && !use_f16(p) && dq::fused_supported(p); }
+// the fused engines implement the product-formula step only; the exact step runs on the generic engine
+bool use_f16(const dq_ising* p) { return p->step_mode == 0 && p->engine == 2 && dq::f16_supported(p); }
+bool use_fused(const dq_ising* p) { return p->step_mode == 0 && p->engine >= 1 && !use_f16(p) && dq::fused_supported(p); }
 
 }  // namespace
 
@@ -77,7 +78,8 @@ int dq_ising_destroy(dq_ising* p) {
     dq::fused_release(p);
     dq::f16_release(p);
     dq::DevBuf* bufs[] = {&p->mdiag, &p->pairs_dev, &p->states, &p->phi, &p->rows_a, &p->rows_b, &p->trig_a,
-                          &p->trig_b, &p->energies, &p->scratch, &p->io, &p->shift_desc, &p->st.psi0};
+                          &p->trig_b, &p->energies, &p->scratch, &p->io, &p->shift_desc, &p->st.psi0, &p->exact_diag, &p->exact_t0,
+                          &p->exact_t1};
     for (auto* b : bufs) b->release();
     delete p;
     return DQ_OK;
@@ -90,12 +92,15 @@ int dq_ising_set_option(dq_ising* p, const char* name, int64_t value) {
         p->engine = (int)value;
     } else if (!strcmp(name, "grid_per_sm")) {
         p->grid_per_sm = (int)value;
+    } else if (!strcmp(name, "step")) {
+        DQ_REQUIRE(value == 0 || value == 1, "step must be 0 (split) or 1 (exact)");
+        p->step_mode = (int)value;
     } else if (!strcmp(name, "linear")) {
         p->linear = value != 0;
     } else if (!strcmp(name, "time_launches")) {
         p->time_launches = value != 0;
     } else if (!strcmp(name, "ket_group")) {
-        DQ_REQUIRE(value >= 1 && value <= 1024, "ket_group out of range");
+        DQ_REQUIRE(value >= 0 && value <= 1024, "ket_group out of range (0 = automatic)");
         p->ket_group = (int)value;
     } else {
         dq::set_error("dq_ising_set_option: unknown option '%s'", name);
@@ -107,7 +112,7 @@ int dq_ising_set_option(dq_ising* p, const char* name, int64_t value) {
 int dq_ising_get_info(dq_ising* p, const char* name, int64_t* value) {
     DQ_REQUIRE(p && name && value, "NULL argument");
     if (!strcmp(name, "engine")) *value = use_f16(p) ? 2 : (use_fused(p) ? 1 : 0);
-    else if (!strcmp(name, "ket_group")) *value = p->ket_group;
+    else if (!strcmp(name, "ket_group")) *value = dq::auto_ket_group(p);
     else if (!strcmp(name, "row_len")) *value = p->row_len;
     else if (!strcmp(name, "n_qubits")) *value = p->n;
     else { dq::set_error("dq_ising_get_info: unknown name '%s'", name); return DQ_ERR_INVALID; }
@@ -163,8 +168,12 @@ int dq_ising_evolve(dq_ising* p, int batch, int n_steps, const double* angles, c
             DQ_TRY(p->trig_a.reserve((size_t)n_steps * p->n * sizeof(double2)));
             DQ_CUDA(cudaMemcpyAsync(p->rows_a.p, angles, (size_t)n_steps * p->row_len * sizeof(double),
                                     cudaMemcpyHostToDevice, st));
-            DQ_TRY(dq::gen_trig(p, p->rows_a.as<double>(), n_steps, p->trig_a.as<double2>()));
-            DQ_TRY(dq::gen_evolve(p, d, batch, p->rows_a.as<double>(), p->trig_a.as<double2>(), n_steps));
+            if (p->step_mode == 1) {
+                DQ_TRY(dq::gen_evolve_exact(p, d, batch, p->rows_a.as<double>(), angles, n_steps));
+            } else {
+                DQ_TRY(dq::gen_trig(p, p->rows_a.as<double>(), n_steps, p->trig_a.as<double2>()));
+                DQ_TRY(dq::gen_evolve(p, d, batch, p->rows_a.as<double>(), p->trig_a.as<double2>(), n_steps));
+            }
         }
         if (energies_out) DQ_TRY(dq::gen_energy(p, d, batch, p->energies.as<double>()));
     }
@@ -268,6 +277,10 @@ int dq_ising_grad_stage(dq_ising* p, int n_samples, const int32_t* prefix_steps,
         DQ_TRY(dq::gen_trig(p, p->rows_a.as<double>(), np, p->trig_a.as<double2>()));
         DQ_TRY(dq::gen_trig(p, p->rows_b.as<double>(), ns, p->trig_b.as<double2>()));
     }
+    if (p->step_mode == 1) {
+        p->host_rows_a.assign(prefix_angles, prefix_angles + np * p->row_len);
+        p->host_rows_b.assign(suffix_angles, suffix_angles + ns * p->row_len);
+    }
     DQ_CUDA(cudaStreamSynchronize(st));          // host vectors above go out of scope
     // keep host copies of the rows for the fused engine's table builder
     s.valid = true;
@@ -294,6 +307,15 @@ int dq_ising_grad_run_staged(dq_ising* p) {
             c128* phi = p->phi.as<c128>();
             if (s.uniform_psi0) DQ_TRY(dq::gen_fill_uniform(p, phi, 1));
             else DQ_CUDA(cudaMemcpyAsync(phi, s.psi0.p, N * sizeof(c128), cudaMemcpyDeviceToDevice, st));
+            if (p->step_mode == 1) {
+                DQ_TRY(dq::gen_evolve_exact(p, phi, 1, p->rows_a.as<double>() + s.prefix_off[b] * p->row_len,
+                                            p->host_rows_a.data() + s.prefix_off[b] * p->row_len, s.prefix_steps[b]));
+                DQ_TRY(dq::gen_fanout(p, phi, p->states.as<c128>(), kets, p->shift_desc.as<dq::ShiftDesc>(), s.r));
+                DQ_TRY(dq::gen_evolve_exact(p, p->states.as<c128>(), kets, p->rows_b.as<double>() + s.suffix_off[b] * p->row_len,
+                                            p->host_rows_b.data() + s.suffix_off[b] * p->row_len, s.suffix_steps[b]));
+                DQ_TRY(dq::gen_energy(p, p->states.as<c128>(), kets, p->energies.as<double>() + (size_t)b * kets));
+                continue;
+            }
             DQ_TRY(dq::gen_evolve(p, phi, 1, p->rows_a.as<double>() + s.prefix_off[b] * p->row_len,
                                   p->trig_a.as<double2>() + s.prefix_off[b] * p->n, s.prefix_steps[b]));
             DQ_TRY(dq::gen_fanout(p, phi, p->states.as<c128>(), kets, p->shift_desc.as<dq::ShiftDesc>(), s.r));

@@ -966,7 +966,7 @@ int f16_evolve(dq_ising* p, c128* d_states, int batch, const double* h_rows, int
     }
     DQ_TRY(pl->kets.reserve(kets.size() * sizeof(KetDesc)));
     DQ_CUDA(cudaMemcpyAsync(pl->kets.p, kets.data(), kets.size() * sizeof(KetDesc), cudaMemcpyHostToDevice, st));
-    const int G = std::max(1, p->ket_group);
+    const int G = auto_ket_group(p);
     for (int g0 = 0; g0 < batch; g0 += G)
         DQ_TRY(launch_group(p, pl, pl->kets.as<KetDesc>() + g0, std::min(G, batch - g0), n_steps + 1, scaled, 0.5));
     if (d_energies) {
@@ -991,7 +991,7 @@ int f16_grad_run(dq_ising* p) {
     const size_t N = p->dim();
     const int tiles = 1 << pl->tiles_log2;
     const int B = s.n_samples, n_shift = s.n_shift, kets_per = 2 * n_shift;
-    const int G = std::max(1, p->ket_group);
+    const int G = auto_ket_group(p);
     const bool scaled = s.scaled_ok;
 
     const long long np = s.prefix_off[B], ns = s.suffix_off[B];

@@ -1074,7 +1074,7 @@ int fused_evolve(dq_ising* p, c128* d_states, int batch, const double* h_rows, i
     }
     DQ_TRY(pl->kets.reserve(kets.size() * sizeof(KetDesc)));
     DQ_CUDA(cudaMemcpyAsync(pl->kets.p, kets.data(), kets.size() * sizeof(KetDesc), cudaMemcpyHostToDevice, st));
-    const int G = std::max(1, p->ket_group);
+    const int G = auto_ket_group(p);
     for (int g0 = 0; g0 < batch; g0 += G)
         DQ_TRY(launch_group(p, pl, pl->kets.as<KetDesc>() + g0, std::min(G, batch - g0), n_steps + 1, scaled, 0.5));
     if (d_energies) {
@@ -1104,7 +1104,7 @@ int fused_grad_run(dq_ising* p) {
     const size_t N = p->dim();
     const int tiles = 1 << pl->tiles_log2;
     const int B = s.n_samples, n_shift = s.n_shift, kets_per = 2 * n_shift;
-    const int G = std::max(1, p->ket_group);
+    const int G = auto_ket_group(p);
     const bool scaled = s.scaled_ok;
     const bool linear = p->linear != 0;   // one shifted ket per term + the unshifted suffix state (see k_linear_fix)
 

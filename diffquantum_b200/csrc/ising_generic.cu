@@ -152,6 +152,50 @@ __global__ void k_build_mdiag(double* __restrict__ m, int n, int n_zz, const int
     }
 }
 
+// ---- exact step (live reference semantics, sim_plain.py:135-150) without the dense matrix -----------------
+// psi <- exp(-i (Diag + sum_q x_q X_q)) psi evaluated as a scaled Taylor series on the vector, the matrix-free
+// variant the reference leaves commented at sim_plain.py:147 (expm_multiply).  diag[x] = c + sum_e g_e z_a z_b.
+__global__ void k_build_diag(double* __restrict__ diag, int n, int n_zz, const int2* __restrict__ pairs,
+                             const double* __restrict__ row) {
+    extern __shared__ double sh[];
+    double* ang = sh;
+    int2* pr = (int2*)(sh + n_zz);
+    for (int e = threadIdx.x; e < n_zz; e += blockDim.x) { ang[e] = row[1 + e]; pr[e] = pairs[e]; }
+    __syncthreads();
+    const double c = row[0];
+    const size_t N = (size_t)1 << n;
+    for (size_t x = blockIdx.x * (size_t)blockDim.x + threadIdx.x; x < N; x += (size_t)gridDim.x * blockDim.x) {
+        double a = c;
+        for (int e = 0; e < n_zz; ++e) a += (((x >> pr[e].x) ^ (x >> pr[e].y)) & 1) ? -ang[e] : ang[e];
+        diag[x] = a;
+    }
+}
+
+struct XTerms { int n; int bit[40]; double ang[40]; };
+
+// term_out = (scale / k) * (-i) * (diag .* term_in + sum_q ang_q term_in[x ^ bit_q]);  acc += term_out
+__global__ void k_taylor_term(const c128* __restrict__ tin, c128* __restrict__ tout, c128* __restrict__ acc,
+                              const double* __restrict__ diag, int n, XTerms xt, double f) {
+    const size_t N = (size_t)1 << n;
+    const c128* ti = tin + blockIdx.y * N;
+    c128* to = tout + blockIdx.y * N;
+    c128* ac = acc + blockIdx.y * N;
+    for (size_t x = blockIdx.x * (size_t)blockDim.x + threadIdx.x; x < N; x += (size_t)gridDim.x * blockDim.x) {
+        const c128 v = ti[x];
+        const double d = diag[x];
+        double hr = d * v.x, hi = d * v.y;
+        for (int q = 0; q < xt.n; ++q) {
+            const c128 w = ti[x ^ ((size_t)1 << xt.bit[q])];
+            hr = fma(xt.ang[q], w.x, hr);
+            hi = fma(xt.ang[q], w.y, hi);
+        }
+        const c128 t = make_double2(f * hi, -f * hr);          // -i (hr + i hi) = hi - i hr
+        to[x] = t;
+        const c128 a = ac[x];
+        ac[x] = make_double2(a.x + t.x, a.y + t.y);
+    }
+}
+
 inline int grid_for(size_t work, int sms) {
     size_t b = (work + kThreads - 1) / kThreads;
     size_t cap = (size_t)sms * 16;
@@ -203,6 +247,51 @@ int gen_evolve(dq_ising* p, c128* d_states, int batch, const double* d_rows, con
         for (int q = 0; q < p->n; ++q)
             k_rx<<<ghalf, kThreads, 0, st>>>(d_states, p->n, p->bitpos[q], d_trig + (size_t)k * p->n + q);
         p->ctx->launches += 1 + p->n;
+    }
+    DQ_CUDA(cudaGetLastError());
+    return DQ_OK;
+}
+
+int gen_evolve_exact(dq_ising* p, c128* d_states, int batch, const double* d_rows, const double* h_rows, int n_steps) {
+    const int sms = p->ctx->prop.multiProcessorCount;
+    cudaStream_t st = p->ctx->stream;
+    const size_t N = p->dim();
+    DQ_TRY(p->exact_diag.reserve(N * sizeof(double)));
+    DQ_TRY(p->exact_t0.reserve(N * batch * sizeof(c128)));
+    DQ_TRY(p->exact_t1.reserve(N * batch * sizeof(c128)));
+    dim3 grid(grid_for(N, sms), batch);
+    const size_t sh = p->n_zz * (sizeof(double) + sizeof(int2));
+    const int m = 18;                                           // theta <= 1: truncation < 1e-17
+    for (int k = 0; k < n_steps; ++k) {
+        const double* row = h_rows + (size_t)k * p->row_len;
+        double bound = fabs(row[0]);
+        for (int e = 0; e < p->n_zz; ++e) bound += fabs(row[1 + e]);
+        XTerms xt;
+        xt.n = p->n;
+        for (int q = 0; q < p->n; ++q) {
+            xt.bit[q] = p->bitpos[q];
+            xt.ang[q] = row[1 + p->n_zz + q];
+            bound += fabs(xt.ang[q]);
+        }
+        int s = 0;
+        while (ldexp(bound, -s) > 1.0) ++s;
+        DQ_REQUIRE(s <= 24, "exact step: ||dt H|| = %g is too large", bound);
+        k_build_diag<<<grid_for(N, sms), kThreads, sh, st>>>(p->exact_diag.as<double>(), p->n, p->n_zz, p->pairs_dev.as<int2>(),
+                                                            d_rows + (size_t)k * p->row_len);
+        p->ctx->launches++;
+        for (long long rep = 0; rep < (1LL << s); ++rep) {
+            c128* bufs[2] = {p->exact_t0.as<c128>(), p->exact_t1.as<c128>()};
+            // term 0 = a copy of the state (the kernel reads neighbours of `tin` while it updates the state in place)
+            DQ_CUDA(cudaMemcpyAsync(bufs[0], d_states, N * batch * sizeof(c128), cudaMemcpyDeviceToDevice, st));
+            const c128* tin = bufs[0];
+            for (int j = 1; j <= m; ++j) {
+                c128* tout = bufs[j & 1];
+                k_taylor_term<<<grid, kThreads, 0, st>>>(tin, tout, d_states, p->exact_diag.as<double>(), p->n, xt,
+                                                        ldexp(1.0, -s) / j);
+                p->ctx->launches++;
+                tin = tout;
+            }
+        }
     }
     DQ_CUDA(cudaGetLastError());
     return DQ_OK;

@@ -112,7 +112,7 @@ class IsingProblem(object):
 class IsingSimulator(object):
     """Device-side evolution and batched stochastic parameter-shift samples for an IsingProblem."""
 
-    def __init__(self, problem, device=0, per_step=10, basis='BSpline', engine=None, ket_group=None):
+    def __init__(self, problem, device=0, per_step=10, basis='BSpline', engine=None, ket_group=None, step='split'):
         self.problem = problem
         self.per_step = per_step
         self.basis = basis
@@ -128,6 +128,12 @@ class IsingSimulator(object):
             self.set_option("engine", engine)
         if ket_group is not None:
             self.set_option("ket_group", ket_group)
+        if step not in ('split', 'exact'):
+            raise ValueError("step must be 'split' (per-term product, diffqc.cc:155-164) or 'exact' "
+                             "(live semantics, sim_plain.py:135-150)")
+        self.step = step
+        if step == 'exact':
+            self.set_option("step", 1)
 
     def __del__(self):
         try:

@@ -105,6 +105,8 @@ int dq_ising_create(dq_context* ctx, int n_qubits, int n_zz, const int32_t* zz_p
                     dq_ising** out);
 int dq_ising_destroy(dq_ising* p);
 /* Tunables: "ket_group" (states co-resident in L2 per launch), "engine" (0 generic, 1 fused v2 = default when 12 <= n <= 20, 2 fused v3),
+ * "step" (0 = per-term product step, diffqc.cc:155-164; 1 = the reference's live exact step
+ * exp(-i dt H(t_k)) psi as a matrix-free scaled Taylor series, sim_plain.py:135-150 with :147; generic engine),
  * "linear" (1, fused v2 only: evolve one shifted ket per term plus the unshifted suffix state and obtain the
  * other sign from ket- = 2 a/sqrt(1+r^2) - ket+; same outputs to rounding, about half the trajectory-steps),
  * "time_launches" (1: bracket every pass-kernel launch with CUDA events, read back via dq_ising_last_stat). */

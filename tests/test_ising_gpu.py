@@ -155,3 +155,40 @@ def test_fused_gradients_agree_with_generic_engine(n, engine):
     if engine == 1:
         sim2.set_option("linear", 1)
         assert rel(sim2.shifted_energies(big, s_list[:1]), ref2) < TOL
+
+
+def test_exact_step_reproduces_the_reference_fixture(golden):
+    """The structured path with step='exact' against the reference's OWN outputs (demo_maxcut.py problem,
+    SimulatorPlain.trotter / compute_energy_grad_MC run unmodified: tests/golden/demo_bspline_ref.npz)."""
+    g = golden("demo_bspline_ref")
+    prob = dq.IsingProblem.maxcut(4, [[0, 1], [0, 3], [1, 2], [2, 3]])
+    sim = dq.IsingSimulator(prob, per_step=int(g["per_step"]), step="exact")
+    psi, en = sim.evolve(g["coeff"], 0, prob.T)
+    assert rel(psi[0], g["final"]) < TOL
+    assert abs(en[0] - complex(g["energy"]).real) < TOL * abs(complex(g["energy"]))
+    for k, s in enumerate(g["s"][:3]):
+        phi, _ = sim.evolve(g["coeff"], 0, float(s))
+        assert rel(phi[0], g["phis"][k]) < TOL
+    grads = sim.grad_samples(g["coeff"], g["s"])
+    assert rel(grads, g["grads"]) < TOL
+
+
+@pytest.mark.parametrize("n,per_step", [(6, 4), (10, 3), (14, 2), (16, 1)])
+def test_exact_step_vs_matrix_free_oracle(n, per_step):
+    """expm_multiply restatement of sim_plain.py:147 (oracle/restate.py evolve_exact_structured)."""
+    edges = graph_for(n)
+    prob = dq.IsingProblem.maxcut(n, edges)
+    ref = R.maxcut_structured(n, edges)
+    coeff = np.random.RandomState(n).normal(0, 1, [len(prob.terms), 6])
+    sim = dq.IsingSimulator(prob, per_step=per_step, step="exact")
+    assert sim.info("engine") == 0
+    ns, dt, ts = R.step_grid(0.3, 1.1, per_step)
+    u = R.coef_table_plain(coeff, ref["omegas"], ref["T"], ts)
+    want = R.evolve_exact_structured(ref, u, dt, ref["psi0"])
+    psi, en = sim.evolve(coeff, 0.3, 1.1)
+    assert rel(psi[0], want) < TOL
+    assert abs(np.linalg.norm(psi[0]) - 1) < 1e-12
+    if n <= 10:
+        g_ref, e_ref = R.grad_mc_structured(ref, coeff, 0.9, per_step, mode="exact", return_energies=True)
+        grads, energies = sim.grad_samples(coeff, [0.9], return_energies=True)
+        assert rel(energies[0], e_ref) < TOL and rel(grads[0], g_ref) < TOL
