@@ -42,6 +42,7 @@ rows = np.zeros((2, prob.row_len)); theta = np.linspace(0.1, 0.7, n)
 rows[:, 1 + prob.n_zz:] = theta
 st.evolve_rows(rows)
 want = np.exp(-2j * theta.sum()) * 2.0 ** (-0.5 * n)
+st.ops.ctx.synchronize()          # the kernels run on the library's stream, the copies below on torch's
 mine = st.psi[:4096].cpu().numpy(); tail = st.psi[-4096:].cpu().numpy()
 out["mixer_only_max_rel_err"] = float(max(np.abs(mine - want).max(), np.abs(tail - want).max()) / abs(want))
 out["exchanges_after_2_steps"] = st.exchanges
