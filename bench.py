@@ -53,6 +53,7 @@ def parse_args():
                     help="controls whose +/- trajectories the bounded CPU sample runs (of n_Hs)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--ket-group", type=int, default=0)
+    ap.add_argument("--item-tiles-log2", type=int, default=-1, help="fused v2: tiles per work item = 2^k (default: library default)")
     ap.add_argument("--engine", type=int, default=1, help="1 fused v2 (32 amps/thread), 2 fused v3 (16 amps/thread)")
     return ap.parse_args()
 
@@ -268,6 +269,8 @@ def run_b200_arm(a):
     sim = dq.IsingSimulator(prob, device=local, per_step=a.per_step, engine=a.engine)
     if a.ket_group:
         sim.set_option("ket_group", a.ket_group)
+    if a.item_tiles_log2 >= 0:
+        sim.set_option("item_tiles_log2", a.item_tiles_log2)
     if sim.info("engine") != a.engine:
         raise RuntimeError("fused engine %d not available for n=%d" % (a.engine, a.n))
     kernel_name = "k_f16_passes" if a.engine == 2 else "k_fused_passes"

@@ -16,6 +16,7 @@ struct dq_ising {
 
     int engine = 1;                // 0 generic, 1 fused v2 (32 amplitudes/thread, default), 2 fused v3 (16 amplitudes/thread); 12 <= n <= 20
     int ket_group = 0;             // states per fused launch; 0 = automatic (auto_ket_group below)
+    int item_tiles_log2 = 0;       // fused v2: a work item is 2^k consecutive tiles (one atomic / poll / release per item); measured: 0 is best (56.0 / 54.5 / 48.3 / 28.9 samples/s for k = 0..3 at n = 20, finer items pipeline better across pass boundaries)
     int grid_per_sm = 0;           // experiment knob: CTAs per SM in the persistent grid (0 = occupancy)
     int linear = 0;                // 1: estimator by linearity (n_H + 1 suffix trajectories per sample instead of 2 n_H)
     int time_launches = 0;         // 1: CUDA-event pairs around every pass-kernel launch (bench.py's roofline)

@@ -90,6 +90,9 @@ int dq_ising_set_option(dq_ising* p, const char* name, int64_t value) {
     if (!strcmp(name, "engine")) {
         DQ_REQUIRE(value >= 0 && value <= 2, "engine must be 0 (generic), 1 (fused v2) or 2 (fused v3)");
         p->engine = (int)value;
+    } else if (!strcmp(name, "item_tiles_log2")) {
+        DQ_REQUIRE(value >= 0 && value <= 6, "item_tiles_log2 out of range");
+        p->item_tiles_log2 = (int)value;
     } else if (!strcmp(name, "grid_per_sm")) {
         p->grid_per_sm = (int)value;
     } else if (!strcmp(name, "step")) {

@@ -115,6 +115,8 @@ struct LaunchArgs {
     int n_kets;
     int max_pass;
     int tiles_log2;
+    int sub_log2;                   // a work item is 2^sub_log2 consecutive tiles: one atomic / poll / release per item
+    int ipp_log2;                   // items per (ket, pass) = tiles >> sub_log2
     double r, ca, sa, c2a, s2a;     // shift gate: r, cos/sin(atan r), cos/sin(2 atan r)
     TypeGeom geom[2];
 };
@@ -202,15 +204,19 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 // One work item = (pass p, ket g, tile t_id); written to shared memory by thread 0.
 struct ItemInfo {
     unsigned item;
-    int p, g, t_id;
+    int p, g, t_id;                 // t_id = tile of THIS visit (an item is visited once per tile)
+    int grp, sub, ip;               // item index inside its (ket, pass); tile index inside the item; item parity (sh.red slot)
     int valid;                      // p < n_pass of that ket
     int ready;                      // its dependency was already satisfied when thread 0 polled
 };
 
 __device__ __forceinline__ void decode_item(const LaunchArgs& A, unsigned item, ItemInfo& I) {
     I.item = item;
-    I.t_id = (int)(item & ((1u << A.tiles_log2) - 1u));
-    const unsigned rest = item >> A.tiles_log2;
+    I.grp = (int)(item & ((1u << A.ipp_log2) - 1u));
+    I.sub = 0;
+    I.ip = 0;
+    I.t_id = I.grp << A.sub_log2;
+    const unsigned rest = item >> A.ipp_log2;
     I.g = (int)(rest % (unsigned)A.n_kets);
     I.p = (int)(rest / (unsigned)A.n_kets);
 }
@@ -273,7 +279,7 @@ __device__ __forceinline__ void flush_pending(const LaunchArgs& A, Shared& sh, P
 // sh.info[nb] half-way through so that every thread can start prefetching that tile in outer-B.
 template <bool SCALED, bool AJ, bool CROSS, int TYPE>
 __device__ __forceinline__ void process_tile(const LaunchArgs& A, const KetDesc* __restrict__ kd, const PassStep& P,
-                                             c128* __restrict__ tile, Shared& sh, const int p, const int t_id,
+                                             c128* __restrict__ tile, Shared& sh, const ItemInfo& I,
                                              const unsigned nxt_raw, const int nb, const unsigned total,
                                              PassStep* __restrict__ cache, const PassStep* (&cached_ps)[2],
                                              const int cb, int& next_cb, bool& next_tables_new, Pending& pd) {
@@ -281,6 +287,8 @@ __device__ __forceinline__ void process_tile(const LaunchArgs& A, const KetDesc*
     const TypeGeom& T = A.geom[TYPE];
     const int tid = threadIdx.x;
     const int flags = P.flags;
+    const int p = I.p, t_id = I.t_id;
+    const bool last_sub = I.sub + 1 == (1 << A.sub_log2);
 
     // tile geometry
     size_t tbase, xK, xJ;
@@ -334,10 +342,18 @@ __device__ __forceinline__ void process_tile(const LaunchArgs& A, const KetDesc*
     nI.valid = 0;
     nI.ready = 0;
     if (tid == 0) {
-        decode_item(A, nxt_raw, nI);
-        if (nxt_raw < total) {
-            nI.valid = nI.p < A.kets[nI.g].n_pass;
-            polled = nI.p > 0 ? ld_acquire(&A.counters[1 + nI.g]) : 0u;
+        if (!last_sub) {                     // next visit = next tile of the same item: nothing to fetch or poll
+            nI = I;
+            nI.sub = I.sub + 1;
+            nI.t_id = I.t_id + 1;
+            nI.valid = 1;
+        } else {
+            decode_item(A, nxt_raw, nI);
+            nI.ip = I.ip ^ 1;
+            if (nxt_raw < total) {
+                nI.valid = nI.p < A.kets[nI.g].n_pass;
+                polled = nI.p > 0 ? ld_acquire(&A.counters[1 + nI.g]) : 0u;
+            }
         }
     }
     TRACE(A, trace_item, 2);
@@ -407,7 +423,7 @@ __device__ __forceinline__ void process_tile(const LaunchArgs& A, const KetDesc*
 #pragma unroll
     for (int j = 0; j < kRegs; ++j) if (!(DQ_EXP & 2)) tile[G::swz(iJ | (j << G::j0))] = v[j];
     if (tid == 0) {                          // publish the following item
-        nI.ready = nI.valid && (nI.p == 0 || polled >= (unsigned)nI.p << A.tiles_log2);
+        nI.ready = nI.valid && (!last_sub || nI.p == 0 || polled >= (unsigned)nI.p << A.ipp_log2);
         sh.info[nb] = nI;
     }
     TRACE(A, trace_item, 3);
@@ -492,10 +508,10 @@ __device__ __forceinline__ void process_tile(const LaunchArgs& A, const KetDesc*
         }
         if (do_energy) {
             for (int o = 16; o > 0; o >>= 1) e += __shfl_xor_sync(0xffffffffu, e, o);
-            if ((tid & 31) == 0) sh.red[nb ^ 1][tid >> 5] = e;
+            if ((tid & 31) == 0) sh.red[I.ip][tid >> 5] = I.sub == 0 ? e : sh.red[I.ip][tid >> 5] + e;
             if (CROSS && cr) {
                 for (int o = 16; o > 0; o >>= 1) e2 += __shfl_xor_sync(0xffffffffu, e2, o);
-                if ((tid & 31) == 0) sh.red2[nb ^ 1][tid >> 5] = e2;
+                if ((tid & 31) == 0) sh.red2[I.ip][tid >> 5] = I.sub == 0 ? e2 : sh.red2[I.ip][tid >> 5] + e2;
             }
         }
     }
@@ -512,7 +528,8 @@ __global__ void __launch_bounds__(kThreads, DQ_CTAS_PER_SM) k_fused_passes(const
     __shared__ Shared sh;
 
     const int tid = threadIdx.x;
-    const unsigned total = ((unsigned)A.max_pass * (unsigned)A.n_kets) << A.tiles_log2;
+    const unsigned total = ((unsigned)A.max_pass * (unsigned)A.n_kets) << A.ipp_log2;
+    const int nsub = 1 << A.sub_log2;
     const PassStep* cached_ps[2] = {nullptr, nullptr};
     int cur = 0, cb = 0;
     bool prefetched = false, tables_new = false;
@@ -557,7 +574,7 @@ __global__ void __launch_bounds__(kThreads, DQ_CTAS_PER_SM) k_fused_passes(const
             if (tid == 0) {
                 flush_pending(A, sh, pd);      // always before spinning: the dependency may be our own tile
                 if (I.p > 0) {
-                    const unsigned need = (unsigned)I.p << A.tiles_log2;
+                    const unsigned need = (unsigned)I.p << A.ipp_log2;
                     while (ld_acquire(&A.counters[1 + I.g]) < need) __nanosleep(32);
                 }
             }
@@ -576,7 +593,7 @@ __global__ void __launch_bounds__(kThreads, DQ_CTAS_PER_SM) k_fused_passes(const
             cp_async_commit();
         }
         unsigned nxt_raw = 0;
-        if (tid == 0) nxt_raw = atomicAdd(&A.counters[0], 1u);      // consumed inside process_tile
+        if (tid == 0 && I.sub + 1 == nsub) nxt_raw = atomicAdd(&A.counters[0], 1u);      // consumed inside process_tile
         TRACE(A, I.item, 0);
         cp_async_wait_all();                   // this thread's own slots (and its share of the tables) landed
         if (tables_new) __syncthreads();       // tables in cache[cb] become visible to every thread
@@ -585,19 +602,19 @@ __global__ void __launch_bounds__(kThreads, DQ_CTAS_PER_SM) k_fused_passes(const
         const PassStep& P = cache[cb];
         const int flags = P.flags;
         if (P.type == 0)
-            process_tile<SCALED, AJ, CROSS, 0>(A, kd, P, tile, sh, I.p, I.t_id, nxt_raw, cur ^ 1, total, cache, cached_ps, cb,
+            process_tile<SCALED, AJ, CROSS, 0>(A, kd, P, tile, sh, I, nxt_raw, cur ^ 1, total, cache, cached_ps, cb,
                                         next_cb, next_tables_new, pd);
         else
-            process_tile<SCALED, AJ, CROSS, 1>(A, kd, P, tile, sh, I.p, I.t_id, nxt_raw, cur ^ 1, total, cache, cached_ps, cb,
+            process_tile<SCALED, AJ, CROSS, 1>(A, kd, P, tile, sh, I, nxt_raw, cur ^ 1, total, cache, cached_ps, cb,
                                         next_cb, next_tables_new, pd);
         TRACE(A, I.item, 7);
-        if (tid == 0) {                        // published after the next item's mid-tile barrier
+        if (tid == 0 && I.sub + 1 == nsub) {   // item complete: published after the next item's mid-tile barrier
             pd.g = I.g;
-            pd.partial = ((flags & F_ENERGY) && kd->partial) ? kd->partial + I.t_id : nullptr;
-            pd.partial2 = (CROSS && (flags & F_ENERGY) && kd->cross) ? kd->partial2 + I.t_id : nullptr;
+            pd.partial = ((flags & F_ENERGY) && kd->partial) ? kd->partial + I.grp : nullptr;
+            pd.partial2 = (CROSS && (flags & F_ENERGY) && kd->cross) ? kd->partial2 + I.grp : nullptr;
             pd.escale = kd->escale;
             pd.escale2 = kd->escale2;
-            pd.slot = cur;
+            pd.slot = I.ip;
         }
         prefetched = sh.info[cur ^ 1].ready != 0;
         cur ^= 1;
@@ -714,10 +731,10 @@ __global__ void __launch_bounds__(128) k_setup(const SetupJob* __restrict__ jobs
     }
 }
 
-__global__ void k_sum_partials(const double* __restrict__ partial, int tiles, const int* __restrict__ out_index,
+__global__ void k_sum_partials(const double* __restrict__ partial, int tiles, int count, const int* __restrict__ out_index,
                                double* __restrict__ out) {
     double acc = 0.0;
-    for (int i = threadIdx.x; i < tiles; i += 32) acc += partial[(size_t)blockIdx.x * tiles + i];
+    for (int i = threadIdx.x; i < count; i += 32) acc += partial[(size_t)blockIdx.x * tiles + i];
     for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
     if (threadIdx.x == 0) out[out_index[blockIdx.x]] = acc;
 }
@@ -737,7 +754,7 @@ __global__ void k_linear_fix(double* __restrict__ out, const double* __restrict_
 // ------------------------------------------------------------------------------------------
 struct Plan {
     bool ok = false;
-    int n = 0, n_col_bits = 0, tiles_log2 = 0;
+    int n = 0, n_col_bits = 0, tiles_log2 = 0, sub_log2 = 0;
     bool has_aj = false;
     TypePlan types[2];
     int jphys[2][5];
@@ -939,11 +956,14 @@ static int launch_group(dq_ising* p, Plan* pl, const KetDesc* d_kets, int n_kets
     A.n_kets = n_kets;
     A.max_pass = max_pass;
     A.tiles_log2 = pl->tiles_log2;
+    pl->sub_log2 = std::min(std::max(0, p->item_tiles_log2), pl->tiles_log2);
+    A.sub_log2 = pl->sub_log2;
+    A.ipp_log2 = pl->tiles_log2 - pl->sub_log2;
     const double alpha = atan(r);
     A.r = r; A.ca = cos(alpha); A.sa = sin(alpha); A.c2a = cos(2 * alpha); A.s2a = sin(2 * alpha);
     A.geom[0] = pl->types[0].g;
     A.geom[1] = pl->types[1].g;
-    const long long all_items = ((long long)n_kets << pl->tiles_log2) * max_pass;
+    const long long all_items = ((long long)n_kets << A.ipp_log2) * max_pass;
     long long grid = (long long)p->ctx->prop.multiProcessorCount * (p->grid_per_sm > 0 ? std::min(p->grid_per_sm, pl->ctas_per_sm) : pl->ctas_per_sm);
     if (grid > all_items) grid = all_items;
     const bool timed = p->time_launches != 0;
@@ -1085,7 +1105,7 @@ int fused_evolve(dq_ising* p, c128* d_states, int batch, const double* h_rows, i
             for (int g = 0; g < batch; ++g) idx[g] = g;
             DQ_TRY(pl->out_index.reserve(batch * sizeof(int)));
             DQ_CUDA(cudaMemcpyAsync(pl->out_index.p, idx.data(), batch * sizeof(int), cudaMemcpyHostToDevice, st));
-            k_sum_partials<<<batch, 32, 0, st>>>(pl->partials.as<double>(), tiles, pl->out_index.as<int>(), d_energies);
+            k_sum_partials<<<batch, 32, 0, st>>>(pl->partials.as<double>(), tiles, tiles >> pl->sub_log2, pl->out_index.as<int>(), d_energies);
             p->ctx->launches++;
         }
     }
@@ -1251,12 +1271,12 @@ int fused_grad_run(dq_ising* p) {
     for (const Group& g : groups)
         DQ_TRY(launch_group(p, pl, pl->kets.as<KetDesc>() + g.first, g.count, g.max_pass, scaled, s.r));
 
-    k_sum_partials<<<B * kets_per, 32, 0, st>>>(pl->partials.as<double>(), tiles, pl->out_index.as<int>(),
+    k_sum_partials<<<B * kets_per, 32, 0, st>>>(pl->partials.as<double>(), tiles, tiles >> pl->sub_log2, pl->out_index.as<int>(),
                                                  p->energies.as<double>());
     p->ctx->launches++;
     if (linear) {
         double* ea_out = pl->ea.as<double>() + (size_t)B * tiles;
-        k_sum_partials<<<B, 32, 0, st>>>(pl->ea.as<double>(), tiles, pl->out_index.as<int>(), ea_out);
+        k_sum_partials<<<B, 32, 0, st>>>(pl->ea.as<double>(), tiles, tiles >> pl->sub_log2, pl->out_index.as<int>(), ea_out);
         const int total = B * kets_per;
         k_linear_fix<<<(total + 255) / 256, 256, 0, st>>>(p->energies.as<double>(), ea_out, kets_per, total, s.r);
         p->ctx->launches += 2;
