@@ -12,6 +12,10 @@ struct dq_ising {
     std::vector<int> pa, pb;       // pair endpoints as physical bit positions
     bool identity_layout = true;   // bitpos[q] == n-1-q for all q
     dq::DevBuf mdiag;              // double[2^n], physical order
+    dq::DevBuf mdiag_ref;          // staging: a caller-supplied table in reference order
+    std::vector<double> m_zz_host, m_diag_host;   // observable as given at creation (the layout can change later)
+    double m_const_host = 0.0;
+    int layout_mode = 1;           // 0 reference order (bit n-1-q), 1 automatic (fused engine: no ZZ pair inside a register set)
     dq::DevBuf pairs_dev;          // int2[n_zz] physical bit positions
 
     int engine = 1;                // 0 generic, 1 fused v2 (32 amplitudes/thread, default), 2 fused v3 (16 amplitudes/thread); 12 <= n <= 20
@@ -48,7 +52,7 @@ namespace dq {
 // States co-resident per fused launch: as many as keep the work ring inside ~80 MiB of the 126 MB L2
 // (5 x 16 MiB measured best at n = 20), at least 5, at most 96 (small states need many kets to fill 148 SMs).
 inline int auto_ket_group(const dq_ising* p) {
-    if (p->ket_group > 0) return p->ket_group;
+    if (p->ket_group > 0) return p->ket_group > 96 ? 96 : p->ket_group;
     const size_t state_bytes = sizeof(double2) << p->n;
     const size_t g = ((size_t)80 << 20) / state_bytes;
     return (int)(g < 5 ? 5 : (g > 96 ? 96 : g));
@@ -59,6 +63,7 @@ struct ShiftDesc { int kind; int b0; int b1; double sign; };
 int gen_fill_uniform(dq_ising* p, c128* psi, int batch);
 int gen_permute_in(dq_ising* p, const c128* src_ref_order, c128* dst_phys, int batch);
 int gen_permute_out(dq_ising* p, const c128* src_phys, c128* dst_ref_order, int batch);
+int gen_permute_real_in(dq_ising* p, const double* src_ref_order, double* dst_phys);
 int gen_trig(dq_ising* p, const double* d_rows, int64_t n_rows, double2* d_trig);
 int gen_evolve(dq_ising* p, c128* d_states, int batch, const double* d_rows, const double2* d_trig,
                int n_steps);

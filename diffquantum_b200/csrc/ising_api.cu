@@ -19,6 +19,114 @@ int check_rows(const dq_ising* p, const double* rows, int64_t n_rows, const char
 bool use_f16(const dq_ising* p) { return p->step_mode == 0 && p->engine == 2 && dq::f16_supported(p); }
 bool use_fused(const dq_ising* p) { return p->step_mode == 0 && p->engine >= 1 && !use_f16(p) && dq::fused_supported(p); }
 
+// ---- qubit -> bit layout ---------------------------------------------------------------------------------
+// Reference order is bit n-1-q for qubit q (np.kron order, demo_maxcut.py:53-57).  The fused engine keeps two
+// sets of five index bits in registers (J_L = bits 0..4 of the L pass, J_H = tile bits 7..11 of the H pass);
+// a ZZ pair with both ends inside one set costs a 32-entry table multiply per amplitude (the `aj` factor).
+// Automatic layout: put two disjoint independent sets of the ZZ graph on those bits, keep every other qubit
+// in reference order.  Falls back to the reference order when no such sets are found.
+bool choose_layout(const dq_ising* p, int* bitpos) {
+    const int n = p->n;
+    for (int q = 0; q < n; ++q) bitpos[q] = n - 1 - q;
+    if (p->layout_mode == 0 || n < 12 || n > 20) return false;
+    int jl[5], jh[5];
+    const int a = 22 - n;
+    for (int i = 0; i < 5; ++i) {
+        jl[i] = i;
+        const int t = 7 + i;
+        jh[i] = t < a ? t : 10 + (t - a);
+    }
+    std::vector<unsigned> adj(n, 0u);
+    for (int e = 0; e < p->n_zz; ++e) {
+        adj[p->qa[e]] |= 1u << p->qb[e];
+        adj[p->qb[e]] |= 1u << p->qa[e];
+    }
+    auto independent = [&](const int* pos) {
+        unsigned set = 0;
+        for (int i = 0; i < 5; ++i) set |= 1u << (n - 1 - pos[i]);     // qubit sitting on bit `pos` in reference order
+        for (int q = 0; q < n; ++q)
+            if (((set >> q) & 1u) && (adj[q] & set)) return false;
+        return true;
+    };
+    if (independent(jl) && independent(jh)) return false;               // the reference order is already good
+    unsigned long long rng = 0x9E3779B97F4A7C15ull;
+    std::vector<int> order(n);
+    for (int attempt = 0; attempt < 4000; ++attempt) {
+        for (int q = 0; q < n; ++q) order[q] = q;
+        for (int q = n - 1; q > 0; --q) {
+            rng = rng * 6364136223846793005ull + 1442695040888963407ull;
+            std::swap(order[q], order[(int)((rng >> 33) % (unsigned)(q + 1))]);
+        }
+        unsigned used = 0, sets[2] = {0u, 0u};
+        bool ok = true;
+        for (int s = 0; s < 2 && ok; ++s) {
+            int cnt = 0;
+            for (int k = 0; k < n && cnt < 5; ++k) {
+                const int q = order[k];
+                if (((used >> q) & 1u) || (adj[q] & sets[s])) continue;
+                sets[s] |= 1u << q;
+                used |= 1u << q;
+                ++cnt;
+            }
+            ok = cnt == 5;
+        }
+        if (!ok) continue;
+        unsigned taken_pos = 0;
+        for (int s = 0; s < 2; ++s) {
+            const int* pos = s == 0 ? jl : jh;
+            int i = 0;
+            for (int q = n - 1; q >= 0; --q)                            // ascending bit = descending qubit, as in the reference order
+                if ((sets[s] >> q) & 1u) { bitpos[q] = pos[i]; taken_pos |= 1u << pos[i]; ++i; }
+        }
+        int pos = 0;
+        for (int q = n - 1; q >= 0; --q) {
+            if ((used >> q) & 1u) continue;
+            while ((taken_pos >> pos) & 1u) ++pos;
+            bitpos[q] = pos++;
+        }
+        return true;
+    }
+    for (int q = 0; q < n; ++q) bitpos[q] = n - 1 - q;
+    return false;
+}
+
+// (re)build everything that depends on the layout: pair endpoints, the observable diagonal, engine plans
+int apply_layout(dq_ising* p) {
+    DQ_TRY(p->ctx->set_device());
+    DQ_CUDA(cudaStreamSynchronize(p->ctx->stream));
+    dq::fused_release(p);
+    dq::f16_release(p);
+    p->st.valid = false;
+    p->identity_layout = !choose_layout(p, p->bitpos);
+    const int n_zz = p->n_zz;
+    p->pa.resize(n_zz);
+    p->pb.resize(n_zz);
+    std::vector<int2> pr(n_zz);
+    for (int e = 0; e < n_zz; ++e) {
+        p->pa[e] = p->bitpos[p->qa[e]];
+        p->pb[e] = p->bitpos[p->qb[e]];
+        pr[e] = make_int2(p->pa[e], p->pb[e]);
+    }
+    DQ_TRY(p->pairs_dev.reserve((n_zz ? n_zz : 1) * sizeof(int2)));
+    DQ_TRY(p->mdiag.reserve(p->dim() * sizeof(double)));
+    if (n_zz) DQ_CUDA(cudaMemcpy(p->pairs_dev.p, pr.data(), n_zz * sizeof(int2), cudaMemcpyHostToDevice));
+    if (!p->m_diag_host.empty()) {
+        // caller's table is in reference order
+        if (p->identity_layout) {
+            DQ_CUDA(cudaMemcpy(p->mdiag.p, p->m_diag_host.data(), p->dim() * sizeof(double), cudaMemcpyHostToDevice));
+        } else {
+            DQ_TRY(p->mdiag_ref.reserve(p->dim() * sizeof(double)));
+            DQ_CUDA(cudaMemcpy(p->mdiag_ref.p, p->m_diag_host.data(), p->dim() * sizeof(double), cudaMemcpyHostToDevice));
+            DQ_TRY(dq::gen_permute_real_in(p, p->mdiag_ref.as<double>(), p->mdiag.as<double>()));
+            DQ_CUDA(cudaStreamSynchronize(p->ctx->stream));
+            p->mdiag_ref.release();
+        }
+    } else {
+        DQ_TRY(dq::gen_build_mdiag(p, p->m_zz_host.data(), p->m_const_host));
+    }
+    return DQ_OK;
+}
+
 }  // namespace
 
 extern "C" {
@@ -45,28 +153,12 @@ int dq_ising_create(dq_context* ctx, int n_qubits, int n_zz, const int32_t* zz_p
         p->qa.push_back(a);
         p->qb.push_back(b);
     }
-    for (int q = 0; q < n_qubits; ++q) p->bitpos[q] = n_qubits - 1 - q;     // reference order
-    p->identity_layout = true;
-    p->pa.resize(n_zz);
-    p->pb.resize(n_zz);
-    std::vector<int2> pr(n_zz);
-    for (int e = 0; e < n_zz; ++e) {
-        p->pa[e] = p->bitpos[p->qa[e]];
-        p->pb[e] = p->bitpos[p->qb[e]];
-        pr[e] = make_int2(p->pa[e], p->pb[e]);
-    }
-    int s = p->pairs_dev.reserve((n_zz ? n_zz : 1) * sizeof(int2));
-    if (s == DQ_OK) s = p->mdiag.reserve(p->dim() * sizeof(double));
+    if (m_diag) p->m_diag_host.assign(m_diag, m_diag + p->dim());
+    p->m_zz_host.assign(n_zz ? n_zz : 1, 0.0);
+    if (m_zz) for (int e = 0; e < n_zz; ++e) p->m_zz_host[e] = m_zz[e];
+    p->m_const_host = m_const;
+    const int s = apply_layout(p);
     if (s != DQ_OK) { dq_ising_destroy(p); return s; }
-    if (n_zz) DQ_CUDA(cudaMemcpy(p->pairs_dev.p, pr.data(), n_zz * sizeof(int2), cudaMemcpyHostToDevice));
-    if (m_diag) {
-        // host table in reference order -> physical order (identity layout today)
-        DQ_CUDA(cudaMemcpy(p->mdiag.p, m_diag, p->dim() * sizeof(double), cudaMemcpyHostToDevice));
-    } else {
-        std::vector<double> zero(n_zz ? n_zz : 1, 0.0);
-        s = dq::gen_build_mdiag(p, m_zz ? m_zz : zero.data(), m_const);
-        if (s != DQ_OK) { dq_ising_destroy(p); return s; }
-    }
     *out = p;
     return DQ_OK;
 }
@@ -77,7 +169,7 @@ int dq_ising_destroy(dq_ising* p) {
     cudaStreamSynchronize(p->ctx->stream);
     dq::fused_release(p);
     dq::f16_release(p);
-    dq::DevBuf* bufs[] = {&p->mdiag, &p->pairs_dev, &p->states, &p->phi, &p->rows_a, &p->rows_b, &p->trig_a,
+    dq::DevBuf* bufs[] = {&p->mdiag, &p->mdiag_ref, &p->pairs_dev, &p->states, &p->phi, &p->rows_a, &p->rows_b, &p->trig_a,
                           &p->trig_b, &p->energies, &p->scratch, &p->io, &p->shift_desc, &p->st.psi0, &p->exact_diag, &p->exact_t0,
                           &p->exact_t1};
     for (auto* b : bufs) b->release();
@@ -98,6 +190,12 @@ int dq_ising_set_option(dq_ising* p, const char* name, int64_t value) {
     } else if (!strcmp(name, "step")) {
         DQ_REQUIRE(value == 0 || value == 1, "step must be 0 (split) or 1 (exact)");
         p->step_mode = (int)value;
+    } else if (!strcmp(name, "layout")) {
+        DQ_REQUIRE(value == 0 || value == 1, "layout must be 0 (reference bit order) or 1 (automatic)");
+        if (p->layout_mode != (int)value) {
+            p->layout_mode = (int)value;
+            DQ_TRY(apply_layout(p));
+        }
     } else if (!strcmp(name, "linear")) {
         p->linear = value != 0;
     } else if (!strcmp(name, "time_launches")) {
@@ -117,6 +215,7 @@ int dq_ising_get_info(dq_ising* p, const char* name, int64_t* value) {
     if (!strcmp(name, "engine")) *value = use_f16(p) ? 2 : (use_fused(p) ? 1 : 0);
     else if (!strcmp(name, "ket_group")) *value = dq::auto_ket_group(p);
     else if (!strcmp(name, "row_len")) *value = p->row_len;
+    else if (!strcmp(name, "identity_layout")) *value = p->identity_layout ? 1 : 0;
     else if (!strcmp(name, "n_qubits")) *value = p->n;
     else { dq::set_error("dq_ising_get_info: unknown name '%s'", name); return DQ_ERR_INVALID; }
     return DQ_OK;

@@ -36,6 +36,7 @@ constexpr int kThreads = 128;              // kTile / 32
 constexpr int kRegs = 32;                  // amplitudes per thread
 constexpr int kMaxNbr = 3;                 // neighbour bits per register qubit held in tables
 constexpr int kMaxPairs = 128;
+constexpr int kMaxGroup = 96;              // kets per launch (their descriptors are staged in shared memory)
 #ifndef DQ_EXP
 #define DQ_EXP 0      // timing experiments only: 1 no FP64 math, 2 no smem exchange, 4 no global traffic
 #endif
@@ -81,7 +82,7 @@ struct TypePlan {
     signed char cls[kMaxPairs], i0[kMaxPairs], i1[kMaxPairs];
 };
 
-struct KetDesc {
+struct __align__(16) KetDesc {
     const c128* src;                // read by pass 0
     c128* buf;                      // written by every storing pass, read by passes > 0
     const PassStep* steps;
@@ -98,6 +99,8 @@ struct KetDesc {
     double escale2;
     double pad2_;
 };
+
+static_assert(sizeof(KetDesc) % 16 == 0, "KetDesc is copied to shared memory in 16-byte pieces");
 
 struct SetupJob {
     long long row_pre;              // row index into the angle table, -1 = none
@@ -279,7 +282,8 @@ __device__ __forceinline__ void flush_pending(const LaunchArgs& A, Shared& sh, P
 // sh.info[nb] half-way through so that every thread can start prefetching that tile in outer-B.
 template <bool SCALED, bool AJ, bool CROSS, int TYPE>
 __device__ __forceinline__ void process_tile(const LaunchArgs& A, const KetDesc* __restrict__ kd, const PassStep& P,
-                                             c128* __restrict__ tile, Shared& sh, const ItemInfo& I,
+                                             c128* __restrict__ tile, Shared& sh, const KetDesc* __restrict__ skets,
+                                             const ItemInfo& I,
                                              const unsigned nxt_raw, const int nb, const unsigned total,
                                              PassStep* __restrict__ cache, const PassStep* (&cached_ps)[2],
                                              const int cb, int& next_cb, bool& next_tables_new, Pending& pd) {
@@ -351,7 +355,7 @@ __device__ __forceinline__ void process_tile(const LaunchArgs& A, const KetDesc*
             decode_item(A, nxt_raw, nI);
             nI.ip = I.ip ^ 1;
             if (nxt_raw < total) {
-                nI.valid = nI.p < A.kets[nI.g].n_pass;
+                nI.valid = nI.p < skets[nI.g].n_pass;
                 polled = nI.p > 0 ? ld_acquire(&A.counters[1 + nI.g]) : 0u;
             }
         }
@@ -449,7 +453,7 @@ __device__ __forceinline__ void process_tile(const LaunchArgs& A, const KetDesc*
         next_cb = cb;
         next_tables_new = false;
         if (N.ready) {                       // ... so the next tile may land in them while we finish this one
-            const KetDesc* __restrict__ nkd = A.kets + N.g;
+            const KetDesc* __restrict__ nkd = skets + N.g;
             const PassStep* nps = nkd->steps + N.p;
             if (nps != cached_ps[cb]) {
                 next_cb = cb ^ 1;
@@ -525,6 +529,9 @@ __global__ void __launch_bounds__(kThreads, DQ_CTAS_PER_SM) k_fused_passes(const
     extern __shared__ __align__(16) unsigned char smem_raw[];
     c128* tile = reinterpret_cast<c128*>(smem_raw);
     PassStep* cache = reinterpret_cast<PassStep*>(smem_raw + sizeof(c128) * kTile);     // two slots
+    // Ket descriptors live in shared memory: the acquire / release fences of the item protocol invalidate
+    // L1 (CCTL.IVALL), so every kd-> field read from global memory was an exposed L2 round trip per tile.
+    KetDesc* skets = reinterpret_cast<KetDesc*>(smem_raw + sizeof(c128) * kTile + 2 * sizeof(PassStep));
     __shared__ Shared sh;
 
     const int tid = threadIdx.x;
@@ -541,13 +548,25 @@ __global__ void __launch_bounds__(kThreads, DQ_CTAS_PER_SM) k_fused_passes(const
     pd.escale2 = 0.0;
     pd.slot = 0;
 
+    // thread 0 reserves items ONE AHEAD: q_next is the raw index of the item after sh.info[cur], taken from
+    // the global counter a whole tile earlier, so the atomic's round trip is never waited for
+    unsigned q_next = 0;
     if (tid == 0) {
+        const unsigned first = atomicAdd(&A.counters[0], 1u);
+        q_next = atomicAdd(&A.counters[0], 1u);
         ItemInfo I;
-        decode_item(A, atomicAdd(&A.counters[0], 1u), I);
-        I.valid = I.item < total && I.p < A.kets[I.g].n_pass;
+        decode_item(A, first, I);
+        I.valid = 0;                           // completed below, once the descriptors are in shared memory
         I.ready = 0;
         sh.info[0] = I;
     }
+    {
+        const int4* src = reinterpret_cast<const int4*>(A.kets);
+        int4* dst = reinterpret_cast<int4*>(skets);
+        for (int i = tid; i < A.n_kets * (int)(sizeof(KetDesc) / 16); i += kThreads) dst[i] = __ldg(src + i);
+    }
+    __syncthreads();
+    if (tid == 0) sh.info[0].valid = sh.info[0].item < total && sh.info[0].p < skets[sh.info[0].g].n_pass;
     __syncthreads();
 
     for (;;) {
@@ -558,8 +577,9 @@ __global__ void __launch_bounds__(kThreads, DQ_CTAS_PER_SM) k_fused_passes(const
             if (tid == 0) {
                 flush_pending(A, sh, pd);
                 ItemInfo N;
-                decode_item(A, atomicAdd(&A.counters[0], 1u), N);
-                N.valid = N.item < total && N.p < A.kets[N.g].n_pass;
+                decode_item(A, q_next, N);
+                q_next = atomicAdd(&A.counters[0], 1u);
+                N.valid = N.item < total && N.p < skets[N.g].n_pass;
                 N.ready = 0;
                 sh.info[cur ^ 1] = N;
             }
@@ -568,7 +588,7 @@ __global__ void __launch_bounds__(kThreads, DQ_CTAS_PER_SM) k_fused_passes(const
             prefetched = false;
             continue;
         }
-        const KetDesc* __restrict__ kd = A.kets + I.g;
+        const KetDesc* __restrict__ kd = skets + I.g;
         if (!prefetched) {                     // cold path: wait for the dependency, then fetch tile and tables
             __syncthreads();                   // previous item's stores are issued: its release may go out
             if (tid == 0) {
@@ -593,7 +613,10 @@ __global__ void __launch_bounds__(kThreads, DQ_CTAS_PER_SM) k_fused_passes(const
             cp_async_commit();
         }
         unsigned nxt_raw = 0;
-        if (tid == 0 && I.sub + 1 == nsub) nxt_raw = atomicAdd(&A.counters[0], 1u);      // consumed inside process_tile
+        if (tid == 0 && I.sub + 1 == nsub) {   // consumed inside process_tile
+            nxt_raw = q_next;
+            q_next = atomicAdd(&A.counters[0], 1u);
+        }
         TRACE(A, I.item, 0);
         cp_async_wait_all();                   // this thread's own slots (and its share of the tables) landed
         if (tables_new) __syncthreads();       // tables in cache[cb] become visible to every thread
@@ -602,10 +625,10 @@ __global__ void __launch_bounds__(kThreads, DQ_CTAS_PER_SM) k_fused_passes(const
         const PassStep& P = cache[cb];
         const int flags = P.flags;
         if (P.type == 0)
-            process_tile<SCALED, AJ, CROSS, 0>(A, kd, P, tile, sh, I, nxt_raw, cur ^ 1, total, cache, cached_ps, cb,
+            process_tile<SCALED, AJ, CROSS, 0>(A, kd, P, tile, sh, skets, I, nxt_raw, cur ^ 1, total, cache, cached_ps, cb,
                                         next_cb, next_tables_new, pd);
         else
-            process_tile<SCALED, AJ, CROSS, 1>(A, kd, P, tile, sh, I, nxt_raw, cur ^ 1, total, cache, cached_ps, cb,
+            process_tile<SCALED, AJ, CROSS, 1>(A, kd, P, tile, sh, skets, I, nxt_raw, cur ^ 1, total, cache, cached_ps, cb,
                                         next_cb, next_tables_new, pd);
         TRACE(A, I.item, 7);
         if (tid == 0 && I.sub + 1 == nsub) {   // item complete: published after the next item's mid-tile barrier
@@ -874,7 +897,7 @@ static Plan* get_plan(dq_ising* p) {
     pl->has_aj = pl->types[0].has_aj || pl->types[1].has_aj;
     pl->n_col_bits = p->n - 10;
     pl->tiles_log2 = p->n - kTileBits;
-    pl->smem_bytes = sizeof(c128) * kTile + 2 * sizeof(PassStep);
+    pl->smem_bytes = sizeof(c128) * kTile + 2 * sizeof(PassStep) + kMaxGroup * sizeof(KetDesc);
     if (pl->d_types.reserve(sizeof(TypePlan) * 2) != DQ_OK) return pl;
     if (cudaMemcpy(pl->d_types.p, pl->types, sizeof(TypePlan) * 2, cudaMemcpyHostToDevice) != cudaSuccess) return pl;
     int occ = 0, o2 = 0;
@@ -937,6 +960,7 @@ static long long all_items_for_trace(int n_kets, int tiles_log2, int max_pass) {
 
 static int launch_group(dq_ising* p, Plan* pl, const KetDesc* d_kets, int n_kets, int max_pass, bool scaled, double r) {
     cudaStream_t st = p->ctx->stream;
+    DQ_REQUIRE(n_kets <= kMaxGroup, "fused engine: at most 96 kets per launch group");
     if (pl->counter_cursor + 1 + n_kets > pl->counter_slots) pl->counter_cursor = 0;
     unsigned* ctr = pl->counters.as<unsigned>() + pl->counter_cursor;
     pl->counter_cursor += 1 + n_kets;

@@ -17,13 +17,14 @@ __global__ void k_fill_uniform(c128* psi, size_t total, double amp) {
 // dst[phys(x)] = src[x] (to_phys) or dst[x] = src[phys(x)]; bit k of x (reference order) moves to
 // physical bit map[k].
 struct BitMap { int8_t map[40]; };
-__global__ void k_permute(const c128* __restrict__ src, c128* __restrict__ dst, int n, BitMap bm,
+template <typename T>
+__global__ void k_permute(const T* __restrict__ src, T* __restrict__ dst, int n, BitMap bm,
                           int to_phys) {
     size_t N = (size_t)1 << n;
     size_t x = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
     size_t stride = (size_t)gridDim.x * blockDim.x;
-    const c128* s = src + blockIdx.y * N;
-    c128* d = dst + blockIdx.y * N;
+    const T* s = src + blockIdx.y * N;
+    T* d = dst + blockIdx.y * N;
     for (; x < N; x += stride) {
         size_t y = 0;
         for (int k = 0; k < n; ++k) y |= ((x >> k) & 1) << bm.map[k];
@@ -213,17 +214,19 @@ int gen_fill_uniform(dq_ising* p, c128* psi, int batch) {
     return DQ_OK;
 }
 
-static int permute(dq_ising* p, const c128* src, c128* dst, int batch, int to_phys) {
+template <typename T>
+static int permute(dq_ising* p, const T* src, T* dst, int batch, int to_phys) {
     BitMap bm;
     for (int k = 0; k < p->n; ++k) bm.map[k] = (int8_t)p->bitpos[p->n - 1 - k];  // ref bit k = qubit n-1-k
     dim3 grid(grid_for(p->dim(), p->ctx->prop.multiProcessorCount), batch);
-    k_permute<<<grid, kThreads, 0, p->ctx->stream>>>(src, dst, p->n, bm, to_phys);
+    k_permute<T><<<grid, kThreads, 0, p->ctx->stream>>>(src, dst, p->n, bm, to_phys);
     p->ctx->launches++;
     DQ_CUDA(cudaGetLastError());
     return DQ_OK;
 }
 int gen_permute_in(dq_ising* p, const c128* s, c128* d, int batch) { return permute(p, s, d, batch, 1); }
 int gen_permute_out(dq_ising* p, const c128* s, c128* d, int batch) { return permute(p, s, d, batch, 0); }
+int gen_permute_real_in(dq_ising* p, const double* s, double* d) { return permute(p, s, d, 1, 1); }
 
 int gen_trig(dq_ising* p, const double* d_rows, int64_t n_rows, double2* d_trig) {
     if (n_rows == 0) return DQ_OK;
