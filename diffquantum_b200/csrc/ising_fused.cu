@@ -251,6 +251,15 @@ __device__ __forceinline__ void prefetch_tables(const PassStep* __restrict__ ps,
     for (int i = threadIdx.x; i < (int)(sizeof(PassStep) / 16); i += kThreads) cp_async16(d + 16 * i, s + 16 * i);
 }
 
+// Which PassStep sits in each of the two shared-memory table slots.  Two scalars, not an array: a dynamically
+// indexed pointer array lives in local memory, and every LDL after a fence is an L2 round trip.
+struct CachedSteps {
+    const PassStep* s0 = nullptr;
+    const PassStep* s1 = nullptr;
+    __device__ __forceinline__ const PassStep* get(int i) const { return i ? s1 : s0; }
+    __device__ __forceinline__ void set(int i, const PassStep* v) { if (i) s1 = v; else s0 = v; }
+};
+
 struct Shared {
     ItemInfo info[2];
     double red[2][kThreads / 32];   // energy partials of the item in slot `cur` (consumed one item later)
@@ -285,7 +294,7 @@ __device__ __forceinline__ void process_tile(const LaunchArgs& A, const KetDesc*
                                              c128* __restrict__ tile, Shared& sh, const KetDesc* __restrict__ skets,
                                              const ItemInfo& I,
                                              const unsigned nxt_raw, const int nb, const unsigned total,
-                                             PassStep* __restrict__ cache, const PassStep* (&cached_ps)[2],
+                                             PassStep* __restrict__ cache, CachedSteps& cached_ps,
                                              const int cb, int& next_cb, bool& next_tables_new, Pending& pd) {
     using G = Geo<TYPE>;
     const TypeGeom& T = A.geom[TYPE];
@@ -455,11 +464,11 @@ __device__ __forceinline__ void process_tile(const LaunchArgs& A, const KetDesc*
         if (N.ready) {                       // ... so the next tile may land in them while we finish this one
             const KetDesc* __restrict__ nkd = skets + N.g;
             const PassStep* nps = nkd->steps + N.p;
-            if (nps != cached_ps[cb]) {
+            if (nps != cached_ps.get(cb)) {
                 next_cb = cb ^ 1;
-                if (nps != cached_ps[next_cb]) {
+                if (nps != cached_ps.get(next_cb)) {
                     prefetch_tables(nps, cache + next_cb);
-                    cached_ps[next_cb] = nps;
+                    cached_ps.set(next_cb, nps);
                     next_tables_new = true;
                 }
             }
@@ -537,7 +546,7 @@ __global__ void __launch_bounds__(kThreads, DQ_CTAS_PER_SM) k_fused_passes(const
     const int tid = threadIdx.x;
     const unsigned total = ((unsigned)A.max_pass * (unsigned)A.n_kets) << A.ipp_log2;
     const int nsub = 1 << A.sub_log2;
-    const PassStep* cached_ps[2] = {nullptr, nullptr};
+    CachedSteps cached_ps;
     int cur = 0, cb = 0;
     bool prefetched = false, tables_new = false;
     Pending pd;
@@ -601,11 +610,11 @@ __global__ void __launch_bounds__(kThreads, DQ_CTAS_PER_SM) k_fused_passes(const
             __syncthreads();
             const PassStep* ps = kd->steps + I.p;
             tables_new = false;
-            if (ps != cached_ps[cb]) {
+            if (ps != cached_ps.get(cb)) {
                 cb ^= 1;
-                if (ps != cached_ps[cb]) {
+                if (ps != cached_ps.get(cb)) {
                     prefetch_tables(ps, cache + cb);
-                    cached_ps[cb] = ps;
+                    cached_ps.set(cb, ps);
                     tables_new = true;
                 }
             }
