@@ -75,6 +75,7 @@ int gen_build_mdiag(dq_ising* p, const double* m_zz, double m_const);
 
 // fused persistent engine (n >= 12)
 int fused_supported(const dq_ising* p);
+void fused_j_sets(int n, int* jl, int* jh);   // physical bits held in registers around the phase, L pass and H pass
 void fused_release(dq_ising* p);
 int fused_launch_times(dq_ising* p, double* total_ms, double* n_launches);
 int fused_grad_run(dq_ising* p);

@@ -21,7 +21,7 @@ bool use_fused(const dq_ising* p) { return p->step_mode == 0 && p->engine >= 1 &
 
 // ---- qubit -> bit layout ---------------------------------------------------------------------------------
 // Reference order is bit n-1-q for qubit q (np.kron order, demo_maxcut.py:53-57).  The fused engine keeps two
-// sets of five index bits in registers (J_L = bits 0..4 of the L pass, J_H = tile bits 7..11 of the H pass);
+// sets of five index bits in registers (J_L and J_H, see Geo<> in ising_fused.cu and dq::fused_j_sets);
 // a ZZ pair with both ends inside one set costs a 32-entry table multiply per amplitude (the `aj` factor).
 // Automatic layout: put two disjoint independent sets of the ZZ graph on those bits, keep every other qubit
 // in reference order.  Falls back to the reference order when no such sets are found.
@@ -30,12 +30,7 @@ bool choose_layout(const dq_ising* p, int* bitpos) {
     for (int q = 0; q < n; ++q) bitpos[q] = n - 1 - q;
     if (p->layout_mode == 0 || n < 12 || n > 20) return false;
     int jl[5], jh[5];
-    const int a = 22 - n;
-    for (int i = 0; i < 5; ++i) {
-        jl[i] = i;
-        const int t = 7 + i;
-        jh[i] = t < a ? t : 10 + (t - a);
-    }
+    dq::fused_j_sets(n, jl, jh);
     std::vector<unsigned> adj(n, 0u);
     for (int e = 0; e < p->n_zz; ++e) {
         adj[p->qa[e]] |= 1u << p->qb[e];
@@ -49,6 +44,11 @@ bool choose_layout(const dq_ising* p, int* bitpos) {
         return true;
     };
     if (independent(jl) && independent(jh)) return false;               // the reference order is already good
+    // J_L and J_H may share one position (bit 2 for n <= 19): the qubit sitting there belongs to both sets
+    int shared_pos = -1;
+    for (int i = 0; i < 5; ++i)
+        for (int k = 0; k < 5; ++k)
+            if (jl[i] == jh[k]) shared_pos = jl[i];
     unsigned long long rng = 0x9E3779B97F4A7C15ull;
     std::vector<int> order(n);
     for (int attempt = 0; attempt < 4000; ++attempt) {
@@ -58,9 +58,14 @@ bool choose_layout(const dq_ising* p, int* bitpos) {
             std::swap(order[q], order[(int)((rng >> 33) % (unsigned)(q + 1))]);
         }
         unsigned used = 0, sets[2] = {0u, 0u};
+        int shared_q = -1;
+        if (shared_pos >= 0) {
+            shared_q = order[0];
+            sets[0] = sets[1] = used = 1u << shared_q;
+        }
         bool ok = true;
         for (int s = 0; s < 2 && ok; ++s) {
-            int cnt = 0;
+            int cnt = shared_q >= 0 ? 1 : 0;
             for (int k = 0; k < n && cnt < 5; ++k) {
                 const int q = order[k];
                 if (((used >> q) & 1u) || (adj[q] & sets[s])) continue;
@@ -72,11 +77,17 @@ bool choose_layout(const dq_ising* p, int* bitpos) {
         }
         if (!ok) continue;
         unsigned taken_pos = 0;
+        if (shared_q >= 0) { bitpos[shared_q] = shared_pos; taken_pos |= 1u << shared_pos; }
         for (int s = 0; s < 2; ++s) {
             const int* pos = s == 0 ? jl : jh;
             int i = 0;
-            for (int q = n - 1; q >= 0; --q)                            // ascending bit = descending qubit, as in the reference order
-                if ((sets[s] >> q) & 1u) { bitpos[q] = pos[i]; taken_pos |= 1u << pos[i]; ++i; }
+            for (int q = n - 1; q >= 0; --q) {                          // ascending bit = descending qubit, as in the reference order
+                if (!((sets[s] >> q) & 1u) || q == shared_q) continue;
+                if (pos[i] == shared_pos) ++i;
+                bitpos[q] = pos[i];
+                taken_pos |= 1u << pos[i];
+                ++i;
+            }
         }
         int pos = 0;
         for (int q = n - 1; q >= 0; --q) {
@@ -98,6 +109,14 @@ int apply_layout(dq_ising* p) {
     dq::f16_release(p);
     p->st.valid = false;
     p->identity_layout = !choose_layout(p, p->bitpos);
+    {
+        unsigned seen = 0;                                              // a layout must be a permutation of the bits
+        for (int q = 0; q < p->n; ++q) seen |= 1u << p->bitpos[q];
+        if (p->n <= 30 && seen != ((1u << p->n) - 1u)) {
+            for (int q = 0; q < p->n; ++q) p->bitpos[q] = p->n - 1 - q;
+            p->identity_layout = true;
+        }
+    }
     const int n_zz = p->n_zz;
     p->pa.resize(n_zz);
     p->pb.resize(n_zz);

@@ -10,8 +10,12 @@
 // so a trajectory of N steps costs N+1 passes = ONE global read+write of the state per step.
 // Inside a pass a CTA owns a tile of 2^12 amplitudes (64 KiB of shared memory); every thread
 // keeps 32 amplitudes in registers and applies 5 qubits' butterflies per register round:
-//     outer-A (5 "K" bits, straight from global)  -> smem -> inner (5 "J" bits, phase, 5 "J" bits)
+//     TMA tile load -> outer-A (5 "K" bits)  -> smem -> inner (5 "J" bits, phase, 5 "J" bits)
 //     -> smem -> outer-B (5 "K" bits) -> global / fused energy reduction.
+// Tiles arrive by TMA (cp.async.bulk.tensor, one instruction per 64 KiB tile, issued by thread 0 as soon as
+// every warp has read its outer-B operands), land in the hardware 128-byte swizzle, and complete on an
+// mbarrier; the K / J bit sets of both pass types are chosen so that this one swizzle is bank-conflict-free
+// in both register rounds (see Geo<>).
 // Rotations use the scaled form a' = a - i tan(theta) b (2 FMA per amplitude per qubit); the product
 // of cosines is folded into the phase tables.  The diagonal phase is never computed per amplitude
 // with sincos: per thread it is  TC[column] * TKK[K bits] * prod XK_m  (base phase) and then a
@@ -23,6 +27,7 @@
 // release/acquire through L2).  Several kets per launch keep every SM busy across pass boundaries,
 // and the ket group is sized to stay resident in the 126 MB L2 between passes.
 #include <algorithm>
+#include <cuda.h>
 #include <math.h>
 #include <string.h>
 #include "ising.cuh"
@@ -72,7 +77,7 @@ struct TypeGeom {
 // Host-side plan of a pass type (superset of TypeGeom; the setup kernel reads it from global memory).
 struct TypePlan {
     TypeGeom g;
-    int k0, j0, start, spare_shift;
+    int start, spare_shift;
     int jq[5], kq[5];               // x-angle column of the qubit on that register bit, -1 = spectator
     int fj_pair[5][kMaxNbr], xk_pair[5][kMaxNbr];
     int n_col_bits;
@@ -93,11 +98,12 @@ struct __align__(16) KetDesc {
     int shift_kind;                 // -1 none, 0 ZZ on (sb0, sb1), 1 X on sb0   (physical bits)
     int sb0, sb1;
     int cls;                        // pass type of its pass 0 (0 = L first, 1 = H first)
-    int pad_;
+    int map_src;                    // tensor-map pair (L view, H view) of `src` in LaunchArgs::maps
     const c128* cross;              // linear mode: final state a = U phi; the energy pass also reduces Re <a|M|ket>
     double* partial2;               // [tiles] partials of that cross term
     double escale2;
-    double pad2_;
+    int map_buf;                    // tensor-map pair of `buf`
+    int pad_;
 };
 
 static_assert(sizeof(KetDesc) % 16 == 0, "KetDesc is copied to shared memory in 16-byte pieces");
@@ -112,6 +118,7 @@ struct SetupJob {
 struct LaunchArgs {
     long long* trace;               // DQ_TRACE only: [item][warp][8] timestamps
     const KetDesc* kets;
+    const CUtensorMap* maps;        // [2 * index + type]: TMA views of every state buffer the kets name
     const double2* tc;
     const double* mdiag;
     unsigned* counters;             // [0] next item, [1 + g] tiles done of ket g
@@ -120,6 +127,8 @@ struct LaunchArgs {
     int tiles_log2;
     int sub_log2;                   // a work item is 2^sub_log2 consecutive tiles: one atomic / poll / release per item
     int ipp_log2;                   // items per (ket, pass) = tiles >> sub_log2
+    int h_c1_shift;                 // H view: coordinate 1 of tile t is t << h_c1_shift
+    int h_sw64;                     // H tiles land in the 64-byte swizzle (rows of 4 amplitudes, n = 20); see process_tile
     double r, ca, sa, c2a, s2a;     // shift gate: r, cos/sin(atan r), cos/sin(2 atan r)
     TypeGeom geom[2];
 };
@@ -127,7 +136,6 @@ struct LaunchArgs {
 // ------------------------------------------------------------------------------------------
 // device helpers
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ int insert5(int t, int p) { return (t & ((1 << p) - 1)) | ((t >> p) << (p + 5)); }
 __device__ __forceinline__ unsigned ld_acquire(const unsigned* p) {
     unsigned v;
     asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
@@ -174,20 +182,44 @@ __device__ __forceinline__ void rot_run(c128 (&v)[kRegs], const double2* rc, con
     rot_bit<SCALED, 4>(v, r4);
 }
 
-// Geometry of the two pass types, compile-time where it can be.
-//   TYPE 0 (L): tile = physical bits [0,12);  K = tile bits 5..9, J = tile bits 0..4.
-//   TYPE 1 (H): tile = `a` low spectator bits + physical bits [10, 10+12-a);  K = tile bits 2..6, J = 7..11
-//               (J on top so that J_L = bits 0..4 and J_H never share two bits: a ZZ shift gate must find a
-//               pass type in which its pair is not J-J).
+// Geometry of the two pass types.  A tile index has 12 bits t0..t11 (L: physical bits 0..11; H: `a` low
+// spectator bits, then physical bits 10..n-1).  Shared memory holds the tile in natural order under the TMA
+// 128-byte swizzle  idx ^ ((idx >> 3) & 7)  (16-byte units), which pairs t0|t3, t1|t4, t2|t5.  A register
+// round is conflict-free when the three lowest lane bits take one bit of each pair and the other bit of every
+// pair is constant across a quarter-warp (a register bit or lane bit 3 / 4):
+//   TYPE 0 (L): K = {t3,t4,t5,t8,t9}, J = {t0,t1,t2,t6,t7}; the warp owns t10,t11 in both rounds, so the whole
+//               pass never leaves the warp's 1024 amplitudes.
+//   TYPE 1 (H): K = {t5..t9}, J = {t2,t3,t4,t10,t11}; spare bits t0,t1.  J_L and J_H share at most one
+//               physical bit for every n: a ZZ shift gate always finds a pass type in which its pair is not J-J.
 template <int TYPE> struct Geo;
 template <> struct Geo<0> {
-    static constexpr int k0 = 5, j0 = 0, spare_shift = 10;
-    __device__ static __forceinline__ int swz(int i) { return i ^ ((i >> 5) & 7); }
+    static constexpr int spare_shift = 10;
+    __host__ __device__ static constexpr int regK(int j) { return ((j & 7) << 3) | ((j >> 3) << 8); }
+    __host__ __device__ static constexpr int regJ(int j) { return (j & 7) | ((j >> 3) << 6); }
+    __device__ static __forceinline__ int baseK(int tid) { return (tid & 7) | (((tid >> 3) & 3) << 6) | ((tid >> 5) << 10); }
+    __device__ static __forceinline__ int baseJ(int tid) { return ((tid & 7) << 3) | (((tid >> 3) & 3) << 8) | ((tid >> 5) << 10); }
+    __device__ static __forceinline__ int kbits(int i) { return ((i >> 3) & 7) | (((i >> 8) & 3) << 3); }
+    __device__ static __forceinline__ int kslot(int tb) { return (tb >= 3 && tb <= 5) ? tb - 3 : ((tb == 8 || tb == 9) ? tb - 5 : -1); }
+    __device__ static __forceinline__ int jslot(int tb) { return (tb >= 0 && tb <= 2) ? tb : ((tb == 6 || tb == 7) ? tb - 3 : -1); }
 };
 template <> struct Geo<1> {
-    static constexpr int k0 = 2, j0 = 7, spare_shift = 0;
-    __device__ static __forceinline__ int swz(int i) { return i ^ (((i >> 7) & 1) << 2); }
+    static constexpr int spare_shift = 0;
+    __host__ __device__ static constexpr int regK(int j) { return j << 5; }
+    __host__ __device__ static constexpr int regJ(int j) { return ((j & 7) << 2) | ((j >> 3) << 10); }
+    __device__ static __forceinline__ int baseK(int tid) { return (tid & 31) | ((tid >> 5) << 10); }
+    __device__ static __forceinline__ int baseJ(int tid) { return (tid & 3) | (((tid >> 2) & 7) << 5) | ((tid >> 5) << 8); }
+    __device__ static __forceinline__ int kbits(int i) { return (i >> 5) & 31; }
+    __device__ static __forceinline__ int kslot(int tb) { return (tb >= 5 && tb <= 9) ? tb - 5 : -1; }
+    __device__ static __forceinline__ int jslot(int tb) { return (tb >= 2 && tb <= 4) ? tb - 2 : ((tb == 10 || tb == 11) ? tb - 7 : -1); }
 };
+// host copies of the two bit lists (build_type, fused_j_sets)
+static const int kJBits[2][5] = {{0, 1, 2, 6, 7}, {2, 3, 4, 10, 11}};
+static const int kKBits[2][5] = {{3, 4, 5, 8, 9}, {5, 6, 7, 8, 9}};
+__host__ __device__ __forceinline__ constexpr int swz(int i) { return i ^ ((i >> 3) & 7); }
+// swz(thread part | register part) = swz(thread part) ^ swz(register part): the swizzle is linear over XOR and the two
+// parts share no bit.  `st` is the thread's (per-tile opaque) swizzled base, `c` the compile-time register part; only
+// the low three bits really XOR, the rest adds -- one LOP3 per distinct low part and an immediate offset per access.
+__device__ __forceinline__ int slot(int st, int c) { return (st ^ (swz(c) & 7)) + (swz(c) & ~7); }
 
 #if DQ_TRACE
 #define TRACE(A, item, slot) do { if ((threadIdx.x & 31) == 0 && (A).trace) (A).trace[((size_t)(item) * 4 + (threadIdx.x >> 5)) * 8 + (slot)] = clock64(); } while (0)
@@ -195,14 +227,32 @@ template <> struct Geo<1> {
 #define TRACE(A, item, slot) do { } while (0)
 #endif
 
-// ---- asynchronous global -> shared copies (LDGSTS) ---------------------------------------------------
+// ---- asynchronous global -> shared copies: LDGSTS for the small tables, TMA for the tiles ----------------
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
-    if (DQ_EXP & 4) return;
     const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+    const unsigned addr = smem_u32(bar);
+    unsigned done;
+    do {
+        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+    } while (!done);
+}
+// named barrier 1: "every thread has read its outer-B operands" -- warps 1..3 only announce it, warp 0 waits
+__device__ __forceinline__ void tile_consumed_arrive() { asm volatile("bar.arrive 1, %0;" ::"n"(kThreads) : "memory"); }
+__device__ __forceinline__ void tile_consumed_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kThreads) : "memory"); }
 
 // One work item = (pass p, ket g, tile t_id); written to shared memory by thread 0.
 struct ItemInfo {
@@ -224,24 +274,20 @@ __device__ __forceinline__ void decode_item(const LaunchArgs& A, unsigned item, 
     I.p = (int)(rest / (unsigned)A.n_kets);
 }
 
-// Each thread copies exactly the 32 amplitudes it will read back in the outer-A round, into exactly
-// the shared-memory slots it reads them from: no barrier is needed between this prefetch and outer-A.
-__device__ __forceinline__ void prefetch_tile(const LaunchArgs& A, const KetDesc* __restrict__ kd, const int type,
-                                              const int p, const int t_id, c128* __restrict__ tile) {
-    const int tid = threadIdx.x;
-    const c128* __restrict__ src = (p == 0 ? kd->src : kd->buf);
+// One TMA instruction brings the whole 64 KiB tile (thread 0 only).  L view: {8 amplitudes, 256 rows, pairs of
+// 2048 amplitudes}; H view: {2^w low amplitudes, low-column groups, high rows 10..17, high rows 18..} (make_maps).
+__device__ __forceinline__ void issue_tile(const LaunchArgs& A, const KetDesc* __restrict__ kd, const int type,
+                                           const int p, const int t_id, c128* __restrict__ tile,
+                                           unsigned long long* __restrict__ full) {
+    const CUtensorMap* map = A.maps + 2 * (p == 0 ? kd->map_src : kd->map_buf) + type;
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    mbar_expect_tx(full, (unsigned)(sizeof(c128) * kTile));
     if (type == 0) {
-        const int iK = insert5(tid, Geo<0>::k0);
-        src += ((size_t)t_id << kTileBits) + iK;
-#pragma unroll
-        for (int j = 0; j < kRegs; ++j) cp_async16(tile + Geo<0>::swz(iK | (j << Geo<0>::k0)), src + (j << Geo<0>::k0));
+        asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                     ::"r"(smem_u32(tile)), "l"(map), "r"(smem_u32(full)), "r"(0), "r"(0), "r"(2 * t_id) : "memory");
     } else {
-        const TypeGeom& T = A.geom[1];
-        const int iK = insert5(tid, Geo<1>::k0);
-        src += (((size_t)(t_id & ((1 << T.tid_lo_bits) - 1)) << T.a) | ((size_t)(t_id >> T.tid_lo_bits) << T.high_end)) +
-               ((size_t)(iK & T.lowmask) | ((size_t)(iK >> T.a) << 10));
-#pragma unroll
-        for (int j = 0; j < kRegs; ++j) cp_async16(tile + Geo<1>::swz(iK | (j << Geo<1>::k0)), src + T.offK[j]);
+        asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+                     ::"r"(smem_u32(tile)), "l"(map), "r"(smem_u32(full)), "r"(0), "r"(t_id << A.h_c1_shift), "r"(0), "r"(0) : "memory");
     }
 }
 
@@ -295,7 +341,8 @@ __device__ __forceinline__ void process_tile(const LaunchArgs& A, const KetDesc*
                                              const ItemInfo& I,
                                              const unsigned nxt_raw, const int nb, const unsigned total,
                                              PassStep* __restrict__ cache, CachedSteps& cached_ps,
-                                             const int cb, int& next_cb, bool& next_tables_new, Pending& pd) {
+                                             const int cb, int& next_cb, bool& next_tables_new, Pending& pd,
+                                             unsigned long long* __restrict__ full) {
     using G = Geo<TYPE>;
     const TypeGeom& T = A.geom[TYPE];
     const int tid = threadIdx.x;
@@ -305,8 +352,12 @@ __device__ __forceinline__ void process_tile(const LaunchArgs& A, const KetDesc*
 
     // tile geometry
     size_t tbase, xK, xJ;
-    const int iK = insert5(tid, G::k0);
-    const int iJ = insert5(tid, G::j0);
+    const int iK = G::baseK(tid);
+    const int iJ = G::baseJ(tid);
+    // Opaque per tile: otherwise the 2 x 8 swizzled slot bases are hoisted out of the item loop, spilled, and
+    // re-read from local memory right after the dependency poll has invalidated L1 (an L2 round trip per tile).
+    int sK = swz(iK), sJ = swz(iJ);
+    asm volatile("" : "+r"(sK), "+r"(sJ));
     if (TYPE == 0) {
         tbase = (size_t)t_id << kTileBits;
         xK = tbase + iK;
@@ -330,8 +381,8 @@ __device__ __forceinline__ void process_tile(const LaunchArgs& A, const KetDesc*
             tb1 = s1 < T.a ? s1 : (s1 >= 10 ? s1 - 10 + T.a : -1);
         }
         if (shift_kind == 1) {
-            if (tb0 >= G::k0 && tb0 < G::k0 + 5) ovK = tb0 - G::k0;
-            if (tb0 >= G::j0 && tb0 < G::j0 + 5) ovJ = tb0 - G::j0;
+            ovK = G::kslot(tb0);
+            ovJ = G::jslot(tb0);
         }
     }
     // (I + i sigma r X) = exp(-i theta X) / cos(theta) with tan(theta) = -sigma r
@@ -345,10 +396,24 @@ __device__ __forceinline__ void process_tile(const LaunchArgs& A, const KetDesc*
     c128 v[kRegs];
     // ---- outer-A : own slots -> registers, K-bit rotations of the previous step -----------------------
 #pragma unroll
-    for (int j = 0; j < kRegs; ++j) v[j] = tile[G::swz(iK | (j << G::k0))];
-    rot_run<SCALED>(v, P.rot[0], ovK, shift_rc);
+    if (TYPE == 0) {
 #pragma unroll
-    for (int j = 0; j < kRegs; ++j) if (!(DQ_EXP & 2)) tile[G::swz(iK | (j << G::k0))] = v[j];
+        for (int j = 0; j < kRegs; ++j) v[j] = tile[slot(sK, G::regK(j))];
+    } else {
+        // An H tile of a 20-qubit state has rows of 4 amplitudes (64 B).  A TMA box row narrower than the swizzle span
+        // is padded to the span, so those tiles land in the 64-byte swizzle  idx ^ ((idx >> 3) & 3)  instead; this first
+        // read is conflict-free in either (quarter-warp = t0,t1,t2; t3,t4 are lane bits 3,4).  The register part
+        // j << 5 meets the 128-byte pattern only through bit 5 (XOR 4 for odd j) and the 64-byte pattern not at all.
+        const int b0 = A.h_sw64 ? (iK ^ ((iK >> 3) & 3)) : sK;
+        const int b1 = A.h_sw64 ? b0 : (b0 ^ 4);
+#pragma unroll
+        for (int j = 0; j < kRegs; ++j) v[j] = tile[((j & 1) ? b1 : b0) + G::regK(j)];
+    }
+    rot_run<SCALED>(v, P.rot[0], ovK, shift_rc);
+    // from here on the tile lives in the 128-byte pattern; the 8 threads that share a 128-byte line are one quarter-warp
+    if (TYPE == 1) __syncwarp();
+#pragma unroll
+    for (int j = 0; j < kRegs; ++j) if (!(DQ_EXP & 2)) tile[slot(sK, G::regK(j))] = v[j];
     // thread 0: the following item's dependency counter, polled now and consumed after the phase
     unsigned polled = 0;
     ItemInfo nI;
@@ -374,10 +439,10 @@ __device__ __forceinline__ void process_tile(const LaunchArgs& A, const KetDesc*
 
     // ---- inner : J-bit rotations, phase, J-bit rotations ---------------------------------------------
 #pragma unroll
-    for (int j = 0; j < kRegs; ++j) if (!(DQ_EXP & 2)) v[j] = tile[G::swz(iJ | (j << G::j0))];
+    for (int j = 0; j < kRegs; ++j) if (!(DQ_EXP & 2)) v[j] = tile[slot(sJ, G::regJ(j))];
     rot_run<SCALED>(v, P.rot[1], ovJ, shift_rc);
     {
-        const int kb = (iJ >> G::k0) & 31;
+        const int kb = G::kbits(iJ);
         c128 phi = cmul(phi_tc, P.tkk[kb]);
 #pragma unroll
         for (int m = 0; m < 5; ++m) {
@@ -391,8 +456,8 @@ __device__ __forceinline__ void process_tile(const LaunchArgs& A, const KetDesc*
 #pragma unroll
         for (int k = 0; k < 5; ++k) F[k] = P.fj[k][gather3(xJ, T.fj_pos[k], T.fj_msk[k])];
         if (shift_kind == 0) {               // ZZ shift gate exp(i sigma alpha z0 z1); never both operands in J
-            const int j0b = (tb0 >= G::j0 && tb0 < G::j0 + 5) ? tb0 - G::j0 : -1;
-            const int j1b = (tb1 >= G::j0 && tb1 < G::j0 + 5) ? tb1 - G::j0 : -1;
+            const int j0b = G::jslot(tb0);
+            const int j1b = G::jslot(tb1);
             const double z0 = ((xJ >> kd->sb0) & 1) ? -1.0 : 1.0;
             const double z1 = ((xJ >> kd->sb1) & 1) ? -1.0 : 1.0;
             // with the J operand at 0 (z = +1) the factor is exp(i sigma alpha z_other)
@@ -434,7 +499,7 @@ __device__ __forceinline__ void process_tile(const LaunchArgs& A, const KetDesc*
     }
     rot_run<SCALED>(v, P.rot[2], -1, shift_rc);
 #pragma unroll
-    for (int j = 0; j < kRegs; ++j) if (!(DQ_EXP & 2)) tile[G::swz(iJ | (j << G::j0))] = v[j];
+    for (int j = 0; j < kRegs; ++j) if (!(DQ_EXP & 2)) tile[slot(sJ, G::regJ(j))] = v[j];
     if (tid == 0) {                          // publish the following item
         nI.ready = nI.valid && (!last_sub || nI.p == 0 || polled >= (unsigned)nI.p << A.ipp_log2);
         sh.info[nb] = nI;
@@ -446,22 +511,23 @@ __device__ __forceinline__ void process_tile(const LaunchArgs& A, const KetDesc*
 
     // ---- outer-B : K-bit rotations of the new step; prefetch of the next tile; store or reduce --------
 #pragma unroll
-    for (int j = 0; j < kRegs; ++j) if (!(DQ_EXP & 2)) v[j] = tile[G::swz(iK | (j << G::k0))];
+    for (int j = 0; j < kRegs; ++j) if (!(DQ_EXP & 2)) v[j] = tile[slot(sK, G::regK(j))];
     if (flags & F_ENERGY) {                  // energy pass: pull the observable (and the cross state) towards L1 now
         const double* __restrict__ mdp = A.mdiag + xK;
 #pragma unroll
         for (int j = 0; j < kRegs; ++j) {
-            const size_t o = TYPE == 0 ? (size_t)(j << G::k0) : (size_t)T.offK[j];
+            const size_t o = TYPE == 0 ? (size_t)G::regK(j) : (size_t)T.offK[j];
             asm volatile("prefetch.global.L1 [%0];" ::"l"(mdp + o));
             if (CROSS && kd->cross) asm volatile("prefetch.global.L2 [%0];" ::"l"(kd->cross + xK + o));
         }
     }
-    rot_bit<SCALED, 0>(v, P.rot[3][0]);      // every slot of this thread has now been consumed ...
+    rot_bit<SCALED, 0>(v, P.rot[3][0]);      // every operand of this thread has now arrived in registers ...
+    if (tid < 32) tile_consumed_sync(); else tile_consumed_arrive();
     {
         const ItemInfo& N = sh.info[nb];
         next_cb = cb;
         next_tables_new = false;
-        if (N.ready) {                       // ... so the next tile may land in them while we finish this one
+        if (N.ready) {                       // ... so the next tile may land while we finish this one
             const KetDesc* __restrict__ nkd = skets + N.g;
             const PassStep* nps = nkd->steps + N.p;
             if (nps != cached_ps.get(cb)) {
@@ -472,7 +538,7 @@ __device__ __forceinline__ void process_tile(const LaunchArgs& A, const KetDesc*
                     next_tables_new = true;
                 }
             }
-            prefetch_tile(A, nkd, (N.p + nkd->cls) & 1, N.p, N.t_id, tile);
+            if (tid == 0) issue_tile(A, nkd, (N.p + nkd->cls) & 1, N.p, N.t_id, tile, full);
             cp_async_commit();
         }
     }
@@ -502,8 +568,8 @@ __device__ __forceinline__ void process_tile(const LaunchArgs& A, const KetDesc*
                 na = make_double2(fma(rc.y, b.y, rc.x * a.x), fma(-rc.y, b.x, rc.x * a.y));
                 nbv = make_double2(fma(rc.y, a.y, rc.x * b.x), fma(-rc.y, a.x, rc.x * b.y));
             }
-            const size_t o0 = TYPE == 0 ? (size_t)(j << G::k0) : (size_t)T.offK[j];
-            const size_t o1 = TYPE == 0 ? (size_t)((j + 16) << G::k0) : (size_t)T.offK[j + 16];
+            const size_t o0 = TYPE == 0 ? (size_t)G::regK(j) : (size_t)T.offK[j];
+            const size_t o1 = TYPE == 0 ? (size_t)G::regK(j + 16) : (size_t)T.offK[j + 16];
             if (do_store) {
                 if (DQ_EXP & 4) { if (na.x == 1.2345e-300) __stcg(dst + j, na); }
                 else { __stcg(dst + o0, na); __stcg(dst + o1, nbv); }
@@ -535,15 +601,23 @@ __device__ __forceinline__ void process_tile(const LaunchArgs& A, const KetDesc*
 // ------------------------------------------------------------------------------------------
 template <bool SCALED, bool AJ, bool CROSS>
 __global__ void __launch_bounds__(kThreads, DQ_CTAS_PER_SM) k_fused_passes(const __grid_constant__ LaunchArgs A) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(16) unsigned char smem_dyn[];
+    // the 128-byte TMA swizzle is a function of the shared-memory address: the tile starts on a 1 KiB boundary
+    unsigned char* smem_raw = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
     c128* tile = reinterpret_cast<c128*>(smem_raw);
     PassStep* cache = reinterpret_cast<PassStep*>(smem_raw + sizeof(c128) * kTile);     // two slots
     // Ket descriptors live in shared memory: the acquire / release fences of the item protocol invalidate
     // L1 (CCTL.IVALL), so every kd-> field read from global memory was an exposed L2 round trip per tile.
     KetDesc* skets = reinterpret_cast<KetDesc*>(smem_raw + sizeof(c128) * kTile + 2 * sizeof(PassStep));
     __shared__ Shared sh;
+    __shared__ __align__(8) unsigned long long full_bar;    // completes when the tile issued by thread 0 has landed
 
     const int tid = threadIdx.x;
+    unsigned full_parity = 0;
+    if (tid == 0) {
+        mbar_init(&full_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
     const unsigned total = ((unsigned)A.max_pass * (unsigned)A.n_kets) << A.ipp_log2;
     const int nsub = 1 << A.sub_log2;
     CachedSteps cached_ps;
@@ -618,7 +692,7 @@ __global__ void __launch_bounds__(kThreads, DQ_CTAS_PER_SM) k_fused_passes(const
                     tables_new = true;
                 }
             }
-            prefetch_tile(A, kd, (I.p + kd->cls) & 1, I.p, I.t_id, tile);
+            if (tid == 0) issue_tile(A, kd, (I.p + kd->cls) & 1, I.p, I.t_id, tile, &full_bar);
             cp_async_commit();
         }
         unsigned nxt_raw = 0;
@@ -627,18 +701,20 @@ __global__ void __launch_bounds__(kThreads, DQ_CTAS_PER_SM) k_fused_passes(const
             q_next = atomicAdd(&A.counters[0], 1u);
         }
         TRACE(A, I.item, 0);
-        cp_async_wait_all();                   // this thread's own slots (and its share of the tables) landed
+        cp_async_wait_all();                   // this thread's share of the tables landed
         if (tables_new) __syncthreads();       // tables in cache[cb] become visible to every thread
+        mbar_wait(&full_bar, full_parity);     // the tile landed (TMA complete_tx)
+        full_parity ^= 1u;
         int next_cb = cb;
         bool next_tables_new = false;
         const PassStep& P = cache[cb];
         const int flags = P.flags;
         if (P.type == 0)
             process_tile<SCALED, AJ, CROSS, 0>(A, kd, P, tile, sh, skets, I, nxt_raw, cur ^ 1, total, cache, cached_ps, cb,
-                                        next_cb, next_tables_new, pd);
+                                        next_cb, next_tables_new, pd, &full_bar);
         else
             process_tile<SCALED, AJ, CROSS, 1>(A, kd, P, tile, sh, skets, I, nxt_raw, cur ^ 1, total, cache, cached_ps, cb,
-                                        next_cb, next_tables_new, pd);
+                                        next_cb, next_tables_new, pd, &full_bar);
         TRACE(A, I.item, 7);
         if (tid == 0 && I.sub + 1 == nsub) {   // item complete: published after the next item's mid-tile barrier
             pd.g = I.g;
@@ -797,7 +873,14 @@ struct Plan {
     int counter_slots = 0, counter_cursor = 0;
     std::vector<cudaEvent_t> ev;    // option time_launches: event pairs around every pass-kernel launch of the last run
     int ev_used = 0;
+    // TMA views, one (L, H) pair per state buffer ever named by a ket; device copy refreshed before a launch
+    std::vector<const void*> map_keys;
+    std::vector<CUtensorMap> h_maps;
+    DevBuf d_maps;
+    size_t maps_uploaded = 0;
+    int h_c1_shift = 0;
 };
+constexpr size_t kMaxMaps = 4096;   // buffer pairs cached per problem
 
 static std::vector<std::pair<dq_ising*, Plan*>> g_plans;     // one plan per problem
 
@@ -811,14 +894,17 @@ static bool build_type(const dq_ising* p, int type, TypePlan& T, int* jphys_out)
     const int n = p->n;
     memset(&T, 0, sizeof(T));
     int a, b;
-    if (type == 0) {            // L: tile = physical bits [0,12), K = bits 5..9, J = bits 0..4
+    if (type == 0) {            // L: tile = physical bits [0,12); K, J as Geo<0>
         a = kTileBits; T.start = kTileBits; b = 0;
-        T.k0 = 5; T.j0 = 0; T.spare_shift = 10;
-    } else {                    // H: tile = low spectators [0,a) + physical bits [10,n); J = top 5 tile bits
+        T.spare_shift = 10;
+    } else {                    // H: tile = low spectators [0,a) + physical bits [10,n); K, J as Geo<1>
         b = n - 10;
         a = kTileBits - b; T.start = 10;
-        T.k0 = 2; T.j0 = 7; T.spare_shift = 0;
+        T.spare_shift = 0;
     }
+    const int* jbits = kJBits[type];
+    const int* kbits = kKBits[type];
+    auto spread = [](int j, const int* bits) { int t = 0; for (int i = 0; i < 5; ++i) t |= ((j >> i) & 1) << bits[i]; return t; };
     T.g.a = a;
     T.g.lowmask = (1 << a) - 1;
     T.g.tid_lo_bits = T.start - a;
@@ -828,8 +914,8 @@ static bool build_type(const dq_ising* p, int type, TypePlan& T, int* jphys_out)
     auto phys_off = [&](int i) { return (i & T.g.lowmask) | ((i >> a) << T.start); };
     auto tile_bit_of_phys = [&](int pos) { return pos < a ? pos : (pos >= T.start && pos < T.start + b ? pos - T.start + a : -1); };
     for (int j = 0; j < kRegs; ++j) {
-        T.g.offK[j] = phys_off(j << T.k0);
-        T.g.offJ[j] = phys_off(j << T.j0);
+        T.g.offK[j] = phys_off(spread(j, kbits));
+        T.g.offJ[j] = phys_off(spread(j, jbits));
     }
     // which physical bits are rotated by this pass type
     auto active = [&](int pos) { return type == 0 ? (pos < 10) : (pos >= 10); };
@@ -837,8 +923,8 @@ static bool build_type(const dq_ising* p, int type, TypePlan& T, int* jphys_out)
     for (int q = 0; q < n; ++q) qubit_of_pos[p->bitpos[q]] = q;
     int jphys[5], kphys[5];
     for (int i = 0; i < 5; ++i) {
-        jphys[i] = phys_of_tile_bit(T.j0 + i);
-        kphys[i] = phys_of_tile_bit(T.k0 + i);
+        jphys[i] = phys_of_tile_bit(jbits[i]);
+        kphys[i] = phys_of_tile_bit(kbits[i]);
         jphys_out[i] = jphys[i];
         T.jq[i] = active(jphys[i]) ? qubit_of_pos[jphys[i]] : -1;
         T.kq[i] = active(kphys[i]) ? qubit_of_pos[kphys[i]] : -1;
@@ -888,6 +974,89 @@ static bool build_type(const dq_ising* p, int type, TypePlan& T, int* jphys_out)
     return true;
 }
 
+// ---- TMA views of a state buffer ----------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* f = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(f);
+        cudaGetLastError();
+    }
+    return fn;
+}
+
+// out[0]: L view, a tile = 4096 consecutive amplitudes as {8 amplitudes (128 B), 256 rows, 2 blocks};
+// out[1]: H view, a tile = 2^a consecutive low amplitudes x every high index, as
+//         {2^w amplitudes, 2^(a-w) of the 2^(10-w) low-column groups, high bits 10..17, high bits 18..}, w = min(a, 3).
+// Both boxes are written to shared memory densely in this order = the natural tile order, 128-byte swizzle
+// (64-byte swizzle when the H rows are only 64 bytes wide: a narrower row would be padded to the swizzle span).
+static bool make_maps(int n, const void* base, CUtensorMap* out) {
+    EncodeTiledFn enc = encode_fn();
+    if (!enc) return false;
+    const cuuint32_t ones[4] = {1, 1, 1, 1};
+    {
+        const cuuint64_t dims[3] = {16, 256, (cuuint64_t)1 << (n - 11)};
+        const cuuint64_t strides[2] = {128, 128 * 256};
+        const cuuint32_t box[3] = {16, 256, 2};
+        if (enc(&out[0], CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, const_cast<void*>(base), dims, strides, box, ones,
+                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+            return false;
+    }
+    {
+        const int a = 22 - n, w = std::min(a, 3);
+        const int hi_lo = std::min(8, n - 10), hi_hi = std::max(0, n - 18);
+        const cuuint64_t dims[4] = {(cuuint64_t)2 << w, (cuuint64_t)1 << (10 - w), (cuuint64_t)1 << hi_lo, (cuuint64_t)1 << hi_hi};
+        const cuuint64_t strides[3] = {(cuuint64_t)16 << w, (cuuint64_t)16 << 10, (cuuint64_t)16 << 18};
+        const cuuint32_t box[4] = {(cuuint32_t)2 << w, (cuuint32_t)1 << (a - w), (cuuint32_t)1 << hi_lo, (cuuint32_t)1 << hi_hi};
+        if (enc(&out[1], CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 4, const_cast<void*>(base), dims, strides, box, ones,
+                CU_TENSOR_MAP_INTERLEAVE_NONE, w < 3 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
+                CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+            return false;
+    }
+    return true;
+}
+
+// Index of the view pair of `base` (created on first use); -1 when the driver refuses the encoding.
+static int map_index(Plan* pl, const void* base) {
+    for (size_t i = 0; i < pl->map_keys.size(); ++i)
+        if (pl->map_keys[i] == base) return (int)i;
+    CUtensorMap m[2];
+    if (!make_maps(pl->n, base, m)) return -1;
+    pl->map_keys.push_back(base);
+    pl->h_maps.push_back(m[0]);
+    pl->h_maps.push_back(m[1]);
+    return (int)pl->map_keys.size() - 1;
+}
+
+// Make room for `need` more buffers; a full cache is dropped (indices are only meaningful within one run).
+static int maps_begin(dq_ising* p, Plan* pl, size_t need) {
+    DQ_REQUIRE(need <= kMaxMaps, "fused engine: more than %zu distinct state buffers in one call", kMaxMaps);
+    if (pl->map_keys.size() + need > kMaxMaps) {
+        DQ_CUDA(cudaStreamSynchronize(p->ctx->stream));
+        pl->map_keys.clear();
+        pl->h_maps.clear();
+        pl->maps_uploaded = 0;
+    }
+    return DQ_OK;
+}
+
+static int maps_upload(dq_ising* p, Plan* pl) {
+    if (pl->maps_uploaded == pl->h_maps.size()) return DQ_OK;
+    DQ_CUDA(cudaMemcpyAsync(pl->d_maps.as<CUtensorMap>() + pl->maps_uploaded, pl->h_maps.data() + pl->maps_uploaded,
+                            (pl->h_maps.size() - pl->maps_uploaded) * sizeof(CUtensorMap), cudaMemcpyHostToDevice, p->ctx->stream));
+    pl->maps_uploaded = pl->h_maps.size();
+    return DQ_OK;
+}
+
 template <typename K> static bool prep_kernel(K kern, size_t smem, int* occ) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return false;
     return cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, kern, kThreads, smem) == cudaSuccess && *occ >= 1;
@@ -906,7 +1075,13 @@ static Plan* get_plan(dq_ising* p) {
     pl->has_aj = pl->types[0].has_aj || pl->types[1].has_aj;
     pl->n_col_bits = p->n - 10;
     pl->tiles_log2 = p->n - kTileBits;
-    pl->smem_bytes = sizeof(c128) * kTile + 2 * sizeof(PassStep) + kMaxGroup * sizeof(KetDesc);
+    pl->smem_bytes = 1024 + sizeof(c128) * kTile + 2 * sizeof(PassStep) + kMaxGroup * sizeof(KetDesc);
+    {
+        const int a = 22 - p->n;
+        pl->h_c1_shift = a - std::min(a, 3);
+    }
+    if (!encode_fn()) return pl;
+    if (pl->d_maps.reserve(kMaxMaps * 2 * sizeof(CUtensorMap)) != DQ_OK) return pl;
     if (pl->d_types.reserve(sizeof(TypePlan) * 2) != DQ_OK) return pl;
     if (cudaMemcpy(pl->d_types.p, pl->types, sizeof(TypePlan) * 2, cudaMemcpyHostToDevice) != cudaSuccess) return pl;
     int occ = 0, o2 = 0;
@@ -965,7 +1140,9 @@ static int run_setup(dq_ising* p, Plan* pl, const std::vector<SetupJob>& jobs, c
     return DQ_OK;
 }
 
+#if DQ_TRACE
 static long long all_items_for_trace(int n_kets, int tiles_log2, int max_pass) { return ((long long)n_kets << tiles_log2) * max_pass; }
+#endif
 
 static int launch_group(dq_ising* p, Plan* pl, const KetDesc* d_kets, int n_kets, int max_pass, bool scaled, double r) {
     cudaStream_t st = p->ctx->stream;
@@ -983,6 +1160,9 @@ static int launch_group(dq_ising* p, Plan* pl, const KetDesc* d_kets, int n_kets
     }
 #endif
     A.kets = d_kets;
+    A.maps = pl->d_maps.as<CUtensorMap>();
+    A.h_c1_shift = pl->h_c1_shift;
+    A.h_sw64 = (22 - pl->n) < 3 ? 1 : 0;
     A.tc = pl->tc.as<double2>();
     A.mdiag = p->mdiag.as<double>();
     A.counters = ctr;
@@ -1068,6 +1248,15 @@ int fused_launch_times(dq_ising* p, double* total_ms, double* n_launches) {
     return DQ_OK;
 }
 
+void fused_j_sets(int n, int* jl, int* jh) {
+    const int a = 22 - n;
+    for (int i = 0; i < 5; ++i) {
+        jl[i] = fused::kJBits[0][i];
+        const int t = fused::kJBits[1][i];
+        jh[i] = t < a ? t : 10 + (t - a);
+    }
+}
+
 int fused_supported(const dq_ising* p) {
     fused::Plan* pl = fused::get_plan(const_cast<dq_ising*>(p));
     return pl->ok ? 1 : 0;
@@ -1078,7 +1267,8 @@ void fused_release(dq_ising* p) {
         if (fused::g_plans[i].first == p) {
             fused::Plan* pl = fused::g_plans[i].second;
             DevBuf* bufs[] = {&pl->d_types, &pl->jobs, &pl->steps, &pl->tc, &pl->kets, &pl->counters, &pl->partials,
-                              &pl->out_index, &pl->work, &pl->rows, &pl->phi, &pl->uniform, &pl->afin, &pl->ea, &pl->ea_index};
+                              &pl->out_index, &pl->work, &pl->rows, &pl->phi, &pl->uniform, &pl->afin, &pl->ea, &pl->ea_index,
+                              &pl->d_maps};
             for (auto* b : bufs) b->release();
             for (cudaEvent_t e : pl->ev) cudaEventDestroy(e);
             delete pl;
@@ -1107,10 +1297,13 @@ int fused_evolve(dq_ising* p, c128* d_states, int batch, const double* h_rows, i
     DQ_TRY(run_setup(p, pl, jobs, pl->rows.as<double>(), scaled));
     std::vector<KetDesc> kets(batch);
     DQ_TRY(pl->partials.reserve((size_t)batch * tiles * sizeof(double)));
+    DQ_TRY(maps_begin(p, pl, (size_t)batch));
     for (int g = 0; g < batch; ++g) {
         KetDesc& k = kets[g];
         k.src = d_states + (size_t)g * N;
         k.buf = d_states + (size_t)g * N;
+        k.map_src = k.map_buf = map_index(pl, k.buf);
+        DQ_REQUIRE(k.map_src >= 0, "fused engine: cuTensorMapEncodeTiled failed for a state buffer");
         k.steps = pl->steps.as<PassStep>();
         k.partial = pl->partials.as<double>() + (size_t)g * tiles;
         k.sigma = 0.0;
@@ -1123,8 +1316,8 @@ int fused_evolve(dq_ising* p, c128* d_states, int batch, const double* h_rows, i
         k.cross = nullptr;
         k.partial2 = nullptr;
         k.escale2 = 0.0;
-        k.pad2_ = 0.0;
     }
+    DQ_TRY(maps_upload(p, pl));
     DQ_TRY(pl->kets.reserve(kets.size() * sizeof(KetDesc)));
     DQ_CUDA(cudaMemcpyAsync(pl->kets.p, kets.data(), kets.size() * sizeof(KetDesc), cudaMemcpyHostToDevice, st));
     const int G = auto_ket_group(p);
@@ -1203,10 +1396,15 @@ int fused_grad_run(dq_ising* p) {
     const double esc_x = scaled ? 1.0 / (1.0 + s.r * s.r) : 1.0;
     std::vector<KetDesc> kets;
     kets.reserve((size_t)B * (kets_per + 1));
+    DQ_TRY(maps_begin(p, pl, (size_t)2 * B + G + 2));
+    auto view_of = [&](const void* base) { return map_index(pl, base); };
+    DQ_REQUIRE(view_of(psi0) >= 0, "fused engine: cuTensorMapEncodeTiled failed for a state buffer");
     for (int b = 0; b < B; ++b) {
         KetDesc k;
         k.src = psi0;
         k.buf = pl->phi.as<c128>() + (size_t)b * N;
+        k.map_src = view_of(k.src);
+        k.map_buf = view_of(k.buf);
         k.steps = pl->steps.as<PassStep>() + pre[b].step0;
         k.partial = nullptr;
         k.sigma = 0.0;
@@ -1219,7 +1417,6 @@ int fused_grad_run(dq_ising* p) {
         k.cross = nullptr;
         k.partial2 = nullptr;
         k.escale2 = 0.0;
-        k.pad2_ = 0.0;
         kets.push_back(k);
     }
     struct Group { size_t first; int count; int max_pass; };
@@ -1234,6 +1431,8 @@ int fused_grad_run(dq_ising* p) {
             KetDesc k = kets[b];
             k.src = pl->phi.as<c128>() + (size_t)b * N;
             k.buf = pl->afin.as<c128>() + (size_t)b * N;
+            k.map_src = view_of(k.src);
+            k.map_buf = view_of(k.buf);
             k.steps = pl->steps.as<PassStep>() + sufA[b].step0;
             k.partial = pl->ea.as<double>() + (size_t)b * tiles;
             k.n_pass = s.suffix_steps[b] + 1;
@@ -1269,8 +1468,9 @@ int fused_grad_run(dq_ising* p) {
                     k.cross = linear ? pl->afin.as<c128>() + (size_t)b * N : nullptr;
                     k.partial2 = linear ? pl->partials.as<double>() + ((size_t)b * kets_per + 2 * i + 1) * tiles : nullptr;
                     k.escale2 = s.shift_kind[i] == 1 ? sqrt(esc_x) : 1.0;
-                    k.pad2_ = 0.0;
                     k.src = pl->phi.as<c128>() + (size_t)b * N;
+                    k.map_src = view_of(k.src);
+                    k.map_buf = -1;
                     k.buf = nullptr;                // slot assigned below
                     k.steps = pl->steps.as<PassStep>() + (cls == 0 ? sufL[b].step0 : sufH[b].step0);
                     const size_t kidx = (size_t)b * kets_per + 2 * i + sg;
@@ -1288,7 +1488,10 @@ int fused_grad_run(dq_ising* p) {
             }
             for (size_t g0 = 0; g0 < mine.size(); g0 += G) {
                 const int cnt = (int)std::min<size_t>(G, mine.size() - g0);
-                for (int g = 0; g < cnt; ++g) mine[g0 + g].buf = pl->work.as<c128>() + (size_t)g * N;
+                for (int g = 0; g < cnt; ++g) {
+                    mine[g0 + g].buf = pl->work.as<c128>() + (size_t)g * N;
+                    mine[g0 + g].map_buf = view_of(mine[g0 + g].buf);
+                }
                 groups.push_back({kets.size() + g0, cnt, s.suffix_steps[b] + 1});
             }
             kets.insert(kets.end(), mine.begin(), mine.end());
@@ -1296,6 +1499,9 @@ int fused_grad_run(dq_ising* p) {
     }
     std::vector<int> out_index((size_t)B * kets_per);
     for (size_t i = 0; i < out_index.size(); ++i) out_index[i] = (int)i;
+    for (const KetDesc& k : kets)
+        DQ_REQUIRE(k.map_src >= 0 && k.map_buf >= 0, "fused engine: cuTensorMapEncodeTiled failed for a state buffer");
+    DQ_TRY(maps_upload(p, pl));
     DQ_TRY(pl->kets.reserve(kets.size() * sizeof(KetDesc)));
     DQ_CUDA(cudaMemcpyAsync(pl->kets.p, kets.data(), kets.size() * sizeof(KetDesc), cudaMemcpyHostToDevice, st));
     DQ_TRY(pl->out_index.reserve(out_index.size() * sizeof(int)));
