@@ -12,10 +12,12 @@
 // keeps 32 amplitudes in registers and applies 5 qubits' butterflies per register round:
 //     TMA tile load -> outer-A (5 "K" bits)  -> smem -> inner (5 "J" bits, phase, 5 "J" bits)
 //     -> smem -> outer-B (5 "K" bits) -> global / fused energy reduction.
-// Tiles arrive by TMA (cp.async.bulk.tensor, one instruction per 64 KiB tile, issued by thread 0 as soon as
-// every warp has read its outer-B operands), land in the hardware 128-byte swizzle, and complete on an
-// mbarrier; the K / J bit sets of both pass types are chosen so that this one swizzle is bank-conflict-free
-// in both register rounds (see Geo<>).
+// Tiles arrive AND leave by TMA (cp.async.bulk.tensor, one instruction per 64 KiB tile): they land in the
+// hardware 128-byte swizzle and complete on an mbarrier; results are written back into the same buffer and
+// stored with one bulk-tensor store.  The K / J bit sets of both pass types are chosen so that this one swizzle
+// is bank-conflict-free in both register rounds (see Geo<>).  A CTA (one per SM) runs two independent TEAMS of
+// four warps that share THREE tile buffers: while a team works in one buffer, the third one receives its next
+// tile or drains the other team's store, so neither the load latency nor the store ever stalls a warp.
 // Rotations use the scaled form a' = a - i tan(theta) b (2 FMA per amplitude per qubit); the product
 // of cosines is folded into the phase tables.  The diagonal phase is never computed per amplitude
 // with sincos: per thread it is  TC[column] * TKK[K bits] * prod XK_m  (base phase) and then a
@@ -37,7 +39,10 @@ namespace fused {
 
 constexpr int kTileBits = 12;
 constexpr int kTile = 1 << kTileBits;      // amplitudes per tile
-constexpr int kThreads = 128;              // kTile / 32
+constexpr int kTeamThreads = 128;          // kTile / 32: one tile is processed by a team of four warps
+constexpr int kTeams = 2;                  // teams per CTA
+constexpr int kThreads = kTeams * kTeamThreads;
+constexpr int kBufs = 3;                   // tile buffers per CTA (one per team + one in flight)
 constexpr int kRegs = 32;                  // amplitudes per thread
 constexpr int kMaxNbr = 3;                 // neighbour bits per register qubit held in tables
 constexpr int kMaxPairs = 128;
@@ -48,8 +53,11 @@ constexpr int kMaxGroup = 96;              // kets per launch (their descriptors
 #ifndef DQ_TRACE
 #define DQ_TRACE 0    // 1: lane 0 of every warp records clock64() at phase boundaries of each item (debug)
 #endif
+#ifndef DQ_STAGGER_NS
+#define DQ_STAGGER_NS 3500
+#endif
 #ifndef DQ_CTAS_PER_SM
-#define DQ_CTAS_PER_SM 2
+#define DQ_CTAS_PER_SM 1
 #endif
 
 enum : int { F_ENERGY = 2, F_STORE = 4 };
@@ -136,6 +144,26 @@ struct LaunchArgs {
 // ------------------------------------------------------------------------------------------
 // device helpers
 // ------------------------------------------------------------------------------------------
+// Poll of a dependency counter on the hot path.  Relaxed on purpose: an acquire load holds back every later memory
+// instruction of warp 0 for an L2 round trip (measured: ~800 cycles per tile, and the other warps wait for warp 0 at the
+// next barrier).  What depends on the counter is only the TMA load of the tile, which is issued under a branch on the
+// polled value, reads L2 directly (the producers' bulk stores are complete and fenced before they bump the counter)
+// and never goes through this SM's L1; nothing else the kernel reads is written during the launch.
+__device__ __forceinline__ unsigned ld_relaxed(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+// Reserve the next work item (called by thread 0 of a team only).  ptxas turns an atomic add on a warp-uniform address
+// into a warp-aggregated atomic whose result is broadcast with a shuffle right away, i.e. it waits for the L2 round trip
+// (~800 cycles per tile, measured) that reserving one item ahead is meant to hide.  An address that formally depends on
+// the lane id (lane 0 -> counters[0], the only lane that ever gets here) keeps it a plain atomic.
+__device__ __forceinline__ unsigned take_item(unsigned* counters) {
+    unsigned lane, v;
+    asm volatile("mov.u32 %0, %%laneid;" : "=r"(lane));
+    asm volatile("atom.relaxed.gpu.global.add.u32 %0, [%1], 1;" : "=r"(v) : "l"(counters + lane) : "memory");
+    return v;
+}
 __device__ __forceinline__ unsigned ld_acquire(const unsigned* p) {
     unsigned v;
     asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
@@ -222,9 +250,12 @@ __host__ __device__ __forceinline__ constexpr int swz(int i) { return i ^ ((i >>
 __device__ __forceinline__ int slot(int st, int c) { return (st ^ (swz(c) & 7)) + (swz(c) & ~7); }
 
 #if DQ_TRACE
-#define TRACE(A, item, slot) do { if ((threadIdx.x & 31) == 0 && (A).trace) (A).trace[((size_t)(item) * 4 + (threadIdx.x >> 5)) * 8 + (slot)] = clock64(); } while (0)
+#define TRACE(A, item, slot) do { if ((threadIdx.x & 31) == 0 && (A).trace) (A).trace[(size_t)(item) * 48 + ((threadIdx.x >> 5) & 3) * 8 + (slot)] = clock64(); } while (0)
+// extras of an item (written by thread 0 of the team that loads it): 0 load issued at, 1 site (1, 2, 3; 9 = cold path), 2 pass type
+#define TRACEX(A, item, k, val) do { if ((A).trace) (A).trace[(size_t)(item) * 48 + 32 + (k)] = (long long)(val); } while (0)
 #else
 #define TRACE(A, item, slot) do { } while (0)
+#define TRACEX(A, item, k, val) do { } while (0)
 #endif
 
 // ---- asynchronous global -> shared copies: LDGSTS for the small tables, TMA for the tiles ----------------
@@ -250,9 +281,40 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned pari
                      : "=r"(done) : "r"(addr), "r"(parity) : "memory");
     } while (!done);
 }
-// named barrier 1: "every thread has read its outer-B operands" -- warps 1..3 only announce it, warp 0 waits
-__device__ __forceinline__ void tile_consumed_arrive() { asm volatile("bar.arrive 1, %0;" ::"n"(kThreads) : "memory"); }
-__device__ __forceinline__ void tile_consumed_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kThreads) : "memory"); }
+// Team-local barriers (barrier 0 stays the CTA-wide __syncthreads of the prologue):
+//   1 + team : the team's "__syncthreads";   3 + team : "this team is done with its tile buffer" -- warps 1..3
+//   only announce it, warp 0 waits and then issues the store / releases the buffer.
+__device__ __forceinline__ void team_sync(int team) { asm volatile("bar.sync %0, %1;" ::"r"(1 + team), "n"(kTeamThreads) : "memory"); }
+__device__ __forceinline__ void tile_done_arrive(int team) { asm volatile("bar.arrive %0, %1;" ::"r"(3 + team), "n"(kTeamThreads) : "memory"); }
+__device__ __forceinline__ void tile_done_sync(int team) { asm volatile("bar.sync %0, %1;" ::"r"(3 + team), "n"(kTeamThreads) : "memory"); }
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }   // stores have read their smem
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }         // stores are complete
+
+// Ownership of the three tile buffers.  Only thread 0 of a team touches this.
+struct CtaShared {
+    unsigned long long full[kBufs]; // tile landed (TMA complete_tx)
+    unsigned free_mask;             // buffers nobody owns
+    unsigned par_bits;              // bit b: the parity the next user of buffer b waits for on full[b]
+    unsigned turn;                  // the team that may claim a free buffer AHEAD of need (they alternate: without this the
+                                    // team that released a buffer takes it straight back and the other one never prefetches)
+    unsigned alive;                 // bit t: team t still has work
+};
+__device__ __forceinline__ int try_acquire(CtaShared& cs) {
+    unsigned m = *reinterpret_cast<volatile unsigned*>(&cs.free_mask);
+    while (m) {
+        const int b = __ffs(m) - 1;
+        const unsigned old = atomicAnd(&cs.free_mask, ~(1u << b));
+        if (old & (1u << b)) return b;
+        m = old & ~(1u << b);
+    }
+    return -1;
+}
+__device__ __forceinline__ int take_parity(CtaShared& cs, int b) { return (int)((atomicXor(&cs.par_bits, 1u << b) >> b) & 1u); }
+__device__ __forceinline__ void release_buffer(CtaShared& cs, int b) {
+    __threadfence_block();
+    atomicOr(&cs.free_mask, 1u << b);
+}
 
 // One work item = (pass p, ket g, tile t_id); written to shared memory by thread 0.
 struct ItemInfo {
@@ -260,7 +322,8 @@ struct ItemInfo {
     int p, g, t_id;                 // t_id = tile of THIS visit (an item is visited once per tile)
     int grp, sub, ip;               // item index inside its (ket, pass); tile index inside the item; item parity (sh.red slot)
     int valid;                      // p < n_pass of that ket
-    int ready;                      // its dependency was already satisfied when thread 0 polled
+    int ready;                      // its dependency was satisfied when thread 0 polled AND its tile load is in flight
+    int buf, par;                   // ... into this buffer, completing full[buf] with this parity
 };
 
 __device__ __forceinline__ void decode_item(const LaunchArgs& A, unsigned item, ItemInfo& I) {
@@ -291,10 +354,24 @@ __device__ __forceinline__ void issue_tile(const LaunchArgs& A, const KetDesc* _
     }
 }
 
+// The mirror image: one TMA instruction writes the finished tile back (thread 0, after the team's done-barrier).
+__device__ __forceinline__ void store_tile(const LaunchArgs& A, const KetDesc* __restrict__ kd, const int type,
+                                           const int t_id, const c128* __restrict__ tile) {
+    const CUtensorMap* map = A.maps + 2 * kd->map_buf + type;
+    if (type == 0) {
+        asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4}], [%1];"
+                     ::"l"(map), "r"(smem_u32(tile)), "r"(0), "r"(0), "r"(2 * t_id) : "memory");
+    } else {
+        asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+                     ::"l"(map), "r"(smem_u32(tile)), "r"(0), "r"(t_id << A.h_c1_shift), "r"(0), "r"(0) : "memory");
+    }
+    bulk_commit();
+}
+
 __device__ __forceinline__ void prefetch_tables(const PassStep* __restrict__ ps, PassStep* __restrict__ slot) {
     const char* s = reinterpret_cast<const char*>(ps);
     char* d = reinterpret_cast<char*>(slot);
-    for (int i = threadIdx.x; i < (int)(sizeof(PassStep) / 16); i += kThreads) cp_async16(d + 16 * i, s + 16 * i);
+    for (int i = threadIdx.x & (kTeamThreads - 1); i < (int)(sizeof(PassStep) / 16); i += kTeamThreads) cp_async16(d + 16 * i, s + 16 * i);
 }
 
 // Which PassStep sits in each of the two shared-memory table slots.  Two scalars, not an array: a dynamically
@@ -308,13 +385,13 @@ struct CachedSteps {
 
 struct Shared {
     ItemInfo info[2];
-    double red[2][kThreads / 32];   // energy partials of the item in slot `cur` (consumed one item later)
-    double red2[2][kThreads / 32];  // cross-term partials (linear mode)
+    double red[2][kTeamThreads / 32];   // energy partials of the item in slot `cur` (consumed one item later)
+    double red2[2][kTeamThreads / 32];  // cross-term partials (linear mode)
 };
 
 // Completion of an item is published one half-item late: thread 0 keeps the record here and releases it
-// right after the next item's mid-tile barrier, when the stores it covers were issued thousands of cycles
-// ago and the fence returns at once.  (Measured: a fence directly after the stores cost ~25% of the kernel.)
+// right after the next item's mid-tile barrier, when the bulk store it covers was issued thousands of cycles
+// ago and both the wait and the fence return at once.  (Measured: a fence directly after the stores cost ~25%.)
 struct Pending {
     double* partial;                // where to write the energy partial (NULL = none)
     double* partial2;               // cross-term partial (NULL = none)
@@ -327,14 +404,16 @@ __device__ __forceinline__ void flush_pending(const LaunchArgs& A, Shared& sh, P
     if (pd.g < 0) return;
     if (pd.partial) *pd.partial = (sh.red[pd.slot][0] + sh.red[pd.slot][1] + sh.red[pd.slot][2] + sh.red[pd.slot][3]) * pd.escale;
     if (pd.partial2) *pd.partial2 = (sh.red2[pd.slot][0] + sh.red2[pd.slot][1] + sh.red2[pd.slot][2] + sh.red2[pd.slot][3]) * pd.escale2;
-    asm volatile("fence.acq_rel.gpu;" ::: "memory");
+    bulk_wait_all();                // the item's bulk-tensor store is complete ...
+    asm volatile("fence.acq_rel.gpu;" ::: "memory");   // ... and ordered before the counter
     atomicAdd(&A.counters[1 + pd.g], 1u);
     pd.g = -1;
 }
 
 // Everything between "the tile is in shared memory" and "the tile is stored / reduced" for one pass type.
 // `nxt_raw` is the raw index of the following item (valid in thread 0 only); thread 0 turns it into
-// sh.info[nb] half-way through so that every thread can start prefetching that tile in outer-B.
+// sh.info[nb] half-way through, and as soon as that item's dependency holds and a tile buffer is free it
+// issues the TMA load of its tile -- usually a whole half-tile before this one is finished.
 template <bool SCALED, bool AJ, bool CROSS, int TYPE>
 __device__ __forceinline__ void process_tile(const LaunchArgs& A, const KetDesc* __restrict__ kd, const PassStep& P,
                                              c128* __restrict__ tile, Shared& sh, const KetDesc* __restrict__ skets,
@@ -342,10 +421,12 @@ __device__ __forceinline__ void process_tile(const LaunchArgs& A, const KetDesc*
                                              const unsigned nxt_raw, const int nb, const unsigned total,
                                              PassStep* __restrict__ cache, CachedSteps& cached_ps,
                                              const int cb, int& next_cb, bool& next_tables_new, Pending& pd,
-                                             unsigned long long* __restrict__ full) {
+                                             CtaShared& cs, c128* __restrict__ tiles, const int team, const int my_buf,
+                                             int& my_free, int& late_buf, int& late_par) {
     using G = Geo<TYPE>;
     const TypeGeom& T = A.geom[TYPE];
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x & (kTeamThreads - 1);
+
     const int flags = P.flags;
     const int p = I.p, t_id = I.t_id;
     const bool last_sub = I.sub + 1 == (1 << A.sub_log2);
@@ -396,6 +477,30 @@ __device__ __forceinline__ void process_tile(const LaunchArgs& A, const KetDesc*
     c128 v[kRegs];
     // ---- outer-A : own slots -> registers, K-bit rotations of the previous step -----------------------
 #pragma unroll
+    // thread 0: claim a free buffer for the next item and start its load (tried at several points of the tile)
+    bool dep_ok = false;
+    ItemInfo nI;
+    nI.valid = 0;
+    nI.ready = 0;
+    nI.buf = 0;
+    nI.par = 0;
+    // Before the mid-tile barrier the claim is published with the item (`ready`); after it (late = true) only thread 0
+    // knows, and the item takes the short form of the cold path at the top of the loop.
+    auto try_issue = [&](int site, bool late) {
+        const unsigned turn = *reinterpret_cast<volatile unsigned*>(&cs.turn);
+        const unsigned alive = *reinterpret_cast<volatile unsigned*>(&cs.alive);
+        if (turn != (unsigned)team && ((alive >> (team ^ 1)) & 1u)) return;
+        const int b = try_acquire(cs);
+        if (b < 0) return;
+        *reinterpret_cast<volatile unsigned*>(&cs.turn) = (unsigned)(team ^ 1);
+        TRACEX(A, nI.item, 0, clock64());
+        TRACEX(A, nI.item, 1, site);
+        const int pr = take_parity(cs, b);
+        if (late) { late_buf = b; late_par = pr; }
+        else { nI.buf = b; nI.par = pr; nI.ready = 1; }
+        const KetDesc* __restrict__ nkd = skets + nI.g;
+        issue_tile(A, nkd, (nI.p + nkd->cls) & 1, nI.p, nI.t_id, tiles + (size_t)b * kTile, &cs.full[b]);
+    };
     if (TYPE == 0) {
 #pragma unroll
         for (int j = 0; j < kRegs; ++j) v[j] = tile[slot(sK, G::regK(j))];
@@ -414,12 +519,14 @@ __device__ __forceinline__ void process_tile(const LaunchArgs& A, const KetDesc*
     if (TYPE == 1) __syncwarp();
 #pragma unroll
     for (int j = 0; j < kRegs; ++j) if (!(DQ_EXP & 2)) tile[slot(sK, G::regK(j))] = v[j];
-    // thread 0: the following item's dependency counter, polled now and consumed after the phase
+    // thread 0: the following item and its dependency counter
     unsigned polled = 0;
-    ItemInfo nI;
-    nI.valid = 0;
-    nI.ready = 0;
     if (tid == 0) {
+        if (my_free >= 0) {                  // the buffer of the previous tile becomes everybody's once its bulk store has read it
+            bulk_wait_read();
+            release_buffer(cs, my_free);
+            my_free = -1;
+        }
         if (!last_sub) {                     // next visit = next tile of the same item: nothing to fetch or poll
             nI = I;
             nI.sub = I.sub + 1;
@@ -430,17 +537,24 @@ __device__ __forceinline__ void process_tile(const LaunchArgs& A, const KetDesc*
             nI.ip = I.ip ^ 1;
             if (nxt_raw < total) {
                 nI.valid = nI.p < skets[nI.g].n_pass;
-                polled = nI.p > 0 ? ld_acquire(&A.counters[1 + nI.g]) : 0u;
+                polled = nI.p > 0 ? ld_relaxed(&A.counters[1 + nI.g]) : 0u;   // consumed after the J1 rotations
             }
         }
+        nI.ready = 0;
+        nI.buf = 0;
+        nI.par = 0;
     }
     TRACE(A, trace_item, 2);
-    if (TYPE == 0) __syncwarp(); else __syncthreads();    // L: the exchange never leaves the warp's 1024 amplitudes
+    if (TYPE == 0) __syncwarp(); else team_sync(team);    // L: the exchange never leaves the warp's 1024 amplitudes
 
     // ---- inner : J-bit rotations, phase, J-bit rotations ---------------------------------------------
 #pragma unroll
     for (int j = 0; j < kRegs; ++j) if (!(DQ_EXP & 2)) v[j] = tile[slot(sJ, G::regJ(j))];
     rot_run<SCALED>(v, P.rot[1], ovJ, shift_rc);
+    if (tid == 0) {
+        dep_ok = nI.valid && (!last_sub || nI.p == 0 || polled >= (unsigned)nI.p << A.ipp_log2);
+        if (dep_ok) try_issue(2, false);
+    }
     {
         const int kb = G::kbits(iJ);
         c128 phi = cmul(phi_tc, P.tkk[kb]);
@@ -501,11 +615,11 @@ __device__ __forceinline__ void process_tile(const LaunchArgs& A, const KetDesc*
 #pragma unroll
     for (int j = 0; j < kRegs; ++j) if (!(DQ_EXP & 2)) tile[slot(sJ, G::regJ(j))] = v[j];
     if (tid == 0) {                          // publish the following item
-        nI.ready = nI.valid && (!last_sub || nI.p == 0 || polled >= (unsigned)nI.p << A.ipp_log2);
+        if (dep_ok && !nI.ready) try_issue(3, false);
         sh.info[nb] = nI;
     }
     TRACE(A, trace_item, 3);
-    __syncthreads();
+    team_sync(team);
     TRACE(A, trace_item, 4);
     if (tid == 0) flush_pending(A, sh, pd);  // previous item: all of its stores were ordered by this barrier
 
@@ -521,13 +635,12 @@ __device__ __forceinline__ void process_tile(const LaunchArgs& A, const KetDesc*
             if (CROSS && kd->cross) asm volatile("prefetch.global.L2 [%0];" ::"l"(kd->cross + xK + o));
         }
     }
-    rot_bit<SCALED, 0>(v, P.rot[3][0]);      // every operand of this thread has now arrived in registers ...
-    if (tid < 32) tile_consumed_sync(); else tile_consumed_arrive();
+    rot_bit<SCALED, 0>(v, P.rot[3][0]);
     {
         const ItemInfo& N = sh.info[nb];
         next_cb = cb;
         next_tables_new = false;
-        if (N.ready) {                       // ... so the next tile may land while we finish this one
+        if (N.valid) {                       // the tables of the next item, whether or not its tile is on its way yet
             const KetDesc* __restrict__ nkd = skets + N.g;
             const PassStep* nps = nkd->steps + N.p;
             if (nps != cached_ps.get(cb)) {
@@ -538,50 +651,66 @@ __device__ __forceinline__ void process_tile(const LaunchArgs& A, const KetDesc*
                     next_tables_new = true;
                 }
             }
-            if (tid == 0) issue_tile(A, nkd, (N.p + nkd->cls) & 1, N.p, N.t_id, tile, full);
             cp_async_commit();
         }
     }
     TRACE(A, trace_item, 5);
+    if (tid == 0 && dep_ok && !nI.ready && late_buf < 0) try_issue(4, true);
     rot_bit<SCALED, 1>(v, P.rot[3][1]);
     rot_bit<SCALED, 2>(v, P.rot[3][2]);
     rot_bit<SCALED, 3>(v, P.rot[3][3]);
+    if (tid == 0 && dep_ok && !nI.ready && late_buf < 0) try_issue(5, true);
     TRACE(A, trace_item, 6);
-    // last level pair by pair: a pair is final as soon as it is rotated, so its two stores (or its two
-    // energy terms) are issued between the FMAs of the following pairs instead of in one blocking burst
+    rot_bit<SCALED, 4>(v, P.rot[3][4]);
     {
-        const double2 rc = P.rot[3][4];
         const bool do_store = (flags & F_STORE) != 0, do_energy = (flags & F_ENERGY) != 0;
-        c128* __restrict__ dst = kd->buf + xK;
         const double* __restrict__ md = A.mdiag + xK;
         const c128* __restrict__ cr = (CROSS && do_energy && kd->cross) ? kd->cross + xK : nullptr;
         double e = 0.0, e2 = 0.0;
+        if (do_store) {                      // back into the landing layout of this buffer; one bulk store takes it from there
+            if (TYPE == 0) {
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-            const c128 a = v[j], b = v[j + 16];
-            c128 na, nbv;
-            if (DQ_EXP & 1) { na = a; nbv = b; }
-            else if (SCALED) {
-                na = make_double2(fma(rc.y, b.y, a.x), fma(-rc.y, b.x, a.y));
-                nbv = make_double2(fma(rc.y, a.y, b.x), fma(-rc.y, a.x, b.y));
+                for (int j = 0; j < kRegs; ++j) tile[slot(sK, G::regK(j))] = v[j];
             } else {
-                na = make_double2(fma(rc.y, b.y, rc.x * a.x), fma(-rc.y, b.x, rc.x * a.y));
-                nbv = make_double2(fma(rc.y, a.y, rc.x * b.x), fma(-rc.y, a.x, rc.x * b.y));
+                __syncwarp();                // 64-byte pattern: these are not the slots this thread has just read
+                const int b0 = A.h_sw64 ? (iK ^ ((iK >> 3) & 3)) : sK;
+                const int b1 = A.h_sw64 ? b0 : (b0 ^ 4);
+#pragma unroll
+                for (int j = 0; j < kRegs; ++j) tile[((j & 1) ? b1 : b0) + G::regK(j)] = v[j];
             }
-            const size_t o0 = TYPE == 0 ? (size_t)G::regK(j) : (size_t)T.offK[j];
-            const size_t o1 = TYPE == 0 ? (size_t)G::regK(j + 16) : (size_t)T.offK[j + 16];
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        }
+        if (tid < 32) tile_done_sync(team); else tile_done_arrive(team);
+        if (tid == 0) {
             if (do_store) {
-                if (DQ_EXP & 4) { if (na.x == 1.2345e-300) __stcg(dst + j, na); }
-                else { __stcg(dst + o0, na); __stcg(dst + o1, nbv); }
+                store_tile(A, kd, TYPE, t_id, tile);
+                my_free = my_buf;            // released at the top of the next tile, when the store has read it
+            } else {
+                release_buffer(cs, my_buf);
             }
-            if (do_energy) {
-                const double m0 = __ldg(md + o0), m1 = __ldg(md + o1);
-                e = fma(m0, fma(na.x, na.x, na.y * na.y), e);
-                e = fma(m1, fma(nbv.x, nbv.x, nbv.y * nbv.y), e);
-                if (CROSS && cr) {               // Re conj(a) ket
-                    const c128 a0 = __ldcg(cr + o0), a1 = __ldcg(cr + o1);
-                    e2 = fma(m0, fma(a0.x, na.x, a0.y * na.y), e2);
-                    e2 = fma(m1, fma(a1.x, nbv.x, a1.y * nbv.y), e2);
+            if (dep_ok && !nI.ready && late_buf < 0) try_issue(6, true);
+            if (dep_ok && !nI.ready && late_buf < 0 && do_store) {
+                // nothing free and the next item is ready to go: take our own buffer back as soon as the store has read it
+                // (the other warps of the team are on their way to the top of the loop and wait there)
+                bulk_wait_read();
+                my_free = -1;
+                late_buf = my_buf;
+                late_par = take_parity(cs, my_buf);
+                TRACEX(A, nI.item, 0, clock64());
+                TRACEX(A, nI.item, 1, 7);
+                const KetDesc* __restrict__ nkd = skets + nI.g;
+                issue_tile(A, nkd, (nI.p + nkd->cls) & 1, nI.p, nI.t_id, tile, &cs.full[my_buf]);
+            }
+        }
+        if (do_energy) {
+#pragma unroll
+            for (int j = 0; j < kRegs; ++j) {
+                const size_t o = TYPE == 0 ? (size_t)G::regK(j) : (size_t)T.offK[j];
+                const double m = __ldg(md + o);
+                e = fma(m, fma(v[j].x, v[j].x, v[j].y * v[j].y), e);
+                if (CROSS && cr) {           // Re conj(a) ket
+                    const c128 a0 = __ldcg(cr + o);
+                    e2 = fma(m, fma(a0.x, v[j].x, a0.y * v[j].y), e2);
                 }
             }
         }
@@ -602,20 +731,26 @@ __device__ __forceinline__ void process_tile(const LaunchArgs& A, const KetDesc*
 template <bool SCALED, bool AJ, bool CROSS>
 __global__ void __launch_bounds__(kThreads, DQ_CTAS_PER_SM) k_fused_passes(const __grid_constant__ LaunchArgs A) {
     extern __shared__ __align__(16) unsigned char smem_dyn[];
-    // the 128-byte TMA swizzle is a function of the shared-memory address: the tile starts on a 1 KiB boundary
+    // the TMA swizzle is a function of the shared-memory address: the tile buffers start on a 1 KiB boundary
     unsigned char* smem_raw = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
-    c128* tile = reinterpret_cast<c128*>(smem_raw);
-    PassStep* cache = reinterpret_cast<PassStep*>(smem_raw + sizeof(c128) * kTile);     // two slots
+    c128* tiles = reinterpret_cast<c128*>(smem_raw);                                                  // kBufs buffers
+    PassStep* cache_all = reinterpret_cast<PassStep*>(smem_raw + sizeof(c128) * kTile * kBufs);      // two table slots per team
     // Ket descriptors live in shared memory: the acquire / release fences of the item protocol invalidate
     // L1 (CCTL.IVALL), so every kd-> field read from global memory was an exposed L2 round trip per tile.
-    KetDesc* skets = reinterpret_cast<KetDesc*>(smem_raw + sizeof(c128) * kTile + 2 * sizeof(PassStep));
-    __shared__ Shared sh;
-    __shared__ __align__(8) unsigned long long full_bar;    // completes when the tile issued by thread 0 has landed
+    KetDesc* skets = reinterpret_cast<KetDesc*>(smem_raw + sizeof(c128) * kTile * kBufs + 2 * kTeams * sizeof(PassStep));
+    __shared__ Shared sh_all[kTeams];
+    __shared__ __align__(8) CtaShared cs;
 
-    const int tid = threadIdx.x;
-    unsigned full_parity = 0;
-    if (tid == 0) {
-        mbar_init(&full_bar, 1);
+    const int team = threadIdx.x / kTeamThreads;
+    const int tid = threadIdx.x & (kTeamThreads - 1);
+    Shared& sh = sh_all[team];
+    PassStep* cache = cache_all + 2 * team;
+    if (threadIdx.x == 0) {
+        for (int b = 0; b < kBufs; ++b) mbar_init(&cs.full[b], 1);
+        cs.free_mask = (1u << kBufs) - 1u;
+        cs.par_bits = 0u;
+        cs.turn = 0u;
+        cs.alive = (1u << kTeams) - 1u;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     const unsigned total = ((unsigned)A.max_pass * (unsigned)A.n_kets) << A.ipp_log2;
@@ -623,6 +758,8 @@ __global__ void __launch_bounds__(kThreads, DQ_CTAS_PER_SM) k_fused_passes(const
     CachedSteps cached_ps;
     int cur = 0, cb = 0;
     bool prefetched = false, tables_new = false;
+    int my_free = -1;                          // thread 0: the buffer its last bulk store may still be reading
+    int late_buf = -1, late_par = 0;           // thread 0: the next tile was claimed after its item had been published
     Pending pd;
     pd.g = -1;
     pd.partial = nullptr;
@@ -631,59 +768,91 @@ __global__ void __launch_bounds__(kThreads, DQ_CTAS_PER_SM) k_fused_passes(const
     pd.escale2 = 0.0;
     pd.slot = 0;
 
-    // thread 0 reserves items ONE AHEAD: q_next is the raw index of the item after sh.info[cur], taken from
-    // the global counter a whole tile earlier, so the atomic's round trip is never waited for
+    // thread 0 of a team reserves items ONE AHEAD: q_next is the raw index of the item after sh.info[cur], taken
+    // from the global counter a whole tile earlier, so the atomic's round trip is never waited for
     unsigned q_next = 0;
     if (tid == 0) {
-        const unsigned first = atomicAdd(&A.counters[0], 1u);
-        q_next = atomicAdd(&A.counters[0], 1u);
+        const unsigned first = take_item(A.counters);
+        q_next = take_item(A.counters);
         ItemInfo I;
         decode_item(A, first, I);
         I.valid = 0;                           // completed below, once the descriptors are in shared memory
         I.ready = 0;
+        I.buf = 0;
+        I.par = 0;
         sh.info[0] = I;
     }
     {
         const int4* src = reinterpret_cast<const int4*>(A.kets);
         int4* dst = reinterpret_cast<int4*>(skets);
-        for (int i = tid; i < A.n_kets * (int)(sizeof(KetDesc) / 16); i += kThreads) dst[i] = __ldg(src + i);
+        for (int i = threadIdx.x; i < A.n_kets * (int)(sizeof(KetDesc) / 16); i += kThreads) dst[i] = __ldg(src + i);
     }
     __syncthreads();
     if (tid == 0) sh.info[0].valid = sh.info[0].item < total && sh.info[0].p < skets[sh.info[0].g].n_pass;
     __syncthreads();
+    // Start the teams half a tile apart: in step, they would want the spare buffer at the same moments and each would
+    // prefetch only every other tile; out of step, the spare alternates between them and every tile is prefetched.
+    if (team == 1) __nanosleep(DQ_STAGGER_NS);
 
     for (;;) {
         const ItemInfo I = sh.info[cur];
         if (I.item >= total) break;
         if (!I.valid) {                        // ragged group: this ket has no such pass; fetch another item
-            __syncthreads();
+            team_sync(team);
             if (tid == 0) {
                 flush_pending(A, sh, pd);
                 ItemInfo N;
                 decode_item(A, q_next, N);
-                q_next = atomicAdd(&A.counters[0], 1u);
+                q_next = take_item(A.counters);
                 N.valid = N.item < total && N.p < skets[N.g].n_pass;
                 N.ready = 0;
+                N.buf = 0;
+                N.par = 0;
                 sh.info[cur ^ 1] = N;
             }
-            __syncthreads();
+            team_sync(team);
             cur ^= 1;
             prefetched = false;
             continue;
         }
         const KetDesc* __restrict__ kd = skets + I.g;
+        int buf = I.buf, par = I.par;
+        if (tid == 0) TRACEX(A, I.item, 9, clock64());
         if (!prefetched) {                     // cold path: wait for the dependency, then fetch tile and tables
-            __syncthreads();                   // previous item's stores are issued: its release may go out
-            if (tid == 0) {
-                flush_pending(A, sh, pd);      // always before spinning: the dependency may be our own tile
+            team_sync(team);                   // the previous item is behind every thread of the team
+            if (tid == 0 && late_buf >= 0) {   // the load is already in flight: only the team has to be told where
+                sh.info[cur].buf = late_buf;
+                sh.info[cur].par = late_par;
+                late_buf = -1;
+            } else if (tid == 0) {
+                int b = try_acquire(cs);       // a free buffer, else our own last one once its store has read it
+                if (b < 0 && my_free >= 0) {
+                    b = my_free;
+                    my_free = -1;
+                    bulk_wait_read();
+                }
+                while (b < 0) {
+                    __nanosleep(64);
+                    b = try_acquire(cs);
+                }
                 if (I.p > 0) {
                     const unsigned need = (unsigned)I.p << A.ipp_log2;
-                    while (ld_acquire(&A.counters[1 + I.g]) < need) __nanosleep(32);
+                    if (ld_acquire(&A.counters[1 + I.g]) < need) {
+                        flush_pending(A, sh, pd);  // always before spinning: the dependency may be our own tile
+                        while (ld_acquire(&A.counters[1 + I.g]) < need) __nanosleep(32);
+                    }
                 }
+                const int pr = take_parity(cs, b);
+                sh.info[cur].buf = b;
+                sh.info[cur].par = pr;
+                TRACEX(A, I.item, 0, clock64());
+                TRACEX(A, I.item, 1, 9);
+                issue_tile(A, kd, (I.p + kd->cls) & 1, I.p, I.t_id, tiles + (size_t)b * kTile, &cs.full[b]);
             }
-            __syncthreads();
+            team_sync(team);
+            buf = sh.info[cur].buf;
+            par = sh.info[cur].par;
             const PassStep* ps = kd->steps + I.p;
-            tables_new = false;
             if (ps != cached_ps.get(cb)) {
                 cb ^= 1;
                 if (ps != cached_ps.get(cb)) {
@@ -692,29 +861,32 @@ __global__ void __launch_bounds__(kThreads, DQ_CTAS_PER_SM) k_fused_passes(const
                     tables_new = true;
                 }
             }
-            if (tid == 0) issue_tile(A, kd, (I.p + kd->cls) & 1, I.p, I.t_id, tile, &full_bar);
             cp_async_commit();
         }
-        unsigned nxt_raw = 0;
-        if (tid == 0 && I.sub + 1 == nsub) {   // consumed inside process_tile
-            nxt_raw = q_next;
-            q_next = atomicAdd(&A.counters[0], 1u);
-        }
+        if (tid == 0) TRACEX(A, I.item, 10, clock64());
         TRACE(A, I.item, 0);
         cp_async_wait_all();                   // this thread's share of the tables landed
-        if (tables_new) __syncthreads();       // tables in cache[cb] become visible to every thread
-        mbar_wait(&full_bar, full_parity);     // the tile landed (TMA complete_tx)
-        full_parity ^= 1u;
+        if (tables_new) team_sync(team);       // tables in cache[cb] become visible to every thread of the team
+        if (tid == 0) TRACEX(A, I.item, 3, clock64());
+        mbar_wait(&cs.full[buf], (unsigned)par);   // the tile landed (TMA complete_tx)
+        if (tid == 0) TRACEX(A, I.item, 4, clock64());
+        c128* tile = tiles + (size_t)buf * kTile;
+        unsigned nxt_raw = 0;
+        if (tid == 0 && I.sub + 1 == nsub) {   // consumed inside process_tile; after the waits above, which would also wait for it
+            nxt_raw = q_next;
+            q_next = take_item(A.counters);
+        }
         int next_cb = cb;
         bool next_tables_new = false;
         const PassStep& P = cache[cb];
         const int flags = P.flags;
+        if (tid == 0) { TRACEX(A, I.item, 2, P.type); TRACEX(A, I.item, 6, blockIdx.x * kTeams + team + 1); TRACEX(A, I.item, 7, I.p); }
         if (P.type == 0)
             process_tile<SCALED, AJ, CROSS, 0>(A, kd, P, tile, sh, skets, I, nxt_raw, cur ^ 1, total, cache, cached_ps, cb,
-                                        next_cb, next_tables_new, pd, &full_bar);
+                                        next_cb, next_tables_new, pd, cs, tiles, team, buf, my_free, late_buf, late_par);
         else
             process_tile<SCALED, AJ, CROSS, 1>(A, kd, P, tile, sh, skets, I, nxt_raw, cur ^ 1, total, cache, cached_ps, cb,
-                                        next_cb, next_tables_new, pd, &full_bar);
+                                        next_cb, next_tables_new, pd, cs, tiles, team, buf, my_free, late_buf, late_par);
         TRACE(A, I.item, 7);
         if (tid == 0 && I.sub + 1 == nsub) {   // item complete: published after the next item's mid-tile barrier
             pd.g = I.g;
@@ -728,10 +900,15 @@ __global__ void __launch_bounds__(kThreads, DQ_CTAS_PER_SM) k_fused_passes(const
         cur ^= 1;
         cb = next_cb;
         tables_new = next_tables_new;
+        if (tid == 0 && sh.info[cur].item < total) TRACEX(A, sh.info[cur].item, 8, clock64());
     }
     cp_async_wait_all();
-    __syncthreads();
-    if (tid == 0) flush_pending(A, sh, pd);
+    team_sync(team);
+    if (tid == 0) {
+        atomicAnd(&cs.alive, ~(1u << team));
+        bulk_wait_all();
+        flush_pending(A, sh, pd);
+    }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1075,7 +1252,7 @@ static Plan* get_plan(dq_ising* p) {
     pl->has_aj = pl->types[0].has_aj || pl->types[1].has_aj;
     pl->n_col_bits = p->n - 10;
     pl->tiles_log2 = p->n - kTileBits;
-    pl->smem_bytes = 1024 + sizeof(c128) * kTile + 2 * sizeof(PassStep) + kMaxGroup * sizeof(KetDesc);
+    pl->smem_bytes = 1024 + sizeof(c128) * kTile * kBufs + 2 * kTeams * sizeof(PassStep) + kMaxGroup * sizeof(KetDesc);
     {
         const int a = 22 - p->n;
         pl->h_c1_shift = a - std::min(a, 3);
@@ -1155,7 +1332,7 @@ static int launch_group(dq_ising* p, Plan* pl, const KetDesc* d_kets, int n_kets
     A.trace = nullptr;
 #if DQ_TRACE
     {
-        const size_t need = (size_t)all_items_for_trace(n_kets, pl->tiles_log2, max_pass) * 32 * sizeof(long long);
+        const size_t need = (size_t)all_items_for_trace(n_kets, pl->tiles_log2, max_pass) * 48 * sizeof(long long);
         if (pl->trace.reserve(need) == DQ_OK) { cudaMemsetAsync(pl->trace.p, 0, need, st); A.trace = pl->trace.as<long long>(); pl->trace_items = all_items_for_trace(n_kets, pl->tiles_log2, max_pass); }
     }
 #endif
@@ -1228,7 +1405,7 @@ extern "C" long long dq_debug_trace(dq_ising* p, long long* out, long long max_i
     if (!pl || !pl->trace.p) return 0;
     cudaStreamSynchronize(p->ctx->stream);
     long long n = std::min(max_items, pl->trace_items);
-    cudaMemcpy(out, pl->trace.p, (size_t)n * 32 * sizeof(long long), cudaMemcpyDeviceToHost);
+    cudaMemcpy(out, pl->trace.p, (size_t)n * 48 * sizeof(long long), cudaMemcpyDeviceToHost);
     return n;
 }
 
