@@ -46,7 +46,7 @@ constexpr int kBufs = 3;                   // tile buffers per CTA (one per team
 constexpr int kRegs = 32;                  // amplitudes per thread
 constexpr int kMaxNbr = 3;                 // neighbour bits per register qubit held in tables
 constexpr int kMaxPairs = 128;
-constexpr int kMaxGroup = 96;              // kets per launch (their descriptors are staged in shared memory)
+constexpr int kMaxGroup = 128;             // kets per launch (their descriptors are staged in shared memory)
 #ifndef DQ_EXP
 #define DQ_EXP 0      // timing experiments only: 1 no FP64 math, 2 no smem exchange, 4 no global traffic
 #endif
@@ -131,6 +131,9 @@ struct LaunchArgs {
     const double* mdiag;
     unsigned* counters;             // [0] next item, [1 + g] tiles done of ket g
     int n_kets;
+    int group;                      // kets that run concurrently; ket k >= group reuses the work buffer of ket k - group and
+                                    // starts when that one has finished (a launch CHAINS n_groups groups of `group` kets)
+    int n_groups;
     int max_pass;
     int tiles_log2;
     int sub_log2;                   // a work item is 2^sub_log2 consecutive tiles: one atomic / poll / release per item
@@ -332,9 +335,32 @@ __device__ __forceinline__ void decode_item(const LaunchArgs& A, unsigned item, 
     I.sub = 0;
     I.ip = 0;
     I.t_id = I.grp << A.sub_log2;
-    const unsigned rest = item >> A.ipp_log2;
-    I.g = (int)(rest % (unsigned)A.n_kets);
-    I.p = (int)(rest / (unsigned)A.n_kets);
+    const unsigned rest = item >> A.ipp_log2;          // group-major, then pass-major inside a group
+    const unsigned gl = rest % (unsigned)A.group;
+    const unsigned r2 = rest / (unsigned)A.group;
+    I.p = (int)(r2 % (unsigned)A.max_pass);
+    I.g = (int)((r2 / (unsigned)A.max_pass) * (unsigned)A.group + gl);
+}
+
+__device__ __forceinline__ bool item_valid(const LaunchArgs& A, const KetDesc* __restrict__ skets, const ItemInfo& I, unsigned total) {
+    return I.item < total && I.g < A.n_kets && I.p < skets[I.g].n_pass;
+}
+
+// What an item waits for: pass p > 0 for every tile of pass p - 1 of its ket; pass 0 of a chained ket for the whole ket
+// that used its work buffer before.  Returns false when there is nothing to wait for.
+__device__ __forceinline__ bool item_dependency(const LaunchArgs& A, const KetDesc* __restrict__ skets, int p, int g,
+                                                int& ctr, unsigned& need) {
+    if (p > 0) {
+        ctr = 1 + g;
+        need = (unsigned)p << A.ipp_log2;
+        return true;
+    }
+    if (g >= A.group) {
+        ctr = 1 + g - A.group;
+        need = (unsigned)skets[g - A.group].n_pass << A.ipp_log2;
+        return true;
+    }
+    return false;
 }
 
 // One TMA instruction brings the whole 64 KiB tile (thread 0 only).  L view: {8 amplitudes, 256 rows, pairs of
@@ -520,7 +546,7 @@ __device__ __forceinline__ void process_tile(const LaunchArgs& A, const KetDesc*
 #pragma unroll
     for (int j = 0; j < kRegs; ++j) if (!(DQ_EXP & 2)) tile[slot(sK, G::regK(j))] = v[j];
     // thread 0: the following item and its dependency counter
-    unsigned polled = 0;
+    unsigned polled = 0, need_next = 0;
     if (tid == 0) {
         if (my_free >= 0) {                  // the buffer of the previous tile becomes everybody's once its bulk store has read it
             bulk_wait_read();
@@ -535,10 +561,10 @@ __device__ __forceinline__ void process_tile(const LaunchArgs& A, const KetDesc*
         } else {
             decode_item(A, nxt_raw, nI);
             nI.ip = I.ip ^ 1;
-            if (nxt_raw < total) {
-                nI.valid = nI.p < skets[nI.g].n_pass;
-                polled = nI.p > 0 ? ld_relaxed(&A.counters[1 + nI.g]) : 0u;   // consumed after the J1 rotations
-            }
+            nI.valid = item_valid(A, skets, nI, total);
+            int ctr;
+            if (nI.valid && item_dependency(A, skets, nI.p, nI.g, ctr, need_next))
+                polled = ld_relaxed(&A.counters[ctr]);                         // consumed after the J1 rotations
         }
         nI.ready = 0;
         nI.buf = 0;
@@ -552,7 +578,7 @@ __device__ __forceinline__ void process_tile(const LaunchArgs& A, const KetDesc*
     for (int j = 0; j < kRegs; ++j) if (!(DQ_EXP & 2)) v[j] = tile[slot(sJ, G::regJ(j))];
     rot_run<SCALED>(v, P.rot[1], ovJ, shift_rc);
     if (tid == 0) {
-        dep_ok = nI.valid && (!last_sub || nI.p == 0 || polled >= (unsigned)nI.p << A.ipp_log2);
+        dep_ok = nI.valid && polled >= need_next;      // need_next = 0: nothing to wait for (or the next tile of this item)
         if (dep_ok) try_issue(2, false);
     }
     {
@@ -753,7 +779,7 @@ __global__ void __launch_bounds__(kThreads, DQ_CTAS_PER_SM) k_fused_passes(const
         cs.alive = (1u << kTeams) - 1u;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    const unsigned total = ((unsigned)A.max_pass * (unsigned)A.n_kets) << A.ipp_log2;
+    const unsigned total = ((unsigned)A.max_pass * (unsigned)A.group * (unsigned)A.n_groups) << A.ipp_log2;
     const int nsub = 1 << A.sub_log2;
     CachedSteps cached_ps;
     int cur = 0, cb = 0;
@@ -788,7 +814,7 @@ __global__ void __launch_bounds__(kThreads, DQ_CTAS_PER_SM) k_fused_passes(const
         for (int i = threadIdx.x; i < A.n_kets * (int)(sizeof(KetDesc) / 16); i += kThreads) dst[i] = __ldg(src + i);
     }
     __syncthreads();
-    if (tid == 0) sh.info[0].valid = sh.info[0].item < total && sh.info[0].p < skets[sh.info[0].g].n_pass;
+    if (tid == 0) sh.info[0].valid = item_valid(A, skets, sh.info[0], total);
     __syncthreads();
     // Start the teams half a tile apart: in step, they would want the spare buffer at the same moments and each would
     // prefetch only every other tile; out of step, the spare alternates between them and every tile is prefetched.
@@ -804,7 +830,7 @@ __global__ void __launch_bounds__(kThreads, DQ_CTAS_PER_SM) k_fused_passes(const
                 ItemInfo N;
                 decode_item(A, q_next, N);
                 q_next = take_item(A.counters);
-                N.valid = N.item < total && N.p < skets[N.g].n_pass;
+                N.valid = item_valid(A, skets, N, total);
                 N.ready = 0;
                 N.buf = 0;
                 N.par = 0;
@@ -835,11 +861,12 @@ __global__ void __launch_bounds__(kThreads, DQ_CTAS_PER_SM) k_fused_passes(const
                     __nanosleep(64);
                     b = try_acquire(cs);
                 }
-                if (I.p > 0) {
-                    const unsigned need = (unsigned)I.p << A.ipp_log2;
-                    if (ld_acquire(&A.counters[1 + I.g]) < need) {
+                int ctr;
+                unsigned need;
+                if (item_dependency(A, skets, I.p, I.g, ctr, need)) {
+                    if (ld_acquire(&A.counters[ctr]) < need) {
                         flush_pending(A, sh, pd);  // always before spinning: the dependency may be our own tile
-                        while (ld_acquire(&A.counters[1 + I.g]) < need) __nanosleep(32);
+                        while (ld_acquire(&A.counters[ctr]) < need) __nanosleep(32);
                     }
                 }
                 const int pr = take_parity(cs, b);
@@ -1321,9 +1348,12 @@ static int run_setup(dq_ising* p, Plan* pl, const std::vector<SetupJob>& jobs, c
 static long long all_items_for_trace(int n_kets, int tiles_log2, int max_pass) { return ((long long)n_kets << tiles_log2) * max_pass; }
 #endif
 
-static int launch_group(dq_ising* p, Plan* pl, const KetDesc* d_kets, int n_kets, int max_pass, bool scaled, double r) {
+static int launch_group(dq_ising* p, Plan* pl, const KetDesc* d_kets, int n_kets, int max_pass, bool scaled, double r,
+                        int chain_group = 0) {
     cudaStream_t st = p->ctx->stream;
-    DQ_REQUIRE(n_kets <= kMaxGroup, "fused engine: at most 96 kets per launch group");
+    DQ_REQUIRE(n_kets <= kMaxGroup, "fused engine: at most %d kets per launch", kMaxGroup);
+    const int group = (chain_group > 0 && chain_group < n_kets) ? chain_group : n_kets;
+    const int n_groups = (n_kets + group - 1) / group;
     if (pl->counter_cursor + 1 + n_kets > pl->counter_slots) pl->counter_cursor = 0;
     unsigned* ctr = pl->counters.as<unsigned>() + pl->counter_cursor;
     pl->counter_cursor += 1 + n_kets;
@@ -1332,8 +1362,8 @@ static int launch_group(dq_ising* p, Plan* pl, const KetDesc* d_kets, int n_kets
     A.trace = nullptr;
 #if DQ_TRACE
     {
-        const size_t need = (size_t)all_items_for_trace(n_kets, pl->tiles_log2, max_pass) * 48 * sizeof(long long);
-        if (pl->trace.reserve(need) == DQ_OK) { cudaMemsetAsync(pl->trace.p, 0, need, st); A.trace = pl->trace.as<long long>(); pl->trace_items = all_items_for_trace(n_kets, pl->tiles_log2, max_pass); }
+        const size_t need = (size_t)all_items_for_trace(group * n_groups, pl->tiles_log2, max_pass) * 48 * sizeof(long long);
+        if (pl->trace.reserve(need) == DQ_OK) { cudaMemsetAsync(pl->trace.p, 0, need, st); A.trace = pl->trace.as<long long>(); pl->trace_items = all_items_for_trace(group * n_groups, pl->tiles_log2, max_pass); }
     }
 #endif
     A.kets = d_kets;
@@ -1344,6 +1374,8 @@ static int launch_group(dq_ising* p, Plan* pl, const KetDesc* d_kets, int n_kets
     A.mdiag = p->mdiag.as<double>();
     A.counters = ctr;
     A.n_kets = n_kets;
+    A.group = group;
+    A.n_groups = n_groups;
     A.max_pass = max_pass;
     A.tiles_log2 = pl->tiles_log2;
     pl->sub_log2 = std::min(std::max(0, p->item_tiles_log2), pl->tiles_log2);
@@ -1353,7 +1385,7 @@ static int launch_group(dq_ising* p, Plan* pl, const KetDesc* d_kets, int n_kets
     A.r = r; A.ca = cos(alpha); A.sa = sin(alpha); A.c2a = cos(2 * alpha); A.s2a = sin(2 * alpha);
     A.geom[0] = pl->types[0].g;
     A.geom[1] = pl->types[1].g;
-    const long long all_items = ((long long)n_kets << A.ipp_log2) * max_pass;
+    const long long all_items = ((long long)(group * n_groups) << A.ipp_log2) * max_pass;
     long long grid = (long long)p->ctx->prop.multiProcessorCount * (p->grid_per_sm > 0 ? std::min(p->grid_per_sm, pl->ctas_per_sm) : pl->ctas_per_sm);
     if (grid > all_items) grid = all_items;
     const bool timed = p->time_launches != 0;
@@ -1596,12 +1628,12 @@ int fused_grad_run(dq_ising* p) {
         k.escale2 = 0.0;
         kets.push_back(k);
     }
-    struct Group { size_t first; int count; int max_pass; };
+    struct Group { size_t first; int count; int max_pass; int chain; };   // chain > 0: groups of `chain` kets share a work ring
     std::vector<Group> groups;
     for (int g0 = 0; g0 < B; g0 += G) {
         int cnt = std::min(G, B - g0), mp = 0;
         for (int g = 0; g < cnt; ++g) mp = std::max(mp, kets[g0 + g].n_pass);
-        groups.push_back({(size_t)g0, cnt, mp});
+        groups.push_back({(size_t)g0, cnt, mp, 0});
     }
     if (linear) {                       // a_b = U(suffix of b) phi_b : stored (cross terms) and reduced (Ea)
         for (int b = 0; b < B; ++b) {
@@ -1618,12 +1650,16 @@ int fused_grad_run(dq_ising* p) {
         for (int g0 = 0; g0 < B; g0 += G) {
             int cnt = std::min(G, B - g0), mp = 0;
             for (int g = 0; g < cnt; ++g) mp = std::max(mp, kets[B + g0 + g].n_pass);
-            groups.push_back({(size_t)(B + g0), cnt, mp});
+            groups.push_back({(size_t)(B + g0), cnt, mp, 0});
         }
     }
+    // One launch per sample: its shifted kets (class 0 first, then class 1) form a chain of groups of G kets that share
+    // the G work buffers -- ket k starts in the buffer of ket k - G as soon as that one is finished, so the SMs never
+    // drain between groups.
+    const int chain_len = std::max(G, (kMaxGroup / G) * G);
     for (int b = 0; b < B; ++b) {
+        std::vector<KetDesc> mine;
         for (int cls = 0; cls < 2; ++cls) {
-            std::vector<KetDesc> mine;
             for (int i = 0; i < n_shift; ++i) {
                 int kcls = 0, b0 = 0, b1 = 0;
                 if (s.shift_kind[i] == 0) {
@@ -1663,16 +1699,16 @@ int fused_grad_run(dq_ising* p) {
                     mine.push_back(k);
                 }
             }
-            for (size_t g0 = 0; g0 < mine.size(); g0 += G) {
-                const int cnt = (int)std::min<size_t>(G, mine.size() - g0);
-                for (int g = 0; g < cnt; ++g) {
-                    mine[g0 + g].buf = pl->work.as<c128>() + (size_t)g * N;
-                    mine[g0 + g].map_buf = view_of(mine[g0 + g].buf);
-                }
-                groups.push_back({kets.size() + g0, cnt, s.suffix_steps[b] + 1});
-            }
-            kets.insert(kets.end(), mine.begin(), mine.end());
         }
+        for (size_t g0 = 0; g0 < mine.size(); g0 += chain_len) {
+            const int cnt = (int)std::min<size_t>(chain_len, mine.size() - g0);
+            for (int g = 0; g < cnt; ++g) {
+                mine[g0 + g].buf = pl->work.as<c128>() + (size_t)(g % G) * N;
+                mine[g0 + g].map_buf = view_of(mine[g0 + g].buf);
+            }
+            groups.push_back({kets.size() + g0, cnt, s.suffix_steps[b] + 1, G});
+        }
+        kets.insert(kets.end(), mine.begin(), mine.end());
     }
     std::vector<int> out_index((size_t)B * kets_per);
     for (size_t i = 0; i < out_index.size(); ++i) out_index[i] = (int)i;
@@ -1685,7 +1721,7 @@ int fused_grad_run(dq_ising* p) {
     DQ_CUDA(cudaMemcpyAsync(pl->out_index.p, out_index.data(), out_index.size() * sizeof(int), cudaMemcpyHostToDevice, st));
 
     for (const Group& g : groups)
-        DQ_TRY(launch_group(p, pl, pl->kets.as<KetDesc>() + g.first, g.count, g.max_pass, scaled, s.r));
+        DQ_TRY(launch_group(p, pl, pl->kets.as<KetDesc>() + g.first, g.count, g.max_pass, scaled, s.r, g.chain));
 
     k_sum_partials<<<B * kets_per, 32, 0, st>>>(pl->partials.as<double>(), tiles, tiles >> pl->sub_log2, pl->out_index.as<int>(),
                                                  p->energies.as<double>());
