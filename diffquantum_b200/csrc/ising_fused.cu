@@ -53,8 +53,8 @@ constexpr int kMaxGroup = 128;             // kets per launch (their descriptors
 #ifndef DQ_TRACE
 #define DQ_TRACE 0    // 1: lane 0 of every warp records clock64() at phase boundaries of each item (debug)
 #endif
-#ifndef DQ_STAGGER_NS
-#define DQ_STAGGER_NS 3500
+#ifndef DQ_PACE_EARLY
+#define DQ_PACE_EARLY 0   // experiment: the follower team starts after the leader's outer-A round instead of after its J1 rotations
 #endif
 #ifndef DQ_CTAS_PER_SM
 #define DQ_CTAS_PER_SM 1
@@ -302,7 +302,28 @@ struct CtaShared {
     unsigned turn;                  // the team that may claim a free buffer AHEAD of need (they alternate: without this the
                                     // team that released a buffer takes it straight back and the other one never prefetches)
     unsigned alive;                 // bit t: team t still has work
+    // Pacing (see pace_team): how many of its tiles team t has taken past the J1 rotations / past the mid-tile barrier
+    unsigned mid2[kTeams], mid3[kTeams];
 };
+
+// The tile body is ~48 KiB of straight-line code per pass type, the per-SM instruction cache holds 32 KiB, and four warps
+// in step share one fetch -- so every line was fetched from the GPC-level cache once per team and tile, and that cache
+// ran at 96 % of its request rate (ncu gcc__cache_requests_type_instruction): the kernel was instruction-fetch bound.
+// Team 1 therefore FOLLOWS team 0 through the same code a few thousand cycles behind, close enough to hit the lines team 0
+// has just brought in: it starts its k-th tile only once team 0 is past the J1 rotations of its k-th tile, and team 0
+// starts its next tile only once team 1 is past the mid-tile barrier of its previous one.  The same distance is what lets
+// the spare tile buffer alternate between the teams.  Waits are bounded: the other team may be spinning on a dependency
+// that only our own pending release can satisfy.
+__device__ __forceinline__ void pace_team(CtaShared& cs, int team, unsigned my_tiles) {
+    const unsigned alive = *reinterpret_cast<volatile unsigned*>(&cs.alive);
+    if (!((alive >> (team ^ 1)) & 1u)) return;
+    volatile unsigned* mark = team == 1 ? &cs.mid2[0] : &cs.mid3[1];
+    const unsigned need = team == 1 ? my_tiles + 1u : my_tiles;
+    for (int spin = 0; spin < 200 && *mark < need; ++spin) {
+        __nanosleep(20);
+        if (!((*reinterpret_cast<volatile unsigned*>(&cs.alive) >> (team ^ 1)) & 1u)) return;
+    }
+}
 __device__ __forceinline__ int try_acquire(CtaShared& cs) {
     unsigned m = *reinterpret_cast<volatile unsigned*>(&cs.free_mask);
     while (m) {
@@ -448,7 +469,7 @@ __device__ __forceinline__ void process_tile(const LaunchArgs& A, const KetDesc*
                                              PassStep* __restrict__ cache, CachedSteps& cached_ps,
                                              const int cb, int& next_cb, bool& next_tables_new, Pending& pd,
                                              CtaShared& cs, c128* __restrict__ tiles, const int team, const int my_buf,
-                                             int& my_free, int& late_buf, int& late_par) {
+                                             int& my_free, int& late_buf, int& late_par, const unsigned my_tiles) {
     using G = Geo<TYPE>;
     const TypeGeom& T = A.geom[TYPE];
     const int tid = threadIdx.x & (kTeamThreads - 1);
@@ -569,6 +590,9 @@ __device__ __forceinline__ void process_tile(const LaunchArgs& A, const KetDesc*
         nI.ready = 0;
         nI.buf = 0;
         nI.par = 0;
+#if DQ_PACE_EARLY
+        *reinterpret_cast<volatile unsigned*>(&cs.mid2[team]) = my_tiles;
+#endif
     }
     TRACE(A, trace_item, 2);
     if (TYPE == 0) __syncwarp(); else team_sync(team);    // L: the exchange never leaves the warp's 1024 amplitudes
@@ -578,6 +602,7 @@ __device__ __forceinline__ void process_tile(const LaunchArgs& A, const KetDesc*
     for (int j = 0; j < kRegs; ++j) if (!(DQ_EXP & 2)) v[j] = tile[slot(sJ, G::regJ(j))];
     rot_run<SCALED>(v, P.rot[1], ovJ, shift_rc);
     if (tid == 0) {
+        *reinterpret_cast<volatile unsigned*>(&cs.mid2[team]) = my_tiles;
         dep_ok = nI.valid && polled >= need_next;      // need_next = 0: nothing to wait for (or the next tile of this item)
         if (dep_ok) try_issue(2, false);
     }
@@ -643,6 +668,7 @@ __device__ __forceinline__ void process_tile(const LaunchArgs& A, const KetDesc*
     if (tid == 0) {                          // publish the following item
         if (dep_ok && !nI.ready) try_issue(3, false);
         sh.info[nb] = nI;
+        *reinterpret_cast<volatile unsigned*>(&cs.mid3[team]) = my_tiles;
     }
     TRACE(A, trace_item, 3);
     team_sync(team);
@@ -777,6 +803,7 @@ __global__ void __launch_bounds__(kThreads, DQ_CTAS_PER_SM) k_fused_passes(const
         cs.par_bits = 0u;
         cs.turn = 0u;
         cs.alive = (1u << kTeams) - 1u;
+        for (int t = 0; t < kTeams; ++t) cs.mid2[t] = cs.mid3[t] = 0u;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     const unsigned total = ((unsigned)A.max_pass * (unsigned)A.group * (unsigned)A.n_groups) << A.ipp_log2;
@@ -786,6 +813,7 @@ __global__ void __launch_bounds__(kThreads, DQ_CTAS_PER_SM) k_fused_passes(const
     bool prefetched = false, tables_new = false;
     int my_free = -1;                          // thread 0: the buffer its last bulk store may still be reading
     int late_buf = -1, late_par = 0;           // thread 0: the next tile was claimed after its item had been published
+    unsigned my_tiles = 0;                     // tiles this team has started
     Pending pd;
     pd.g = -1;
     pd.partial = nullptr;
@@ -816,9 +844,6 @@ __global__ void __launch_bounds__(kThreads, DQ_CTAS_PER_SM) k_fused_passes(const
     __syncthreads();
     if (tid == 0) sh.info[0].valid = item_valid(A, skets, sh.info[0], total);
     __syncthreads();
-    // Start the teams half a tile apart: in step, they would want the spare buffer at the same moments and each would
-    // prefetch only every other tile; out of step, the spare alternates between them and every tile is prefetched.
-    if (team == 1) __nanosleep(DQ_STAGGER_NS);
 
     for (;;) {
         const ItemInfo I = sh.info[cur];
@@ -843,6 +868,9 @@ __global__ void __launch_bounds__(kThreads, DQ_CTAS_PER_SM) k_fused_passes(const
         }
         const KetDesc* __restrict__ kd = skets + I.g;
         int buf = I.buf, par = I.par;
+        if (tid == 0) pace_team(cs, team, my_tiles);
+        ++my_tiles;
+        team_sync(team);
         if (tid == 0) TRACEX(A, I.item, 9, clock64());
         if (!prefetched) {                     // cold path: wait for the dependency, then fetch tile and tables
             team_sync(team);                   // the previous item is behind every thread of the team
@@ -910,10 +938,10 @@ __global__ void __launch_bounds__(kThreads, DQ_CTAS_PER_SM) k_fused_passes(const
         if (tid == 0) { TRACEX(A, I.item, 2, P.type); TRACEX(A, I.item, 6, blockIdx.x * kTeams + team + 1); TRACEX(A, I.item, 7, I.p); }
         if (P.type == 0)
             process_tile<SCALED, AJ, CROSS, 0>(A, kd, P, tile, sh, skets, I, nxt_raw, cur ^ 1, total, cache, cached_ps, cb,
-                                        next_cb, next_tables_new, pd, cs, tiles, team, buf, my_free, late_buf, late_par);
+                                        next_cb, next_tables_new, pd, cs, tiles, team, buf, my_free, late_buf, late_par, my_tiles);
         else
             process_tile<SCALED, AJ, CROSS, 1>(A, kd, P, tile, sh, skets, I, nxt_raw, cur ^ 1, total, cache, cached_ps, cb,
-                                        next_cb, next_tables_new, pd, cs, tiles, team, buf, my_free, late_buf, late_par);
+                                        next_cb, next_tables_new, pd, cs, tiles, team, buf, my_free, late_buf, late_par, my_tiles);
         TRACE(A, I.item, 7);
         if (tid == 0 && I.sub + 1 == nsub) {   // item complete: published after the next item's mid-tile barrier
             pd.g = I.g;
