@@ -53,6 +53,9 @@ constexpr int kMaxGroup = 128;             // kets per launch (their descriptors
 #ifndef DQ_TRACE
 #define DQ_TRACE 0    // 1: lane 0 of every warp records clock64() at phase boundaries of each item (debug)
 #endif
+#ifndef DQ_PACE_TIGHT
+#define DQ_PACE_TIGHT 0   // experiment: the leader waits for the follower's mid-tile barrier instead of its J1 mark (measured: -2 %)
+#endif
 #ifndef DQ_PACE_EARLY
 #define DQ_PACE_EARLY 0   // experiment: the follower team starts after the leader's outer-A round instead of after its J1 rotations
 #endif
@@ -311,13 +314,17 @@ struct CtaShared {
 // ran at 96 % of its request rate (ncu gcc__cache_requests_type_instruction): the kernel was instruction-fetch bound.
 // Team 1 therefore FOLLOWS team 0 through the same code a few thousand cycles behind, close enough to hit the lines team 0
 // has just brought in: it starts its k-th tile only once team 0 is past the J1 rotations of its k-th tile, and team 0
-// starts its next tile only once team 1 is past the mid-tile barrier of its previous one.  The same distance is what lets
+// starts its next tile only once team 1 is past the J1 rotations of its previous one.  The same distance is what lets
 // the spare tile buffer alternate between the teams.  Waits are bounded: the other team may be spinning on a dependency
 // that only our own pending release can satisfy.
 __device__ __forceinline__ void pace_team(CtaShared& cs, int team, unsigned my_tiles) {
     const unsigned alive = *reinterpret_cast<volatile unsigned*>(&cs.alive);
     if (!((alive >> (team ^ 1)) & 1u)) return;
+#if DQ_PACE_TIGHT
     volatile unsigned* mark = team == 1 ? &cs.mid2[0] : &cs.mid3[1];
+#else
+    volatile unsigned* mark = &cs.mid2[team ^ 1];
+#endif
     const unsigned need = team == 1 ? my_tiles + 1u : my_tiles;
     for (int spin = 0; spin < 200 && *mark < need; ++spin) {
         __nanosleep(20);
@@ -469,7 +476,7 @@ __device__ __forceinline__ void process_tile(const LaunchArgs& A, const KetDesc*
                                              PassStep* __restrict__ cache, CachedSteps& cached_ps,
                                              const int cb, int& next_cb, bool& next_tables_new, Pending& pd,
                                              CtaShared& cs, c128* __restrict__ tiles, const int team, const int my_buf,
-                                             int& my_free, int& late_buf, int& late_par, const unsigned my_tiles) {
+                                             int& my_free, const unsigned my_tiles) {
     using G = Geo<TYPE>;
     const TypeGeom& T = A.geom[TYPE];
     const int tid = threadIdx.x & (kTeamThreads - 1);
@@ -531,8 +538,8 @@ __device__ __forceinline__ void process_tile(const LaunchArgs& A, const KetDesc*
     nI.ready = 0;
     nI.buf = 0;
     nI.par = 0;
-    // Before the mid-tile barrier the claim is published with the item (`ready`); after it (late = true) only thread 0
-    // knows, and the item takes the short form of the cold path at the top of the loop.
+    // Before the mid-tile barrier the claim is published with the item; after it (late = true) thread 0 patches the
+    // published item -- every thread reads it behind the team barrier at the top of the loop.
     auto try_issue = [&](int site, bool late) {
         const unsigned turn = *reinterpret_cast<volatile unsigned*>(&cs.turn);
         const unsigned alive = *reinterpret_cast<volatile unsigned*>(&cs.alive);
@@ -543,8 +550,14 @@ __device__ __forceinline__ void process_tile(const LaunchArgs& A, const KetDesc*
         TRACEX(A, nI.item, 0, clock64());
         TRACEX(A, nI.item, 1, site);
         const int pr = take_parity(cs, b);
-        if (late) { late_buf = b; late_par = pr; }
-        else { nI.buf = b; nI.par = pr; nI.ready = 1; }
+        nI.buf = b;
+        nI.par = pr;
+        nI.ready = 1;
+        if (late) {
+            sh.info[nb].buf = b;
+            sh.info[nb].par = pr;
+            sh.info[nb].ready = 1;
+        }
         const KetDesc* __restrict__ nkd = skets + nI.g;
         issue_tile(A, nkd, (nI.p + nkd->cls) & 1, nI.p, nI.t_id, tiles + (size_t)b * kTile, &cs.full[b]);
     };
@@ -707,11 +720,11 @@ __device__ __forceinline__ void process_tile(const LaunchArgs& A, const KetDesc*
         }
     }
     TRACE(A, trace_item, 5);
-    if (tid == 0 && dep_ok && !nI.ready && late_buf < 0) try_issue(4, true);
+    if (tid == 0 && dep_ok && !nI.ready) try_issue(4, true);
     rot_bit<SCALED, 1>(v, P.rot[3][1]);
     rot_bit<SCALED, 2>(v, P.rot[3][2]);
     rot_bit<SCALED, 3>(v, P.rot[3][3]);
-    if (tid == 0 && dep_ok && !nI.ready && late_buf < 0) try_issue(5, true);
+    if (tid == 0 && dep_ok && !nI.ready) try_issue(5, true);
     TRACE(A, trace_item, 6);
     rot_bit<SCALED, 4>(v, P.rot[3][4]);
     {
@@ -740,14 +753,15 @@ __device__ __forceinline__ void process_tile(const LaunchArgs& A, const KetDesc*
             } else {
                 release_buffer(cs, my_buf);
             }
-            if (dep_ok && !nI.ready && late_buf < 0) try_issue(6, true);
-            if (dep_ok && !nI.ready && late_buf < 0 && do_store) {
+            if (dep_ok && !nI.ready) try_issue(6, true);
+            if (dep_ok && !nI.ready && do_store) {
                 // nothing free and the next item is ready to go: take our own buffer back as soon as the store has read it
                 // (the other warps of the team are on their way to the top of the loop and wait there)
                 bulk_wait_read();
                 my_free = -1;
-                late_buf = my_buf;
-                late_par = take_parity(cs, my_buf);
+                sh.info[nb].buf = my_buf;
+                sh.info[nb].par = take_parity(cs, my_buf);
+                sh.info[nb].ready = 1;
                 TRACEX(A, nI.item, 0, clock64());
                 TRACEX(A, nI.item, 1, 7);
                 const KetDesc* __restrict__ nkd = skets + nI.g;
@@ -810,9 +824,8 @@ __global__ void __launch_bounds__(kThreads, DQ_CTAS_PER_SM) k_fused_passes(const
     const int nsub = 1 << A.sub_log2;
     CachedSteps cached_ps;
     int cur = 0, cb = 0;
-    bool prefetched = false, tables_new = false;
+    bool tables_new = false;
     int my_free = -1;                          // thread 0: the buffer its last bulk store may still be reading
-    int late_buf = -1, late_par = 0;           // thread 0: the next tile was claimed after its item had been published
     unsigned my_tiles = 0;                     // tiles this team has started
     Pending pd;
     pd.g = -1;
@@ -846,6 +859,8 @@ __global__ void __launch_bounds__(kThreads, DQ_CTAS_PER_SM) k_fused_passes(const
     __syncthreads();
 
     for (;;) {
+        if (tid == 0) pace_team(cs, team, my_tiles);
+        team_sync(team);                       // also: thread 0's late claim of this item's tile is visible to the team
         const ItemInfo I = sh.info[cur];
         if (I.item >= total) break;
         if (!I.valid) {                        // ragged group: this ket has no such pass; fetch another item
@@ -863,22 +878,14 @@ __global__ void __launch_bounds__(kThreads, DQ_CTAS_PER_SM) k_fused_passes(const
             }
             team_sync(team);
             cur ^= 1;
-            prefetched = false;
             continue;
         }
         const KetDesc* __restrict__ kd = skets + I.g;
         int buf = I.buf, par = I.par;
-        if (tid == 0) pace_team(cs, team, my_tiles);
         ++my_tiles;
-        team_sync(team);
         if (tid == 0) TRACEX(A, I.item, 9, clock64());
-        if (!prefetched) {                     // cold path: wait for the dependency, then fetch tile and tables
-            team_sync(team);                   // the previous item is behind every thread of the team
-            if (tid == 0 && late_buf >= 0) {   // the load is already in flight: only the team has to be told where
-                sh.info[cur].buf = late_buf;
-                sh.info[cur].par = late_par;
-                late_buf = -1;
-            } else if (tid == 0) {
+        if (!I.ready) {                        // cold path: wait for the dependency, then fetch tile and tables
+            if (tid == 0) {
                 int b = try_acquire(cs);       // a free buffer, else our own last one once its store has read it
                 if (b < 0 && my_free >= 0) {
                     b = my_free;
@@ -938,10 +945,10 @@ __global__ void __launch_bounds__(kThreads, DQ_CTAS_PER_SM) k_fused_passes(const
         if (tid == 0) { TRACEX(A, I.item, 2, P.type); TRACEX(A, I.item, 6, blockIdx.x * kTeams + team + 1); TRACEX(A, I.item, 7, I.p); }
         if (P.type == 0)
             process_tile<SCALED, AJ, CROSS, 0>(A, kd, P, tile, sh, skets, I, nxt_raw, cur ^ 1, total, cache, cached_ps, cb,
-                                        next_cb, next_tables_new, pd, cs, tiles, team, buf, my_free, late_buf, late_par, my_tiles);
+                                        next_cb, next_tables_new, pd, cs, tiles, team, buf, my_free, my_tiles);
         else
             process_tile<SCALED, AJ, CROSS, 1>(A, kd, P, tile, sh, skets, I, nxt_raw, cur ^ 1, total, cache, cached_ps, cb,
-                                        next_cb, next_tables_new, pd, cs, tiles, team, buf, my_free, late_buf, late_par, my_tiles);
+                                        next_cb, next_tables_new, pd, cs, tiles, team, buf, my_free, my_tiles);
         TRACE(A, I.item, 7);
         if (tid == 0 && I.sub + 1 == nsub) {   // item complete: published after the next item's mid-tile barrier
             pd.g = I.g;
@@ -951,7 +958,6 @@ __global__ void __launch_bounds__(kThreads, DQ_CTAS_PER_SM) k_fused_passes(const
             pd.escale2 = kd->escale2;
             pd.slot = I.ip;
         }
-        prefetched = sh.info[cur ^ 1].ready != 0;
         cur ^= 1;
         cb = next_cb;
         tables_new = next_tables_new;
