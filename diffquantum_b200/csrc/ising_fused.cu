@@ -138,6 +138,7 @@ struct LaunchArgs {
                                     // starts when that one has finished (a launch CHAINS n_groups groups of `group` kets)
     int n_groups;
     int max_pass;
+    unsigned long long inv_group, inv_pass;   // floor(2^64 / d) + 1: x / d = umul64hi(x, inv) for every 32-bit x (d >= 2)
     int tiles_log2;
     int sub_log2;                   // a work item is 2^sub_log2 consecutive tiles: one atomic / poll / release per item
     int ipp_log2;                   // items per (ket, pass) = tiles >> sub_log2
@@ -300,11 +301,12 @@ __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wa
 // Ownership of the three tile buffers.  Only thread 0 of a team touches this.
 struct CtaShared {
     unsigned long long full[kBufs]; // tile landed (TMA complete_tx)
-    unsigned free_mask;             // buffers nobody owns
-    unsigned par_bits;              // bit b: the parity the next user of buffer b waits for on full[b]
-    unsigned turn;                  // the team that may claim a free buffer AHEAD of need (they alternate: without this the
-                                    // team that released a buffer takes it straight back and the other one never prefetches)
-    unsigned alive;                 // bit t: team t still has work
+    // One word, so that a claim is one load and one compare-and-swap:
+    //   bits 0..2  buffers nobody owns          bits 3..5  the parity the next user of buffer b waits for on full[b]
+    //   bit  6     the team that may claim a free buffer AHEAD of need (they alternate: without this the team that
+    //              released a buffer takes it straight back and the other one never prefetches)
+    //   bits 7..8  team t still has work
+    unsigned state;
     // Pacing (see pace_team): how many of its tiles team t has taken past the J1 rotations / past the mid-tile barrier
     unsigned mid2[kTeams], mid3[kTeams];
 };
@@ -318,8 +320,7 @@ struct CtaShared {
 // the spare tile buffer alternate between the teams.  Waits are bounded: the other team may be spinning on a dependency
 // that only our own pending release can satisfy.
 __device__ __forceinline__ void pace_team(CtaShared& cs, int team, unsigned my_tiles) {
-    const unsigned alive = *reinterpret_cast<volatile unsigned*>(&cs.alive);
-    if (!((alive >> (team ^ 1)) & 1u)) return;
+    if (!((*reinterpret_cast<volatile unsigned*>(&cs.state) >> (7 + (team ^ 1))) & 1u)) return;
 #if DQ_PACE_TIGHT
     volatile unsigned* mark = team == 1 ? &cs.mid2[0] : &cs.mid3[1];
 #else
@@ -328,23 +329,30 @@ __device__ __forceinline__ void pace_team(CtaShared& cs, int team, unsigned my_t
     const unsigned need = team == 1 ? my_tiles + 1u : my_tiles;
     for (int spin = 0; spin < 200 && *mark < need; ++spin) {
         __nanosleep(20);
-        if (!((*reinterpret_cast<volatile unsigned*>(&cs.alive) >> (team ^ 1)) & 1u)) return;
+        if (!((*reinterpret_cast<volatile unsigned*>(&cs.state) >> (7 + (team ^ 1))) & 1u)) return;
     }
 }
-__device__ __forceinline__ int try_acquire(CtaShared& cs) {
-    unsigned m = *reinterpret_cast<volatile unsigned*>(&cs.free_mask);
-    while (m) {
+// Claim a free buffer: returns buffer | parity << 4, or -1.  `ahead`: a claim ahead of need honours the turn (unless the
+// other team is gone) and passes it on.
+__device__ __forceinline__ int claim_buffer(CtaShared& cs, int team, bool ahead) {
+    unsigned st = *reinterpret_cast<volatile unsigned*>(&cs.state);
+    for (;;) {
+        if (ahead && ((st >> 6) & 1u) != (unsigned)team && ((st >> (7 + (team ^ 1))) & 1u)) return -1;
+        const unsigned m = st & 7u;
+        if (!m) return -1;
         const int b = __ffs(m) - 1;
-        const unsigned old = atomicAnd(&cs.free_mask, ~(1u << b));
-        if (old & (1u << b)) return b;
-        m = old & ~(1u << b);
+        unsigned nw = (st & ~(1u << b)) ^ (8u << b);
+        if (ahead) nw = (nw & ~64u) | ((unsigned)(team ^ 1) << 6);
+        const unsigned old = atomicCAS(&cs.state, st, nw);
+        if (old == st) return b | (int)(((st >> (3 + b)) & 1u) << 4);
+        st = old;
     }
-    return -1;
 }
-__device__ __forceinline__ int take_parity(CtaShared& cs, int b) { return (int)((atomicXor(&cs.par_bits, 1u << b) >> b) & 1u); }
+// Keep a buffer we already own for one more tile: only its parity advances.
+__device__ __forceinline__ int take_parity(CtaShared& cs, int b) { return (int)((atomicXor(&cs.state, 8u << b) >> (3 + b)) & 1u); }
 __device__ __forceinline__ void release_buffer(CtaShared& cs, int b) {
     __threadfence_block();
-    atomicOr(&cs.free_mask, 1u << b);
+    atomicOr(&cs.state, 1u << b);
 }
 
 // One work item = (pass p, ket g, tile t_id); written to shared memory by thread 0.
@@ -364,10 +372,11 @@ __device__ __forceinline__ void decode_item(const LaunchArgs& A, unsigned item, 
     I.ip = 0;
     I.t_id = I.grp << A.sub_log2;
     const unsigned rest = item >> A.ipp_log2;          // group-major, then pass-major inside a group
-    const unsigned gl = rest % (unsigned)A.group;
-    const unsigned r2 = rest / (unsigned)A.group;
-    I.p = (int)(r2 % (unsigned)A.max_pass);
-    I.g = (int)((r2 / (unsigned)A.max_pass) * (unsigned)A.group + gl);
+    const unsigned r2 = A.group > 1 ? (unsigned)__umul64hi((unsigned long long)rest, A.inv_group) : rest;
+    const unsigned gl = rest - r2 * (unsigned)A.group;
+    const unsigned r3 = A.max_pass > 1 ? (unsigned)__umul64hi((unsigned long long)r2, A.inv_pass) : r2;
+    I.p = (int)(r2 - r3 * (unsigned)A.max_pass);
+    I.g = (int)(r3 * (unsigned)A.group + gl);
 }
 
 __device__ __forceinline__ bool item_valid(const LaunchArgs& A, const KetDesc* __restrict__ skets, const ItemInfo& I, unsigned total) {
@@ -458,8 +467,9 @@ __device__ __forceinline__ void flush_pending(const LaunchArgs& A, Shared& sh, P
     if (pd.g < 0) return;
     if (pd.partial) *pd.partial = (sh.red[pd.slot][0] + sh.red[pd.slot][1] + sh.red[pd.slot][2] + sh.red[pd.slot][3]) * pd.escale;
     if (pd.partial2) *pd.partial2 = (sh.red2[pd.slot][0] + sh.red2[pd.slot][1] + sh.red2[pd.slot][2] + sh.red2[pd.slot][3]) * pd.escale2;
-    bulk_wait_all();                // the item's bulk-tensor store is complete ...
-    asm volatile("fence.acq_rel.gpu;" ::: "memory");   // ... and ordered before the counter
+    // The item's bulk-tensor store is complete (performed at L2) before the counter moves; the consumers read the tile with
+    // a TMA load from L2.  No gpu-scope fence: it cost thread 0 ~500 cycles per tile and orders nothing that is still in flight.
+    bulk_wait_all();
     atomicAdd(&A.counters[1 + pd.g], 1u);
     pd.g = -1;
 }
@@ -541,15 +551,12 @@ __device__ __forceinline__ void process_tile(const LaunchArgs& A, const KetDesc*
     // Before the mid-tile barrier the claim is published with the item; after it (late = true) thread 0 patches the
     // published item -- every thread reads it behind the team barrier at the top of the loop.
     auto try_issue = [&](int site, bool late) {
-        const unsigned turn = *reinterpret_cast<volatile unsigned*>(&cs.turn);
-        const unsigned alive = *reinterpret_cast<volatile unsigned*>(&cs.alive);
-        if (turn != (unsigned)team && ((alive >> (team ^ 1)) & 1u)) return;
-        const int b = try_acquire(cs);
-        if (b < 0) return;
-        *reinterpret_cast<volatile unsigned*>(&cs.turn) = (unsigned)(team ^ 1);
+        const int got = claim_buffer(cs, team, true);
+        if (got < 0) return;
+        const int b = got & 15;
         TRACEX(A, nI.item, 0, clock64());
         TRACEX(A, nI.item, 1, site);
-        const int pr = take_parity(cs, b);
+        const int pr = got >> 4;
         nI.buf = b;
         nI.par = pr;
         nI.ready = 1;
@@ -813,10 +820,7 @@ __global__ void __launch_bounds__(kThreads, DQ_CTAS_PER_SM) k_fused_passes(const
     PassStep* cache = cache_all + 2 * team;
     if (threadIdx.x == 0) {
         for (int b = 0; b < kBufs; ++b) mbar_init(&cs.full[b], 1);
-        cs.free_mask = (1u << kBufs) - 1u;
-        cs.par_bits = 0u;
-        cs.turn = 0u;
-        cs.alive = (1u << kTeams) - 1u;
+        cs.state = ((1u << kBufs) - 1u) | (((1u << kTeams) - 1u) << 7);
         for (int t = 0; t < kTeams; ++t) cs.mid2[t] = cs.mid3[t] = 0u;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -886,16 +890,17 @@ __global__ void __launch_bounds__(kThreads, DQ_CTAS_PER_SM) k_fused_passes(const
         if (tid == 0) TRACEX(A, I.item, 9, clock64());
         if (!I.ready) {                        // cold path: wait for the dependency, then fetch tile and tables
             if (tid == 0) {
-                int b = try_acquire(cs);       // a free buffer, else our own last one once its store has read it
-                if (b < 0 && my_free >= 0) {
-                    b = my_free;
-                    my_free = -1;
+                int got = claim_buffer(cs, team, false);   // a free buffer, else our own last one once its store has read it
+                if (got < 0 && my_free >= 0) {
                     bulk_wait_read();
+                    got = my_free | (take_parity(cs, my_free) << 4);
+                    my_free = -1;
                 }
-                while (b < 0) {
+                while (got < 0) {
                     __nanosleep(64);
-                    b = try_acquire(cs);
+                    got = claim_buffer(cs, team, false);
                 }
+                const int b = got & 15;
                 int ctr;
                 unsigned need;
                 if (item_dependency(A, skets, I.p, I.g, ctr, need)) {
@@ -904,7 +909,7 @@ __global__ void __launch_bounds__(kThreads, DQ_CTAS_PER_SM) k_fused_passes(const
                         while (ld_acquire(&A.counters[ctr]) < need) __nanosleep(32);
                     }
                 }
-                const int pr = take_parity(cs, b);
+                const int pr = got >> 4;
                 sh.info[cur].buf = b;
                 sh.info[cur].par = pr;
                 TRACEX(A, I.item, 0, clock64());
@@ -966,7 +971,7 @@ __global__ void __launch_bounds__(kThreads, DQ_CTAS_PER_SM) k_fused_passes(const
     cp_async_wait_all();
     team_sync(team);
     if (tid == 0) {
-        atomicAnd(&cs.alive, ~(1u << team));
+        atomicAnd(&cs.state, ~(128u << team));
         bulk_wait_all();
         flush_pending(A, sh, pd);
     }
@@ -1411,6 +1416,8 @@ static int launch_group(dq_ising* p, Plan* pl, const KetDesc* d_kets, int n_kets
     A.group = group;
     A.n_groups = n_groups;
     A.max_pass = max_pass;
+    A.inv_group = group > 1 ? ~0ull / (unsigned long long)group + 1ull : 0ull;
+    A.inv_pass = max_pass > 1 ? ~0ull / (unsigned long long)max_pass + 1ull : 0ull;
     A.tiles_log2 = pl->tiles_log2;
     pl->sub_log2 = std::min(std::max(0, p->item_tiles_log2), pl->tiles_log2);
     A.sub_log2 = pl->sub_log2;
