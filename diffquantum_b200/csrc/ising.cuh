@@ -18,8 +18,9 @@ struct dq_ising {
     int layout_mode = 1;           // 0 reference order (bit n-1-q), 1 automatic (fused engine: no ZZ pair inside a register set)
     dq::DevBuf pairs_dev;          // int2[n_zz] physical bit positions
 
-    int engine = 1;                // 0 generic, 1 fused v2 (32 amplitudes/thread, default), 2 fused v3 (16 amplitudes/thread); 12 <= n <= 20
-    int ket_group = 0;             // states per fused launch; 0 = automatic (auto_ket_group below)
+    int engine = 1;                // 0 generic, 1 fused TMA engine (32 amplitudes/thread, two teams x three tile buffers per SM, default),
+                                   // 2 fused v3 (16 amplitudes/thread, LDGSTS); 12 <= n <= 20
+    int ket_group = 0;             // states co-resident in a fused launch (the work ring a chained launch cycles through); 0 = automatic
     int item_tiles_log2 = 0;       // fused v2: a work item is 2^k consecutive tiles (one atomic / poll / release per item); measured: 0 is best (56.0 / 54.5 / 48.3 / 28.9 samples/s for k = 0..3 at n = 20, finer items pipeline better across pass boundaries)
     int grid_per_sm = 0;           // experiment knob: CTAs per SM in the persistent grid (0 = occupancy)
     int linear = 0;                // 1: estimator by linearity (n_H + 1 suffix trajectories per sample instead of 2 n_H)
