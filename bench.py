@@ -158,6 +158,7 @@ def cpu_bounded_sample(n, per_step, coeff, edges, s, n_terms):
     from oracle import c_port as C, restate as R
     if not C.available():
         raise RuntimeError("oracle/c/liboracle_c.so missing: run __graft_entry__.build()")
+    C.use_host_cores()                      # torchrun exports OMP_NUM_THREADS=1; the CPU arm uses every host core
     prob = R.maxcut_structured(n, edges)
     cp = C.CProblem(prob)
     n_H = len(prob["terms"])

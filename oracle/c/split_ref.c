@@ -33,6 +33,16 @@ int oc_num_threads(void) {
 #endif
 }
 
+/* Launchers such as torchrun export OMP_NUM_THREADS=1 before the process starts; the CPU arm of bench.py asks for the
+ * host's cores explicitly. */
+void oc_set_num_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 /* kind[h] 0: Z_qa Z_qb, 1: X_qa.  u: [n_steps][n_terms].  h0_diag: [2^n].  psi evolves in place. */
 int oc_evolve_split(int n, int n_terms, const int32_t* kind, const int32_t* qa, const int32_t* qb,
                     const double* h0_diag, const double* u, int n_steps, double dt, c128* psi) {

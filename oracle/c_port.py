@@ -26,6 +26,8 @@ def load():
         lib = ctypes.CDLL(LIB_PATH)
         vp = ctypes.c_void_p
         lib.oc_num_threads.restype = ctypes.c_int
+        lib.oc_set_num_threads.restype = None
+        lib.oc_set_num_threads.argtypes = [ctypes.c_int]
         lib.oc_evolve_split.restype = ctypes.c_int
         lib.oc_evolve_split.argtypes = [ctypes.c_int, ctypes.c_int, vp, vp, vp, vp, vp, ctypes.c_int,
                                         ctypes.c_double, vp]
@@ -40,6 +42,13 @@ def load():
 
 def num_threads():
     return load().oc_num_threads()
+
+
+def use_host_cores():
+    """All cores this process may run on, whatever OMP_NUM_THREADS the launcher exported (torchrun sets it to 1)."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    load().oc_set_num_threads(n)
+    return num_threads()
 
 
 def _p(a):
