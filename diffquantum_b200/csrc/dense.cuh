@@ -8,6 +8,7 @@
 // a complex product is four real DMMA (mma.sync.m8n8k4.f64) accumulations.
 #pragma once
 #include <array>
+#include <vector>
 #include "common.cuh"
 
 namespace dq {
@@ -31,9 +32,12 @@ struct State {                         // per context
     Problem global_H;                  // what dq_dense_set_H stored
     Problem scratch_H;                 // what dq_dense_evolve / dq_dense_grad were last called with
     DevBuf A, P0, P1, U, K0, K1, K2, u_dev, meta, phi, out;
+    DevBuf small_H, small_traj;        // resident engine (dim <= 16): [(2 + n_H)][16][16] c128 (H0, H_h, M) and descriptors
     double last_gemm_flops = 0;        // real flops issued to the DMMA GEMM in the last call
-    int last_strategy = 0;             // 0 block-Taylor, 1 per-step propagator, 2 chained propagator
+    int last_strategy = 0;             // 0 block-Taylor, 1 per-step propagator, 2 chained propagator, 3 resident (dim <= 16)
     int last_squarings = 0, last_degree = 0;
+    double last_kernel_ms = 0;         // resident engine: device time of its launches in the last call (CUDA events)
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
 };
 
 struct Gemm {                          // C[z] = alpha * A[z] B[z] (+ Add[z]) (+ I),  z < batch
@@ -53,6 +57,21 @@ int gather_blocks(dq_context* ctx, const double* src, double* dst, const int* d_
                   int scatter);
 int fanout(dq_context* ctx, const Problem& P, int B, const double* d_phi, int ncp_phi, double* d_K, int ncp, double r);
 int energies(dq_context* ctx, const Problem& P, int B, const double* d_K, int ncp, int n_cols, double* d_out);
+
+// Resident engine for dim <= 16 (dense_small.cu): one warp per trajectory, all steps in one launch.
+struct SmallTraj {
+    long long row;                     // first pulse row of the trajectory in the packed table
+    double scale;                      // dt / 2^s
+    double shift;                      // +r / -r: shift gate (I + i shift H_term) / sqrt(1 + r^2) first; 0 = none
+    int steps;
+    int src;                           // index of the start ket
+    int term;                          // control index of the shift gate
+    int out;                           // index of the result (ket or energy)
+};
+bool small_fits(const Problem& P);
+int small_upload(dq_context* ctx, const Problem& P, const double* M);
+int small_run(dq_context* ctx, const Problem& P, int mode, int s, int m, const std::vector<SmallTraj>& traj,
+              const double* d_u, const double* d_src, double* d_dst_kets, double* d_dst_energy, double inv_norm);
 State* state_of(dq_context* ctx);
 void release(dq_context* ctx);
 

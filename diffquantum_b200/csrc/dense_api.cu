@@ -5,6 +5,8 @@
 //   0  block-Taylor : K <- T_m(A/2^s) applied 2^s times to the block          (2^s m GEMMs  Dp x Dp x Ncp)
 //   1  propagator   : P = T_m(A/2^s), s squarings, K <- P K                   (m-1+s GEMMs  Dp^3, one Dp x Dp x Ncp)
 //   2  chained      : as 1 but U <- P U per step and one K <- U K at the end  (more kets than dim)
+//   3  resident     : dim <= 16 only - one warp per ket, whole trajectory in one launch (dense_small.cu); the automatic
+//                     choice there, because 16 x 16 GEMM launches are latency, not arithmetic
 // The polynomial is evaluated in Horner form P <- I + (A/j) P, so every term is one GEMM with a fused
 // "+ I" / "+ K" epilogue.  A is skew-Hermitian, so squaring is norm-preserving and well conditioned.
 #include <algorithm>
@@ -25,8 +27,10 @@ void release(dq_context* ctx) {
     State* S = ctx->dense;
     if (!S) return;
     DevBuf* bufs[] = {&S->global_H.H, &S->global_H.M, &S->scratch_H.H, &S->scratch_H.M, &S->A, &S->P0, &S->P1, &S->U,
-                      &S->K0, &S->K1, &S->K2, &S->u_dev, &S->meta, &S->phi, &S->out};
+                      &S->K0, &S->K1, &S->K2, &S->u_dev, &S->meta, &S->phi, &S->out, &S->small_H, &S->small_traj};
     for (auto* b : bufs) b->release();
+    if (S->ev0) cudaEventDestroy(S->ev0);
+    if (S->ev1) cudaEventDestroy(S->ev1);
     delete S;
     ctx->dense = nullptr;
 }
@@ -102,6 +106,35 @@ inline int log2_ceil_ratio(double x, double theta) {
     return (int)std::ceil(std::log2(x / theta));
 }
 
+// max over all steps of ||dt H(t_k)||_1 (mode 0) or of the largest single term (mode 1): decides the scaling 2^s
+int norm_bound(const Problem& P, int mode, int B, const int* steps, const double* dts, const long long* row_off,
+               const double* h_u, double* out) {
+    const int n_H = P.n_H;
+    double bound = 0.0;
+    for (int b = 0; b < B; ++b)
+        for (int k = 0; k < steps[b]; ++k) {
+            const double* row = h_u + (row_off[b] + k) * n_H;
+            double nb = mode == 0 ? P.norm1[0] : 0.0;
+            for (int h = 0; h < n_H; ++h) {
+                DQ_REQUIRE(std::isfinite(row[h]), "dense path: non-finite pulse value (sample %d step %d term %d)", b, k, h);
+                if (mode == 0) nb += fabs(row[h]) * P.norm1[h + 1];
+                else nb = std::max(nb, fabs(row[h]) * P.norm1[h + 1]);
+            }
+            if (mode != 0) nb = std::max(nb, P.norm1[0]);
+            bound = std::max(bound, fabs(dts[b]) * nb);
+        }
+    *out = bound;
+    return DQ_OK;
+}
+
+// strategy 3 applies: automatic for dim <= 16, or forced; forcing it on a larger problem is an error
+int want_resident(dq_context* ctx, const Problem& P, bool* yes) {
+    const int f = ctx->dense_force_strategy;
+    DQ_REQUIRE(f != 3 || small_fits(P), "dense path: strategy 3 (resident) needs dim <= 16, got %d", P.dim);
+    *yes = small_fits(P) && (f < 0 || f == 3);
+    return DQ_OK;
+}
+
 // Evolve B ket blocks (sample order, planar [B][2][Dp*Ncp], in place in d_K) through their own step lists.
 // steps/dts/row_off are per sample; h_u is the packed host table [total_rows][n_H].
 int evolve_blocks(dq_context* ctx, Problem& P, int mode, int B, int Ncp, const int* steps, const double* dts,
@@ -118,18 +151,7 @@ int evolve_blocks(dq_context* ctx, Problem& P, int mode, int B, int Ncp, const i
 
     // ---- norm bound -> scaling -------------------------------------------------------------------
     double bound = 0.0;
-    for (int b = 0; b < B; ++b)
-        for (int k = 0; k < steps[b]; ++k) {
-            const double* row = h_u + (row_off[b] + k) * n_H;
-            double nb = mode == 0 ? P.norm1[0] : 0.0;
-            for (int h = 0; h < n_H; ++h) {
-                DQ_REQUIRE(std::isfinite(row[h]), "dense path: non-finite pulse value (sample %d step %d term %d)", b, k, h);
-                if (mode == 0) nb += fabs(row[h]) * P.norm1[h + 1];
-                else nb = std::max(nb, fabs(row[h]) * P.norm1[h + 1]);
-            }
-            if (mode != 0) nb = std::max(nb, P.norm1[0]);
-            bound = std::max(bound, fabs(dts[b]) * nb);
-        }
+    DQ_TRY(norm_bound(P, mode, B, steps, dts, row_off, h_u, &bound));
     const int m_blk = 18, m_mat = 9;
     const int s_blk = log2_ceil_ratio(bound, 1.0), s_mat = log2_ceil_ratio(bound, 0.125);
     DQ_REQUIRE(s_blk <= 20, "dense path: ||dt H|| = %g is too large", bound);
@@ -142,7 +164,8 @@ int evolve_blocks(dq_context* ctx, Problem& P, int mode, int B, int Ncp, const i
     const double cost_mat = n_mat * (4e-6 + B * 8.0 * d3 / 12e12) + (4e-6 + B * 8.0 * d2n / 4e12);
     int strategy = cost_blk <= cost_mat ? 0 : 1;
     if (strategy == 1 && mode == 0 && Ncp > Dp) strategy = 2;
-    if (ctx->dense_force_strategy >= 0 && (ctx->dense_force_strategy < 2 || mode == 0)) strategy = ctx->dense_force_strategy;
+    if (ctx->dense_force_strategy >= 0 && ctx->dense_force_strategy <= 2 && (ctx->dense_force_strategy < 2 || mode == 0))
+        strategy = ctx->dense_force_strategy;
     const int s = strategy == 0 ? s_blk : s_mat, m = strategy == 0 ? m_blk : m_mat;
     S->last_strategy = strategy;
     S->last_squarings = s;
@@ -391,6 +414,37 @@ int dq_dense_evolve(dq_context* ctx, int dim, const double* H0, int n_H, const d
     Problem& P = S->scratch_H;
     DQ_TRY(upload_problem(ctx, P, dim, H0, n_H, Hs));
     for (size_t i = 0; i < (size_t)2 * dim * batch; ++i) DQ_REQUIRE(std::isfinite(psi_in[i]), "dq_dense_evolve: non-finite psi entry");
+    bool resident = false;
+    DQ_TRY(want_resident(ctx, P, &resident));
+    if (resident) {
+        static const double no_u0 = 0.0;
+        const long long off0 = 0;
+        double bound = 0.0;
+        DQ_TRY(norm_bound(P, mode, 1, &n_steps, &dt, &off0, u ? u : &no_u0, &bound));
+        const int s = log2_ceil_ratio(bound, 1.0), m = 18;
+        DQ_REQUIRE(s <= 20, "dense path: ||dt H|| = %g is too large", bound);
+        S->last_kernel_ms = 0;
+        DQ_TRY(small_upload(ctx, P, nullptr));
+        std::vector<double> kets((size_t)batch * 32, 0.0);
+        for (int c = 0; c < batch; ++c) memcpy(kets.data() + (size_t)c * 32, psi_in + (size_t)2 * dim * c, sizeof(double) * 2 * dim);
+        DQ_TRY(S->phi.reserve(kets.size() * sizeof(double)));
+        DQ_TRY(S->out.reserve(kets.size() * sizeof(double)));
+        const size_t u_count = (size_t)n_steps * n_H;
+        DQ_TRY(S->u_dev.reserve(std::max<size_t>(1, u_count) * sizeof(double)));
+        if (u_count) DQ_CUDA(cudaMemcpyAsync(S->u_dev.p, u, u_count * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        DQ_CUDA(cudaMemcpyAsync(S->phi.p, kets.data(), kets.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        std::vector<SmallTraj> traj(batch);
+        for (int c = 0; c < batch; ++c) traj[c] = SmallTraj{0, std::ldexp(dt, -s), 0.0, n_steps, c, 0, c};
+        DQ_TRY(small_run(ctx, P, mode, s, m, traj, S->u_dev.as<double>(), S->phi.as<double>(), S->out.as<double>(), nullptr, 1.0));
+        DQ_CUDA(cudaMemcpyAsync(kets.data(), S->out.p, kets.size() * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        DQ_CUDA(cudaStreamSynchronize(ctx->stream));
+        for (int c = 0; c < batch; ++c) memcpy(psi_out + (size_t)2 * dim * c, kets.data() + (size_t)c * 32, sizeof(double) * 2 * dim);
+        S->last_gemm_flops = 0;
+        S->last_strategy = 3;
+        S->last_squarings = s;
+        S->last_degree = m;
+        return DQ_OK;
+    }
     const int Ncp = round8(batch);
     std::vector<double> blk((size_t)2 * P.Dp * Ncp, 0.0);
     for (int c = 0; c < batch; ++c) put_column(blk, P.Dp, Ncp, dim, c, psi_in + (size_t)2 * dim * c);
@@ -429,6 +483,55 @@ int dq_dense_grad(dq_context* ctx, int dim, const double* H0, int n_H, const dou
         suf_off[b + 1] = suf_off[b] + suffix_steps[b];
     }
     DQ_REQUIRE((pre_off[n_samples] == 0 || u_prefix) && (suf_off[n_samples] == 0 || u_suffix), "dq_dense_grad: NULL pulse table");
+    bool resident = false;
+    DQ_TRY(want_resident(ctx, P, &resident));
+    if (resident) {
+        static const double no_u0 = 0.0;
+        const long long n_pre = pre_off[n_samples], n_suf = suf_off[n_samples];
+        double b_pre = 0.0, b_suf = 0.0;
+        DQ_TRY(norm_bound(P, mode, n_samples, prefix_steps, prefix_dt, pre_off.data(), u_prefix ? u_prefix : &no_u0, &b_pre));
+        DQ_TRY(norm_bound(P, mode, n_samples, suffix_steps, suffix_dt, suf_off.data(), u_suffix ? u_suffix : &no_u0, &b_suf));
+        const double bound = std::max(b_pre, b_suf);
+        const int s = log2_ceil_ratio(bound, 1.0), m = 18;
+        DQ_REQUIRE(s <= 20, "dense path: ||dt H|| = %g is too large", bound);
+        S->last_kernel_ms = 0;
+        DQ_TRY(small_upload(ctx, P, M));
+        // pulse rows: prefix table, then suffix table
+        DQ_TRY(S->u_dev.reserve(std::max<size_t>(1, (size_t)(n_pre + n_suf) * n_H) * sizeof(double)));
+        if (n_pre) DQ_CUDA(cudaMemcpyAsync(S->u_dev.p, u_prefix, (size_t)n_pre * n_H * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        if (n_suf) DQ_CUDA(cudaMemcpyAsync(S->u_dev.as<double>() + (size_t)n_pre * n_H, u_suffix, (size_t)n_suf * n_H * sizeof(double),
+                                           cudaMemcpyHostToDevice, ctx->stream));
+        // kets: [0] = psi0, [1 .. n_samples] = phi_b
+        std::vector<double> k0(32, 0.0);
+        memcpy(k0.data(), psi0, sizeof(double) * 2 * dim);
+        DQ_TRY(S->phi.reserve((size_t)(1 + n_samples) * 32 * sizeof(double)));
+        DQ_TRY(S->out.reserve((size_t)n_samples * 2 * n_H * sizeof(double)));
+        DQ_CUDA(cudaMemcpyAsync(S->phi.p, k0.data(), 32 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        // longest trajectories first: a warp is busy for steps x terms, CTAs retire in launch order
+        std::vector<int> order(n_samples);
+        std::iota(order.begin(), order.end(), 0);
+        std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return prefix_steps[a] > prefix_steps[b]; });
+        std::vector<SmallTraj> traj;
+        traj.reserve((size_t)n_samples * 2 * n_H);
+        for (int b : order) traj.push_back(SmallTraj{pre_off[b], std::ldexp(prefix_dt[b], -s), 0.0, prefix_steps[b], 0, 0, b});
+        DQ_TRY(small_run(ctx, P, mode, s, m, traj, S->u_dev.as<double>(), S->phi.as<double>(), S->phi.as<double>() + 32, nullptr, 1.0));
+        std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return suffix_steps[a] > suffix_steps[b]; });
+        traj.clear();
+        for (int b : order)
+            for (int i = 0; i < n_H; ++i)
+                for (int sg = 0; sg < 2; ++sg)
+                    traj.push_back(SmallTraj{n_pre + suf_off[b], std::ldexp(suffix_dt[b], -s), sg == 0 ? r : -r, suffix_steps[b],
+                                             b, i, (b * n_H + i) * 2 + sg});
+        DQ_TRY(small_run(ctx, P, mode, s, m, traj, S->u_dev.as<double>(), S->phi.as<double>() + 32, nullptr, S->out.as<double>(),
+                         1.0 / sqrt(1.0 + r * r)));
+        DQ_CUDA(cudaMemcpyAsync(energies_out, S->out.p, (size_t)n_samples * 2 * n_H * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        DQ_CUDA(cudaStreamSynchronize(ctx->stream));
+        S->last_gemm_flops = 0;
+        S->last_strategy = 3;
+        S->last_squarings = s;
+        S->last_degree = m;
+        return DQ_OK;
+    }
     const int Ncp = round8(2 * n_H), Dp = P.Dp;
     const size_t mat_bytes = 2 * P.plane() * sizeof(double);
     // samples per chunk: three Dp x Dp work matrices and three ket blocks per sample within ~4 GiB
@@ -472,6 +575,7 @@ int dq_dense_last_stat(dq_context* ctx, const char* name, double* value) {
     else if (!strcmp(name, "strategy")) *value = S->last_strategy;
     else if (!strcmp(name, "squarings")) *value = S->last_squarings;
     else if (!strcmp(name, "degree")) *value = S->last_degree;
+    else if (!strcmp(name, "kernel_ms")) *value = S->last_kernel_ms;
     else { dq::set_error("dq_dense_last_stat: unknown name '%s'", name); return DQ_ERR_INVALID; }
     return DQ_OK;
 }
@@ -479,7 +583,7 @@ int dq_dense_last_stat(dq_context* ctx, const char* name, double* value) {
 int dq_dense_set_option(dq_context* ctx, const char* name, int64_t value) {
     DQ_REQUIRE(ctx && name, "NULL argument");
     if (!strcmp(name, "strategy")) {
-        DQ_REQUIRE(value >= -1 && value <= 2, "strategy must be -1 (auto), 0, 1 or 2");
+        DQ_REQUIRE(value >= -1 && value <= 3, "strategy must be -1 (auto), 0, 1, 2 or 3");
         ctx->dense_force_strategy = (int)value;
     } else { dq::set_error("dq_dense_set_option: unknown option '%s'", name); return DQ_ERR_INVALID; }
     return DQ_OK;

@@ -1,0 +1,200 @@
+// Resident engine of the dense path for dim <= 16 (strategy 3): one WARP owns one ket for its whole trajectory.
+//
+// The DMMA GEMM strategies (dense_api.cu) issue ~m 2^s launches per step; at D = 16 (demo_maxcut.py as shipped,
+// H2 VQE: BASELINE configs[0], [1]) every one of them is a 16 x 16 problem and the path is launch-bound.  Here a
+// trajectory  psi <- expm(-i dt (H0 + sum_h u_h(t_k) H_h)) psi, k < steps  (sim_plain.py:135-150, diffqc.cc:190-200)
+// runs start to finish inside one warp: the generator A = -i dt/2^s H(t_k) is assembled in registers (lane = row r,
+// half h: eight entries of row r), the ket lives in shared memory, and exp(A) psi is the same block-Taylor Horner
+// recurrence as strategy 0,  y <- psi + (A/j) y for j = m..1, applied 2^s times.  The estimator
+// (sim_plain.py:186-220) is two launches: the prefix states phi_b, then all 2 n_H shifted kets of every sample
+// with the shift gate (I +/- i r H_i)/sqrt(1+r^2) fused in front and Re <ket|M|ket> fused behind.
+// mode 1 is the per-term product of diffqc.cc:155-164 (one generator per term, list order).
+#include <algorithm>
+#include <cmath>
+#include <numeric>
+#include <vector>
+#include "dense.cuh"
+
+namespace dq {
+namespace dense {
+namespace {
+
+constexpr int kD = 16;          // padded dimension
+constexpr int kWarps = 4;       // trajectories per CTA
+constexpr int kMaxDegree = 32;
+
+__device__ __forceinline__ double2 cfma(const double2 a, const double2 b, double2 acc) {
+    acc.x = fma(a.x, b.x, acc.x);
+    acc.x = fma(-a.y, b.y, acc.x);
+    acc.y = fma(a.x, b.y, acc.y);
+    acc.y = fma(a.y, b.x, acc.y);
+    return acc;
+}
+
+// sum over this lane's eight columns, then over the two halves of the row: every lane of the pair gets (Mat x)_r
+__device__ __forceinline__ double2 pair_sum(double2 acc) {
+    acc.x += __shfl_xor_sync(0xffffffffu, acc.x, 1);
+    acc.y += __shfl_xor_sync(0xffffffffu, acc.y, 1);
+    return acc;
+}
+
+__device__ __forceinline__ double2 matvec_global(const double2* __restrict__ mat, const double2* x, int r, int h) {
+    double2 acc = make_double2(0.0, 0.0);
+#pragma unroll
+    for (int c = 0; c < 8; ++c) acc = cfma(__ldg(mat + r * kD + 8 * h + c), x[8 * h + c], acc);
+    return pair_sum(acc);
+}
+
+template <bool ENERGY>
+__global__ void __launch_bounds__(32 * kWarps, 4) k_small(const double2* __restrict__ H, const double2* __restrict__ M, int n_H,
+                                                        int mode, int reps, int m, const double* __restrict__ u,
+                                                        const SmallTraj* __restrict__ traj, int n_traj,
+                                                        const double2* __restrict__ src, double2* __restrict__ dst_kets,
+                                                        double* __restrict__ dst_energy, double inv_norm) {
+    __shared__ double2 xs[kWarps][3][kD];
+    __shared__ double inv_j[kMaxDegree + 1];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x <= kMaxDegree) inv_j[threadIdx.x] = threadIdx.x ? 1.0 / (double)threadIdx.x : 0.0;
+    __syncthreads();
+    const int w = blockIdx.x * kWarps + warp;
+    if (w >= n_traj) return;
+    const SmallTraj t = traj[w];
+    const int r = lane >> 1, h = lane & 1;
+    double2* cur = xs[warp][0];
+    double2* o1 = xs[warp][1];
+    double2* o2 = xs[warp][2];
+    if (lane < kD) cur[lane] = src[(size_t)t.src * kD + lane];
+    __syncwarp();
+    if (t.shift != 0.0) {                   // (phi + i shift H_i phi) / sqrt(1 + r^2)     (sim_plain.py:197-199)
+        const double2 hp = matvec_global(H + (size_t)(t.term + 1) * kD * kD, cur, r, h);
+        const double2 c = cur[r];
+        if (h == 0) o1[r] = make_double2((c.x - t.shift * hp.y) * inv_norm, (c.y + t.shift * hp.x) * inv_norm);
+        __syncwarp();
+        double2* tmp = cur; cur = o1; o1 = tmp;
+    }
+    const int t_lo = mode == 0 ? -1 : 0, t_hi = mode == 0 ? -1 : n_H;
+    for (int k = 0; k < t.steps; ++k) {
+        const double* __restrict__ ur = u + (t.row + k) * n_H;
+        for (int term = t_lo; term <= t_hi; ++term) {
+            // generator entries of this lane: A[r][8h .. 8h+7] = -i scale (H0 + sum_h u_h H_h)  or one term of it
+            double2 a[8];
+            const double2* __restrict__ hrow = H + r * kD + 8 * h;
+            if (term < 0) {
+#pragma unroll
+                for (int c = 0; c < 8; ++c) a[c] = __ldg(hrow + c);
+                for (int q = 0; q < n_H; ++q) {
+                    const double cq = __ldg(ur + q);
+                    const double2* __restrict__ hq = hrow + (size_t)(q + 1) * kD * kD;
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) {
+                        const double2 e = __ldg(hq + c);
+                        a[c].x = fma(cq, e.x, a[c].x);
+                        a[c].y = fma(cq, e.y, a[c].y);
+                    }
+                }
+            } else {
+                const double cq = term == 0 ? 1.0 : __ldg(ur + term - 1);
+                const double2* __restrict__ hq = hrow + (size_t)term * kD * kD;
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    const double2 e = __ldg(hq + c);
+                    a[c] = make_double2(cq * e.x, cq * e.y);
+                }
+            }
+#pragma unroll
+            for (int c = 0; c < 8; ++c) a[c] = make_double2(t.scale * a[c].y, -t.scale * a[c].x);   // -i (x + i y) = y - i x
+            for (int rep = 0; rep < reps; ++rep) {
+                const double2 c0 = cur[r];
+                const double2* in = cur;
+                for (int j = m; j >= 1; --j) {
+                    double2 acc = make_double2(0.0, 0.0);
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) acc = cfma(a[c], in[8 * h + c], acc);
+                    acc = pair_sum(acc);
+                    const double f = inv_j[j];
+                    if (h == 0) o1[r] = make_double2(fma(f, acc.x, c0.x), fma(f, acc.y, c0.y));
+                    __syncwarp();
+                    in = o1;
+                    double2* tmp = o1; o1 = o2; o2 = tmp;
+                }
+                // result sits in `in` (= o2 after the last swap); the old `cur` becomes a work buffer
+                double2* res = o2;
+                o2 = cur;
+                cur = res;
+            }
+        }
+    }
+    if (ENERGY) {                           // Re <ket| M |ket>     (sim_plain.py:205,215)
+        const double2 mk = matvec_global(M, cur, r, h);
+        const double2 c = cur[r];
+        double e = h == 0 ? fma(c.x, mk.x, c.y * mk.y) : 0.0;
+        for (int o = 16; o > 0; o >>= 1) e += __shfl_xor_sync(0xffffffffu, e, o);
+        if (lane == 0) dst_energy[t.out] = e;
+    } else {
+        if (lane < kD) dst_kets[(size_t)t.out * kD + lane] = cur[lane];
+    }
+}
+
+// interleaved c128 [dim][dim] -> zero-padded [16][16]
+void pad16(const double* src, int dim, double* dst) {
+    std::fill(dst, dst + 2 * kD * kD, 0.0);
+    for (int i = 0; i < dim; ++i)
+        for (int j = 0; j < dim; ++j) {
+            dst[2 * (i * kD + j)] = src[2 * ((size_t)i * dim + j)];
+            dst[2 * (i * kD + j) + 1] = src[2 * ((size_t)i * dim + j) + 1];
+        }
+}
+
+}  // namespace
+
+bool small_fits(const Problem& P) { return P.dim >= 1 && P.dim <= kD; }
+
+int small_upload(dq_context* ctx, const Problem& P, const double* M) {
+    State* S = state_of(ctx);
+    const size_t per = (size_t)2 * kD * kD, src_per = (size_t)P.dim * P.dim * 2;
+    std::vector<double> host((size_t)(2 + P.n_H) * per);
+    for (int h = 0; h <= P.n_H; ++h) pad16(P.host_copy.data() + src_per * h, P.dim, host.data() + per * h);
+    if (M) pad16(M, P.dim, host.data() + per * (1 + P.n_H));
+    else std::fill(host.begin() + per * (1 + P.n_H), host.end(), 0.0);
+    DQ_TRY(S->small_H.reserve(host.size() * sizeof(double)));
+    DQ_CUDA(cudaMemcpyAsync(S->small_H.p, host.data(), host.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    DQ_CUDA(cudaStreamSynchronize(ctx->stream));        // `host` goes out of scope
+    return DQ_OK;
+}
+
+// d_src / d_dst_kets: [..][16] c128; d_u: packed pulse rows [..][n_H]; traj: host descriptors (copied here)
+int small_run(dq_context* ctx, const Problem& P, int mode, int s, int m, const std::vector<SmallTraj>& traj,
+              const double* d_u, const double* d_src, double* d_dst_kets, double* d_dst_energy, double inv_norm) {
+    State* S = state_of(ctx);
+    DQ_REQUIRE(m >= 1 && m <= kMaxDegree && s >= 0 && s <= 20, "dense resident engine: degree %d / squarings %d out of range", m, s);
+    if (traj.empty()) return DQ_OK;
+    DQ_TRY(S->small_traj.reserve(traj.size() * sizeof(SmallTraj)));
+    DQ_CUDA(cudaMemcpyAsync(S->small_traj.p, traj.data(), traj.size() * sizeof(SmallTraj), cudaMemcpyHostToDevice, ctx->stream));
+    const double2* H = S->small_H.as<double2>();
+    const double2* M = H + (size_t)(1 + P.n_H) * kD * kD;
+    const int n = (int)traj.size();
+    const unsigned grid = (unsigned)((n + kWarps - 1) / kWarps);
+    if (!S->ev0) {
+        DQ_CUDA(cudaEventCreate(&S->ev0));
+        DQ_CUDA(cudaEventCreate(&S->ev1));
+    }
+    DQ_CUDA(cudaEventRecord(S->ev0, ctx->stream));
+    if (d_dst_energy)
+        k_small<true><<<grid, 32 * kWarps, 0, ctx->stream>>>(H, M, P.n_H, mode, 1 << s, m, d_u, S->small_traj.as<SmallTraj>(), n,
+                                                             reinterpret_cast<const double2*>(d_src), nullptr, d_dst_energy, inv_norm);
+    else
+        k_small<false><<<grid, 32 * kWarps, 0, ctx->stream>>>(H, M, P.n_H, mode, 1 << s, m, d_u, S->small_traj.as<SmallTraj>(), n,
+                                                              reinterpret_cast<const double2*>(d_src),
+                                                              reinterpret_cast<double2*>(d_dst_kets), nullptr, inv_norm);
+    ctx->launches++;
+    DQ_CUDA(cudaGetLastError());
+    DQ_CUDA(cudaEventRecord(S->ev1, ctx->stream));
+    DQ_CUDA(cudaStreamSynchronize(ctx->stream));        // the descriptor buffer is reused by the next call
+    float ms = 0.f;
+    DQ_CUDA(cudaEventElapsedTime(&ms, S->ev0, S->ev1));
+    S->last_kernel_ms += ms;
+    return DQ_OK;
+}
+
+}  // namespace dense
+}  // namespace dq

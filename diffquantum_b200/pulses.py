@@ -55,6 +55,26 @@ def basis_table(basis, n_basis, ts, T):
     raise ValueError("unsupported basis %r (reference hot path ships BSpline and Legendre)" % (basis,))
 
 
+def step_grids(T0s, Ts, per_step):
+    """step_grid for many (T0, T) pairs at once: n[b], dt[b] and the accumulated times of all pairs packed in pair
+    order (sum(n) values).  Row-wise np.add.accumulate is the same sequential `t += dt` fold as step_grid, so the
+    packed times are bit-identical to per-pair calls."""
+    T0s, Ts = np.broadcast_arrays(np.asarray(T0s, dtype=np.float64), np.asarray(Ts, dtype=np.float64))
+    T0s, Ts = T0s.reshape(-1), Ts.reshape(-1)
+    n = (per_step * ((Ts - T0s) + 1)).astype(np.int64)              # int() truncation (sim_plain.py:123)
+    n = np.maximum(n, 0)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        dt = np.where(n > 0, (Ts - T0s) / np.maximum(n, 1), 0.0)
+    width = int(n.max()) if n.size else 0
+    if width == 0:
+        return n.astype(np.int32), dt, np.zeros(0)
+    grid = np.repeat(dt[:, None], width, axis=1)
+    grid[:, 0] = T0s
+    ts = np.add.accumulate(grid, axis=1)
+    keep = np.arange(width)[None, :] < n[:, None]
+    return n.astype(np.int32), dt, ts[keep]
+
+
 def _sigmoid(a):
     return 1 / (1 + np.exp(-a))
 
@@ -78,6 +98,18 @@ def dudc_table(coeff, omegas, T, s, basis='BSpline'):
         a = a + coeff[:, j] * phi[j]
     sg = _sigmoid(a)
     return (np.asarray(omegas, dtype=np.float64) * 2.0 * sg * (1.0 - sg))[:, None] * phi[None, :]
+
+
+def dudc_tables(coeff, omegas, T, s_list, basis='BSpline'):
+    """dudc_table for many sample times: [len(s_list), n_H, n_basis], bit-identical to per-sample calls."""
+    coeff = np.asarray(coeff, dtype=np.float64)
+    s_list = np.asarray(s_list, dtype=np.float64).reshape(-1)
+    phi = basis_table(basis, coeff.shape[1], s_list, T)             # [B, n_basis]
+    a = np.zeros((s_list.size, coeff.shape[0]))
+    for j in range(coeff.shape[1]):
+        a = a + coeff[None, :, j] * phi[:, j:j + 1]
+    sg = _sigmoid(a)
+    return (np.asarray(omegas, dtype=np.float64)[None, :] * 2.0 * sg * (1.0 - sg))[:, :, None] * phi[:, None, :]
 
 
 # ---- native twin (diffqc.cc) -------------------------------------------------------------------

@@ -88,9 +88,10 @@ int dq_dense_grad(dq_context* ctx, int dim, const double* H0, int n_H, const dou
                   int mode, double* energies_out);
 
 /* Counters of the last dense call: "gemm_flops" (real flops issued to the DMMA GEMM), "strategy"
- * (0 block-Taylor, 1 per-step propagator, 2 chained propagator), "squarings", "degree". */
+ * (0 block-Taylor, 1 per-step propagator, 2 chained propagator, 3 resident warp-per-trajectory engine, dim <= 16),
+ * "squarings", "degree", "kernel_ms" (strategy 3: device time of its launches, CUDA events). */
 int dq_dense_last_stat(dq_context* ctx, const char* name, double* value);
-/* "strategy": -1 automatic (flop count), or force 0/1/2 (parity tests cover all three). */
+/* "strategy": -1 automatic (resident engine for dim <= 16, else by flop count), or force 0/1/2/3 (parity tests cover all). */
 int dq_dense_set_option(dq_context* ctx, const char* name, int64_t value);
 
 /* ---- structured path: H(t) = c0 + sum_e (w_e + u_e(t)) Z_a Z_b + sum_q u_q(t) X_q ------------

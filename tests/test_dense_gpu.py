@@ -27,7 +27,7 @@ def sim_from(g, **kw):
 
 
 @pytest.mark.parametrize("name", DENSE_REF)
-@pytest.mark.parametrize("strategy", [-1, 0, 1, 2])
+@pytest.mark.parametrize("strategy", [-1, 0, 1, 2, 3])
 def test_exact_evolution_matches_reference_fixture(golden, name, strategy):
     g = golden(name)
     sim = sim_from(g)
@@ -45,7 +45,7 @@ def test_exact_evolution_matches_reference_fixture(golden, name, strategy):
 
 
 @pytest.mark.parametrize("name", DENSE_REF)
-@pytest.mark.parametrize("strategy", [-1, 0, 2])
+@pytest.mark.parametrize("strategy", [-1, 0, 2, 3])
 def test_gradient_samples_match_reference_fixture(golden, name, strategy):
     g = golden(name)
     sim = sim_from(g)
@@ -117,6 +117,69 @@ def test_random_hermitian_any_dimension(dim, n_H, steps):
         for b in range(3):
             assert rel(out[b], f(H0, Hs, u, 0.21, psi[b])) < TOL
         assert np.abs(np.linalg.norm(out, axis=1) - 1).max() < 1e-12
+
+
+@pytest.mark.parametrize("dim,n_H", [(2, 1), (4, 3), (7, 2), (16, 8)])
+def test_resident_engine_is_the_automatic_choice_up_to_dim_16(dim, n_H):
+    """dense_small.cu (one warp per trajectory): automatic for dim <= 16, same numbers as the GEMM strategies and the
+    oracle in both step semantics; ragged batches (per-sample step counts) through the gradient entry point."""
+    rng = np.random.RandomState(100 + dim)
+
+    def herm():
+        a = rng.normal(size=(dim, dim)) + 1j * rng.normal(size=(dim, dim))
+        return (a + a.conj().T) / 2
+    H0, Hs, M = herm(), [herm() for _ in range(n_H)], herm()
+    u = rng.uniform(-2, 2, size=(7, n_H))
+    psi = rng.normal(size=(5, dim)) + 1j * rng.normal(size=(5, dim))
+    psi /= np.linalg.norm(psi, axis=1, keepdims=True)
+    ctx = dq.Context.get(0)
+    lib = dq._lib.load()
+
+    def force(v):
+        dq._lib.check(lib.dq_dense_set_option(ctx.handle, b"strategy", v))
+    try:
+        for mode, f in (("exact", R.evolve_exact_dense), ("split", R.evolve_split_dense)):
+            force(-1)
+            out = dq.dense_evolve(ctx, H0, Hs, u, 0.17, psi, mode)
+            import ctypes
+            v = ctypes.c_double()
+            dq._lib.check(lib.dq_dense_last_stat(ctx.handle, b"strategy", ctypes.byref(v)))
+            assert v.value == 3
+            force(0)
+            out0 = dq.dense_evolve(ctx, H0, Hs, u, 0.17, psi, mode)
+            assert rel(out, out0) < 1e-13
+            for b in range(5):
+                assert rel(out[b], f(H0, Hs, u, 0.17, psi[b])) < TOL
+    finally:
+        force(-1)
+    omegas = np.full(n_H, np.pi)
+    sim = dq.DenseSimulator(H0, Hs, omegas, 2.0, M=M, psi0=psi[0], per_step=5, basis="BSpline")
+    coeff = rng.normal(size=(n_H, 6))
+    s = rng.uniform(size=9) * 2.0
+    try:
+        g3, e3 = sim.grad_samples(coeff, s, return_energies=True)
+        assert sim.stat("strategy") == 3
+        sim.set_option("strategy", 0)
+        g0, e0 = sim.grad_samples(coeff, s, return_energies=True)
+        assert rel(e3, e0) < 1e-12 and rel(g3, g0) < 1e-11
+    finally:
+        sim.set_option("strategy", -1)
+
+
+def test_resident_engine_rejects_larger_problems():
+    rng = np.random.RandomState(3)
+    dim = 17
+    a = rng.normal(size=(dim, dim))
+    H0 = (a + a.T) / 2
+    psi = np.zeros(dim, dtype=complex); psi[0] = 1
+    ctx = dq.Context.get(0)
+    lib = dq._lib.load()
+    dq._lib.check(lib.dq_dense_set_option(ctx.handle, b"strategy", 3))
+    try:
+        with pytest.raises(Exception):
+            dq.dense_evolve(ctx, H0, np.zeros((0, dim, dim)), np.zeros((2, 0)), 0.1, psi, "exact")
+    finally:
+        dq._lib.check(lib.dq_dense_set_option(ctx.handle, b"strategy", -1))
 
 
 def test_large_norm_needs_squaring_and_dim_1024_single_step():
@@ -196,8 +259,14 @@ def test_demo_maxcut_training_follows_the_reference_run(golden):
     assert np.abs(losses - g["losses_energy"]).max() < 1e-8          # 202 Adam steps amplify 1e-14 differences
     assert rel(coeff, g["final_coeff"]) < 1e-8
     state, prob = tr.find_state()
-    assert state == int(g["cut_state"]) and bin(state)[2:] == str(g["stdout_tail"]).split()[-1]
     np.testing.assert_allclose(prob, g["prob"], atol=1e-8)
+    # The printed cut is an argmax over a Z2-degenerate pair: |0101> and |1010> are the same cut and their probabilities
+    # are equal in exact arithmetic (the reference's own run separates them by 5.6e-17, one ulp).  Either member is the
+    # reference's answer; which one wins is not a property any implementation can pin.
+    ref_state = int(g["cut_state"])
+    assert bin(ref_state)[2:] == str(g["stdout_tail"]).split()[-1]
+    assert state in (ref_state, ref_state ^ 0b1111)
+    assert abs(prob[state] - g["prob"][ref_state]) < 1e-12
 
 
 def test_structured_training_reaches_a_maximum_cut():

@@ -36,11 +36,12 @@ np.random.seed(7)
 s_list = np.random.uniform(size=K) * sim.T
 sim.shifted_energies(g["coeff"], s_list[:64])                      # warm-up
 res = {}
-for strat in (-1, 0, 1, 2):
+for strat in (-1, 0, 1, 2, 3):
     sim.set_option("strategy", strat)
     t = time.perf_counter(); en = sim.shifted_energies(g["coeff"], s_list); dt = time.perf_counter() - t
     res["strategy_%d" % strat] = {"seconds": dt, "samples_per_s": K / dt, "chosen": sim.stat("strategy"),
-                                  "gemm_TFLOPs": sim.stat("gemm_flops") / dt / 1e12}
+                                  "gemm_TFLOPs": sim.stat("gemm_flops") / dt / 1e12,
+                                  "resident_kernel_ms": sim.stat("kernel_ms") if sim.stat("strategy") == 3 else None}
 sim.set_option("strategy", -1)
 t = time.perf_counter()
 for s in s_list[:8]:
