@@ -62,15 +62,16 @@ int energies(dq_context* ctx, const Problem& P, int B, const double* d_K, int nc
 struct SmallTraj {
     long long row;                     // first pulse row of the trajectory in the packed table
     double scale;                      // dt / 2^s
-    double shift;                      // +r / -r: shift gate (I + i shift H_term) / sqrt(1 + r^2) first; 0 = none
+    double shift;                      // shift gate (I + i shift H_term) / sqrt(1 + r^2) first; 0 = none.  With NK kets per
+                                       // trajectory ket g uses control term + g/2 and the sign pattern +shift, -shift, ...
     int steps;
     int src;                           // index of the start ket
-    int term;                          // control index of the shift gate
-    int out;                           // index of the result (ket or energy)
+    int term;                          // control index of the (first) shift gate
+    int out;                           // index of the (first) result (ket or energy); ket g writes out + g
 };
 bool small_fits(const Problem& P);
 int small_upload(dq_context* ctx, const Problem& P, const double* M);
-int small_run(dq_context* ctx, const Problem& P, int mode, int s, int m, const std::vector<SmallTraj>& traj,
+int small_run(dq_context* ctx, const Problem& P, int mode, int s, int m, int kets_per_traj, const std::vector<SmallTraj>& traj,
               const double* d_u, const double* d_src, double* d_dst_kets, double* d_dst_energy, double inv_norm);
 State* state_of(dq_context* ctx);
 void release(dq_context* ctx);

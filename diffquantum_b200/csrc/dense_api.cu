@@ -435,7 +435,7 @@ int dq_dense_evolve(dq_context* ctx, int dim, const double* H0, int n_H, const d
         DQ_CUDA(cudaMemcpyAsync(S->phi.p, kets.data(), kets.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
         std::vector<SmallTraj> traj(batch);
         for (int c = 0; c < batch; ++c) traj[c] = SmallTraj{0, std::ldexp(dt, -s), 0.0, n_steps, c, 0, c};
-        DQ_TRY(small_run(ctx, P, mode, s, m, traj, S->u_dev.as<double>(), S->phi.as<double>(), S->out.as<double>(), nullptr, 1.0));
+        DQ_TRY(small_run(ctx, P, mode, s, m, 1, traj, S->u_dev.as<double>(), S->phi.as<double>(), S->out.as<double>(), nullptr, 1.0));
         DQ_CUDA(cudaMemcpyAsync(kets.data(), S->out.p, kets.size() * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
         DQ_CUDA(cudaStreamSynchronize(ctx->stream));
         for (int c = 0; c < batch; ++c) memcpy(psi_out + (size_t)2 * dim * c, kets.data() + (size_t)c * 32, sizeof(double) * 2 * dim);
@@ -514,15 +514,15 @@ int dq_dense_grad(dq_context* ctx, int dim, const double* H0, int n_H, const dou
         std::vector<SmallTraj> traj;
         traj.reserve((size_t)n_samples * 2 * n_H);
         for (int b : order) traj.push_back(SmallTraj{pre_off[b], std::ldexp(prefix_dt[b], -s), 0.0, prefix_steps[b], 0, 0, b});
-        DQ_TRY(small_run(ctx, P, mode, s, m, traj, S->u_dev.as<double>(), S->phi.as<double>(), S->phi.as<double>() + 32, nullptr, 1.0));
+        DQ_TRY(small_run(ctx, P, mode, s, m, 1, traj, S->u_dev.as<double>(), S->phi.as<double>(), S->phi.as<double>() + 32, nullptr, 1.0));
         std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return suffix_steps[a] > suffix_steps[b]; });
         traj.clear();
+        // the +/- kets of a control (and of two neighbouring controls when n_H is even) share their generator: one warp each
+        const int nk = (n_H % 2 == 0) ? 4 : 2;
         for (int b : order)
-            for (int i = 0; i < n_H; ++i)
-                for (int sg = 0; sg < 2; ++sg)
-                    traj.push_back(SmallTraj{n_pre + suf_off[b], std::ldexp(suffix_dt[b], -s), sg == 0 ? r : -r, suffix_steps[b],
-                                             b, i, (b * n_H + i) * 2 + sg});
-        DQ_TRY(small_run(ctx, P, mode, s, m, traj, S->u_dev.as<double>(), S->phi.as<double>() + 32, nullptr, S->out.as<double>(),
+            for (int i = 0; i < n_H; i += nk / 2)
+                traj.push_back(SmallTraj{n_pre + suf_off[b], std::ldexp(suffix_dt[b], -s), r, suffix_steps[b], b, i, (b * n_H + i) * 2});
+        DQ_TRY(small_run(ctx, P, mode, s, m, nk, traj, S->u_dev.as<double>(), S->phi.as<double>() + 32, nullptr, S->out.as<double>(),
                          1.0 / sqrt(1.0 + r * r)));
         DQ_CUDA(cudaMemcpyAsync(energies_out, S->out.p, (size_t)n_samples * 2 * n_H * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
         DQ_CUDA(cudaStreamSynchronize(ctx->stream));

@@ -38,20 +38,29 @@ __device__ __forceinline__ double2 pair_sum(double2 acc) {
     return acc;
 }
 
+// Shared-memory slot of ket entry i: the upper half is shifted by one entry, so that the two halves of a row pair
+// (lanes h = 0 / 1 read entries c and 8 + c in the same LDS.128) fall into different banks.
+__device__ __forceinline__ int xslot(int i) { return i + (i >> 3); }
+constexpr int kXs = kD + 1;
+
 __device__ __forceinline__ double2 matvec_global(const double2* __restrict__ mat, const double2* x, int r, int h) {
-    double2 acc = make_double2(0.0, 0.0);
+    double2 acc0 = make_double2(0.0, 0.0), acc1 = make_double2(0.0, 0.0);
 #pragma unroll
-    for (int c = 0; c < 8; ++c) acc = cfma(__ldg(mat + r * kD + 8 * h + c), x[8 * h + c], acc);
-    return pair_sum(acc);
+    for (int c = 0; c < 8; c += 2) {
+        acc0 = cfma(__ldg(mat + r * kD + 8 * h + c), x[9 * h + c], acc0);
+        acc1 = cfma(__ldg(mat + r * kD + 8 * h + c + 1), x[9 * h + c + 1], acc1);
+    }
+    return pair_sum(make_double2(acc0.x + acc1.x, acc0.y + acc1.y));
 }
 
-template <bool ENERGY>
-__global__ void __launch_bounds__(32 * kWarps, 4) k_small(const double2* __restrict__ H, const double2* __restrict__ M, int n_H,
-                                                        int mode, int reps, int m, const double* __restrict__ u,
-                                                        const SmallTraj* __restrict__ traj, int n_traj,
-                                                        const double2* __restrict__ src, double2* __restrict__ dst_kets,
-                                                        double* __restrict__ dst_energy, double inv_norm) {
-    __shared__ double2 xs[kWarps][3][kD];
+// NK kets per warp share one trajectory (same pulse rows, same generator): ket g starts from the same source ket with the
+// shift gate of control term + g/2 and sign (+, -, +, -); its result goes to out + g.  NK = 1: a plain trajectory.
+template <bool ENERGY, int NK>
+__global__ void __launch_bounds__(32 * kWarps, NK == 1 ? 6 : 4)
+k_small(const double2* __restrict__ H, const double2* __restrict__ M, int n_H, int mode, int reps, int m,
+        const double* __restrict__ u, const SmallTraj* __restrict__ traj, int n_traj, const double2* __restrict__ src,
+        double2* __restrict__ dst_kets, double* __restrict__ dst_energy, double inv_norm) {
+    __shared__ double2 xs[kWarps][3][NK * kXs];
     __shared__ double inv_j[kMaxDegree + 1];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x <= kMaxDegree) inv_j[threadIdx.x] = threadIdx.x ? 1.0 / (double)threadIdx.x : 0.0;
@@ -63,12 +72,20 @@ __global__ void __launch_bounds__(32 * kWarps, 4) k_small(const double2* __restr
     double2* cur = xs[warp][0];
     double2* o1 = xs[warp][1];
     double2* o2 = xs[warp][2];
-    if (lane < kD) cur[lane] = src[(size_t)t.src * kD + lane];
+    if (lane < kD) {
+        const double2 v = src[(size_t)t.src * kD + lane];
+#pragma unroll
+        for (int g = 0; g < NK; ++g) cur[g * kXs + xslot(lane)] = v;
+    }
     __syncwarp();
     if (t.shift != 0.0) {                   // (phi + i shift H_i phi) / sqrt(1 + r^2)     (sim_plain.py:197-199)
-        const double2 hp = matvec_global(H + (size_t)(t.term + 1) * kD * kD, cur, r, h);
-        const double2 c = cur[r];
-        if (h == 0) o1[r] = make_double2((c.x - t.shift * hp.y) * inv_norm, (c.y + t.shift * hp.x) * inv_norm);
+#pragma unroll
+        for (int g = 0; g < NK; ++g) {
+            const double sh = (g & 1) ? -t.shift : t.shift;
+            const double2 hp = matvec_global(H + (size_t)(t.term + (g >> 1) + 1) * kD * kD, cur + g * kXs, r, h);
+            const double2 c = cur[g * kXs + xslot(r)];
+            if (h == 0) o1[g * kXs + xslot(r)] = make_double2((c.x - sh * hp.y) * inv_norm, (c.y + sh * hp.x) * inv_norm);
+        }
         __syncwarp();
         double2* tmp = cur; cur = o1; o1 = tmp;
     }
@@ -104,15 +121,29 @@ __global__ void __launch_bounds__(32 * kWarps, 4) k_small(const double2* __restr
 #pragma unroll
             for (int c = 0; c < 8; ++c) a[c] = make_double2(t.scale * a[c].y, -t.scale * a[c].x);   // -i (x + i y) = y - i x
             for (int rep = 0; rep < reps; ++rep) {
-                const double2 c0 = cur[r];
+                double2 c0[NK];
+#pragma unroll
+                for (int g = 0; g < NK; ++g) c0[g] = cur[g * kXs + xslot(r)];
                 const double2* in = cur;
                 for (int j = m; j >= 1; --j) {
-                    double2 acc = make_double2(0.0, 0.0);
+                    // 2 NK independent accumulation chains (NK = 1: the row is split in two): the recurrence is latency-bound
+                    double2 acc[NK], acc1[NK];
 #pragma unroll
-                    for (int c = 0; c < 8; ++c) acc = cfma(a[c], in[8 * h + c], acc);
-                    acc = pair_sum(acc);
+                    for (int g = 0; g < NK; ++g) acc[g] = acc1[g] = make_double2(0.0, 0.0);
+#pragma unroll
+                    for (int c = 0; c < 8; c += 2) {
+#pragma unroll
+                        for (int g = 0; g < NK; ++g) {
+                            acc[g] = cfma(a[c], in[g * kXs + 9 * h + c], acc[g]);
+                            acc1[g] = cfma(a[c + 1], in[g * kXs + 9 * h + c + 1], acc1[g]);
+                        }
+                    }
                     const double f = inv_j[j];
-                    if (h == 0) o1[r] = make_double2(fma(f, acc.x, c0.x), fma(f, acc.y, c0.y));
+#pragma unroll
+                    for (int g = 0; g < NK; ++g) {
+                        const double2 sum = pair_sum(make_double2(acc[g].x + acc1[g].x, acc[g].y + acc1[g].y));
+                        if (h == 0) o1[g * kXs + xslot(r)] = make_double2(fma(f, sum.x, c0[g].x), fma(f, sum.y, c0[g].y));
+                    }
                     __syncwarp();
                     in = o1;
                     double2* tmp = o1; o1 = o2; o2 = tmp;
@@ -124,14 +155,17 @@ __global__ void __launch_bounds__(32 * kWarps, 4) k_small(const double2* __restr
             }
         }
     }
-    if (ENERGY) {                           // Re <ket| M |ket>     (sim_plain.py:205,215)
-        const double2 mk = matvec_global(M, cur, r, h);
-        const double2 c = cur[r];
-        double e = h == 0 ? fma(c.x, mk.x, c.y * mk.y) : 0.0;
-        for (int o = 16; o > 0; o >>= 1) e += __shfl_xor_sync(0xffffffffu, e, o);
-        if (lane == 0) dst_energy[t.out] = e;
-    } else {
-        if (lane < kD) dst_kets[(size_t)t.out * kD + lane] = cur[lane];
+#pragma unroll
+    for (int g = 0; g < NK; ++g) {
+        if (ENERGY) {                       // Re <ket| M |ket>     (sim_plain.py:205,215)
+            const double2 mk = matvec_global(M, cur + g * kXs, r, h);
+            const double2 c = cur[g * kXs + xslot(r)];
+            double e = h == 0 ? fma(c.x, mk.x, c.y * mk.y) : 0.0;
+            for (int o = 16; o > 0; o >>= 1) e += __shfl_xor_sync(0xffffffffu, e, o);
+            if (lane == 0) dst_energy[t.out + g] = e;
+        } else {
+            if (lane < kD) dst_kets[(size_t)(t.out + g) * kD + lane] = cur[g * kXs + xslot(lane)];
+        }
     }
 }
 
@@ -163,15 +197,19 @@ int small_upload(dq_context* ctx, const Problem& P, const double* M) {
 }
 
 // d_src / d_dst_kets: [..][16] c128; d_u: packed pulse rows [..][n_H]; traj: host descriptors (copied here)
-int small_run(dq_context* ctx, const Problem& P, int mode, int s, int m, const std::vector<SmallTraj>& traj,
+int small_run(dq_context* ctx, const Problem& P, int mode, int s, int m, int kets_per_traj, const std::vector<SmallTraj>& traj,
               const double* d_u, const double* d_src, double* d_dst_kets, double* d_dst_energy, double inv_norm) {
     State* S = state_of(ctx);
     DQ_REQUIRE(m >= 1 && m <= kMaxDegree && s >= 0 && s <= 20, "dense resident engine: degree %d / squarings %d out of range", m, s);
+    DQ_REQUIRE(kets_per_traj == 1 || ((kets_per_traj == 2 || kets_per_traj == 4) && d_dst_energy),
+               "dense resident engine: %d kets per trajectory", kets_per_traj);
     if (traj.empty()) return DQ_OK;
     DQ_TRY(S->small_traj.reserve(traj.size() * sizeof(SmallTraj)));
     DQ_CUDA(cudaMemcpyAsync(S->small_traj.p, traj.data(), traj.size() * sizeof(SmallTraj), cudaMemcpyHostToDevice, ctx->stream));
     const double2* H = S->small_H.as<double2>();
     const double2* M = H + (size_t)(1 + P.n_H) * kD * kD;
+    const SmallTraj* d_traj = S->small_traj.as<SmallTraj>();
+    const double2* src = reinterpret_cast<const double2*>(d_src);
     const int n = (int)traj.size();
     const unsigned grid = (unsigned)((n + kWarps - 1) / kWarps);
     if (!S->ev0) {
@@ -179,13 +217,16 @@ int small_run(dq_context* ctx, const Problem& P, int mode, int s, int m, const s
         DQ_CUDA(cudaEventCreate(&S->ev1));
     }
     DQ_CUDA(cudaEventRecord(S->ev0, ctx->stream));
-    if (d_dst_energy)
-        k_small<true><<<grid, 32 * kWarps, 0, ctx->stream>>>(H, M, P.n_H, mode, 1 << s, m, d_u, S->small_traj.as<SmallTraj>(), n,
-                                                             reinterpret_cast<const double2*>(d_src), nullptr, d_dst_energy, inv_norm);
+    const int reps = 1 << s;
+    if (!d_dst_energy)
+        k_small<false, 1><<<grid, 32 * kWarps, 0, ctx->stream>>>(H, M, P.n_H, mode, reps, m, d_u, d_traj, n, src,
+                                                                 reinterpret_cast<double2*>(d_dst_kets), nullptr, inv_norm);
+    else if (kets_per_traj == 1)
+        k_small<true, 1><<<grid, 32 * kWarps, 0, ctx->stream>>>(H, M, P.n_H, mode, reps, m, d_u, d_traj, n, src, nullptr, d_dst_energy, inv_norm);
+    else if (kets_per_traj == 2)
+        k_small<true, 2><<<grid, 32 * kWarps, 0, ctx->stream>>>(H, M, P.n_H, mode, reps, m, d_u, d_traj, n, src, nullptr, d_dst_energy, inv_norm);
     else
-        k_small<false><<<grid, 32 * kWarps, 0, ctx->stream>>>(H, M, P.n_H, mode, 1 << s, m, d_u, S->small_traj.as<SmallTraj>(), n,
-                                                              reinterpret_cast<const double2*>(d_src),
-                                                              reinterpret_cast<double2*>(d_dst_kets), nullptr, inv_norm);
+        k_small<true, 4><<<grid, 32 * kWarps, 0, ctx->stream>>>(H, M, P.n_H, mode, reps, m, d_u, d_traj, n, src, nullptr, d_dst_energy, inv_norm);
     ctx->launches++;
     DQ_CUDA(cudaGetLastError());
     DQ_CUDA(cudaEventRecord(S->ev1, ctx->stream));

@@ -110,10 +110,13 @@ class DenseSimulator(object):
             _lib.ptr(suf_n), _lib.ptr(suf_dt), _lib.ptr(suf_u), MODES[mode or self.mode], _lib.ptr(out)))
         return out
 
-    def grad_samples(self, coeff, s_list, r=0.5, coeff_sign=1.0, return_energies=False, mode=None):
-        """Per-sample gradients of compute_energy_grad_MC (sim_plain.py:156-231) at explicit times."""
+    def grad_samples(self, coeff, s_list, r=0.5, coeff_sign=1.0, return_energies=False, mode=None, is_noisy=False):
+        """Per-sample gradients of compute_energy_grad_MC (sim_plain.py:156-231) at explicit times.  is_noisy: the
+        reference's measurement noise on every shifted energy (pulses.add_measurement_noise)."""
         s_list = np.asarray(s_list, dtype=np.float64).reshape(-1)
         en = self.shifted_energies(coeff, s_list, r, mode)
+        if is_noisy:
+            pulses.add_measurement_noise(en)
         ps = coeff_sign * ((1 + r ** 2) / 2 / r * (en[:, :, 1] - en[:, :, 0]))
         grads = ps[:, :, None] * pulses.dudc_tables(coeff, self.omegas, self.T, s_list, self.basis)
         return (grads, en) if return_energies else grads
@@ -151,11 +154,15 @@ def solver_for(sim, device=0, mode="exact"):
 def estimator_for(sim, device=0, mode="exact"):
     """Batched replacement for SimulatorPlain.compute_energy_grad_MC (sim_plain.py:156-231).
     Same signature and return type (torch.float64 [n_Hs, n_basis]); draws s = np.random.uniform() * T
-    exactly where the reference does (:167) unless `s` is passed."""
+    exactly where the reference does (:167) unless `s` is passed.  `sim.is_noisy` adds the reference's measurement noise
+    (:207-208,217-218) from the same global stream; `sim.sampling_measure` (shot sampling through Pauli_M eigenbases,
+    :101-117) needs the kets on the host and is rejected."""
     ctx = _lib.Context.get(device)
 
     def compute_energy_grad_MC(M, H_, psi0_, coeff=1.0, s=None):
         import torch
+        if getattr(sim, "sampling_measure", False):
+            raise ValueError("sampling_measure=True is not supported by the device estimator (sim_plain.py:101-117)")
         H0, Hs, fs = _split_H(H_)
         if s is None:
             s = np.random.uniform() * sim.T
@@ -176,6 +183,8 @@ def estimator_for(sim, device=0, mode="exact"):
             _lib.ptr(np.array([pn], dtype=np.int32)), _lib.ptr(np.array([pdt])), _lib.ptr(np.ascontiguousarray(pu)),
             _lib.ptr(np.array([sn], dtype=np.int32)), _lib.ptr(np.array([sdt])), _lib.ptr(np.ascontiguousarray(su)),
             MODES[mode], _lib.ptr(en)))
+        if getattr(sim, "is_noisy", False):
+            pulses.add_measurement_noise(en)
         ps = coeff * ((1 + r ** 2) / 2 / r * (en[0, :, 1] - en[0, :, 0]))
         grad = ps[:, None] * pulses.dudc_table(c, sim.omegas, sim.T, s, sim.basis)
         return torch.from_numpy(grad)

@@ -239,11 +239,14 @@ class IsingSimulator(object):
             grads[b] = ps[:, None] * pulses.dudc_table(coeff, p.omegas, p.T, s, self.basis)
         return grads
 
-    def grad_samples(self, coeff, s_list, r=0.5, coeff_sign=1.0, return_energies=False):
+    def grad_samples(self, coeff, s_list, r=0.5, coeff_sign=1.0, return_energies=False, is_noisy=False):
         """Per-sample gradients of compute_energy_grad_MC (sim_plain.py:156-231) for explicit
-        sampled times s_list (the reference draws s = np.random.uniform() * T at :167)."""
+        sampled times s_list (the reference draws s = np.random.uniform() * T at :167).  is_noisy: the reference's
+        measurement noise on every shifted energy (sim_plain.py:207-208,217-218; pulses.add_measurement_noise)."""
         s_list = np.asarray(s_list, dtype=np.float64).reshape(-1)
         en = self.shifted_energies(coeff, s_list, r)
+        if is_noisy:
+            pulses.add_measurement_noise(en)
         g = self.assemble_gradients(coeff, s_list, en, r, coeff_sign)
         return (g, en) if return_energies else g
 

@@ -112,6 +112,17 @@ def dudc_tables(coeff, omegas, T, s_list, basis='BSpline'):
     return (np.asarray(omegas, dtype=np.float64)[None, :] * 2.0 * sg * (1.0 - sg))[:, :, None] * phi[:, None, :]
 
 
+def add_measurement_noise(en):
+    """is_noisy of the reference (sim_plain.py:207-208,217-218): every shifted energy ps gets
+    np.random.normal(scale=|ps|/5) added, drawn from the GLOBAL NumPy stream in the reference's order - per sample, per
+    control, ps_p (column 0) before ps_m (column 1).  en: [B, n_H, 2], modified in place and returned."""
+    for b in range(en.shape[0]):
+        for i in range(en.shape[1]):
+            for k in range(2):
+                en[b, i, k] += np.random.normal(scale=np.abs(en[b, i, k]) / 5)
+    return en
+
+
 # ---- native twin (diffqc.cc) -------------------------------------------------------------------
 
 def _expit_cc(x):

@@ -9,13 +9,14 @@ class EnergyTrainer(object):
     """backend: DenseSimulator or IsingSimulator (needs .evolve energies and .grad_samples).
     n_samples > 1 averages that many stochastic samples per epoch (the reference uses 1)."""
 
-    def __init__(self, backend, n_basis=6, n_epoch=202, lr=2e-2, n_samples=1, ground_energy=None):
+    def __init__(self, backend, n_basis=6, n_epoch=202, lr=2e-2, n_samples=1, ground_energy=None, is_noisy=False):
         self.backend = backend
         self.n_basis = n_basis
         self.n_epoch = n_epoch
         self.lr = lr
         self.n_samples = n_samples
         self.ground_energy = ground_energy
+        self.is_noisy = is_noisy                       # SimulatorPlain(is_noisy=True): sim_plain.py:283-284, 207-208, 217-218
         self.losses_energy = []
         self.final_state = None
         self.spectral_coeff = None
@@ -52,9 +53,11 @@ class EnergyTrainer(object):
         for epoch in range(1, self.n_epoch + 1):
             c = self.spectral_coeff.detach().numpy().copy()
             self.final_state, loss_energy = self._final(c)                  # :276-281
+            if self.is_noisy:
+                loss_energy += np.random.normal(scale=np.abs(loss_energy) / 5)   # :283-284, before the estimator's draws
             optimizer.zero_grad()
             s_list = [np.random.uniform() * T for _ in range(self.n_samples)]   # :167
-            grads = self.backend.grad_samples(c, s_list)
+            grads = self.backend.grad_samples(c, s_list, is_noisy=self.is_noisy)
             self.spectral_coeff.grad = torch.from_numpy(np.asarray(grads).mean(axis=0))
             optimizer.step()                                                # :291-292
             self.losses_energy.append(loss_energy - e0)

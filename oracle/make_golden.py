@@ -101,6 +101,27 @@ def golden_dense_reference(sp, qp, name, H0, Hs, M, psi0, omegas, T, basis, n_ba
     print(name, "energy", energy.real, "|grad0|", np.linalg.norm(grads[0]))
 
 
+def golden_noisy_estimator(sp, qp, name, base, n_samples=3):
+    """REFERENCE: compute_energy_grad_MC with is_noisy=True (sim_plain.py:207-208,217-218) on the inputs of the
+    fixture `base`: every shifted energy gets np.random.normal(scale=|ps|/5) added, drawn from the same global
+    stream right after the sample time."""
+    g = np.load(os.path.join(OUT, base + ".npz"), allow_pickle=False)
+    coeff = g["coeff"]
+    sim = make_sim(sp, int(g["n_basis"]), str(g["basis"]), float(g["T"]), g["omegas"], len(g["Hs"]), coeff, int(g["per_step"]))
+    sim.is_noisy = True
+    H = ref_H(sim, qp, g["H0"], list(g["Hs"]), coeff)
+    grads, s_list = [], []
+    for k in range(n_samples):
+        np.random.seed(2000 + k)
+        state = np.random.get_state()
+        grads.append(sim.compute_energy_grad_MC(qp.Qobj(g["M"]), H, qp.Qobj(g["psi0"])).numpy().copy())
+        np.random.set_state(state)
+        s_list.append(np.random.uniform() * float(g["T"]))
+    np.savez(os.path.join(OUT, name + ".npz"), base=base, s=np.array(s_list), grads=np.array(grads), seed0=2000,
+             source="REFERENCE sim_plain.py:156-231 with is_noisy=True, run unmodified behind oracle/standin")
+    print(name, "|grad0|", np.linalg.norm(grads[0]))
+
+
 def golden_demo_training(name):
     """REFERENCE: the shipped demo, demo_maxcut.py, run end to end with np.random.seed(0)."""
     ns = ref_loader.run_demo_maxcut(seed=0)
@@ -185,6 +206,9 @@ def main():
     os.makedirs(OUT, exist_ok=True)
     sp = ref_loader.load_sim_plain()
     qp = ref_loader.load_qutip_standin()
+    if sys.argv[1:] == ["noisy"]:                       # only the fixture added last; the others stay as committed
+        golden_noisy_estimator(sp, qp, "demo_noisy_ref", "demo_bspline_ref")
+        return
     demo = R.maxcut_structured(4, DEMO_GRAPH)
     H0, Hs, M = R.maxcut_dense(demo)
     golden_dense_reference(sp, qp, "demo_bspline_ref", H0, Hs, M, demo["psi0"], demo["omegas"],
@@ -201,6 +225,7 @@ def main():
     golden_split("split_n12", 12, R.random_regular_edges(12, seed=3), seed=14, per_step=3,
                  n_samples=1)
     golden_diffqc_cc("diffqc_cc_restated")
+    golden_noisy_estimator(sp, qp, "demo_noisy_ref", "demo_bspline_ref")
 
 
 if __name__ == "__main__":

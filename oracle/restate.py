@@ -372,8 +372,10 @@ def grad_mc_structured(prob, coeff, s, per_step, mode='split', basis='BSpline', 
 
 
 def grad_mc_dense(H0, Hs, M, psi0, coeff, omegas, T, s, per_step, mode='exact', basis='BSpline',
-                  coeff_sign=1.0, r=0.5, return_energies=False):
-    """Dense twin of grad_mc_structured: sim_plain.py:156-231 on explicit matrices."""
+                  coeff_sign=1.0, r=0.5, return_energies=False, is_noisy=False):
+    """Dense twin of grad_mc_structured: sim_plain.py:156-231 on explicit matrices.  is_noisy adds the reference's
+    measurement noise (sim_plain.py:207-208,217-218): one np.random.normal(scale=|ps|/5) per shifted energy, drawn from
+    the global stream in the order ps_p, ps_m per control."""
     n_H = len(Hs)
     d = len(psi0)
 
@@ -388,8 +390,12 @@ def grad_mc_dense(H0, Hs, M, psi0, coeff, omegas, T, s, per_step, mode='exact', 
         gate_m = (np.eye(d) - r * 1.j * Hs[i]) / np.sqrt(1. + r ** 2)
         ket_p = run(gate_p @ phi, s, T)
         ps_p = (ket_p.conj() @ M @ ket_p)
+        if is_noisy:
+            ps_p += np.random.normal(scale=np.abs(ps_p.real) / 5)
         ket_m = run(gate_m @ phi, s, T)
         ps_m = (ket_m.conj() @ M @ ket_m)
+        if is_noisy:
+            ps_m += np.random.normal(scale=np.abs(ps_m.real) / 5)
         energies[i] = (ps_p.real, ps_m.real)
         ps = coeff_sign * ((1 + r ** 2) / 2 / r * (ps_m - ps_p)).real
         grad[i, :] = ps * dudc_plain(i, s, coeff, omegas, T, basis)

@@ -238,6 +238,36 @@ def test_solver_hook_and_estimator_dropins(golden):
         assert rel(grad.numpy(), g["grads"][k]) < TOL
 
 
+def test_noisy_estimator_dropin_follows_the_reference_stream(golden):
+    """sim.is_noisy = True: the drop-in draws the reference's measurement noise from the same global stream
+    (sim_plain.py:207-208,217-218); fixture = the reference's own noisy run."""
+    here = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "oracle", "standin")
+    sys.path.insert(0, here)
+    try:
+        import qutip as qp
+    finally:
+        sys.path.remove(here)
+    gn = golden("demo_noisy_ref")
+    g = golden(str(gn["base"]))
+    sim = _FakeSim(g)
+    sim.is_noisy = True
+    H = [qp.Qobj(g["H0"])] + [[qp.Qobj(g["Hs"][i]),
+                               (lambda i: lambda t, args: R.u_plain(i, t, g["coeff"], g["omegas"], sim.T))(i)]
+                              for i in range(sim.n_Hs)]
+    est = dq.estimator_for(sim)
+    for k in range(len(gn["s"])):
+        np.random.seed(int(gn["seed0"]) + k)
+        grad = est(qp.Qobj(g["M"]), H, qp.Qobj(g["psi0"]))
+        assert rel(grad.numpy(), gn["grads"][k]) < TOL
+    ds = sim_from(g)
+    np.random.seed(int(gn["seed0"]))
+    s0 = np.random.uniform() * float(g["T"])
+    assert rel(ds.grad_samples(g["coeff"], [s0], is_noisy=True)[0], gn["grads"][0]) < TOL
+    sim.sampling_measure = True
+    with pytest.raises(ValueError):
+        est(qp.Qobj(g["M"]), H, qp.Qobj(g["psi0"]))
+
+
 def test_dense_errors_are_python_exceptions():
     ctx = dq.Context.get(0)
     H0 = np.eye(4)

@@ -9,6 +9,7 @@ import sys
 import time
 
 import numpy as np
+import torch  # noqa: F401  (first import takes seconds on a fresh box: keep it out of the timed demo loop)
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
