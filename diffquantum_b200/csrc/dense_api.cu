@@ -173,7 +173,7 @@ int evolve_blocks(dq_context* ctx, Problem& P, int mode, int B, int Ncp, const i
 
     // ---- device tables -----------------------------------------------------------------------------
     DQ_TRY(S->u_dev.reserve(std::max<size_t>(1, (size_t)total_rows * n_H) * sizeof(double)));
-    if (total_rows * n_H)
+    if (total_rows > 0 && n_H > 0)
         DQ_CUDA(cudaMemcpyAsync(S->u_dev.p, h_u, (size_t)total_rows * n_H * sizeof(double), cudaMemcpyHostToDevice, st));
     std::vector<long long> rows(B);
     std::vector<double> scale(B);
