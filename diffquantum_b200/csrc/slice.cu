@@ -5,6 +5,9 @@
 // currently sits on a bit below L.  Qubits on the top g bits are made local by an all-to-all that swaps
 // bits [L-g, L) with the rank bits (done by the host through NCCL, diffquantum_b200/distributed.py).
 // Step semantics: the per-term product of diffqc.cc:155-164.
+#include <algorithm>
+#include <string.h>
+#include <utility>
 #include "common.cuh"
 
 namespace {
@@ -40,6 +43,59 @@ __global__ void __launch_bounds__(kThreads) k_slice_phase(double2* __restrict__ 
     }
 }
 
+// Diagonal phase with incremental angles: a thread owns one value of the low S = L - B index bits and walks the top B
+// local bits in Gray-code order, so consecutive amplitudes differ in ONE bit p and
+//     exp(-i a(g ^ 1<<p)) = exp(-i a(g)) * prod_{pairs e containing p} (cos 2w_e + i sigma_e(g) sin 2w_e),   sigma_e = z_a z_b.
+// One full angle evaluation + sincos per 2^B amplitudes instead of one per amplitude (the full form is compute-bound:
+// ~400 instructions per amplitude at 45 pairs); accesses stay coalesced because lanes differ in the low bits.
+constexpr int kGrayBits = 6, kGrayDeg = 16;
+struct GrayArgs {
+    int B, S;
+    int deg[kGrayBits];
+    unsigned char other[kGrayBits][kGrayDeg];
+    double c2[kGrayBits][kGrayDeg], s2[kGrayBits][kGrayDeg];
+};
+
+__global__ void __launch_bounds__(kThreads) k_slice_phase_gray(double2* __restrict__ psi, int L, unsigned long long high,
+                                                               const PhaseArgs* __restrict__ pa, const GrayArgs* __restrict__ ga) {
+    __shared__ double ang[kMaxPairs];
+    __shared__ unsigned char ba[kMaxPairs], bb[kMaxPairs];
+    __shared__ GrayArgs G;
+    const int n_zz = pa->n_zz;
+    for (int e = threadIdx.x; e < n_zz; e += blockDim.x) { ang[e] = pa->ang[e]; ba[e] = pa->a[e]; bb[e] = pa->b[e]; }
+    if (threadIdx.x == 0) G = *ga;
+    __syncthreads();
+    const double c0 = pa->c0;
+    const int B = G.B, S = G.S;
+    const size_t n_low = (size_t)1 << S;
+    const unsigned long long hi = high << L;
+    for (size_t low = blockIdx.x * (size_t)blockDim.x + threadIdx.x; low < n_low; low += (size_t)gridDim.x * blockDim.x) {
+        unsigned long long g = hi | low;
+        double a = c0;
+        for (int e = 0; e < n_zz; ++e) a += (((g >> ba[e]) ^ (g >> bb[e])) & 1ull) ? -ang[e] : ang[e];
+        double sn, cs;
+        sincos(a, &sn, &cs);
+        double2 ph = make_double2(cs, -sn);                                  // exp(-i a)
+        {
+            const double2 v = psi[low];
+            psi[low] = make_double2(v.x * ph.x - v.y * ph.y, v.x * ph.y + v.y * ph.x);
+        }
+        for (int k = 1; k < (1 << B); ++k) {
+            const int j = __ffs(k) - 1, p = S + j;
+            const int d = G.deg[j];
+            for (int q = 0; q < d; ++q) {
+                const bool differ = (((g >> G.other[j][q]) ^ (g >> p)) & 1ull) != 0;
+                const double c2 = G.c2[j][q], s2 = differ ? -G.s2[j][q] : G.s2[j][q];
+                ph = make_double2(ph.x * c2 - ph.y * s2, ph.x * s2 + ph.y * c2);
+            }
+            g ^= 1ull << p;
+            const size_t x = (size_t)(g & ((1ull << L) - 1ull));
+            const double2 v = psi[x];
+            psi[x] = make_double2(v.x * ph.x - v.y * ph.y, v.x * ph.y + v.y * ph.x);
+        }
+    }
+}
+
 __global__ void __launch_bounds__(kThreads) k_slice_rx(double2* __restrict__ psi, int L, int bit, double c, double s) {
     const size_t half = (size_t)1 << (L - 1);
     const size_t low = ((size_t)1 << bit) - 1;
@@ -48,6 +104,94 @@ __global__ void __launch_bounds__(kThreads) k_slice_rx(double2* __restrict__ psi
         const double2 a = psi[x0], b = psi[x1];
         psi[x0] = make_double2(c * a.x + s * b.y, c * a.y - s * b.x);
         psi[x1] = make_double2(c * b.x + s * a.y, c * b.y - s * a.x);
+    }
+}
+
+// ---- fused X-rotation pass ---------------------------------------------------------------------------------------
+// X rotations on different qubits commute, so all rotations of a step whose bits fit one TILE are applied in a single
+// read + write of the slice.  A tile is 2^T amplitudes (T <= 12, 64 KiB of shared memory) spanned by T physical bits
+// pos[0] < pos[1] < ...: the `lo` lowest are bits 0 .. lo-1 (contiguous 16 * 2^lo byte runs in global memory), the others
+// are the rotation targets of this pass.  Inside the tile two bits are rotated per shared-memory round trip (radix 4).
+struct TileArgs {
+    int T, lo;
+    int n_active;
+    unsigned char pos[12];          // physical bit of tile bit i
+    unsigned char active[12];       // tile bits to rotate
+    double c[12], s[12];            // per active entry
+    unsigned long long mask;        // OR of 1 << pos[i]
+};
+
+__device__ __forceinline__ void rot_pair(double2& a, double2& b, double c, double s) {
+    const double2 a0 = a, b0 = b;
+    a = make_double2(fma(s, b0.y, c * a0.x), fma(-s, b0.x, c * a0.y));
+    b = make_double2(fma(s, a0.y, c * b0.x), fma(-s, a0.x, c * b0.y));
+}
+
+// shared-memory slot of tile element e: XOR swizzle of the 16-byte unit inside each 128-byte row, so that the low-bit
+// rounds (threads 32 / 64 / 128 bytes apart) stay bank-conflict free
+__device__ __forceinline__ int tslot(int e) { return e ^ ((e >> 3) & 7); }
+
+template <bool CONTIG>
+__global__ void __launch_bounds__(kThreads) k_slice_rx_tile(double2* __restrict__ psi, int L, const TileArgs* __restrict__ ta) {
+    extern __shared__ __align__(16) double2 tile[];
+    __shared__ TileArgs A;
+    if (threadIdx.x == 0) A = *ta;
+    __syncthreads();
+    const int T = A.T, lo = A.lo, n_el = 1 << T;
+    const unsigned lowmask = (1u << lo) - 1u;
+    const unsigned long long n_tiles = 1ull << (L - T);
+    // physical offset of the non-contiguous tile bits, tabulated once per CTA (at most 2^8 entries: lo >= 4 when T = 12)
+    __shared__ unsigned long long hi_off[256];
+    for (int v = threadIdx.x; v < (1 << (T - lo)); v += kThreads) {
+        unsigned long long off = 0;
+        for (int i = lo; i < T; ++i) off |= (unsigned long long)((v >> (i - lo)) & 1) << A.pos[i];
+        hi_off[v] = off;
+    }
+    __syncthreads();
+    for (unsigned long long t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        // deposit the bits of t into the physical positions the tile does not span
+        unsigned long long base = 0;
+        {
+            unsigned long long rest = t;
+            for (int p = 0; p < L; ++p)
+                if (!((A.mask >> p) & 1ull)) { base |= (rest & 1ull) << p; rest >>= 1; }
+        }
+        for (int e = threadIdx.x; e < n_el; e += kThreads)
+            tile[tslot(e)] = psi[base + (CONTIG ? (unsigned long long)e : ((e & lowmask) | hi_off[e >> lo]))];
+        __syncthreads();
+        int k = 0;
+        for (; k + 1 < A.n_active; k += 2) {                // two bits per round trip
+            const int i0 = min(A.active[k], A.active[k + 1]), i1 = max(A.active[k], A.active[k + 1]);
+            const double c0 = A.active[k] == i0 ? A.c[k] : A.c[k + 1], s0 = A.active[k] == i0 ? A.s[k] : A.s[k + 1];
+            const double c1 = A.active[k] == i0 ? A.c[k + 1] : A.c[k], s1 = A.active[k] == i0 ? A.s[k + 1] : A.s[k];
+            for (int q = threadIdx.x; q < (n_el >> 2); q += kThreads) {
+                int e = ((q >> i0) << (i0 + 1)) | (q & ((1 << i0) - 1));            // zero at bit i0
+                e = ((e >> i1) << (i1 + 1)) | (e & ((1 << i1) - 1));                // zero at bit i1
+                const int s00 = tslot(e), s01 = tslot(e | (1 << i0)), s10 = tslot(e | (1 << i1)), s11 = tslot(e | (1 << i0) | (1 << i1));
+                double2 v00 = tile[s00], v01 = tile[s01], v10 = tile[s10], v11 = tile[s11];
+                rot_pair(v00, v01, c0, s0);
+                rot_pair(v10, v11, c0, s0);
+                rot_pair(v00, v10, c1, s1);
+                rot_pair(v01, v11, c1, s1);
+                tile[s00] = v00; tile[s01] = v01; tile[s10] = v10; tile[s11] = v11;
+            }
+            __syncthreads();
+        }
+        if (k < A.n_active) {
+            const int i0 = A.active[k];
+            const double c0 = A.c[k], s0 = A.s[k];
+            for (int q = threadIdx.x; q < (n_el >> 1); q += kThreads) {
+                const int e = ((q >> i0) << (i0 + 1)) | (q & ((1 << i0) - 1));
+                const int sa = tslot(e), sb = tslot(e | (1 << i0));
+                double2 a = tile[sa], b = tile[sb];
+                rot_pair(a, b, c0, s0);
+                tile[sa] = a; tile[sb] = b;
+            }
+            __syncthreads();
+        }
+        for (int e = threadIdx.x; e < n_el; e += kThreads)
+            psi[base + (CONTIG ? (unsigned long long)e : ((e & lowmask) | hi_off[e >> lo]))] = tile[tslot(e)];
+        __syncthreads();
     }
 }
 
@@ -143,7 +287,31 @@ int dq_slice_phase(dq_context* ctx, void* psi_dev, int L, uint64_t high_bits, in
     DQ_TRY(fill_args(h, n_total, n_zz, pair_bits, angles + 1, angles[0]));
     PhaseArgs* d;
     DQ_TRY(upload_args(ctx, h, &d));
-    k_slice_phase<<<grid_for(ctx, (size_t)1 << L), kThreads, 0, ctx->stream>>>((double2*)psi_dev, L, high_bits, d);
+    // Gray-code walk over the top B local bits when every one of them has a short pair list (any sparse graph)
+    static_assert(sizeof(GrayArgs) <= sizeof(PhaseArgs), "ring slot too small");
+    GrayArgs gh;
+    memset(&gh, 0, sizeof(gh));
+    gh.B = std::min(kGrayBits, L);
+    gh.S = L - gh.B;
+    bool gray_ok = L >= 10;                                // small slices: the plain kernel is a single wave anyway
+    for (int j = 0; j < gh.B && gray_ok; ++j)
+        for (int e = 0; e < n_zz && gray_ok; ++e) {
+            const int p = gh.S + j;
+            if (h.a[e] != p && h.b[e] != p) continue;
+            if (gh.deg[j] == kGrayDeg) { gray_ok = false; break; }
+            gh.other[j][gh.deg[j]] = h.a[e] == p ? h.b[e] : h.a[e];
+            gh.c2[j][gh.deg[j]] = cos(2.0 * h.ang[e]);
+            gh.s2[j][gh.deg[j]] = sin(2.0 * h.ang[e]);
+            ++gh.deg[j];
+        }
+    if (gray_ok) {
+        GrayArgs* dg = reinterpret_cast<GrayArgs*>(reinterpret_cast<PhaseArgs*>(ctx->slice_ring) + (ctx->slice_cursor++ & 63));
+        if ((ctx->slice_cursor & 63) == 0) DQ_CUDA(cudaStreamSynchronize(ctx->stream));
+        DQ_CUDA(cudaMemcpyAsync(dg, &gh, sizeof(GrayArgs), cudaMemcpyHostToDevice, ctx->stream));
+        k_slice_phase_gray<<<grid_for(ctx, (size_t)1 << gh.S), kThreads, 0, ctx->stream>>>((double2*)psi_dev, L, high_bits, d, dg);
+    } else {
+        k_slice_phase<<<grid_for(ctx, (size_t)1 << L), kThreads, 0, ctx->stream>>>((double2*)psi_dev, L, high_bits, d);
+    }
     ctx->launches++;
     DQ_CUDA(cudaGetLastError());
     return DQ_OK;
@@ -157,6 +325,81 @@ int dq_slice_rx(dq_context* ctx, void* psi_dev, int L, int bit, double theta) {
     k_slice_rx<<<grid_for(ctx, (size_t)1 << (L - 1)), kThreads, 0, ctx->stream>>>((double2*)psi_dev, L, bit, cos(theta), sin(theta));
     ctx->launches++;
     DQ_CUDA(cudaGetLastError());
+    return DQ_OK;
+}
+
+int dq_slice_rx_many(dq_context* ctx, void* psi_dev, int L, int count, const int32_t* bits, const double* thetas) {
+    DQ_REQUIRE(ctx && psi_dev && (count == 0 || (bits && thetas)), "NULL argument");
+    DQ_REQUIRE(L >= 1 && L <= 33 && count >= 0 && count <= L, "dq_slice_rx_many: L=%d count=%d", L, count);
+    DQ_TRY(ctx->set_device());
+    std::vector<std::pair<int, double>> tg(count);
+    unsigned long long seen = 0;
+    for (int i = 0; i < count; ++i) {
+        DQ_REQUIRE(bits[i] >= 0 && bits[i] < L, "dq_slice_rx_many: bit %d is not local (L=%d)", bits[i], L);
+        DQ_REQUIRE(!((seen >> bits[i]) & 1ull), "dq_slice_rx_many: bit %d listed twice", bits[i]);
+        DQ_REQUIRE(isfinite(thetas[i]), "dq_slice_rx_many: non-finite angle");
+        seen |= 1ull << bits[i];
+        tg[i] = {bits[i], thetas[i]};
+    }
+    std::sort(tg.begin(), tg.end());
+    const int Tmax = std::min(12, L);
+    static bool attr_set = false;
+    if (!attr_set) {
+        DQ_CUDA(cudaFuncSetAttribute(k_slice_rx_tile<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double2) << 12)));
+        DQ_CUDA(cudaFuncSetAttribute(k_slice_rx_tile<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double2) << 12)));
+        attr_set = true;
+    }
+    size_t next = 0;
+    while (next < tg.size()) {
+        TileArgs h;
+        memset(&h, 0, sizeof(h));
+        if (tg[next].first < Tmax) {                        // pass over the contiguous tile bits [0, Tmax)
+            h.T = Tmax;
+            h.lo = Tmax;
+            for (int i = 0; i < Tmax; ++i) h.pos[i] = (unsigned char)i;
+            while (next < tg.size() && tg[next].first < Tmax) {
+                h.active[h.n_active] = (unsigned char)tg[next].first;
+                h.c[h.n_active] = cos(tg[next].second);
+                h.s[h.n_active] = sin(tg[next].second);
+                ++h.n_active;
+                ++next;
+            }
+        } else {
+            // High targets: the tile is always 2^Tmax amplitudes - `lo` contiguous low bits (16 * 2^lo byte runs in global
+            // memory) + the targets of this pass; the remaining targets are split evenly over the fewest passes that
+            // leave lo >= 4, so a pass with few targets gets long contiguous runs instead of a small tile.
+            const int rest = (int)(tg.size() - next), cap = std::max(1, Tmax - std::min(4, Tmax - 1));
+            const int passes = (rest + cap - 1) / cap, cnt = (rest + passes - 1) / passes;
+            const int lo = Tmax - cnt;
+            h.lo = lo;
+            for (int i = 0; i < lo; ++i) h.pos[i] = (unsigned char)i;
+            int T = lo;
+            for (int k = 0; k < cnt && next < tg.size(); ++k) {
+                h.pos[T] = (unsigned char)tg[next].first;
+                h.active[h.n_active] = (unsigned char)T;
+                h.c[h.n_active] = cos(tg[next].second);
+                h.s[h.n_active] = sin(tg[next].second);
+                ++h.n_active;
+                ++T;
+                ++next;
+            }
+            h.T = T;
+        }
+        for (int i = 0; i < h.T; ++i) h.mask |= 1ull << h.pos[i];
+        if (!ctx->slice_ring) DQ_CUDA(cudaMalloc(&ctx->slice_ring, sizeof(PhaseArgs) * 64));
+        static_assert(sizeof(TileArgs) <= sizeof(PhaseArgs), "ring slot too small");
+        TileArgs* d = reinterpret_cast<TileArgs*>(reinterpret_cast<PhaseArgs*>(ctx->slice_ring) + (ctx->slice_cursor++ & 63));
+        if ((ctx->slice_cursor & 63) == 0) DQ_CUDA(cudaStreamSynchronize(ctx->stream));
+        DQ_CUDA(cudaMemcpyAsync(d, &h, sizeof(TileArgs), cudaMemcpyHostToDevice, ctx->stream));
+        const unsigned long long n_tiles = 1ull << (L - h.T);
+        const size_t smem = sizeof(double2) << h.T;
+        const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, ((size_t)200 << 10) / std::max<size_t>(smem, 1)));
+        const unsigned grid = (unsigned)std::min<unsigned long long>(n_tiles, (unsigned long long)ctx->prop.multiProcessorCount * per_sm);
+        if (h.lo == h.T) k_slice_rx_tile<true><<<grid, kThreads, smem, ctx->stream>>>((double2*)psi_dev, L, d);
+        else k_slice_rx_tile<false><<<grid, kThreads, smem, ctx->stream>>>((double2*)psi_dev, L, d);
+        ctx->launches++;
+        DQ_CUDA(cudaGetLastError());
+    }
     return DQ_OK;
 }
 

@@ -52,6 +52,11 @@ class CudaSliceOps(object):
     def rx(self, psi, L, bit, theta):
         _lib.check(self.lib.dq_slice_rx(self.ctx.handle, self._p(psi), L, int(bit), float(theta)))
 
+    def rx_many(self, psi, L, bits, thetas):
+        bits = np.ascontiguousarray(bits, dtype=np.int32)
+        thetas = np.ascontiguousarray(thetas, dtype=np.float64)
+        _lib.check(self.lib.dq_slice_rx_many(self.ctx.handle, self._p(psi), L, len(bits), _lib.ptr(bits), _lib.ptr(thetas)))
+
     def energy(self, psi, L, high, n, pair_bits, m_zz, m_const):
         pair_bits = np.ascontiguousarray(pair_bits, dtype=np.int32)
         m_zz = np.ascontiguousarray(m_zz, dtype=np.float64)
@@ -104,6 +109,7 @@ class DistributedState(object):
         self.pos = [self.n - 1 - q for q in range(self.n)]
         self.exchanges = 0
         self.exchanged_bytes = 0
+        self.fused_rx = True               # False: one kernel per rotation (dq_slice_rx), kept for cross-checks
 
     # -- layout ------------------------------------------------------------------------------------
     def pair_bits(self):
@@ -150,12 +156,19 @@ class DistributedState(object):
         x = row[1 + p.n_zz:]
         self.ops.phase(self.psi, self.L, self.rank, self.n, self.pair_bits(), row[:1 + p.n_zz])
         was_global = self.global_qubits()
-        for q in range(self.n):
-            if self.pos[q] < self.L:
-                self.ops.rx(self.psi, self.L, self.pos[q], x[q])
+        self._rotate([q for q in range(self.n) if self.pos[q] < self.L], x)
         if was_global:
             self.swap_global_local()
-            for q in was_global:
+            self._rotate(was_global, x)
+
+    def _rotate(self, qubits, x):
+        """X rotations of one step on local qubits: they commute, so the fused pass kernel takes them all at once."""
+        if not qubits:
+            return
+        if self.fused_rx and hasattr(self.ops, "rx_many"):
+            self.ops.rx_many(self.psi, self.L, [self.pos[q] for q in qubits], [x[q] for q in qubits])
+        else:
+            for q in qubits:
                 self.ops.rx(self.psi, self.L, self.pos[q], x[q])
 
     def evolve_rows(self, rows):

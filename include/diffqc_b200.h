@@ -158,6 +158,9 @@ int dq_slice_phase(dq_context* ctx, void* psi_dev, int L, uint64_t high_bits, in
                    const int32_t* pair_bits, const double* angles);
 /* exp(-i theta X) on local bit `bit` < L */
 int dq_slice_rx(dq_context* ctx, void* psi_dev, int L, int bit, double theta);
+/* exp(-i thetas[k] X) on `count` distinct local bits in as few passes over the slice as their positions allow (the
+ * rotations of one product-formula step commute, diffqc.cc:155-164): up to 12 bits per read + write. */
+int dq_slice_rx_many(dq_context* ctx, void* psi_dev, int L, int count, const int32_t* bits, const double* thetas);
 /* this rank's part of <psi| m_const + sum_e m_zz[e] Z_a Z_b |psi> (sim_plain.py:205,215,281) */
 int dq_slice_energy(dq_context* ctx, const void* psi_dev, int L, uint64_t high_bits, int n_total, int n_zz,
                     const int32_t* pair_bits, const double* m_zz, double m_const, double* partial_out);

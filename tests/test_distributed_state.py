@@ -149,6 +149,40 @@ def test_cuda_slice_kernels_single_rank(n):
     _check(n, 0, 1, None, steps_per=2)
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("L,bits", [(3, [0, 2]), (5, [4, 1, 0, 3, 2]), (12, list(range(12))), (14, [13, 3, 12, 0, 7]),
+                                    (17, list(range(17))), (20, [19, 5, 12, 18, 13, 0, 1, 17, 14, 15, 16]), (21, [20])])
+def test_fused_rotation_pass_equals_one_kernel_per_rotation(L, bits):
+    """dq_slice_rx_many (up to 12 bits per read + write of the slice, any bit set) against dq_slice_rx term by term and,
+    for small slices, against the NumPy stand-in."""
+    import torch
+    ops = distributed.CudaSliceOps(0)
+    rng = np.random.RandomState(L)
+    host = rng.normal(size=1 << L) + 1j * rng.normal(size=1 << L)
+    host /= np.linalg.norm(host)
+    thetas = rng.uniform(-1.5, 1.5, size=len(bits))
+    a, b = ops.alloc(1 << L), ops.alloc(1 << L)
+    ops.from_host(a, host)
+    ops.from_host(b, host)
+    ops.rx_many(a, L, bits, thetas)
+    for bit, th in zip(bits, thetas):
+        ops.rx(b, L, bit, th)
+    ops.ctx.synchronize()
+    got, want = ops.to_host(a), ops.to_host(b)
+    assert np.abs(got - want).max() < 1e-14
+    assert abs(np.linalg.norm(got) - 1.0) < 1e-13
+    if L <= 14:
+        ref = torch.from_numpy(host.copy())
+        cpu = NumpySliceOps()
+        for bit, th in zip(bits, thetas):
+            cpu.rx(ref, L, bit, th)
+        assert np.abs(got - ref.numpy()).max() < 1e-14
+    with pytest.raises(ValueError):
+        ops.rx_many(a, L, [0, 0], [0.1, 0.2])
+    with pytest.raises(ValueError):
+        ops.rx_many(a, L, [L], [0.1])
+
+
 def _gpu_worker(rank, world, port, n):
     sys.path.insert(0, ROOT)
     import torch

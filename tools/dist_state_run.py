@@ -30,6 +30,7 @@ edges = sorted(tuple(sorted(e)) for e in g.edges())
 prob = dq.IsingProblem.maxcut(n, edges)
 coeff = np.random.default_rng(0).normal(0, 1, [len(prob.terms), 6])
 st = distributed.DistributedState(prob, device=local, per_step=10)
+st.fused_rx = bool(int(os.environ.get("FUSED", "1")))       # 0: one kernel per X rotation (round-1 baseline)
 out = {"n": n, "world": world, "slice_GiB": 16 * (1 << st.L) / 2 ** 30, "edges": len(edges)}
 
 # (1) uniform state: <M> = -|E|/2 exactly, norm 1
@@ -54,6 +55,7 @@ st.ops.ctx.synchronize(); torch.cuda.synchronize()
 if world > 1:
     dist.barrier(device_ids=[local])
 x0, b0 = st.exchanges, st.exchanged_bytes
+launches0 = st.ops.ctx.launch_count
 t = time.perf_counter()
 st.evolve_rows(rows)
 st.ops.ctx.synchronize(); torch.cuda.synchronize()
@@ -62,7 +64,8 @@ if world > 1:
 dt = time.perf_counter() - t
 out["steps"] = len(rows); out["seconds_per_step"] = dt / len(rows)
 out["alg_GBs_per_gpu"] = 32.0 * (1 << st.L) * len(rows) / dt / 1e9
-out["kernel_passes_per_step"] = n + 1
+out["fused_rx"] = st.fused_rx
+out["kernel_launches_per_step"] = (st.ops.ctx.launch_count - launches0) / len(rows)
 out["exchange_GB_per_step_per_gpu"] = (st.exchanged_bytes - b0) / max(1, st.exchanges - x0) / 1e9
 out["exchanges"] = st.exchanges - x0
 out["norm2_after"] = st.norm2()
@@ -70,6 +73,6 @@ out["energy_after"] = st.energy()
 if rank == 0:
     print(json.dumps(out, indent=1))
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
-    json.dump(out, open(os.path.join(ROOT, "gpurun_out", "dist_state_n%d_w%d.json" % (n, world)), "w"), indent=1)
+    json.dump(out, open(os.path.join(ROOT, "gpurun_out", "dist_state_n%d_w%d_fused%d.json" % (n, world, int(st.fused_rx))), "w"), indent=1)
 if world > 1:
     dist.destroy_process_group()
