@@ -6,6 +6,7 @@
 // bits [L-g, L) with the rank bits (done by the host through NCCL, diffquantum_b200/distributed.py).
 // Step semantics: the per-term product of diffqc.cc:155-164.
 #include <algorithm>
+#include <stdlib.h>
 #include <string.h>
 #include <utility>
 #include "common.cuh"
@@ -117,21 +118,31 @@ struct TileArgs {
     int n_active;
     unsigned char pos[12];          // physical bit of tile bit i
     unsigned char active[12];       // tile bits to rotate
-    double c[12], s[12];            // per active entry
+    double c[12], s[12];            // per active entry; scaled form: c = 1, s = tan(theta)
     unsigned long long mask;        // OR of 1 << pos[i]
+    double post;                    // scaled form: product of the cosines, applied once when the tile is stored
+    int scaled;
 };
 
+// exp(-i theta X) on a pair.  SCALED: a' = a - i tan(theta) b (one FMA per real component, the cosines are applied once per
+// pass) - the rotation passes are co-limited by the FP64 pipe, so halving its work is worth a template parameter.
+template <bool SCALED>
 __device__ __forceinline__ void rot_pair(double2& a, double2& b, double c, double s) {
     const double2 a0 = a, b0 = b;
-    a = make_double2(fma(s, b0.y, c * a0.x), fma(-s, b0.x, c * a0.y));
-    b = make_double2(fma(s, a0.y, c * b0.x), fma(-s, a0.x, c * b0.y));
+    if (SCALED) {
+        a = make_double2(fma(s, b0.y, a0.x), fma(-s, b0.x, a0.y));
+        b = make_double2(fma(s, a0.y, b0.x), fma(-s, a0.x, b0.y));
+    } else {
+        a = make_double2(fma(s, b0.y, c * a0.x), fma(-s, b0.x, c * a0.y));
+        b = make_double2(fma(s, a0.y, c * b0.x), fma(-s, a0.x, c * b0.y));
+    }
 }
 
 // shared-memory slot of tile element e: XOR swizzle of the 16-byte unit inside each 128-byte row, so that the low-bit
 // rounds (threads 32 / 64 / 128 bytes apart) stay bank-conflict free
 __device__ __forceinline__ int tslot(int e) { return e ^ ((e >> 3) & 7); }
 
-template <bool CONTIG>
+template <bool CONTIG, bool SCALED>
 __global__ void __launch_bounds__(kThreads) k_slice_rx_tile(double2* __restrict__ psi, int L, const TileArgs* __restrict__ ta) {
     extern __shared__ __align__(16) double2 tile[];
     __shared__ TileArgs A;
@@ -169,10 +180,10 @@ __global__ void __launch_bounds__(kThreads) k_slice_rx_tile(double2* __restrict_
                 e = ((e >> i1) << (i1 + 1)) | (e & ((1 << i1) - 1));                // zero at bit i1
                 const int s00 = tslot(e), s01 = tslot(e | (1 << i0)), s10 = tslot(e | (1 << i1)), s11 = tslot(e | (1 << i0) | (1 << i1));
                 double2 v00 = tile[s00], v01 = tile[s01], v10 = tile[s10], v11 = tile[s11];
-                rot_pair(v00, v01, c0, s0);
-                rot_pair(v10, v11, c0, s0);
-                rot_pair(v00, v10, c1, s1);
-                rot_pair(v01, v11, c1, s1);
+                rot_pair<SCALED>(v00, v01, c0, s0);
+                rot_pair<SCALED>(v10, v11, c0, s0);
+                rot_pair<SCALED>(v00, v10, c1, s1);
+                rot_pair<SCALED>(v01, v11, c1, s1);
                 tile[s00] = v00; tile[s01] = v01; tile[s10] = v10; tile[s11] = v11;
             }
             __syncthreads();
@@ -184,13 +195,17 @@ __global__ void __launch_bounds__(kThreads) k_slice_rx_tile(double2* __restrict_
                 const int e = ((q >> i0) << (i0 + 1)) | (q & ((1 << i0) - 1));
                 const int sa = tslot(e), sb = tslot(e | (1 << i0));
                 double2 a = tile[sa], b = tile[sb];
-                rot_pair(a, b, c0, s0);
+                rot_pair<SCALED>(a, b, c0, s0);
                 tile[sa] = a; tile[sb] = b;
             }
             __syncthreads();
         }
         for (int e = threadIdx.x; e < n_el; e += kThreads)
-            psi[base + (CONTIG ? (unsigned long long)e : ((e & lowmask) | hi_off[e >> lo]))] = tile[tslot(e)];
+        {
+            double2 v = tile[tslot(e)];
+            if (SCALED) v = make_double2(v.x * A.post, v.y * A.post);
+            psi[base + (CONTIG ? (unsigned long long)e : ((e & lowmask) | hi_off[e >> lo]))] = v;
+        }
         __syncthreads();
     }
 }
@@ -342,11 +357,21 @@ int dq_slice_rx_many(dq_context* ctx, void* psi_dev, int L, int count, const int
         tg[i] = {bits[i], thetas[i]};
     }
     std::sort(tg.begin(), tg.end());
-    const int Tmax = std::min(12, L);
+    // tile size: 2^12 amplitudes (64 KiB, 3 CTAs per SM) unless DQ_SLICE_TILE_BITS says otherwise (8..12; experiments)
+    static int tile_bits = 0;
+    if (!tile_bits) {
+        const char* env = getenv("DQ_SLICE_TILE_BITS");
+        const int v = env ? atoi(env) : 12;
+        tile_bits = (v >= 8 && v <= 12) ? v : 12;
+    }
+    const int Tmax = std::min(tile_bits, L);
     static bool attr_set = false;
     if (!attr_set) {
-        DQ_CUDA(cudaFuncSetAttribute(k_slice_rx_tile<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double2) << 12)));
-        DQ_CUDA(cudaFuncSetAttribute(k_slice_rx_tile<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double2) << 12)));
+        const int max_smem = (int)(sizeof(double2) << 12);
+        DQ_CUDA(cudaFuncSetAttribute(k_slice_rx_tile<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+        DQ_CUDA(cudaFuncSetAttribute(k_slice_rx_tile<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+        DQ_CUDA(cudaFuncSetAttribute(k_slice_rx_tile<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+        DQ_CUDA(cudaFuncSetAttribute(k_slice_rx_tile<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
         attr_set = true;
     }
     size_t next = 0;
@@ -386,6 +411,17 @@ int dq_slice_rx_many(dq_context* ctx, void* psi_dev, int L, int count, const int
             h.T = T;
         }
         for (int i = 0; i < h.T; ++i) h.mask |= 1ull << h.pos[i];
+        // scaled form unless a rotation angle sits close to pi/2 (|tan| large: the cosine product would lose digits)
+        h.scaled = 1;
+        h.post = 1.0;
+        for (int k = 0; k < h.n_active; ++k)
+            if (fabs(h.c[k]) < 0.05) h.scaled = 0;
+        if (h.scaled)
+            for (int k = 0; k < h.n_active; ++k) {
+                h.post *= h.c[k];
+                h.s[k] = h.s[k] / h.c[k];
+                h.c[k] = 1.0;
+            }
         if (!ctx->slice_ring) DQ_CUDA(cudaMalloc(&ctx->slice_ring, sizeof(PhaseArgs) * 64));
         static_assert(sizeof(TileArgs) <= sizeof(PhaseArgs), "ring slot too small");
         TileArgs* d = reinterpret_cast<TileArgs*>(reinterpret_cast<PhaseArgs*>(ctx->slice_ring) + (ctx->slice_cursor++ & 63));
@@ -395,8 +431,11 @@ int dq_slice_rx_many(dq_context* ctx, void* psi_dev, int L, int count, const int
         const size_t smem = sizeof(double2) << h.T;
         const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, ((size_t)200 << 10) / std::max<size_t>(smem, 1)));
         const unsigned grid = (unsigned)std::min<unsigned long long>(n_tiles, (unsigned long long)ctx->prop.multiProcessorCount * per_sm);
-        if (h.lo == h.T) k_slice_rx_tile<true><<<grid, kThreads, smem, ctx->stream>>>((double2*)psi_dev, L, d);
-        else k_slice_rx_tile<false><<<grid, kThreads, smem, ctx->stream>>>((double2*)psi_dev, L, d);
+        double2* psi = (double2*)psi_dev;
+        if (h.lo == h.T && h.scaled) k_slice_rx_tile<true, true><<<grid, kThreads, smem, ctx->stream>>>(psi, L, d);
+        else if (h.lo == h.T) k_slice_rx_tile<true, false><<<grid, kThreads, smem, ctx->stream>>>(psi, L, d);
+        else if (h.scaled) k_slice_rx_tile<false, true><<<grid, kThreads, smem, ctx->stream>>>(psi, L, d);
+        else k_slice_rx_tile<false, false><<<grid, kThreads, smem, ctx->stream>>>(psi, L, d);
         ctx->launches++;
         DQ_CUDA(cudaGetLastError());
     }

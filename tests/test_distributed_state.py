@@ -161,6 +161,8 @@ def test_fused_rotation_pass_equals_one_kernel_per_rotation(L, bits):
     host = rng.normal(size=1 << L) + 1j * rng.normal(size=1 << L)
     host /= np.linalg.norm(host)
     thetas = rng.uniform(-1.5, 1.5, size=len(bits))
+    if L in (14, 20):
+        thetas[0] = np.pi / 2                   # cos = 0: that pass must take the unscaled form of the rotation
     a, b = ops.alloc(1 << L), ops.alloc(1 << L)
     ops.from_host(a, host)
     ops.from_host(b, host)
