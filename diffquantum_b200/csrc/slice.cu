@@ -245,6 +245,54 @@ __global__ void __launch_bounds__(kThreads) k_slice_energy(const double2* __rest
     }
 }
 
+// <psi|M|psi> partial with the same Gray-code walk: m(g ^ 1<<p) = m(g) - 2 sum_{pairs e containing p} w_e sigma_e(g).
+// GrayArgs::c2 holds 2 w_e here.
+__global__ void __launch_bounds__(kThreads) k_slice_energy_gray(const double2* __restrict__ psi, int L, unsigned long long high,
+                                                                const PhaseArgs* __restrict__ pa, const GrayArgs* __restrict__ ga,
+                                                                double* __restrict__ partial) {
+    __shared__ double w[kMaxPairs];
+    __shared__ unsigned char ba[kMaxPairs], bb[kMaxPairs];
+    __shared__ double red[kThreads / 32];
+    __shared__ GrayArgs G;
+    const int n_zz = pa->n_zz;
+    for (int e = threadIdx.x; e < n_zz; e += blockDim.x) { w[e] = pa->ang[e]; ba[e] = pa->a[e]; bb[e] = pa->b[e]; }
+    if (threadIdx.x == 0) G = *ga;
+    __syncthreads();
+    const double c0 = pa->c0;
+    const int B = G.B, S = G.S;
+    const size_t n_low = (size_t)1 << S;
+    const unsigned long long hi = high << L;
+    double acc = 0.0;
+    for (size_t low = blockIdx.x * (size_t)blockDim.x + threadIdx.x; low < n_low; low += (size_t)gridDim.x * blockDim.x) {
+        unsigned long long g = hi | low;
+        double m = c0;
+        for (int e = 0; e < n_zz; ++e) m += (((g >> ba[e]) ^ (g >> bb[e])) & 1ull) ? -w[e] : w[e];
+        {
+            const double2 v = psi[low];
+            acc = fma(m, v.x * v.x + v.y * v.y, acc);
+        }
+        for (int k = 1; k < (1 << B); ++k) {
+            const int j = __ffs(k) - 1, p = S + j;
+            const int d = G.deg[j];
+            for (int q = 0; q < d; ++q) {
+                const bool differ = (((g >> G.other[j][q]) ^ (g >> p)) & 1ull) != 0;
+                m += differ ? G.c2[j][q] : -G.c2[j][q];                      // sigma flips sign: -w -> +w adds 2w
+            }
+            g ^= 1ull << p;
+            const double2 v = psi[(size_t)(g & ((1ull << L) - 1ull))];
+            acc = fma(m, v.x * v.x + v.y * v.y, acc);
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        double v = threadIdx.x < kThreads / 32 ? red[threadIdx.x] : 0.0;
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (threadIdx.x == 0) partial[blockIdx.x] = v;
+    }
+}
+
 int grid_for(const dq_context* ctx, size_t work) {
     const size_t b = (work + kThreads - 1) / kThreads, cap = (size_t)ctx->prop.multiProcessorCount * 16;
     return (int)std::max<size_t>(1, std::min(b, cap));
@@ -277,6 +325,34 @@ int upload_args(dq_context* ctx, const PhaseArgs& h, PhaseArgs** d_out) {
     return DQ_OK;
 }
 
+// pair lists of the top B local bits; false when a bit has more than kGrayDeg pairs (dense graphs: use the plain kernels)
+bool build_gray(const PhaseArgs& h, int L, bool energy, GrayArgs& gh) {
+    memset(&gh, 0, sizeof(gh));
+    gh.B = std::min(kGrayBits, L);
+    gh.S = L - gh.B;
+    if (L < 10) return false;                              // small slices: the plain kernel is a single wave anyway
+    for (int j = 0; j < gh.B; ++j)
+        for (int e = 0; e < h.n_zz; ++e) {
+            const int p = gh.S + j;
+            if (h.a[e] != p && h.b[e] != p) continue;
+            if (gh.deg[j] == kGrayDeg) return false;
+            gh.other[j][gh.deg[j]] = h.a[e] == p ? h.b[e] : h.a[e];
+            gh.c2[j][gh.deg[j]] = energy ? 2.0 * h.ang[e] : cos(2.0 * h.ang[e]);
+            gh.s2[j][gh.deg[j]] = energy ? 0.0 : sin(2.0 * h.ang[e]);
+            ++gh.deg[j];
+        }
+    return true;
+}
+
+int upload_gray(dq_context* ctx, const GrayArgs& gh, GrayArgs** d_out) {
+    static_assert(sizeof(GrayArgs) <= sizeof(PhaseArgs), "ring slot too small");
+    GrayArgs* dg = reinterpret_cast<GrayArgs*>(reinterpret_cast<PhaseArgs*>(ctx->slice_ring) + (ctx->slice_cursor++ & 63));
+    if ((ctx->slice_cursor & 63) == 0) DQ_CUDA(cudaStreamSynchronize(ctx->stream));
+    DQ_CUDA(cudaMemcpyAsync(dg, &gh, sizeof(GrayArgs), cudaMemcpyHostToDevice, ctx->stream));
+    *d_out = dg;
+    return DQ_OK;
+}
+
 }  // namespace
 
 extern "C" {
@@ -303,26 +379,11 @@ int dq_slice_phase(dq_context* ctx, void* psi_dev, int L, uint64_t high_bits, in
     PhaseArgs* d;
     DQ_TRY(upload_args(ctx, h, &d));
     // Gray-code walk over the top B local bits when every one of them has a short pair list (any sparse graph)
-    static_assert(sizeof(GrayArgs) <= sizeof(PhaseArgs), "ring slot too small");
     GrayArgs gh;
-    memset(&gh, 0, sizeof(gh));
-    gh.B = std::min(kGrayBits, L);
-    gh.S = L - gh.B;
-    bool gray_ok = L >= 10;                                // small slices: the plain kernel is a single wave anyway
-    for (int j = 0; j < gh.B && gray_ok; ++j)
-        for (int e = 0; e < n_zz && gray_ok; ++e) {
-            const int p = gh.S + j;
-            if (h.a[e] != p && h.b[e] != p) continue;
-            if (gh.deg[j] == kGrayDeg) { gray_ok = false; break; }
-            gh.other[j][gh.deg[j]] = h.a[e] == p ? h.b[e] : h.a[e];
-            gh.c2[j][gh.deg[j]] = cos(2.0 * h.ang[e]);
-            gh.s2[j][gh.deg[j]] = sin(2.0 * h.ang[e]);
-            ++gh.deg[j];
-        }
+    const bool gray_ok = build_gray(h, L, false, gh);
     if (gray_ok) {
-        GrayArgs* dg = reinterpret_cast<GrayArgs*>(reinterpret_cast<PhaseArgs*>(ctx->slice_ring) + (ctx->slice_cursor++ & 63));
-        if ((ctx->slice_cursor & 63) == 0) DQ_CUDA(cudaStreamSynchronize(ctx->stream));
-        DQ_CUDA(cudaMemcpyAsync(dg, &gh, sizeof(GrayArgs), cudaMemcpyHostToDevice, ctx->stream));
+        GrayArgs* dg;
+        DQ_TRY(upload_gray(ctx, gh, &dg));
         k_slice_phase_gray<<<grid_for(ctx, (size_t)1 << gh.S), kThreads, 0, ctx->stream>>>((double2*)psi_dev, L, high_bits, d, dg);
     } else {
         k_slice_phase<<<grid_for(ctx, (size_t)1 << L), kThreads, 0, ctx->stream>>>((double2*)psi_dev, L, high_bits, d);
@@ -451,10 +512,18 @@ int dq_slice_energy(dq_context* ctx, const void* psi_dev, int L, uint64_t high_b
     DQ_TRY(fill_args(h, n_total, n_zz, pair_bits, m_zz, m_const));
     PhaseArgs* d;
     DQ_TRY(upload_args(ctx, h, &d));
-    const int blocks = std::min(grid_for(ctx, (size_t)1 << L), 1024);
+    const int blocks = std::min(grid_for(ctx, (size_t)1 << std::max(0, L - kGrayBits)), 1024);
     double* d_part = nullptr;
     DQ_CUDA(cudaMalloc(&d_part, blocks * sizeof(double)));
-    k_slice_energy<<<blocks, kThreads, 0, ctx->stream>>>((const double2*)psi_dev, L, high_bits, d, d_part);
+    GrayArgs gh;
+    if (build_gray(h, L, true, gh)) {
+        GrayArgs* dg = nullptr;
+        const int st = upload_gray(ctx, gh, &dg);
+        if (st != DQ_OK) { cudaFree(d_part); return st; }
+        k_slice_energy_gray<<<blocks, kThreads, 0, ctx->stream>>>((const double2*)psi_dev, L, high_bits, d, dg, d_part);
+    } else {
+        k_slice_energy<<<blocks, kThreads, 0, ctx->stream>>>((const double2*)psi_dev, L, high_bits, d, d_part);
+    }
     ctx->launches++;
     std::vector<double> part(blocks);
     cudaError_t e = cudaMemcpyAsync(part.data(), d_part, blocks * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);

@@ -48,6 +48,13 @@ class NumpySliceOps(object):
         a[:, 0, :] = c * x0 - 1j * s * x1
         a[:, 1, :] = c * x1 - 1j * s * x0
 
+    def rx_many(self, psi, L, bits, thetas):
+        """Stand-in of dq_slice_rx_many: the rotations commute, so any order is the fused pass."""
+        assert len(set(bits)) == len(bits) and all(0 <= b < L for b in bits)
+        self.rx_many_calls = getattr(self, "rx_many_calls", 0) + 1
+        for b, th in zip(bits, thetas):
+            self.rx(psi, L, b, th)
+
     def energy(self, psi, L, high, n, pair_bits, m_zz, m_const):
         a = psi.numpy()
         return float(np.sum(self._diag(L, high, pair_bits, m_zz, m_const) * (a.real ** 2 + a.imag ** 2)))
@@ -82,6 +89,8 @@ def _check(n, rank, world, ops, device=0, steps_per=3):
     ns, dt, ts = R.step_grid(0.2, 1.7, steps_per)
     want = R.evolve_split_structured(ref, R.coef_table_plain(coeff, ref["omegas"], ref["T"], ts), dt, ref["psi0"])
     assert st.exchanges == (ns if world > 1 else 0)                     # one all-to-all per step, no more
+    if hasattr(st.ops, "rx_many_calls"):                                # fused rotations: local set, then the swapped-in qubits
+        assert st.ops.rx_many_calls == ns * (2 if world > 1 else 1)
     e = st.energy()                                                     # layout-agnostic: no restore needed
     assert abs(e - R.energy_diag(ref["m_diag"], want)) < 1e-10
     assert abs(st.norm2() - 1) < 1e-12
