@@ -143,7 +143,7 @@ __device__ __forceinline__ void rot_pair(double2& a, double2& b, double c, doubl
 __device__ __forceinline__ int tslot(int e) { return e ^ ((e >> 3) & 7); }
 
 template <bool CONTIG, bool SCALED>
-__global__ void __launch_bounds__(kThreads) k_slice_rx_tile(double2* __restrict__ psi, int L, const TileArgs* __restrict__ ta) {
+__global__ void __launch_bounds__(kThreads, 3) k_slice_rx_tile(double2* __restrict__ psi, int L, const TileArgs* __restrict__ ta) {
     extern __shared__ __align__(16) double2 tile[];
     __shared__ TileArgs A;
     if (threadIdx.x == 0) A = *ta;
@@ -171,6 +171,31 @@ __global__ void __launch_bounds__(kThreads) k_slice_rx_tile(double2* __restrict_
             tile[tslot(e)] = psi[base + (CONTIG ? (unsigned long long)e : ((e & lowmask) | hi_off[e >> lo]))];
         __syncthreads();
         int k = 0;
+        for (; k + 2 < A.n_active; k += 3) {                // three bits per round trip (A.active is ascending)
+            const int i0 = A.active[k], i1 = A.active[k + 1], i2 = A.active[k + 2];
+            const double c0 = A.c[k], s0 = A.s[k], c1 = A.c[k + 1], s1 = A.s[k + 1], c2 = A.c[k + 2], s2 = A.s[k + 2];
+            for (int q = threadIdx.x; q < (n_el >> 3); q += kThreads) {
+                int e = ((q >> i0) << (i0 + 1)) | (q & ((1 << i0) - 1));
+                e = ((e >> i1) << (i1 + 1)) | (e & ((1 << i1) - 1));
+                e = ((e >> i2) << (i2 + 1)) | (e & ((1 << i2) - 1));
+                int sl[8];
+                double2 v[8];
+#pragma unroll
+                for (int b = 0; b < 8; ++b) {
+                    sl[b] = tslot(e | ((b & 1) << i0) | (((b >> 1) & 1) << i1) | (((b >> 2) & 1) << i2));
+                    v[b] = tile[sl[b]];
+                }
+                rot_pair<SCALED>(v[0], v[1], c0, s0); rot_pair<SCALED>(v[2], v[3], c0, s0);
+                rot_pair<SCALED>(v[4], v[5], c0, s0); rot_pair<SCALED>(v[6], v[7], c0, s0);
+                rot_pair<SCALED>(v[0], v[2], c1, s1); rot_pair<SCALED>(v[1], v[3], c1, s1);
+                rot_pair<SCALED>(v[4], v[6], c1, s1); rot_pair<SCALED>(v[5], v[7], c1, s1);
+                rot_pair<SCALED>(v[0], v[4], c2, s2); rot_pair<SCALED>(v[1], v[5], c2, s2);
+                rot_pair<SCALED>(v[2], v[6], c2, s2); rot_pair<SCALED>(v[3], v[7], c2, s2);
+#pragma unroll
+                for (int b = 0; b < 8; ++b) tile[sl[b]] = v[b];
+            }
+            __syncthreads();
+        }
         for (; k + 1 < A.n_active; k += 2) {                // two bits per round trip
             const int i0 = min(A.active[k], A.active[k + 1]), i1 = max(A.active[k], A.active[k + 1]);
             const double c0 = A.active[k] == i0 ? A.c[k] : A.c[k + 1], s0 = A.active[k] == i0 ? A.s[k] : A.s[k + 1];
