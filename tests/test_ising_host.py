@@ -2,6 +2,7 @@
 import numpy as np
 
 from diffquantum_b200 import pulses as P
+from diffquantum_b200 import pulses
 from diffquantum_b200.ising import IsingProblem
 from oracle import restate as R
 
@@ -67,3 +68,46 @@ def test_maxcut_angle_rows_reproduce_oracle_phases():
             want = want + dt * u[k, i] * R.term_diag(ref, t)
     np.testing.assert_allclose(angle, want, atol=1e-13)
     np.testing.assert_allclose(rows[k, 1 + prob.n_zz:], dt * u[k, len(edges):], atol=1e-16)
+
+
+def test_batched_grids_and_tables_are_bit_identical_to_per_sample_calls():
+    """step_grids / dudc_tables (one vectorised call per gradient batch) against step_grid / dudc_table per sample,
+    including the end points s = 0 and s = T (ten zero-length steps, as the reference does at sim_plain.py:123,133)."""
+    rng = np.random.RandomState(3)
+    T = 2.0
+    s = rng.uniform(size=200) * T
+    s[0], s[1] = 0.0, T
+    for basis, n_basis in (("BSpline", 6), ("Legendre", 5)):
+        coeff = rng.normal(size=(7, n_basis))
+        om = rng.uniform(1, 4, size=7)
+        for T0s, T1s in ((0.0, s), (s, T)):
+            n, dt, ts = pulses.step_grids(T0s, T1s, 10)
+            a, b = np.broadcast_arrays(np.asarray(T0s, float), np.asarray(T1s, float))
+            off = 0
+            U = pulses.u_table(coeff, om, T, ts, basis)
+            for i in range(len(s)):
+                n1, dt1, ts1 = pulses.step_grid(float(a[i]), float(b[i]), 10)
+                assert n1 == n[i] and dt1 == dt[i]
+                assert np.array_equal(ts1, ts[off:off + n1])
+                assert np.array_equal(pulses.u_table(coeff, om, T, ts1, basis), U[off:off + n1])
+                off += n1
+            assert off == len(ts)
+        D = pulses.dudc_tables(coeff, om, T, s, basis)
+        for i in range(len(s)):
+            assert np.array_equal(D[i], pulses.dudc_table(coeff, om, T, s[i], basis))
+    n, dt, ts = pulses.step_grids([1.0, 3.0], [0.5, -1.0], 1)          # negative spans: int() truncation, zero steps allowed
+    assert list(n) == [int(1 * ((0.5 - 1.0) + 1)), 0] and len(ts) == int(n.sum())
+
+
+def test_measurement_noise_consumes_the_global_stream_in_reference_order():
+    """is_noisy (sim_plain.py:207-208,217-218): per control, ps_p then ps_m, one normal(scale=|ps|/5) each."""
+    en = np.arange(1.0, 13.0).reshape(2, 3, 2)
+    np.random.seed(5)
+    want = en.copy()
+    for b in range(2):
+        for i in range(3):
+            want[b, i, 0] += np.random.normal(scale=abs(want[b, i, 0]) / 5)
+            want[b, i, 1] += np.random.normal(scale=abs(want[b, i, 1]) / 5)
+    np.random.seed(5)
+    got = pulses.add_measurement_noise(en.copy())
+    assert np.array_equal(got, want)
