@@ -35,6 +35,15 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
+_JSON_OUT = None          # the process's real stdout once fd 1 has been pointed at stderr (N > 1: NCCL prints to fd 1)
+
+
+def emit_json(line):
+    out = _JSON_OUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 METRIC = "gradient samples/s at n=20 MaxCut"
 UNIT = "samples/s"
 FALLBACK_HBM_GBS = 6650.0          # /opt/skills/guides/B200_PROFILING.md, used only without MEASURED_PEAKS.json
@@ -236,6 +245,12 @@ def run_b200_arm(a):
     if world > 1:
         import torch.distributed as dist
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        # NCCL writes its banner ("NCCL version ...") to file descriptor 1; stdout carries the one JSON line.  Keep a private
+        # copy of the real stdout for that line and point fd 1 at stderr for everything else in this process.
+        global _JSON_OUT
+        sys.stdout.flush()
+        _JSON_OUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
         torch.cuda.set_device(local)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     if not torch.cuda.is_available():
@@ -427,7 +442,7 @@ def run_b200_arm(a):
         except Exception as e:            # the baseline is a report, never a reason to lose the GPU number
             line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": "failed: %s" % e}
     if rank == 0:
-        print(json.dumps(line))
+        emit_json(line)
     if world > 1:
         import torch.distributed as dist
         dist.destroy_process_group()
