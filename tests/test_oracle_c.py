@@ -47,3 +47,16 @@ def test_c_shift_gate_is_the_reference_gate():
     for i, term in enumerate(prob["terms"]):
         for sign in (+1, -1):
             np.testing.assert_allclose(cp.shift(i, phi, sign), R.apply_shift_gate(prob, term, phi, sign), atol=1e-15)
+
+
+def test_host_core_override_ignores_the_launcher_setting():
+    """torchrun exports OMP_NUM_THREADS=1; bench.py's CPU arm asks for every core of the host explicitly."""
+    import os
+    from oracle import c_port as C
+    if not C.available():
+        import pytest
+        pytest.skip("oracle/c/liboracle_c.so not built")
+    want = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    C.load().oc_set_num_threads(1)
+    assert C.num_threads() == 1
+    assert C.use_host_cores() == want
