@@ -3,7 +3,6 @@
 mkdir -p gpurun_out
 ( time timeout 600 python -m pytest tests/test_distributed_state.py -m gpu -x -q ) > gpurun_out/s26_tests.log 2>&1
 tail -4 gpurun_out/s26_tests.log
-true
 N=28 STEPS=2 FUSED=1 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:k_slice --csv --log-file gpurun_out/s26_fused.csv python tools/dist_state_run.py > gpurun_out/s26_fused.log 2>&1
 python - <<'PY'
 import csv
