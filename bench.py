@@ -181,11 +181,11 @@ def cpu_bounded_sample(n, per_step, coeff, edges, s, n_terms):
         if xx and len(order) < n_terms:
             order.append(xx.pop(0))
     t0 = time.perf_counter()
-    _, _, steps = C.grad_mc(cp, coeff, float(s), per_step, terms=order, return_energies=True)
+    _, energies, steps = C.grad_mc(cp, coeff, float(s), per_step, terms=order, return_energies=True)
     dt = time.perf_counter() - t0
     full = steps_of_sample(s, prob["T"], per_step, n_H)[2]
     return dict(seconds=dt, steps=steps, full_steps=full, samples_per_s=(steps / dt) / full,
-                cores=C.num_threads(), n_terms=len(order), n_H=n_H)
+                cores=C.num_threads(), n_terms=len(order), n_H=n_H, order=order, energies=energies[order])
 
 
 def run_reference_arm(a):
@@ -427,6 +427,19 @@ def run_b200_arm(a):
     }
     if per_rank:
         line["per_rank"] = per_rank
+    if world > 1:
+        # untimed: per-sample gradients sharded over the N GPUs must be BIT-equal to the same samples on one GPU (rank 0)
+        s_par = step_samples(12345, 2, world, prob.T)
+        plain = sharding.ShardedEstimator(lambda c, s_: sim.grad_samples(c, s_), device=dev)
+        every = plain.per_sample_gradients(coeff, s_par)
+        if rank == 0:
+            alone = sim.grad_samples(coeff, s_par)
+            diff = float(np.abs(every - alone).max())
+            line["parity_multi_gpu"] = {"max_abs_diff": diff, "bit_equal": bool(diff == 0.0), "samples": int(len(s_par)),
+                                        "what": "ShardedEstimator.per_sample_gradients over %d GPUs vs the same samples on "
+                                                "GPU 0 alone (n=%d, per_step=%d)" % (world, a.n, a.per_step)}
+            if diff != 0.0:
+                raise SystemExit("bench.py: %d-GPU per-sample gradients differ from the 1-GPU result: %r" % (world, diff))
     if linear_leg:
         line["linear_estimator"] = linear_leg
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
@@ -434,6 +447,16 @@ def run_b200_arm(a):
             s0 = step_samples(a.warmup, a.samples_per_step, 1, prob.T)[0]
             cpu_bounded_sample(a.n, a.per_step, coeff, edges, s0, 1)            # warm the OpenMP pool / page in
             r = cpu_bounded_sample(a.n, a.per_step, coeff, edges, s0, a.cpu_terms)
+            # parity at the headline size (untimed): the CPU port's shifted energies of this very sample against the
+            # GPU's, through the public API -- same graph, coefficients, sampled time, per_step as the timed steps
+            gpu_en = sim.shifted_energies(coeff, [s0])[0][r["order"]]
+            err = float(np.abs(gpu_en - r["energies"]).max() / np.abs(r["energies"]).max())
+            line["parity"] = {"max_rel_err": err, "tol": 1e-10, "ok": bool(err < 1e-10),
+                              "what": "shifted energies <ket+-|M|ket+-> of %d controls (%d values) of the sample at s=%.4f, "
+                                      "n=%d per_step=%d: CUDA (dq_ising_grad) vs the plain-C port of diffqc.cc:155-164 / "
+                                      "sim_plain.py:186-230" % (r["n_terms"], 2 * r["n_terms"], s0, a.n, a.per_step)}
+            if not line["parity"]["ok"]:
+                raise SystemExit("bench.py: GPU energies differ from the CPU oracle: %r" % (line["parity"],))
             line["cpu_baseline"] = {
                 "value": r["samples_per_s"], "unit": UNIT, "cores": r["cores"], "kind": "port",
                 "sample": "1 prefix + the +/- trajectories of %d of %d controls of one sample at s=%.4f (%d of %d "

@@ -27,6 +27,8 @@ SIGNATURES = {
                                       ctypes.c_double, ctypes.c_int]),
     "dq_dense_trotter": (ctypes.c_int, [_VP, _VP, ctypes.c_double, ctypes.c_double, ctypes.c_int, _VP,
                                         ctypes.c_int, ctypes.c_int, _VP, _VP]),
+    "dq_pulse_f_u_table": (ctypes.c_int, [ctypes.c_int, _VP, _VP, ctypes.c_double, ctypes.c_int, _VP, ctypes.c_int,
+                                          ctypes.c_int, ctypes.c_int, _VP, _VP]),
     "dq_dense_evolve": (ctypes.c_int, [_VP, ctypes.c_int, _VP, ctypes.c_int, _VP, _VP, ctypes.c_int,
                                        ctypes.c_double, ctypes.c_int, ctypes.c_int, _VP, _VP]),
     "dq_dense_grad": (ctypes.c_int, [_VP, ctypes.c_int, _VP, ctypes.c_int, _VP, _VP, _VP, ctypes.c_double,

@@ -307,16 +307,18 @@ double bump(int b, int n_basis, double t) {
     if (t < r && t > l) return (t - l) * (t - r) / (-(1.5 * tau) * (1.5 * tau));
     return 0.;
 }
-int f_u(const Problem& P, int h, double t, const double* vv, int n_param, int n_basis, double* out) {
+typedef std::vector<std::vector<std::array<double, 4>>> Channels;
+int f_u_channels(const Channels& channels, double duration, int func_type, int h, double t, const double* vv, int n_param,
+                 int n_basis, double* out) {
     double ans = 0;
-    for (const auto& chan : P.channels[h]) {
+    for (const auto& chan : channels[h]) {
         const double omega = chan[1], w = chan[2];
         const int idx = (int)std::round(chan[3]);
         DQ_REQUIRE(idx >= 0 && idx < n_param, "dq_dense_trotter: channel parameter index %d outside vv (n_param=%d)", idx, n_param);
         double A = 0, B = 0;
         for (int j = 0; j < n_basis; ++j) {
-            const double fv = P.func_type == 0 ? std::legendre((unsigned)j, 2 * t / P.duration - 1)
-                                               : bump(j, n_basis, t / P.duration);
+            const double fv = func_type == 0 ? std::legendre((unsigned)j, 2 * t / duration - 1)
+                                             : bump(j, n_basis, t / duration);
             A += vv[((size_t)0 * n_param + idx) * n_basis + j] * fv;
             B += vv[((size_t)1 * n_param + idx) * n_basis + j] * fv;
         }
@@ -327,6 +329,9 @@ int f_u(const Problem& P, int h, double t, const double* vv, int n_param, int n_
     *out = ans;
     return DQ_OK;
 }
+int f_u(const Problem& P, int h, double t, const double* vv, int n_param, int n_basis, double* out) {
+    return f_u_channels(P.channels, P.duration, P.func_type, h, t, vv, n_param, n_basis, out);
+}
 
 }  // namespace
 }  // namespace dense
@@ -335,6 +340,20 @@ int f_u(const Problem& P, int h, double t, const double* vv, int n_param, int n_
 using namespace dq::dense;
 
 extern "C" {
+
+int dq_pulse_f_u_table(int n_H, const int32_t* chan_counts, const double* channels, double duration, int func_type,
+                       const double* vv, int n_param, int n_basis, int n_t, const double* ts, double* u_out) {
+    DQ_REQUIRE(n_H >= 0 && n_t >= 0 && (n_H == 0 || chan_counts) && vv && (n_t == 0 || (ts && u_out)), "dq_pulse_f_u_table: bad argument");
+    DQ_REQUIRE(n_param >= 1 && n_basis >= 1, "dq_pulse_f_u_table: vv must be [2][n_param>=1][n_basis>=1]");
+    DQ_REQUIRE(std::isfinite(duration) && duration != 0.0, "dq_pulse_f_u_table: duration must be finite and non-zero");
+    Channels ch((size_t)n_H);
+    size_t k = 0;
+    for (int h = 0; h < n_H; ++h)
+        for (int c = 0; c < chan_counts[h]; ++c, ++k) ch[h].push_back({channels[4 * k], channels[4 * k + 1], channels[4 * k + 2], channels[4 * k + 3]});
+    for (int i = 0; i < n_t; ++i)
+        for (int h = 0; h < n_H; ++h) DQ_TRY(f_u_channels(ch, duration, func_type, h, ts[i], vv, n_param, n_basis, &u_out[(size_t)i * n_H + h]));
+    return DQ_OK;
+}
 
 int dq_dense_set_H(dq_context* ctx, int dim, const double* H0, int n_H, const double* Hs, const int32_t* chan_counts,
                    const double* channels, double duration, int func_type) {

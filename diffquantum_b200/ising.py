@@ -55,6 +55,15 @@ class IsingProblem(object):
                 self.term_index[i] = int(t[1])
             else:
                 raise ValueError("unsupported control %r (ZZ and X Pauli terms only)" % (t,))
+        # One step is exp(-i dt H0), then exp(-i dt u_h H_h) in LIST order (diffqc.cc:155-164).  The device applies the
+        # whole diagonal factor first and every X rotation after it, which is that product exactly when no X control
+        # precedes a ZZ control in the list (the demo's order, demo_maxcut.py:68-79: edges, then qubits) -- diagonal
+        # factors commute with each other, X rotations on different qubits commute with each other, nothing else does.
+        kinds = self.term_kind.tolist()
+        if 1 in kinds and 0 in kinds[kinds.index(1):]:
+            raise ValueError("unsupported control order: an X control precedes a ZZ control; the per-term product "
+                             "exp(-i dt u_h H_h) in list order (diffqc.cc:155-164) is only implemented for ZZ controls "
+                             "first, X controls after (demo_maxcut.py:68-79)")
         for (a, b) in list(h0_zz) + list(m_zz):
             pair_id(a, b)
         self.zz_pairs = np.array(sorted(pairs, key=pairs.get), dtype=np.int32).reshape(-1, 2)

@@ -159,3 +159,19 @@ def f_u_table(channels, duration, func_type, vv, ts):
             term = omega * (2 * _expit_cc(Ns) - 1) / Ns * (np.cos(w * ts) * A + np.sin(w * ts) * B)
             out[:, h] += np.where(small, 0.0, term)
     return out
+
+
+def f_u_table_lib(channels, duration, func_type, vv, ts):
+    """The same table from the library's own host routine (dq_pulse_f_u_table, the code dq_dense_trotter evaluates its
+    step grid with; diffqc.cc:95-135).  Needs the shared library, not a device."""
+    from . import _lib
+    counts = np.array([len(c) for c in channels], dtype=np.int32)
+    flat = np.ascontiguousarray(np.array([ch for c in channels for ch in c], dtype=np.float64).reshape(-1, 4))
+    v = np.ascontiguousarray(np.asarray(vv, dtype=np.float64))
+    if v.ndim != 3 or v.shape[0] != 2:
+        raise ValueError("vv must be [2][n_param][n_basis]")
+    ts = np.ascontiguousarray(ts, dtype=np.float64).reshape(-1)
+    out = np.empty((ts.size, len(channels)))
+    _lib.check(_lib.load().dq_pulse_f_u_table(len(channels), _lib.ptr(counts), _lib.ptr(flat), float(duration), int(func_type),
+                                              _lib.ptr(v), v.shape[1], v.shape[2], ts.size, _lib.ptr(ts), _lib.ptr(out)))
+    return out

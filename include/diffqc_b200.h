@@ -11,6 +11,7 @@
  *
  *   dq_dense_set_H      diffqc.set_H            diffqc.cc:43-73    (+ pybind11 list casters, stl.h:129-142)
  *   dq_dense_trotter    diffqc.trotter + f_u    diffqc.cc:95-135, 173-205
+ *   dq_pulse_f_u_table  f_u / my_expit / bspline diffqc.cc:75-135  (host only)
  *   dq_dense_evolve     SimulatorPlain.trotter  sim_plain.py:119-153   (solver hook, sim_plain.py:43)
  *   dq_dense_grad       compute_energy_grad_MC  sim_plain.py:186-220   (prefix + 2*n_H shifted suffixes)
  *   dq_ising_*          the same two paths for Pauli-term (MaxCut/QAOA) Hamiltonians that the dense
@@ -69,6 +70,13 @@ int dq_dense_set_H(dq_context* ctx, int dim, const double* H0, int n_H, const do
  * u_out, if not NULL, receives the [n_steps][n_H] envelope values f_u (for parity tests). */
 int dq_dense_trotter(dq_context* ctx, const double* psi0, double T0, double T, int per_step,
                      const double* vv, int n_param, int n_basis, double* psi_out, double* u_out);
+
+/* The pulse envelope f_u of diffqc.cc:95-135 alone, on the HOST (no context, no device): u_out[i][h] = f_u(h, ts[i], vv)
+ * for the channel table of dq_dense_set_H.  This is the routine dq_dense_trotter evaluates its step grid with; it is
+ * exported so that parity tests can compare it with the reference's own compiled f_u (oracle/_ref/libfu.so). */
+int dq_pulse_f_u_table(int n_H, const int32_t* chan_counts, const double* channels, double duration,
+                       int func_type, const double* vv, int n_param, int n_basis, int n_t, const double* ts,
+                       double* u_out);
 
 /* Solver-hook form: the host has already evaluated u[k][h] (Python closures, sim_plain.py:81-98).
  * mode 0 = exact (live reference code), 1 = split (per-term product, diffqc.cc:155-164).

@@ -170,6 +170,82 @@ def golden_split(name, n, edges, seed, per_step, n_samples=3):
     print(name, "energy", R.energy_diag(prob["m_diag"], final))
 
 
+def golden_split_reference(sp_split, qp, name, n, edges, seed, per_step, n_samples=3):
+    """REFERENCE (its own disabled lines, enabled in memory): SimulatorPlain.trotter with sim_plain.py:139,142 active
+    and :140,143,145-146,149 off (oracle/ref_loader.py: load_sim_plain_split), on the demo's dense construction of an
+    n-qubit MaxCut problem; step grid, pulse closures and compute_energy_grad_MC are the reference's unchanged code."""
+    prob = R.maxcut_structured(n, edges)
+    H0, Hs, M = R.maxcut_dense(prob)
+    rng = np.random.RandomState(seed)
+    coeff = rng.normal(0, 1, [len(Hs), 6])
+    sim = make_sim(sp_split, 6, "BSpline", prob["T"], prob["omegas"], len(Hs), coeff, per_step)
+    H = ref_H(sim, qp, H0, Hs, coeff)
+    q0 = qp.Qobj(prob["psi0"])
+    final = sim.trotter(H, q0, 0, prob["T"]).full().reshape(-1)
+    partial = sim.trotter(H, q0, 0.31, 1.17).full().reshape(-1)
+    energy = qp.Qobj(M).matrix_element(qp.Qobj(final), qp.Qobj(final))
+    s_list, grads, phis = [], [], []
+    for k in range(n_samples):
+        np.random.seed(3000 + k)
+        state = np.random.get_state()
+        g = sim.compute_energy_grad_MC(qp.Qobj(M), H, q0).numpy().copy()
+        np.random.set_state(state)
+        s = np.random.uniform() * prob["T"]
+        s_list.append(s)
+        grads.append(g)
+        phis.append(sim.trotter(H, q0, 0, s).full().reshape(-1))
+    np.savez(os.path.join(OUT, name + ".npz"), n=n, edges=np.array(edges), coeff=coeff, per_step=per_step,
+             T=prob["T"], omegas=prob["omegas"], final=final, partial=partial, partial_span=np.array([0.31, 1.17]),
+             energy=energy, s=np.array(s_list), grads=np.array(grads), phis=np.array(phis),
+             source="REFERENCE sim_plain.py:119-231 with its own commented product-form lines :139,:142 enabled and "
+                    ":140,:143,:145-146,:149 disabled in memory (oracle/ref_loader.py load_sim_plain_split), run behind "
+                    "oracle/standin")
+    print(name, "energy", energy.real, "|grad0|", np.linalg.norm(grads[0]))
+
+
+def fu_cases():
+    """Inputs that walk every branch of diffqc.cc:75-135: both bases, the +-32 cutoff of my_expit, |N| < 1e-6,
+    idx rounding (C round: half away from zero), times outside [0, duration] (bump support / Legendre beyond +-1)."""
+    rng = np.random.RandomState(31)
+    cases = []
+    for func_type in (0, 1):
+        for n_basis in (3, 5, 6):
+            n_param = 4
+            vv = rng.normal(0, 1, [2, n_param, n_basis])
+            vv[:, 1, :] *= 1e-8                      # |N| < 1e-6  (diffqc.cc:128-129)
+            vv[:, 2, :] *= 60.0                      # N > 32      (diffqc.cc:76-77)
+            channels = [[[0.0, 1.5, 0.7, 0.0]],
+                        [[0.0, 2.0, 0.0, 1.0], [0.0, 0.5, 1.3, 2.0]],
+                        [[0.0, 1.0, 2.1, 2.4999], [0.0, -0.8, -3.0, 2.5], [0.0, 0.3, 0.2, 0.5]],
+                        []]
+            ts = np.concatenate([np.linspace(-0.3, 2.4, 28), [0.0, 2.0, 1.0, 0.5, 1.5]])
+            cases.append(dict(func_type=func_type, n_basis=n_basis, vv=vv, channels=channels, duration=2.0, ts=ts))
+    return cases
+
+
+def golden_fu_reference(name):
+    """REFERENCE (compiled): f_u of diffqc.cc:95-135 built from the reference source by oracle/ref_cc/Makefile."""
+    from oracle import ref_cc
+    if not ref_cc.build():
+        raise RuntimeError("oracle/_ref/libfu.so could not be built")
+    out = {}
+    lib = ref_cc.load()
+    for i, c in enumerate(fu_cases()):
+        out["u_%d" % i] = ref_cc.f_u_table(c["channels"], c["duration"], c["func_type"], c["vv"], c["ts"])
+        out["vv_%d" % i] = c["vv"]
+        out["ts_%d" % i] = c["ts"]
+        out["meta_%d" % i] = np.array([c["func_type"], c["n_basis"]])
+    xs = np.array([-40.0, -32.0, -31.999, -1.0, 0.0, 1e-7, 3.0, 31.999, 32.0, 32.001, 50.0])
+    out["expit_x"] = xs
+    out["expit_y"] = np.array([lib.ref_my_expit(float(x)) for x in xs])
+    np.savez(os.path.join(OUT, name + ".npz"), n_cases=len(fu_cases()),
+             chan_flat=np.array([ch for c in fu_cases()[0]["channels"] for ch in c]),
+             chan_counts=np.array([len(c) for c in fu_cases()[0]["channels"]]), duration=2.0,
+             source="REFERENCE diffqc.cc:75-135 compiled from the reference source (oracle/ref_cc/Makefile -> oracle/_ref/libfu.so)",
+             **out)
+    print(name, "cases", len(fu_cases()))
+
+
 def golden_diffqc_cc(name):
     """RESTATEMENT of diffqc.set_H/trotter (diffqc.cc:43-135,173-205); Eigen is absent so the
     C++ cannot be built here.  Two-level + coupled-qubit style inputs, both basis types."""
@@ -209,6 +285,14 @@ def main():
     if sys.argv[1:] == ["noisy"]:                       # only the fixture added last; the others stay as committed
         golden_noisy_estimator(sp, qp, "demo_noisy_ref", "demo_bspline_ref")
         return
+    if sys.argv[1:] == ["fu_ref"]:
+        golden_fu_reference("fu_cc_ref")
+        return
+    if sys.argv[1:] == ["split_ref"]:
+        sps = ref_loader.load_sim_plain_split()
+        golden_split_reference(sps, qp, "split_ref_n4", 4, DEMO_GRAPH, seed=21, per_step=10)
+        golden_split_reference(sps, qp, "split_ref_n6", 6, R.random_regular_edges(6, seed=1), seed=22, per_step=10)
+        return
     demo = R.maxcut_structured(4, DEMO_GRAPH)
     H0, Hs, M = R.maxcut_dense(demo)
     golden_dense_reference(sp, qp, "demo_bspline_ref", H0, Hs, M, demo["psi0"], demo["omegas"],
@@ -226,6 +310,10 @@ def main():
                  n_samples=1)
     golden_diffqc_cc("diffqc_cc_restated")
     golden_noisy_estimator(sp, qp, "demo_noisy_ref", "demo_bspline_ref")
+    sps = ref_loader.load_sim_plain_split()
+    golden_split_reference(sps, qp, "split_ref_n4", 4, DEMO_GRAPH, seed=21, per_step=10)
+    golden_split_reference(sps, qp, "split_ref_n6", 6, R.random_regular_edges(6, seed=1), seed=22, per_step=10)
+    golden_fu_reference("fu_cc_ref")
 
 
 if __name__ == "__main__":

@@ -192,3 +192,49 @@ def test_exact_step_vs_matrix_free_oracle(n, per_step):
         g_ref, e_ref = R.grad_mc_structured(ref, coeff, 0.9, per_step, mode="exact", return_energies=True)
         grads, energies = sim.grad_samples(coeff, [0.9], return_energies=True)
         assert rel(energies[0], e_ref) < TOL and rel(grads[0], g_ref) < TOL
+
+
+@pytest.mark.parametrize("name", ["split_ref_n4", "split_ref_n6"])
+def test_split_step_matches_reference_executed_fixture(golden, name):
+    """CUDA vs output of the reference's OWN product-form lines (sim_plain.py:139,142 enabled in memory by
+    oracle/ref_loader.load_sim_plain_split; fixture made by oracle/make_golden.py split_ref)."""
+    g = golden(name)
+    n = int(g["n"])
+    prob = dq.IsingProblem.maxcut(n, g["edges"].tolist())
+    sim = dq.IsingSimulator(prob, per_step=int(g["per_step"]))
+    psi, en = sim.evolve(g["coeff"], 0, prob.T)
+    assert rel(psi[0], g["final"]) < TOL
+    assert abs(en[0] - complex(g["energy"]).real) < TOL * abs(complex(g["energy"]))
+    part, _ = sim.evolve(g["coeff"], float(g["partial_span"][0]), float(g["partial_span"][1]))
+    assert rel(part[0], g["partial"]) < TOL
+    for k, s in enumerate(g["s"]):
+        phi, _ = sim.evolve(g["coeff"], 0, float(s))
+        assert rel(phi[0], g["phis"][k]) < TOL
+    assert rel(sim.grad_samples(g["coeff"], g["s"]), g["grads"]) < TOL
+
+
+def test_headline_config_gradients_vs_c_port():
+    """BASELINE configs[3] at its own size: n=20 random 3-regular MaxCut (the bench graph and coefficients),
+    per_step=10, fused engine, through IsingSimulator.grad_samples -- against the plain-C port of the reference step
+    and estimator (oracle/c, pinned to restate.py, which is pinned to the reference-executed fixtures)."""
+    from oracle import c_port as C
+    if not C.available():
+        pytest.skip("oracle/c/liboracle_c.so not built")
+    import networkx as nx
+    n, per_step = 20, 10
+    g = nx.random_regular_graph(3, n, seed=0)
+    edges = sorted(tuple(sorted(e)) for e in g.edges())
+    prob = dq.IsingProblem.maxcut(n, edges)
+    n_H = len(prob.terms)
+    coeff = np.random.default_rng(0).normal(0, 1, [n_H, 6])
+    sim = dq.IsingSimulator(prob, per_step=per_step, engine=1)
+    assert sim.info("engine") == 1
+    s = 1.87                                    # 28 prefix steps, 11 suffix steps per shifted ket
+    grads, energies = sim.grad_samples(coeff, [s], return_energies=True)
+    C.use_host_cores()
+    ref = R.maxcut_structured(n, edges)
+    terms = [0, 17, 29, 30, 41, 49]             # three ZZ controls, three X controls (low, middle, high bit)
+    g_ref, e_ref, _ = C.grad_mc(C.CProblem(ref), coeff, s, per_step, terms=terms, return_energies=True)
+    assert rel(energies[0][terms], e_ref[terms]) < TOL
+    assert rel(grads[0][terms], g_ref[terms]) < TOL
+    assert np.abs(g_ref[terms]).max() > 1e-3    # not a comparison of zeros

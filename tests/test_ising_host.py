@@ -111,3 +111,40 @@ def test_measurement_noise_consumes_the_global_stream_in_reference_order():
     np.random.seed(5)
     got = pulses.add_measurement_noise(en.copy())
     assert np.array_equal(got, want)
+
+
+def test_control_order_x_before_zz_is_rejected():
+    """the device applies the diagonal factor first, then every X rotation; a list with an X control before
+    a ZZ control is a different (non-commuting) product under diffqc.cc:155-164 and must not be accepted silently."""
+    import pytest
+    from diffquantum_b200.ising import IsingProblem
+    with pytest.raises(ValueError):
+        IsingProblem(2, [('x', 0), ('zz', 0, 1)], [1.0, 1.0], 1.0)
+    with pytest.raises(ValueError):
+        IsingProblem(3, [('zz', 0, 1), ('x', 2), ('zz', 1, 2), ('x', 0)], [1.0] * 4, 1.0)
+    p = IsingProblem(3, [('zz', 0, 1), ('zz', 1, 2), ('x', 2), ('x', 0), ('x', 2)], [1.0] * 5, 1.0)   # ZZ first: fine
+    rows = p.angle_rows(np.array([[0.1, 0.2, 0.3, 0.4, 0.5]]), 0.5)
+    np.testing.assert_allclose(rows[0, 1 + p.n_zz:], [0.2, 0.0, 0.4])       # commuting X pulses on one qubit add
+
+
+def test_interleaved_commuting_order_matches_oracle_semantics():
+    """ZZ-then-X lists in any internal order give the oracle's list-order product (everything that is reordered commutes)."""
+    from diffquantum_b200.ising import IsingProblem
+    from oracle import restate as R
+    terms = [('zz', 1, 2), ('zz', 0, 1), ('x', 2), ('x', 0), ('x', 1)]
+    p = IsingProblem(3, terms, [1.0] * 5, 1.0, h0_zz={(0, 2): 0.3}, h0_const=0.1)
+    u = np.random.RandomState(0).normal(size=(4, 5))
+    rows = p.angle_rows(u, 0.25)
+    # replay the angle rows with plain numpy: diagonal phase then rotations
+    prob = dict(n=3, terms=terms, h0_diag=0.1 + 0.3 * R.z_diag(3, 0) * R.z_diag(3, 2))
+    psi0 = np.random.RandomState(1).normal(size=8) + 1j * np.random.RandomState(2).normal(size=8)
+    want = R.evolve_split_structured(prob, u, 0.25, psi0)
+    psi = psi0.copy()
+    for k in range(4):
+        ang = rows[k, 0] + sum(rows[k, 1 + e] * R.z_diag(3, a) * R.z_diag(3, b) for e, (a, b) in enumerate(p.zz_pairs))
+        psi = psi * np.exp(-1j * ang)
+        for q in range(3):
+            th = rows[k, 1 + p.n_zz + q]
+            v = psi.reshape(1 << q, 2, -1)
+            psi = np.stack([np.cos(th) * v[:, 0] - 1j * np.sin(th) * v[:, 1], np.cos(th) * v[:, 1] - 1j * np.sin(th) * v[:, 0]], axis=1).reshape(-1)
+    np.testing.assert_allclose(psi, want, atol=1e-14)
