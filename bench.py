@@ -63,7 +63,7 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--ket-group", type=int, default=0)
     ap.add_argument("--item-tiles-log2", type=int, default=-1, help="fused v2: tiles per work item = 2^k (default: library default)")
-    ap.add_argument("--engine", type=int, default=1, help="1 fused v2 (32 amps/thread), 2 fused v3 (16 amps/thread)")
+    ap.add_argument("--engine", type=int, default=1, help="1 = the fused pass engine (the only product engine at n=20)")
     return ap.parse_args()
 
 
@@ -289,7 +289,7 @@ def run_b200_arm(a):
         sim.set_option("item_tiles_log2", a.item_tiles_log2)
     if sim.info("engine") != a.engine:
         raise RuntimeError("fused engine %d not available for n=%d" % (a.engine, a.n))
-    kernel_name = "k_f16_passes" if a.engine == 2 else "k_fused_passes"
+    kernel_name = "k_fused_passes"
     n_H = len(prob.terms)
     stream = torch.cuda.ExternalStream(sim.ctx.stream, device=dev)
     flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)

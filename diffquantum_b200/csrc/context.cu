@@ -1,5 +1,6 @@
 // Context, error reporting and calibration micro-benchmarks.
 #include <stdarg.h>
+#include <memory>
 #include "common.cuh"
 #include "dense.cuh"
 
@@ -41,18 +42,18 @@ int dq_context_create(int device, dq_context** out) {
     int count = 0;
     DQ_TRY(dq_device_count(&count));
     DQ_REQUIRE(device >= 0 && device < count, "dq_context_create: device %d of %d", device, count);
-    dq_context* c = new dq_context();
+    std::unique_ptr<dq_context> owner(new dq_context());      // freed on every early return below
+    dq_context* c = owner.get();
     c->device = device;
     DQ_CUDA(cudaSetDevice(device));
     DQ_CUDA(cudaGetDeviceProperties(&c->prop, device));
     if (c->prop.major != 10) {
         dq::set_error("dq_context_create: device %d is sm_%d%d; this library is built for sm_100a only",
                       device, c->prop.major, c->prop.minor);
-        delete c;
         return DQ_ERR_UNSUPPORTED;
     }
     DQ_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
-    *out = c;
+    *out = owner.release();
     return DQ_OK;
 }
 
@@ -62,6 +63,7 @@ int dq_context_destroy(dq_context* ctx) {
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     dq::dense::release(ctx);
     if (ctx->slice_ring) cudaFree(ctx->slice_ring);
+    if (ctx->slice_partials) cudaFree(ctx->slice_partials);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
     return DQ_OK;
@@ -143,15 +145,21 @@ __global__ void mb_smem(double* out, int iters) {
     out[blockIdx.x * blockDim.x + t] = acc.x + acc.y;
 }
 
+// released on every exit path of dq_microbench (the DQ_CUDA / DQ_REQUIRE macros return early)
+struct ScopedDev { void* p = nullptr; ~ScopedDev() { if (p) cudaFree(p); } };
+struct ScopedEvent { cudaEvent_t e = nullptr; ~ScopedEvent() { if (e) cudaEventDestroy(e); } };
+
 }  // namespace
 
 extern "C" int dq_microbench(dq_context* ctx, int kind, int64_t bytes, int iters, double* result) {
     DQ_REQUIRE(ctx && result, "NULL argument");
     DQ_REQUIRE(iters > 0, "iters must be positive");
     DQ_TRY(ctx->set_device());
-    cudaEvent_t e0, e1;
-    DQ_CUDA(cudaEventCreate(&e0));
-    DQ_CUDA(cudaEventCreate(&e1));
+    ScopedEvent g0, g1;
+    ScopedDev ga, gb;
+    DQ_CUDA(cudaEventCreate(&g0.e));
+    DQ_CUDA(cudaEventCreate(&g1.e));
+    cudaEvent_t e0 = g0.e, e1 = g1.e;
     float ms = 0;
     const int sms = ctx->prop.multiProcessorCount;
     if (kind == 0 || kind == 2) {
@@ -159,9 +167,11 @@ extern "C" int dq_microbench(dq_context* ctx, int kind, int64_t bytes, int iters
         size_t n = (size_t)bytes / sizeof(double2);
         double2 *a = nullptr, *b = nullptr;
         DQ_CUDA(cudaMalloc(&a, n * sizeof(double2)));
+        ga.p = a;
         DQ_CUDA(cudaMemsetAsync(a, 0, n * sizeof(double2), ctx->stream));
         if (kind == 0) {
             DQ_CUDA(cudaMalloc(&b, n * sizeof(double2)));
+            gb.p = b;
             mb_copy<<<sms * 8, 256, 0, ctx->stream>>>(a, b, n);
             DQ_CUDA(cudaEventRecord(e0, ctx->stream));
             for (int i = 0; i < iters; ++i) mb_copy<<<sms * 8, 256, 0, ctx->stream>>>(a, b, n);
@@ -175,12 +185,11 @@ extern "C" int dq_microbench(dq_context* ctx, int kind, int64_t bytes, int iters
         DQ_CUDA(cudaEventSynchronize(e1));
         DQ_CUDA(cudaEventElapsedTime(&ms, e0, e1));
         *result = 2.0 * n * sizeof(double2) * iters / (ms * 1e-3) / 1e9;
-        cudaFree(a);
-        if (b) cudaFree(b);
     } else if (kind == 1 || kind == 3) {
         double* out = nullptr;
         const int blocks = sms * 8, threads = 256;
         DQ_CUDA(cudaMalloc(&out, (size_t)blocks * threads * sizeof(double)));
+        ga.p = out;
         if (kind == 1) {
             mb_dfma<<<blocks, threads, 0, ctx->stream>>>(out, 16);
             DQ_CUDA(cudaEventRecord(e0, ctx->stream));
@@ -199,13 +208,10 @@ extern "C" int dq_microbench(dq_context* ctx, int kind, int64_t bytes, int iters
             DQ_CUDA(cudaEventElapsedTime(&ms, e0, e1));
             *result = 16.0 * 32.0 * iters * (sms * 2) * 128 / (ms * 1e-3) / 1e9;   // GB/s smem read
         }
-        cudaFree(out);
     } else {
         dq::set_error("dq_microbench: unknown kind %d", kind);
         return DQ_ERR_INVALID;
     }
-    cudaEventDestroy(e0);
-    cudaEventDestroy(e1);
     DQ_CUDA(cudaGetLastError());
     return DQ_OK;
 }

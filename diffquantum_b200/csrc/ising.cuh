@@ -18,7 +18,7 @@ struct dq_ising {
     int layout_mode = 1;           // 0 reference order (bit n-1-q), 1 automatic (fused engine: no ZZ pair inside a register set)
     dq::DevBuf pairs_dev;          // int2[n_zz] physical bit positions
 
-    int engine = 1;                // 0 generic, 1 fused TMA engine (32 amplitudes/thread, two teams x three tile buffers per SM, default),
+    int engine = 1;                // 0 generic, 1 fused TMA engine (32 amplitudes/thread, two teams x three tile buffers per SM, default)
                                    // 2 fused v3 (16 amplitudes/thread, LDGSTS); 12 <= n <= 20
     int ket_group = 0;             // states co-resident in a fused launch (the work ring a chained launch cycles through); 0 = automatic
     int item_tiles_log2 = 0;       // fused v2: a work item is 2^k consecutive tiles (one atomic / poll / release per item); measured: 0 is best (56.0 / 54.5 / 48.3 / 28.9 samples/s for k = 0..3 at n = 20, finer items pipeline better across pass boundaries)
@@ -83,11 +83,4 @@ int fused_grad_run(dq_ising* p);
 int fused_evolve(dq_ising* p, c128* d_states, int batch, const double* h_rows, int n_steps,
                  double* d_energies, bool want_states);
 
-// fused persistent engine v3 (ising_f16.cu): 16 amplitudes per thread, 16 warps per SM
-int f16_supported(const dq_ising* p);
-void f16_release(dq_ising* p);
-int f16_launch_times(dq_ising* p, double* total_ms, double* n_launches);
-int f16_grad_run(dq_ising* p);
-int f16_evolve(dq_ising* p, c128* d_states, int batch, const double* h_rows, int n_steps,
-               double* d_energies, bool want_states);
 }  // namespace dq

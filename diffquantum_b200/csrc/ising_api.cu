@@ -16,8 +16,7 @@ int check_rows(const dq_ising* p, const double* rows, int64_t n_rows, const char
 }
 
 // the fused engines implement the product-formula step only; the exact step runs on the generic engine
-bool use_f16(const dq_ising* p) { return p->step_mode == 0 && p->engine == 2 && dq::f16_supported(p); }
-bool use_fused(const dq_ising* p) { return p->step_mode == 0 && p->engine >= 1 && !use_f16(p) && dq::fused_supported(p); }
+bool use_fused(const dq_ising* p) { return p->step_mode == 0 && p->engine >= 1 && dq::fused_supported(p); }
 
 // ---- qubit -> bit layout ---------------------------------------------------------------------------------
 // Reference order is bit n-1-q for qubit q (np.kron order, demo_maxcut.py:53-57).  The fused engine keeps two
@@ -106,7 +105,6 @@ int apply_layout(dq_ising* p) {
     DQ_TRY(p->ctx->set_device());
     DQ_CUDA(cudaStreamSynchronize(p->ctx->stream));
     dq::fused_release(p);
-    dq::f16_release(p);
     p->st.valid = false;
     p->identity_layout = !choose_layout(p, p->bitpos);
     {
@@ -187,7 +185,6 @@ int dq_ising_destroy(dq_ising* p) {
     cudaSetDevice(p->ctx->device);
     cudaStreamSynchronize(p->ctx->stream);
     dq::fused_release(p);
-    dq::f16_release(p);
     dq::DevBuf* bufs[] = {&p->mdiag, &p->mdiag_ref, &p->pairs_dev, &p->states, &p->phi, &p->rows_a, &p->rows_b, &p->trig_a,
                           &p->trig_b, &p->energies, &p->scratch, &p->io, &p->shift_desc, &p->st.psi0, &p->exact_diag, &p->exact_t0,
                           &p->exact_t1};
@@ -199,7 +196,7 @@ int dq_ising_destroy(dq_ising* p) {
 int dq_ising_set_option(dq_ising* p, const char* name, int64_t value) {
     DQ_REQUIRE(p && name, "NULL argument");
     if (!strcmp(name, "engine")) {
-        DQ_REQUIRE(value >= 0 && value <= 2, "engine must be 0 (generic), 1 (fused v2) or 2 (fused v3)");
+        DQ_REQUIRE(value >= 0 && value <= 1, "engine must be 0 (generic, one kernel per term group) or 1 (fused pass engine)");
         p->engine = (int)value;
     } else if (!strcmp(name, "item_tiles_log2")) {
         DQ_REQUIRE(value >= 0 && value <= 6, "item_tiles_log2 out of range");
@@ -231,7 +228,7 @@ int dq_ising_set_option(dq_ising* p, const char* name, int64_t value) {
 
 int dq_ising_get_info(dq_ising* p, const char* name, int64_t* value) {
     DQ_REQUIRE(p && name && value, "NULL argument");
-    if (!strcmp(name, "engine")) *value = use_f16(p) ? 2 : (use_fused(p) ? 1 : 0);
+    if (!strcmp(name, "engine")) *value = use_fused(p) ? 1 : 0;
     else if (!strcmp(name, "ket_group")) *value = dq::auto_ket_group(p);
     else if (!strcmp(name, "row_len")) *value = p->row_len;
     else if (!strcmp(name, "identity_layout")) *value = p->identity_layout ? 1 : 0;
@@ -247,8 +244,7 @@ int dq_ising_last_stat(dq_ising* p, const char* name, double* value) {
     else if (!strcmp(name, "alg_bytes")) *value = p->stat_alg_bytes;
     else if (!strcmp(name, "pass_kernel_ms") || !strcmp(name, "pass_kernel_launches")) {
         double ms = 0, nl = 0;
-        if (use_f16(p)) DQ_TRY(dq::f16_launch_times(p, &ms, &nl));
-        else DQ_TRY(dq::fused_launch_times(p, &ms, &nl));
+        DQ_TRY(dq::fused_launch_times(p, &ms, &nl));
         *value = !strcmp(name, "pass_kernel_ms") ? ms : nl;
     }
     else { dq::set_error("dq_ising_last_stat: unknown name '%s'", name); return DQ_ERR_INVALID; }
@@ -259,6 +255,7 @@ int dq_ising_evolve(dq_ising* p, int batch, int n_steps, const double* angles, c
                     void* psi_out, int psi_is_device, double* energies_out) {
     DQ_REQUIRE(p, "NULL problem");
     DQ_REQUIRE(batch >= 1 && n_steps >= 0, "dq_ising_evolve: batch=%d n_steps=%d", batch, n_steps);
+    DQ_REQUIRE(batch <= 65535, "dq_ising_evolve: batch=%d exceeds 65535 states per call (the batch is a grid dimension)", batch);
     DQ_REQUIRE(psi_out || energies_out, "dq_ising_evolve: nothing requested");
     DQ_TRY(check_rows(p, angles, n_steps, "dq_ising_evolve"));
     DQ_TRY(p->ctx->set_device());
@@ -277,10 +274,7 @@ int dq_ising_evolve(dq_ising* p, int batch, int n_steps, const double* angles, c
         DQ_TRY(dq::gen_permute_in(p, p->io.as<c128>(), d, batch));
     }
     DQ_TRY(p->energies.reserve(batch * sizeof(double)));
-    if (use_f16(p)) {
-        DQ_TRY(dq::f16_evolve(p, d, batch, angles, n_steps, energies_out ? p->energies.as<double>() : nullptr,
-                              psi_out != nullptr));
-    } else if (use_fused(p)) {
+    if (use_fused(p)) {
         DQ_TRY(dq::fused_evolve(p, d, batch, angles, n_steps, energies_out ? p->energies.as<double>() : nullptr,
                                 psi_out != nullptr));
     } else {
@@ -392,7 +386,7 @@ int dq_ising_grad_stage(dq_ising* p, int n_samples, const int32_t* prefix_steps,
         }
     }
     DQ_TRY(p->energies.reserve((size_t)n_samples * 2 * n_shift * sizeof(double)));
-    if (!use_fused(p) && !use_f16(p)) {
+    if (!use_fused(p)) {
         DQ_TRY(p->trig_a.reserve((np ? np : 1) * p->n * sizeof(double2)));
         DQ_TRY(p->trig_b.reserve((ns ? ns : 1) * p->n * sizeof(double2)));
         DQ_TRY(dq::gen_trig(p, p->rows_a.as<double>(), np, p->trig_a.as<double2>()));
@@ -416,9 +410,7 @@ int dq_ising_grad_run_staged(dq_ising* p) {
     const size_t N = p->dim();
     const int kets = 2 * s.n_shift;
     double steps = 0;
-    if (use_f16(p)) {
-        DQ_TRY(dq::f16_grad_run(p));
-    } else if (use_fused(p)) {
+    if (use_fused(p)) {
         DQ_TRY(dq::fused_grad_run(p));
     } else {
         cudaStream_t st = p->ctx->stream;

@@ -458,14 +458,12 @@ int dq_slice_rx_many(dq_context* ctx, void* psi_dev, int L, int count, const int
         tile_bits = (v >= 8 && v <= 12) ? v : 12;
     }
     const int Tmax = std::min(tile_bits, L);
-    static bool attr_set = false;
-    if (!attr_set) {
+    {   // the attribute is per device and cheap to set: no process-wide "done" flag (two contexts, two devices)
         const int max_smem = (int)(sizeof(double2) << 12);
         DQ_CUDA(cudaFuncSetAttribute(k_slice_rx_tile<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
         DQ_CUDA(cudaFuncSetAttribute(k_slice_rx_tile<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
         DQ_CUDA(cudaFuncSetAttribute(k_slice_rx_tile<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
         DQ_CUDA(cudaFuncSetAttribute(k_slice_rx_tile<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
-        attr_set = true;
     }
     size_t next = 0;
     while (next < tg.size()) {
@@ -545,13 +543,13 @@ int dq_slice_energy(dq_context* ctx, const void* psi_dev, int L, uint64_t high_b
     PhaseArgs* d;
     DQ_TRY(upload_args(ctx, h, &d));
     const int blocks = std::min(grid_for(ctx, (size_t)1 << std::max(0, L - kGrayBits)), 1024);
-    double* d_part = nullptr;
-    DQ_CUDA(cudaMalloc(&d_part, blocks * sizeof(double)));
+    if (!ctx->slice_partials) DQ_CUDA(cudaMalloc(&ctx->slice_partials, 1024 * sizeof(double)));   // kept: no malloc / free (device-wide syncs) per energy
+    double* d_part = (double*)ctx->slice_partials;
     GrayArgs gh;
     if (build_gray(h, L, true, gh)) {
         GrayArgs* dg = nullptr;
         const int st = upload_gray(ctx, gh, &dg);
-        if (st != DQ_OK) { cudaFree(d_part); return st; }
+        if (st != DQ_OK) return st;
         k_slice_energy_gray<<<blocks, kThreads, 0, ctx->stream>>>((const double2*)psi_dev, L, high_bits, d, dg, d_part);
     } else {
         k_slice_energy<<<blocks, kThreads, 0, ctx->stream>>>((const double2*)psi_dev, L, high_bits, d, d_part);
@@ -560,7 +558,6 @@ int dq_slice_energy(dq_context* ctx, const void* psi_dev, int L, uint64_t high_b
     std::vector<double> part(blocks);
     cudaError_t e = cudaMemcpyAsync(part.data(), d_part, blocks * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-    cudaFree(d_part);
     DQ_CUDA(e);
     double acc = 0.0;
     for (double v : part) acc += v;            // fixed order: deterministic

@@ -113,7 +113,7 @@ int dq_ising_create(dq_context* ctx, int n_qubits, int n_zz, const int32_t* zz_p
                     const double* m_diag /*[2^n] host, overrides m_zz when not NULL*/,
                     dq_ising** out);
 int dq_ising_destroy(dq_ising* p);
-/* Tunables: "ket_group" (states co-resident in L2 per launch), "engine" (0 generic, 1 fused TMA engine = default when 12 <= n <= 20, 2 fused v3),
+/* Tunables: "ket_group" (states co-resident in L2 per launch), "engine" (0 generic = one kernel per term group, 1 fused TMA pass engine = default when 12 <= n <= 20),
  * "step" (0 = per-term product step, diffqc.cc:155-164; 1 = the reference's live exact step
  * exp(-i dt H(t_k)) psi as a matrix-free scaled Taylor series, sim_plain.py:135-150 with :147; generic engine),
  * "linear" (1, fused v2 only: evolve one shifted ket per term plus the unshifted suffix state and obtain the

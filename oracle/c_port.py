@@ -16,13 +16,49 @@ LIB_PATH = os.path.join(_HERE, "c", "liboracle_c.so")
 _lib = None
 
 
-def available():
+_STAMP = os.path.join(_HERE, "c", "built_for.txt")
+
+
+def _host_id():
+    """CPU model + ISA flags of this machine: the library is built with -march=native, so it only runs where it was built."""
+    try:
+        txt = open("/proc/cpuinfo").read()
+        import hashlib
+        model = [l for l in txt.splitlines() if l.startswith("model name")][:1]
+        flags = [l for l in txt.splitlines() if l.startswith("flags")][:1]
+        return hashlib.sha1(("".join(model) + "".join(flags)).encode()).hexdigest()
+    except OSError:
+        return "unknown"
+
+
+def ensure_built():
+    """(Re)build liboracle_c.so when it is missing or was built on a different CPU (the snapshot that travels to the GPU box
+    carries the build container's .so).  Needs gcc and make; returns available()."""
+    import subprocess
+    have = os.path.isfile(LIB_PATH) and os.path.isfile(_STAMP) and open(_STAMP).read().strip() == _host_id()
+    if not have:
+        try:
+            subprocess.check_call(["make", "-s", "-B", "-C", os.path.join(_HERE, "c")])
+            open(_STAMP, "w").write(_host_id() + "\n")
+        except (OSError, subprocess.CalledProcessError):
+            return False
     return os.path.isfile(LIB_PATH)
+
+
+_avail = None
+
+
+def available():
+    global _avail
+    if _avail is None:
+        _avail = ensure_built()
+    return _avail
 
 
 def load():
     global _lib
     if _lib is None:
+        available()
         lib = ctypes.CDLL(LIB_PATH)
         vp = ctypes.c_void_p
         lib.oc_num_threads.restype = ctypes.c_int

@@ -27,7 +27,7 @@ def rel(a, b):
 
 
 @pytest.mark.parametrize("name", ["split_n4_demo", "split_n6", "split_n8", "split_n12"])
-@pytest.mark.parametrize("engine", [0, 1, 2])
+@pytest.mark.parametrize("engine", [0, 1])
 def test_split_golden_fixture(golden, name, engine):
     g = golden(name)
     n = int(g["n"])
@@ -43,9 +43,8 @@ def test_split_golden_fixture(golden, name, engine):
 
 
 @pytest.mark.parametrize("n,per_step,engine", [(1, 5, 0), (2, 5, 0), (3, 4, 0), (10, 3, 0), (13, 3, 1),
-                                               (14, 2, 1), (16, 1, 1), (16, 1, 0), (20, 1, 1), (19, 1, 1), (12, 3, 2), (13, 3, 2),
-                                               (14, 2, 2), (15, 2, 2), (16, 1, 2), (17, 1, 2), (18, 1, 2),
-                                               (19, 1, 2), (20, 1, 2)])
+                                               (14, 2, 1), (15, 2, 1), (16, 1, 1), (16, 1, 0), (17, 1, 1), (18, 1, 1),
+                                               (20, 1, 1), (19, 1, 1), (12, 3, 1)])
 def test_evolve_vs_oracle_live(n, per_step, engine):
     edges = graph_for(n)
     prob = dq.IsingProblem.maxcut(n, edges)
@@ -125,7 +124,7 @@ def test_norm_is_preserved_and_errors_are_python_exceptions():
         dq.IsingProblem(3, [("zz", 0, 3)], [1.0], 1.0)
 
 
-@pytest.mark.parametrize("n,engine", [(12, 2), (15, 2), (17, 2), (20, 2), (16, 1), (12, 1), (20, 1)])
+@pytest.mark.parametrize("n,engine", [(12, 1), (15, 1), (16, 1), (17, 1), (20, 1)])
 def test_fused_gradients_agree_with_generic_engine(n, engine):
     """Every shifted ket (each ZZ pair and each X qubit, both signs) through the fused passes vs the
     one-kernel-per-term engine on the same device; the generic engine is pinned to the oracle above."""

@@ -14,7 +14,7 @@ np.random.seed(1)
 s_list = np.random.uniform(size=B) * prob.T
 res = []
 base = None
-engines = [int(x) for x in os.environ.get("ENGINES", "1,2").split(",")]
+engines = [int(x) for x in os.environ.get("ENGINES", "1").split(",")]
 groups = [int(x) for x in os.environ.get("KG", "2,3,4,5,6,8").split(",")]
 for engine, G in [(0, 1)] + [(e, g) for e in engines for g in groups]:
     if engine == 0 and os.environ.get("SKIP_GENERIC"):
