@@ -66,6 +66,7 @@ constexpr int kMaxGroup = 128;             // kets per launch (their descriptors
 #define DQ_CTAS_PER_SM 1
 #endif
 
+
 enum : int { F_ENERGY = 2, F_STORE = 4 };
 
 struct __align__(16) PassStep {
@@ -81,7 +82,8 @@ struct __align__(16) PassStep {
 
 // Launch-constant geometry of one pass type; lives in kernel parameters (constant bank).
 struct TypeGeom {
-    int a, lowmask;                 // tile bit t -> physical: t < a ? t : 10 + (t - a)   (type H; L is identity)
+    int a, lowmask;                 // tile bit t -> physical: t < a ? t : start + (t - a)   (H: start = 10; L: a = start = 12, identity)
+    int start;
     int tid_lo_bits, high_end;
     int fj_pos[5][kMaxNbr], fj_msk[5][kMaxNbr];
     int xk_pos[5][kMaxNbr], xk_msk[5][kMaxNbr];
@@ -93,6 +95,8 @@ struct TypePlan {
     TypeGeom g;
     int start, spare_shift;
     int jq[5], kq[5];               // x-angle column of the qubit on that register bit, -1 = spectator
+    int jq_all[5], kq_all[5];       // qubit whose index bit sits on that register position, rotated by this pass type or not
+    int colq[16];                   // qubit on column bit i (-1: none)
     int fj_pair[5][kMaxNbr], xk_pair[5][kMaxNbr];
     int n_col_bits;
     int n_pairs;
@@ -148,6 +152,9 @@ struct LaunchArgs {
     int h_c1_shift;                 // H view: coordinate 1 of tile t is t << h_c1_shift
     int h_sw64;                     // H tiles land in the 64-byte swizzle (rows of 4 amplitudes, n = 20); see process_tile
     double r, ca, sa, c2a, s2a;     // shift gate: r, cos/sin(atan r), cos/sin(2 atan r)
+    double rtau;                    // r / (1 + r^2): second coefficient of the shift gate's lifting butterfly
+    const PassStep* steps0;         // first PassStep of the run: (ps - steps0) << n_col_bits is that pass-step's column table
+    int n_col_bits;
     TypeGeom geom[2];
 };
 
@@ -199,6 +206,35 @@ __device__ __forceinline__ void rot_bit(c128 (&v)[kRegs], const double2 rc) {
             v[j | (1 << B)] = make_double2(fma(rc.y, a.y, rc.x * b.x), fma(-rc.y, a.x, rc.x * b.y));
         }
     }
+}
+
+// LIFTING form of the same rotation, every FMA accumulating IN PLACE (destination = addend), rc = (t, tau) = (tan, sin cos):
+//     a <- a - i t b            = a'/cos                      (the scaled butterfly for the bit-0 half)
+//     b <- b - i tau a(new)     = (b - i t a)/(1 + t^2) = b' cos
+// Same 4 DFMA per pair as the scaled form, but no value ever changes register -- the accumulator pattern of a GEMM inner
+// loop -- so ptxas keeps the 128 amplitude registers in place across loop back-edges and ONE copy of the 320-DFMA run
+// serves all four rotation rounds of a tile (the straight-line form needs four: 37 KB of code per pass type against a
+// 32 KB instruction cache, the measured limiter of round 1).  The price is a per-amplitude pending factor
+// (bit ? cos : 1/cos) for every rotated bit; it is a product over index bits, exactly the shape of the phase tables,
+// and k_setup folds its inverse into them (see "resolve" there): no instruction is spent on it here.
+template <int B>
+__device__ __forceinline__ void lift_bit(c128 (&v)[kRegs], const double2 rc) {
+#pragma unroll
+    for (int j = 0; j < kRegs; ++j) {
+        if (j & (1 << B)) continue;
+        const int k = j | (1 << B);
+        v[j].x = fma(rc.x, v[k].y, v[j].x);
+        v[j].y = fma(-rc.x, v[k].x, v[j].y);
+        v[k].x = fma(rc.y, v[j].y, v[k].x);
+        v[k].y = fma(-rc.y, v[j].x, v[k].y);
+    }
+}
+__device__ __forceinline__ void lift_run(c128 (&v)[kRegs], const double2* rc) {
+    lift_bit<0>(v, rc[0]);
+    lift_bit<1>(v, rc[1]);
+    lift_bit<2>(v, rc[2]);
+    lift_bit<3>(v, rc[3]);
+    lift_bit<4>(v, rc[4]);
 }
 
 // Straight-line on purpose: a branch around a butterfly block makes ptxas reconcile the 128
@@ -490,6 +526,7 @@ __device__ __forceinline__ void flush_pending(const LaunchArgs& A, Shared& sh, P
     pd.g = -1;
 }
 
+#ifndef DQ_PROBE_ONLY
 // Everything between "the tile is in shared memory" and "the tile is stored / reduced" for one pass type.
 // `nxt_raw` is the raw index of the following item (valid in thread 0 only); thread 0 turns it into
 // sh.info[nb] half-way through, and as soon as that item's dependency holds and a tile buffer is free it
@@ -965,10 +1002,10 @@ __global__ void __launch_bounds__(kThreads, DQ_CTAS_PER_SM) k_fused_passes(const
         const int flags = P.flags;
         if (tid == 0) { TRACEX(A, I.item, 2, P.type); TRACEX(A, I.item, 6, blockIdx.x * kTeams + team + 1); TRACEX(A, I.item, 7, I.p); }
         if (P.type == 0)
-            process_tile<SCALED, AJ, CROSS, 0>(A, kd, P, tile, sh, skets, I, nxt_raw, cur ^ 1, total, cache, cached_ps, cb,
+            process_tile<false, AJ, CROSS, 0>(A, kd, P, tile, sh, skets, I, nxt_raw, cur ^ 1, total, cache, cached_ps, cb,
                                         next_cb, next_tables_new, pd, cs, tiles, team, buf, my_free, my_tiles);
         else
-            process_tile<SCALED, AJ, CROSS, 1>(A, kd, P, tile, sh, skets, I, nxt_raw, cur ^ 1, total, cache, cached_ps, cb,
+            process_tile<false, AJ, CROSS, 1>(A, kd, P, tile, sh, skets, I, nxt_raw, cur ^ 1, total, cache, cached_ps, cb,
                                         next_cb, next_tables_new, pd, cs, tiles, team, buf, my_free, my_tiles);
         TRACE(A, I.item, 7);
         if (tid == 0 && I.sub + 1 == nsub) {   // item complete: published after the next item's mid-tile barrier
@@ -993,6 +1030,437 @@ __global__ void __launch_bounds__(kThreads, DQ_CTAS_PER_SM) k_fused_passes(const
     }
 }
 
+#endif  // DQ_PROBE_ONLY
+
+// ------------------------------------------------------------------------------------------
+// the persistent pass kernel, WARP-SPECIALISED LOOP form (scaled mode: |angle| <= 1)
+// ------------------------------------------------------------------------------------------
+// Same passes, tiles, TMA views and inter-CTA dependency counters as k_fused_passes.  Two things change.
+//
+// (1) The tile body is a loop.  The four rotation rounds {KA, J1, J2, KB} share ONE copy of the 320-DFMA butterfly run
+//     (lifting form, lift_bit: every FMA accumulates in place, so the 128 amplitude registers stay put across the
+//     back-edge); what differs between rounds -- the shared-memory slots read and written, the phase -- sits in uniform
+//     branches in front of it.  ~900 instructions per pass type instead of 2330: both types fit the 32 KB instruction
+//     cache (the straight-line body streamed 37 KB per tile from the GPC-level cache, round 1's measured limiter).
+//
+// (2) The protocol leaves the compute warps.  A CTA is three warpgroups:
+//       WG0, WG1  consumer teams (4 warps, 128 threads, 232 registers each after setmaxnreg): wait for a full tile buffer,
+//                 run the tile body, write the result back into the buffer, arrive on its `done` barrier.  Team t takes
+//                 tiles k = t, t+2, ... of this CTA, tile k lives in buffer k mod 3.  No item decoding, no polling,
+//                 no TMA, no atomics in these warps.
+//       WG2       warp 8 = LOADER: reserves work items from the global counter (one ahead), skips items of ragged groups,
+//                 waits for the buffer to be free and for the item's dependency (all tiles of the previous pass of its ket),
+//                 then issues three async copies onto the buffer's `full` mbarrier: the tile (one TMA tensor load), the
+//                 pass-step tables (2.6 KB bulk copy) and the four base-phase column entries of the tile (64 B bulk copy).
+//                 warp 9 = STORER: waits for `done`, issues the TMA tensor store, frees the buffer when the store has read
+//                 it, writes the tile's energy partial, and publishes the tile (per-ket counter) once the store is complete
+//                 at L2 -- one tile late, so it never waits for a store it has just issued.
+//                 (40 registers after setmaxnreg; warps 10, 11 only give their registers back.)
+//     Every wait of the data path is an mbarrier; the only spinning on global memory is the loader's dependency poll.
+struct WsSlot {                     // one per tile buffer; written by the loader before `full` completes
+    int p, g, t_id, grp;
+    int stop;                       // 1: no more tiles for the team that receives this buffer
+    int pad_[3];
+    double2 tc[4];                  // base-phase column entries of this tile (bulk-copied from the column table)
+};
+struct WsShared {
+    unsigned long long full[kBufs], done[kBufs], empty[kBufs];
+    WsSlot slot[kBufs];
+    double red[kBufs][kTeamThreads / 32];
+    double red2[kBufs][kTeamThreads / 32];
+};
+constexpr int kWsThreads = 384;
+constexpr int kWsConsumerRegs = 232, kWsProducerRegs = 40;     // 2 x 128 x 232 + 128 x 40 = 64512 <= 65536
+
+__device__ __forceinline__ bool mbar_test(unsigned long long* bar, unsigned parity) {
+    unsigned done;
+    asm volatile("{\n.reg .pred p;\nmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+                 : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return done != 0;
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void bulk_copy_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+template <int N> __device__ __forceinline__ void bulk_wait_group() { asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory"); }
+
+// The tile body of a consumer team: everything between "the buffer is full" and "the result is back in the buffer".
+// ONE body serves both pass types: the type is a run-time value, and only the small blocks that move amplitudes between
+// registers and shared memory are written out per type (their slot offsets are compile-time constants of Geo<>); the
+// butterfly run, the phase and the energy reduction exist once.  (Two fully inlined per-type bodies behind one branch
+// made ptxas spill; this form does not, and it is half the code.)
+#define DQ_FOR_REGS(stmt) _Pragma("unroll") for (int j = 0; j < kRegs; ++j) { stmt; }
+template <bool AJ, bool CROSS>
+__device__ __forceinline__ void ws_tile(const LaunchArgs& A, WsShared& ws, const KetDesc* __restrict__ skets,
+                                        PassStep& P, c128* __restrict__ tile, const int b, const int team) {
+    using G0 = Geo<0>;
+    using G1 = Geo<1>;
+    const int type = P.type;
+    const TypeGeom& T = A.geom[type];
+    int tid = threadIdx.x & (kTeamThreads - 1);
+    const WsSlot& S = ws.slot[b];
+
+    auto tile_bit_of = [&](int s) { return s < T.a ? s : (s >= T.start ? s - T.start + T.a : -1); };   // physical bit -> tile bit
+
+    // Pass 0 of a shifted ket: the X shift gate (I + i sigma r X) = exp(-i theta X)/cos(theta), tan(theta) = -sigma r, rides on
+    // the KA or J1 round as one more butterfly.  This buffer's copy of the pass-step tables is private to the tile, so the
+    // gate is PATCHED into it -- the lifting pair (t, t/(1+t^2)) into the (otherwise identity) rotation slot, and the factor
+    // (1 + r^2) that the lifting form leaves its bit-1 half short of (relative to the scaled form `escale` expects) into the
+    // phase tables -- and the round loop below stays free of shift-gate code.
+    if (S.p == 0) {
+        const KetDesc* __restrict__ kd = skets + S.g;
+        if (kd->shift_kind == 1) {
+            const int tb0 = tile_bit_of(kd->sb0);
+            const int ovK = type == 0 ? G0::kslot(tb0) : G1::kslot(tb0), ovJ = type == 0 ? G0::jslot(tb0) : G1::jslot(tb0);
+            const double r2p1 = fma(A.r, A.r, 1.0);
+            if (tid == 0) {
+                const double2 rc = make_double2(-kd->sigma * A.r, -kd->sigma * A.rtau);
+                if (ovK >= 0) P.rot[0][ovK] = rc;
+                if (ovJ >= 0) P.rot[1][ovJ] = rc;
+            }
+            if (ovK >= 0 && tid < 32 && ((tid >> ovK) & 1)) { P.tkk[tid].x *= r2p1; P.tkk[tid].y *= r2p1; }
+            if (ovJ >= 0 && tid < 8) { P.fj[ovJ][tid].x *= r2p1; P.fj[ovJ][tid].y *= r2p1; }
+        }
+        team_sync(team);
+    }
+
+    c128 v[kRegs];
+#pragma unroll 1
+    for (int r = 0; r < 4; ++r) {
+        // opaque per round: what a round derives from the thread index (slot addresses, gather indices, table addresses) is
+        // formed where it is used instead of being hoisted out of the loop and kept alive across the butterfly run
+        asm volatile("" : "+r"(tid));
+        const int iK = type == 0 ? G0::baseK(tid) : G1::baseK(tid);
+        const int iJ = type == 0 ? G0::baseJ(tid) : G1::baseJ(tid);
+        const int sK = swz(iK), sJ = swz(iJ);
+        if (r == 0) {
+            // ---- KA : landing layout -> registers --------------------------------------------------------
+            if (type == 0) {
+                DQ_FOR_REGS(v[j] = tile[slot(sK, G0::regK(j))])
+            } else {
+                // an H tile whose rows are 64 bytes (n = 20) lands in the 64-byte swizzle (see process_tile)
+                const int b0 = A.h_sw64 ? (iK ^ ((iK >> 3) & 3)) : sK;
+                const int b1 = A.h_sw64 ? b0 : (b0 ^ 4);
+                DQ_FOR_REGS(v[j] = tile[((j & 1) ? b1 : b0) + G1::regK(j)])
+            }
+        } else if (r == 1) {
+            // ---- K -> J exchange --------------------------------------------------------------------------
+            if (type == 0) {                     // L: the exchange never leaves the warp's 1024 amplitudes
+                DQ_FOR_REGS(tile[slot(sK, G0::regK(j))] = v[j])
+                __syncwarp();
+                DQ_FOR_REGS(v[j] = tile[slot(sJ, G0::regJ(j))])
+            } else {
+                __syncwarp();                    // from here on the tile lives in the 128-byte pattern
+                DQ_FOR_REGS(tile[slot(sK, G1::regK(j))] = v[j])
+                team_sync(team);
+                DQ_FOR_REGS(v[j] = tile[slot(sJ, G1::regJ(j))])
+            }
+        } else if (r == 2) {
+            // ---- phase of the new step (the J1 rotations are done) ------------------------------------------
+            const int t_id = S.t_id;
+            const size_t tbase = ((size_t)(t_id & ((1 << T.tid_lo_bits) - 1)) << T.a) | ((size_t)(t_id >> T.tid_lo_bits) << T.high_end);
+            const size_t xJ = tbase + ((size_t)(iJ & T.lowmask) | ((size_t)(iJ >> T.a) << T.start));
+            const int kb = type == 0 ? G0::kbits(iJ) : G1::kbits(iJ);
+            c128 phi = cmul(S.tc[(iJ >> (type == 0 ? G0::spare_shift : G1::spare_shift)) & 3], P.tkk[kb]);
+#pragma unroll
+            for (int m = 0; m < 5; ++m) {
+                if (T.xk_msk[m][0]) {            // launch-uniform
+                    c128 w = P.xk[m][gather3(xJ, T.xk_pos[m], T.xk_msk[m])];
+                    if ((kb >> m) & 1) w.y = -w.y;
+                    phi = cmul(phi, w);
+                }
+            }
+            c128 F[5];
+#pragma unroll
+            for (int k = 0; k < 5; ++k) F[k] = P.fj[k][gather3(xJ, T.fj_pos[k], T.fj_msk[k])];
+            if (S.p == 0) {
+                const KetDesc* __restrict__ kd = skets + S.g;
+                if (kd->shift_kind == 0) {       // ZZ shift gate exp(i sigma alpha z0 z1); never both operands in J
+                    const int tb0 = tile_bit_of(kd->sb0), tb1 = tile_bit_of(kd->sb1);
+                    const double sigma = kd->sigma;
+                    const int j0b = type == 0 ? G0::jslot(tb0) : G1::jslot(tb0);
+                    const int j1b = type == 0 ? G0::jslot(tb1) : G1::jslot(tb1);
+                    const double z0 = ((xJ >> kd->sb0) & 1) ? -1.0 : 1.0;
+                    const double z1 = ((xJ >> kd->sb1) & 1) ? -1.0 : 1.0;
+                    // with the J operand at 0 (z = +1) the factor is exp(i sigma alpha z_other)
+                    phi = cmul(phi, make_double2(A.ca, sigma * A.sa * z0 * z1));
+                    const int jb = j0b >= 0 ? j0b : j1b;
+                    if (jb >= 0) {               // flipping that J bit multiplies by exp(-2 i sigma alpha z_other)
+                        const double zo = j0b >= 0 ? z1 : z0;
+                        const c128 f = make_double2(A.c2a, -sigma * A.s2a * zo);
+#pragma unroll
+                        for (int k = 0; k < 5; ++k)
+                            if (k == jb) F[k] = cmul(F[k], f);
+                    }
+                }
+            }
+#pragma unroll
+            for (int b4 = 0; b4 < 2; ++b4) {
+                const c128 p4 = b4 ? cmul(phi, F[4]) : phi;
+#pragma unroll
+                for (int b3 = 0; b3 < 2; ++b3) {
+                    const c128 p3 = b3 ? cmul(p4, F[3]) : p4;
+#pragma unroll
+                    for (int b2 = 0; b2 < 2; ++b2) {
+                        const c128 p2 = b2 ? cmul(p3, F[2]) : p3;
+#pragma unroll
+                        for (int b1 = 0; b1 < 2; ++b1) {
+                            const c128 p1 = b1 ? cmul(p2, F[1]) : p2;
+                            const int j = (b4 << 4) | (b3 << 3) | (b2 << 2) | (b1 << 1);
+                            v[j] = cmul(v[j], p1);
+                            v[j | 1] = cmul(v[j | 1], cmul(p1, F[0]));
+                        }
+                    }
+                }
+            }
+            if (AJ) {
+                DQ_FOR_REGS(v[j] = cmul(v[j], P.aj[j]))
+            }
+        } else {
+            // ---- J -> K exchange --------------------------------------------------------------------------
+            if (type == 0) {
+                DQ_FOR_REGS(tile[slot(sJ, G0::regJ(j))] = v[j])
+                team_sync(team);
+                DQ_FOR_REGS(v[j] = tile[slot(sK, G0::regK(j))])
+            } else {
+                DQ_FOR_REGS(tile[slot(sJ, G1::regJ(j))] = v[j])
+                team_sync(team);
+                DQ_FOR_REGS(v[j] = tile[slot(sK, G1::regK(j))])
+            }
+        }
+        lift_run(v, P.rot[r]);
+    }
+    {
+        const int flags = P.flags;
+        const int iK = type == 0 ? G0::baseK(tid) : G1::baseK(tid);
+        if (flags & F_STORE) {               // back into the landing layout of this buffer; one bulk store takes it from there
+            const int sK = swz(iK);
+            if (type == 0) {
+                DQ_FOR_REGS(tile[slot(sK, G0::regK(j))] = v[j])
+            } else {
+                __syncwarp();                // 64-byte pattern: these are not the slots this thread has just read
+                const int b0 = A.h_sw64 ? (iK ^ ((iK >> 3) & 3)) : sK;
+                const int b1 = A.h_sw64 ? b0 : (b0 ^ 4);
+                DQ_FOR_REGS(tile[((j & 1) ? b1 : b0) + G1::regK(j)] = v[j])
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        }
+        if (flags & F_ENERGY) {
+            const KetDesc* __restrict__ kd = skets + S.g;
+            const int t_id = S.t_id;
+            const size_t tbase = ((size_t)(t_id & ((1 << T.tid_lo_bits) - 1)) << T.a) | ((size_t)(t_id >> T.tid_lo_bits) << T.high_end);
+            const size_t xK = tbase + ((size_t)(iK & T.lowmask) | ((size_t)(iK >> T.a) << T.start));
+            const double* __restrict__ md = A.mdiag + xK;
+            const c128* __restrict__ cr = (CROSS && kd->cross) ? kd->cross + xK : nullptr;
+            double e = 0.0, e2 = 0.0;
+#pragma unroll
+            for (int j = 0; j < kRegs; ++j) {
+                const size_t o = (size_t)T.offK[j];
+                const double m = __ldg(md + o);
+                e = fma(m, fma(v[j].x, v[j].x, v[j].y * v[j].y), e);
+                if (CROSS && cr) {           // Re conj(a) ket
+                    const c128 a0 = __ldcg(cr + o);
+                    e2 = fma(m, fma(a0.x, v[j].x, a0.y * v[j].y), e2);
+                }
+            }
+            for (int o = 16; o > 0; o >>= 1) e += __shfl_xor_sync(0xffffffffu, e, o);
+            if ((tid & 31) == 0) ws.red[b][tid >> 5] = e;
+            if (CROSS) {
+                for (int o = 16; o > 0; o >>= 1) e2 += __shfl_xor_sync(0xffffffffu, e2, o);
+                if ((tid & 31) == 0) ws.red2[b][tid >> 5] = e2;
+            }
+        }
+    }
+}
+#undef DQ_FOR_REGS
+
+template <bool AJ, bool CROSS>
+__global__ void __launch_bounds__(kWsThreads, 1) k_fused_ws(const __grid_constant__ LaunchArgs A) {
+    extern __shared__ __align__(16) unsigned char smem_dyn[];
+    unsigned char* smem_raw = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);      // TMA swizzle: 1 KiB aligned buffers
+    c128* tiles = reinterpret_cast<c128*>(smem_raw);
+    PassStep* tables = reinterpret_cast<PassStep*>(smem_raw + sizeof(c128) * kTile * kBufs);     // one per tile buffer
+    KetDesc* skets = reinterpret_cast<KetDesc*>(smem_raw + sizeof(c128) * kTile * kBufs + kBufs * sizeof(PassStep));
+    __shared__ __align__(16) WsShared ws;
+
+    if (threadIdx.x == 0) {
+        for (int b = 0; b < kBufs; ++b) {
+            mbar_init(&ws.full[b], 1);
+            mbar_init(&ws.done[b], kTeamThreads);
+            mbar_init(&ws.empty[b], 1);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    {
+        const int4* src = reinterpret_cast<const int4*>(A.kets);
+        int4* dst = reinterpret_cast<int4*>(skets);
+        for (int i = threadIdx.x; i < A.n_kets * (int)(sizeof(KetDesc) / 16); i += kWsThreads) dst[i] = __ldg(src + i);
+    }
+    __syncthreads();                              // the last CTA-wide barrier: the roles part ways here
+    const unsigned total = ((unsigned)A.max_pass * (unsigned)A.group * (unsigned)A.n_groups) << A.ipp_log2;
+    const int wg = threadIdx.x / kTeamThreads;
+
+    if (wg < kTeams) {
+        // ------------------------------ consumer team ---------------------------------------------------------
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kWsConsumerRegs));
+        const int team = wg;
+        for (unsigned k = (unsigned)team;; k += kTeams) {
+            const int b = (int)(k % kBufs);
+            mbar_wait(&ws.full[b], (k / kBufs) & 1u);
+            if (ws.slot[b].stop) {
+                mbar_arrive(&ws.done[b]);         // the storer sees the stop in tile order
+                break;
+            }
+            PassStep& P = tables[b];
+            c128* tile = tiles + (size_t)b * kTile;
+            ws_tile<AJ, CROSS>(A, ws, skets, P, tile, b, team);
+            mbar_arrive(&ws.done[b]);             // release: this thread's tile writes (fenced for the async proxy) and partials
+        }
+    } else {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kWsProducerRegs));
+        const int w = (threadIdx.x - kTeams * kTeamThreads) >> 5;
+        if (w == 0 && (threadIdx.x & 31) == 0) {
+            // ------------------------------ loader ------------------------------------------------------------
+            unsigned q_next = take_item(A.counters);
+            unsigned stops = 0;
+            for (unsigned k = 0;; ++k) {
+                ItemInfo I;
+                bool have = false;
+                if (!stops) {
+                    for (;;) {                    // next item that exists (ragged groups: kets with fewer passes are skipped)
+                        const unsigned item = q_next;
+                        if (item >= total) break;
+                        q_next = take_item(A.counters);
+                        decode_item(A, item, I);
+                        if (item_valid(A, skets, I, total)) { have = true; break; }
+                    }
+                }
+                const int b = (int)(k % kBufs);
+                if (k >= kBufs) mbar_wait(&ws.empty[b], ((k / kBufs) - 1u) & 1u);   // the store of tile k - 3 has read the buffer
+                WsSlot& S = ws.slot[b];
+                if (!have) {                      // out of work: one stop per team, then done
+                    S.stop = 1;
+                    mbar_arrive(&ws.full[b]);
+                    if (++stops == kTeams) break;
+                    continue;
+                }
+                int ctr;
+                unsigned need;
+                if (item_dependency(A, skets, I.p, I.g, ctr, need)) {
+                    // relaxed poll (see ld_relaxed): what depends on it is the TMA load below, which reads L2
+                    while (ld_relaxed(&A.counters[ctr]) < need) __nanosleep(20);
+                }
+                const KetDesc* __restrict__ kd = skets + I.g;
+                const PassStep* ps = kd->steps + I.p;
+                S.p = I.p;
+                S.g = I.g;
+                S.t_id = I.t_id;
+                S.grp = I.grp;
+                S.stop = 0;
+                const int type = (I.p + kd->cls) & 1;
+                const CUtensorMap* map = A.maps + 2 * (I.p == 0 ? kd->map_src : kd->map_buf) + type;
+                c128* tile = tiles + (size_t)b * kTile;
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                mbar_expect_tx(&ws.full[b], (unsigned)(sizeof(c128) * kTile + sizeof(PassStep) + sizeof(S.tc)));
+                if (type == 0) {
+                    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                                 ::"r"(smem_u32(tile)), "l"(map), "r"(smem_u32(&ws.full[b])), "r"(0), "r"(0), "r"(2 * I.t_id) : "memory");
+                } else {
+                    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+                                 ::"r"(smem_u32(tile)), "l"(map), "r"(smem_u32(&ws.full[b])), "r"(0), "r"(I.t_id << A.h_c1_shift), "r"(0), "r"(0) : "memory");
+                }
+                bulk_copy_g2s(&tables[b], ps, (unsigned)sizeof(PassStep), &ws.full[b]);
+                const double2* tc = A.tc + ((unsigned long long)(ps - A.steps0) << A.n_col_bits) + ((unsigned)I.t_id << 2);
+                bulk_copy_g2s(S.tc, tc, (unsigned)sizeof(S.tc), &ws.full[b]);
+            }
+        } else if (w == 1 && (threadIdx.x & 31) == 0) {
+            // ------------------------------ storer ------------------------------------------------------------
+            int pend_g = -1;                      // tile whose completion is not published yet
+            bool pend_stored = false;
+            unsigned stops = 0;
+            for (unsigned k = 0;; ++k) {
+                const int b = (int)(k % kBufs);
+                const unsigned par = (k / kBufs) & 1u;
+                while (!mbar_test(&ws.done[b], par)) {
+                    if (pend_g >= 0) {            // idle: publish what is pending (its store is the most recent group)
+                        if (pend_stored) bulk_wait_group<0>();
+                        atomicAdd(&A.counters[1 + pend_g], 1u);
+                        pend_g = -1;
+                    } else {
+                        __nanosleep(20);
+                    }
+                }
+                const WsSlot& S = ws.slot[b];
+                if (S.stop) {
+                    if (++stops == kTeams) break;
+                    continue;
+                }
+                const KetDesc* __restrict__ kd = skets + S.g;
+                const int flags = tables[b].flags;
+                const int type = tables[b].type;
+                const bool stored = (flags & F_STORE) != 0;
+                if (stored) {
+                    store_tile(A, kd, type, S.t_id, tiles + (size_t)b * kTile);
+                    // the tile before this one: its store is now the second most recent group
+                    if (pend_g >= 0) {
+                        if (pend_stored) bulk_wait_group<1>();
+                        atomicAdd(&A.counters[1 + pend_g], 1u);
+                        pend_g = -1;
+                    }
+                    bulk_wait_read();             // the store has read the buffer: the loader may refill it
+                } else if (pend_g >= 0) {
+                    if (pend_stored) bulk_wait_group<0>();
+                    atomicAdd(&A.counters[1 + pend_g], 1u);
+                    pend_g = -1;
+                }
+                if (flags & F_ENERGY) {
+                    if (kd->partial) kd->partial[S.grp] = (ws.red[b][0] + ws.red[b][1] + ws.red[b][2] + ws.red[b][3]) * kd->escale;
+                    if (CROSS && kd->cross) kd->partial2[S.grp] = (ws.red2[b][0] + ws.red2[b][1] + ws.red2[b][2] + ws.red2[b][3]) * kd->escale2;
+                }
+                pend_g = S.g;
+                pend_stored = stored;
+                mbar_arrive(&ws.empty[b]);
+            }
+            if (pend_g >= 0) {
+                bulk_wait_group<0>();
+                atomicAdd(&A.counters[1 + pend_g], 1u);
+            }
+        }
+    }
+}
+
+#ifdef DQ_PROBE_ONLY
+// Register-allocation probe (build with -DDQ_PROBE_ONLY, never linked): the consumer loop alone under the register budget
+// the consumer warpgroups get from setmaxnreg (launch bounds 280 threads -> 232 registers).
+template <bool AJ, bool CROSS>
+__global__ void k_ws_probe(const __grid_constant__ LaunchArgs A) {
+    extern __shared__ __align__(16) unsigned char smem_dyn[];
+    unsigned char* smem_raw = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
+    c128* tiles = reinterpret_cast<c128*>(smem_raw);
+    PassStep* tables = reinterpret_cast<PassStep*>(smem_raw + sizeof(c128) * kTile * kBufs);
+    KetDesc* skets = reinterpret_cast<KetDesc*>(smem_raw + sizeof(c128) * kTile * kBufs + kBufs * sizeof(PassStep));
+    __shared__ __align__(16) WsShared ws;
+    const int team = threadIdx.x / kTeamThreads;
+    for (unsigned k = (unsigned)team;; k += kTeams) {
+        const int b = (int)(k % kBufs);
+        mbar_wait(&ws.full[b], (k / kBufs) & 1u);
+        if (ws.slot[b].stop) {
+            mbar_arrive(&ws.done[b]);
+            break;
+        }
+        PassStep& P = tables[b];
+        c128* tile = tiles + (size_t)b * kTile;
+        ws_tile<AJ, CROSS>(A, ws, skets, P, tile, b, team);
+        mbar_arrive(&ws.done[b]);
+    }
+}
+template __global__ void k_ws_probe<false, false>(const __grid_constant__ LaunchArgs);
+}  // namespace fused
+}  // namespace dq
+#else
 // ------------------------------------------------------------------------------------------
 // table setup: one CTA per pass-step (y = column-table chunk)
 // ------------------------------------------------------------------------------------------
@@ -1021,23 +1489,32 @@ __global__ void __launch_bounds__(128) k_setup(const SetupJob* __restrict__ jobs
         const double j1 = (pre && T.jq[b] >= 0) ? pre[off_x + T.jq[b]] : 0.0;
         const double j2 = (cur && T.jq[b] >= 0) ? cur[off_x + T.jq[b]] : 0.0;
         const double kbv = (cur && T.kq[b] >= 0) ? cur[off_x + T.kq[b]] : 0.0;
-        ang[0][b] = cur ? ka : 0.0;
+        // final pass (no `cur`): the straight-line body moves the K rotations of the last step to slot KB (energy from the
+        // coalesced outer layout either way); the lifting body keeps them in KA so that every pending factor is resolved
+        // by this pass's phase and its KB round is the identity
+        ang[0][b] = (cur || scaled) ? ka : 0.0;
         ang[1][b] = j1;
         ang[2][b] = j2;
-        ang[3][b] = cur ? kbv : ka;
+        ang[3][b] = cur ? kbv : (scaled ? 0.0 : ka);
     }
-    if (scaled) {
+    // Lifting butterflies (scaled mode) leave amplitude x with the factor  prod_b (bit_b(x) ? cos_b : 1/cos_b)  over every
+    // bit b rotated since the last phase: the bits of THIS pass type by its KA / J1 rounds and the bits of the OTHER type by
+    // the previous pass's J2 / KB rounds -- together every qubit, each with its angle of row `pre`.  The phase of this pass
+    // "resolves" them: the inverse factor is a product over index bits, so it folds into the tables by position of the bit
+    // (K position -> tkk, J position -> base and fj, column bit -> tc).
+    double rk[5], rj[5];
 #pragma unroll
-        for (int s = 0; s < 4; ++s)
-#pragma unroll
-            for (int b = 0; b < 5; ++b) scale *= cos(ang[s][b]);
+    for (int b = 0; b < 5; ++b) {
+        rk[b] = (scaled && pre && T.kq_all[b] >= 0) ? cos(pre[off_x + T.kq_all[b]]) : 1.0;
+        rj[b] = (scaled && pre && T.jq_all[b] >= 0) ? cos(pre[off_x + T.jq_all[b]]) : 1.0;
     }
+    (void)scale;
     if (blockIdx.y == 0) {
         if (tid < 20) {
             const int s = tid / 5, b = tid % 5;
             double sn, cs;
             sincos(ang[s][b], &sn, &cs);
-            P.rot[s][b] = scaled ? make_double2(1.0, sn / cs) : make_double2(cs, sn);
+            P.rot[s][b] = scaled ? make_double2(sn / cs, sn * cs) : make_double2(cs, sn);     // (tan, sin cos) | (cos, sin)
         }
         if (tid == 0) {
             P.flags = job.flags;
@@ -1057,9 +1534,12 @@ __global__ void __launch_bounds__(128) k_setup(const SetupJob* __restrict__ jobs
                         default: break;
                     }
                 }
+            double res = 1.0;                   // resolve: K positions by their bit of tid, J positions at bit 0
+#pragma unroll
+            for (int b = 0; b < 5; ++b) res *= (((tid >> b) & 1) ? 1.0 / rk[b] : rk[b]) * rj[b];
             double sn, cs;
             sincos(a, &sn, &cs);
-            P.tkk[tid] = make_double2(scale * cs, -scale * sn);
+            P.tkk[tid] = make_double2(res * cs, -res * sn);
             sincos(aa, &sn, &cs);
             P.aj[tid] = make_double2(cs, -sn);
         } else if (tid < 32 + 40) {             // xk[m][pat]
@@ -1079,7 +1559,8 @@ __global__ void __launch_bounds__(128) k_setup(const SetupJob* __restrict__ jobs
                     if (T.g.fj_msk[k][t]) a += cur[1 + T.fj_pair[k][t]] * zsign(pat, t);
             double sn, cs;
             sincos(2.0 * a, &sn, &cs);
-            P.fj[k][pat] = make_double2(cs, sn);
+            const double res = 1.0 / (rj[k] * rj[k]);           // resolve: J position k at bit 1 relative to bit 0
+            P.fj[k][pat] = make_double2(res * cs, res * sn);
         }
     }
     // column table: CC pairs + fields from J neighbours
@@ -1092,9 +1573,16 @@ __global__ void __launch_bounds__(128) k_setup(const SetupJob* __restrict__ jobs
                 if (T.cls[e] == 5) a += g * ((((col >> T.i0[e]) ^ (col >> T.i1[e])) & 1) ? -1.0 : 1.0);
                 else if (T.cls[e] == 3) a += g * (((col >> T.i1[e]) & 1) ? -1.0 : 1.0);
             }
+        double res = 1.0;                       // resolve: column bits
+        if (scaled && pre)
+            for (int i = 0; i < n_col_bits; ++i)
+                if (T.colq[i] >= 0) {
+                    const double c = cos(pre[off_x + T.colq[i]]);
+                    res *= ((col >> i) & 1) ? 1.0 / c : c;
+                }
         double sn, cs;
         sincos(a, &sn, &cs);
-        tc[tc_off + col] = make_double2(cs, -sn);
+        tc[tc_off + col] = make_double2(res * cs, -res * sn);
     }
 }
 
@@ -1127,7 +1615,7 @@ struct Plan {
     int jphys[2][5];
     DevBuf d_types, jobs, steps, tc, kets, counters, partials, out_index, work, rows, phi, uniform, trace, afin, ea, ea_index;
     long long trace_items = 0;
-    size_t smem_bytes = 0;
+    size_t smem_bytes = 0, ws_smem_bytes = 0;
     int ctas_per_sm = 0;
     int counter_slots = 0, counter_cursor = 0;
     std::vector<cudaEvent_t> ev;    // option time_launches: event pairs around every pass-kernel launch of the last run
@@ -1165,6 +1653,7 @@ static bool build_type(const dq_ising* p, int type, TypePlan& T, int* jphys_out)
     const int* kbits = kKBits[type];
     auto spread = [](int j, const int* bits) { int t = 0; for (int i = 0; i < 5; ++i) t |= ((j >> i) & 1) << bits[i]; return t; };
     T.g.a = a;
+    T.g.start = T.start;
     T.g.lowmask = (1 << a) - 1;
     T.g.tid_lo_bits = T.start - a;
     T.g.high_end = T.start + b;
@@ -1187,6 +1676,8 @@ static bool build_type(const dq_ising* p, int type, TypePlan& T, int* jphys_out)
         jphys_out[i] = jphys[i];
         T.jq[i] = active(jphys[i]) ? qubit_of_pos[jphys[i]] : -1;
         T.kq[i] = active(kphys[i]) ? qubit_of_pos[kphys[i]] : -1;
+        T.jq_all[i] = qubit_of_pos[jphys[i]];
+        T.kq_all[i] = qubit_of_pos[kphys[i]];
     }
     // column bits: the two spare tile bits, then the tile-id bits in ascending physical order
     std::vector<int> colphys;
@@ -1195,6 +1686,7 @@ static bool build_type(const dq_ising* p, int type, TypePlan& T, int* jphys_out)
     for (int pos = 0; pos < n; ++pos)
         if (tile_bit_of_phys(pos) < 0) colphys.push_back(pos);
     if ((int)colphys.size() != n - 10) return false;
+    for (int i = 0; i < 16; ++i) T.colq[i] = i < (int)colphys.size() ? qubit_of_pos[colphys[i]] : -1;
     auto local = [&](int pos, int& kind, int& idx) {
         for (int i = 0; i < 5; ++i) if (jphys[i] == pos) { kind = 0; idx = i; return; }
         for (int i = 0; i < 5; ++i) if (kphys[i] == pos) { kind = 1; idx = i; return; }
@@ -1316,9 +1808,9 @@ static int maps_upload(dq_ising* p, Plan* pl) {
     return DQ_OK;
 }
 
-template <typename K> static bool prep_kernel(K kern, size_t smem, int* occ) {
+template <typename K> static bool prep_kernel(K kern, size_t smem, int* occ, int threads = kThreads) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return false;
-    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, kern, kThreads, smem) == cudaSuccess && *occ >= 1;
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, kern, threads, smem) == cudaSuccess && *occ >= 1;
 }
 
 static Plan* get_plan(dq_ising* p) {
@@ -1335,6 +1827,7 @@ static Plan* get_plan(dq_ising* p) {
     pl->n_col_bits = p->n - 10;
     pl->tiles_log2 = p->n - kTileBits;
     pl->smem_bytes = 1024 + sizeof(c128) * kTile * kBufs + 2 * kTeams * sizeof(PassStep) + kMaxGroup * sizeof(KetDesc);
+    pl->ws_smem_bytes = 1024 + sizeof(c128) * kTile * kBufs + kBufs * sizeof(PassStep) + kMaxGroup * sizeof(KetDesc);
     {
         const int a = 22 - p->n;
         pl->h_c1_shift = a - std::min(a, 3);
@@ -1345,13 +1838,13 @@ static Plan* get_plan(dq_ising* p) {
     if (cudaMemcpy(pl->d_types.p, pl->types, sizeof(TypePlan) * 2, cudaMemcpyHostToDevice) != cudaSuccess) return pl;
     int occ = 0, o2 = 0;
     int o3 = 0, o4 = 0;
-    bool good = pl->has_aj ? (prep_kernel(k_fused_passes<true, true, false>, pl->smem_bytes, &occ) &&
+    bool good = pl->has_aj ? (prep_kernel(k_fused_ws<true, false>, pl->ws_smem_bytes, &occ, kWsThreads) &&
                               prep_kernel(k_fused_passes<false, true, false>, pl->smem_bytes, &o2) &&
-                              prep_kernel(k_fused_passes<true, true, true>, pl->smem_bytes, &o3) &&
+                              prep_kernel(k_fused_ws<true, true>, pl->ws_smem_bytes, &o3, kWsThreads) &&
                               prep_kernel(k_fused_passes<false, true, true>, pl->smem_bytes, &o4))
-                           : (prep_kernel(k_fused_passes<true, false, false>, pl->smem_bytes, &occ) &&
+                           : (prep_kernel(k_fused_ws<false, false>, pl->ws_smem_bytes, &occ, kWsThreads) &&
                               prep_kernel(k_fused_passes<false, false, false>, pl->smem_bytes, &o2) &&
-                              prep_kernel(k_fused_passes<true, false, true>, pl->smem_bytes, &o3) &&
+                              prep_kernel(k_fused_ws<false, true>, pl->ws_smem_bytes, &o3, kWsThreads) &&
                               prep_kernel(k_fused_passes<false, false, true>, pl->smem_bytes, &o4));
     o2 = std::min(o2, std::min(o3, o4));
     if (!good) { cudaGetLastError(); return pl; }
@@ -1426,6 +1919,8 @@ static int launch_group(dq_ising* p, Plan* pl, const KetDesc* d_kets, int n_kets
     A.h_c1_shift = pl->h_c1_shift;
     A.h_sw64 = (22 - pl->n) < 3 ? 1 : 0;
     A.tc = pl->tc.as<double2>();
+    A.steps0 = pl->steps.as<PassStep>();
+    A.n_col_bits = pl->n_col_bits;
     A.mdiag = p->mdiag.as<double>();
     A.counters = ctr;
     A.n_kets = n_kets;
@@ -1435,11 +1930,13 @@ static int launch_group(dq_ising* p, Plan* pl, const KetDesc* d_kets, int n_kets
     A.inv_group = group > 1 ? ~0ull / (unsigned long long)group + 1ull : 0ull;
     A.inv_pass = max_pass > 1 ? ~0ull / (unsigned long long)max_pass + 1ull : 0ull;
     A.tiles_log2 = pl->tiles_log2;
-    pl->sub_log2 = std::min(std::max(0, p->item_tiles_log2), pl->tiles_log2);
+    // multi-tile work items exist in the straight-line kernel only (measured slower, kept as an experiment switch)
+    pl->sub_log2 = scaled ? 0 : std::min(std::max(0, p->item_tiles_log2), pl->tiles_log2);
     A.sub_log2 = pl->sub_log2;
     A.ipp_log2 = pl->tiles_log2 - pl->sub_log2;
     const double alpha = atan(r);
     A.r = r; A.ca = cos(alpha); A.sa = sin(alpha); A.c2a = cos(2 * alpha); A.s2a = sin(2 * alpha);
+    A.rtau = r / (1.0 + r * r);
     A.geom[0] = pl->types[0].g;
     A.geom[1] = pl->types[1].g;
     const long long all_items = ((long long)(group * n_groups) << A.ipp_log2) * max_pass;
@@ -1454,15 +1951,17 @@ static int launch_group(dq_ising* p, Plan* pl, const KetDesc* d_kets, int n_kets
         }
         DQ_CUDA(cudaEventRecord(pl->ev[pl->ev_used], st));
     }
-#define DQ_LAUNCH(S, J, C) k_fused_passes<S, J, C><<<(unsigned)grid, kThreads, pl->smem_bytes, st>>>(A)
+#define DQ_LAUNCH(J, C) k_fused_passes<false, J, C><<<(unsigned)grid, kThreads, pl->smem_bytes, st>>>(A)
+#define DQ_LAUNCH_LIFT(J, C) k_fused_ws<J, C><<<(unsigned)grid, kWsThreads, pl->ws_smem_bytes, st>>>(A)
     const bool cross = p->linear != 0;
-    if (scaled) {
-        if (pl->has_aj) { if (cross) DQ_LAUNCH(true, true, true); else DQ_LAUNCH(true, true, false); }
-        else { if (cross) DQ_LAUNCH(true, false, true); else DQ_LAUNCH(true, false, false); }
-    } else {
-        if (pl->has_aj) { if (cross) DQ_LAUNCH(false, true, true); else DQ_LAUNCH(false, true, false); }
-        else { if (cross) DQ_LAUNCH(false, false, true); else DQ_LAUNCH(false, false, false); }
+    if (scaled) {                           // |angle| <= 1 everywhere: loop-form kernel (lifting butterflies)
+        if (pl->has_aj) { if (cross) DQ_LAUNCH_LIFT(true, true); else DQ_LAUNCH_LIFT(true, false); }
+        else { if (cross) DQ_LAUNCH_LIFT(false, true); else DQ_LAUNCH_LIFT(false, false); }
+    } else {                                // large angles: straight-line (cos, sin) body
+        if (pl->has_aj) { if (cross) DQ_LAUNCH(true, true); else DQ_LAUNCH(true, false); }
+        else { if (cross) DQ_LAUNCH(false, true); else DQ_LAUNCH(false, false); }
     }
+#undef DQ_LAUNCH_LIFT
 #undef DQ_LAUNCH
     p->ctx->launches++;
     if (timed) {
@@ -1795,3 +2294,4 @@ int fused_grad_run(dq_ising* p) {
 }
 
 }  // namespace dq
+#endif  // DQ_PROBE_ONLY
