@@ -50,13 +50,14 @@ struct dq_ising {
 };
 
 namespace dq {
-// States co-resident per fused launch: as many as keep the work ring inside ~80 MiB of the 126 MB L2
-// (5 x 16 MiB measured best at n = 20), at least 5, at most 96 (small states need many kets to fill 148 SMs).
+// States co-resident per fused launch: as many as keep the work ring inside ~72 MiB of the 126 MB L2
+// (measured with the warp-specialised kernel: 4 x 16 MiB best at n = 20 -- 72.3 vs 70.0 / 69.9 samples/s for 3 / 5 --,
+// 16-20 at n = 18, 80-96 at n = 16), at least 4, at most 96 (small states need many kets to fill 148 SMs).
 inline int auto_ket_group(const dq_ising* p) {
     if (p->ket_group > 0) return p->ket_group > 96 ? 96 : p->ket_group;
     const size_t state_bytes = sizeof(double2) << p->n;
-    const size_t g = ((size_t)80 << 20) / state_bytes;
-    return (int)(g < 5 ? 5 : (g > 96 ? 96 : g));
+    const size_t g = ((size_t)72 << 20) / state_bytes;
+    return (int)(g < 4 ? 4 : (g > 96 ? 96 : g));
 }
 // one shifted ket of the estimator: exp(sign * i * atan(r) * P), P = Z_b0 Z_b1 (kind 0) or X_b0 (kind 1)
 struct ShiftDesc { int kind; int b0; int b1; double sign; };

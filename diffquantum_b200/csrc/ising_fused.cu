@@ -1060,7 +1060,8 @@ __global__ void __launch_bounds__(kThreads, DQ_CTAS_PER_SM) k_fused_passes(const
 struct WsSlot {                     // one per tile buffer; written by the loader before `full` completes
     int p, g, t_id, grp;
     int stop;                       // 1: no more tiles for the team that receives this buffer
-    int pad_[3];
+    unsigned item;                  // raw work-item index (DQ_TRACE builds index the trace with it)
+    int pad_[2];
     double2 tc[4];                  // base-phase column entries of this tile (bulk-copied from the column table)
 };
 struct WsShared {
@@ -1068,6 +1069,7 @@ struct WsShared {
     WsSlot slot[kBufs];
     double red[kBufs][kTeamThreads / 32];
     double red2[kBufs][kTeamThreads / 32];
+    unsigned math_lock[kTeamThreads / 32];      // see math_acquire
 };
 constexpr int kWsThreads = 384;
 constexpr int kWsConsumerRegs = 232, kWsProducerRegs = 40;     // 2 x 128 x 232 + 128 x 40 = 64512 <= 65536
@@ -1087,12 +1089,36 @@ __device__ __forceinline__ void bulk_copy_g2s(void* dst, const void* src, unsign
 }
 template <int N> __device__ __forceinline__ void bulk_wait_group() { asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory"); }
 
+// Warp i of team 0 and warp i of team 1 sit on the same SM sub-partition and share its FP64 pipe (one DFMA per two
+// cycles: a single warp saturates it) and, with the other six warps, the shared-memory pipe.  Left alone, the two fall
+// into a convoy -- both in their butterfly runs at half speed each, then both in their shared-memory exchanges -- and
+// neither pipe is ever busy while the other is: measured 44 % FP64 and 47 % LSU, i.e. no overlap at all.  The lock below
+// makes the math sections of the two warps mutually exclusive: whoever gets there second waits, runs alone at full
+// speed afterwards, and from then on is in its exchange while the other one computes.
+#ifndef DQ_MATH_LOCK
+#define DQ_MATH_LOCK 0
+#endif
+__device__ __forceinline__ void math_acquire(WsShared& ws, int w) {
+    if ((threadIdx.x & 31) == 0)
+        while (atomicCAS(&ws.math_lock[w], 0u, 1u) != 0u) __nanosleep(32);
+    __syncwarp();
+}
+__device__ __forceinline__ void math_release(WsShared& ws, int w) {
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0) atomicExch(&ws.math_lock[w], 0u);
+}
+
 // The tile body of a consumer team: everything between "the buffer is full" and "the result is back in the buffer".
 // ONE body serves both pass types: the type is a run-time value, and only the small blocks that move amplitudes between
 // registers and shared memory are written out per type (their slot offsets are compile-time constants of Geo<>); the
 // butterfly run, the phase and the energy reduction exist once.  (Two fully inlined per-type bodies behind one branch
 // made ptxas spill; this form does not, and it is half the code.)
 #define DQ_FOR_REGS(stmt) _Pragma("unroll") for (int j = 0; j < kRegs; ++j) { stmt; }
+#if DQ_TRACE
+#define WS_TRACE(A, item, slot) do { if ((threadIdx.x & 31) == 0 && (A).trace) (A).trace[(size_t)(item) * 48 + ((threadIdx.x >> 5) & 3) * 8 + (slot)] = clock64(); } while (0)
+#else
+#define WS_TRACE(A, item, slot) do { } while (0)
+#endif
 template <bool AJ, bool CROSS>
 __device__ __forceinline__ void ws_tile(const LaunchArgs& A, WsShared& ws, const KetDesc* __restrict__ skets,
                                         PassStep& P, c128* __restrict__ tile, const int b, const int team) {
@@ -1221,9 +1247,9 @@ __device__ __forceinline__ void ws_tile(const LaunchArgs& A, WsShared& ws, const
             }
         } else {
             // ---- J -> K exchange --------------------------------------------------------------------------
-            if (type == 0) {
+            if (type == 0) {                     // L: warp-local again (the warp owns t10, t11 in both rounds)
                 DQ_FOR_REGS(tile[slot(sJ, G0::regJ(j))] = v[j])
-                team_sync(team);
+                __syncwarp();
                 DQ_FOR_REGS(v[j] = tile[slot(sK, G0::regK(j))])
             } else {
                 DQ_FOR_REGS(tile[slot(sJ, G1::regJ(j))] = v[j])
@@ -1231,7 +1257,18 @@ __device__ __forceinline__ void ws_tile(const LaunchArgs& A, WsShared& ws, const
                 DQ_FOR_REGS(v[j] = tile[slot(sK, G1::regK(j))])
             }
         }
+#if DQ_MATH_LOCK
+        if (r != 2) math_acquire(ws, tid >> 5);      // r == 2 still holds it from the J1 run (J1, phase, J2 are one math section)
+#endif
+        if (r == 1) WS_TRACE(A, S.item, 3);
+        if (r == 3) WS_TRACE(A, S.item, 5);
         lift_run(v, P.rot[r]);
+        if (r == 0) WS_TRACE(A, S.item, 2);
+        if (r == 2) WS_TRACE(A, S.item, 4);
+        if (r == 3) WS_TRACE(A, S.item, 6);
+#if DQ_MATH_LOCK
+        if (r != 1) math_release(ws, tid >> 5);
+#endif
     }
     {
         const int flags = P.flags;
@@ -1292,6 +1329,7 @@ __global__ void __launch_bounds__(kWsThreads, 1) k_fused_ws(const __grid_constan
             mbar_init(&ws.done[b], kTeamThreads);
             mbar_init(&ws.empty[b], 1);
         }
+        for (int w = 0; w < kTeamThreads / 32; ++w) ws.math_lock[w] = 0u;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     {
@@ -1309,6 +1347,9 @@ __global__ void __launch_bounds__(kWsThreads, 1) k_fused_ws(const __grid_constan
         const int team = wg;
         for (unsigned k = (unsigned)team;; k += kTeams) {
             const int b = (int)(k % kBufs);
+#if DQ_TRACE
+            const long long t_top = clock64();
+#endif
             mbar_wait(&ws.full[b], (k / kBufs) & 1u);
             if (ws.slot[b].stop) {
                 mbar_arrive(&ws.done[b]);         // the storer sees the stop in tile order
@@ -1316,8 +1357,17 @@ __global__ void __launch_bounds__(kWsThreads, 1) k_fused_ws(const __grid_constan
             }
             PassStep& P = tables[b];
             c128* tile = tiles + (size_t)b * kTile;
+#if DQ_TRACE
+            if ((threadIdx.x & 31) == 0 && A.trace) {
+                long long* tr = A.trace + (size_t)ws.slot[b].item * 48;
+                tr[((threadIdx.x >> 5) & 3) * 8 + 0] = t_top;
+                tr[((threadIdx.x >> 5) & 3) * 8 + 1] = clock64();
+                if ((threadIdx.x & 127) == 0) { tr[32 + 2] = P.type; tr[32 + 6] = blockIdx.x * kTeams + team + 1; tr[32 + 7] = ws.slot[b].p; }
+            }
+#endif
             ws_tile<AJ, CROSS>(A, ws, skets, P, tile, b, team);
             mbar_arrive(&ws.done[b]);             // release: this thread's tile writes (fenced for the async proxy) and partials
+            WS_TRACE(A, ws.slot[b].item, 7);
         }
     } else {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kWsProducerRegs));
@@ -1339,6 +1389,13 @@ __global__ void __launch_bounds__(kWsThreads, 1) k_fused_ws(const __grid_constan
                     }
                 }
                 const int b = (int)(k % kBufs);
+                // first poll of the item's dependency BEFORE the buffer wait: its L2 round trip overlaps the time the buffer
+                // is still busy instead of adding to the buffer's turn-around (relaxed, see ld_relaxed: what depends on the
+                // value is the TMA load below, which reads L2)
+                int ctr = 0;
+                unsigned need = 0, seen = 0;
+                const bool dep = have && item_dependency(A, skets, I.p, I.g, ctr, need);
+                if (dep) seen = ld_relaxed(&A.counters[ctr]);
                 if (k >= kBufs) mbar_wait(&ws.empty[b], ((k / kBufs) - 1u) & 1u);   // the store of tile k - 3 has read the buffer
                 WsSlot& S = ws.slot[b];
                 if (!have) {                      // out of work: one stop per team, then done
@@ -1347,18 +1404,15 @@ __global__ void __launch_bounds__(kWsThreads, 1) k_fused_ws(const __grid_constan
                     if (++stops == kTeams) break;
                     continue;
                 }
-                int ctr;
-                unsigned need;
-                if (item_dependency(A, skets, I.p, I.g, ctr, need)) {
-                    // relaxed poll (see ld_relaxed): what depends on it is the TMA load below, which reads L2
+                if (dep && seen < need)
                     while (ld_relaxed(&A.counters[ctr]) < need) __nanosleep(20);
-                }
                 const KetDesc* __restrict__ kd = skets + I.g;
                 const PassStep* ps = kd->steps + I.p;
                 S.p = I.p;
                 S.g = I.g;
                 S.t_id = I.t_id;
                 S.grp = I.grp;
+                S.item = I.item;
                 S.stop = 0;
                 const int type = (I.p + kd->cls) & 1;
                 const CUtensorMap* map = A.maps + 2 * (I.p == 0 ? kd->map_src : kd->map_buf) + type;

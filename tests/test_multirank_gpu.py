@@ -145,4 +145,4 @@ def test_distributed_state_cuda_vs_oracle(world, n):
 
 @pytest.mark.parametrize("world", [2, 4, 8])
 def test_sharded_per_sample_gradients_bit_equal_to_one_rank(world):
-    _spawn(_grad_worker, world, 13)
+    _spawn(_grad_worker, world, 14)
