@@ -3,8 +3,14 @@
 (BASELINE.json configs[3]: random 3-regular MaxCut, n=20, per_step=10 as shipped, T=2, B-spline
 basis with 6 coefficients per control, 50 controls -> 1 + 100 trajectories per sample).
 
-  python bench.py [--gpus N] [--steps K] [--warmup W]            our arm (CUDA, sm_100a)
+  python bench.py [--gpus N] [--steps K] [--warmup W]            our arm (CUDA, sm_100a), BASELINE configs[3] (the headline)
   python bench.py --impl reference [...]                          reference arm (CPU, host cores)
+  python bench.py --config {0,1,2,4} [...]                        the other BASELINE configs, same JSON contract:
+      0  demo_maxcut.py as shipped (n=4, 202 epochs)              metric: training epochs/s
+      1  H2 VQE, 4 qubits, 4096 batched samples (dense path)      metric: gradient samples/s
+      2  n=16 MaxCut, 1024 Trotter steps, 1024 samples            metric: gradient samples/s
+      4  one oversize state split on its high qubits (n=32 at 8 GPUs, 29 + log2 N below)   metric: product-formula steps/s
+  python bench.py --scaling strong [...]                          configs[3] with the GLOBAL batch fixed (64 samples per step)
 
 A "step" is one batch of --samples-per-step gradient samples PER GPU (weak scaling): the sample
 times of step i are the reference's own stream, np.random.seed(i); np.random.uniform(size=B*N)*T
@@ -44,8 +50,22 @@ def emit_json(line):
     out.flush()
 
 
-METRIC = "gradient samples/s at n=20 MaxCut"
+METRIC = "gradient samples/s at n=20 MaxCut"        # configs[3], the headline; the other configs name theirs (metric_of)
 UNIT = "samples/s"
+
+
+def metric_of(a):
+    if a.config == 0:
+        return "training epochs/s, demo_maxcut.py as shipped (n=4, 202 epochs)", "epochs/s"
+    if a.config == 1:
+        return "gradient samples/s, H2 VQE 4 qubits (dense path)", "samples/s"
+    if a.config == 2:
+        return "gradient samples/s at n=16 MaxCut, 1024 Trotter steps", "samples/s"
+    if a.config == 4:
+        return "product-formula steps/s of one state split over the GPUs on its high qubits", "steps/s"
+    return (METRIC if a.n == 20 else "gradient samples/s at n=%d MaxCut" % a.n), UNIT
+
+
 FALLBACK_HBM_GBS = 6650.0          # /opt/skills/guides/B200_PROFILING.md, used only without MEASURED_PEAKS.json
 
 
@@ -55,16 +75,30 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--n", type=int, default=20)
-    ap.add_argument("--per-step", type=int, default=10)
-    ap.add_argument("--samples-per-step", type=int, default=8, help="gradient samples per GPU per step")
+    ap.add_argument("--config", type=int, default=3, choices=[0, 1, 2, 3, 4], help="index into BASELINE.json configs")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="configs[2,3]: weak = --samples-per-step per GPU; strong = the same GLOBAL batch at every N")
+    ap.add_argument("--n", type=int, default=None)
+    ap.add_argument("--per-step", type=int, default=None)
+    ap.add_argument("--samples-per-step", type=int, default=None,
+                    help="gradient samples per GPU per step (strong scaling: per step over all GPUs)")
     ap.add_argument("--cpu-terms", type=int, default=6,
                     help="controls whose +/- trajectories the bounded CPU sample runs (of n_Hs)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--ket-group", type=int, default=0)
     ap.add_argument("--item-tiles-log2", type=int, default=-1, help="fused v2: tiles per work item = 2^k (default: library default)")
     ap.add_argument("--engine", type=int, default=1, help="1 = the fused pass engine (the only product engine at n=20)")
-    return ap.parse_args()
+    a = ap.parse_args()
+    # per-config defaults: config 2 = omega 2 pi -> T = 1, per_step 512 -> 1024 steps per full evolution
+    dflt = {3: dict(n=20, per_step=10, sps=8), 2: dict(n=16, per_step=512, sps=128), 1: dict(n=4, per_step=10, sps=4096),
+            0: dict(n=4, per_step=10, sps=1), 4: dict(n=None, per_step=10, sps=1)}[a.config]
+    if a.n is None:
+        a.n = dflt["n"]
+    if a.per_step is None:
+        a.per_step = dflt["per_step"]
+    if a.samples_per_step is None:
+        a.samples_per_step = dflt["sps"] * (8 if (a.scaling == "strong" and a.config == 3) else 1)
+    return a
 
 
 # ---------------------------------------------------------------------------------------------
@@ -77,6 +111,16 @@ def workload(n):
     n_H = len(edges) + n
     coeff = np.random.default_rng(0).normal(0, 1, [n_H, 6])
     return edges, coeff
+
+
+def omega_of(a):
+    """configs[2]: omega = 2 pi -> T = 1.0 (1024 steps at per_step 512); configs[3]: omega = pi -> T = 2.0 as shipped."""
+    return 2 * np.pi if a.config == 2 else np.pi
+
+
+def per_gpu_samples(a, world):
+    """samples each rank sees per step: fixed per GPU (weak) or the global batch split over the ranks (strong)."""
+    return a.samples_per_step if a.scaling == "weak" else max(1, a.samples_per_step // world)
 
 
 def step_samples(step, per_gpu, world, T):
@@ -163,12 +207,12 @@ class ClockSampler(object):
 # ---------------------------------------------------------------------------------------------
 # CPU arm: plain-C OpenMP port of the reference step + estimator (oracle/c), bounded sample
 # ---------------------------------------------------------------------------------------------
-def cpu_bounded_sample(n, per_step, coeff, edges, s, n_terms):
+def cpu_bounded_sample(n, per_step, coeff, edges, s, n_terms, omega=np.pi):
     from oracle import c_port as C, restate as R
     if not C.available():
         raise RuntimeError("oracle/c/liboracle_c.so missing: run __graft_entry__.build()")
     C.use_host_cores()                      # torchrun exports OMP_NUM_THREADS=1; the CPU arm uses every host core
-    prob = R.maxcut_structured(n, edges)
+    prob = R.maxcut_structured(n, edges, omega0=omega, omega1=omega)
     cp = C.CProblem(prob)
     n_H = len(prob["terms"])
     # one ZZ control and one X control first, then alternate, so the sample sees both gate kinds
@@ -192,13 +236,19 @@ def run_reference_arm(a):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
+    if a.config in (0, 1):
+        return run_reference_dense(a)
+    if a.config == 4:
+        print(json.dumps({"impl": "reference", "unavailable": "configs[4] (n >= 29 per GPU, 64 GiB at n=32) has no CPU "
+                          "reference: the state does not fit the host and the reference's dense operators stop at n~13 (SURVEY H2)"}))
+        return 0
     edges, coeff = workload(a.n)
-    T = 2.0
+    T = np.pi * 2.0 / omega_of(a)
     vals, last = [], None
     for i in range(a.warmup + a.steps):
         # warm-up steps use a reduced sample (page-in, OpenMP pool start-up); timed ones the bounded sample
         s = step_samples(i, a.samples_per_step, 1, T)[0]
-        r = cpu_bounded_sample(a.n, a.per_step, coeff, edges, s, 1 if i < a.warmup else a.cpu_terms)
+        r = cpu_bounded_sample(a.n, a.per_step, coeff, edges, s, 1 if i < a.warmup else (a.cpu_terms if a.config == 3 else 2), omega_of(a))
         if i >= a.warmup:
             vals.append(r)
             last = r
@@ -209,11 +259,12 @@ def run_reference_arm(a):
     sample = ("per step: 1 prefix + the +/- trajectories of %d of %d controls of one sample (%d of ~%d "
               "trajectory-steps), scaled by steps" % (last["n_terms"], last["n_H"], last["steps"], last["full_steps"]))
     line = {
-        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
-        "warmup": a.warmup, "ms_per_step": 1e3 * tot_sec / a.steps, "higher_is_better": True, "scaling": "weak",
+        "impl": "reference", "metric": metric_of(a)[0], "value": v, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
+        "warmup": a.warmup, "ms_per_step": 1e3 * tot_sec / a.steps, "higher_is_better": True, "scaling": a.scaling,
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": workload_config(a, 1),
-        "cpu_baseline": {"value": v, "unit": UNIT, "cores": last["cores"], "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": last["cores"], "kind": "port", "sample": sample,
+                         "build": "gcc -O3 -march=native -fopenmp (oracle/c/Makefile), rebuilt on this host"},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
         "note": "reference's own dense code cannot build n=20 operators (SURVEY F3); this is the plain-C OpenMP port "
@@ -224,11 +275,396 @@ def run_reference_arm(a):
 
 
 def workload_config(a, world):
-    return {"workload": "configs[3]: random 3-regular MaxCut n=%d (networkx seed 0), per_step=%d, T=2.0, "
-                        "n_basis=6 BSpline, 1+2*n_Hs trajectories per sample" % (a.n, a.per_step),
-            "samples_per_step_per_gpu": a.samples_per_step, "global_samples_per_step": a.samples_per_step * world,
+    T = np.pi * 2.0 / omega_of(a)
+    per_gpu = per_gpu_samples(a, world)
+    full = {3: "8192 gradient samples", 2: "1024 gradient samples"}[a.config]
+    return {"workload": "configs[%d]: random 3-regular MaxCut n=%d (networkx seed 0), per_step=%d, T=%.1f (%d steps per full "
+                        "evolution), n_basis=6 BSpline, 1+2*n_Hs trajectories per sample" % (
+                            a.config, a.n, a.per_step, T, int(a.per_step * (T + 1))),
+            "samples_per_step_per_gpu": per_gpu, "global_samples_per_step": per_gpu * world,
+            "samples_timed": per_gpu * world * a.steps,
+            "of_the_configs_batch": "%s in BASELINE.json; samples are independent and identically distributed in cost, so the "
+                                    "timed subset measures the same per-sample work" % full,
             "parallelism": "sample-sharded x%d (cost-balanced shards), one all-reduce of the gradient per step" % world,
             "l2": "L2 flushed (512 MiB write) between timed steps"}
+
+
+# ---------------------------------------------------------------------------------------------
+# shared plumbing for the other configs
+# ---------------------------------------------------------------------------------------------
+class Ranks(object):
+    """torch.distributed bring-up as the driver launches it (RANK / LOCAL_RANK / WORLD_SIZE / MASTER_* in the env)."""
+
+    def __init__(self):
+        import torch
+        self.torch = torch
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        if not torch.cuda.is_available():
+            raise RuntimeError("bench.py: no CUDA device (there is no CPU fallback; use --impl reference for the CPU arm)")
+        torch.cuda.set_device(self.local)
+        self.dev = torch.device("cuda", self.local)
+        if self.world > 1:
+            import torch.distributed as dist
+            os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+            global _JSON_OUT
+            sys.stdout.flush()
+            _JSON_OUT = os.fdopen(os.dup(1), "w")        # NCCL prints its banner to fd 1: keep the JSON line apart
+            os.dup2(2, 1)
+            dist.init_process_group("nccl", device_id=self.dev)
+
+    def barrier(self):
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.barrier(device_ids=[self.local])
+        self.torch.cuda.synchronize(self.dev)
+
+    def reduce(self, x, op="max"):
+        if self.world == 1:
+            return float(x)
+        import torch.distributed as dist
+        t = self.torch.tensor([float(x)], dtype=self.torch.float64, device=self.dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX if op == "max" else dist.ReduceOp.SUM)
+        return float(t.item())
+
+    def close(self):
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.destroy_process_group()
+
+
+def golden(name):
+    return np.load(os.path.join(ROOT, "tests", "golden", name + ".npz"), allow_pickle=False)
+
+
+def fp64_peak_tflops(ctx):
+    """FP64 FMA rate of this GPU, measured now (dq_microbench kind 1: 8 x 256 threads per SM of dependent-free DFMA)."""
+    try:
+        return float(ctx.microbench(1, iters=4000)), "measured now (dq_microbench: DFMA issue rate, 2 flops per FMA)"
+    except Exception as e:           # pragma: no cover
+        return 36.0, "fallback 36 TFLOP/s (round-1 measurement); microbench failed: %s" % e
+
+
+# ---------------------------------------------------------------------------------------------
+# configs[0] and configs[1]: the dense path (dim = 16)
+# ---------------------------------------------------------------------------------------------
+def dense_problem(a):
+    g = golden("demo_training_ref" if a.config == 0 else "h2_vqe_ref")
+    M = g["H_cost"] if a.config == 0 else g["M"]
+    coeff = None if a.config == 0 else g["coeff"]
+    return dict(H0=g["H0"], Hs=g["Hs"], M=M, psi0=g["psi0"], omegas=g["omegas"], T=float(g["T"]), coeff=coeff, g=g)
+
+
+def dense_ket_steps(s_list, T, per_step, n_H):
+    pre = (per_step * (s_list + 1)).astype(np.int64)
+    suf = (per_step * ((T - s_list) + 1)).astype(np.int64)
+    return int(pre.sum() + 2 * n_H * suf.sum())
+
+
+def _cpu_dense_samples(args):
+    """Worker of the CPU arm of configs[1]: the oracle's restatement of compute_energy_grad_MC (sim_plain.py:156-231)."""
+    os.environ["OMP_NUM_THREADS"] = "1"
+    from oracle import restate as R
+    P, s_list, per_step = args
+    t0 = time.perf_counter()
+    for s in s_list:
+        R.grad_mc_dense(P["H0"], list(P["Hs"]), P["M"], P["psi0"], P["coeff"], P["omegas"], P["T"], float(s), per_step)
+    return time.perf_counter() - t0
+
+
+def cpu_dense_rate(P, per_step, n_workers, per_worker):
+    """samples/s of the CPU oracle over n_workers processes (one thread each), per_worker samples per process."""
+    import multiprocessing as mp
+    P = {k: v for k, v in P.items() if k != "g"}
+    rng = np.random.RandomState(123)
+    jobs = [(P, rng.uniform(size=per_worker) * P["T"], per_step) for _ in range(n_workers)]
+    t0 = time.perf_counter()
+    if n_workers == 1:
+        _cpu_dense_samples(jobs[0])
+    else:
+        with mp.get_context("spawn").Pool(n_workers) as pool:
+            pool.map(_cpu_dense_samples, jobs)
+    return n_workers * per_worker / (time.perf_counter() - t0)
+
+
+def _cpu_demo_epochs(P, per_step, n_epoch):
+    """The reference's training loop (sim_plain.py:245-305) restated on the CPU oracle; seconds per epoch."""
+    import torch
+    from oracle import restate as R
+    np.random.seed(0)
+    n_H = len(P["Hs"])
+    coeff = torch.tensor(np.random.normal(0, 1e-3, [n_H, 6]), requires_grad=True)
+    opt = torch.optim.Adam([coeff], lr=2e-2)
+    t0 = time.perf_counter()
+    for _ in range(n_epoch):
+        c = coeff.detach().numpy().copy()
+        R.trotter_plain(P["H0"], list(P["Hs"]), c, P["omegas"], P["T"], P["psi0"], 0, P["T"], per_step)
+        s = np.random.uniform() * P["T"]
+        g = R.grad_mc_dense(P["H0"], list(P["Hs"]), P["M"], P["psi0"], c, P["omegas"], P["T"], s, per_step)
+        opt.zero_grad()
+        coeff.grad = torch.from_numpy(g)
+        opt.step()
+        np.linalg.eigvalsh(P["M"])                # M.eigenenergies() every epoch, sim_plain.py:294
+    return (time.perf_counter() - t0) / n_epoch
+
+
+def run_reference_dense(a):
+    if int(os.environ.get("RANK", "0")) != 0:
+        return 0
+    P = dense_problem(a)
+    metric, unit = metric_of(a)
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    vals = []
+    for i in range(a.warmup + a.steps):
+        if a.config == 1:
+            v = cpu_dense_rate(P, a.per_step, cores, 2 if i < a.warmup else 6)
+            sample = "%d processes x 6 samples of the 4096 (oracle restatement of compute_energy_grad_MC, one thread each)" % cores
+            used = cores
+        else:
+            v = 1.0 / _cpu_demo_epochs(P, a.per_step, 3 if i < a.warmup else 12)
+            sample = "12 of the 202 epochs (restated train_energy loop: full evolution + one gradient sample + Adam + eigvalsh)"
+            used = 1
+        if i >= a.warmup:
+            vals.append(v)
+    v = float(np.mean(vals))
+    line = {"impl": "reference", "metric": metric, "value": v, "unit": unit, "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
+            "ms_per_step": None, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": dense_config(a, 1), "cpu_baseline": {"value": v, "unit": unit, "cores": used, "kind": "port", "sample": sample},
+            "e2e": {"value": v, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0,
+            "note": "NumPy/SciPy restatement of the reference's dense path (oracle/restate.py, pinned to the reference's own "
+                    "outputs); the reference tree itself does not travel to the GPU box"}
+    print(json.dumps(line))
+    return 0
+
+
+def dense_config(a, world):
+    if a.config == 0:
+        return {"workload": "configs[0]: demo_maxcut.py as shipped -- 4-qubit ring MaxCut, 8 controls, n_basis=6 BSpline, per_step=10, "
+                            "202 epochs of (full evolution + energy + one stochastic gradient sample + Adam), np.random.seed(0)",
+                "parallelism": "replicas x%d (the dense path does not shard: SURVEY 8e)" % world,
+                "l2": "working set < 1 MB: L2 residency is the design, nothing to flush"}
+    return {"workload": "configs[1]: H2 VQE, 4 qubits (dim 16), 8 controls (X_q, Y_q), n_basis=6 BSpline, per_step=10, T=1.5, "
+                        "%d batched parameter-shift samples per step (1 + 16 trajectories each)" % a.samples_per_step,
+            "samples_per_step_per_gpu": a.samples_per_step, "global_samples_per_step": a.samples_per_step * world,
+            "parallelism": "replicas x%d (the dense path does not shard: SURVEY 8e)" % world,
+            "l2": "working set (pulse tables + 17 kets per sample) < L2 by design; FP64-bound, not HBM-bound"}
+
+
+def run_dense_config(a):
+    import diffquantum_b200 as dq
+    R_ = Ranks()
+    P = dense_problem(a)
+    metric, unit = metric_of(a)
+    sim = dq.DenseSimulator(P["H0"], P["Hs"], P["omegas"], P["T"], M=P["M"], psi0=P["psi0"], per_step=a.per_step, device=R_.local)
+    n_H = sim.n_H
+    sampler = ClockSampler(R_.local)
+    dev_s, e2e_s, flops, launches, h2d, d2h = [], [], 0.0, 0, 0, 0
+    parity = None
+    t_start = time.time()
+    for i in range(a.warmup + a.steps):
+        timed = i >= a.warmup
+        if i == a.warmup:
+            R_.barrier()
+            t_start = time.time()
+        l0 = sim.ctx.launch_count
+        if a.config == 1:
+            np.random.seed(i)
+            s_list = np.random.uniform(size=a.samples_per_step) * sim.T
+            R_.barrier()
+            t0 = time.perf_counter()
+            grads, en = sim.grad_samples(P["coeff"], s_list, return_energies=True)
+            dt = time.perf_counter() - t0
+            units = len(s_list)
+            kms = sim.stat("kernel_ms")
+            steps_i = dense_ket_steps(s_list, sim.T, a.per_step, n_H)
+            fl = steps_i * sim.stat("degree") * (2.0 ** sim.stat("squarings")) * 8.0 * sim.dim * sim.dim
+            bi = ((a.per_step * (s_list + 1)).astype(int).sum() + (a.per_step * (sim.T - s_list + 1)).astype(int).sum()) * n_H * 8
+            bo = en.nbytes
+        else:
+            np.random.seed(0)
+            tr = dq.EnergyTrainer(sim, n_basis=6, n_epoch=202, lr=2e-2)
+            R_.barrier()
+            t0 = time.perf_counter()
+            tr.train_energy()
+            dt = time.perf_counter() - t0
+            units = 202
+            kms = getattr(tr, "device_ms", 0.0) or dt * 1e3
+            fl, bi, bo = 0.0, 0, 0
+            if timed:
+                ref = P["g"]["losses_energy"]
+                parity = {"max_abs_loss_diff": float(np.abs(np.array(tr.losses_energy) - ref).max()), "tol": 1e-8,
+                          "what": "202-epoch loss_energy trajectory vs the reference's own demo_maxcut.py run (tests/golden/"
+                                  "demo_training_ref.npz, np.random.seed(0))", "cut": bin(tr.find_state()[0])[2:]}
+                parity["ok"] = bool(parity["max_abs_loss_diff"] < 1e-8)
+        if timed:
+            dev_s.append(kms * 1e-3)
+            e2e_s.append(dt)
+            flops += fl
+            launches += sim.ctx.launch_count - l0
+            h2d, d2h = int(bi), int(bo)
+    R_.barrier()
+    window = (t_start, time.time())
+    t_dev = R_.reduce(sum(dev_s))
+    t_e2e = R_.reduce(sum(e2e_s))
+    total = units * a.steps * R_.world
+    if a.config == 1:
+        from oracle import restate as R
+        e_ref = R.grad_mc_dense(P["H0"], list(P["Hs"]), P["M"], P["psi0"], P["coeff"], P["omegas"], P["T"], float(s_list[0]),
+                                a.per_step, return_energies=True)[1]
+        err = float(np.abs(en[0] - e_ref).max() / np.abs(e_ref).max())
+        parity = {"max_rel_err": err, "tol": 1e-10, "ok": bool(err < 1e-10),
+                  "what": "shifted energies of sample 0 of the last step: CUDA (dq_dense_grad) vs the oracle's restatement of "
+                          "compute_energy_grad_MC (pinned to the reference's own run, tests/golden/h2_vqe_ref.npz)"}
+    if parity and not parity["ok"]:
+        raise SystemExit("bench.py: GPU result differs from the oracle: %r" % (parity,))
+    peak, peak_src = fp64_peak_tflops(sim.ctx)
+    ach = flops / t_dev / 1e12 if (flops and t_dev) else None
+    line = {"metric": metric, "value": total / t_dev, "unit": unit, "n_gpus": R_.world, "steps": a.steps, "warmup": a.warmup,
+            "ms_per_step": 1e3 * t_dev / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic", "config": dense_config(a, R_.world),
+            "e2e": {"value": total / t_e2e, "unit": unit, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": 1e3 * t_e2e / a.steps,
+                    "note": "public API with host buffers: host pulse tables + H2D + kernels + D2H + gradient assembly"},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "fp64", "kernel": "k_small (resident warp-per-trajectory engine)" if sim.stat("strategy") == 3 else "k_zgemm",
+                         "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": (ach / peak) if ach else None,
+                         "peak_source": peak_src, "traffic": None,
+                         "flops_note": "degree x 2^squarings complex 16x16 mat-vecs per ket-step, 8 real flops per complex MAC"},
+            "parity": parity, "clocks": sampler.window(*window)}
+    if a.config == 0:
+        line["value_note"] = ("device time = the sum of the event-timed kernel launches of the training run when the trainer is "
+                              "device-resident, else the wall time of the host-driven loop")
+    if R_.rank == 0 and R_.world == 1 and not a.no_cpu_baseline:
+        try:
+            if a.config == 1:
+                v = cpu_dense_rate(P, a.per_step, 1, 8)
+                line["cpu_baseline"] = {"value": v, "unit": unit, "cores": 1, "kind": "port",
+                                        "sample": "8 of the %d samples, oracle restatement of compute_energy_grad_MC on one core" % a.samples_per_step}
+            else:
+                v = 1.0 / _cpu_demo_epochs(P, a.per_step, 12)
+                line["cpu_baseline"] = {"value": v, "unit": unit, "cores": 1, "kind": "port",
+                                        "sample": "12 of the 202 epochs of the restated train_energy loop on one core"}
+        except Exception as e:
+            line["cpu_baseline"] = {"value": None, "unit": unit, "cores": 0, "kind": "port", "sample": "failed: %s" % e}
+    if R_.rank == 0:
+        emit_json(line)
+    R_.close()
+    return 0
+
+
+# ---------------------------------------------------------------------------------------------
+# configs[4]: one state split over the GPUs on its high qubits
+# ---------------------------------------------------------------------------------------------
+def run_distributed_state(a):
+    import diffquantum_b200 as dq
+    from diffquantum_b200 import distributed
+    import networkx as nx
+    R_ = Ranks()
+    torch = R_.torch
+    g_bits = R_.world.bit_length() - 1
+    n = a.n if a.n else 29 + g_bits                  # 8 GiB of complex128 per GPU: n = 32 at 8 GPUs
+    metric, unit = metric_of(a)
+
+    # ---- parity first, at a size the oracle can check (same code path, same world size) ----------------
+    from oracle import restate as R
+    n_small = 16
+    e_small = R.random_regular_edges(n_small, seed=n_small)
+    p_small = dq.IsingProblem.maxcut(n_small, e_small)
+    ref = R.maxcut_structured(n_small, e_small)
+    c_small = np.random.RandomState(n_small).normal(0, 1, [len(p_small.terms), 6])
+    st = distributed.DistributedState(p_small, device=R_.local, per_step=2)
+    st.fill_uniform()
+    st.evolve(c_small, 0.2, 1.7)
+    ns, dt_s, ts = R.step_grid(0.2, 1.7, 2)
+    want = R.evolve_split_structured(ref, R.coef_table_plain(c_small, ref["omegas"], ref["T"], ts), dt_s, ref["psi0"])
+    N_loc = 1 << (n_small - g_bits)
+    err = float(np.abs(st.local_slice() - want[R_.rank * N_loc:(R_.rank + 1) * N_loc]).max() / np.abs(want).max())
+    err = R_.reduce(err)
+    e_err = abs(st.energy() - R.energy_diag(ref["m_diag"], want))
+    parity = {"max_rel_err": err, "energy_abs_err": float(e_err), "tol": 1e-10, "ok": bool(err < 1e-10 and e_err < 1e-10),
+              "what": "DistributedState at n=%d over %d GPU(s), %d product-formula steps: every rank's slice and <M> vs the oracle "
+                      "(oracle/restate.py evolve_split_structured = diffqc.cc:155-164)" % (n_small, R_.world, ns)}
+    if not parity["ok"]:
+        raise SystemExit("bench.py: distributed state differs from the oracle: %r" % (parity,))
+    del st
+
+    # ---- the timed state ---------------------------------------------------------------------------------
+    if n % 2 == 0:
+        gr = nx.random_regular_graph(3, n, seed=0)
+        edges = sorted(tuple(sorted(e)) for e in gr.edges())
+    else:                                            # no 3-regular graph on an odd number of nodes: n-1 regular + one node of degree 3
+        gr = nx.random_regular_graph(3, n - 1, seed=0)
+        edges = sorted(tuple(sorted(e)) for e in gr.edges()) + [(0, n - 1), (1, n - 1), (2, n - 1)]
+    prob = dq.IsingProblem.maxcut(n, edges)
+    coeff = np.random.default_rng(0).normal(0, 1, [len(prob.terms), 6])
+    st = distributed.DistributedState(prob, device=R_.local, per_step=a.per_step)
+    st.fill_uniform()
+    rows = prob.trajectory_rows(coeff, 0.0, prob.T, a.per_step)
+    sampler = ClockSampler(R_.local)
+    k = 0
+    times = []
+    t_start = time.time()
+    l0 = st.ops.ctx.launch_count
+    x0, b0 = st.exchanges, st.exchanged_bytes
+    for i in range(a.warmup + a.steps):
+        if i == a.warmup:
+            t_start = time.time()
+            l0 = st.ops.ctx.launch_count
+            x0, b0 = st.exchanges, st.exchanged_bytes
+        st.ops.ctx.synchronize()
+        R_.barrier()
+        t0 = time.perf_counter()
+        st.step(rows[k % len(rows)])
+        st.ops.ctx.synchronize()
+        torch.cuda.synchronize(R_.dev)
+        dt = time.perf_counter() - t0
+        k += 1
+        if i >= a.warmup:
+            times.append(dt)
+    R_.barrier()
+    window = (t_start, time.time())
+    t_tot = R_.reduce(sum(times))
+    launches = st.ops.ctx.launch_count - l0
+    norm2 = st.norm2()
+    slice_bytes = 16.0 * (1 << st.L)
+    peak, peak_src = measured_peak()
+    passes = getattr(st, "last_passes", None)
+    exch_bytes = (st.exchanged_bytes - b0) / max(1, a.steps)
+    exch_ms = getattr(st, "exchange_ms", None)
+    ach = 2 * slice_bytes * a.steps / t_tot / 1e9
+    line = {"metric": metric, "value": a.steps / t_tot, "unit": unit, "n_gpus": R_.world, "steps": a.steps, "warmup": a.warmup,
+            "ms_per_step": 1e3 * t_tot / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
+            "config": {"workload": "configs[4]: one MaxCut state of n=%d qubits (random 3-regular graph, networkx seed 0), %.1f GiB of "
+                                   "complex128 per GPU, product-formula steps of the pulse trajectory (per_step=%d)" % (
+                                       n, slice_bytes / 2 ** 30, a.per_step),
+                       "parallelism": "state split on its %d high-order qubits over %d GPUs; one all-to-all per step" % (g_bits, R_.world),
+                       "l2": "slice (%.1f GiB) >> L2" % (slice_bytes / 2 ** 30)},
+            "e2e": {"value": a.steps / t_tot, "unit": unit, "h2d_bytes_per_step": int(rows.shape[1] * 8), "d2h_bytes_per_step": 8,
+                    "note": "the state lives on the devices by definition (64 GiB at n=32); per step the host sends one angle row; "
+                            "`value` and `e2e` are the same wall-clock measurement through DistributedState.step"},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "kernel": "k_slice_rx_tile / k_slice_phase_gray (whole step, exchange included)",
+                         "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "peak_source": peak_src, "traffic": None,
+                         "alg_bytes_per_step_per_gpu": 2 * slice_bytes,
+                         "passes_per_step": passes, "launches_per_step": launches / max(1, a.steps),
+                         "per_pass_GBs": (launches / max(1, a.steps)) * ach,
+                         "per_pass_note": "every launch of a step is one read + write of the slice (phase pass, rotation passes): "
+                                          "per-pass rate = launches per step x the per-step figure; an exchange lowers it",
+                         "exchange_GB_per_step_per_gpu": exch_bytes / 1e9,
+                         "exchange_GBs_per_gpu": (exch_bytes / (exch_ms * 1e-3) / 1e9) if exch_ms else None,
+                         "nvlink_peak_GBs": 900.0,
+                         "limiter": ("the all-to-all (%.1f GB per GPU per step over NVLink)" % (exch_bytes / 1e9)) if R_.world > 1 else
+                                    "HBM passes (no exchange on one GPU)"},
+            "parity": parity, "norm2_after": norm2, "clocks": sampler.window(*window),
+            "cpu_baseline": {"value": None, "unit": unit, "cores": 0, "kind": "port",
+                             "sample": "not runnable: a %d-qubit state is %.0f GiB; the reference's dense operators stop at n~13" % (
+                                 n, 16.0 * 2 ** n / 2 ** 30)}}
+    if R_.rank == 0:
+        emit_json(line)
+    R_.close()
+    return 0
 
 
 # ---------------------------------------------------------------------------------------------
@@ -281,8 +717,9 @@ def run_b200_arm(a):
         return float(t.item())
 
     edges, coeff = workload(a.n)
-    prob = dq.IsingProblem.maxcut(a.n, edges)
+    prob = dq.IsingProblem.maxcut(a.n, edges, omega0=omega_of(a), omega1=omega_of(a))
     sim = dq.IsingSimulator(prob, device=local, per_step=a.per_step, engine=a.engine)
+    per_gpu = per_gpu_samples(a, world)
     if a.ket_group:
         sim.set_option("ket_group", a.ket_group)
     if a.item_tiles_log2 >= 0:
@@ -297,7 +734,7 @@ def run_b200_arm(a):
     est = sharding.ShardedEstimator(lambda c, s: sim.grad_samples(c, s), device=dev, cost=cost)
 
     def my_samples(i):
-        return est.my_samples(step_samples(i, a.samples_per_step, world, prob.T))
+        return est.my_samples(step_samples(i, per_gpu, world, prob.T))
 
     # ---- value: tables staged in HBM, device-timed ----------------------------------------------
     def staged_loop(linear):
@@ -349,7 +786,7 @@ def run_b200_arm(a):
         per_rank = [{"rank": r, "device_ms": float(t[0]), "pass_kernel_ms": float(t[1]), "trajectory_steps": float(t[2]),
                      "launches": int(t[3])} for r, t in enumerate(allr)]
     t_value = max_over_ranks(sum(dev_ms) * 1e-3)
-    total_samples = a.samples_per_step * world * a.steps
+    total_samples = per_gpu * world * a.steps
     value = total_samples / t_value
     linear_leg = None
     if a.engine == 1:
@@ -371,7 +808,7 @@ def run_b200_arm(a):
     e2e_s = []
     for i in range(a.warmup + a.steps):
         timed = i >= a.warmup
-        s_all = step_samples(i, a.samples_per_step, world, prob.T)
+        s_all = step_samples(i, per_gpu, world, prob.T)
         flush.zero_()
         barrier()
         t0 = time.perf_counter()
@@ -414,8 +851,8 @@ def run_b200_arm(a):
                         "exceed DRAM GB/s; `traffic` is the ncu DRAM figure"}
 
     line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
-        "ms_per_step": 1e3 * t_value / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "metric": metric_of(a)[0], "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+        "ms_per_step": 1e3 * t_value / a.steps, "higher_is_better": True, "scaling": a.scaling, "vs_baseline": None,
         "dtype": "f64", "data": "synthetic", "config": workload_config(a, world),
         "trajectory_steps_per_s": sum_over_ranks(traj_steps) / t_value,
         "alg_GBs_whole_job": sum_over_ranks(alg_bytes) / t_value / 1e9,
@@ -444,9 +881,10 @@ def run_b200_arm(a):
         line["linear_estimator"] = linear_leg
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
         try:
-            s0 = step_samples(a.warmup, a.samples_per_step, 1, prob.T)[0]
-            cpu_bounded_sample(a.n, a.per_step, coeff, edges, s0, 1)            # warm the OpenMP pool / page in
-            r = cpu_bounded_sample(a.n, a.per_step, coeff, edges, s0, a.cpu_terms)
+            s0 = step_samples(a.warmup, per_gpu, 1, prob.T)[0]
+            n_cpu = a.cpu_terms if a.config == 3 else 1                           # configs[2]: ~1300 steps per trajectory
+            cpu_bounded_sample(a.n, a.per_step, coeff, edges, s0, 1, omega_of(a))  # warm the OpenMP pool / page in
+            r = cpu_bounded_sample(a.n, a.per_step, coeff, edges, s0, n_cpu, omega_of(a))
             # parity at the headline size (untimed): the CPU port's shifted energies of this very sample against the
             # GPU's, through the public API -- same graph, coefficients, sampled time, per_step as the timed steps
             gpu_en = sim.shifted_energies(coeff, [s0])[0][r["order"]]
@@ -459,6 +897,7 @@ def run_b200_arm(a):
                 raise SystemExit("bench.py: GPU energies differ from the CPU oracle: %r" % (line["parity"],))
             line["cpu_baseline"] = {
                 "value": r["samples_per_s"], "unit": UNIT, "cores": r["cores"], "kind": "port",
+                "build": "gcc -O3 -march=native -fopenmp (oracle/c/Makefile), rebuilt on this host",
                 "sample": "1 prefix + the +/- trajectories of %d of %d controls of one sample at s=%.4f (%d of %d "
                           "trajectory-steps, %.1f s), scaled by steps" % (r["n_terms"], r["n_H"], s0, r["steps"],
                                                                          r["full_steps"], r["seconds"])}
@@ -476,6 +915,10 @@ def main():
     a = parse_args()
     if a.impl == "reference":
         return run_reference_arm(a)
+    if a.config in (0, 1):
+        return run_dense_config(a)
+    if a.config == 4:
+        return run_distributed_state(a)
     return run_b200_arm(a)
 
 
