@@ -75,6 +75,7 @@ struct dq_context {
     dq::dense::State* dense = nullptr;     // dense-path state (diffqc.set_H globals + workspaces), lazily created
     int dense_force_strategy = -1;         // tests: -1 auto, 0 block-Taylor, 1 per-step propagator, 2 chained
     void* slice_ring = nullptr;            // slice.cu: ring of small device argument tables
+    int dense_small_mma = 1;               // dense resident engine: shifted kets of a sample on the FP64 tensor cores (k_small_mma)
     void* slice_partials = nullptr;        // slice.cu: per-block energy partials (1024 doubles)
     unsigned slice_cursor = 0;
     int device = 0;

@@ -333,6 +333,103 @@ int f_u(const Problem& P, int h, double t, const double* vv, int n_param, int n_
     return f_u_channels(P.channels, P.duration, P.func_type, h, t, vv, n_param, n_basis, out);
 }
 
+
+// Resident engine (dim <= 16) for a batch of estimator samples: prefix kets, then every shifted ket of every sample.
+// u_prefix / u_suffix: packed HOST pulse tables, or both NULL when S->u_dev already holds [prefix rows | suffix rows]
+// (filled on the device by k_pulse_rows).
+int grad_resident(dq_context* ctx, Problem& P, const double* M, const double* psi0, double r, int n_samples,
+                  const int32_t* prefix_steps, const double* prefix_dt, const int32_t* suffix_steps, const double* suffix_dt,
+                  const std::vector<long long>& pre_off, const std::vector<long long>& suf_off, double bound,
+                  const double* u_prefix, const double* u_suffix, int mode, double* energies_out) {
+    State* S = state_of(ctx);
+    const int n_H = P.n_H, dim = P.dim;
+    const long long n_pre = pre_off[n_samples], n_suf = suf_off[n_samples];
+    const int s = log2_ceil_ratio(bound, 1.0), m = 18;
+    DQ_REQUIRE(s <= 20, "dense path: ||dt H|| = %g is too large", bound);
+    S->last_kernel_ms = 0;
+    DQ_TRY(small_upload(ctx, P, M));
+    if (u_prefix || u_suffix) {          // pulse rows: prefix table, then suffix table
+        DQ_TRY(S->u_dev.reserve(std::max<size_t>(1, (size_t)(n_pre + n_suf) * n_H) * sizeof(double)));
+        if (n_pre) DQ_CUDA(cudaMemcpyAsync(S->u_dev.p, u_prefix, (size_t)n_pre * n_H * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        if (n_suf) DQ_CUDA(cudaMemcpyAsync(S->u_dev.as<double>() + (size_t)n_pre * n_H, u_suffix, (size_t)n_suf * n_H * sizeof(double),
+                                           cudaMemcpyHostToDevice, ctx->stream));
+    }
+    // kets: [0] = psi0, [1 .. n_samples] = phi_b
+    std::vector<double> k0(32, 0.0);
+    memcpy(k0.data(), psi0, sizeof(double) * 2 * dim);
+    DQ_TRY(S->phi.reserve((size_t)(1 + n_samples) * 32 * sizeof(double)));
+    DQ_TRY(S->out.reserve((size_t)n_samples * 2 * n_H * sizeof(double)));
+    DQ_CUDA(cudaMemcpyAsync(S->phi.p, k0.data(), 32 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    // longest trajectories first: a warp is busy for steps x terms, CTAs retire in launch order
+    std::vector<int> order(n_samples);
+    std::iota(order.begin(), order.end(), 0);
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return prefix_steps[a] > prefix_steps[b]; });
+    std::vector<SmallTraj> traj;
+    traj.reserve((size_t)n_samples * 2 * n_H);
+    for (int b : order) traj.push_back(SmallTraj{pre_off[b], std::ldexp(prefix_dt[b], -s), 0.0, prefix_steps[b], 0, 0, b});
+    DQ_TRY(small_run(ctx, P, mode, s, m, 1, traj, S->u_dev.as<double>(), S->phi.as<double>(), S->phi.as<double>() + 32, nullptr, 1.0));
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return suffix_steps[a] > suffix_steps[b]; });
+    traj.clear();
+    // Every shifted ket of a sample shares its generator.  Exact step: a warp takes up to 16 of them through the tensor-core
+    // recurrence (k_small_mma; option "small_mma" 0 = the DFMA kernel below instead).  Per-term product (mode 1): the +/-
+    // kets of a control (and of two neighbouring controls when n_H is even) per warp on the DFMA kernel.
+    const bool mma = mode == 0 && ctx->dense_small_mma != 0;
+    const int nk = mma ? (2 * n_H > 8 ? 16 : 8) : ((n_H % 2 == 0) ? 4 : 2);
+    for (int b : order)
+        for (int i = 0; i < n_H; i += nk / 2)
+            traj.push_back(SmallTraj{n_pre + suf_off[b], std::ldexp(suffix_dt[b], -s), r, suffix_steps[b], b, i, (b * n_H + i) * 2});
+    DQ_TRY(small_run(ctx, P, mode, s, m, nk, traj, S->u_dev.as<double>(), S->phi.as<double>() + 32, nullptr, S->out.as<double>(),
+                     1.0 / sqrt(1.0 + r * r)));
+    DQ_CUDA(cudaMemcpyAsync(energies_out, S->out.p, (size_t)n_samples * 2 * n_H * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    DQ_CUDA(cudaStreamSynchronize(ctx->stream));
+    S->last_gemm_flops = 0;
+    S->last_strategy = 3;
+    S->last_squarings = s;
+    S->last_degree = m;
+    return DQ_OK;
+}
+
+// ---- pulse rows of the Python twin on the device ---------------------------------------------------------------------------
+// u[row][i] = omega_i (2 sigma(sum_j c_ij phi_j(t/T)) - 1), phi = the open-support quadratic bumps (sim_plain.py:52-99), for every
+// step of every prefix (0 -> s_b) and suffix (s_b -> T) trajectory of a batch: the table pulses.u_table builds on the host,
+// in the same operation order -- t accumulated by repeated `t += dt` (sim_plain.py:134,150), the sum over j sequential from
+// j = 0 with a separate multiply and add (no FMA contraction), 1 / (1 + exp(-a)) -- so that the two agree to the last bit of
+// everything but exp() (libdevice vs NumPy: each within 1 ulp).  One thread per row.
+__global__ void k_pulse_rows(const double* __restrict__ s_list, const long long* __restrict__ pre_off,
+                             const long long* __restrict__ suf_off, const int* __restrict__ pre_n, const int* __restrict__ suf_n,
+                             const double* __restrict__ pre_dt, const double* __restrict__ suf_dt, int n_samples, long long n_pre_total,
+                             double T, const double* __restrict__ coeff, const double* __restrict__ omegas, int n_H, int n_basis,
+                             const double* __restrict__ bl, const double* __restrict__ br, double norm_factor,
+                             double* __restrict__ u, const double* __restrict__ norm1, int sum_mode,
+                             unsigned long long* __restrict__ bound_bits) {
+    const int b = blockIdx.x;
+    const int which = blockIdx.y;                          // 0 prefix, 1 suffix
+    const int n = which ? suf_n[b] : pre_n[b];
+    const double dt = which ? suf_dt[b] : pre_dt[b];
+    const double t0 = which ? s_list[b] : 0.0;
+    const long long row0 = which ? n_pre_total + suf_off[b] : pre_off[b];
+    for (int k = threadIdx.x; k < n; k += blockDim.x) {
+        double t = t0;
+        for (int i = 0; i < k; ++i) t = __dadd_rn(t, dt);  // the reference's repeated t += dt
+        const double x = t / T;
+        double* __restrict__ out = u + (row0 + k) * n_H;
+        double nb = norm1[0];                              // ||dt H(t_k)||_1 bound of this row (scaling choice of the Taylor series)
+        for (int i = 0; i < n_H; ++i) {
+            double a = 0.0;
+            for (int j = 0; j < n_basis; ++j) {
+                double phi = 0.0;
+                if (!(x >= br[j] || x <= bl[j])) phi = __dmul_rn(__dadd_rn(x, -bl[j]), __dadd_rn(x, -br[j])) / norm_factor;
+                a = __dadd_rn(a, __dmul_rn(phi, coeff[i * n_basis + j]));
+            }
+            const double sg = 1.0 / (1.0 + exp(-a));
+            const double ui = __dmul_rn(__dadd_rn(__dmul_rn(sg, 2.0), -1.0), omegas[i]);
+            out[i] = ui;
+            nb = sum_mode ? nb + fabs(ui) * norm1[i + 1] : fmax(nb, fabs(ui) * norm1[i + 1]);
+        }
+        atomicMax(bound_bits, (unsigned long long)__double_as_longlong(fabs(dt) * nb));   // non-negative doubles order like integers
+    }
+}
+
 }  // namespace
 }  // namespace dense
 }  // namespace dq
@@ -506,50 +603,11 @@ int dq_dense_grad(dq_context* ctx, int dim, const double* H0, int n_H, const dou
     DQ_TRY(want_resident(ctx, P, &resident));
     if (resident) {
         static const double no_u0 = 0.0;
-        const long long n_pre = pre_off[n_samples], n_suf = suf_off[n_samples];
         double b_pre = 0.0, b_suf = 0.0;
         DQ_TRY(norm_bound(P, mode, n_samples, prefix_steps, prefix_dt, pre_off.data(), u_prefix ? u_prefix : &no_u0, &b_pre));
         DQ_TRY(norm_bound(P, mode, n_samples, suffix_steps, suffix_dt, suf_off.data(), u_suffix ? u_suffix : &no_u0, &b_suf));
-        const double bound = std::max(b_pre, b_suf);
-        const int s = log2_ceil_ratio(bound, 1.0), m = 18;
-        DQ_REQUIRE(s <= 20, "dense path: ||dt H|| = %g is too large", bound);
-        S->last_kernel_ms = 0;
-        DQ_TRY(small_upload(ctx, P, M));
-        // pulse rows: prefix table, then suffix table
-        DQ_TRY(S->u_dev.reserve(std::max<size_t>(1, (size_t)(n_pre + n_suf) * n_H) * sizeof(double)));
-        if (n_pre) DQ_CUDA(cudaMemcpyAsync(S->u_dev.p, u_prefix, (size_t)n_pre * n_H * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-        if (n_suf) DQ_CUDA(cudaMemcpyAsync(S->u_dev.as<double>() + (size_t)n_pre * n_H, u_suffix, (size_t)n_suf * n_H * sizeof(double),
-                                           cudaMemcpyHostToDevice, ctx->stream));
-        // kets: [0] = psi0, [1 .. n_samples] = phi_b
-        std::vector<double> k0(32, 0.0);
-        memcpy(k0.data(), psi0, sizeof(double) * 2 * dim);
-        DQ_TRY(S->phi.reserve((size_t)(1 + n_samples) * 32 * sizeof(double)));
-        DQ_TRY(S->out.reserve((size_t)n_samples * 2 * n_H * sizeof(double)));
-        DQ_CUDA(cudaMemcpyAsync(S->phi.p, k0.data(), 32 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-        // longest trajectories first: a warp is busy for steps x terms, CTAs retire in launch order
-        std::vector<int> order(n_samples);
-        std::iota(order.begin(), order.end(), 0);
-        std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return prefix_steps[a] > prefix_steps[b]; });
-        std::vector<SmallTraj> traj;
-        traj.reserve((size_t)n_samples * 2 * n_H);
-        for (int b : order) traj.push_back(SmallTraj{pre_off[b], std::ldexp(prefix_dt[b], -s), 0.0, prefix_steps[b], 0, 0, b});
-        DQ_TRY(small_run(ctx, P, mode, s, m, 1, traj, S->u_dev.as<double>(), S->phi.as<double>(), S->phi.as<double>() + 32, nullptr, 1.0));
-        std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return suffix_steps[a] > suffix_steps[b]; });
-        traj.clear();
-        // the +/- kets of a control (and of two neighbouring controls when n_H is even) share their generator: one warp each
-        const int nk = (n_H % 2 == 0) ? 4 : 2;
-        for (int b : order)
-            for (int i = 0; i < n_H; i += nk / 2)
-                traj.push_back(SmallTraj{n_pre + suf_off[b], std::ldexp(suffix_dt[b], -s), r, suffix_steps[b], b, i, (b * n_H + i) * 2});
-        DQ_TRY(small_run(ctx, P, mode, s, m, nk, traj, S->u_dev.as<double>(), S->phi.as<double>() + 32, nullptr, S->out.as<double>(),
-                         1.0 / sqrt(1.0 + r * r)));
-        DQ_CUDA(cudaMemcpyAsync(energies_out, S->out.p, (size_t)n_samples * 2 * n_H * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-        DQ_CUDA(cudaStreamSynchronize(ctx->stream));
-        S->last_gemm_flops = 0;
-        S->last_strategy = 3;
-        S->last_squarings = s;
-        S->last_degree = m;
-        return DQ_OK;
+        return grad_resident(ctx, P, M, psi0, r, n_samples, prefix_steps, prefix_dt, suffix_steps, suffix_dt, pre_off, suf_off,
+                             std::max(b_pre, b_suf), u_prefix, u_suffix, mode, energies_out);
     }
     const int Ncp = round8(2 * n_H), Dp = P.Dp;
     const size_t mat_bytes = 2 * P.plane() * sizeof(double);
@@ -587,6 +645,103 @@ int dq_dense_grad(dq_context* ctx, int dim, const double* H0, int n_H, const dou
     return DQ_OK;
 }
 
+int dq_dense_grad_times(dq_context* ctx, int dim, const double* H0, int n_H, const double* Hs, const double* M,
+                        const double* psi0, double r, int n_samples, const double* s_list, double T, int per_step,
+                        const double* coeff, const double* omegas, int n_basis, int mode, double* energies_out, double* u_out) {
+    DQ_REQUIRE(ctx && M && psi0 && energies_out && s_list && coeff && omegas, "dq_dense_grad_times: NULL argument");
+    DQ_REQUIRE(mode == 0 || mode == 1, "dq_dense_grad_times: mode must be 0 (exact) or 1 (split)");
+    DQ_REQUIRE(n_samples >= 1 && n_H >= 1 && n_basis >= 3 && per_step >= 1, "dq_dense_grad_times: n_samples=%d n_H=%d n_basis=%d per_step=%d",
+               n_samples, n_H, n_basis, per_step);
+    DQ_REQUIRE(r > 0 && std::isfinite(r) && T > 0 && std::isfinite(T), "dq_dense_grad_times: r and T must be positive");
+    DQ_TRY(ctx->set_device());
+    State* S = state_of(ctx);
+    Problem& P = S->scratch_H;
+    DQ_TRY(upload_problem(ctx, P, dim, H0, n_H, Hs));
+    bool resident = false;
+    DQ_TRY(want_resident(ctx, P, &resident));
+    if (!resident) {
+        dq::set_error("dq_dense_grad_times: device-side pulse tables exist for the resident engine (dim <= 16) only");
+        return DQ_ERR_UNSUPPORTED;
+    }
+    for (int i = 0; i < 2 * dim; ++i) DQ_REQUIRE(std::isfinite(psi0[i]), "dq_dense_grad_times: non-finite psi0 entry");
+    for (int i = 0; i < n_H * n_basis; ++i) DQ_REQUIRE(std::isfinite(coeff[i]), "dq_dense_grad_times: non-finite coefficient");
+    // step grids exactly as sim_plain.py:123,133: n = int(per_step ((T1 - T0) + 1)), dt = (T1 - T0) / n
+    std::vector<int32_t> pre_n(n_samples), suf_n(n_samples);
+    std::vector<double> pre_dt(n_samples), suf_dt(n_samples);
+    std::vector<long long> pre_off(n_samples + 1, 0), suf_off(n_samples + 1, 0);
+    double w_sum = P.norm1[0], w_max = P.norm1[0], dt_max = 0.0;
+    for (int h = 0; h < n_H; ++h) {
+        DQ_REQUIRE(std::isfinite(omegas[h]), "dq_dense_grad_times: non-finite omega");
+        w_sum += fabs(omegas[h]) * P.norm1[h + 1];          // |u_h| <= |omega_h|
+        w_max = std::max(w_max, fabs(omegas[h]) * P.norm1[h + 1]);
+    }
+    for (int b = 0; b < n_samples; ++b) {
+        const double sb = s_list[b];
+        DQ_REQUIRE(std::isfinite(sb) && sb >= 0.0 && sb <= T, "dq_dense_grad_times: sample time %g outside [0, T]", sb);
+        pre_n[b] = (int)(per_step * ((sb - 0.0) + 1));
+        suf_n[b] = (int)(per_step * ((T - sb) + 1));
+        pre_dt[b] = pre_n[b] > 0 ? (sb - 0.0) / pre_n[b] : 0.0;
+        suf_dt[b] = suf_n[b] > 0 ? (T - sb) / suf_n[b] : 0.0;
+        pre_off[b + 1] = pre_off[b] + pre_n[b];
+        suf_off[b + 1] = suf_off[b] + suf_n[b];
+        dt_max = std::max(dt_max, std::max(fabs(pre_dt[b]), fabs(suf_dt[b])));
+    }
+    const long long n_pre = pre_off[n_samples], n_suf = suf_off[n_samples];
+    // bump supports as get_func_bspline computes them (sim_plain.py:53-58)
+    std::vector<double> bl(n_basis), br(n_basis);
+    const double tau = 1. / (n_basis - 2);
+    for (int b = 0; b < n_basis; ++b) {
+        const double tau_b = tau * (b - 1.5);
+        bl[b] = tau_b - 1.5 * tau;
+        br[b] = tau_b + 1.5 * tau;
+    }
+    const double norm_factor = -((1.5 * tau) * (1.5 * tau));
+    // one staging buffer: s | pre_dt | suf_dt | coeff | omegas | bl | br | pre_off | suf_off | pre_n | suf_n
+    const size_t nd = (size_t)3 * n_samples + (size_t)n_H * n_basis + n_H + 2 * n_basis + (1 + n_H) + 1;
+    std::vector<double> hd(nd, 0.0);
+    double* q = hd.data();
+    memcpy(q, s_list, n_samples * sizeof(double)); q += n_samples;
+    memcpy(q, pre_dt.data(), n_samples * sizeof(double)); q += n_samples;
+    memcpy(q, suf_dt.data(), n_samples * sizeof(double)); q += n_samples;
+    memcpy(q, coeff, (size_t)n_H * n_basis * sizeof(double)); q += (size_t)n_H * n_basis;
+    memcpy(q, omegas, n_H * sizeof(double)); q += n_H;
+    memcpy(q, bl.data(), n_basis * sizeof(double)); q += n_basis;
+    memcpy(q, br.data(), n_basis * sizeof(double)); q += n_basis;
+    memcpy(q, P.norm1.data(), (1 + n_H) * sizeof(double));            // then one zeroed slot: the bound (as integer bits)
+    const size_t bytes_d = nd * sizeof(double), bytes_o = (size_t)2 * n_samples * sizeof(long long), bytes_n = (size_t)2 * n_samples * sizeof(int);
+    DQ_TRY(S->meta.reserve(bytes_d + bytes_o + bytes_n));
+    char* dm = S->meta.as<char>();
+    DQ_CUDA(cudaMemcpyAsync(dm, hd.data(), bytes_d, cudaMemcpyHostToDevice, ctx->stream));
+    DQ_CUDA(cudaMemcpyAsync(dm + bytes_d, pre_off.data(), n_samples * sizeof(long long), cudaMemcpyHostToDevice, ctx->stream));
+    DQ_CUDA(cudaMemcpyAsync(dm + bytes_d + n_samples * sizeof(long long), suf_off.data(), n_samples * sizeof(long long), cudaMemcpyHostToDevice, ctx->stream));
+    DQ_CUDA(cudaMemcpyAsync(dm + bytes_d + bytes_o, pre_n.data(), n_samples * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    DQ_CUDA(cudaMemcpyAsync(dm + bytes_d + bytes_o + n_samples * sizeof(int), suf_n.data(), n_samples * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    DQ_TRY(S->u_dev.reserve(std::max<size_t>(1, (size_t)(n_pre + n_suf) * n_H) * sizeof(double)));
+    const double* dd = reinterpret_cast<const double*>(dm);
+    const long long* dof = reinterpret_cast<const long long*>(dm + bytes_d);
+    const int* dn = reinterpret_cast<const int*>(dm + bytes_d + bytes_o);
+    k_pulse_rows<<<dim3((unsigned)n_samples, 2), 64, 0, ctx->stream>>>(
+        dd, dof, dof + n_samples, dn, dn + n_samples, dd + n_samples, dd + 2 * n_samples, n_samples, n_pre, T,
+        dd + 3 * n_samples, dd + 3 * n_samples + (size_t)n_H * n_basis, n_H, n_basis,
+        dd + 3 * n_samples + (size_t)n_H * n_basis + n_H, dd + 3 * n_samples + (size_t)n_H * n_basis + n_H + n_basis, norm_factor,
+        S->u_dev.as<double>(), dd + nd - (2 + n_H), mode == 0 ? 1 : 0,
+        reinterpret_cast<unsigned long long*>(dm) + (nd - 1));
+    ctx->launches++;
+    DQ_CUDA(cudaGetLastError());
+    double bound = 0.0;                                     // 8 bytes back: the scaling of the series is chosen from the actual pulses
+    DQ_CUDA(cudaMemcpyAsync(&bound, dm + (nd - 1) * sizeof(double), sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    DQ_CUDA(cudaStreamSynchronize(ctx->stream));
+    DQ_REQUIRE(std::isfinite(bound), "dq_dense_grad_times: non-finite pulse value");
+    if (u_out) {
+        DQ_CUDA(cudaMemcpyAsync(u_out, S->u_dev.p, (size_t)(n_pre + n_suf) * n_H * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        DQ_CUDA(cudaStreamSynchronize(ctx->stream));
+    }
+    DQ_TRY(upload_observable(ctx, P, M));
+    (void)w_sum; (void)w_max; (void)dt_max;
+    return grad_resident(ctx, P, M, psi0, r, n_samples, pre_n.data(), pre_dt.data(), suf_n.data(), suf_dt.data(), pre_off, suf_off, bound,
+                         nullptr, nullptr, mode, energies_out);
+}
+
 int dq_dense_last_stat(dq_context* ctx, const char* name, double* value) {
     DQ_REQUIRE(ctx && name && value, "NULL argument");
     State* S = state_of(ctx);
@@ -604,6 +759,8 @@ int dq_dense_set_option(dq_context* ctx, const char* name, int64_t value) {
     if (!strcmp(name, "strategy")) {
         DQ_REQUIRE(value >= -1 && value <= 3, "strategy must be -1 (auto), 0, 1, 2 or 3");
         ctx->dense_force_strategy = (int)value;
+    } else if (!strcmp(name, "small_mma")) {
+        ctx->dense_small_mma = value != 0;
     } else { dq::set_error("dq_dense_set_option: unknown option '%s'", name); return DQ_ERR_INVALID; }
     return DQ_OK;
 }

@@ -169,6 +169,186 @@ k_small(const double2* __restrict__ H, const double2* __restrict__ M, int n_H, i
     }
 }
 
+// ---- the same recurrence on the FP64 tensor cores ---------------------------------------------------------------------------
+// All 2 n_H shifted kets of a sample share their generator (sim_plain.py:196-215: same H list, same step grid), so the
+// Horner step  Y <- X + (A/j) Y  on the 16 x K block of kets is a complex 16x16 x 16xK matrix product: four real products,
+// each a chain of mma.sync.m8n8k4.f64 (DMMA).  One warp owns up to 16 kets (KT ket tiles of 8) of ONE sample for the whole
+// suffix trajectory; nothing but the per-step pulse row and the operator stack (shared memory) is read between launch and
+// energy.  The block is kept TRANSPOSED, Z = Y^T (kets x states), so that the product is Z G with G = A^T the B operand:
+//   * the accumulator layout of m8n8k4 (thread (g, q) holds columns 2q, 2q+1 of row g) read as an A operand (thread holds
+//     column q of row g) is the same tile with its contraction index permuted to (0,2,4,6 | 1,3,5,7); G's B fragments are
+//     loaded with the same permutation (it is fixed per step), so the result of one Horner step feeds the next one
+//     without a single shuffle or shared-memory round trip;
+//   * PTX has no negated operand for DMMA: the fragments of -Im G are kept next to Re G and Im G.
+// Per Horner step and 16 kets: 64 DMMA (8 output tiles x 8-long accumulation chains) + 16 DFMA for the 1/j scaling.
+__device__ __forceinline__ void dmma(double (&d)[2], const double a, const double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
+                 : "+d"(d[0]), "+d"(d[1]) : "d"(a), "d"(b));
+}
+
+// B fragments of G[c][n] = Mat[n][c] * (gr, gi) for this thread: index [ct][p][nn] <-> c = 8 ct + 2 q + p, n = 8 nn + g.
+struct GFrag { double r[2][2][2], i[2][2][2], ni[2][2][2]; };
+
+template <int KT>
+__global__ void __launch_bounds__(32 * kWarps, KT == 1 ? 3 : 2)
+k_small_mma(const double2* __restrict__ H, const double2* __restrict__ M, int n_H, int reps, int m,
+            const double* __restrict__ u, const SmallTraj* __restrict__ traj, int n_traj, const double2* __restrict__ src,
+            double* __restrict__ dst_energy, double inv_norm) {
+    extern __shared__ double2 smem_mma[];
+    double2* Hs = smem_mma;                                     // [(2 + n_H)][16][16]: H0, H_1..H_nH, M
+    double2* stage = Hs + (size_t)(2 + n_H) * kD * kD;           // [kWarps][8 KT][17] kets of a warp's chunk (+ phi)
+    __shared__ double inv_j[kMaxDegree + 1];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x <= kMaxDegree) inv_j[threadIdx.x] = threadIdx.x ? 1.0 / (double)threadIdx.x : 0.0;
+    for (int i = threadIdx.x; i < (2 + n_H) * kD * kD; i += blockDim.x) Hs[i] = __ldg(H + i);   // M follows the H stack
+    __syncthreads();
+    const int w = blockIdx.x * kWarps + warp;
+    if (w >= n_traj) return;
+    const SmallTraj t = traj[w];
+    const int g = lane >> 2, q = lane & 3;
+    double2* st = stage + (size_t)warp * (8 * KT + 1) * kXs;
+    double2* phi = st + (size_t)8 * KT * kXs;
+
+    // ---- shift gates: ket k = (phi + sigma_k i r H_{term + k/2} phi) / sqrt(1 + r^2), sigma = +, -, +, - ...  (sim_plain.py:197-199)
+    if (lane < kD) phi[lane] = src[(size_t)t.src * kD + lane];
+    __syncwarp();
+    const int n_valid = min(8 * KT, 2 * (n_H - t.term));
+    for (int k = 0; k < 8 * KT; ++k) {
+        if (lane < kD) {
+            double2 v = make_double2(0.0, 0.0);
+            if (k < n_valid) {
+                const double2* __restrict__ hrow = Hs + (size_t)(t.term + (k >> 1) + 1) * kD * kD + lane * kD;
+                double2 hp = make_double2(0.0, 0.0);
+#pragma unroll
+                for (int c = 0; c < kD; ++c) hp = cfma(hrow[c], phi[c], hp);
+                const double sh = (k & 1) ? -t.shift : t.shift;
+                const double2 c0 = phi[lane];
+                v = make_double2((c0.x - sh * hp.y) * inv_norm, (c0.y + sh * hp.x) * inv_norm);
+            }
+            st[k * kXs + lane] = v;
+        }
+    }
+    __syncwarp();
+    // Z fragments: [rt][ct][e] <-> ket 8 rt + g, state 8 ct + 2 q + e
+    double zr[KT][2][2], zi[KT][2][2];
+#pragma unroll
+    for (int rt = 0; rt < KT; ++rt)
+#pragma unroll
+        for (int ct = 0; ct < 2; ++ct)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const double2 v = st[(8 * rt + g) * kXs + 8 * ct + 2 * q + e];
+                zr[rt][ct][e] = v.x;
+                zi[rt][ct][e] = v.y;
+            }
+
+    auto load_g = [&](GFrag& G, const double* __restrict__ ur, const double scale) {
+        // G = A^T with A = -i scale (H0 + sum_h u_h H_h):  Re A = scale Im H,  Im A = -scale Re H
+#pragma unroll
+        for (int ct = 0; ct < 2; ++ct)
+#pragma unroll
+            for (int p = 0; p < 2; ++p)
+#pragma unroll
+                for (int nn = 0; nn < 2; ++nn) {
+                    const int idx = (8 * nn + g) * kD + 8 * ct + 2 * q + p;          // Mat[n][c]
+                    double2 a = Hs[idx];
+                    for (int h = 0; h < n_H; ++h) {
+                        const double cq = __ldg(ur + h);
+                        const double2 e = Hs[(size_t)(h + 1) * kD * kD + idx];
+                        a.x = fma(cq, e.x, a.x);
+                        a.y = fma(cq, e.y, a.y);
+                    }
+                    G.r[ct][p][nn] = scale * a.y;
+                    G.i[ct][p][nn] = -scale * a.x;
+                    G.ni[ct][p][nn] = scale * a.x;
+                }
+    };
+    // D = Y G (complex): dr = yr Gr + yi (-Gi), di = yr Gi + yi Gr; output tile (rt, nn), contraction over (ct, p)
+    auto product = [&](const double (&yr)[KT][2][2], const double (&yi)[KT][2][2], const GFrag& G, double (&dr)[KT][2][2],
+                       double (&di)[KT][2][2]) {
+#pragma unroll
+        for (int rt = 0; rt < KT; ++rt)
+#pragma unroll
+            for (int nn = 0; nn < 2; ++nn) dr[rt][nn][0] = dr[rt][nn][1] = di[rt][nn][0] = di[rt][nn][1] = 0.0;
+#pragma unroll
+        for (int ct = 0; ct < 2; ++ct)
+#pragma unroll
+            for (int p = 0; p < 2; ++p)
+#pragma unroll
+                for (int rt = 0; rt < KT; ++rt)
+#pragma unroll
+                    for (int nn = 0; nn < 2; ++nn) {
+                        dmma(dr[rt][nn], yr[rt][ct][p], G.r[ct][p][nn]);
+                        dmma(dr[rt][nn], yi[rt][ct][p], G.ni[ct][p][nn]);
+                        dmma(di[rt][nn], yr[rt][ct][p], G.i[ct][p][nn]);
+                        dmma(di[rt][nn], yi[rt][ct][p], G.r[ct][p][nn]);
+                    }
+    };
+
+    for (int k = 0; k < t.steps; ++k) {
+        GFrag G;
+        load_g(G, u + (t.row + k) * n_H, t.scale);
+        for (int rep = 0; rep < reps; ++rep) {
+            double yr[KT][2][2], yi[KT][2][2];
+#pragma unroll
+            for (int rt = 0; rt < KT; ++rt)
+#pragma unroll
+                for (int ct = 0; ct < 2; ++ct)
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) { yr[rt][ct][e] = zr[rt][ct][e]; yi[rt][ct][e] = zi[rt][ct][e]; }
+            for (int j = m; j >= 1; --j) {          // y <- x + (A / j) y
+                double dr[KT][2][2], di[KT][2][2];
+                product(yr, yi, G, dr, di);
+                const double f = inv_j[j];
+#pragma unroll
+                for (int rt = 0; rt < KT; ++rt)
+#pragma unroll
+                    for (int ct = 0; ct < 2; ++ct)
+#pragma unroll
+                        for (int e = 0; e < 2; ++e) {
+                            yr[rt][ct][e] = fma(f, dr[rt][ct][e], zr[rt][ct][e]);
+                            yi[rt][ct][e] = fma(f, di[rt][ct][e], zi[rt][ct][e]);
+                        }
+            }
+#pragma unroll
+            for (int rt = 0; rt < KT; ++rt)
+#pragma unroll
+                for (int ct = 0; ct < 2; ++ct)
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) { zr[rt][ct][e] = yr[rt][ct][e]; zi[rt][ct][e] = yi[rt][ct][e]; }
+        }
+    }
+    // ---- energies: W = Z M^T, E_k = sum_c Re conj(Z[k][c]) W[k][c]      (sim_plain.py:205,215) ---------------------------------
+    {
+        GFrag G;
+        const double2* Ms = Hs + (size_t)(1 + n_H) * kD * kD;
+#pragma unroll
+        for (int ct = 0; ct < 2; ++ct)
+#pragma unroll
+            for (int p = 0; p < 2; ++p)
+#pragma unroll
+                for (int nn = 0; nn < 2; ++nn) {
+                    const double2 a = Ms[(8 * nn + g) * kD + 8 * ct + 2 * q + p];
+                    G.r[ct][p][nn] = a.x;
+                    G.i[ct][p][nn] = a.y;
+                    G.ni[ct][p][nn] = -a.y;
+                }
+        double wr[KT][2][2], wi[KT][2][2];
+        product(zr, zi, G, wr, wi);
+#pragma unroll
+        for (int rt = 0; rt < KT; ++rt) {
+            double e = 0.0;
+#pragma unroll
+            for (int ct = 0; ct < 2; ++ct)
+#pragma unroll
+                for (int c = 0; c < 2; ++c) e += zr[rt][ct][c] * wr[rt][ct][c] + zi[rt][ct][c] * wi[rt][ct][c];
+            e += __shfl_xor_sync(0xffffffffu, e, 1);
+            e += __shfl_xor_sync(0xffffffffu, e, 2);
+            if (q == 0 && 8 * rt + g < n_valid) dst_energy[t.out + 8 * rt + g] = e;
+        }
+    }
+}
+
 // interleaved c128 [dim][dim] -> zero-padded [16][16]
 void pad16(const double* src, int dim, double* dst) {
     std::fill(dst, dst + 2 * kD * kD, 0.0);
@@ -201,7 +381,7 @@ int small_run(dq_context* ctx, const Problem& P, int mode, int s, int m, int ket
               const double* d_u, const double* d_src, double* d_dst_kets, double* d_dst_energy, double inv_norm) {
     State* S = state_of(ctx);
     DQ_REQUIRE(m >= 1 && m <= kMaxDegree && s >= 0 && s <= 20, "dense resident engine: degree %d / squarings %d out of range", m, s);
-    DQ_REQUIRE(kets_per_traj == 1 || ((kets_per_traj == 2 || kets_per_traj == 4) && d_dst_energy),
+    DQ_REQUIRE(kets_per_traj == 1 || ((kets_per_traj == 2 || kets_per_traj == 4 || kets_per_traj == 8 || kets_per_traj == 16) && d_dst_energy),
                "dense resident engine: %d kets per trajectory", kets_per_traj);
     if (traj.empty()) return DQ_OK;
     DQ_TRY(S->small_traj.reserve(traj.size() * sizeof(SmallTraj)));
@@ -218,7 +398,18 @@ int small_run(dq_context* ctx, const Problem& P, int mode, int s, int m, int ket
     }
     DQ_CUDA(cudaEventRecord(S->ev0, ctx->stream));
     const int reps = 1 << s;
-    if (!d_dst_energy)
+    if (d_dst_energy && kets_per_traj >= 8) {                 // suffix trajectories of the estimator, exact step: tensor cores
+        DQ_REQUIRE(mode == 0 && (kets_per_traj == 8 || kets_per_traj == 16), "dense resident engine: DMMA path is mode 0, 8 or 16 kets per warp");
+        const size_t smem = ((size_t)(2 + P.n_H) * kD * kD + (size_t)kWarps * (kets_per_traj + 1) * kXs) * sizeof(double2);
+        DQ_REQUIRE(smem <= 200 * 1024, "dense resident engine: %d controls do not fit the shared-memory operator stack", P.n_H);
+        if (kets_per_traj == 8) {
+            DQ_CUDA(cudaFuncSetAttribute(k_small_mma<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            k_small_mma<1><<<grid, 32 * kWarps, smem, ctx->stream>>>(H, M, P.n_H, reps, m, d_u, d_traj, n, src, d_dst_energy, inv_norm);
+        } else {
+            DQ_CUDA(cudaFuncSetAttribute(k_small_mma<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            k_small_mma<2><<<grid, 32 * kWarps, smem, ctx->stream>>>(H, M, P.n_H, reps, m, d_u, d_traj, n, src, d_dst_energy, inv_norm);
+        }
+    } else if (!d_dst_energy)
         k_small<false, 1><<<grid, 32 * kWarps, 0, ctx->stream>>>(H, M, P.n_H, mode, reps, m, d_u, d_traj, n, src,
                                                                  reinterpret_cast<double2*>(d_dst_kets), nullptr, inv_norm);
     else if (kets_per_traj == 1)

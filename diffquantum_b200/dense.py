@@ -70,6 +70,24 @@ class DenseSimulator(object):
         self.basis = basis
         self.mode = mode
         self.ctx = _lib.Context.get(device)
+        # dim <= 16 with the B-spline ansatz: the device evaluates the pulse rows itself (dq_dense_grad_times); only the
+        # sample times and the coefficients cross the bus.  False = host tables (pulses.u_table) through dq_dense_grad.
+        self.device_tables = True
+
+    def _times_call(self, coeff, s_list, r, mode, want_u=False):
+        """dq_dense_grad_times: energies [B, n_H, 2] (and the device-built pulse table when want_u)."""
+        coeff = np.ascontiguousarray(coeff, dtype=np.float64)
+        s_list = np.ascontiguousarray(s_list, dtype=np.float64)
+        out = np.empty((len(s_list), self.n_H, 2))
+        u = None
+        if want_u:
+            rows = int((self.per_step * (s_list + 1)).astype(np.int64).sum() + (self.per_step * ((self.T - s_list) + 1)).astype(np.int64).sum())
+            u = np.empty((rows, self.n_H))
+        _lib.check(_lib.load().dq_dense_grad_times(
+            self.ctx.handle, self.dim, _lib.ptr(self.H0), self.n_H, _lib.ptr(self.Hs), _lib.ptr(self.M), _lib.ptr(self.psi0),
+            float(r), len(s_list), _lib.ptr(s_list), self.T, int(self.per_step), _lib.ptr(coeff), _lib.ptr(self.omegas),
+            coeff.shape[1], MODES[mode or self.mode], _lib.ptr(out), _lib.ptr(u)))
+        return out, u
 
     def stat(self, name):
         v = ctypes.c_double()
@@ -78,6 +96,12 @@ class DenseSimulator(object):
 
     def set_option(self, name, value):
         _lib.check(_lib.load().dq_dense_set_option(self.ctx.handle, name.encode(), int(value)))
+        if name == "strategy":
+            self._strategy = int(value)
+
+    def ctx_strategy_allows_resident(self):
+        """The device-side tables belong to the resident engine: not when a GEMM strategy (0, 1, 2) is forced."""
+        return getattr(self, "_strategy", -1) in (-1, 3)
 
     def evolve(self, coeff, T0, T1, psi0=None, mode=None):
         """SimulatorPlain.trotter (sim_plain.py:119-153) on the reference's step grid."""
@@ -97,6 +121,9 @@ class DenseSimulator(object):
         if self.M is None or self.psi0 is None:
             raise ValueError("shifted_energies needs M and psi0")
         s_list = np.asarray(s_list, dtype=np.float64).reshape(-1)
+        if (self.device_tables and self.basis == 'BSpline' and self.dim <= 16 and isinstance(self.per_step, (int, np.integer))
+                and self.ctx_strategy_allows_resident()):
+            return self._times_call(coeff, s_list, r, mode)[0]
         # all step grids and pulse tables of the batch in four vectorised calls (bit-identical to per-sample calls)
         pre_n, pre_dt, pre_ts = pulses.step_grids(0.0, s_list, self.per_step)
         suf_n, suf_dt, suf_ts = pulses.step_grids(s_list, self.T, self.per_step)

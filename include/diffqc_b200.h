@@ -14,6 +14,7 @@
  *   dq_pulse_f_u_table  f_u / my_expit / bspline diffqc.cc:75-135  (host only)
  *   dq_dense_evolve     SimulatorPlain.trotter  sim_plain.py:119-153   (solver hook, sim_plain.py:43)
  *   dq_dense_grad       compute_energy_grad_MC  sim_plain.py:186-220   (prefix + 2*n_H shifted suffixes)
+ *   dq_dense_grad_times the same + generate_u   sim_plain.py:52-99,186-220 (pulse rows evaluated on the device)
  *   dq_ising_*          the same two paths for Pauli-term (MaxCut/QAOA) Hamiltonians that the dense
  *                       nested-list API cannot express beyond n~13 (demo_maxcut.py:19-85 builds
  *                       them with np.kron) — step semantics of diffqc.cc:155-164.
@@ -95,11 +96,22 @@ int dq_dense_grad(dq_context* ctx, int dim, const double* H0, int n_H, const dou
                   const int32_t* suffix_steps, const double* suffix_dt, const double* u_suffix,
                   int mode, double* energies_out);
 
+/* The same batch from SAMPLE TIMES: the device evaluates the step grids' pulse rows itself -- the B-spline ansatz of the Python
+ * twin, u_i(t) = omega_i (2 sigma(sum_j coeff[i][j] phi_j(t/T)) - 1) on the grid of sim_plain.py:123-150 (sim_plain.py:52-99),
+ * in the reference's operation order -- so nothing but s_list [n_samples] and coeff [n_H][n_basis] crosses the bus.  Resident
+ * engine only (dim <= 16; DQ_ERR_UNSUPPORTED otherwise: use dq_dense_grad with host tables).  u_out, if not NULL, receives the
+ * device-built table [prefix rows of all samples | suffix rows of all samples][n_H] (parity tests against the host table). */
+int dq_dense_grad_times(dq_context* ctx, int dim, const double* H0, int n_H, const double* Hs, const double* M,
+                        const double* psi0, double r, int n_samples, const double* s_list, double T, int per_step,
+                        const double* coeff, const double* omegas, int n_basis, int mode, double* energies_out,
+                        double* u_out);
+
 /* Counters of the last dense call: "gemm_flops" (real flops issued to the DMMA GEMM), "strategy"
  * (0 block-Taylor, 1 per-step propagator, 2 chained propagator, 3 resident warp-per-trajectory engine, dim <= 16),
  * "squarings", "degree", "kernel_ms" (strategy 3: device time of its launches, CUDA events). */
 int dq_dense_last_stat(dq_context* ctx, const char* name, double* value);
-/* "strategy": -1 automatic (resident engine for dim <= 16, else by flop count), or force 0/1/2/3 (parity tests cover all). */
+/* "strategy": -1 automatic (resident engine for dim <= 16, else by flop count), or force 0/1/2/3 (parity tests cover all);
+ * "small_mma": 1 (default) the shifted kets of a sample run on the FP64 tensor cores in the resident engine, 0 the DFMA kernel. */
 int dq_dense_set_option(dq_context* ctx, const char* name, int64_t value);
 
 /* ---- structured path: H(t) = c0 + sum_e (w_e + u_e(t)) Z_a Z_b + sum_q u_q(t) X_q ------------

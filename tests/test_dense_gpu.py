@@ -308,3 +308,78 @@ def test_structured_training_reaches_a_maximum_cut():
     tr.train_energy()
     state, _ = tr.find_state()
     assert state in (0b0101, 0b1010) and tr.losses_energy[-1] < 0.05
+
+
+@pytest.mark.parametrize("name", DENSE_REF)
+@pytest.mark.parametrize("small_mma", [1, 0])
+def test_resident_engine_tensor_core_and_dfma_kernels_match_reference_fixture(golden, name, small_mma):
+    """dim <= 16: the shifted kets of a sample on the FP64 tensor cores (k_small_mma, the default) and on the DFMA kernel
+    (k_small), each against the reference's own compute_energy_grad_MC outputs."""
+    g = golden(name)
+    sim = sim_from(g)
+    sim.set_option("strategy", 3)
+    sim.set_option("small_mma", small_mma)
+    try:
+        grads, en = sim.grad_samples(g["coeff"], g["s"], return_energies=True)
+        assert sim.stat("strategy") == 3
+        assert rel(grads, g["grads"]) < TOL
+    finally:
+        sim.set_option("strategy", -1)
+        sim.set_option("small_mma", 1)
+
+
+@pytest.mark.parametrize("dim,n_H", [(16, 8), (16, 3), (12, 5), (5, 1), (16, 11), (9, 4)])
+def test_tensor_core_resident_engine_ragged_shapes(dim, n_H):
+    """Ket counts that do not fill the 8- or 16-ket tiles of a warp, dims that do not fill the 16 x 16 operators: DMMA kernel
+    vs the DFMA kernel and vs the oracle's dense estimator."""
+    from oracle import restate as R
+    rng = np.random.RandomState(dim * 31 + n_H)
+
+    def herm():
+        a = rng.normal(size=(dim, dim)) + 1j * rng.normal(size=(dim, dim))
+        return (a + a.conj().T) / 2
+
+    H0, Hs, M = herm() * 0.3, np.array([herm() for _ in range(n_H)]), herm()
+    for h in Hs:                      # the shift gate of the estimator is unitary for involutions; keep the operators bounded
+        h /= np.linalg.norm(h, 2)
+    psi0 = rng.normal(size=dim) + 1j * rng.normal(size=dim)
+    psi0 /= np.linalg.norm(psi0)
+    omegas = np.full(n_H, 2.0)
+    sim = dq.DenseSimulator(H0, Hs, omegas, 1.5, M=M, psi0=psi0, per_step=6)
+    coeff = rng.normal(size=(n_H, 6))
+    s = rng.uniform(size=5) * 1.5
+    try:
+        e_mma = sim.shifted_energies(coeff, s)
+        assert sim.stat("strategy") == 3
+        sim.set_option("small_mma", 0)
+        e_dfma = sim.shifted_energies(coeff, s)
+        assert rel(e_mma, e_dfma) < 1e-12
+        e_ref = R.grad_mc_dense(H0, list(Hs), M, psi0, coeff, omegas, 1.5, float(s[2]), 6, return_energies=True)[1]
+        assert rel(e_mma[2], e_ref) < TOL
+    finally:
+        sim.set_option("small_mma", 1)
+
+
+@pytest.mark.parametrize("name", ["demo_bspline_ref", "h2_vqe_ref"])
+def test_device_pulse_tables_match_host_tables_and_reference(golden, name):
+    """dq_dense_grad_times: the device evaluates the B-spline pulse rows (generate_u, sim_plain.py:52-99) on the reference's step
+    grids.  Its table against pulses.u_table (itself pinned to the reference's closures): identical but for exp() -- libdevice vs
+    NumPy, each within an ulp -- and the gradients against the reference's own compute_energy_grad_MC outputs."""
+    from diffquantum_b200 import pulses
+    g = golden(name)
+    sim = sim_from(g)
+    assert sim.device_tables and sim.basis == "BSpline"
+    s = np.concatenate([g["s"], [0.0, sim.T, 0.5 * sim.T]])            # edge cases: empty-span prefix / suffix keep per_step steps
+    en, u_dev = sim._times_call(g["coeff"], s, 0.5, None, want_u=True)
+    pre_n, pre_dt, pre_ts = pulses.step_grids(0.0, s, sim.per_step)
+    suf_n, suf_dt, suf_ts = pulses.step_grids(s, sim.T, sim.per_step)
+    u_host = np.concatenate([pulses.u_table(g["coeff"], sim.omegas, sim.T, pre_ts), pulses.u_table(g["coeff"], sim.omegas, sim.T, suf_ts)])
+    assert u_dev.shape == u_host.shape
+    # u = (2 sigma - 1) omega: an ulp of sigma (~1.1e-16 at sigma ~ 1/2) is up to 2.2e-16 omega in u; allow a few of them
+    err = np.abs(u_dev - u_host).max()
+    assert err <= 2e-15 * np.abs(sim.omegas).max(), err
+    assert (u_dev == u_host).mean() > 0.3, (u_dev == u_host).mean()      # and a good share of the entries is bit-equal
+    grads = sim.grad_samples(g["coeff"], g["s"])                         # default path = device tables
+    assert rel(grads, g["grads"]) < TOL
+    sim.device_tables = False
+    assert rel(sim.grad_samples(g["coeff"], g["s"]), grads) < 1e-13
