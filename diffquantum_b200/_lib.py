@@ -35,6 +35,9 @@ SIGNATURES = {
                                      ctypes.c_int, _VP, _VP, _VP, _VP, _VP, _VP, ctypes.c_int, _VP]),
     "dq_dense_grad_times": (ctypes.c_int, [_VP, ctypes.c_int, _VP, ctypes.c_int, _VP, _VP, _VP, ctypes.c_double, ctypes.c_int, _VP,
                                            ctypes.c_double, ctypes.c_int, _VP, _VP, ctypes.c_int, ctypes.c_int, _VP, _VP]),
+    "dq_dense_train": (ctypes.c_int, [_VP, ctypes.c_int, _VP, ctypes.c_int, _VP, _VP, _VP, _VP, ctypes.c_double, ctypes.c_int,
+                                      ctypes.c_int, _VP, ctypes.c_int, ctypes.c_int, _VP, ctypes.c_double, ctypes.c_double,
+                                      ctypes.c_double, ctypes.c_double, ctypes.c_double, ctypes.c_double, ctypes.c_int, _VP, _VP]),
     "dq_dense_last_stat": (ctypes.c_int, [_VP, ctypes.c_char_p, ctypes.POINTER(ctypes.c_double)]),
     "dq_dense_set_option": (ctypes.c_int, [_VP, ctypes.c_char_p, ctypes.c_int64]),
     "dq_ising_create": (ctypes.c_int, [_VP, ctypes.c_int, ctypes.c_int, _VP, _VP, ctypes.c_double, _VP,

@@ -33,6 +33,7 @@ struct State {                         // per context
     Problem scratch_H;                 // what dq_dense_evolve / dq_dense_grad were last called with
     DevBuf A, P0, P1, U, K0, K1, K2, u_dev, meta, phi, out;
     DevBuf small_H, small_traj;        // resident engine (dim <= 16): [(2 + n_H)][16][16] c128 (H0, H_h, M) and descriptors
+    DevBuf train;                      // device-resident training loop (dense_train.cu): coefficients, Adam state, descriptors
     double last_gemm_flops = 0;        // real flops issued to the DMMA GEMM in the last call
     int last_strategy = 0;             // 0 block-Taylor, 1 per-step propagator, 2 chained propagator, 3 resident (dim <= 16)
     int last_squarings = 0, last_degree = 0;
@@ -73,6 +74,9 @@ bool small_fits(const Problem& P);
 int small_upload(dq_context* ctx, const Problem& P, const double* M);
 int small_run(dq_context* ctx, const Problem& P, int mode, int s, int m, int kets_per_traj, const std::vector<SmallTraj>& traj,
               const double* d_u, const double* d_src, double* d_dst_kets, double* d_dst_energy, double inv_norm);
+int small_enqueue(dq_context* ctx, const Problem& P, int mode, int s, int m, int kets_per_traj, const SmallTraj* d_traj, int n,
+                  const double* d_u, const double* d_src, double* d_dst_kets, double* d_dst_energy, double inv_norm, const int* d_s);
+int upload_problem(dq_context* ctx, Problem& P, int dim, const double* H0, int n_H, const double* Hs);
 State* state_of(dq_context* ctx);
 void release(dq_context* ctx);
 

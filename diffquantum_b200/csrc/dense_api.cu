@@ -27,7 +27,7 @@ void release(dq_context* ctx) {
     State* S = ctx->dense;
     if (!S) return;
     DevBuf* bufs[] = {&S->global_H.H, &S->global_H.M, &S->scratch_H.H, &S->scratch_H.M, &S->A, &S->P0, &S->P1, &S->U,
-                      &S->K0, &S->K1, &S->K2, &S->u_dev, &S->meta, &S->phi, &S->out, &S->small_H, &S->small_traj};
+                      &S->K0, &S->K1, &S->K2, &S->u_dev, &S->meta, &S->phi, &S->out, &S->small_H, &S->small_traj, &S->train};
     for (auto* b : bufs) b->release();
     if (S->ev0) cudaEventDestroy(S->ev0);
     if (S->ev1) cudaEventDestroy(S->ev1);
@@ -59,6 +59,8 @@ double norm1_of(const double* src, int dim) {
     return best;
 }
 
+}  // namespace
+
 int upload_problem(dq_context* ctx, Problem& P, int dim, const double* H0, int n_H, const double* Hs) {
     DQ_REQUIRE(dim >= 1 && dim <= 1024, "dense path: dim=%d outside [1,1024]", dim);
     DQ_REQUIRE(n_H >= 0 && H0 && (n_H == 0 || Hs), "dense path: NULL Hamiltonian");
@@ -89,6 +91,9 @@ int upload_problem(dq_context* ctx, Problem& P, int dim, const double* H0, int n
     DQ_CUDA(cudaStreamSynchronize(ctx->stream));
     return DQ_OK;
 }
+
+namespace {
+
 
 int upload_observable(dq_context* ctx, Problem& P, const double* M) {
     const size_t per = (size_t)P.dim * P.dim * 2;

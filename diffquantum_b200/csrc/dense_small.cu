@@ -59,7 +59,7 @@ template <bool ENERGY, int NK>
 __global__ void __launch_bounds__(32 * kWarps, NK == 1 ? 6 : 4)
 k_small(const double2* __restrict__ H, const double2* __restrict__ M, int n_H, int mode, int reps, int m,
         const double* __restrict__ u, const SmallTraj* __restrict__ traj, int n_traj, const double2* __restrict__ src,
-        double2* __restrict__ dst_kets, double* __restrict__ dst_energy, double inv_norm) {
+        double2* __restrict__ dst_kets, double* __restrict__ dst_energy, double inv_norm, const int* __restrict__ d_s) {
     __shared__ double2 xs[kWarps][3][NK * kXs];
     __shared__ double inv_j[kMaxDegree + 1];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -67,7 +67,12 @@ k_small(const double2* __restrict__ H, const double2* __restrict__ M, int n_H, i
     __syncthreads();
     const int w = blockIdx.x * kWarps + warp;
     if (w >= n_traj) return;
-    const SmallTraj t = traj[w];
+    SmallTraj t = traj[w];
+    if (d_s) {                              // device-resident training: the scaling of the series was chosen on the device
+        const int sd = *d_s;
+        reps = 1 << sd;
+        t.scale = ldexp(t.scale, -sd);
+    }
     const int r = lane >> 1, h = lane & 1;
     double2* cur = xs[warp][0];
     double2* o1 = xs[warp][1];
@@ -193,7 +198,7 @@ template <int KT>
 __global__ void __launch_bounds__(32 * kWarps, KT == 1 ? 3 : 2)
 k_small_mma(const double2* __restrict__ H, const double2* __restrict__ M, int n_H, int reps, int m,
             const double* __restrict__ u, const SmallTraj* __restrict__ traj, int n_traj, const double2* __restrict__ src,
-            double* __restrict__ dst_energy, double inv_norm) {
+            double* __restrict__ dst_energy, double inv_norm, const int* __restrict__ d_s) {
     extern __shared__ double2 smem_mma[];
     double2* Hs = smem_mma;                                     // [(2 + n_H)][16][16]: H0, H_1..H_nH, M
     double2* stage = Hs + (size_t)(2 + n_H) * kD * kD;           // [kWarps][8 KT][17] kets of a warp's chunk (+ phi)
@@ -204,7 +209,12 @@ k_small_mma(const double2* __restrict__ H, const double2* __restrict__ M, int n_
     __syncthreads();
     const int w = blockIdx.x * kWarps + warp;
     if (w >= n_traj) return;
-    const SmallTraj t = traj[w];
+    SmallTraj t = traj[w];
+    if (d_s) {
+        const int sd = *d_s;
+        reps = 1 << sd;
+        t.scale = ldexp(t.scale, -sd);
+    }
     const int g = lane >> 2, q = lane & 3;
     double2* st = stage + (size_t)warp * (8 * KT + 1) * kXs;
     double2* phi = st + (size_t)8 * KT * kXs;
@@ -376,27 +386,19 @@ int small_upload(dq_context* ctx, const Problem& P, const double* M) {
     return DQ_OK;
 }
 
-// d_src / d_dst_kets: [..][16] c128; d_u: packed pulse rows [..][n_H]; traj: host descriptors (copied here)
-int small_run(dq_context* ctx, const Problem& P, int mode, int s, int m, int kets_per_traj, const std::vector<SmallTraj>& traj,
-              const double* d_u, const double* d_src, double* d_dst_kets, double* d_dst_energy, double inv_norm) {
+// Enqueue one launch of the resident engine on the context's stream; d_traj are DEVICE descriptors.  d_s: NULL, or a device int
+// holding the squarings chosen on the device (then `s` is ignored and the descriptors carry the unscaled dt).
+int small_enqueue(dq_context* ctx, const Problem& P, int mode, int s, int m, int kets_per_traj, const SmallTraj* d_traj, int n,
+                  const double* d_u, const double* d_src, double* d_dst_kets, double* d_dst_energy, double inv_norm, const int* d_s) {
     State* S = state_of(ctx);
     DQ_REQUIRE(m >= 1 && m <= kMaxDegree && s >= 0 && s <= 20, "dense resident engine: degree %d / squarings %d out of range", m, s);
     DQ_REQUIRE(kets_per_traj == 1 || ((kets_per_traj == 2 || kets_per_traj == 4 || kets_per_traj == 8 || kets_per_traj == 16) && d_dst_energy),
                "dense resident engine: %d kets per trajectory", kets_per_traj);
-    if (traj.empty()) return DQ_OK;
-    DQ_TRY(S->small_traj.reserve(traj.size() * sizeof(SmallTraj)));
-    DQ_CUDA(cudaMemcpyAsync(S->small_traj.p, traj.data(), traj.size() * sizeof(SmallTraj), cudaMemcpyHostToDevice, ctx->stream));
+    if (n <= 0) return DQ_OK;
     const double2* H = S->small_H.as<double2>();
     const double2* M = H + (size_t)(1 + P.n_H) * kD * kD;
-    const SmallTraj* d_traj = S->small_traj.as<SmallTraj>();
     const double2* src = reinterpret_cast<const double2*>(d_src);
-    const int n = (int)traj.size();
     const unsigned grid = (unsigned)((n + kWarps - 1) / kWarps);
-    if (!S->ev0) {
-        DQ_CUDA(cudaEventCreate(&S->ev0));
-        DQ_CUDA(cudaEventCreate(&S->ev1));
-    }
-    DQ_CUDA(cudaEventRecord(S->ev0, ctx->stream));
     const int reps = 1 << s;
     if (d_dst_energy && kets_per_traj >= 8) {                 // suffix trajectories of the estimator, exact step: tensor cores
         DQ_REQUIRE(mode == 0 && (kets_per_traj == 8 || kets_per_traj == 16), "dense resident engine: DMMA path is mode 0, 8 or 16 kets per warp");
@@ -404,22 +406,39 @@ int small_run(dq_context* ctx, const Problem& P, int mode, int s, int m, int ket
         DQ_REQUIRE(smem <= 200 * 1024, "dense resident engine: %d controls do not fit the shared-memory operator stack", P.n_H);
         if (kets_per_traj == 8) {
             DQ_CUDA(cudaFuncSetAttribute(k_small_mma<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            k_small_mma<1><<<grid, 32 * kWarps, smem, ctx->stream>>>(H, M, P.n_H, reps, m, d_u, d_traj, n, src, d_dst_energy, inv_norm);
+            k_small_mma<1><<<grid, 32 * kWarps, smem, ctx->stream>>>(H, M, P.n_H, reps, m, d_u, d_traj, n, src, d_dst_energy, inv_norm, d_s);
         } else {
             DQ_CUDA(cudaFuncSetAttribute(k_small_mma<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            k_small_mma<2><<<grid, 32 * kWarps, smem, ctx->stream>>>(H, M, P.n_H, reps, m, d_u, d_traj, n, src, d_dst_energy, inv_norm);
+            k_small_mma<2><<<grid, 32 * kWarps, smem, ctx->stream>>>(H, M, P.n_H, reps, m, d_u, d_traj, n, src, d_dst_energy, inv_norm, d_s);
         }
     } else if (!d_dst_energy)
         k_small<false, 1><<<grid, 32 * kWarps, 0, ctx->stream>>>(H, M, P.n_H, mode, reps, m, d_u, d_traj, n, src,
-                                                                 reinterpret_cast<double2*>(d_dst_kets), nullptr, inv_norm);
+                                                                 reinterpret_cast<double2*>(d_dst_kets), nullptr, inv_norm, d_s);
     else if (kets_per_traj == 1)
-        k_small<true, 1><<<grid, 32 * kWarps, 0, ctx->stream>>>(H, M, P.n_H, mode, reps, m, d_u, d_traj, n, src, nullptr, d_dst_energy, inv_norm);
+        k_small<true, 1><<<grid, 32 * kWarps, 0, ctx->stream>>>(H, M, P.n_H, mode, reps, m, d_u, d_traj, n, src, nullptr, d_dst_energy, inv_norm, d_s);
     else if (kets_per_traj == 2)
-        k_small<true, 2><<<grid, 32 * kWarps, 0, ctx->stream>>>(H, M, P.n_H, mode, reps, m, d_u, d_traj, n, src, nullptr, d_dst_energy, inv_norm);
+        k_small<true, 2><<<grid, 32 * kWarps, 0, ctx->stream>>>(H, M, P.n_H, mode, reps, m, d_u, d_traj, n, src, nullptr, d_dst_energy, inv_norm, d_s);
     else
-        k_small<true, 4><<<grid, 32 * kWarps, 0, ctx->stream>>>(H, M, P.n_H, mode, reps, m, d_u, d_traj, n, src, nullptr, d_dst_energy, inv_norm);
+        k_small<true, 4><<<grid, 32 * kWarps, 0, ctx->stream>>>(H, M, P.n_H, mode, reps, m, d_u, d_traj, n, src, nullptr, d_dst_energy, inv_norm, d_s);
     ctx->launches++;
     DQ_CUDA(cudaGetLastError());
+    return DQ_OK;
+}
+
+// d_src / d_dst_kets: [..][16] c128; d_u: packed pulse rows [..][n_H]; traj: host descriptors (copied here)
+int small_run(dq_context* ctx, const Problem& P, int mode, int s, int m, int kets_per_traj, const std::vector<SmallTraj>& traj,
+              const double* d_u, const double* d_src, double* d_dst_kets, double* d_dst_energy, double inv_norm) {
+    State* S = state_of(ctx);
+    if (traj.empty()) return DQ_OK;
+    DQ_TRY(S->small_traj.reserve(traj.size() * sizeof(SmallTraj)));
+    DQ_CUDA(cudaMemcpyAsync(S->small_traj.p, traj.data(), traj.size() * sizeof(SmallTraj), cudaMemcpyHostToDevice, ctx->stream));
+    if (!S->ev0) {
+        DQ_CUDA(cudaEventCreate(&S->ev0));
+        DQ_CUDA(cudaEventCreate(&S->ev1));
+    }
+    DQ_CUDA(cudaEventRecord(S->ev0, ctx->stream));
+    DQ_TRY(small_enqueue(ctx, P, mode, s, m, kets_per_traj, S->small_traj.as<SmallTraj>(), (int)traj.size(), d_u, d_src, d_dst_kets,
+                         d_dst_energy, inv_norm, nullptr));
     DQ_CUDA(cudaEventRecord(S->ev1, ctx->stream));
     DQ_CUDA(cudaStreamSynchronize(ctx->stream));        // the descriptor buffer is reused by the next call
     float ms = 0.f;

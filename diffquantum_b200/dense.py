@@ -89,6 +89,29 @@ class DenseSimulator(object):
             coeff.shape[1], MODES[mode or self.mode], _lib.ptr(out), _lib.ptr(u)))
         return out, u
 
+    def train_energy_device(self, coeff0, s_all, lr=2e-2, betas=(0.9, 0.999), eps=1e-8, r=0.5, e0=None, mode=None):
+        """The whole train_energy loop (sim_plain.py:245-305) on the device: dq_dense_train.  s_all [n_epoch, K] are the
+        sample times of every epoch (the caller draws them: np.random.uniform() * T each, sim_plain.py:167).
+        Returns (trained coefficients, losses [n_epoch] = loss_energy - e0, state of the last epoch's evolution)."""
+        if self.M is None or self.psi0 is None:
+            raise ValueError("train_energy_device needs M and psi0")
+        if self.basis != 'BSpline':
+            raise ValueError("the device-resident loop evaluates the B-spline ansatz only")
+        coeff = np.array(coeff0, dtype=np.float64, order="C")
+        s_all = np.ascontiguousarray(s_all, dtype=np.float64)
+        if s_all.ndim == 1:
+            s_all = s_all.reshape(-1, 1)
+        if e0 is None:
+            e0 = float(np.linalg.eigvalsh(self.M)[0])                  # M.eigenenergies()[0], sim_plain.py:294
+        losses = np.empty(s_all.shape[0])
+        final = np.empty(self.dim, dtype=np.complex128)
+        _lib.check(_lib.load().dq_dense_train(
+            self.ctx.handle, self.dim, _lib.ptr(self.H0), self.n_H, _lib.ptr(self.Hs), _lib.ptr(self.M), _lib.ptr(self.psi0),
+            _lib.ptr(self.omegas), self.T, int(self.per_step), coeff.shape[1], _lib.ptr(coeff), s_all.shape[0], s_all.shape[1],
+            _lib.ptr(s_all), float(lr), float(betas[0]), float(betas[1]), float(eps), float(r), float(e0),
+            MODES[mode or self.mode], _lib.ptr(losses), _lib.ptr(final)))
+        return coeff, losses, final
+
     def stat(self, name):
         v = ctypes.c_double()
         _lib.check(_lib.load().dq_dense_last_stat(self.ctx.handle, name.encode(), ctypes.byref(v)))

@@ -9,7 +9,8 @@ class EnergyTrainer(object):
     """backend: DenseSimulator or IsingSimulator (needs .evolve energies and .grad_samples).
     n_samples > 1 averages that many stochastic samples per epoch (the reference uses 1)."""
 
-    def __init__(self, backend, n_basis=6, n_epoch=202, lr=2e-2, n_samples=1, ground_energy=None, is_noisy=False):
+    def __init__(self, backend, n_basis=6, n_epoch=202, lr=2e-2, n_samples=1, ground_energy=None, is_noisy=False,
+                 device_resident=False):
         self.backend = backend
         self.n_basis = n_basis
         self.n_epoch = n_epoch
@@ -17,6 +18,10 @@ class EnergyTrainer(object):
         self.n_samples = n_samples
         self.ground_energy = ground_energy
         self.is_noisy = is_noisy                       # SimulatorPlain(is_noisy=True): sim_plain.py:283-284, 207-208, 217-218
+        # True: the whole loop runs on the device (backend.train_energy_device); the sample times are drawn up front from the
+        # same np.random stream the reference consumes one per epoch (nothing else draws from it unless is_noisy)
+        self.device_resident = device_resident
+        self.device_ms = None
         self.losses_energy = []
         self.final_state = None
         self.spectral_coeff = None
@@ -41,6 +46,16 @@ class EnergyTrainer(object):
         import torch
         n_H, T = self._n_terms(), self._T()
         coeff = np.random.normal(0, 1e-3, [n_H, self.n_basis])             # sim_plain.py:259
+        if self.device_resident:
+            if self.is_noisy:
+                raise ValueError("is_noisy interleaves noise draws with the sample times: use the host loop")
+            s_all = np.array([[np.random.uniform() * T for _ in range(self.n_samples)] for _ in range(self.n_epoch)])   # :167
+            c, losses, final = self.backend.train_energy_device(coeff, s_all, lr=self.lr, e0=self.ground_energy)
+            self.spectral_coeff = torch.tensor(c, requires_grad=True)
+            self.losses_energy = list(losses)
+            self.final_state = final
+            self.device_ms = self.backend.stat("kernel_ms") if hasattr(self.backend, "stat") else None
+            return self.spectral_coeff
         self.spectral_coeff = torch.tensor(coeff, requires_grad=True)
         optimizer = torch.optim.Adam([self.spectral_coeff], lr=self.lr)     # :266
         e0 = self.ground_energy

@@ -15,6 +15,7 @@
  *   dq_dense_evolve     SimulatorPlain.trotter  sim_plain.py:119-153   (solver hook, sim_plain.py:43)
  *   dq_dense_grad       compute_energy_grad_MC  sim_plain.py:186-220   (prefix + 2*n_H shifted suffixes)
  *   dq_dense_grad_times the same + generate_u   sim_plain.py:52-99,186-220 (pulse rows evaluated on the device)
+ *   dq_dense_train      train_energy            sim_plain.py:245-305   (whole loop on the device, dim <= 16)
  *   dq_ising_*          the same two paths for Pauli-term (MaxCut/QAOA) Hamiltonians that the dense
  *                       nested-list API cannot express beyond n~13 (demo_maxcut.py:19-85 builds
  *                       them with np.kron) — step semantics of diffqc.cc:155-164.
@@ -105,6 +106,17 @@ int dq_dense_grad_times(dq_context* ctx, int dim, const double* H0, int n_H, con
                         const double* psi0, double r, int n_samples, const double* s_list, double T, int per_step,
                         const double* coeff, const double* omegas, int n_basis, int mode, double* energies_out,
                         double* u_out);
+
+/* Device-resident SimulatorPlain.train_energy (sim_plain.py:245-305) for dim <= 16 and the B-spline ansatz: n_epoch epochs of
+ * (full evolution + energy, K stochastic gradient samples, their mean, torch-style Adam) enqueued without a host round trip.
+ * s_all [n_epoch][K]: the sample times, drawn by the caller from the reference's stream (one np.random.uniform() * T per
+ * sample, sim_plain.py:167).  coeff_inout [n_H][n_basis]: start coefficients in, trained coefficients out.  e0: the
+ * observable's lowest eigenvalue (the reference recomputes it every epoch, :294).  losses_out [n_epoch] = loss_energy - e0
+ * as train_energy logs it; final_state_out [dim] c128 (may be NULL) = the state of the last epoch's full evolution (:303). */
+int dq_dense_train(dq_context* ctx, int dim, const double* H0, int n_H, const double* Hs, const double* M,
+                   const double* psi0, const double* omegas, double T, int per_step, int n_basis, double* coeff_inout,
+                   int n_epoch, int K, const double* s_all, double lr, double beta1, double beta2, double eps, double r,
+                   double e0, int mode, double* losses_out, double* final_state_out);
 
 /* Counters of the last dense call: "gemm_flops" (real flops issued to the DMMA GEMM), "strategy"
  * (0 block-Taylor, 1 per-step propagator, 2 chained propagator, 3 resident warp-per-trajectory engine, dim <= 16),

@@ -383,3 +383,32 @@ def test_device_pulse_tables_match_host_tables_and_reference(golden, name):
     assert rel(grads, g["grads"]) < TOL
     sim.device_tables = False
     assert rel(sim.grad_samples(g["coeff"], g["s"]), grads) < 1e-13
+
+
+def test_device_resident_training_follows_the_reference_run(golden):
+    """dq_dense_train: the whole train_energy loop (full evolution, gradient sample, Adam) on the device, no host round trip
+    between epochs -- against the reference's own 202-epoch demo_maxcut.py run (np.random.seed(0)) and against the host-driven
+    loop (EnergyTrainer with torch Adam)."""
+    g = golden("demo_training_ref")
+    sim = dq.DenseSimulator(g["H0"], g["Hs"], g["omegas"], float(g["T"]), M=g["H_cost"], psi0=g["psi0"], per_step=10)
+    np.random.seed(0)
+    dev = dq.EnergyTrainer(sim, n_basis=6, n_epoch=202, lr=2e-2, device_resident=True)
+    dev.train_energy()
+    ref = g["losses_energy"]
+    assert len(dev.losses_energy) == 202
+    assert np.abs(np.array(dev.losses_energy) - ref).max() < 1e-8                 # the 1e-8 is Adam's rounding over 202 steps
+    assert np.abs(dev.spectral_coeff.detach().numpy() - g["final_coeff"]).max() < 1e-8
+    assert rel(dev.final_state, g["final_state"]) < 1e-8
+    assert dev.find_state()[0] in (0b0101, 0b1010)                                # a maximum cut of the 4-ring (demo_maxcut.py:88-89)
+    np.random.seed(0)
+    host = dq.EnergyTrainer(sim, n_basis=6, n_epoch=202, lr=2e-2)
+    host.train_energy()
+    assert np.abs(np.array(dev.losses_energy) - np.array(host.losses_energy)).max() < 1e-9
+    # K > 1: the gradient is the mean over the epoch's samples
+    np.random.seed(3)
+    a = dq.EnergyTrainer(sim, n_basis=6, n_epoch=12, lr=2e-2, n_samples=5, device_resident=True)
+    a.train_energy()
+    np.random.seed(3)
+    b = dq.EnergyTrainer(sim, n_basis=6, n_epoch=12, lr=2e-2, n_samples=5)
+    b.train_energy()
+    assert np.abs(np.array(a.losses_energy) - np.array(b.losses_energy)).max() < 1e-10
