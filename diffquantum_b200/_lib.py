@@ -53,6 +53,10 @@ SIGNATURES = {
     "dq_ising_grad_run_staged": (ctypes.c_int, [_VP]),
     "dq_ising_grad_fetch": (ctypes.c_int, [_VP, _VP]),
     "dq_ising_last_stat": (ctypes.c_int, [_VP, ctypes.c_char_p, ctypes.POINTER(ctypes.c_double)]),
+    "dq_ising_train": (ctypes.c_int, [_VP, ctypes.c_int, _VP, _VP, _VP, _VP, ctypes.c_double, ctypes.c_double, ctypes.c_int,
+                                      ctypes.c_int, _VP, ctypes.c_int, ctypes.c_int, _VP, ctypes.c_double, ctypes.c_double,
+                                      ctypes.c_double, ctypes.c_double, ctypes.c_double, ctypes.c_double, _VP, _VP, _VP,
+                                      ctypes.POINTER(ctypes.c_double)]),
     "dq_slice_fill_uniform": (ctypes.c_int, [_VP, _VP, ctypes.c_int, ctypes.c_int]),
     "dq_slice_phase": (ctypes.c_int, [_VP, _VP, ctypes.c_int, ctypes.c_uint64, ctypes.c_int, ctypes.c_int, _VP, _VP]),
     "dq_slice_rx": (ctypes.c_int, [_VP, _VP, ctypes.c_int, ctypes.c_int, ctypes.c_double]),

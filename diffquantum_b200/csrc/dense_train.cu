@@ -18,6 +18,7 @@
 #include <string.h>
 #include <vector>
 #include "dense.cuh"
+#include "train_update.cuh"
 
 namespace dq {
 namespace dense {
@@ -65,51 +66,12 @@ __global__ void k_train_scale(unsigned long long* __restrict__ bound_bits, int* 
     *bound_bits = 0ull;                                      // ready for the next epoch
 }
 
-// one thread per coefficient (i, j); a single block
-__global__ void k_train_update(const double* __restrict__ energies, const double* __restrict__ s_vals, int K, double* __restrict__ coeff,
-                               double* __restrict__ m1, double* __restrict__ m2, const double* __restrict__ omegas, double T,
-                               int n_H, int n_basis, const double* __restrict__ bl, const double* __restrict__ br, double norm_factor,
-                               double r, double beta1, double beta2, double eps, double step_size, double bc2_sqrt,
-                               const double* __restrict__ e_full, double e0, double* __restrict__ losses, int epoch) {
-    const int idx = threadIdx.x;
-    const int i = idx / n_basis, j = idx % n_basis;
-    double newc = 0.0;
-    if (idx < n_H * n_basis) {
-        double g = 0.0;
-        for (int k = 0; k < K; ++k) {
-            const double x = s_vals[k] / T;
-            double a = 0.0, phij = 0.0;
-            for (int jj = 0; jj < n_basis; ++jj) {
-                const double ph = bump(x, bl[jj], br[jj], norm_factor);
-                a = __dadd_rn(a, __dmul_rn(coeff[i * n_basis + jj], ph));
-                if (jj == j) phij = ph;
-            }
-            const double sg = 1.0 / (1.0 + exp(-a));
-            const double dudc = omegas[i] * 2.0 * sg * (1.0 - sg) * phij;                // sim_plain.py:169-184 in closed form
-            const double* e = energies + ((size_t)k * n_H + i) * 2;
-            const double ps = (1.0 + r * r) / 2.0 / r * (e[1] - e[0]);                    // :220
-            g += ps * dudc;                                                              // :227
-        }
-        g /= (double)K;
-        // torch.optim.Adam, single-tensor path: exp_avg.lerp_(g, 1 - b1); exp_avg_sq.mul_(b2).addcmul_(g, g, 1 - b2);
-        // denom = sqrt(exp_avg_sq) / sqrt(bc2) + eps; param += -(lr / bc1) * exp_avg / denom
-        const double a1 = m1[idx] + (1.0 - beta1) * (g - m1[idx]);
-        const double a2 = m2[idx] * beta2 + (1.0 - beta2) * g * g;
-        m1[idx] = a1;
-        m2[idx] = a2;
-        const double denom = sqrt(a2) / bc2_sqrt + eps;
-        newc = coeff[idx] - step_size * (a1 / denom);
-    }
-    __syncthreads();                                         // every thread has read the old coefficients of its row
-    if (idx < n_H * n_basis) coeff[idx] = newc;
-    if (idx == 0) losses[epoch] = *e_full - e0;              // loss_energy - M.eigenenergies()[0], :281,:294
-}
-
 }  // namespace
 }  // namespace dense
 }  // namespace dq
 
 using namespace dq::dense;
+using dq::k_train_update;
 
 extern "C" int dq_dense_train(dq_context* ctx, int dim, const double* H0, int n_H, const double* Hs, const double* M,
                               const double* psi0, const double* omegas, double T, int per_step, int n_basis, double* coeff_inout,

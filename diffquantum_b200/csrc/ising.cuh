@@ -29,6 +29,7 @@ struct dq_ising {
     // work buffers
     dq::DevBuf states, phi, rows_a, rows_b, trig_a, trig_b, energies, scratch, io, shift_desc;
     dq::DevBuf exact_diag, exact_t0, exact_t1;     // exact-step workspaces (generic engine)
+    dq::DevBuf train;                              // device-resident training loop (ising_train.cu)
     int step_mode = 0;             // 0 split (per-term product, diffqc.cc:155-164), 1 exact (live semantics, sim_plain.py:135-150)
     std::vector<double> host_rows_a, host_rows_b;  // exact step: host copy of the staged rows (norm bound per step)
 
@@ -40,7 +41,9 @@ struct dq_ising {
         std::vector<int> prefix_steps, suffix_steps, shift_kind, shift_index;
         std::vector<int64_t> prefix_off, suffix_off;     // row offsets
         bool uniform_psi0 = true;
-        bool scaled_ok = true;                            // every |x angle| and atan(r) <= 1 rad
+        bool scaled_ok = true;                            // every |x angle| and atan(r) <= 1 rad (all samples)
+        std::vector<char> scaled_sample;                  // the same per sample; empty: scaled_ok for all
+        double exact_bound = -1.0;                        // >= 0: rows live on the device only; bound on every ||dt H(t_k)|| (exact step)
         dq::DevBuf psi0;                                  // physical order, when not uniform
     } st;
 
@@ -69,11 +72,18 @@ int gen_permute_real_in(dq_ising* p, const double* src_ref_order, double* dst_ph
 int gen_trig(dq_ising* p, const double* d_rows, int64_t n_rows, double2* d_trig);
 int gen_evolve(dq_ising* p, c128* d_states, int batch, const double* d_rows, const double2* d_trig,
                int n_steps);
-int gen_evolve_exact(dq_ising* p, c128* d_states, int batch, const double* d_rows, const double* h_rows, int n_steps);
+int gen_evolve_exact(dq_ising* p, c128* d_states, int batch, const double* d_rows, const double* h_rows, int n_steps,
+                     double uniform_bound = -1.0);
 int gen_fanout(dq_ising* p, const c128* d_phi, c128* d_kets, int n_kets, const ShiftDesc* d_desc,
                double r);
 int gen_energy(dq_ising* p, const c128* d_states, int batch, double* d_out);
 int gen_build_mdiag(dq_ising* p, const double* m_zz, double m_const);
+
+// staging pieces shared by dq_ising_grad_stage and the device-resident training loop (ising_api.cu)
+int stage_meta(dq_ising* p, int n_samples, const int32_t* prefix_steps, const int32_t* suffix_steps, int n_shift,
+               const int32_t* shift_kind, const int32_t* shift_index, double r, const double* psi0);
+int stage_trig(dq_ising* p);
+bool engine_is_fused(const dq_ising* p);
 
 // fused persistent engine (n >= 12)
 int fused_supported(const dq_ising* p);
@@ -82,6 +92,6 @@ void fused_release(dq_ising* p);
 int fused_launch_times(dq_ising* p, double* total_ms, double* n_launches);
 int fused_grad_run(dq_ising* p);
 int fused_evolve(dq_ising* p, c128* d_states, int batch, const double* h_rows, int n_steps,
-                 double* d_energies, bool want_states);
+                 double* d_energies, bool want_states, const double* d_rows = nullptr, int scaled_hint = -1);
 
 }  // namespace dq

@@ -146,6 +146,95 @@ int apply_layout(dq_ising* p) {
 
 }  // namespace
 
+namespace dq {
+
+// Everything of a staged gradient batch except the angle rows: step counts and row offsets, the shifted-ket descriptors,
+// the initial state, buffer sizes.  The rows are written into p->rows_a / p->rows_b by the caller (H2D copy in
+// dq_ising_grad_stage, a device kernel in the device-resident training loop).
+int stage_meta(dq_ising* p, int n_samples, const int32_t* prefix_steps, const int32_t* suffix_steps, int n_shift,
+               const int32_t* shift_kind, const int32_t* shift_index, double r, const double* psi0) {
+    DQ_REQUIRE(p, "NULL problem");
+    DQ_REQUIRE(n_samples >= 1 && n_shift >= 1, "dq_ising_grad: n_samples=%d n_shift=%d", n_samples, n_shift);
+    DQ_REQUIRE(prefix_steps && suffix_steps && shift_kind && shift_index, "dq_ising_grad: NULL table");
+    DQ_REQUIRE(r > 0 && isfinite(r), "dq_ising_grad: r must be positive");
+    DQ_TRY(p->ctx->set_device());
+    auto& s = p->st;
+    s.valid = false;
+    s.exact_bound = -1.0;
+    s.scaled_sample.clear();
+    s.n_samples = n_samples;
+    s.n_shift = n_shift;
+    s.r = r;
+    s.prefix_steps.assign(prefix_steps, prefix_steps + n_samples);
+    s.suffix_steps.assign(suffix_steps, suffix_steps + n_samples);
+    s.shift_kind.assign(shift_kind, shift_kind + n_shift);
+    s.shift_index.assign(shift_index, shift_index + n_shift);
+    s.prefix_off.resize(n_samples + 1);
+    s.suffix_off.resize(n_samples + 1);
+    s.prefix_off[0] = s.suffix_off[0] = 0;
+    for (int b = 0; b < n_samples; ++b) {
+        DQ_REQUIRE(prefix_steps[b] >= 0 && suffix_steps[b] >= 0, "dq_ising_grad: negative step count (sample %d)", b);
+        s.prefix_off[b + 1] = s.prefix_off[b] + prefix_steps[b];
+        s.suffix_off[b + 1] = s.suffix_off[b] + suffix_steps[b];
+    }
+    for (int i = 0; i < n_shift; ++i) {
+        if (shift_kind[i] == 0)
+            DQ_REQUIRE(shift_index[i] >= 0 && shift_index[i] < p->n_zz, "dq_ising_grad: shift %d: ZZ pair %d of %d", i, shift_index[i], p->n_zz);
+        else if (shift_kind[i] == 1)
+            DQ_REQUIRE(shift_index[i] >= 0 && shift_index[i] < p->n, "dq_ising_grad: shift %d: qubit %d of %d", i, shift_index[i], p->n);
+        else
+            DQ_REQUIRE(false, "dq_ising_grad: shift %d: unknown kind %d", i, shift_kind[i]);
+    }
+    const int64_t np = s.prefix_off[n_samples], ns = s.suffix_off[n_samples];
+    cudaStream_t st = p->ctx->stream;
+    const size_t rb = p->row_len * sizeof(double);
+    DQ_TRY(p->rows_a.reserve((np ? np : 1) * rb));
+    DQ_TRY(p->rows_b.reserve((ns ? ns : 1) * rb));
+    // shifted-ket descriptors, order [i][+,-]
+    std::vector<dq::ShiftDesc> h(2 * n_shift);
+    for (int i = 0; i < n_shift; ++i)
+        for (int sg = 0; sg < 2; ++sg) {
+            dq::ShiftDesc d;
+            d.kind = shift_kind[i];
+            if (d.kind == 0) { d.b0 = p->pa[shift_index[i]]; d.b1 = p->pb[shift_index[i]]; }
+            else { d.b0 = p->bitpos[shift_index[i]]; d.b1 = 0; }
+            d.sign = sg == 0 ? +1.0 : -1.0;
+            h[2 * i + sg] = d;
+        }
+    DQ_TRY(p->shift_desc.reserve(h.size() * sizeof(dq::ShiftDesc)));
+    DQ_CUDA(cudaMemcpyAsync(p->shift_desc.p, h.data(), h.size() * sizeof(dq::ShiftDesc), cudaMemcpyHostToDevice, st));
+    s.uniform_psi0 = psi0 == nullptr;
+    if (psi0) {
+        DQ_TRY(s.psi0.reserve(p->dim() * sizeof(c128)));
+        if (p->identity_layout) {
+            DQ_CUDA(cudaMemcpyAsync(s.psi0.p, psi0, p->dim() * sizeof(c128), cudaMemcpyHostToDevice, st));
+        } else {
+            DQ_TRY(p->io.reserve(p->dim() * sizeof(c128)));
+            DQ_CUDA(cudaMemcpyAsync(p->io.p, psi0, p->dim() * sizeof(c128), cudaMemcpyHostToDevice, st));
+            DQ_TRY(dq::gen_permute_in(p, p->io.as<c128>(), s.psi0.as<c128>(), 1));
+        }
+    }
+    DQ_TRY(p->energies.reserve((size_t)n_samples * 2 * n_shift * sizeof(double)));
+    DQ_CUDA(cudaStreamSynchronize(st));          // `h` goes out of scope
+    return DQ_OK;
+}
+
+// generic engine only: (cos, sin) of the X angles of the rows now in p->rows_a / p->rows_b
+int stage_trig(dq_ising* p) {
+    if (use_fused(p)) return DQ_OK;
+    auto& s = p->st;
+    const int64_t np = s.prefix_off[s.n_samples], ns = s.suffix_off[s.n_samples];
+    DQ_TRY(p->trig_a.reserve((np ? np : 1) * p->n * sizeof(double2)));
+    DQ_TRY(p->trig_b.reserve((ns ? ns : 1) * p->n * sizeof(double2)));
+    DQ_TRY(dq::gen_trig(p, p->rows_a.as<double>(), np, p->trig_a.as<double2>()));
+    DQ_TRY(dq::gen_trig(p, p->rows_b.as<double>(), ns, p->trig_b.as<double2>()));
+    return DQ_OK;
+}
+
+bool engine_is_fused(const dq_ising* p) { return use_fused(p); }
+
+}  // namespace dq
+
 extern "C" {
 
 int dq_ising_create(dq_context* ctx, int n_qubits, int n_zz, const int32_t* zz_pairs,
@@ -187,7 +276,7 @@ int dq_ising_destroy(dq_ising* p) {
     dq::fused_release(p);
     dq::DevBuf* bufs[] = {&p->mdiag, &p->mdiag_ref, &p->pairs_dev, &p->states, &p->phi, &p->rows_a, &p->rows_b, &p->trig_a,
                           &p->trig_b, &p->energies, &p->scratch, &p->io, &p->shift_desc, &p->st.psi0, &p->exact_diag, &p->exact_t0,
-                          &p->exact_t1};
+                          &p->exact_t1, &p->train};
     for (auto* b : bufs) b->release();
     delete p;
     return DQ_OK;
@@ -313,91 +402,35 @@ int dq_ising_evolve(dq_ising* p, int batch, int n_steps, const double* angles, c
 int dq_ising_grad_stage(dq_ising* p, int n_samples, const int32_t* prefix_steps, const double* prefix_angles,
                         const int32_t* suffix_steps, const double* suffix_angles, int n_shift,
                         const int32_t* shift_kind, const int32_t* shift_index, double r, const double* psi0) {
-    DQ_REQUIRE(p, "NULL problem");
-    DQ_REQUIRE(n_samples >= 1 && n_shift >= 1, "dq_ising_grad: n_samples=%d n_shift=%d", n_samples, n_shift);
-    DQ_REQUIRE(prefix_steps && suffix_steps && shift_kind && shift_index, "dq_ising_grad: NULL table");
-    DQ_REQUIRE(r > 0 && isfinite(r), "dq_ising_grad: r must be positive");
-    DQ_TRY(p->ctx->set_device());
+    DQ_TRY(dq::stage_meta(p, n_samples, prefix_steps, suffix_steps, n_shift, shift_kind, shift_index, r, psi0));
     auto& s = p->st;
-    s.valid = false;
-    s.n_samples = n_samples;
-    s.n_shift = n_shift;
-    s.r = r;
-    s.prefix_steps.assign(prefix_steps, prefix_steps + n_samples);
-    s.suffix_steps.assign(suffix_steps, suffix_steps + n_samples);
-    s.shift_kind.assign(shift_kind, shift_kind + n_shift);
-    s.shift_index.assign(shift_index, shift_index + n_shift);
-    s.prefix_off.resize(n_samples + 1);
-    s.suffix_off.resize(n_samples + 1);
-    s.prefix_off[0] = s.suffix_off[0] = 0;
-    for (int b = 0; b < n_samples; ++b) {
-        DQ_REQUIRE(prefix_steps[b] >= 0 && suffix_steps[b] >= 0, "dq_ising_grad: negative step count (sample %d)", b);
-        s.prefix_off[b + 1] = s.prefix_off[b] + prefix_steps[b];
-        s.suffix_off[b + 1] = s.suffix_off[b] + suffix_steps[b];
-    }
-    for (int i = 0; i < n_shift; ++i) {
-        if (shift_kind[i] == 0)
-            DQ_REQUIRE(shift_index[i] >= 0 && shift_index[i] < p->n_zz, "dq_ising_grad: shift %d: ZZ pair %d of %d", i, shift_index[i], p->n_zz);
-        else if (shift_kind[i] == 1)
-            DQ_REQUIRE(shift_index[i] >= 0 && shift_index[i] < p->n, "dq_ising_grad: shift %d: qubit %d of %d", i, shift_index[i], p->n);
-        else
-            DQ_REQUIRE(false, "dq_ising_grad: shift %d: unknown kind %d", i, shift_kind[i]);
-    }
     const int64_t np = s.prefix_off[n_samples], ns = s.suffix_off[n_samples];
     DQ_TRY(check_rows(p, prefix_angles, np, "dq_ising_grad(prefix)"));
     DQ_TRY(check_rows(p, suffix_angles, ns, "dq_ising_grad(suffix)"));
     cudaStream_t st = p->ctx->stream;
     const size_t rb = p->row_len * sizeof(double);
-    DQ_TRY(p->rows_a.reserve((np ? np : 1) * rb));
-    DQ_TRY(p->rows_b.reserve((ns ? ns : 1) * rb));
     if (np) DQ_CUDA(cudaMemcpyAsync(p->rows_a.p, prefix_angles, np * rb, cudaMemcpyHostToDevice, st));
     if (ns) DQ_CUDA(cudaMemcpyAsync(p->rows_b.p, suffix_angles, ns * rb, cudaMemcpyHostToDevice, st));
-    // shifted-ket descriptors, order [i][+,-]
-    std::vector<dq::ShiftDesc> h(2 * n_shift);
-    for (int i = 0; i < n_shift; ++i)
-        for (int sg = 0; sg < 2; ++sg) {
-            dq::ShiftDesc d;
-            d.kind = shift_kind[i];
-            if (d.kind == 0) { d.b0 = p->pa[shift_index[i]]; d.b1 = p->pb[shift_index[i]]; }
-            else { d.b0 = p->bitpos[shift_index[i]]; d.b1 = 0; }
-            d.sign = sg == 0 ? +1.0 : -1.0;
-            h[2 * i + sg] = d;
-        }
-    DQ_TRY(p->shift_desc.reserve(h.size() * sizeof(dq::ShiftDesc)));
-    DQ_CUDA(cudaMemcpyAsync(p->shift_desc.p, h.data(), h.size() * sizeof(dq::ShiftDesc), cudaMemcpyHostToDevice, st));
     {
-        double mx = fabs(atan(r));
         const int off_x = 1 + p->n_zz;
-        for (int64_t k = 0; k < np; ++k)
-            for (int q = 0; q < p->n; ++q) mx = fmax(mx, fabs(prefix_angles[k * p->row_len + off_x + q]));
-        for (int64_t k = 0; k < ns; ++k)
-            for (int q = 0; q < p->n; ++q) mx = fmax(mx, fabs(suffix_angles[k * p->row_len + off_x + q]));
-        s.scaled_ok = mx <= 1.0;
-    }
-    s.uniform_psi0 = psi0 == nullptr;
-    if (psi0) {
-        DQ_TRY(s.psi0.reserve(p->dim() * sizeof(c128)));
-        if (p->identity_layout) {
-            DQ_CUDA(cudaMemcpyAsync(s.psi0.p, psi0, p->dim() * sizeof(c128), cudaMemcpyHostToDevice, st));
-        } else {
-            DQ_TRY(p->io.reserve(p->dim() * sizeof(c128)));
-            DQ_CUDA(cudaMemcpyAsync(p->io.p, psi0, p->dim() * sizeof(c128), cudaMemcpyHostToDevice, st));
-            DQ_TRY(dq::gen_permute_in(p, p->io.as<c128>(), s.psi0.as<c128>(), 1));
+        s.scaled_sample.assign(n_samples, 0);
+        s.scaled_ok = true;
+        for (int b = 0; b < n_samples; ++b) {
+            double mx = fabs(atan(r));
+            for (int64_t k = s.prefix_off[b]; k < s.prefix_off[b + 1]; ++k)
+                for (int q = 0; q < p->n; ++q) mx = fmax(mx, fabs(prefix_angles[k * p->row_len + off_x + q]));
+            for (int64_t k = s.suffix_off[b]; k < s.suffix_off[b + 1]; ++k)
+                for (int q = 0; q < p->n; ++q) mx = fmax(mx, fabs(suffix_angles[k * p->row_len + off_x + q]));
+            s.scaled_sample[b] = mx <= 1.0;
+            s.scaled_ok = s.scaled_ok && mx <= 1.0;
         }
     }
-    DQ_TRY(p->energies.reserve((size_t)n_samples * 2 * n_shift * sizeof(double)));
-    if (!use_fused(p)) {
-        DQ_TRY(p->trig_a.reserve((np ? np : 1) * p->n * sizeof(double2)));
-        DQ_TRY(p->trig_b.reserve((ns ? ns : 1) * p->n * sizeof(double2)));
-        DQ_TRY(dq::gen_trig(p, p->rows_a.as<double>(), np, p->trig_a.as<double2>()));
-        DQ_TRY(dq::gen_trig(p, p->rows_b.as<double>(), ns, p->trig_b.as<double2>()));
-    }
+    DQ_TRY(dq::stage_trig(p));
     if (p->step_mode == 1) {
         p->host_rows_a.assign(prefix_angles, prefix_angles + np * p->row_len);
         p->host_rows_b.assign(suffix_angles, suffix_angles + ns * p->row_len);
     }
-    DQ_CUDA(cudaStreamSynchronize(st));          // host vectors above go out of scope
-    // keep host copies of the rows for the fused engine's table builder
+    DQ_CUDA(cudaStreamSynchronize(st));          // the caller's tables may go out of scope
     s.valid = true;
     return DQ_OK;
 }
@@ -421,11 +454,14 @@ int dq_ising_grad_run_staged(dq_ising* p) {
             if (s.uniform_psi0) DQ_TRY(dq::gen_fill_uniform(p, phi, 1));
             else DQ_CUDA(cudaMemcpyAsync(phi, s.psi0.p, N * sizeof(c128), cudaMemcpyDeviceToDevice, st));
             if (p->step_mode == 1) {
+                const bool dev_rows = s.exact_bound >= 0.0;
                 DQ_TRY(dq::gen_evolve_exact(p, phi, 1, p->rows_a.as<double>() + s.prefix_off[b] * p->row_len,
-                                            p->host_rows_a.data() + s.prefix_off[b] * p->row_len, s.prefix_steps[b]));
+                                            dev_rows ? nullptr : p->host_rows_a.data() + s.prefix_off[b] * p->row_len, s.prefix_steps[b],
+                                            s.exact_bound));
                 DQ_TRY(dq::gen_fanout(p, phi, p->states.as<c128>(), kets, p->shift_desc.as<dq::ShiftDesc>(), s.r));
                 DQ_TRY(dq::gen_evolve_exact(p, p->states.as<c128>(), kets, p->rows_b.as<double>() + s.suffix_off[b] * p->row_len,
-                                            p->host_rows_b.data() + s.suffix_off[b] * p->row_len, s.suffix_steps[b]));
+                                            dev_rows ? nullptr : p->host_rows_b.data() + s.suffix_off[b] * p->row_len, s.suffix_steps[b],
+                                            s.exact_bound));
                 DQ_TRY(dq::gen_energy(p, p->states.as<c128>(), kets, p->energies.as<double>() + (size_t)b * kets));
                 continue;
             }

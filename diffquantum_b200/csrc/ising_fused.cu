@@ -67,7 +67,7 @@ constexpr int kMaxGroup = 128;             // kets per launch (their descriptors
 #endif
 
 
-enum : int { F_ENERGY = 2, F_STORE = 4 };
+enum : int { F_ENERGY = 2, F_STORE = 4, F_SCALED = 8 };   // F_SCALED: setup jobs only (lifting-form tables for this trajectory)
 
 struct __align__(16) PassStep {
     double2 tkk[32];                // base phase over the 5 K bits (includes constant + cos scale)
@@ -1523,8 +1523,9 @@ __device__ __forceinline__ double zsign(int bits, int i) { return ((bits >> i) &
 __global__ void __launch_bounds__(128) k_setup(const SetupJob* __restrict__ jobs, const double* __restrict__ rows,
                                                int row_len, int n_zz, const TypePlan* __restrict__ types,
                                                PassStep* __restrict__ steps, double2* __restrict__ tc,
-                                               int n_col_bits, int scaled) {
+                                               int n_col_bits) {
     const SetupJob job = jobs[blockIdx.x];
+    const bool scaled = (job.flags & F_SCALED) != 0;
     const TypePlan& T = types[job.type];
     PassStep& P = steps[blockIdx.x];
     const double* pre = job.row_pre >= 0 ? rows + job.row_pre * row_len : nullptr;
@@ -1571,7 +1572,7 @@ __global__ void __launch_bounds__(128) k_setup(const SetupJob* __restrict__ jobs
             P.rot[s][b] = scaled ? make_double2(sn / cs, sn * cs) : make_double2(cs, sn);     // (tan, sin cos) | (cos, sin)
         }
         if (tid == 0) {
-            P.flags = job.flags;
+            P.flags = job.flags & ~F_SCALED;
             P.type = job.type;
             P.tc_offset = tc_off;
         }
@@ -1917,6 +1918,7 @@ struct Traj {
     bool final_energy;
     size_t step0;          // first PassStep index (filled by add_traj)
     bool final_both = false;   // final pass stores AND reduces (the unshifted trajectory of the linear mode)
+    bool scaled = false;       // lifting-form tables (every |x angle| of the trajectory's sample <= 1)
 };
 
 static void add_traj(std::vector<SetupJob>& jobs, Traj& t) {
@@ -1927,11 +1929,12 @@ static void add_traj(std::vector<SetupJob>& jobs, Traj& t) {
         j.row_cur = p < t.n_steps ? t.row0 + p : -1;
         j.type = (p + t.cls) & 1;
         j.flags = p < t.n_steps ? F_STORE : (t.final_both ? (F_ENERGY | F_STORE) : (t.final_energy ? F_ENERGY : F_STORE));
+        if (t.scaled) j.flags |= F_SCALED;
         jobs.push_back(j);
     }
 }
 
-static int run_setup(dq_ising* p, Plan* pl, const std::vector<SetupJob>& jobs, const double* d_rows, bool scaled) {
+static int run_setup(dq_ising* p, Plan* pl, const std::vector<SetupJob>& jobs, const double* d_rows) {
     cudaStream_t st = p->ctx->stream;
     DQ_TRY(pl->jobs.reserve(jobs.size() * sizeof(SetupJob)));
     DQ_TRY(pl->steps.reserve(jobs.size() * sizeof(PassStep)));
@@ -1940,7 +1943,7 @@ static int run_setup(dq_ising* p, Plan* pl, const std::vector<SetupJob>& jobs, c
     const unsigned ncol = 1u << pl->n_col_bits;
     dim3 grid((unsigned)jobs.size(), std::max(1u, std::min(8u, ncol / 128)));
     k_setup<<<grid, 128, 0, st>>>(pl->jobs.as<SetupJob>(), d_rows, p->row_len, p->n_zz, pl->d_types.as<TypePlan>(),
-                                  pl->steps.as<PassStep>(), pl->tc.as<double2>(), pl->n_col_bits, scaled ? 1 : 0);
+                                  pl->steps.as<PassStep>(), pl->tc.as<double2>(), pl->n_col_bits);
     p->ctx->launches++;
     DQ_CUDA(cudaGetLastError());
     return DQ_OK;
@@ -2098,22 +2101,25 @@ void fused_release(dq_ising* p) {
 
 // Evolve `batch` states in place through the same rows (API: dq_ising_evolve).
 int fused_evolve(dq_ising* p, c128* d_states, int batch, const double* h_rows, int n_steps, double* d_energies,
-                 bool want_states) {
+                 bool want_states, const double* d_rows, int scaled_hint) {
     using namespace fused;
     Plan* pl = get_plan(p);
     DQ_REQUIRE(pl->ok, "fused engine unavailable for this problem");
     pl->ev_used = 0;
     cudaStream_t st = p->ctx->stream;
-    const bool scaled = rows_allow_scaled(p, h_rows, n_steps, 0.0);
+    // d_rows: the angle rows are already on the device (device-resident training); the caller vouches for the angle range
+    const bool scaled = d_rows ? scaled_hint != 0 : rows_allow_scaled(p, h_rows, n_steps, 0.0);
     const size_t N = p->dim();
     const int tiles = 1 << pl->tiles_log2;
     DQ_TRY(pl->rows.reserve((size_t)std::max(1, n_steps) * p->row_len * sizeof(double)));
     if (n_steps)
-        DQ_CUDA(cudaMemcpyAsync(pl->rows.p, h_rows, (size_t)n_steps * p->row_len * sizeof(double), cudaMemcpyHostToDevice, st));
+        DQ_CUDA(cudaMemcpyAsync(pl->rows.p, d_rows ? d_rows : h_rows, (size_t)n_steps * p->row_len * sizeof(double),
+                                d_rows ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
     std::vector<SetupJob> jobs;
     Traj tr{0, n_steps, 0, !want_states, 0};       // energy-only: the final pass reduces instead of storing
+    tr.scaled = scaled;
     add_traj(jobs, tr);
-    DQ_TRY(run_setup(p, pl, jobs, pl->rows.as<double>(), scaled));
+    DQ_TRY(run_setup(p, pl, jobs, pl->rows.as<double>()));
     std::vector<KetDesc> kets(batch);
     DQ_TRY(pl->partials.reserve((size_t)batch * tiles * sizeof(double)));
     DQ_TRY(maps_begin(p, pl, (size_t)batch));
@@ -2170,7 +2176,9 @@ int fused_grad_run(dq_ising* p) {
     const int tiles = 1 << pl->tiles_log2;
     const int B = s.n_samples, n_shift = s.n_shift, kets_per = 2 * n_shift;
     const int G = auto_ket_group(p);
-    const bool scaled = s.scaled_ok;
+    // lifting form or straight-line form is decided per SAMPLE (its own angles), so a sample's result does not depend on
+    // which other samples share its batch (bit-equal sharded runs, SURVEY 4 iv)
+    auto scaled_of = [&](int b) { return s.scaled_sample.empty() ? s.scaled_ok : s.scaled_sample[b] != 0; };
     const bool linear = p->linear != 0;   // one shifted ket per term + the unshifted suffix state (see k_linear_fix)
 
     // ---- tables: rows_a (prefix) and rows_b (suffix) live in one device table ---------------------
@@ -2184,15 +2192,17 @@ int fused_grad_run(dq_ising* p) {
         pre[b] = Traj{s.prefix_off[b], s.prefix_steps[b], 0, false, 0};
         sufL[b] = Traj{np + s.suffix_off[b], s.suffix_steps[b], 0, true, 0};
         sufH[b] = Traj{np + s.suffix_off[b], s.suffix_steps[b], 1, true, 0};
+        pre[b].scaled = sufL[b].scaled = sufH[b].scaled = scaled_of(b);
         add_traj(jobs, pre[b]);
         add_traj(jobs, sufL[b]);
         add_traj(jobs, sufH[b]);
         if (linear) {
             sufA[b] = Traj{np + s.suffix_off[b], s.suffix_steps[b], 0, true, 0, true};
+            sufA[b].scaled = scaled_of(b);
             add_traj(jobs, sufA[b]);
         }
     }
-    DQ_TRY(run_setup(p, pl, jobs, pl->rows.as<double>(), scaled));
+    DQ_TRY(run_setup(p, pl, jobs, pl->rows.as<double>()));
 
     // ---- buffers -------------------------------------------------------------------------------------
     DQ_TRY(pl->phi.reserve((size_t)B * N * sizeof(c128)));
@@ -2212,7 +2222,6 @@ int fused_grad_run(dq_ising* p) {
     }
 
     // ---- ket descriptors: B prefix kets, then per sample the shifted kets ordered by class ------------
-    const double esc_x = scaled ? 1.0 / (1.0 + s.r * s.r) : 1.0;
     std::vector<KetDesc> kets;
     kets.reserve((size_t)B * (kets_per + 1));
     DQ_TRY(maps_begin(p, pl, (size_t)2 * B + G + 2));
@@ -2238,13 +2247,21 @@ int fused_grad_run(dq_ising* p) {
         k.escale2 = 0.0;
         kets.push_back(k);
     }
-    struct Group { size_t first; int count; int max_pass; int chain; };   // chain > 0: groups of `chain` kets share a work ring
+    struct Group { size_t first; int count; int max_pass; int chain; bool scaled; };   // chain > 0: groups of `chain` kets share a work ring
     std::vector<Group> groups;
-    for (int g0 = 0; g0 < B; g0 += G) {
-        int cnt = std::min(G, B - g0), mp = 0;
-        for (int g = 0; g < cnt; ++g) mp = std::max(mp, kets[g0 + g].n_pass);
-        groups.push_back({(size_t)g0, cnt, mp, 0});
-    }
+    // launches are homogeneous in the butterfly form: consecutive samples of one form, at most G per launch
+    auto group_runs = [&](size_t base) {
+        for (int g0 = 0; g0 < B;) {
+            int cnt = 1, mp = kets[base + g0].n_pass;
+            while (g0 + cnt < B && cnt < G && scaled_of(g0 + cnt) == scaled_of(g0)) {
+                mp = std::max(mp, kets[base + g0 + cnt].n_pass);
+                ++cnt;
+            }
+            groups.push_back({base + g0, cnt, mp, 0, scaled_of(g0)});
+            g0 += cnt;
+        }
+    };
+    group_runs(0);
     if (linear) {                       // a_b = U(suffix of b) phi_b : stored (cross terms) and reduced (Ea)
         for (int b = 0; b < B; ++b) {
             KetDesc k = kets[b];
@@ -2257,11 +2274,7 @@ int fused_grad_run(dq_ising* p) {
             k.n_pass = s.suffix_steps[b] + 1;
             kets.push_back(k);
         }
-        for (int g0 = 0; g0 < B; g0 += G) {
-            int cnt = std::min(G, B - g0), mp = 0;
-            for (int g = 0; g < cnt; ++g) mp = std::max(mp, kets[B + g0 + g].n_pass);
-            groups.push_back({(size_t)(B + g0), cnt, mp, 0});
-        }
+        group_runs((size_t)B);
     }
     // One launch per sample: its shifted kets (class 0 first, then class 1) form a chain of groups of G kets that share
     // the G work buffers -- ket k starts in the buffer of ket k - G as soon as that one is finished, so the SMs never
@@ -2269,6 +2282,7 @@ int fused_grad_run(dq_ising* p) {
     const int chain_len = std::max(G, (kMaxGroup / G) * G);
     for (int b = 0; b < B; ++b) {
         std::vector<KetDesc> mine;
+        const double esc_x = scaled_of(b) ? 1.0 / (1.0 + s.r * s.r) : 1.0;
         for (int cls = 0; cls < 2; ++cls) {
             for (int i = 0; i < n_shift; ++i) {
                 int kcls = 0, b0 = 0, b1 = 0;
@@ -2316,7 +2330,7 @@ int fused_grad_run(dq_ising* p) {
                 mine[g0 + g].buf = pl->work.as<c128>() + (size_t)(g % G) * N;
                 mine[g0 + g].map_buf = view_of(mine[g0 + g].buf);
             }
-            groups.push_back({kets.size() + g0, cnt, s.suffix_steps[b] + 1, G});
+            groups.push_back({kets.size() + g0, cnt, s.suffix_steps[b] + 1, G, scaled_of(b)});
         }
         kets.insert(kets.end(), mine.begin(), mine.end());
     }
@@ -2331,7 +2345,7 @@ int fused_grad_run(dq_ising* p) {
     DQ_CUDA(cudaMemcpyAsync(pl->out_index.p, out_index.data(), out_index.size() * sizeof(int), cudaMemcpyHostToDevice, st));
 
     for (const Group& g : groups)
-        DQ_TRY(launch_group(p, pl, pl->kets.as<KetDesc>() + g.first, g.count, g.max_pass, scaled, s.r, g.chain));
+        DQ_TRY(launch_group(p, pl, pl->kets.as<KetDesc>() + g.first, g.count, g.max_pass, g.scaled, s.r, g.chain));
 
     k_sum_partials<<<B * kets_per, 32, 0, st>>>(pl->partials.as<double>(), tiles, tiles >> pl->sub_log2, pl->out_index.as<int>(),
                                                  p->energies.as<double>());

@@ -172,7 +172,7 @@ __global__ void k_build_diag(double* __restrict__ diag, int n, int n_zz, const i
     }
 }
 
-struct XTerms { int n; int bit[40]; double ang[40]; };
+struct XTerms { int n; int bit[40]; double ang[40]; const double* rows; };   // rows != NULL: X angles read from the device row
 
 // term_out = (scale / k) * (-i) * (diag .* term_in + sum_q ang_q term_in[x ^ bit_q]);  acc += term_out
 __global__ void k_taylor_term(const c128* __restrict__ tin, c128* __restrict__ tout, c128* __restrict__ acc,
@@ -187,8 +187,9 @@ __global__ void k_taylor_term(const c128* __restrict__ tin, c128* __restrict__ t
         double hr = d * v.x, hi = d * v.y;
         for (int q = 0; q < xt.n; ++q) {
             const c128 w = ti[x ^ ((size_t)1 << xt.bit[q])];
-            hr = fma(xt.ang[q], w.x, hr);
-            hi = fma(xt.ang[q], w.y, hi);
+            const double aq = xt.rows ? __ldg(xt.rows + q) : xt.ang[q];
+            hr = fma(aq, w.x, hr);
+            hi = fma(aq, w.y, hi);
         }
         const c128 t = make_double2(f * hi, -f * hr);          // -i (hr + i hi) = hi - i hr
         to[x] = t;
@@ -255,7 +256,8 @@ int gen_evolve(dq_ising* p, c128* d_states, int batch, const double* d_rows, con
     return DQ_OK;
 }
 
-int gen_evolve_exact(dq_ising* p, c128* d_states, int batch, const double* d_rows, const double* h_rows, int n_steps) {
+int gen_evolve_exact(dq_ising* p, c128* d_states, int batch, const double* d_rows, const double* h_rows, int n_steps,
+                     double uniform_bound) {
     const int sms = p->ctx->prop.multiProcessorCount;
     cudaStream_t st = p->ctx->stream;
     const size_t N = p->dim();
@@ -265,16 +267,23 @@ int gen_evolve_exact(dq_ising* p, c128* d_states, int batch, const double* d_row
     dim3 grid(grid_for(N, sms), batch);
     const size_t sh = p->n_zz * (sizeof(double) + sizeof(int2));
     const int m = 18;                                           // theta <= 1: truncation < 1e-17
+    DQ_REQUIRE(h_rows || uniform_bound >= 0.0, "exact step: neither host rows nor a norm bound");
     for (int k = 0; k < n_steps; ++k) {
-        const double* row = h_rows + (size_t)k * p->row_len;
-        double bound = fabs(row[0]);
-        for (int e = 0; e < p->n_zz; ++e) bound += fabs(row[1 + e]);
+        // h_rows == NULL (device-resident training): the rows exist on the device only; the caller's bound on every
+        // ||dt H(t_k)|| picks the number of squarings (any s with bound / 2^s <= 1 gives the same propagator)
+        double bound = h_rows ? 0.0 : uniform_bound;
         XTerms xt;
         xt.n = p->n;
-        for (int q = 0; q < p->n; ++q) {
-            xt.bit[q] = p->bitpos[q];
-            xt.ang[q] = row[1 + p->n_zz + q];
-            bound += fabs(xt.ang[q]);
+        xt.rows = h_rows ? nullptr : d_rows + (size_t)k * p->row_len + 1 + p->n_zz;
+        for (int q = 0; q < p->n; ++q) xt.bit[q] = p->bitpos[q];
+        if (h_rows) {
+            const double* row = h_rows + (size_t)k * p->row_len;
+            bound = fabs(row[0]);
+            for (int e = 0; e < p->n_zz; ++e) bound += fabs(row[1 + e]);
+            for (int q = 0; q < p->n; ++q) {
+                xt.ang[q] = row[1 + p->n_zz + q];
+                bound += fabs(xt.ang[q]);
+            }
         }
         int s = 0;
         while (ldexp(bound, -s) > 1.0) ++s;

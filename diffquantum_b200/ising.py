@@ -259,6 +259,34 @@ class IsingSimulator(object):
         g = self.assemble_gradients(coeff, s_list, en, r, coeff_sign)
         return (g, en) if return_energies else g
 
+    # -- device-resident training loop ---------------------------------------------------------------
+    def train_energy_device(self, coeff0, s_all, lr=2e-2, betas=(0.9, 0.999), eps=1e-8, r=0.5, e0=None, want_state=True):
+        """The whole train_energy loop (sim_plain.py:245-305) on the device: dq_ising_train.  s_all [n_epoch, K] are the
+        sample times of every epoch (the caller draws them: np.random.uniform() * T each, sim_plain.py:167); e0 the lowest
+        eigenvalue of the observable (:294) -- required, the dense eigendecomposition does not exist here.
+        Returns (trained coefficients, losses [n_epoch] = loss_energy - e0, state of the last epoch's evolution or None)."""
+        p = self.problem
+        if self.basis != 'BSpline':
+            raise ValueError("the device-resident loop evaluates the B-spline ansatz only")
+        if e0 is None:
+            raise ValueError("pass e0 (lowest eigenvalue of the observable = min of its diagonal)")
+        coeff = np.array(coeff0, dtype=np.float64, order="C")
+        if coeff.shape[0] != len(p.terms):
+            raise ValueError("one coefficient row per control term is required")
+        s_all = np.ascontiguousarray(s_all, dtype=np.float64)
+        if s_all.ndim == 1:
+            s_all = s_all.reshape(-1, 1)
+        losses = np.empty(s_all.shape[0])
+        final = np.empty(1 << p.n, dtype=np.complex128) if want_state else None
+        ms = ctypes.c_double()
+        _lib.check(_lib.load().dq_ising_train(
+            self.handle, len(p.terms), _lib.ptr(p.term_kind), _lib.ptr(p.term_index), _lib.ptr(p.omegas), _lib.ptr(p.h0_zz),
+            p.h0_const, p.T, int(self.per_step), coeff.shape[1], _lib.ptr(coeff), s_all.shape[0], s_all.shape[1],
+            _lib.ptr(s_all), float(lr), float(betas[0]), float(betas[1]), float(eps), float(r), float(e0), _lib.ptr(p.psi0),
+            _lib.ptr(losses), _lib.ptr(final), ctypes.byref(ms)))
+        self.train_device_ms = ms.value
+        return coeff, losses, final
+
     # staged variant for benchmarking (inputs resident in HBM before the timed region)
     def stage(self, coeff, s_list, r=0.5):
         tables = self.sample_tables(coeff, np.asarray(s_list, dtype=np.float64).reshape(-1))

@@ -37,7 +37,7 @@ class EnergyTrainer(object):
     def _final(self, coeff):
         b = self.backend
         if hasattr(b, "problem"):                       # IsingSimulator
-            psi, en = b.evolve(coeff, 0, b.problem.T)
+            psi, en = b.evolve(coeff, 0, b.problem.T, psi0=b.problem.psi0)
             return psi[0], float(en[0])
         psi = b.evolve(coeff, 0, b.T)
         return psi, float(b.energy(psi))
@@ -50,11 +50,15 @@ class EnergyTrainer(object):
             if self.is_noisy:
                 raise ValueError("is_noisy interleaves noise draws with the sample times: use the host loop")
             s_all = np.array([[np.random.uniform() * T for _ in range(self.n_samples)] for _ in range(self.n_epoch)])   # :167
+            if self.ground_energy is None and hasattr(self.backend, "problem"):
+                raise ValueError("pass ground_energy (min of the observable diagonal) for structured problems")
             c, losses, final = self.backend.train_energy_device(coeff, s_all, lr=self.lr, e0=self.ground_energy)
             self.spectral_coeff = torch.tensor(c, requires_grad=True)
             self.losses_energy = list(losses)
             self.final_state = final
-            self.device_ms = self.backend.stat("kernel_ms") if hasattr(self.backend, "stat") else None
+            self.device_ms = getattr(self.backend, "train_device_ms", None)
+            if self.device_ms is None and hasattr(self.backend, "stat"):
+                self.device_ms = self.backend.stat("kernel_ms")
             return self.spectral_coeff
         self.spectral_coeff = torch.tensor(coeff, requires_grad=True)
         optimizer = torch.optim.Adam([self.spectral_coeff], lr=self.lr)     # :266

@@ -16,6 +16,7 @@
  *   dq_dense_grad       compute_energy_grad_MC  sim_plain.py:186-220   (prefix + 2*n_H shifted suffixes)
  *   dq_dense_grad_times the same + generate_u   sim_plain.py:52-99,186-220 (pulse rows evaluated on the device)
  *   dq_dense_train      train_energy            sim_plain.py:245-305   (whole loop on the device, dim <= 16)
+ *   dq_ising_train      train_energy            sim_plain.py:245-305   (whole loop on the device, Pauli-term problems)
  *   dq_ising_*          the same two paths for Pauli-term (MaxCut/QAOA) Hamiltonians that the dense
  *                       nested-list API cannot express beyond n~13 (demo_maxcut.py:19-85 builds
  *                       them with np.kron) — step semantics of diffqc.cc:155-164.
@@ -173,6 +174,21 @@ int dq_ising_grad_stage(dq_ising* p, int n_samples, const int32_t* prefix_steps,
                         const int32_t* shift_index, double r, const double* psi0);
 int dq_ising_grad_run_staged(dq_ising* p);                      /* asynchronous on the ctx stream */
 int dq_ising_grad_fetch(dq_ising* p, double* energies_out);     /* synchronises, copies D2H */
+
+/* Device-resident SimulatorPlain.train_energy (sim_plain.py:245-305) for a Pauli-term problem and the B-spline ansatz: n_epoch
+ * epochs of (full evolution + energy, K stochastic gradient samples, their mean, torch-style Adam) enqueued on the context stream
+ * with no host round trip of data in between; the device evaluates the pulses and angle rows itself (sim_plain.py:52-99 and the
+ * row layout of dq_ising_evolve).  Controls: term i is Z_a Z_b of pair term_index[i] (term_kind 0) or X of qubit term_index[i]
+ * (term_kind 1), ZZ controls first; drift H0 = h0_const + sum_e h0_zz[e] Z_a Z_b (h0_zz may be NULL).  s_all [n_epoch][K]: sample
+ * times drawn by the caller from the reference's stream (np.random.uniform() * T each, :167).  coeff_inout [n_terms][n_basis].
+ * e0: the observable's lowest eigenvalue (min of its diagonal; the reference recomputes it densely every epoch, :294).
+ * psi0 (host c128[2^n], reference bit order) or NULL = uniform superposition.  losses_out [n_epoch] = loss_energy - e0;
+ * final_state_out (host c128[2^n], may be NULL) = state of the last epoch's full evolution (:304); device_ms_out (may be NULL)
+ * = device time of the whole loop (CUDA events).  Step semantics and engine follow the handle's options. */
+int dq_ising_train(dq_ising* p, int n_terms, const int32_t* term_kind, const int32_t* term_index, const double* omegas,
+                   const double* h0_zz, double h0_const, double T, int per_step, int n_basis, double* coeff_inout,
+                   int n_epoch, int K, const double* s_all, double lr, double beta1, double beta2, double eps, double r,
+                   double e0, const double* psi0, double* losses_out, double* final_state_out, double* device_ms_out);
 
 /* Counters of the last run: "steps" (trajectory-steps executed), "launches", "alg_bytes",
  * "pass_kernel_ms" / "pass_kernel_launches" (event-timed fused pass kernel; needs time_launches=1). */

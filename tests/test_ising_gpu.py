@@ -237,3 +237,46 @@ def test_headline_config_gradients_vs_c_port():
     assert rel(energies[0][terms], e_ref[terms]) < TOL
     assert rel(grads[0][terms], g_ref[terms]) < TOL
     assert np.abs(g_ref[terms]).max() > 1e-3    # not a comparison of zeros
+
+
+def test_device_resident_training_exact_step_follows_the_reference_run(golden):
+    """dq_ising_train with step='exact' on the demo problem (n=4, generic engine): pulses, angle rows, evolution, K=1 gradient
+    sample and Adam on the device for 202 epochs -- against the reference's OWN demo_maxcut.py run (np.random.seed(0))."""
+    g = golden("demo_training_ref")
+    prob = dq.IsingProblem.maxcut(4, [[0, 1], [0, 3], [1, 2], [2, 3]])
+    sim = dq.IsingSimulator(prob, per_step=10, step="exact")
+    np.random.seed(0)
+    dev = dq.EnergyTrainer(sim, n_basis=6, n_epoch=202, lr=2e-2, device_resident=True, ground_energy=-4.0)
+    dev.train_energy()
+    assert np.abs(np.array(dev.losses_energy) - g["losses_energy"]).max() < 1e-8      # Adam's rounding over 202 steps
+    assert np.abs(dev.spectral_coeff.detach().numpy() - g["final_coeff"]).max() < 1e-8
+    assert rel(dev.final_state, g["final_state"]) < 1e-8
+    assert dev.find_state()[0] in (0b0101, 0b1010)
+    assert dev.device_ms > 0
+
+
+@pytest.mark.parametrize("n,engine,K,n_epoch", [(6, 0, 3, 8), (12, 1, 2, 5), (13, 1, 1, 4)])
+def test_device_resident_training_matches_host_loop(n, engine, K, n_epoch):
+    """Split step: the device-resident loop against the host-driven EnergyTrainer (NumPy pulse tables, torch Adam) on the same
+    sample times; both engines; K > 1 = mean over the epoch's samples; non-uniform start state at n=6."""
+    edges = graph_for(n)
+    psi0 = None
+    if n == 6:
+        rs = np.random.RandomState(1)
+        psi0 = rs.normal(size=1 << n) + 1j * rs.normal(size=1 << n)
+        psi0 /= np.linalg.norm(psi0)
+    prob = dq.IsingProblem.maxcut(n, edges)
+    prob.psi0 = psi0
+    sim = dq.IsingSimulator(prob, per_step=3, engine=engine)
+    assert sim.info("engine") == engine
+    e0 = float(-len(edges))
+    np.random.seed(n)
+    a = dq.EnergyTrainer(sim, n_basis=6, n_epoch=n_epoch, lr=5e-2, n_samples=K, device_resident=True, ground_energy=e0)
+    a.train_energy()
+    np.random.seed(n)
+    b = dq.EnergyTrainer(sim, n_basis=6, n_epoch=n_epoch, lr=5e-2, n_samples=K, ground_energy=e0)
+    b.train_energy()
+    assert np.abs(np.array(a.losses_energy) - np.array(b.losses_energy)).max() < 1e-10
+    assert np.abs(a.spectral_coeff.detach().numpy() - b.spectral_coeff.detach().numpy()).max() < 1e-10
+    assert rel(a.final_state, b.final_state) < 1e-10
+    assert np.abs(np.array(a.losses_energy)).max() > 1e-3
