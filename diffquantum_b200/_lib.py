@@ -35,6 +35,9 @@ SIGNATURES = {
                                      ctypes.c_int, _VP, _VP, _VP, _VP, _VP, _VP, ctypes.c_int, _VP]),
     "dq_dense_grad_times": (ctypes.c_int, [_VP, ctypes.c_int, _VP, ctypes.c_int, _VP, _VP, _VP, ctypes.c_double, ctypes.c_int, _VP,
                                            ctypes.c_double, ctypes.c_int, _VP, _VP, ctypes.c_int, ctypes.c_int, _VP, _VP]),
+    "dq_dense_grad_probs": (ctypes.c_int, [_VP, ctypes.c_int, _VP, ctypes.c_int, _VP, _VP, ctypes.c_double, ctypes.c_int, _VP, _VP, _VP,
+                                           _VP, _VP, _VP, ctypes.c_int, ctypes.c_int, _VP, _VP]),
+    "dq_dense_outcome_probs": (ctypes.c_int, [_VP, ctypes.c_int, ctypes.c_int, _VP, ctypes.c_int, _VP, _VP]),
     "dq_dense_train": (ctypes.c_int, [_VP, ctypes.c_int, _VP, ctypes.c_int, _VP, _VP, _VP, _VP, ctypes.c_double, ctypes.c_int,
                                       ctypes.c_int, _VP, ctypes.c_int, ctypes.c_int, _VP, ctypes.c_double, ctypes.c_double,
                                       ctypes.c_double, ctypes.c_double, ctypes.c_double, ctypes.c_double, ctypes.c_int, _VP, _VP]),
@@ -53,6 +56,8 @@ SIGNATURES = {
     "dq_ising_grad_run_staged": (ctypes.c_int, [_VP]),
     "dq_ising_grad_fetch": (ctypes.c_int, [_VP, _VP]),
     "dq_ising_last_stat": (ctypes.c_int, [_VP, ctypes.c_char_p, ctypes.POINTER(ctypes.c_double)]),
+    "dq_ising_grad_pairs": (ctypes.c_int, [_VP, ctypes.c_int, _VP, _VP, _VP, _VP, ctypes.c_int, _VP, _VP, ctypes.c_double, _VP, _VP]),
+    "dq_ising_pair_expect": (ctypes.c_int, [_VP, ctypes.c_int, _VP, ctypes.c_int, _VP]),
     "dq_ising_train": (ctypes.c_int, [_VP, ctypes.c_int, _VP, _VP, _VP, _VP, ctypes.c_double, ctypes.c_double, ctypes.c_int,
                                       ctypes.c_int, _VP, ctypes.c_int, ctypes.c_int, _VP, ctypes.c_double, ctypes.c_double,
                                       ctypes.c_double, ctypes.c_double, ctypes.c_double, ctypes.c_double, _VP, _VP, _VP,

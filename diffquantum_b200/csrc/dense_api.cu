@@ -339,13 +339,64 @@ int f_u(const Problem& P, int h, double t, const double* vv, int n_param, int n_
 }
 
 
+// ---- shot sampling support: outcome distributions of measurement bases (sim_plain.py:101-117) -------------------------------
+// For every ket and every basis m: distr[j] = |<e_mj | ket>|^2, j < dim -- what stochastic_measure computes one inner product at
+// a time (:108-109) before it hands the vector to np.random.choice (:112; the draws stay on the host, in the reference's order).
+struct Measure {
+    int n_meas;
+    const double* bases;            // host [n_meas][dim (j)][dim (x)] c128: component x of eigenvector j of basis m
+    double* probs_out;              // host [n_kets][n_meas][dim]
+};
+
+// ket k = kets[(k / group) * group_stride + (k % group) * ket_stride + ...], element x: re at + x * xs, im at + x * xs + ims
+__global__ void k_outcome_probs(const double* __restrict__ kets, long long n_kets, int group, long long group_stride, long long ket_stride,
+                                long long xs, long long ims, const double2* __restrict__ bases, int n_meas, int dim,
+                                double* __restrict__ probs) {
+    const long long total = n_kets * n_meas * dim;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+        const int j = (int)(idx % dim);
+        const int mi = (int)((idx / dim) % n_meas);
+        const long long k = idx / ((long long)dim * n_meas);
+        const double* kp = kets + (k / group) * group_stride + (k % group) * ket_stride;
+        const double2* e = bases + ((size_t)mi * dim + j) * dim;
+        double ar = 0.0, ai = 0.0;                                  // <e_j|ket> = sum_x conj(e_j[x]) ket[x]
+        for (int x = 0; x < dim; ++x) {
+            const double2 v = __ldg(e + x);
+            const double kr = kp[x * xs], ki = kp[x * xs + ims];
+            ar = fma(v.x, kr, fma(v.y, ki, ar));
+            ai = fma(v.x, ki, fma(-v.y, kr, ai));
+        }
+        probs[idx] = ar * ar + ai * ai;
+    }
+}
+
+int outcome_probs(dq_context* ctx, const Measure& meas, int dim, const double* d_kets, long long n_kets, int group, long long group_stride,
+                  long long ket_stride, long long xs, long long ims, double* probs_out) {
+    State* S = state_of(ctx);
+    const size_t nb = (size_t)meas.n_meas * dim * dim * 2 * sizeof(double), np = (size_t)n_kets * meas.n_meas * dim * sizeof(double);
+    DQ_TRY(S->K1.reserve(nb));
+    DQ_TRY(S->K2.reserve(np));
+    DQ_CUDA(cudaMemcpyAsync(S->K1.p, meas.bases, nb, cudaMemcpyHostToDevice, ctx->stream));
+    const long long total = n_kets * meas.n_meas * dim;
+    const int grid = (int)std::min<long long>((total + 255) / 256, (long long)ctx->prop.multiProcessorCount * 16);
+    k_outcome_probs<<<grid, 256, 0, ctx->stream>>>(d_kets, n_kets, group, group_stride, ket_stride, xs, ims, S->K1.as<double2>(),
+                                                   meas.n_meas, dim, S->K2.as<double>());
+    ctx->launches++;
+    DQ_CUDA(cudaGetLastError());
+    DQ_CUDA(cudaMemcpyAsync(probs_out, S->K2.p, np, cudaMemcpyDeviceToHost, ctx->stream));
+    DQ_CUDA(cudaStreamSynchronize(ctx->stream));
+    return DQ_OK;
+}
+
+
 // Resident engine (dim <= 16) for a batch of estimator samples: prefix kets, then every shifted ket of every sample.
 // u_prefix / u_suffix: packed HOST pulse tables, or both NULL when S->u_dev already holds [prefix rows | suffix rows]
 // (filled on the device by k_pulse_rows).
 int grad_resident(dq_context* ctx, Problem& P, const double* M, const double* psi0, double r, int n_samples,
                   const int32_t* prefix_steps, const double* prefix_dt, const int32_t* suffix_steps, const double* suffix_dt,
                   const std::vector<long long>& pre_off, const std::vector<long long>& suf_off, double bound,
-                  const double* u_prefix, const double* u_suffix, int mode, double* energies_out) {
+                  const double* u_prefix, const double* u_suffix, int mode, double* energies_out,
+                  const Measure* meas = nullptr) {
     State* S = state_of(ctx);
     const int n_H = P.n_H, dim = P.dim;
     const long long n_pre = pre_off[n_samples], n_suf = suf_off[n_samples];
@@ -375,6 +426,25 @@ int grad_resident(dq_context* ctx, Problem& P, const double* M, const double* ps
     DQ_TRY(small_run(ctx, P, mode, s, m, 1, traj, S->u_dev.as<double>(), S->phi.as<double>(), S->phi.as<double>() + 32, nullptr, 1.0));
     std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return suffix_steps[a] > suffix_steps[b]; });
     traj.clear();
+    if (meas) {
+        // shot sampling (sim_plain.py:101-117,202-203,212-213): the shifted kets themselves are needed, one warp each
+        // (k_small<false, 1>), then |<e_j|ket>|^2 for every eigenvector of every measurement basis
+        const size_t n_kets = (size_t)n_samples * 2 * n_H;
+        DQ_TRY(S->K0.reserve(n_kets * 32 * sizeof(double)));
+        for (int b : order)
+            for (int i = 0; i < n_H; ++i)
+                for (int sg = 0; sg < 2; ++sg)
+                    traj.push_back(SmallTraj{n_pre + suf_off[b], std::ldexp(suffix_dt[b], -s), sg ? -r : r, suffix_steps[b], b, i,
+                                             (b * n_H + i) * 2 + sg});
+        DQ_TRY(small_run(ctx, P, mode, s, m, 1, traj, S->u_dev.as<double>(), S->phi.as<double>() + 32, S->K0.as<double>(), nullptr,
+                         1.0 / sqrt(1.0 + r * r)));
+        DQ_TRY(outcome_probs(ctx, *meas, dim, S->K0.as<double>(), (long long)n_kets, 1, 32, 0, 2, 1, meas->probs_out));
+        S->last_gemm_flops = 0;
+        S->last_strategy = 3;
+        S->last_squarings = s;
+        S->last_degree = m;
+        return DQ_OK;
+    }
     // Every shifted ket of a sample shares its generator.  Exact step: a warp takes up to 16 of them through the tensor-core
     // recurrence (k_small_mma; option "small_mma" 0 = the DFMA kernel below instead).  Per-term product (mode 1): the +/-
     // kets of a control (and of two neighbouring controls when n_H is even) per warp on the DFMA kernel.
@@ -581,11 +651,11 @@ int dq_dense_evolve(dq_context* ctx, int dim, const double* H0, int n_H, const d
     return DQ_OK;
 }
 
-int dq_dense_grad(dq_context* ctx, int dim, const double* H0, int n_H, const double* Hs, const double* M,
+static int grad_impl(dq_context* ctx, int dim, const double* H0, int n_H, const double* Hs, const double* M,
                   const double* psi0, double r, int n_samples, const int32_t* prefix_steps, const double* prefix_dt,
                   const double* u_prefix, const int32_t* suffix_steps, const double* suffix_dt, const double* u_suffix,
-                  int mode, double* energies_out) {
-    DQ_REQUIRE(ctx && M && psi0 && energies_out, "dq_dense_grad: NULL argument");
+                  int mode, double* energies_out, const Measure* meas) {
+    DQ_REQUIRE(ctx && psi0 && ((M && energies_out) || meas), "dq_dense_grad: NULL argument");
     DQ_REQUIRE(prefix_steps && prefix_dt && suffix_steps && suffix_dt, "dq_dense_grad: NULL step table");
     DQ_REQUIRE(mode == 0 || mode == 1, "dq_dense_grad: mode must be 0 (exact) or 1 (split)");
     DQ_REQUIRE(n_samples >= 1 && n_H >= 1, "dq_dense_grad: n_samples=%d n_H=%d", n_samples, n_H);
@@ -594,7 +664,7 @@ int dq_dense_grad(dq_context* ctx, int dim, const double* H0, int n_H, const dou
     State* S = state_of(ctx);
     Problem& P = S->scratch_H;
     DQ_TRY(upload_problem(ctx, P, dim, H0, n_H, Hs));
-    DQ_TRY(upload_observable(ctx, P, M));
+    if (M) DQ_TRY(upload_observable(ctx, P, M));
     for (int i = 0; i < 2 * dim; ++i) DQ_REQUIRE(std::isfinite(psi0[i]), "dq_dense_grad: non-finite psi0 entry");
     std::vector<long long> pre_off(n_samples + 1, 0), suf_off(n_samples + 1, 0);
     for (int b = 0; b < n_samples; ++b) {
@@ -612,7 +682,7 @@ int dq_dense_grad(dq_context* ctx, int dim, const double* H0, int n_H, const dou
         DQ_TRY(norm_bound(P, mode, n_samples, prefix_steps, prefix_dt, pre_off.data(), u_prefix ? u_prefix : &no_u0, &b_pre));
         DQ_TRY(norm_bound(P, mode, n_samples, suffix_steps, suffix_dt, suf_off.data(), u_suffix ? u_suffix : &no_u0, &b_suf));
         return grad_resident(ctx, P, M, psi0, r, n_samples, prefix_steps, prefix_dt, suffix_steps, suffix_dt, pre_off, suf_off,
-                             std::max(b_pre, b_suf), u_prefix, u_suffix, mode, energies_out);
+                             std::max(b_pre, b_suf), u_prefix, u_suffix, mode, energies_out, meas);
     }
     const int Ncp = round8(2 * n_H), Dp = P.Dp;
     const size_t mat_bytes = 2 * P.plane() * sizeof(double);
@@ -642,12 +712,47 @@ int dq_dense_grad(dq_context* ctx, int dim, const double* H0, int n_H, const dou
         DQ_TRY(fanout(ctx, P, nb, S->phi.as<double>(), 8, K, Ncp, r));
         DQ_TRY(evolve_blocks(ctx, P, mode, nb, Ncp, suffix_steps + b0, suffix_dt + b0, so.data(),
                              u_suffix ? u_suffix + suf_off[b0] * n_H : &no_u, n_suf, K));
+        if (meas) {                  // kets of sample b: planar block [2][Dp][Ncp], column c = 2 i + sign
+            DQ_TRY(outcome_probs(ctx, *meas, dim, K, (long long)nb * 2 * n_H, 2 * n_H, (long long)2 * Dp * Ncp, 1, Ncp, (long long)Dp * Ncp,
+                                 meas->probs_out + (size_t)b0 * 2 * n_H * meas->n_meas * dim));
+            continue;
+        }
         DQ_TRY(energies(ctx, P, nb, K, Ncp, 2 * n_H, E));
         DQ_CUDA(cudaMemcpyAsync(energies_out + (size_t)b0 * 2 * n_H, E, (size_t)nb * 2 * n_H * sizeof(double),
                                 cudaMemcpyDeviceToHost, ctx->stream));
         DQ_CUDA(cudaStreamSynchronize(ctx->stream));
     }
     return DQ_OK;
+}
+
+int dq_dense_grad(dq_context* ctx, int dim, const double* H0, int n_H, const double* Hs, const double* M,
+                  const double* psi0, double r, int n_samples, const int32_t* prefix_steps, const double* prefix_dt,
+                  const double* u_prefix, const int32_t* suffix_steps, const double* suffix_dt, const double* u_suffix,
+                  int mode, double* energies_out) {
+    DQ_REQUIRE(M && energies_out, "dq_dense_grad: NULL argument");
+    return grad_impl(ctx, dim, H0, n_H, Hs, M, psi0, r, n_samples, prefix_steps, prefix_dt, u_prefix, suffix_steps, suffix_dt, u_suffix,
+                     mode, energies_out, nullptr);
+}
+
+int dq_dense_grad_probs(dq_context* ctx, int dim, const double* H0, int n_H, const double* Hs, const double* psi0, double r,
+                        int n_samples, const int32_t* prefix_steps, const double* prefix_dt, const double* u_prefix,
+                        const int32_t* suffix_steps, const double* suffix_dt, const double* u_suffix, int mode, int n_meas,
+                        const double* bases, double* probs_out) {
+    DQ_REQUIRE(n_meas >= 1 && bases && probs_out, "dq_dense_grad_probs: n_meas=%d or NULL basis / output", n_meas);
+    for (size_t i = 0; i < (size_t)n_meas * dim * dim * 2; ++i) DQ_REQUIRE(std::isfinite(bases[i]), "dq_dense_grad_probs: non-finite basis entry");
+    Measure meas{n_meas, bases, probs_out};
+    return grad_impl(ctx, dim, H0, n_H, Hs, nullptr, psi0, r, n_samples, prefix_steps, prefix_dt, u_prefix, suffix_steps, suffix_dt,
+                     u_suffix, mode, nullptr, &meas);
+}
+
+int dq_dense_outcome_probs(dq_context* ctx, int dim, int n_kets, const double* kets, int n_meas, const double* bases, double* probs_out) {
+    DQ_REQUIRE(ctx && kets && bases && probs_out && dim >= 1 && n_kets >= 1 && n_meas >= 1, "dq_dense_outcome_probs: bad argument");
+    DQ_TRY(ctx->set_device());
+    State* S = state_of(ctx);
+    DQ_TRY(S->K0.reserve((size_t)n_kets * dim * 2 * sizeof(double)));
+    DQ_CUDA(cudaMemcpyAsync(S->K0.p, kets, (size_t)n_kets * dim * 2 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    Measure meas{n_meas, bases, probs_out};
+    return outcome_probs(ctx, meas, dim, S->K0.as<double>(), n_kets, 1, (long long)2 * dim, 0, 2, 1, probs_out);
 }
 
 int dq_dense_grad_times(dq_context* ctx, int dim, const double* H0, int n_H, const double* Hs, const double* M,

@@ -30,6 +30,8 @@ struct dq_ising {
     dq::DevBuf states, phi, rows_a, rows_b, trig_a, trig_b, energies, scratch, io, shift_desc;
     dq::DevBuf exact_diag, exact_t0, exact_t1;     // exact-step workspaces (generic engine)
     dq::DevBuf train;                              // device-resident training loop (ising_train.cu)
+    dq::DevBuf pair_out;                           // shot sampling: <Z_a Z_b> of every shifted ket, [n_samples][2 n_shift][n_zz]
+    bool want_pairs = false;                       // the staged run also fills pair_out (generic engine: the kets must exist)
     int step_mode = 0;             // 0 split (per-term product, diffqc.cc:155-164), 1 exact (live semantics, sim_plain.py:135-150)
     std::vector<double> host_rows_a, host_rows_b;  // exact step: host copy of the staged rows (norm bound per step)
 
@@ -78,6 +80,7 @@ int gen_fanout(dq_ising* p, const c128* d_phi, c128* d_kets, int n_kets, const S
                double r);
 int gen_energy(dq_ising* p, const c128* d_states, int batch, double* d_out);
 int gen_build_mdiag(dq_ising* p, const double* m_zz, double m_const);
+int gen_pair_expect(dq_ising* p, const c128* d_states, int batch, double* d_out);   // <Z_a Z_b> of every ZZ pair, [batch][n_zz]
 
 // staging pieces shared by dq_ising_grad_stage and the device-resident training loop (ising_api.cu)
 int stage_meta(dq_ising* p, int n_samples, const int32_t* prefix_steps, const int32_t* suffix_steps, int n_shift,

@@ -16,7 +16,7 @@ int check_rows(const dq_ising* p, const double* rows, int64_t n_rows, const char
 }
 
 // the fused engines implement the product-formula step only; the exact step runs on the generic engine
-bool use_fused(const dq_ising* p) { return p->step_mode == 0 && p->engine >= 1 && dq::fused_supported(p); }
+bool use_fused(const dq_ising* p) { return p->step_mode == 0 && p->engine >= 1 && !p->want_pairs && dq::fused_supported(p); }
 
 // ---- qubit -> bit layout ---------------------------------------------------------------------------------
 // Reference order is bit n-1-q for qubit q (np.kron order, demo_maxcut.py:53-57).  The fused engine keeps two
@@ -276,7 +276,7 @@ int dq_ising_destroy(dq_ising* p) {
     dq::fused_release(p);
     dq::DevBuf* bufs[] = {&p->mdiag, &p->mdiag_ref, &p->pairs_dev, &p->states, &p->phi, &p->rows_a, &p->rows_b, &p->trig_a,
                           &p->trig_b, &p->energies, &p->scratch, &p->io, &p->shift_desc, &p->st.psi0, &p->exact_diag, &p->exact_t0,
-                          &p->exact_t1, &p->train};
+                          &p->exact_t1, &p->train, &p->pair_out};
     for (auto* b : bufs) b->release();
     delete p;
     return DQ_OK;
@@ -463,6 +463,7 @@ int dq_ising_grad_run_staged(dq_ising* p) {
                                             dev_rows ? nullptr : p->host_rows_b.data() + s.suffix_off[b] * p->row_len, s.suffix_steps[b],
                                             s.exact_bound));
                 DQ_TRY(dq::gen_energy(p, p->states.as<c128>(), kets, p->energies.as<double>() + (size_t)b * kets));
+                if (p->want_pairs) DQ_TRY(dq::gen_pair_expect(p, p->states.as<c128>(), kets, p->pair_out.as<double>() + (size_t)b * kets * p->n_zz));
                 continue;
             }
             DQ_TRY(dq::gen_evolve(p, phi, 1, p->rows_a.as<double>() + s.prefix_off[b] * p->row_len,
@@ -471,6 +472,7 @@ int dq_ising_grad_run_staged(dq_ising* p) {
             DQ_TRY(dq::gen_evolve(p, p->states.as<c128>(), kets, p->rows_b.as<double>() + s.suffix_off[b] * p->row_len,
                                   p->trig_b.as<double2>() + s.suffix_off[b] * p->n, s.suffix_steps[b]));
             DQ_TRY(dq::gen_energy(p, p->states.as<c128>(), kets, p->energies.as<double>() + (size_t)b * kets));
+            if (p->want_pairs) DQ_TRY(dq::gen_pair_expect(p, p->states.as<c128>(), kets, p->pair_out.as<double>() + (size_t)b * kets * p->n_zz));
         }
     }
     const bool lin = p->linear && use_fused(p);
@@ -488,6 +490,48 @@ int dq_ising_grad_fetch(dq_ising* p, double* energies_out) {
     DQ_CUDA(cudaMemcpyAsync(energies_out, p->energies.p, (size_t)p->st.n_samples * 2 * p->st.n_shift * sizeof(double),
                             cudaMemcpyDeviceToHost, p->ctx->stream));
     DQ_CUDA(cudaStreamSynchronize(p->ctx->stream));
+    return DQ_OK;
+}
+
+int dq_ising_grad_pairs(dq_ising* p, int n_samples, const int32_t* prefix_steps, const double* prefix_angles,
+                        const int32_t* suffix_steps, const double* suffix_angles, int n_shift, const int32_t* shift_kind,
+                        const int32_t* shift_index, double r, const double* psi0, double* zz_out) {
+    DQ_REQUIRE(p && zz_out, "dq_ising_grad_pairs: NULL argument");
+    DQ_REQUIRE(n_samples >= 1 && n_shift >= 1, "dq_ising_grad_pairs: n_samples=%d n_shift=%d", n_samples, n_shift);
+    DQ_TRY(p->ctx->set_device());
+    const size_t count = (size_t)n_samples * 2 * n_shift * p->n_zz;
+    DQ_TRY(p->pair_out.reserve((count ? count : 1) * sizeof(double)));
+    p->want_pairs = true;            // the shifted kets themselves are needed: one kernel per term group, no fused passes
+    int rc = dq_ising_grad_stage(p, n_samples, prefix_steps, prefix_angles, suffix_steps, suffix_angles, n_shift, shift_kind,
+                                 shift_index, r, psi0);
+    if (rc == DQ_OK) rc = dq_ising_grad_run_staged(p);
+    p->want_pairs = false;
+    p->st.valid = false;
+    DQ_TRY(rc);
+    DQ_CUDA(cudaMemcpyAsync(zz_out, p->pair_out.p, count * sizeof(double), cudaMemcpyDeviceToHost, p->ctx->stream));
+    DQ_CUDA(cudaStreamSynchronize(p->ctx->stream));
+    return DQ_OK;
+}
+
+int dq_ising_pair_expect(dq_ising* p, int batch, const void* psi, int psi_is_device, double* zz_out) {
+    DQ_REQUIRE(p && psi && zz_out && batch >= 1, "dq_ising_pair_expect: bad argument");
+    DQ_TRY(p->ctx->set_device());
+    cudaStream_t st = p->ctx->stream;
+    const size_t bytes = p->dim() * batch * sizeof(c128);
+    DQ_TRY(p->states.reserve(bytes));
+    c128* d = p->states.as<c128>();
+    if (p->identity_layout) {
+        DQ_CUDA(cudaMemcpyAsync(d, psi, bytes, psi_is_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
+    } else {
+        DQ_TRY(p->io.reserve(bytes));
+        DQ_CUDA(cudaMemcpyAsync(p->io.p, psi, bytes, psi_is_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
+        DQ_TRY(dq::gen_permute_in(p, p->io.as<c128>(), d, batch));
+    }
+    const size_t count = (size_t)batch * p->n_zz;
+    DQ_TRY(p->pair_out.reserve((count ? count : 1) * sizeof(double)));
+    DQ_TRY(dq::gen_pair_expect(p, d, batch, p->pair_out.as<double>()));
+    DQ_CUDA(cudaMemcpyAsync(zz_out, p->pair_out.p, count * sizeof(double), cudaMemcpyDeviceToHost, st));
+    DQ_CUDA(cudaStreamSynchronize(st));
     return DQ_OK;
 }
 

@@ -130,6 +130,52 @@ __global__ void k_energy(const c128* __restrict__ psi, const double* __restrict_
     }
 }
 
+// Shot sampling (stochastic_measure, sim_plain.py:101-117) on Z-string observables: the outcome distribution of Z_a Z_b in a
+// state collapses to P(-1) = (1 - <Z_a Z_b>) / 2, so per state and pair  zz[e] = sum_x |psi_x|^2 (-1)^(x_a xor x_b).
+// One pass over the state serves kPairChunk pairs (register accumulators); partial[(state * gridDim.x + block) * n_zz + e].
+constexpr int kPairChunk = 16;
+__global__ void k_pair_expect(const c128* __restrict__ psi, int n, int n_zz, const int2* __restrict__ pairs, int e0,
+                              double* __restrict__ partial) {
+    const size_t N = (size_t)1 << n;
+    const c128* s = psi + blockIdx.y * N;
+    unsigned mask[kPairChunk];
+    double acc[kPairChunk];
+#pragma unroll
+    for (int k = 0; k < kPairChunk; ++k) {
+        const int e = e0 + k;
+        mask[k] = e < n_zz ? ((1u << pairs[e].x) | (1u << pairs[e].y)) : 0u;
+        acc[k] = 0.0;
+    }
+    for (size_t x = blockIdx.x * (size_t)blockDim.x + threadIdx.x; x < N; x += (size_t)gridDim.x * blockDim.x) {
+        const c128 v = s[x];
+        const double pr = v.x * v.x + v.y * v.y;
+#pragma unroll
+        for (int k = 0; k < kPairChunk; ++k) acc[k] += (__popc((unsigned)x & mask[k]) & 1) ? -pr : pr;
+    }
+    __shared__ double red[kThreads / 32][kPairChunk];
+#pragma unroll
+    for (int k = 0; k < kPairChunk; ++k) {
+        double a = acc[k];
+        for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5][k] = a;
+    }
+    __syncthreads();
+    if (threadIdx.x < kPairChunk && e0 + threadIdx.x < n_zz) {
+        double v = 0.0;
+        for (int w = 0; w < kThreads / 32; ++w) v += red[w][threadIdx.x];
+        partial[((size_t)blockIdx.y * gridDim.x + blockIdx.x) * n_zz + e0 + threadIdx.x] = v;
+    }
+}
+
+// out[state][e] = sum over blocks, fixed order
+__global__ void k_sum_pair_partials(const double* __restrict__ partial, int blocks, int n_zz, double* __restrict__ out) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n_zz) return;
+    double acc = 0.0;
+    for (int b = 0; b < blocks; ++b) acc += partial[((size_t)blockIdx.y * blocks + b) * n_zz + e];
+    out[(size_t)blockIdx.y * n_zz + e] = acc;
+}
+
 __global__ void k_sum_partials(const double* __restrict__ partial, int per, double* __restrict__ out) {
     // deterministic: one warp per state sums its partials in a fixed order
     double acc = 0.0;
@@ -328,6 +374,24 @@ int gen_energy(dq_ising* p, const c128* d_states, int batch, double* d_out) {
                                                     p->scratch.as<double>());
     k_sum_partials<<<batch, 32, 0, p->ctx->stream>>>(p->scratch.as<double>(), gx, d_out);
     p->ctx->launches += 2;
+    DQ_CUDA(cudaGetLastError());
+    return DQ_OK;
+}
+
+int gen_pair_expect(dq_ising* p, const c128* d_states, int batch, double* d_out) {
+    if (p->n_zz == 0) return DQ_OK;
+    int gx = grid_for(p->dim(), p->ctx->prop.multiProcessorCount);
+    if (gx > 128) gx = 128;
+    DQ_REQUIRE(batch <= 65535, "pair expectations: batch=%d exceeds 65535 states per call", batch);
+    DQ_TRY(p->scratch.reserve((size_t)gx * batch * p->n_zz * sizeof(double)));
+    dim3 grid(gx, batch);
+    for (int e0 = 0; e0 < p->n_zz; e0 += kPairChunk) {
+        k_pair_expect<<<grid, kThreads, 0, p->ctx->stream>>>(d_states, p->n, p->n_zz, p->pairs_dev.as<int2>(), e0, p->scratch.as<double>());
+        p->ctx->launches++;
+    }
+    dim3 g2((p->n_zz + 63) / 64, batch);
+    k_sum_pair_partials<<<g2, 64, 0, p->ctx->stream>>>(p->scratch.as<double>(), gx, p->n_zz, d_out);
+    p->ctx->launches++;
     DQ_CUDA(cudaGetLastError());
     return DQ_OK;
 }

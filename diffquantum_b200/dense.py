@@ -73,6 +73,49 @@ class DenseSimulator(object):
         # dim <= 16 with the B-spline ansatz: the device evaluates the pulse rows itself (dq_dense_grad_times); only the
         # sample times and the coefficients cross the bus.  False = host tables (pulses.u_table) through dq_dense_grad.
         self.device_tables = True
+        self.measure = None            # (weights, evals, bases) of sim.Pauli_M: shot sampling, set_measurement()
+
+    def set_measurement(self, pauli_m):
+        """Pauli_M of the reference (demo_maxcut.py:47-65): [[matrix, weight, (evals, estates)], ...] -- the measurement
+        bases of stochastic_measure (sim_plain.py:101-117)."""
+        self.measure = pulses.measurement_bases(pauli_m)
+
+    def outcome_probs(self, kets):
+        """distr[j] = |<e_mj|ket>|^2 for every ket and measurement basis (sim_plain.py:105-109), on the device:
+        [n_kets, n_meas, dim]."""
+        if self.measure is None:
+            raise ValueError("set_measurement(Pauli_M) first")
+        bases = self.measure[2]
+        kets = _c128(kets).reshape(-1, self.dim)
+        out = np.empty((kets.shape[0], bases.shape[0], self.dim))
+        _lib.check(_lib.load().dq_dense_outcome_probs(self.ctx.handle, self.dim, kets.shape[0], _lib.ptr(kets), bases.shape[0],
+                                                      _lib.ptr(bases), _lib.ptr(out)))
+        return out
+
+    def stochastic_measure(self, psi, per_Pauli=100):
+        """SimulatorPlain.stochastic_measure (sim_plain.py:101-117): distributions on the device, draws from np.random."""
+        return pulses.stochastic_measure_from_probs(self.outcome_probs(psi)[0], self.measure[0], self.measure[1], per_Pauli)
+
+    def shifted_outcome_probs(self, coeff, s_list, r=0.5, mode=None):
+        """Outcome distributions of every shifted ket: [B, n_H, 2, n_meas, dim] (dq_dense_grad_probs)."""
+        if self.measure is None or self.psi0 is None:
+            raise ValueError("shifted_outcome_probs needs set_measurement(Pauli_M) and psi0")
+        s_list = np.asarray(s_list, dtype=np.float64).reshape(-1)
+        pre_n, pre_dt, pre_ts = pulses.step_grids(0.0, s_list, self.per_step)
+        suf_n, suf_dt, suf_ts = pulses.step_grids(s_list, self.T, self.per_step)
+        pre_u = np.ascontiguousarray(pulses.u_table(coeff, self.omegas, self.T, pre_ts, self.basis).reshape(-1, self.n_H))
+        suf_u = np.ascontiguousarray(pulses.u_table(coeff, self.omegas, self.T, suf_ts, self.basis).reshape(-1, self.n_H))
+        return self._probs_call(s_list.size, pre_n, pre_dt, pre_u, suf_n, suf_dt, suf_u, r, mode)
+
+    def _probs_call(self, B, pre_n, pre_dt, pre_u, suf_n, suf_dt, suf_u, r, mode):
+        bases = self.measure[2]
+        pre_dt = np.ascontiguousarray(pre_dt, dtype=np.float64); suf_dt = np.ascontiguousarray(suf_dt, dtype=np.float64)
+        out = np.empty((B, self.n_H, 2, bases.shape[0], self.dim))
+        _lib.check(_lib.load().dq_dense_grad_probs(
+            self.ctx.handle, self.dim, _lib.ptr(self.H0), self.n_H, _lib.ptr(self.Hs), _lib.ptr(self.psi0), float(r), B,
+            _lib.ptr(pre_n), _lib.ptr(pre_dt), _lib.ptr(pre_u), _lib.ptr(suf_n), _lib.ptr(suf_dt), _lib.ptr(suf_u),
+            MODES[mode or self.mode], bases.shape[0], _lib.ptr(bases), _lib.ptr(out)))
+        return out
 
     def _times_call(self, coeff, s_list, r, mode, want_u=False):
         """dq_dense_grad_times: energies [B, n_H, 2] (and the device-built pulse table when want_u)."""
@@ -160,13 +203,20 @@ class DenseSimulator(object):
             _lib.ptr(suf_n), _lib.ptr(suf_dt), _lib.ptr(suf_u), MODES[mode or self.mode], _lib.ptr(out)))
         return out
 
-    def grad_samples(self, coeff, s_list, r=0.5, coeff_sign=1.0, return_energies=False, mode=None, is_noisy=False):
+    def grad_samples(self, coeff, s_list, r=0.5, coeff_sign=1.0, return_energies=False, mode=None, is_noisy=False,
+                     sampling_measure=False, per_Pauli=100):
         """Per-sample gradients of compute_energy_grad_MC (sim_plain.py:156-231) at explicit times.  is_noisy: the
-        reference's measurement noise on every shifted energy (pulses.add_measurement_noise)."""
+        reference's measurement noise on every shifted energy (pulses.add_measurement_noise).  sampling_measure: every
+        shifted energy by shot sampling (stochastic_measure, :202-203,212-213) -- outcome distributions from the device,
+        np.random.choice draws on the host in the reference's order."""
         s_list = np.asarray(s_list, dtype=np.float64).reshape(-1)
-        en = self.shifted_energies(coeff, s_list, r, mode)
-        if is_noisy:
-            pulses.add_measurement_noise(en)
+        if sampling_measure:
+            probs = self.shifted_outcome_probs(coeff, s_list, r, mode)
+            en = pulses.sampled_shifted_energies(probs, self.measure[0], self.measure[1], per_Pauli, is_noisy)
+        else:
+            en = self.shifted_energies(coeff, s_list, r, mode)
+            if is_noisy:
+                pulses.add_measurement_noise(en)
         ps = coeff_sign * ((1 + r ** 2) / 2 / r * (en[:, :, 1] - en[:, :, 0]))
         grads = ps[:, :, None] * pulses.dudc_tables(coeff, self.omegas, self.T, s_list, self.basis)
         return (grads, en) if return_energies else grads
@@ -205,14 +255,13 @@ def estimator_for(sim, device=0, mode="exact"):
     """Batched replacement for SimulatorPlain.compute_energy_grad_MC (sim_plain.py:156-231).
     Same signature and return type (torch.float64 [n_Hs, n_basis]); draws s = np.random.uniform() * T
     exactly where the reference does (:167) unless `s` is passed.  `sim.is_noisy` adds the reference's measurement noise
-    (:207-208,217-218) from the same global stream; `sim.sampling_measure` (shot sampling through Pauli_M eigenbases,
-    :101-117) needs the kets on the host and is rejected."""
+    (:207-208,217-218) from the same global stream; `sim.sampling_measure` replaces every shifted energy by
+    stochastic_measure (:101-117,202-203,212-213): the outcome distributions of sim.Pauli_M's eigenbases come from the device
+    (dq_dense_grad_probs), the np.random.choice draws happen here in the reference's order."""
     ctx = _lib.Context.get(device)
 
     def compute_energy_grad_MC(M, H_, psi0_, coeff=1.0, s=None):
         import torch
-        if getattr(sim, "sampling_measure", False):
-            raise ValueError("sampling_measure=True is not supported by the device estimator (sim_plain.py:101-117)")
         H0, Hs, fs = _split_H(H_)
         if s is None:
             s = np.random.uniform() * sim.T
@@ -228,13 +277,19 @@ def estimator_for(sim, device=0, mode="exact"):
         sn, sdt, su = table(s, sim.T)
         en = np.empty((1, len(fs), 2))
         r = 1 / 2
-        _lib.check(_lib.load().dq_dense_grad(
-            ctx.handle, ds.dim, _lib.ptr(ds.H0), ds.n_H, _lib.ptr(ds.Hs), _lib.ptr(ds.M), _lib.ptr(ds.psi0), r, 1,
-            _lib.ptr(np.array([pn], dtype=np.int32)), _lib.ptr(np.array([pdt])), _lib.ptr(np.ascontiguousarray(pu)),
-            _lib.ptr(np.array([sn], dtype=np.int32)), _lib.ptr(np.array([sdt])), _lib.ptr(np.ascontiguousarray(su)),
-            MODES[mode], _lib.ptr(en)))
-        if getattr(sim, "is_noisy", False):
-            pulses.add_measurement_noise(en)
+        if getattr(sim, "sampling_measure", False):
+            ds.set_measurement(sim.Pauli_M)
+            probs = ds._probs_call(1, np.array([pn], dtype=np.int32), np.array([pdt]), np.ascontiguousarray(pu),
+                                   np.array([sn], dtype=np.int32), np.array([sdt]), np.ascontiguousarray(su), r, mode)
+            en = pulses.sampled_shifted_energies(probs, ds.measure[0], ds.measure[1], 100, getattr(sim, "is_noisy", False))
+        else:
+            _lib.check(_lib.load().dq_dense_grad(
+                ctx.handle, ds.dim, _lib.ptr(ds.H0), ds.n_H, _lib.ptr(ds.Hs), _lib.ptr(ds.M), _lib.ptr(ds.psi0), r, 1,
+                _lib.ptr(np.array([pn], dtype=np.int32)), _lib.ptr(np.array([pdt])), _lib.ptr(np.ascontiguousarray(pu)),
+                _lib.ptr(np.array([sn], dtype=np.int32)), _lib.ptr(np.array([sdt])), _lib.ptr(np.ascontiguousarray(su)),
+                MODES[mode], _lib.ptr(en)))
+            if getattr(sim, "is_noisy", False):
+                pulses.add_measurement_noise(en)
         ps = coeff * ((1 + r ** 2) / 2 / r * (en[0, :, 1] - en[0, :, 0]))
         grad = ps[:, None] * pulses.dudc_table(c, sim.omegas, sim.T, s, sim.basis)
         return torch.from_numpy(grad)

@@ -79,6 +79,23 @@ class IsingProblem(object):
         self.m_diag = None if m_diag is None else np.ascontiguousarray(m_diag, dtype=np.float64)
         self.psi0 = None if psi0 is None else np.ascontiguousarray(psi0, dtype=np.complex128)
         self.row_len = 1 + self.n_zz + self.n
+        # shot sampling (sim.Pauli_M of the reference, demo_maxcut.py:47-65): Z-string terms [(pair id or -1 = identity, weight)]
+        self.measure_terms = None
+
+    def set_measurement(self, terms):
+        """Pauli_M in structured form: [((a, b), weight), ..., (None, weight)] -- Z_a Z_b strings and the identity, in the
+        reference's order (the draw order of stochastic_measure, sim_plain.py:104).  Every pair must be one of the problem's."""
+        ids = {tuple(map(int, pr)): i for i, pr in enumerate(self.zz_pairs)}
+        out = []
+        for pair, w in terms:
+            if pair is None:
+                out.append((-1, float(w)))
+            else:
+                key = (min(pair), max(pair))
+                if key not in ids:
+                    raise ValueError("measurement pair %r is not a ZZ pair of this problem" % (pair,))
+                out.append((ids[key], float(w)))
+        self.measure_terms = out
 
     # -- the reference's MaxCut construction ---------------------------------------------------
     @classmethod
@@ -95,8 +112,10 @@ class IsingProblem(object):
         for a, b in edges:
             h0[(a, b)] = h0.get((a, b), 0.0) - 1.0
             mz[(a, b)] = mz.get((a, b), 0.0) + 0.5
-        return cls(n, terms, omegas, T, h0_zz=h0, h0_const=float(len(edges)), m_zz=mz,
+        prob = cls(n, terms, omegas, T, h0_zz=h0, h0_const=float(len(edges)), m_zz=mz,
                    m_const=-0.5 * len(edges))
+        prob.set_measurement([((a, b), 0.5) for a, b in edges] + [(None, -0.5 * len(edges))])   # demo_maxcut.py:47-62
+        return prob
 
     # -- host-side angle tables ------------------------------------------------------------------
     def angle_rows(self, u, dt):
@@ -248,16 +267,62 @@ class IsingSimulator(object):
             grads[b] = ps[:, None] * pulses.dudc_table(coeff, p.omegas, p.T, s, self.basis)
         return grads
 
-    def grad_samples(self, coeff, s_list, r=0.5, coeff_sign=1.0, return_energies=False, is_noisy=False):
+    def grad_samples(self, coeff, s_list, r=0.5, coeff_sign=1.0, return_energies=False, is_noisy=False,
+                     sampling_measure=False, per_Pauli=100):
         """Per-sample gradients of compute_energy_grad_MC (sim_plain.py:156-231) for explicit
         sampled times s_list (the reference draws s = np.random.uniform() * T at :167).  is_noisy: the reference's
-        measurement noise on every shifted energy (sim_plain.py:207-208,217-218; pulses.add_measurement_noise)."""
+        measurement noise on every shifted energy (sim_plain.py:207-208,217-218; pulses.add_measurement_noise).
+        sampling_measure: shifted energies by shot sampling (stochastic_measure, :202-203,212-213)."""
         s_list = np.asarray(s_list, dtype=np.float64).reshape(-1)
-        en = self.shifted_energies(coeff, s_list, r)
-        if is_noisy:
-            pulses.add_measurement_noise(en)
+        if sampling_measure:
+            en = self.sampled_shifted_energies(coeff, s_list, r, per_Pauli, is_noisy)
+        else:
+            en = self.shifted_energies(coeff, s_list, r)
+            if is_noisy:
+                pulses.add_measurement_noise(en)
         g = self.assemble_gradients(coeff, s_list, en, r, coeff_sign)
         return (g, en) if return_energies else g
+
+    # -- shot sampling (stochastic_measure, sim_plain.py:101-117) --------------------------------------
+    def pair_expectations(self, psi):
+        """<Z_a Z_b> of every ZZ pair for host states [batch, 2^n]: [batch, n_zz] (dq_ising_pair_expect)."""
+        N = 1 << self.problem.n
+        psi = np.ascontiguousarray(psi, dtype=np.complex128).reshape(-1, N)
+        out = np.empty((psi.shape[0], self.problem.n_zz))
+        _lib.check(_lib.load().dq_ising_pair_expect(self.handle, psi.shape[0], _lib.ptr(psi), 0, _lib.ptr(out)))
+        return out
+
+    def _measure_tables(self):
+        mt = self.problem.measure_terms
+        if mt is None:
+            raise ValueError("problem.set_measurement(...) first (the Z-string terms of sim.Pauli_M)")
+        return np.array([t[0] for t in mt]), [t[1] for t in mt]
+
+    def stochastic_measure(self, psi, per_Pauli=100):
+        pair, w = self._measure_tables()
+        return pulses.stochastic_measure_zstrings(self.pair_expectations(psi)[0], pair, w, per_Pauli)
+
+    def shifted_pair_expectations(self, coeff, s_list, r=0.5):
+        """<Z_a Z_b> of every pair in every shifted ket: [B, n_terms, 2, n_zz] (dq_ising_grad_pairs)."""
+        s_list = np.asarray(s_list, dtype=np.float64).reshape(-1)
+        tables = self.sample_tables(coeff, s_list)
+        out = np.empty((len(s_list), len(self.problem.terms), 2, self.problem.n_zz))
+        _lib.check(_lib.load().dq_ising_grad_pairs(*(self._grad_args(tables, r) + (_lib.ptr(out),))))
+        return out
+
+    def sampled_shifted_energies(self, coeff, s_list, r=0.5, per_Pauli=100, is_noisy=False):
+        """ps_p / ps_m by shot sampling in the reference's draw order (sim_plain.py:196-218)."""
+        pair, w = self._measure_tables()
+        zz = self.shifted_pair_expectations(coeff, s_list, r)
+        en = np.empty(zz.shape[:3])
+        for b in range(zz.shape[0]):
+            for i in range(zz.shape[1]):
+                for k in range(2):
+                    v = pulses.stochastic_measure_zstrings(zz[b, i, k], pair, w, per_Pauli)
+                    if is_noisy:
+                        v += np.random.normal(scale=np.abs(v) / 5)
+                    en[b, i, k] = v
+        return en
 
     # -- device-resident training loop ---------------------------------------------------------------
     def train_energy_device(self, coeff0, s_all, lr=2e-2, betas=(0.9, 0.999), eps=1e-8, r=0.5, e0=None, want_state=True):

@@ -175,3 +175,62 @@ def f_u_table_lib(channels, duration, func_type, vv, ts):
     _lib.check(_lib.load().dq_pulse_f_u_table(len(channels), _lib.ptr(counts), _lib.ptr(flat), float(duration), int(func_type),
                                               _lib.ptr(v), v.shape[1], v.shape[2], ts.size, _lib.ptr(ts), _lib.ptr(out)))
     return out
+
+
+# ---- shot sampling (SimulatorPlain.stochastic_measure, sim_plain.py:101-117) ----------------------------------------------------
+
+def measurement_bases(pauli_m):
+    """sim.Pauli_M as the reference's callers build it (demo_maxcut.py:47-65): entries [matrix, weight, (evals, estates)].
+    Returns (weights [n_meas], evals [n_meas, dim], bases [n_meas, dim, dim] complex128 with bases[m, j] = eigenvector j)."""
+    weights, evals, bases = [], [], []
+    for entry in pauli_m:
+        w, (ev, es) = entry[1], entry[2]
+        weights.append(w)
+        evals.append(np.asarray(ev, dtype=np.float64).reshape(-1))
+        bases.append(np.stack([np.asarray(e.full() if hasattr(e, "full") else e, dtype=np.complex128).reshape(-1) for e in es]))
+    return weights, np.array(evals), np.ascontiguousarray(np.array(bases, dtype=np.complex128))
+
+
+def stochastic_measure_from_probs(probs, weights, evals, per_Pauli=100):
+    """stochastic_measure (sim_plain.py:101-117) given the outcome distributions probs[m, j] = |<e_mj|psi>|^2 (:105-109) the
+    device computed: one np.random.choice(dim, per_Pauli, p=distr) per Pauli term from the GLOBAL stream (:112), then
+    ans += weight * evals[j] * freq_j / per_Pauli over j in order (:113-116; outcomes never drawn add exactly 0)."""
+    ans = 0
+    for m in range(len(weights)):
+        distr = probs[m]
+        res = np.random.choice(len(distr), per_Pauli, p=distr)
+        freq = np.bincount(res, minlength=len(distr))
+        weight = weights[m]
+        for j in np.nonzero(freq)[0]:
+            ans += weight * evals[m][j] * int(freq[j]) / per_Pauli
+    return ans
+
+
+def sampled_shifted_energies(probs, weights, evals, per_Pauli=100, is_noisy=False):
+    """ps_p / ps_m of every control of every sample by shot sampling, in the reference's draw order (sim_plain.py:196-218):
+    per sample, per control, ket_p (its Pauli terms in order, then its noise draw when is_noisy), then ket_m.
+    probs: [B, n_H, 2, n_meas, dim] -> energies [B, n_H, 2]."""
+    B, n_H = probs.shape[:2]
+    en = np.empty((B, n_H, 2))
+    for b in range(B):
+        for i in range(n_H):
+            for k in range(2):
+                v = stochastic_measure_from_probs(probs[b, i, k], weights, evals, per_Pauli)
+                if is_noisy:
+                    v += np.random.normal(scale=np.abs(np.real(v)) / 5)
+                en[b, i, k] = np.real(v)
+    return en
+
+
+def stochastic_measure_zstrings(zz, term_pair, weights, per_Pauli=100):
+    """stochastic_measure (sim_plain.py:101-117) for Z-string Pauli terms (demo_maxcut.py:47-65) given zz[e] = <Z_a Z_b>:
+    the eigenvalues of Z_a Z_b come sorted (-1 block first, eigenstates()), so the index np.random.choice(dim, per_Pauli, p)
+    draws (:112: per_Pauli uniforms, searchsorted in the cumulative distribution) has eigenvalue -1 exactly when its uniform
+    falls below P(-1) = (1 - <ZZ>) / 2.  Same stream consumption as the reference; the value differs from its j-by-j sum
+    only by the rounding of that sum (1e-16).  term_pair[m]: pair id, or -1 for the identity term (always +1)."""
+    ans = 0.0
+    for m in range(len(weights)):
+        u = np.random.random_sample(per_Pauli)
+        k_minus = 0 if term_pair[m] < 0 else int(np.count_nonzero(u < 0.5 * (1.0 - zz[term_pair[m]])))
+        ans += weights[m] * (per_Pauli - 2 * k_minus) / per_Pauli
+    return ans

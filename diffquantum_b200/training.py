@@ -10,7 +10,7 @@ class EnergyTrainer(object):
     n_samples > 1 averages that many stochastic samples per epoch (the reference uses 1)."""
 
     def __init__(self, backend, n_basis=6, n_epoch=202, lr=2e-2, n_samples=1, ground_energy=None, is_noisy=False,
-                 device_resident=False):
+                 device_resident=False, sampling_measure=False):
         self.backend = backend
         self.n_basis = n_basis
         self.n_epoch = n_epoch
@@ -21,6 +21,9 @@ class EnergyTrainer(object):
         # True: the whole loop runs on the device (backend.train_energy_device); the sample times are drawn up front from the
         # same np.random stream the reference consumes one per epoch (nothing else draws from it unless is_noisy)
         self.device_resident = device_resident
+        # SimulatorPlain(sampling_measure=True): energies by shot sampling (stochastic_measure, sim_plain.py:101-117,278-279,
+        # 202-203,212-213); the backend needs set_measurement(Pauli_M)
+        self.sampling_measure = sampling_measure
         self.device_ms = None
         self.losses_energy = []
         self.final_state = None
@@ -47,8 +50,8 @@ class EnergyTrainer(object):
         n_H, T = self._n_terms(), self._T()
         coeff = np.random.normal(0, 1e-3, [n_H, self.n_basis])             # sim_plain.py:259
         if self.device_resident:
-            if self.is_noisy:
-                raise ValueError("is_noisy interleaves noise draws with the sample times: use the host loop")
+            if self.is_noisy or self.sampling_measure:
+                raise ValueError("is_noisy / sampling_measure interleave host draws with the sample times: use the host loop")
             s_all = np.array([[np.random.uniform() * T for _ in range(self.n_samples)] for _ in range(self.n_epoch)])   # :167
             if self.ground_energy is None and hasattr(self.backend, "problem"):
                 raise ValueError("pass ground_energy (min of the observable diagonal) for structured problems")
@@ -72,11 +75,14 @@ class EnergyTrainer(object):
         for epoch in range(1, self.n_epoch + 1):
             c = self.spectral_coeff.detach().numpy().copy()
             self.final_state, loss_energy = self._final(c)                  # :276-281
+            if self.sampling_measure:
+                loss_energy = float(np.real(self.backend.stochastic_measure(self.final_state)))   # :278-279
             if self.is_noisy:
                 loss_energy += np.random.normal(scale=np.abs(loss_energy) / 5)   # :283-284, before the estimator's draws
             optimizer.zero_grad()
             s_list = [np.random.uniform() * T for _ in range(self.n_samples)]   # :167
-            grads = self.backend.grad_samples(c, s_list, is_noisy=self.is_noisy)
+            kw = {"sampling_measure": True} if self.sampling_measure else {}
+            grads = self.backend.grad_samples(c, s_list, is_noisy=self.is_noisy, **kw)
             self.spectral_coeff.grad = torch.from_numpy(np.asarray(grads).mean(axis=0))
             optimizer.step()                                                # :291-292
             self.losses_energy.append(loss_energy - e0)

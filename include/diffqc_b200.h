@@ -14,6 +14,7 @@
  *   dq_pulse_f_u_table  f_u / my_expit / bspline diffqc.cc:75-135  (host only)
  *   dq_dense_evolve     SimulatorPlain.trotter  sim_plain.py:119-153   (solver hook, sim_plain.py:43)
  *   dq_dense_grad       compute_energy_grad_MC  sim_plain.py:186-220   (prefix + 2*n_H shifted suffixes)
+ *   dq_dense_grad_probs / dq_dense_outcome_probs  stochastic_measure  sim_plain.py:101-117 (outcome distributions; draws on the host)
  *   dq_dense_grad_times the same + generate_u   sim_plain.py:52-99,186-220 (pulse rows evaluated on the device)
  *   dq_dense_train      train_energy            sim_plain.py:245-305   (whole loop on the device, dim <= 16)
  *   dq_ising_train      train_energy            sim_plain.py:245-305   (whole loop on the device, Pauli-term problems)
@@ -98,6 +99,20 @@ int dq_dense_grad(dq_context* ctx, int dim, const double* H0, int n_H, const dou
                   const int32_t* suffix_steps, const double* suffix_dt, const double* u_suffix,
                   int mode, double* energies_out);
 
+/* Shot-sampling support (SimulatorPlain.stochastic_measure, sim_plain.py:101-117, called at :202-203,212-213,278-279): the same
+ * batch of shifted trajectories, but instead of Re<ket|M|ket> the device returns, for every shifted ket and every measurement
+ * basis m, the outcome distribution distr[j] = |<e_mj|ket>|^2 that stochastic_measure builds at :105-109 and hands to
+ * np.random.choice (:112; the draws stay on the host, in the reference's order).  bases [n_meas][dim][dim] c128: component x of
+ * eigenvector j of basis m at bases[m][j][x] (sim.Pauli_M[m][2][1][j]).  probs_out [n_samples][n_H][2][n_meas][dim]. */
+int dq_dense_grad_probs(dq_context* ctx, int dim, const double* H0, int n_H, const double* Hs, const double* psi0, double r,
+                        int n_samples, const int32_t* prefix_steps, const double* prefix_dt, const double* u_prefix,
+                        const int32_t* suffix_steps, const double* suffix_dt, const double* u_suffix, int mode, int n_meas,
+                        const double* bases, double* probs_out);
+/* The same distributions for n_kets host kets [n_kets][dim] c128 (the final state of train_energy, :278-279).
+ * probs_out [n_kets][n_meas][dim]. */
+int dq_dense_outcome_probs(dq_context* ctx, int dim, int n_kets, const double* kets, int n_meas, const double* bases,
+                           double* probs_out);
+
 /* The same batch from SAMPLE TIMES: the device evaluates the step grids' pulse rows itself -- the B-spline ansatz of the Python
  * twin, u_i(t) = omega_i (2 sigma(sum_j coeff[i][j] phi_j(t/T)) - 1) on the grid of sim_plain.py:123-150 (sim_plain.py:52-99),
  * in the reference's operation order -- so nothing but s_list [n_samples] and coeff [n_H][n_basis] crosses the bus.  Resident
@@ -174,6 +189,16 @@ int dq_ising_grad_stage(dq_ising* p, int n_samples, const int32_t* prefix_steps,
                         const int32_t* shift_index, double r, const double* psi0);
 int dq_ising_grad_run_staged(dq_ising* p);                      /* asynchronous on the ctx stream */
 int dq_ising_grad_fetch(dq_ising* p, double* energies_out);     /* synchronises, copies D2H */
+
+/* Shot-sampling support on the structured path (stochastic_measure, sim_plain.py:101-117, for Z-string observables as
+ * demo_maxcut.py:47-65 builds them): <Z_a Z_b> of every ZZ pair of the problem in every shifted ket of the batch,
+ * zz_out [n_samples][n_shift][2][n_zz]; the outcome distribution of a pair collapses to P(-1) = (1 - <ZZ>) / 2 and the draws stay
+ * on the host.  The kets themselves are needed, so this call runs one kernel per term group (not the fused pass engine). */
+int dq_ising_grad_pairs(dq_ising* p, int n_samples, const int32_t* prefix_steps, const double* prefix_angles,
+                        const int32_t* suffix_steps, const double* suffix_angles, int n_shift, const int32_t* shift_kind,
+                        const int32_t* shift_index, double r, const double* psi0, double* zz_out);
+/* The same expectations for `batch` given states (host or device c128[batch][2^n], reference bit order): zz_out [batch][n_zz]. */
+int dq_ising_pair_expect(dq_ising* p, int batch, const void* psi, int psi_is_device, double* zz_out);
 
 /* Device-resident SimulatorPlain.train_energy (sim_plain.py:245-305) for a Pauli-term problem and the B-spline ansatz: n_epoch
  * epochs of (full evolution + energy, K stochastic gradient samples, their mean, torch-style Adam) enqueued on the context stream

@@ -203,6 +203,68 @@ def golden_split_reference(sp_split, qp, name, n, edges, seed, per_step, n_sampl
     print(name, "energy", energy.real, "|grad0|", np.linalg.norm(grads[0]))
 
 
+def demo_pauli_m(qp, n_qubit=4, graph=DEMO_GRAPH):
+    """sim.Pauli_M exactly as demo_maxcut.py:47-65 builds it (Z-strings of the edges with weight 0.5, the identity with
+    weight -len(graph)/2, each with the stand-in's eigenstates())."""
+    I = np.array([[1, 0], [0, 1]])
+    Z = np.array([[1, 0], [0, -1]])
+    II = I
+    for i in range(n_qubit - 1):
+        II = np.kron(II, I)
+    pauli_m = []
+    for e in graph:
+        curr = Z if 0 in e else I
+        for i in range(1, n_qubit):
+            curr = np.kron(curr, Z if i in e else I)
+        pauli_m.append([curr, 0.5])
+    pauli_m.append([II, -0.5 * len(graph)])
+    for i in range(len(pauli_m)):
+        pauli_m[i].append(qp.Qobj(pauli_m[i][0]).eigenstates())
+    return pauli_m
+
+
+def golden_sampling(sp, qp, name, base, n_samples=3, n_epoch=8):
+    """REFERENCE: shot sampling (sampling_measure=True -> stochastic_measure, sim_plain.py:101-117,202-203,212-213,278-279).
+    (i) compute_energy_grad_MC on the inputs of fixture `base`, plain and with is_noisy; (ii) train_energy for n_epoch epochs
+    on the demo problem.  Pauli_M as demo_maxcut.py:47-65 builds it."""
+    g = np.load(os.path.join(OUT, base + ".npz"), allow_pickle=False)
+    coeff = g["coeff"]
+    pauli_m = demo_pauli_m(qp)
+    out = {}
+    for tag, noisy in (("plain", False), ("noisy", True)):
+        sim = make_sim(sp, int(g["n_basis"]), str(g["basis"]), float(g["T"]), g["omegas"], len(g["Hs"]), coeff, int(g["per_step"]))
+        sim.sampling_measure = True
+        sim.is_noisy = noisy
+        sim.Pauli_M = pauli_m
+        H = ref_H(sim, qp, g["H0"], list(g["Hs"]), coeff)
+        grads, s_list = [], []
+        for k in range(n_samples):
+            np.random.seed(4000 + k)
+            state = np.random.get_state()
+            grads.append(sim.compute_energy_grad_MC(qp.Qobj(g["M"]), H, qp.Qobj(g["psi0"])).numpy().copy())
+            np.random.set_state(state)
+            s_list.append(np.random.uniform() * float(g["T"]))
+        out["grads_" + tag] = np.array(grads)
+        out["s"] = np.array(s_list)
+    # one direct stochastic_measure call on the final state of the base fixture
+    np.random.seed(4100)
+    out["measure_final"] = sim.stochastic_measure(qp.Qobj(g["final"]))
+    # train_energy with shot sampling
+    sim = sp.SimulatorPlain(lr=2e-2, n_basis=6, n_epoch=n_epoch, sampling_measure=True)
+    sim.T = float(g["T"])
+    sim.omegas = list(g["omegas"])
+    sim.Pauli_M = pauli_m
+    np.random.seed(7)
+    sim.train_energy(qp.Qobj(g["M"]), qp.Qobj(g["H0"]), [qp.Qobj(h) for h in g["Hs"]], qp.Qobj(g["psi0"]))
+    np.savez(os.path.join(OUT, name + ".npz"), base=base, seed0=4000, train_seed=7, n_epoch=n_epoch,
+             weights=np.array([p[1] for p in pauli_m]), evals=np.array([p[2][0] for p in pauli_m]),
+             estates=np.array([[e.full().reshape(-1) for e in p[2][1]] for p in pauli_m]),
+             losses_energy=np.array(sim.losses_energy, dtype=float), final_coeff=sim.spectral_coeff.detach().numpy(),
+             source="REFERENCE sim_plain.py:101-117,156-231,245-305 with sampling_measure=True, run unmodified behind oracle/standin",
+             **out)
+    print(name, "|grad0|", np.linalg.norm(out["grads_plain"][0]), "loss[-1]", sim.losses_energy[-1])
+
+
 def fu_cases():
     """Inputs that walk every branch of diffqc.cc:75-135: both bases, the +-32 cutoff of my_expit, |N| < 1e-6,
     idx rounding (C round: half away from zero), times outside [0, duration] (bump support / Legendre beyond +-1)."""
@@ -285,6 +347,9 @@ def main():
     if sys.argv[1:] == ["noisy"]:                       # only the fixture added last; the others stay as committed
         golden_noisy_estimator(sp, qp, "demo_noisy_ref", "demo_bspline_ref")
         return
+    if sys.argv[1:] == ["sampling"]:
+        golden_sampling(sp, qp, "demo_sampling_ref", "demo_bspline_ref")
+        return
     if sys.argv[1:] == ["fu_ref"]:
         golden_fu_reference("fu_cc_ref")
         return
@@ -314,6 +379,7 @@ def main():
     golden_split_reference(sps, qp, "split_ref_n4", 4, DEMO_GRAPH, seed=21, per_step=10)
     golden_split_reference(sps, qp, "split_ref_n6", 6, R.random_regular_edges(6, seed=1), seed=22, per_step=10)
     golden_fu_reference("fu_cc_ref")
+    golden_sampling(sp, qp, "demo_sampling_ref", "demo_bspline_ref")
 
 
 if __name__ == "__main__":

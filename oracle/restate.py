@@ -371,11 +371,25 @@ def grad_mc_structured(prob, coeff, s, per_step, mode='split', basis='BSpline', 
     return grad
 
 
+def stochastic_measure(psi, weights, evals, estates, per_Pauli=100):
+    """sim_plain.py:101-117: per Pauli term, distr[j] = |<psi|e_j>|^2, per_Pauli draws with np.random.choice from the global
+    stream, ans += weight * evals[j] * freq_j / per_Pauli over j in order."""
+    ans = 0
+    for i in range(len(weights)):
+        distr = [abs(np.vdot(psi, estates[i][j])) ** 2 for j in range(len(evals[i]))]
+        res = np.random.choice(len(evals[i]), per_Pauli, p=distr)
+        for j in range(len(evals[i])):
+            freq = np.count_nonzero(res == j)
+            ans += weights[i] * evals[i][j] * freq / per_Pauli
+    return ans
+
+
 def grad_mc_dense(H0, Hs, M, psi0, coeff, omegas, T, s, per_step, mode='exact', basis='BSpline',
-                  coeff_sign=1.0, r=0.5, return_energies=False, is_noisy=False):
+                  coeff_sign=1.0, r=0.5, return_energies=False, is_noisy=False, sampling=None):
     """Dense twin of grad_mc_structured: sim_plain.py:156-231 on explicit matrices.  is_noisy adds the reference's
     measurement noise (sim_plain.py:207-208,217-218): one np.random.normal(scale=|ps|/5) per shifted energy, drawn from
-    the global stream in the order ps_p, ps_m per control."""
+    the global stream in the order ps_p, ps_m per control.  sampling = (weights, evals, estates): shot sampling
+    (sampling_measure=True, :202-203,212-213)."""
     n_H = len(Hs)
     d = len(psi0)
 
@@ -389,11 +403,11 @@ def grad_mc_dense(H0, Hs, M, psi0, coeff, omegas, T, s, per_step, mode='exact', 
         gate_p = (np.eye(d) + r * 1.j * Hs[i]) / np.sqrt(1. + r ** 2)
         gate_m = (np.eye(d) - r * 1.j * Hs[i]) / np.sqrt(1. + r ** 2)
         ket_p = run(gate_p @ phi, s, T)
-        ps_p = (ket_p.conj() @ M @ ket_p)
+        ps_p = (ket_p.conj() @ M @ ket_p) if sampling is None else stochastic_measure(ket_p, *sampling) + 0j
         if is_noisy:
             ps_p += np.random.normal(scale=np.abs(ps_p.real) / 5)
         ket_m = run(gate_m @ phi, s, T)
-        ps_m = (ket_m.conj() @ M @ ket_m)
+        ps_m = (ket_m.conj() @ M @ ket_m) if sampling is None else stochastic_measure(ket_m, *sampling) + 0j
         if is_noisy:
             ps_m += np.random.normal(scale=np.abs(ps_m.real) / 5)
         energies[i] = (ps_p.real, ps_m.real)

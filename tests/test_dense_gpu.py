@@ -263,9 +263,6 @@ def test_noisy_estimator_dropin_follows_the_reference_stream(golden):
     np.random.seed(int(gn["seed0"]))
     s0 = np.random.uniform() * float(g["T"])
     assert rel(ds.grad_samples(g["coeff"], [s0], is_noisy=True)[0], gn["grads"][0]) < TOL
-    sim.sampling_measure = True
-    with pytest.raises(ValueError):
-        est(qp.Qobj(g["M"]), H, qp.Qobj(g["psi0"]))
 
 
 def test_dense_errors_are_python_exceptions():
@@ -412,3 +409,65 @@ def test_device_resident_training_follows_the_reference_run(golden):
     b = dq.EnergyTrainer(sim, n_basis=6, n_epoch=12, lr=2e-2, n_samples=5)
     b.train_energy()
     assert np.abs(np.array(a.losses_energy) - np.array(b.losses_energy)).max() < 1e-10
+
+
+def pauli_m_of(gs):
+    """sim.Pauli_M in the reference's layout (demo_maxcut.py:47-65) from the fixture's arrays."""
+    return [[None, float(w), (ev, list(es))] for w, ev, es in zip(gs["weights"], gs["evals"], gs["estates"])]
+
+
+@pytest.mark.parametrize("strategy", [-1, 0])
+def test_shot_sampling_matches_the_reference_run(golden, strategy):
+    """sampling_measure=True (stochastic_measure, sim_plain.py:101-117): outcome distributions of every shifted ket from the
+    device (dq_dense_grad_probs: resident engine and GEMM strategy), np.random.choice draws on the host in the reference's
+    order -- gradients, a direct measurement and an 8-epoch train_energy against the reference's own run with the same seeds."""
+    gs = golden("demo_sampling_ref")
+    g = golden(str(gs["base"]))
+    ds = sim_from(g)
+    if strategy >= 0:
+        ds.set_option("strategy", strategy)
+    try:
+        ds.set_measurement(pauli_m_of(gs))
+        probs = ds.outcome_probs(g["final"])
+        assert probs.shape == (1, len(gs["weights"]), ds.dim)
+        assert np.abs(probs.sum(axis=2) - 1).max() < 1e-12
+        np.random.seed(4100)
+        assert ds.stochastic_measure(g["final"]) == complex(gs["measure_final"]).real
+        for tag, noisy in (("plain", False), ("noisy", True)):
+            for k, s in enumerate(gs["s"]):
+                np.random.seed(int(gs["seed0"]) + k)
+                s_k = np.random.uniform() * float(g["T"])
+                grad = ds.grad_samples(g["coeff"], [s_k], is_noisy=noisy, sampling_measure=True)[0]
+                assert rel(grad, gs["grads_" + tag][k]) < TOL
+        np.random.seed(int(gs["train_seed"]))
+        tr = dq.EnergyTrainer(ds, n_basis=6, n_epoch=int(gs["n_epoch"]), lr=2e-2, sampling_measure=True)
+        tr.train_energy()
+        assert np.abs(np.array(tr.losses_energy) - gs["losses_energy"]).max() < 1e-9
+        assert np.abs(tr.spectral_coeff.detach().numpy() - gs["final_coeff"]).max() < 1e-9
+    finally:
+        ds.set_option("strategy", -1)
+
+
+def test_shot_sampling_estimator_dropin(golden):
+    """estimator_for(sim) with sim.sampling_measure = True and sim.Pauli_M set, as a caller of the reference would."""
+    here = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "oracle", "standin")
+    sys.path.insert(0, here)
+    try:
+        import qutip as qp
+    finally:
+        sys.path.remove(here)
+    gs = golden("demo_sampling_ref")
+    g = golden(str(gs["base"]))
+    sim = _FakeSim(g)
+    sim.sampling_measure = True
+    sim.Pauli_M = [[None, float(w), (ev, [qp.Qobj(e) for e in es])] for w, ev, es in zip(gs["weights"], gs["evals"], gs["estates"])]
+    H = [qp.Qobj(g["H0"])] + [[qp.Qobj(g["Hs"][i]),
+                               (lambda i: lambda t, args: R.u_plain(i, t, g["coeff"], g["omegas"], sim.T))(i)]
+                              for i in range(sim.n_Hs)]
+    est = dq.estimator_for(sim)
+    for tag, noisy in (("plain", False), ("noisy", True)):
+        sim.is_noisy = noisy
+        for k in range(len(gs["s"])):
+            np.random.seed(int(gs["seed0"]) + k)
+            grad = est(qp.Qobj(g["M"]), H, qp.Qobj(g["psi0"]))
+            assert rel(grad.numpy(), gs["grads_" + tag][k]) < TOL

@@ -280,3 +280,54 @@ def test_device_resident_training_matches_host_loop(n, engine, K, n_epoch):
     assert np.abs(a.spectral_coeff.detach().numpy() - b.spectral_coeff.detach().numpy()).max() < 1e-10
     assert rel(a.final_state, b.final_state) < 1e-10
     assert np.abs(np.array(a.losses_energy)).max() > 1e-3
+
+
+def test_shot_sampling_matches_the_reference_run(golden):
+    """sampling_measure=True on the structured path: <Z_a Z_b> of every shifted ket from the device (dq_ising_grad_pairs),
+    the reference's draws on the host -- against the reference's own run of the demo problem (exact step, tests/golden/
+    demo_sampling_ref.npz: gradients plain and noisy, a direct measurement, an 8-epoch train_energy)."""
+    gs = golden("demo_sampling_ref")
+    g = golden(str(gs["base"]))
+    prob = dq.IsingProblem.maxcut(4, [[0, 1], [0, 3], [1, 2], [2, 3]])
+    assert [w for _, w in prob.measure_terms] == list(gs["weights"])
+    sim = dq.IsingSimulator(prob, per_step=int(g["per_step"]), step="exact")
+    zz = sim.pair_expectations(g["final"])[0]
+    dense_zz = [float(np.real(np.vdot(g["final"], np.diag(R.z_diag(4, a) * R.z_diag(4, b)) @ g["final"]))) for a, b in prob.zz_pairs]
+    assert np.abs(zz - dense_zz).max() < 1e-13
+    np.random.seed(4100)
+    assert abs(sim.stochastic_measure(g["final"]) - complex(gs["measure_final"]).real) < 1e-12
+    for tag, noisy in (("plain", False), ("noisy", True)):
+        for k in range(len(gs["s"])):
+            np.random.seed(int(gs["seed0"]) + k)
+            s_k = np.random.uniform() * prob.T
+            grad = sim.grad_samples(g["coeff"], [s_k], is_noisy=noisy, sampling_measure=True)[0]
+            assert rel(grad, gs["grads_" + tag][k]) < TOL
+    np.random.seed(int(gs["train_seed"]))
+    tr = dq.EnergyTrainer(sim, n_basis=6, n_epoch=int(gs["n_epoch"]), lr=2e-2, sampling_measure=True, ground_energy=-4.0)
+    tr.train_energy()
+    assert np.abs(np.array(tr.losses_energy) - gs["losses_energy"]).max() < 1e-9
+    assert np.abs(tr.spectral_coeff.detach().numpy() - gs["final_coeff"]).max() < 1e-9
+
+
+def test_pair_expectations_with_the_automatic_layout_and_split_step():
+    """n=14 (fused engine would be the default; the pair call runs the per-term kernels): <ZZ> of the shifted kets vs the oracle."""
+    n = 14
+    edges = graph_for(n)
+    prob = dq.IsingProblem.maxcut(n, edges)
+    ref = R.maxcut_structured(n, edges)
+    coeff = np.random.RandomState(3).normal(0, 1, [len(prob.terms), 6])
+    sim = dq.IsingSimulator(prob, per_step=2)
+    assert sim.info("engine") == 1 and sim.info("identity_layout") in (0, 1)
+    s = 0.77
+    zz = sim.shifted_pair_expectations(coeff, [s])[0]
+    assert sim.info("engine") == 1                         # back on the fused engine afterwards
+    en = sim.shifted_energies(coeff, [s])[0]
+    # the observable is -1/2 sum_e (1 - Z_a Z_b): the pair expectations must reproduce the fused engine's energies
+    assert np.abs((-0.5 * (len(edges) - zz.sum(axis=2))) - en).max() < 1e-10
+    ns, dt, ts = R.step_grid(s, ref["T"], 2)
+    phi = R.evolve_split_structured(ref, R.coef_table_plain(coeff, ref["omegas"], ref["T"], R.step_grid(0, s, 2)[2]), R.step_grid(0, s, 2)[1], ref["psi0"])
+    for i in (0, len(edges) + 3):
+        for k, sign in enumerate((+1, -1)):
+            ket = R.evolve_split_structured(ref, R.coef_table_plain(coeff, ref["omegas"], ref["T"], ts), dt, R.apply_shift_gate(ref, ref["terms"][i], phi, sign))
+            want = [float(np.sum(np.abs(ket) ** 2 * R.z_diag(n, a) * R.z_diag(n, b))) for a, b in prob.zz_pairs]
+            assert np.abs(zz[i, k] - want).max() < 1e-10
