@@ -10,5 +10,7 @@ from .ising import IsingProblem, IsingSimulator  # noqa: F401
 from .dense import DenseSimulator, dense_evolve, estimator_for, solver_for  # noqa: F401
 from . import diffqc, sharding  # noqa: F401
 from .training import EnergyTrainer  # noqa: F401
+from . import comparators  # noqa: F401
+from .comparators import FDTrainer, FidelityTrainer  # noqa: F401
 
 __version__ = "dev"

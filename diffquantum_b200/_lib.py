@@ -38,6 +38,8 @@ SIGNATURES = {
     "dq_dense_grad_probs": (ctypes.c_int, [_VP, ctypes.c_int, _VP, ctypes.c_int, _VP, _VP, ctypes.c_double, ctypes.c_int, _VP, _VP, _VP,
                                            _VP, _VP, _VP, ctypes.c_int, ctypes.c_int, _VP, _VP]),
     "dq_dense_outcome_probs": (ctypes.c_int, [_VP, ctypes.c_int, ctypes.c_int, _VP, ctypes.c_int, _VP, _VP]),
+    "dq_dense_evolve_many": (ctypes.c_int, [_VP, ctypes.c_int, _VP, ctypes.c_int, _VP, _VP, ctypes.c_int, _VP, _VP, _VP, _VP, ctypes.c_int,
+                                            _VP, _VP]),
     "dq_dense_train": (ctypes.c_int, [_VP, ctypes.c_int, _VP, ctypes.c_int, _VP, _VP, _VP, _VP, ctypes.c_double, ctypes.c_int,
                                       ctypes.c_int, _VP, ctypes.c_int, ctypes.c_int, _VP, ctypes.c_double, ctypes.c_double,
                                       ctypes.c_double, ctypes.c_double, ctypes.c_double, ctypes.c_double, ctypes.c_int, _VP, _VP]),

@@ -651,6 +651,91 @@ int dq_dense_evolve(dq_context* ctx, int dim, const double* H0, int n_H, const d
     return DQ_OK;
 }
 
+int dq_dense_evolve_many(dq_context* ctx, int dim, const double* H0, int n_H, const double* Hs, const double* M, int n_traj,
+                         const double* psi_in, const int32_t* steps, const double* dts, const double* u, int mode,
+                         double* energies_out, double* psi_out) {
+    DQ_REQUIRE(ctx && psi_in && steps && dts && (energies_out || psi_out), "dq_dense_evolve_many: NULL argument");
+    DQ_REQUIRE(!energies_out || M, "dq_dense_evolve_many: energies need the observable");
+    DQ_REQUIRE(mode == 0 || mode == 1, "dq_dense_evolve_many: mode must be 0 (exact) or 1 (split)");
+    DQ_REQUIRE(n_traj >= 1, "dq_dense_evolve_many: n_traj=%d", n_traj);
+    DQ_TRY(ctx->set_device());
+    State* S = state_of(ctx);
+    Problem& P = S->scratch_H;
+    DQ_TRY(upload_problem(ctx, P, dim, H0, n_H, Hs));
+    if (M) DQ_TRY(upload_observable(ctx, P, M));
+    for (size_t i = 0; i < (size_t)2 * dim * n_traj; ++i) DQ_REQUIRE(std::isfinite(psi_in[i]), "dq_dense_evolve_many: non-finite psi entry");
+    std::vector<long long> off(n_traj + 1, 0);
+    for (int b = 0; b < n_traj; ++b) {
+        DQ_REQUIRE(steps[b] >= 0 && std::isfinite(dts[b]), "dq_dense_evolve_many: bad step count or dt (trajectory %d)", b);
+        off[b + 1] = off[b] + steps[b];
+    }
+    DQ_REQUIRE(off[n_traj] == 0 || n_H == 0 || u, "dq_dense_evolve_many: NULL pulse table");
+    static const double no_u = 0.0;
+    const double* uu = (u && n_H) ? u : &no_u;
+    bool resident = false;
+    DQ_TRY(want_resident(ctx, P, &resident));
+    S->last_gemm_flops = 0;
+    if (resident) {
+        double bound = 0.0;
+        DQ_TRY(norm_bound(P, mode, n_traj, steps, dts, off.data(), uu, &bound));
+        const int s = log2_ceil_ratio(bound, 1.0), m = 18;
+        DQ_REQUIRE(s <= 20, "dense path: ||dt H|| = %g is too large", bound);
+        S->last_kernel_ms = 0;
+        DQ_TRY(small_upload(ctx, P, M));
+        std::vector<double> kets((size_t)n_traj * 32, 0.0);
+        for (int c = 0; c < n_traj; ++c) memcpy(kets.data() + (size_t)c * 32, psi_in + (size_t)2 * dim * c, sizeof(double) * 2 * dim);
+        DQ_TRY(S->phi.reserve(kets.size() * sizeof(double)));
+        DQ_TRY(S->out.reserve((kets.size() + n_traj) * sizeof(double)));
+        const size_t u_count = (size_t)off[n_traj] * n_H;
+        DQ_TRY(S->u_dev.reserve(std::max<size_t>(1, u_count) * sizeof(double)));
+        if (u_count) DQ_CUDA(cudaMemcpyAsync(S->u_dev.p, uu, u_count * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        DQ_CUDA(cudaMemcpyAsync(S->phi.p, kets.data(), kets.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        std::vector<SmallTraj> traj(n_traj);
+        for (int c = 0; c < n_traj; ++c) traj[c] = SmallTraj{off[c], std::ldexp(dts[c], -s), 0.0, steps[c], c, 0, c};
+        if (psi_out) {
+            DQ_TRY(small_run(ctx, P, mode, s, m, 1, traj, S->u_dev.as<double>(), S->phi.as<double>(), S->out.as<double>(), nullptr, 1.0));
+            DQ_CUDA(cudaMemcpyAsync(kets.data(), S->out.p, kets.size() * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        }
+        if (energies_out) {
+            double* dE = S->out.as<double>() + kets.size();
+            DQ_TRY(small_run(ctx, P, mode, s, m, 1, traj, S->u_dev.as<double>(), S->phi.as<double>(), nullptr, dE, 1.0));
+            DQ_CUDA(cudaMemcpyAsync(energies_out, dE, (size_t)n_traj * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        }
+        DQ_CUDA(cudaStreamSynchronize(ctx->stream));
+        if (psi_out)
+            for (int c = 0; c < n_traj; ++c) memcpy(psi_out + (size_t)2 * dim * c, kets.data() + (size_t)c * 32, sizeof(double) * 2 * dim);
+        S->last_strategy = 3;
+        S->last_squarings = s;
+        S->last_degree = m;
+        return DQ_OK;
+    }
+    // GEMM strategies: one 8-column ket block per trajectory (column 0 carries the state), every block its own step list
+    const int Ncp = 8, Dp = P.Dp;
+    const size_t blk = (size_t)2 * Dp * Ncp;
+    std::vector<double> host((size_t)n_traj * blk, 0.0), one(blk);
+    for (int c = 0; c < n_traj; ++c) {
+        std::fill(one.begin(), one.end(), 0.0);
+        put_column(one, Dp, Ncp, dim, 0, psi_in + (size_t)2 * dim * c);
+        memcpy(host.data() + (size_t)c * blk, one.data(), blk * sizeof(double));
+    }
+    DQ_TRY(S->phi.reserve(host.size() * sizeof(double)));
+    DQ_TRY(S->out.reserve((size_t)n_traj * sizeof(double)));
+    DQ_CUDA(cudaMemcpyAsync(S->phi.p, host.data(), host.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    DQ_TRY(evolve_blocks(ctx, P, mode, n_traj, Ncp, steps, dts, off.data(), uu, off[n_traj], S->phi.as<double>()));
+    if (energies_out) {
+        DQ_TRY(energies(ctx, P, n_traj, S->phi.as<double>(), Ncp, 1, S->out.as<double>()));
+        DQ_CUDA(cudaMemcpyAsync(energies_out, S->out.p, (size_t)n_traj * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    if (psi_out) DQ_CUDA(cudaMemcpyAsync(host.data(), S->phi.p, host.size() * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    DQ_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (psi_out)
+        for (int c = 0; c < n_traj; ++c) {
+            memcpy(one.data(), host.data() + (size_t)c * blk, blk * sizeof(double));
+            get_column(one, Dp, Ncp, dim, 0, psi_out + (size_t)2 * dim * c);
+        }
+    return DQ_OK;
+}
+
 static int grad_impl(dq_context* ctx, int dim, const double* H0, int n_H, const double* Hs, const double* M,
                   const double* psi0, double r, int n_samples, const int32_t* prefix_steps, const double* prefix_dt,
                   const double* u_prefix, const int32_t* suffix_steps, const double* suffix_dt, const double* u_suffix,

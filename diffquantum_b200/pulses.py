@@ -52,7 +52,22 @@ def basis_table(basis, n_basis, ts, T):
         return bspline_table(n_basis, ts / T)
     if basis == 'Legendre':
         return legendre_table(n_basis, 2 * ts / T - 1)
-    raise ValueError("unsupported basis %r (reference hot path ships BSpline and Legendre)" % (basis,))
+    if basis == 'poly':
+        # sim_plain.py:86-87: (t - 0.5) ** j on the raw time; Python float powers, element by element (NumPy's vectorised pow
+        # may round differently)
+        return np.array([[(float(t) - 0.5) ** j for j in range(n_basis)] for t in ts.reshape(-1)], dtype=np.float64).reshape(-1, n_basis)
+    if basis == 'Fourier':
+        # sim_plain.py:90-92: columns [cos(2 pi j t) for j < n | sin(2 pi j t) for j < n], n = int(n_basis / 2); scalar calls as
+        # in the reference (the vectorised sin / cos kernels may round differently)
+        n = int(n_basis / 2)
+        out = np.zeros((ts.size, n_basis))
+        for k, t in enumerate(ts.reshape(-1)):
+            t = float(t)
+            for j in range(n):
+                out[k, j] = np.cos(2 * np.pi * j * t)
+                out[k, j + n] = np.sin(2 * np.pi * j * t)
+        return out
+    raise ValueError("unsupported basis %r (sim_plain.py:84-94 knows BSpline, Legendre, poly, Fourier)" % (basis,))
 
 
 def step_grids(T0s, Ts, per_step):
@@ -84,13 +99,27 @@ def u_table(coeff, omegas, T, ts, basis='BSpline'):
     coeff = np.asarray(coeff, dtype=np.float64)
     phi = basis_table(basis, coeff.shape[1], ts, T)             # [K, n_basis]
     a = np.zeros((phi.shape[0], coeff.shape[0]))
-    for j in range(coeff.shape[1]):                             # same summation order as the loop at :85
-        a = a + phi[:, j:j + 1] * coeff[None, :, j]
+    if basis == 'Fourier':                                      # :90-92: u += (c_j cos + c_{j+n} sin), the pair summed first
+        n = int(coeff.shape[1] / 2)
+        for j in range(n):
+            a = a + (coeff[None, :, j] * phi[:, j:j + 1] + coeff[None, :, j + n] * phi[:, j + n:j + n + 1])
+    else:
+        for j in range(coeff.shape[1]):                         # same summation order as the loop at :85
+            a = a + phi[:, j:j + 1] * coeff[None, :, j]
     return (_sigmoid(a) * 2 - 1) * np.asarray(omegas, dtype=np.float64)[None, :]
+
+
+def _estimator_basis(basis):
+    """compute_energy_grad_MC only defines its derivative block for two bases (sim_plain.py:171-176): with 'poly' or 'Fourier'
+    the reference itself stops at :178 (coeff_A is never assigned).  Same behaviour here."""
+    if basis not in ('BSpline', 'Legendre'):
+        raise ValueError("compute_energy_grad_MC is undefined for basis %r in the reference (sim_plain.py:171-178 assigns coeff_A "
+                         "for 'Legendre' and 'BSpline' only); the evolution (generate_u) supports it" % (basis,))
 
 
 def dudc_table(coeff, omegas, T, s, basis='BSpline'):
     """dDdv[i, j] = d u_i(s) / d c_ij = omega_i 2 sigma'(A_i) phi_j(s)  (sim_plain.py:169-184)."""
+    _estimator_basis(basis)
     coeff = np.asarray(coeff, dtype=np.float64)
     phi = basis_table(basis, coeff.shape[1], [s], T)[0]
     a = np.zeros(coeff.shape[0])
@@ -102,6 +131,7 @@ def dudc_table(coeff, omegas, T, s, basis='BSpline'):
 
 def dudc_tables(coeff, omegas, T, s_list, basis='BSpline'):
     """dudc_table for many sample times: [len(s_list), n_H, n_basis], bit-identical to per-sample calls."""
+    _estimator_basis(basis)
     coeff = np.asarray(coeff, dtype=np.float64)
     s_list = np.asarray(s_list, dtype=np.float64).reshape(-1)
     phi = basis_table(basis, coeff.shape[1], s_list, T)             # [B, n_basis]

@@ -13,6 +13,7 @@
  *   dq_dense_trotter    diffqc.trotter + f_u    diffqc.cc:95-135, 173-205
  *   dq_pulse_f_u_table  f_u / my_expit / bspline diffqc.cc:75-135  (host only)
  *   dq_dense_evolve     SimulatorPlain.trotter  sim_plain.py:119-153   (solver hook, sim_plain.py:43)
+ *   dq_dense_evolve_many  forward runs of compute_energy_grad_FD / train_fidelity  sim_plain.py:322-351, 441-449
  *   dq_dense_grad       compute_energy_grad_MC  sim_plain.py:186-220   (prefix + 2*n_H shifted suffixes)
  *   dq_dense_grad_probs / dq_dense_outcome_probs  stochastic_measure  sim_plain.py:101-117 (outcome distributions; draws on the host)
  *   dq_dense_grad_times the same + generate_u   sim_plain.py:52-99,186-220 (pulse rows evaluated on the device)
@@ -88,6 +89,14 @@ int dq_pulse_f_u_table(int n_H, const int32_t* chan_counts, const double* channe
 int dq_dense_evolve(dq_context* ctx, int dim, const double* H0, int n_H, const double* Hs,
                     const double* u, int n_steps, double dt, int mode, int batch,
                     const double* psi_in, double* psi_out);
+
+/* n_traj independent trajectories, each with its OWN start ket, step count, dt and pulse rows (u packed [sum_b steps_b][n_H]):
+ * the forward runs of the finite-difference comparator (compute_energy_grad_FD, sim_plain.py:322-351: one evolution per
+ * perturbed coefficient) and of train_fidelity's state batch (:441-449).  energies_out [n_traj] = Re<psi|M|psi> (needs M),
+ * psi_out [n_traj][dim] c128; either may be NULL. */
+int dq_dense_evolve_many(dq_context* ctx, int dim, const double* H0, int n_H, const double* Hs, const double* M, int n_traj,
+                         const double* psi_in, const int32_t* steps, const double* dts, const double* u, int mode,
+                         double* energies_out, double* psi_out);
 
 /* Batched stochastic parameter-shift samples on a dense problem (sim_plain.py:186-220).
  * For each sample b: phi = U(prefix_b) psi0; for each term i and sign +/-:

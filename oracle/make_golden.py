@@ -203,6 +203,78 @@ def golden_split_reference(sp_split, qp, name, n, edges, seed, per_step, n_sampl
     print(name, "energy", energy.real, "|grad0|", np.linalg.norm(grads[0]))
 
 
+def golden_basis_evolution(sp, qp, name, basis, n_basis, seed, per_step=10):
+    """REFERENCE: generate_u / trotter with the 'poly' and 'Fourier' bases (sim_plain.py:84-92) on the demo problem, and what
+    compute_energy_grad_MC does with them (it stops at :178: coeff_A is only assigned for 'Legendre' and 'BSpline')."""
+    demo = R.maxcut_structured(4, DEMO_GRAPH)
+    H0, Hs, M = R.maxcut_dense(demo)
+    rng = np.random.RandomState(seed)
+    coeff = rng.normal(0, 1, [len(Hs), n_basis])
+    sim = make_sim(sp, n_basis, basis, demo["T"], demo["omegas"], len(Hs), coeff, per_step)
+    H = ref_H(sim, qp, H0, Hs, coeff)
+    q0 = qp.Qobj(demo["psi0"])
+    final = sim.trotter(H, q0, 0, demo["T"]).full().reshape(-1)
+    part = sim.trotter(H, q0, 0.4, 1.3).full().reshape(-1)
+    n_steps, dt, ts = R.step_grid(0, demo["T"], per_step)
+    u_tab = np.array([[H[i + 1][1](t, None) for i in range(len(Hs))] for t in ts])
+    try:
+        np.random.seed(1)
+        sim.compute_energy_grad_MC(qp.Qobj(M), H, q0)
+        err = ""
+    except Exception as e:                                   # UnboundLocalError at sim_plain.py:178
+        err = type(e).__name__
+    np.savez(os.path.join(OUT, name + ".npz"), H0=H0, Hs=np.array(Hs), M=M, psi0=demo["psi0"], omegas=demo["omegas"], T=demo["T"],
+             n_basis=n_basis, basis=basis, per_step=per_step, coeff=coeff, final=final, partial=part,
+             partial_span=np.array([0.4, 1.3]), ts=ts, dt=dt, u_tab=u_tab, estimator_error=err,
+             source="REFERENCE sim_plain.py:73-99,119-153 run unmodified behind oracle/standin")
+    print(name, "estimator:", err or "ran", "|final|", np.linalg.norm(final))
+
+
+def golden_comparators(sp, qp, name):
+    """REFERENCE: the comparison methods (sim_plain.py:308-475) behind the stand-in's mesolve (DOP853, rtol 1e-12).
+    (i) compute_energy_grad_FD and a noisy one on the demo problem; (ii) train_energy_FD, 2 epochs; (iii) train_fidelity,
+    4 epochs over two (initial, target) pairs of a two-qubit problem, plain and noisy."""
+    demo = R.maxcut_structured(4, DEMO_GRAPH)
+    H0, Hs, M = R.maxcut_dense(demo)
+    rng = np.random.RandomState(61)
+    coeff = rng.normal(0, 1, [len(Hs), 6])
+    out = {}
+    for tag, noisy in (("plain", False), ("noisy", True)):
+        sim = make_sim(sp, 6, "BSpline", demo["T"], demo["omegas"], len(Hs), coeff)
+        sim.is_noisy = noisy
+        H = ref_H(sim, qp, H0, Hs, coeff)
+        np.random.seed(5000)
+        out["fd_grad_" + tag] = sim.compute_energy_grad_FD(qp.Qobj(M), H, qp.Qobj(demo["psi0"])).numpy().copy()
+    sim = sp.SimulatorPlain(lr=2e-2, n_basis=6, n_epoch=2)
+    sim.T = demo["T"]
+    sim.omegas = list(demo["omegas"])
+    np.random.seed(5001)
+    sim.train_energy_FD(qp.Qobj(M), qp.Qobj(H0), [qp.Qobj(h) for h in Hs], qp.Qobj(demo["psi0"]))
+    out["fd_train_losses"] = np.array(sim.losses_energy, dtype=float)
+    out["fd_train_coeff"] = sim.spectral_coeff.detach().numpy()
+    out["fd_train_final"] = sim.final_state.full().reshape(-1)
+    # state transfer on two qubits: drift ZZ, controls X and Y on each qubit; |00> -> Bell-like, |01> -> its partner
+    F_H0 = 0.4 * pauli_string("ZZ")
+    F_Hs = [pauli_string(s) for s in ("XI", "IX", "YI", "IY")]
+    inits = [np.array([1, 0, 0, 0], dtype=complex), np.array([0, 1, 0, 0], dtype=complex)]
+    targets = [np.array([1, 0, 0, 1j], dtype=complex) / np.sqrt(2), np.array([0, 1, 1j, 0], dtype=complex) / np.sqrt(2)]
+    for tag, noisy in (("plain", False), ("noisy", True)):
+        sim = sp.SimulatorPlain(lr=5e-2, n_basis=5, n_epoch=4, is_noisy=noisy)
+        sim.T = 1.5
+        sim.omegas = [2.0, 2.0, 1.5, 1.5]
+        import contextlib, io
+        np.random.seed(5002)
+        with contextlib.redirect_stdout(io.StringIO()):
+            sim.train_fidelity(qp.Qobj(F_H0), [qp.Qobj(h) for h in F_Hs], [qp.Qobj(p) for p in inits], [qp.Qobj(p) for p in targets])
+        out["fid_losses_" + tag] = np.array(sim.losses_energy, dtype=float)
+        out["fid_coeff_" + tag] = sim.spectral_coeff.detach().numpy()
+    np.savez(os.path.join(OUT, name + ".npz"), H0=H0, Hs=np.array(Hs), M=M, psi0=demo["psi0"], omegas=demo["omegas"], T=demo["T"],
+             coeff=coeff, delta=1e-3, F_H0=F_H0, F_Hs=np.array(F_Hs), F_inits=np.array(inits), F_targets=np.array(targets),
+             F_T=1.5, F_omegas=np.array([2.0, 2.0, 1.5, 1.5]),
+             source="REFERENCE sim_plain.py:308-475 run unmodified behind oracle/standin (mesolve = SciPy DOP853 at rtol 1e-12)", **out)
+    print(name, "|fd grad|", np.linalg.norm(out["fd_grad_plain"]), "fid losses", out["fid_losses_plain"])
+
+
 def demo_pauli_m(qp, n_qubit=4, graph=DEMO_GRAPH):
     """sim.Pauli_M exactly as demo_maxcut.py:47-65 builds it (Z-strings of the edges with weight 0.5, the identity with
     weight -len(graph)/2, each with the stand-in's eigenstates())."""
@@ -347,6 +419,13 @@ def main():
     if sys.argv[1:] == ["noisy"]:                       # only the fixture added last; the others stay as committed
         golden_noisy_estimator(sp, qp, "demo_noisy_ref", "demo_bspline_ref")
         return
+    if sys.argv[1:] == ["bases"]:
+        golden_basis_evolution(sp, qp, "demo_poly_ref", "poly", 4, seed=51)
+        golden_basis_evolution(sp, qp, "demo_fourier_ref", "Fourier", 6, seed=52)
+        return
+    if sys.argv[1:] == ["comparators"]:
+        golden_comparators(sp, qp, "comparators_ref")
+        return
     if sys.argv[1:] == ["sampling"]:
         golden_sampling(sp, qp, "demo_sampling_ref", "demo_bspline_ref")
         return
@@ -380,6 +459,9 @@ def main():
     golden_split_reference(sps, qp, "split_ref_n6", 6, R.random_regular_edges(6, seed=1), seed=22, per_step=10)
     golden_fu_reference("fu_cc_ref")
     golden_sampling(sp, qp, "demo_sampling_ref", "demo_bspline_ref")
+    golden_basis_evolution(sp, qp, "demo_poly_ref", "poly", 4, seed=51)
+    golden_basis_evolution(sp, qp, "demo_fourier_ref", "Fourier", 6, seed=52)
+    golden_comparators(sp, qp, "comparators_ref")
 
 
 if __name__ == "__main__":

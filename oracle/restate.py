@@ -68,11 +68,16 @@ def u_plain(i, t, coeff, omegas, T, basis='BSpline'):
     """u_i(t) of the Python twin: sim_plain.py:73-99 (sequential accumulation from j=0)."""
     n_basis = coeff.shape[1]
     u = 0
-    for j in range(n_basis):
+    n = int(n_basis / 2) if basis == 'Fourier' else n_basis                # :84
+    for j in range(n):
         if basis == 'BSpline':
             u += coeff[i][j] * bspline_value(j, n_basis, t / T)
         elif basis == 'Legendre':
             u += coeff[i][j] * eval_legendre(j, 2 * t / T - 1)
+        elif basis == 'poly':                                              # :86-87 (raw t, not t / T)
+            u += coeff[i][j] * (t - 0.5) ** j
+        elif basis == 'Fourier':                                           # :90-92
+            u += coeff[i][j] * np.cos(2 * np.pi * j * t) + coeff[i][j + n] * np.sin(2 * np.pi * j * t)
         else:
             raise ValueError(basis)
     return (sigmoid_py(u) * 2 - 1) * omegas[i]

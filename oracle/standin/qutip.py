@@ -6,7 +6,7 @@ is imported UNMODIFIED behind this module so that its own NumPy/SciPy code can
 be run as the parity oracle.  Use sites in the reference:
   sim_plain.py:121,129,131 (.full), :152 (Qobj(ndarray)), :197-199 (qeye, +, -, *, /),
   :205,215,281 (matrix_element), :294 (eigenenergies), :496-499 (.data, [i]);
-  demo_maxcut.py:65 (eigenstates), :81-85 (Qobj(ndarray)).
+  demo_maxcut.py:65 (eigenstates), :81-85 (Qobj(ndarray)); sim_plain.py:330,386,448 (mesolve, comparators only).
 Nothing here tidies small elements (real qutip may); the stand-in run is authoritative.
 """
 import numpy as np
@@ -90,5 +90,30 @@ def qeye(d):
     return Qobj(np.eye(int(d)))
 
 
-def mesolve(*a, **k):  # pragma: no cover - off the hot path (FD / fidelity comparators)
-    raise NotImplementedError("qutip.mesolve is outside the hot path; not provided by the stand-in")
+class _Result(object):
+    def __init__(self, states):
+        self.states = states
+
+
+def mesolve(H, psi0, tlist, *a, **k):
+    """Stand-in for qutip.mesolve on a closed system with a ket (use sites: sim_plain.py:330,386,448): the Schroedinger
+    equation d psi / dt = -i (H0 + sum_i u_i(t, args) H_i) psi for H = [H0, [H_i, u_i], ...], integrated with SciPy's DOP853 at
+    tolerances far below anything the comparators resolve (qutip's own default is an Adams method at rtol 1e-6).  Returns an
+    object with .states = [Qobj at every t in tlist]."""
+    from scipy.integrate import solve_ivp
+    H0 = H[0].full() if isinstance(H[0], Qobj) else np.asarray(H[0], dtype=np.complex128)
+    terms = [(h[0].full(), h[1]) for h in H[1:]]
+    y0 = psi0.full().reshape(-1)
+
+    def rhs(t, y):
+        Ht = H0.copy()
+        for (Hi, ui) in terms:
+            Ht = Ht + ui(t, None) * Hi
+        return -1j * (Ht @ y)
+
+    tlist = np.asarray(tlist, dtype=np.float64)
+    sol = solve_ivp(rhs, (float(tlist[0]), float(tlist[-1])), y0, method="DOP853", t_eval=tlist, rtol=1e-12, atol=1e-14,
+                    max_step=1e-2)
+    if not sol.success:
+        raise RuntimeError("stand-in mesolve: %s" % sol.message)
+    return _Result([Qobj(sol.y[:, i]) for i in range(sol.y.shape[1])])

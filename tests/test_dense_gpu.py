@@ -471,3 +471,63 @@ def test_shot_sampling_estimator_dropin(golden):
             np.random.seed(int(gs["seed0"]) + k)
             grad = est(qp.Qobj(g["M"]), H, qp.Qobj(g["psi0"]))
             assert rel(grad.numpy(), gs["grads_" + tag][k]) < TOL
+
+
+@pytest.mark.parametrize("name", ["demo_poly_ref", "demo_fourier_ref"])
+def test_poly_and_fourier_bases_evolution_matches_reference(golden, name):
+    """basis 'poly' / 'Fourier' (sim_plain.py:84-92): SimulatorPlain.trotter of the reference vs the dense path and the
+    structured path (exact step); compute_energy_grad_MC is undefined for them in the reference (raises at :178) -> ValueError."""
+    g = golden(name)
+    ds = sim_from(g)
+    assert rel(ds.evolve(g["coeff"], 0, float(g["T"])), g["final"]) < TOL
+    assert rel(ds.evolve(g["coeff"], float(g["partial_span"][0]), float(g["partial_span"][1])), g["partial"]) < TOL
+    with pytest.raises(ValueError):
+        ds.grad_samples(g["coeff"], [0.5])
+    prob = dq.IsingProblem.maxcut(4, [[0, 1], [0, 3], [1, 2], [2, 3]])
+    sim = dq.IsingSimulator(prob, per_step=int(g["per_step"]), step="exact", basis=str(g["basis"]))
+    psi, _ = sim.evolve(g["coeff"], 0, prob.T)
+    assert rel(psi[0], g["final"]) < TOL
+    with pytest.raises(ValueError):
+        sim.grad_samples(g["coeff"], [0.5])
+
+
+def test_finite_difference_comparator_matches_reference(golden):
+    """compute_energy_grad_FD / train_energy_FD (sim_plain.py:308-412): forward runs = 4th-order Magnus integration on the
+    device (all 2 n_H n_basis perturbed runs in one batch per segment) vs the reference behind the stand-in's mesolve."""
+    from diffquantum_b200 import comparators as C
+    g = golden("comparators_ref")
+    ds = dq.DenseSimulator(g["H0"], g["Hs"], g["omegas"], float(g["T"]), M=g["M"], psi0=g["psi0"], per_step=10)
+    grad = C.grad_fd(ds, g["coeff"], delta=float(g["delta"]))
+    assert np.abs(grad - g["fd_grad_plain"]).max() < 1e-9
+    np.random.seed(5000)
+    noisy = C.grad_fd(ds, g["coeff"], delta=float(g["delta"]), is_noisy=True)
+    assert np.abs(noisy - g["fd_grad_noisy"]).max() < 1e-7 * np.abs(g["fd_grad_noisy"]).max()
+    # the stochastic estimator agrees with the finite differences in expectation only; the two integrate different spans
+    # ([0, 1] vs [0, T]) in the reference, so no cross-check between them here
+    np.random.seed(5001)
+    tr = C.FDTrainer(ds, n_basis=6, n_epoch=2, lr=2e-2)
+    tr.train_energy_FD()
+    assert np.abs(np.array(tr.losses_energy) - g["fd_train_losses"]).max() < 1e-9
+    assert np.abs(tr.spectral_coeff.detach().numpy() - g["fd_train_coeff"]).max() < 1e-8
+    assert rel(tr.final_state, g["fd_train_final"]) < 1e-8
+    # the GEMM strategies take the same batch
+    ds.set_option("strategy", 0)
+    try:
+        assert np.abs(C.grad_fd(ds, g["coeff"], delta=float(g["delta"]), h=1e-2) - g["fd_grad_plain"]).max() < 1e-7
+    finally:
+        ds.set_option("strategy", -1)
+
+
+@pytest.mark.parametrize("tag", ["plain", "noisy"])
+def test_train_fidelity_matches_reference(golden, tag):
+    """train_fidelity (sim_plain.py:414-475): projector observable, gradient = compute_energy_grad_MC(coeff=-1), one Adam
+    step per (initial, target) pair -- against the reference's own 4-epoch run on a two-qubit transfer problem."""
+    from diffquantum_b200 import comparators as C
+    g = golden("comparators_ref")
+    ds = dq.DenseSimulator(g["F_H0"], g["F_Hs"], g["F_omegas"], float(g["F_T"]), per_step=10)
+    np.random.seed(5002)
+    tr = C.FidelityTrainer(ds, n_basis=5, n_epoch=4, lr=5e-2, is_noisy=(tag == "noisy"))
+    tr.train_fidelity(list(g["F_inits"]), list(g["F_targets"]))
+    assert np.abs(tr.spectral_coeff.detach().numpy() - g["fid_coeff_" + tag]).max() < 1e-9
+    assert np.abs(np.array(tr.losses_energy) - g["fid_losses_" + tag]).max() < 1e-8
+    assert ds.M is None and ds.psi0 is None                    # the trainer leaves the simulator as it found it

@@ -1,5 +1,6 @@
 """Host-side logic of the structured path (no GPU): pulse tables, step grids, angle rows."""
 import numpy as np
+import pytest
 
 from diffquantum_b200 import pulses as P
 from diffquantum_b200 import pulses
@@ -24,6 +25,24 @@ def test_u_table_matches_reference_closures(golden):
         g = golden(name)
         u = P.u_table(g["coeff"], g["omegas"], float(g["T"]), g["ts"], str(g["basis"]))
         np.testing.assert_allclose(u, g["u_tab"], rtol=1e-13, atol=1e-15)
+
+
+def test_poly_and_fourier_bases_match_reference_closures(golden):
+    """generate_u with basis 'poly' / 'Fourier' (sim_plain.py:84-92): the host table and the oracle's scalar restatement
+    against the values of the reference's own closures; the estimator is undefined for them in the reference (it raises at
+    :178) and is rejected here."""
+    for name in ("demo_poly_ref", "demo_fourier_ref"):
+        g = golden(name)
+        basis = str(g["basis"])
+        u = P.u_table(g["coeff"], g["omegas"], float(g["T"]), g["ts"], basis)
+        np.testing.assert_allclose(u, g["u_tab"], rtol=1e-13, atol=1e-15)      # np.exp vs math.exp: 1 ulp
+        ref = np.array([[R.u_plain(i, t, g["coeff"], g["omegas"], float(g["T"]), basis) for i in range(len(g["omegas"]))] for t in g["ts"]])
+        np.testing.assert_array_equal(ref, g["u_tab"])
+        assert str(g["estimator_error"]) == "UnboundLocalError"
+        with pytest.raises(ValueError):
+            P.dudc_table(g["coeff"], g["omegas"], float(g["T"]), 0.3, basis)
+        with pytest.raises(ValueError):
+            P.dudc_tables(g["coeff"], g["omegas"], float(g["T"]), [0.3, 0.4], basis)
 
 
 def test_dudc_matches_autograd_restatement():
