@@ -68,6 +68,8 @@ SIGNATURES = {
     "dq_slice_phase": (ctypes.c_int, [_VP, _VP, ctypes.c_int, ctypes.c_uint64, ctypes.c_int, ctypes.c_int, _VP, _VP]),
     "dq_slice_rx": (ctypes.c_int, [_VP, _VP, ctypes.c_int, ctypes.c_int, ctypes.c_double]),
     "dq_slice_rx_many": (ctypes.c_int, [_VP, _VP, ctypes.c_int, ctypes.c_int, _VP, _VP]),
+    "dq_slice_phase_rx_many": (ctypes.c_int, [_VP, _VP, ctypes.c_int, ctypes.c_uint64, ctypes.c_int, ctypes.c_int, _VP, _VP,
+                                              ctypes.c_int, _VP, _VP]),
     "dq_slice_energy": (ctypes.c_int, [_VP, _VP, ctypes.c_int, ctypes.c_uint64, ctypes.c_int, ctypes.c_int, _VP, _VP,
                                        ctypes.c_double, ctypes.POINTER(ctypes.c_double)]),
     "dq_microbench": (ctypes.c_int, [_VP, ctypes.c_int, ctypes.c_int64, ctypes.c_int,

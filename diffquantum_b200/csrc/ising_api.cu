@@ -18,6 +18,54 @@ int check_rows(const dq_ising* p, const double* rows, int64_t n_rows, const char
 // the fused engines implement the product-formula step only; the exact step runs on the generic engine
 bool use_fused(const dq_ising* p) { return p->step_mode == 0 && p->engine >= 1 && !p->want_pairs && dq::fused_supported(p); }
 
+// n > 20 (the persistent pass engine plans 12 <= n <= 20): the product step runs on the fused slice kernels of slice.cu --
+// one Gray-code phase pass and ceil-ish(n / 12) rotation passes per step instead of n + 1 per-term kernels.
+bool use_slice_passes(const dq_ising* p) { return p->step_mode == 0 && p->engine >= 1 && !p->want_pairs && p->n > 20; }
+
+// One product-formula step sequence on ONE state of n qubits held whole on this device (L = n, no high bits).
+int slice_evolve(dq_ising* p, c128* psi, const double* h_rows, int n_steps) {
+    std::vector<int32_t> pair_bits(2 * (size_t)std::max(1, p->n_zz)), xbits(p->n);
+    for (int e = 0; e < p->n_zz; ++e) { pair_bits[2 * e] = p->pa[e]; pair_bits[2 * e + 1] = p->pb[e]; }
+    for (int q = 0; q < p->n; ++q) xbits[q] = p->bitpos[q];
+    for (int k = 0; k < n_steps; ++k) {
+        const double* row = h_rows + (size_t)k * p->row_len;
+        DQ_TRY(dq_slice_phase_rx_many(p->ctx, psi, p->n, 0, p->n, p->n_zz, pair_bits.data(), row, p->n, xbits.data(),
+                                      row + 1 + p->n_zz));
+    }
+    return DQ_OK;
+}
+
+// Batched gradient samples for n > 20: per sample the prefix state, then the 2 n_shift shifted kets in chunks that fit the
+// device (a ket is 16 * 2^n bytes: 1 GiB at n = 26), each evolved by the slice passes, energies by the generic reduction.
+int slice_grad_run(dq_ising* p) {
+    auto& s = p->st;
+    cudaStream_t st = p->ctx->stream;
+    const size_t N = p->dim();
+    const int kets = 2 * s.n_shift;
+    DQ_REQUIRE(!p->host_rows_a.empty() || s.prefix_off[s.n_samples] == 0, "slice passes: host angle rows missing");
+    DQ_TRY(p->phi.reserve(N * sizeof(c128)));
+    size_t free_b = 0, total_b = 0;
+    DQ_CUDA(cudaMemGetInfo(&free_b, &total_b));
+    const size_t have = p->states.cap + free_b / 2;              // what the chunk buffer may grow to
+    const int chunk = (int)std::max<size_t>(1, std::min<size_t>((size_t)kets, have / (N * sizeof(c128))));
+    DQ_TRY(p->states.reserve((size_t)chunk * N * sizeof(c128)));
+    c128* phi = p->phi.as<c128>();
+    for (int b = 0; b < s.n_samples; ++b) {
+        if (s.uniform_psi0) DQ_TRY(dq::gen_fill_uniform(p, phi, 1));
+        else DQ_CUDA(cudaMemcpyAsync(phi, s.psi0.p, N * sizeof(c128), cudaMemcpyDeviceToDevice, st));
+        DQ_TRY(slice_evolve(p, phi, p->host_rows_a.data() + s.prefix_off[b] * p->row_len, s.prefix_steps[b]));
+        for (int k0 = 0; k0 < kets; k0 += chunk) {
+            const int cnt = std::min(chunk, kets - k0);
+            DQ_TRY(dq::gen_fanout(p, phi, p->states.as<c128>(), cnt, p->shift_desc.as<dq::ShiftDesc>() + k0, s.r));
+            for (int g = 0; g < cnt; ++g)
+                DQ_TRY(slice_evolve(p, p->states.as<c128>() + (size_t)g * N, p->host_rows_b.data() + s.suffix_off[b] * p->row_len,
+                                    s.suffix_steps[b]));
+            DQ_TRY(dq::gen_energy(p, p->states.as<c128>(), cnt, p->energies.as<double>() + (size_t)b * kets + k0));
+        }
+    }
+    return DQ_OK;
+}
+
 // ---- qubit -> bit layout ---------------------------------------------------------------------------------
 // Reference order is bit n-1-q for qubit q (np.kron order, demo_maxcut.py:53-57).  The fused engine keeps two
 // sets of five index bits in registers (J_L and J_H, see Geo<> in ising_fused.cu and dq::fused_j_sets);
@@ -317,7 +365,7 @@ int dq_ising_set_option(dq_ising* p, const char* name, int64_t value) {
 
 int dq_ising_get_info(dq_ising* p, const char* name, int64_t* value) {
     DQ_REQUIRE(p && name && value, "NULL argument");
-    if (!strcmp(name, "engine")) *value = use_fused(p) ? 1 : 0;
+    if (!strcmp(name, "engine")) *value = use_fused(p) ? 1 : (use_slice_passes(p) ? 2 : 0);   // 2: fused slice passes (n > 20)
     else if (!strcmp(name, "ket_group")) *value = dq::auto_ket_group(p);
     else if (!strcmp(name, "row_len")) *value = p->row_len;
     else if (!strcmp(name, "identity_layout")) *value = p->identity_layout ? 1 : 0;
@@ -366,6 +414,9 @@ int dq_ising_evolve(dq_ising* p, int batch, int n_steps, const double* angles, c
     if (use_fused(p)) {
         DQ_TRY(dq::fused_evolve(p, d, batch, angles, n_steps, energies_out ? p->energies.as<double>() : nullptr,
                                 psi_out != nullptr));
+    } else if (use_slice_passes(p)) {
+        for (int g = 0; g < batch; ++g) DQ_TRY(slice_evolve(p, d + (size_t)g * N, angles, n_steps));
+        if (energies_out) DQ_TRY(dq::gen_energy(p, d, batch, p->energies.as<double>()));
     } else {
         if (n_steps) {
             DQ_TRY(p->rows_a.reserve((size_t)n_steps * p->row_len * sizeof(double)));
@@ -426,9 +477,12 @@ int dq_ising_grad_stage(dq_ising* p, int n_samples, const int32_t* prefix_steps,
         }
     }
     DQ_TRY(dq::stage_trig(p));
-    if (p->step_mode == 1) {
+    if (p->step_mode == 1 || use_slice_passes(p)) {
         p->host_rows_a.assign(prefix_angles, prefix_angles + np * p->row_len);
         p->host_rows_b.assign(suffix_angles, suffix_angles + ns * p->row_len);
+    } else {
+        p->host_rows_a.clear();
+        p->host_rows_b.clear();
     }
     DQ_CUDA(cudaStreamSynchronize(st));          // the caller's tables may go out of scope
     s.valid = true;
@@ -445,6 +499,8 @@ int dq_ising_grad_run_staged(dq_ising* p) {
     double steps = 0;
     if (use_fused(p)) {
         DQ_TRY(dq::fused_grad_run(p));
+    } else if (use_slice_passes(p) && !(p->host_rows_a.empty() && p->host_rows_b.empty() && s.prefix_off[s.n_samples] + s.suffix_off[s.n_samples] > 0)) {
+        DQ_TRY(slice_grad_run(p));
     } else {
         cudaStream_t st = p->ctx->stream;
         DQ_TRY(p->phi.reserve(N * sizeof(c128)));

@@ -142,11 +142,95 @@ __device__ __forceinline__ void rot_pair(double2& a, double2& b, double c, doubl
 // rounds (threads 32 / 64 / 128 bytes apart) stay bank-conflict free
 __device__ __forceinline__ int tslot(int e) { return e ^ ((e >> 3) & 7); }
 
-template <bool CONTIG, bool SCALED>
-__global__ void __launch_bounds__(kThreads, 3) k_slice_rx_tile(double2* __restrict__ psi, int L, const TileArgs* __restrict__ ta) {
+// PHASE (contiguous 12-bit tiles only): the diagonal phase of the SAME step rides on this pass -- applied to the tile in shared
+// memory right after it has landed, before the first rotation round -- so a product-formula step costs one pass over the
+// slice less.  Thread t owns tile bits 0..7 (= its index) and walks tile bits 8..11 in Gray-code order exactly like
+// k_slice_phase_gray: one full angle evaluation + sincos per 16 amplitudes, then per flipped bit the <= kGrayDeg pair factors
+// exp(+-2i w_e) of that bit.
+constexpr int kWalkBits = 4, kWalkLo = 8, kTileBits = 12, kMaxIn = 96;
+template <bool CONTIG, bool SCALED, bool PHASE>
+__global__ void __launch_bounds__(kThreads, 3) k_slice_rx_tile(double2* __restrict__ psi, int L, const TileArgs* __restrict__ ta,
+                                                               const PhaseArgs* __restrict__ pa, unsigned long long high) {
     extern __shared__ __align__(16) double2 tile[];
     __shared__ TileArgs A;
-    if (threadIdx.x == 0) A = *ta;
+    // PHASE tables, built once per CTA from the pair list (tile bit = physical bit k < 12 in a contiguous pass):
+    //   out_*   per tile bit k: its pairs whose other end lies OUTSIDE the tile -> per tile a field h[k] on z_k
+    //   in_*    pairs with both ends inside the tile
+    //   oo_idx  pairs with both ends outside the tile -> per tile a constant
+    //   w_*     per walk bit j (tile bit 8 + j): exp(2i w) factors of its in-tile pairs, and of its outside pairs (per tile
+    //           folded into ONE factor f_out[j]; z_p = -1 takes its conjugate)
+    __shared__ int out_n[kTileBits], w_in_n[kWalkBits], w_out_n[kWalkBits], in_n, oo_n;
+    __shared__ unsigned char out_other[kTileBits][kGrayDeg], in_a[kMaxIn], in_b[kMaxIn], oo_idx[kMaxPairs];
+    __shared__ unsigned char w_in_other[kWalkBits][kGrayDeg], w_out_other[kWalkBits][kGrayDeg];
+    __shared__ double out_ang[kTileBits][kGrayDeg], in_ang[kMaxIn], oo_ang[PHASE ? kMaxPairs : 1];
+    __shared__ double w_in_c2[kWalkBits][kGrayDeg], w_in_s2[kWalkBits][kGrayDeg], w_out_c2[kWalkBits][kGrayDeg], w_out_s2[kWalkBits][kGrayDeg];
+    __shared__ double h_field[kTileBits], c_tile;
+    __shared__ double2 f_out[kWalkBits], ww[1 << kWalkBits];
+    __shared__ int has_ww;
+    if (threadIdx.x == 0) { A = *ta; has_ww = 0; }
+    __syncthreads();
+    if (PHASE) {
+        const int n_zz = pa->n_zz;
+        if (threadIdx.x < kTileBits) {
+            const int k = threadIdx.x;
+            int d = 0;
+            for (int e = 0; e < n_zz; ++e) {
+                const int a = pa->a[e], b = pa->b[e];
+                if ((a != k && b != k) || (a < kTileBits && b < kTileBits)) continue;
+                out_other[k][d] = (unsigned char)(a == k ? b : a);
+                out_ang[k][d] = pa->ang[e];
+                ++d;
+            }
+            out_n[k] = d;
+        } else if (threadIdx.x == kTileBits) {
+            int d = 0, o = 0;
+            for (int e = 0; e < n_zz; ++e) {
+                const int a = pa->a[e], b = pa->b[e];
+                if (a < kTileBits && b < kTileBits) { in_a[d] = (unsigned char)a; in_b[d] = (unsigned char)b; in_ang[d] = pa->ang[e]; ++d; }
+                else if (a >= kTileBits && b >= kTileBits) { oo_idx[o] = (unsigned char)e; oo_ang[o] = pa->ang[e]; ++o; }
+            }
+            in_n = d;
+            oo_n = o;
+        } else if (threadIdx.x < kTileBits + 1 + kWalkBits) {
+            const int j = threadIdx.x - kTileBits - 1, p = kWalkLo + j;
+            int di = 0, dout = 0;
+            for (int e = 0; e < n_zz; ++e) {
+                const int a = pa->a[e], b = pa->b[e];
+                if (a != p && b != p) continue;
+                const int o = a == p ? b : a;
+                if (o >= kWalkLo && o < kTileBits) continue;                 // walk-walk pair: ww[] below
+                double sn, cs;
+                sincos(2.0 * pa->ang[e], &sn, &cs);
+                if (o < kWalkLo) { w_in_other[j][di] = (unsigned char)o; w_in_c2[j][di] = cs; w_in_s2[j][di] = sn; ++di; }
+                else { w_out_other[j][dout] = (unsigned char)o; w_out_c2[j][dout] = cs; w_out_s2[j][dout] = sn; ++dout; }
+            }
+            w_in_n[j] = di;
+            w_out_n[j] = dout;
+        } else if (threadIdx.x >= 32 && threadIdx.x < 32 + (1 << kWalkBits)) {
+            // pairs among the walk bits themselves: the Gray sequence is fixed, so the state of the other walk bits at step kk
+            // is known -- one factor per step, the same for every thread and tile
+            const int kk = threadIdx.x - 32;
+            double2 f = make_double2(1.0, 0.0);
+            if (kk >= 1) {
+                const int j = __ffs(kk) - 1, p = kWalkLo + j;
+                const int before = (kk - 1) ^ ((kk - 1) >> 1);               // Gray code of the previous step = walk bits before this flip
+                const bool zp_neg = ((before >> j) & 1) != 0;
+                for (int e = 0; e < n_zz; ++e) {
+                    const int a = pa->a[e], b = pa->b[e];
+                    if (a != p && b != p) continue;
+                    const int o = a == p ? b : a;
+                    if (o < kWalkLo || o >= kTileBits) continue;
+                    double sn, cs;
+                    sincos(2.0 * pa->ang[e], &sn, &cs);
+                    const bool differ = (((before >> (o - kWalkLo)) & 1) != 0) != zp_neg;
+                    const double s2 = differ ? -sn : sn;
+                    f = make_double2(f.x * cs - f.y * s2, f.x * s2 + f.y * cs);
+                    has_ww = 1;
+                }
+            }
+            ww[kk] = f;
+        }
+    }
     __syncthreads();
     const int T = A.T, lo = A.lo, n_el = 1 << T;
     const unsigned lowmask = (1u << lo) - 1u;
@@ -175,7 +259,76 @@ __global__ void __launch_bounds__(kThreads, 3) k_slice_rx_tile(double2* __restri
             asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
-        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        if (PHASE) {
+            // per-tile constants while the tile is in flight: fields of the outside bits on every tile bit, the
+            // outside-outside constant, the outside factor of every walk bit (fixed summation / product order)
+            const unsigned long long G = (high << L) | base;                 // tile bits are zero in `base`
+            if (threadIdx.x < kTileBits) {
+                const int k = threadIdx.x;
+                double hsum = 0.0;
+                for (int q = 0; q < out_n[k]; ++q) hsum += ((G >> out_other[k][q]) & 1ull) ? -out_ang[k][q] : out_ang[k][q];
+                h_field[k] = hsum;
+            } else if (threadIdx.x == kTileBits) {
+                double c = pa->c0;
+                for (int q = 0; q < oo_n; ++q) {
+                    const int e = oo_idx[q];
+                    c += (((G >> pa->a[e]) ^ (G >> pa->b[e])) & 1ull) ? -oo_ang[q] : oo_ang[q];
+                }
+                c_tile = c;
+            } else if (threadIdx.x < kTileBits + 1 + kWalkBits) {
+                const int j = threadIdx.x - kTileBits - 1;
+                double2 f = make_double2(1.0, 0.0);
+                for (int q = 0; q < w_out_n[j]; ++q) {
+                    const double c2 = w_out_c2[j][q], s2 = ((G >> w_out_other[j][q]) & 1ull) ? -w_out_s2[j][q] : w_out_s2[j][q];
+                    f = make_double2(f.x * c2 - f.y * s2, f.x * s2 + f.y * c2);
+                }
+                f_out[j] = f;
+            }
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+            __syncthreads();
+            int e = threadIdx.x;                                             // tile bits 0..7; walk bits 8..11 start at 0
+            double a = c_tile;
+#pragma unroll
+            for (int k = 0; k < kTileBits; ++k) a += ((e >> k) & 1) ? -h_field[k] : h_field[k];
+            for (int q = 0; q < in_n; ++q) a += (((e >> in_a[q]) ^ (e >> in_b[q])) & 1) ? -in_ang[q] : in_ang[q];
+            double sn, cs;
+            sincos(a, &sn, &cs);
+            double2 ph = make_double2(cs, -sn);                              // exp(-i a)
+            // flip factor of walk bit j for THIS thread and tile (z_p = +1 form): the outside pairs (f_out) times the pairs
+            // with this thread's own bits -- constant over the walk, so the walk itself is one multiply per flip
+            double2 F[kWalkBits];
+#pragma unroll
+            for (int j = 0; j < kWalkBits; ++j) {
+                double2 f = f_out[j];
+                for (int q = 0; q < w_in_n[j]; ++q) {
+                    const double c2 = w_in_c2[j][q], s2 = ((e >> w_in_other[j][q]) & 1) ? -w_in_s2[j][q] : w_in_s2[j][q];
+                    f = make_double2(f.x * c2 - f.y * s2, f.x * s2 + f.y * c2);
+                }
+                F[j] = f;
+            }
+            const bool any_ww = has_ww != 0;
+            {
+                const double2 v = tile[tslot(e)];
+                tile[tslot(e)] = make_double2(v.x * ph.x - v.y * ph.y, v.x * ph.y + v.y * ph.x);
+            }
+#pragma unroll
+            for (int kk = 1; kk < (1 << kWalkBits); ++kk) {
+                const int j = (kk & 1) ? 0 : ((kk & 2) ? 1 : ((kk & 4) ? 2 : 3));       // lowest set bit of kk (compile time after unrolling)
+                const int before = (kk - 1) ^ ((kk - 1) >> 1);
+                const bool zp_neg = ((before >> j) & 1) != 0;                // z_p before the flip: known from the Gray sequence
+                const double fy = zp_neg ? -F[j].y : F[j].y;
+                ph = make_double2(ph.x * F[j].x - ph.y * fy, ph.x * fy + ph.y * F[j].x);
+                if (any_ww) {
+                    const double2 w = ww[kk];
+                    ph = make_double2(ph.x * w.x - ph.y * w.y, ph.x * w.y + ph.y * w.x);
+                }
+                e ^= 1 << (kWalkLo + j);
+                const double2 v = tile[tslot(e)];
+                tile[tslot(e)] = make_double2(v.x * ph.x - v.y * ph.y, v.x * ph.y + v.y * ph.x);
+            }
+        } else {
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+        }
         __syncthreads();
         int k = 0;
         for (; k + 2 < A.n_active; k += 3) {                // three bits per round trip (A.active is ascending)
@@ -436,7 +589,14 @@ int dq_slice_rx(dq_context* ctx, void* psi_dev, int L, int bit, double theta) {
     return DQ_OK;
 }
 
-int dq_slice_rx_many(dq_context* ctx, void* psi_dev, int L, int count, const int32_t* bits, const double* thetas) {
+}  // extern "C"
+
+namespace {
+// All rotations of a step; d_phase != NULL: the step's diagonal phase is applied by the first pass if that pass is a
+// contiguous 12-bit tile pass (*phase_done says whether it was).
+int rx_many_impl(dq_context* ctx, void* psi_dev, int L, int count, const int32_t* bits, const double* thetas,
+                 const PhaseArgs* d_phase, unsigned long long high_bits, bool* phase_done) {
+    if (phase_done) *phase_done = false;
     DQ_REQUIRE(ctx && psi_dev && (count == 0 || (bits && thetas)), "NULL argument");
     DQ_REQUIRE(L >= 1 && L <= 33 && count >= 0 && count <= L, "dq_slice_rx_many: L=%d count=%d", L, count);
     DQ_TRY(ctx->set_device());
@@ -460,20 +620,27 @@ int dq_slice_rx_many(dq_context* ctx, void* psi_dev, int L, int count, const int
     const int Tmax = std::min(tile_bits, L);
     {   // the attribute is per device and cheap to set: no process-wide "done" flag (two contexts, two devices)
         const int max_smem = (int)(sizeof(double2) << 12);
-        DQ_CUDA(cudaFuncSetAttribute(k_slice_rx_tile<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
-        DQ_CUDA(cudaFuncSetAttribute(k_slice_rx_tile<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
-        DQ_CUDA(cudaFuncSetAttribute(k_slice_rx_tile<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
-        DQ_CUDA(cudaFuncSetAttribute(k_slice_rx_tile<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+        DQ_CUDA(cudaFuncSetAttribute(k_slice_rx_tile<true, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+        DQ_CUDA(cudaFuncSetAttribute(k_slice_rx_tile<true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+        DQ_CUDA(cudaFuncSetAttribute(k_slice_rx_tile<false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+        DQ_CUDA(cudaFuncSetAttribute(k_slice_rx_tile<false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+        DQ_CUDA(cudaFuncSetAttribute(k_slice_rx_tile<true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+        DQ_CUDA(cudaFuncSetAttribute(k_slice_rx_tile<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
     }
+    // The contiguous pass takes every target below bit 12 whether or not it carries the phase.  (Measured at n = 24: the phase
+    // adds ~70 us to it -- 181 us against 109 us alone and 88 us for the phase as its own pass, the tile kernel being bound by
+    // instruction issue and shared-memory latency rather than HBM -- and moving targets 8..11 to the high-bit passes to
+    // balance the three passes made the step slower, 386 us against 371 us: every tile pass pays a fixed load/store latency.)
+    const int contig_take = Tmax;
     size_t next = 0;
     while (next < tg.size()) {
         TileArgs h;
         memset(&h, 0, sizeof(h));
-        if (tg[next].first < Tmax) {                        // pass over the contiguous tile bits [0, Tmax)
+        if (tg[next].first < contig_take) {                 // pass over the contiguous tile bits [0, Tmax)
             h.T = Tmax;
             h.lo = Tmax;
             for (int i = 0; i < Tmax; ++i) h.pos[i] = (unsigned char)i;
-            while (next < tg.size() && tg[next].first < Tmax) {
+            while (next < tg.size() && tg[next].first < contig_take) {
                 h.active[h.n_active] = (unsigned char)tg[next].first;
                 h.c[h.n_active] = cos(tg[next].second);
                 h.s[h.n_active] = sin(tg[next].second);
@@ -523,13 +690,59 @@ int dq_slice_rx_many(dq_context* ctx, void* psi_dev, int L, int count, const int
         const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, ((size_t)200 << 10) / std::max<size_t>(smem, 1)));
         const unsigned grid = (unsigned)std::min<unsigned long long>(n_tiles, (unsigned long long)ctx->prop.multiProcessorCount * per_sm);
         double2* psi = (double2*)psi_dev;
-        if (h.lo == h.T && h.scaled) k_slice_rx_tile<true, true><<<grid, kThreads, smem, ctx->stream>>>(psi, L, d);
-        else if (h.lo == h.T) k_slice_rx_tile<true, false><<<grid, kThreads, smem, ctx->stream>>>(psi, L, d);
-        else if (h.scaled) k_slice_rx_tile<false, true><<<grid, kThreads, smem, ctx->stream>>>(psi, L, d);
-        else k_slice_rx_tile<false, false><<<grid, kThreads, smem, ctx->stream>>>(psi, L, d);
+        const bool with_phase = d_phase && phase_done && !*phase_done && h.lo == h.T && h.T == kWalkLo + kWalkBits;
+        if (with_phase) {
+            if (h.scaled) k_slice_rx_tile<true, true, true><<<grid, kThreads, smem, ctx->stream>>>(psi, L, d, d_phase, high_bits);
+            else k_slice_rx_tile<true, false, true><<<grid, kThreads, smem, ctx->stream>>>(psi, L, d, d_phase, high_bits);
+            *phase_done = true;
+        }
+        else if (h.lo == h.T && h.scaled) k_slice_rx_tile<true, true, false><<<grid, kThreads, smem, ctx->stream>>>(psi, L, d, nullptr, 0);
+        else if (h.lo == h.T) k_slice_rx_tile<true, false, false><<<grid, kThreads, smem, ctx->stream>>>(psi, L, d, nullptr, 0);
+        else if (h.scaled) k_slice_rx_tile<false, true, false><<<grid, kThreads, smem, ctx->stream>>>(psi, L, d, nullptr, 0);
+        else k_slice_rx_tile<false, false, false><<<grid, kThreads, smem, ctx->stream>>>(psi, L, d, nullptr, 0);
         ctx->launches++;
         DQ_CUDA(cudaGetLastError());
     }
+    return DQ_OK;
+}
+}  // namespace
+
+extern "C" {
+
+int dq_slice_rx_many(dq_context* ctx, void* psi_dev, int L, int count, const int32_t* bits, const double* thetas) {
+    return rx_many_impl(ctx, psi_dev, L, count, bits, thetas, nullptr, 0, nullptr);
+}
+
+int dq_slice_phase_rx_many(dq_context* ctx, void* psi_dev, int L, uint64_t high_bits, int n_total, int n_zz,
+                           const int32_t* pair_bits, const double* angles, int count, const int32_t* bits, const double* thetas) {
+    DQ_REQUIRE(ctx && psi_dev && angles, "NULL argument");
+    DQ_REQUIRE(L >= 1 && L <= 33 && n_total >= L && n_total <= 40, "dq_slice_phase_rx_many: L=%d n=%d", L, n_total);
+    DQ_REQUIRE((high_bits >> (n_total - L)) == 0, "dq_slice_phase_rx_many: high_bits do not fit %d global bits", n_total - L);
+    DQ_TRY(ctx->set_device());
+    // fusable when the rotations start with a contiguous 12-bit tile pass (some target below bit 12, L >= 12) and no walk
+    // bit (8..11) carries more than kGrayDeg pairs; otherwise the phase runs as its own pass first
+    bool low_target = false;
+    for (int i = 0; i < count; ++i) low_target = low_target || (bits && bits[i] >= 0 && bits[i] < kWalkLo + kWalkBits);
+    PhaseArgs h;
+    DQ_TRY(fill_args(h, n_total, n_zz, pair_bits, angles + 1, angles[0]));
+    bool fusable = low_target && L >= kTileBits && !getenv("DQ_SLICE_NO_PHASE_FUSION");
+    int n_in = 0;
+    for (int e = 0; e < h.n_zz; ++e) n_in += (h.a[e] < kTileBits && h.b[e] < kTileBits) ? 1 : 0;
+    fusable = fusable && n_in <= kMaxIn;
+    for (int k = 0; k < kTileBits && fusable; ++k) {      // every tile bit's pair list must fit the kernel's tables
+        int d = 0;
+        for (int e = 0; e < h.n_zz; ++e) d += (h.a[e] == k || h.b[e] == k) ? 1 : 0;
+        fusable = d <= kGrayDeg;
+    }
+    if (!fusable) {
+        DQ_TRY(dq_slice_phase(ctx, psi_dev, L, high_bits, n_total, n_zz, pair_bits, angles));
+        return rx_many_impl(ctx, psi_dev, L, count, bits, thetas, nullptr, 0, nullptr);
+    }
+    PhaseArgs* d;
+    DQ_TRY(upload_args(ctx, h, &d));
+    bool done = false;
+    DQ_TRY(rx_many_impl(ctx, psi_dev, L, count, bits, thetas, d, high_bits, &done));
+    DQ_REQUIRE(done, "dq_slice_phase_rx_many: internal error: the phase was not applied");
     return DQ_OK;
 }
 

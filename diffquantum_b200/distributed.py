@@ -57,6 +57,15 @@ class CudaSliceOps(object):
         thetas = np.ascontiguousarray(thetas, dtype=np.float64)
         _lib.check(self.lib.dq_slice_rx_many(self.ctx.handle, self._p(psi), L, len(bits), _lib.ptr(bits), _lib.ptr(thetas)))
 
+    def phase_rx_many(self, psi, L, high, n, pair_bits, angles, bits, thetas):
+        """Phase + the step's local rotations in one call: the phase rides on the first rotation pass (dq_slice_phase_rx_many)."""
+        pair_bits = np.ascontiguousarray(pair_bits, dtype=np.int32)
+        angles = np.ascontiguousarray(angles, dtype=np.float64)
+        bits = np.ascontiguousarray(bits, dtype=np.int32)
+        thetas = np.ascontiguousarray(thetas, dtype=np.float64)
+        _lib.check(self.lib.dq_slice_phase_rx_many(self.ctx.handle, self._p(psi), L, high, n, len(pair_bits), _lib.ptr(pair_bits),
+                                                   _lib.ptr(angles), len(bits), _lib.ptr(bits), _lib.ptr(thetas)))
+
     def energy(self, psi, L, high, n, pair_bits, m_zz, m_const):
         pair_bits = np.ascontiguousarray(pair_bits, dtype=np.int32)
         m_zz = np.ascontiguousarray(m_zz, dtype=np.float64)
@@ -110,6 +119,7 @@ class DistributedState(object):
         self.exchanges = 0
         self.exchanged_bytes = 0
         self.fused_rx = True               # False: one kernel per rotation (dq_slice_rx), kept for cross-checks
+        self.fused_phase = True            # False: the diagonal phase as its own pass (dq_slice_phase)
 
     # -- layout ------------------------------------------------------------------------------------
     def pair_bits(self):
@@ -154,9 +164,14 @@ class DistributedState(object):
         p = self.problem
         row = np.asarray(row, dtype=np.float64)
         x = row[1 + p.n_zz:]
-        self.ops.phase(self.psi, self.L, self.rank, self.n, self.pair_bits(), row[:1 + p.n_zz])
         was_global = self.global_qubits()
-        self._rotate([q for q in range(self.n) if self.pos[q] < self.L], x)
+        local = [q for q in range(self.n) if self.pos[q] < self.L]
+        if self.fused_rx and self.fused_phase and hasattr(self.ops, "phase_rx_many") and local:
+            self.ops.phase_rx_many(self.psi, self.L, self.rank, self.n, self.pair_bits(), row[:1 + p.n_zz],
+                                   [self.pos[q] for q in local], [x[q] for q in local])
+        else:
+            self.ops.phase(self.psi, self.L, self.rank, self.n, self.pair_bits(), row[:1 + p.n_zz])
+            self._rotate(local, x)
         if was_global:
             self.swap_global_local()
             self._rotate(was_global, x)

@@ -226,6 +226,20 @@ class IsingSimulator(object):
         rows = self.problem.trajectory_rows(coeff, T0, T1, self.per_step, self.basis)
         return self.evolve_rows(rows, psi0, **kw)
 
+    def trotter_cc(self, channels, duration, func_type, vv, T0, T, psi0=None, **kw):
+        """diffqc.trotter (diffqc.cc:173-205) for a Pauli-term Hamiltonian: the IQ-channel pulse model f_u of the native twin
+        (diffqc.cc:95-135: per control a sum over channels [_, omega, w, idx] of omega (2 expit(N) - 1) / N (cos(w t) A +
+        sin(w t) B), A/B = basis expansions of vv[0][idx] / vv[1][idx]) evaluated by the library's host routine on the
+        native step grid (n_steps from |T - T0|, diffqc.cc:182-184), one channel list per control term of the problem."""
+        p = self.problem
+        if len(channels) != len(p.terms):
+            raise ValueError("one channel list per control term is required (%d terms, %d lists)" % (len(p.terms), len(channels)))
+        n_steps, dt, ts = pulses.step_grid(T0, T, self.per_step, use_abs=True)
+        if n_steps == 0:
+            raise ValueError("per_step=%r gives no steps (the reference divides by zero here)" % (self.per_step,))
+        u = pulses.f_u_table_lib(channels, duration, func_type, vv, ts)
+        return self.evolve_rows(p.angle_rows(u, dt), psi0, **kw)
+
     # -- batched estimator --------------------------------------------------------------------------
     def sample_tables(self, coeff, s_list):
         """Host tables for a batch of sampled times: step counts and packed angle rows."""

@@ -243,6 +243,11 @@ int dq_slice_rx(dq_context* ctx, void* psi_dev, int L, int bit, double theta);
 /* exp(-i thetas[k] X) on `count` distinct local bits in as few passes over the slice as their positions allow (the
  * rotations of one product-formula step commute, diffqc.cc:155-164): up to 12 bits per read + write. */
 int dq_slice_rx_many(dq_context* ctx, void* psi_dev, int L, int count, const int32_t* bits, const double* thetas);
+/* dq_slice_phase followed by dq_slice_rx_many as ONE call: when the rotations start with a contiguous 12-bit tile pass the
+ * phase rides on that pass (applied to the tile in shared memory before the first rotation round), one pass over the slice
+ * less per product-formula step. */
+int dq_slice_phase_rx_many(dq_context* ctx, void* psi_dev, int L, uint64_t high_bits, int n_total, int n_zz,
+                           const int32_t* pair_bits, const double* angles, int count, const int32_t* bits, const double* thetas);
 /* this rank's part of <psi| m_const + sum_e m_zz[e] Z_a Z_b |psi> (sim_plain.py:205,215,281) */
 int dq_slice_energy(dq_context* ctx, const void* psi_dev, int L, uint64_t high_bits, int n_total, int n_zz,
                     const int32_t* pair_bits, const double* m_zz, double m_const, double* partial_out);

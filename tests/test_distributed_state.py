@@ -194,6 +194,41 @@ def test_fused_rotation_pass_equals_one_kernel_per_rotation(L, bits):
         ops.rx_many(a, L, [L], [0.1])
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("L,n,high", [(12, 12, 0), (16, 16, 0), (18, 20, 3), (21, 21, 0)])
+def test_phase_fused_into_the_first_rotation_pass(L, n, high):
+    """dq_slice_phase_rx_many (the step's diagonal phase applied inside the contiguous 12-bit rotation pass) against
+    dq_slice_phase followed by dq_slice_rx_many; high rank bits included, and a bit list without low targets (no fusion)."""
+    from oracle import restate as R
+    ops = distributed.CudaSliceOps(0)
+    rng = np.random.RandomState(100 + L)
+    edges = R.random_regular_edges(n, seed=L) if n % 2 == 0 else [(i, (i + 1) % n) for i in range(n)] + [(i, (i + 5) % n) for i in range(0, n, 3)]
+    pair_bits = np.array([[n - 1 - a, n - 1 - b] for a, b in edges], dtype=np.int32)
+    angles = rng.normal(size=1 + len(edges))
+    host = rng.normal(size=1 << L) + 1j * rng.normal(size=1 << L)
+    host /= np.linalg.norm(host)
+    for bits in (list(range(L)), [b for b in range(L) if b >= 12 or b % 3 == 0], [b for b in range(L) if b >= 12]):
+        if not bits:
+            continue
+        thetas = rng.uniform(-1.2, 1.2, size=len(bits))
+        a, b = ops.alloc(1 << L), ops.alloc(1 << L)
+        ops.from_host(a, host)
+        ops.from_host(b, host)
+        l0 = ops.ctx.launch_count
+        ops.phase_rx_many(a, L, high, n, pair_bits, angles, bits, thetas)
+        fused_launches = ops.ctx.launch_count - l0
+        l0 = ops.ctx.launch_count
+        ops.phase(b, L, high, n, pair_bits, angles)
+        ops.rx_many(b, L, bits, thetas)
+        split_launches = ops.ctx.launch_count - l0
+        ops.ctx.synchronize()
+        got, want = ops.to_host(a), ops.to_host(b)
+        assert np.abs(got - want).max() < 1e-13
+        assert abs(np.linalg.norm(got) - 1.0) < 1e-12
+        low_target = any(bit < 12 for bit in bits)
+        assert fused_launches == split_launches - (1 if low_target else 0)
+
+
 def _gpu_worker(rank, world, port, n):
     sys.path.insert(0, ROOT)
     import torch

@@ -331,3 +331,61 @@ def test_pair_expectations_with_the_automatic_layout_and_split_step():
             ket = R.evolve_split_structured(ref, R.coef_table_plain(coeff, ref["omegas"], ref["T"], ts), dt, R.apply_shift_gate(ref, ref["terms"][i], phi, sign))
             want = [float(np.sum(np.abs(ket) ** 2 * R.z_diag(n, a) * R.z_diag(n, b))) for a, b in prob.zz_pairs]
             assert np.abs(zz[i, k] - want).max() < 1e-10
+
+
+@pytest.mark.parametrize("n,step,func_type", [(4, "exact", 0), (6, "split", 1), (13, "split", 1)])
+def test_iq_channel_pulse_model_on_the_structured_path(n, step, func_type):
+    """IsingSimulator.trotter_cc: the native twin's pulse model f_u (diffqc.cc:95-135, library host routine pinned to the
+    compiled reference) driving Pauli-term evolution, forward and backward spans -- against the oracle's restatement of
+    diffqc.trotter (oracle/restate.py trotter_cc) on the dense twin (n <= 6) or its structured split step (n = 13)."""
+    edges = graph_for(n)
+    prob = dq.IsingProblem.maxcut(n, edges)
+    ref = R.maxcut_structured(n, edges)
+    rng = np.random.RandomState(40 + n)
+    n_param, n_basis = 5, 5
+    channels = [[[0.0, float(rng.uniform(0.5, 2.0)), float(rng.uniform(0, 2.5)), float(rng.randint(n_param))]
+                 for _ in range(1 + i % 2)] for i in range(len(prob.terms))]
+    vv = rng.normal(0, 1, [2, n_param, n_basis])
+    sim = dq.IsingSimulator(prob, per_step=4, step=step)
+    for (T0, T) in ((0.0, 1.3), (1.1, 0.35)):
+        psi, en = sim.trotter_cc(channels, 2.0, func_type, vv, T0, T)
+        ns, dt, ts = R.step_grid(T0, T, 4, use_abs=True)
+        if n <= 6:
+            H0, Hs, M = R.maxcut_dense(ref)
+            want = R.trotter_cc(H0, Hs, channels, 2.0, func_type, ref["psi0"], T0, T, 4, vv, mode=step)
+        else:
+            u = np.array([[R.f_u_cc(h, t, vv, channels, 2.0, func_type) for h in range(len(prob.terms))] for t in ts])
+            want = R.evolve_split_structured(ref, u, dt, ref["psi0"])
+        assert rel(psi[0], want) < TOL
+        assert abs(en[0] - R.energy_diag(ref["m_diag"], want)) < TOL * max(1.0, abs(en[0]))
+
+
+@pytest.mark.parametrize("n", [21, 22])
+def test_slice_pass_engine_for_batched_gradients_above_20_qubits(n):
+    """n > 20: dq_ising_grad / dq_ising_evolve run the fused slice passes (one Gray-code phase pass + rotation passes of up to
+    12 qubits per read/write, engine 2) instead of n + 1 per-term kernels -- against the per-term engine on the device and,
+    for a subset of controls, against the plain-C port of the reference step and estimator."""
+    from oracle import c_port as C
+    edges = graph_for(n)
+    prob = dq.IsingProblem.maxcut(n, edges)
+    coeff = np.random.RandomState(n).normal(0, 1, [len(prob.terms), 6])
+    sim = dq.IsingSimulator(prob, per_step=2)
+    assert sim.info("engine") == 2
+    s = 0.9
+    grads, energies = sim.grad_samples(coeff, [s], return_energies=True)
+    psi, en = sim.evolve(coeff, 0.0, 0.7)
+    assert abs(np.linalg.norm(psi[0]) - 1) < 1e-12
+    gen = dq.IsingSimulator(prob, per_step=2, engine=0)
+    assert gen.info("engine") == 0
+    psi0, en0 = gen.evolve(coeff, 0.0, 0.7)
+    assert rel(psi[0], psi0[0]) < TOL and abs(en[0] - en0[0]) < TOL * abs(en0[0])
+    if n == 21:
+        e_gen = gen.shifted_energies(coeff, [s])
+        assert rel(energies, e_gen) < TOL
+    if C.available():
+        C.use_host_cores()
+        ref = R.maxcut_structured(n, edges)
+        terms = [0, len(edges) - 1, len(edges), len(prob.terms) - 1]
+        g_ref, e_ref, _ = C.grad_mc(C.CProblem(ref), coeff, s, 2, terms=terms, return_energies=True)
+        assert rel(energies[0][terms], e_ref[terms]) < TOL
+        assert rel(grads[0][terms], g_ref[terms]) < TOL
