@@ -85,6 +85,9 @@ def parse_args():
     ap.add_argument("--cpu-terms", type=int, default=6,
                     help="controls whose +/- trajectories the bounded CPU sample runs (of n_Hs)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
+                    help="configs[4]: the per-step exchange as stores of the last local pass into peer memory (default) or as an "
+                         "NCCL all_to_all_single")
     ap.add_argument("--ket-group", type=int, default=0)
     ap.add_argument("--item-tiles-log2", type=int, default=-1, help="fused v2: tiles per work item = 2^k (default: library default)")
     ap.add_argument("--engine", type=int, default=1, help="1 = the fused pass engine (the only product engine at n=20)")
@@ -598,7 +601,8 @@ def run_distributed_state(a):
         edges = sorted(tuple(sorted(e)) for e in gr.edges()) + [(0, n - 1), (1, n - 1), (2, n - 1)]
     prob = dq.IsingProblem.maxcut(n, edges)
     coeff = np.random.default_rng(0).normal(0, 1, [len(prob.terms), 6])
-    st = distributed.DistributedState(prob, device=R_.local, per_step=a.per_step)
+    st = distributed.DistributedState(prob, device=R_.local, per_step=a.per_step,
+                                      peer_exchange=(False if a.exchange == "nccl" else None))
     st.fill_uniform()
     rows = prob.trajectory_rows(coeff, 0.0, prob.T, a.per_step)
     sampler = ClockSampler(R_.local)
@@ -639,7 +643,10 @@ def run_distributed_state(a):
             "config": {"workload": "configs[4]: one MaxCut state of n=%d qubits (random 3-regular graph, networkx seed 0), %.1f GiB of "
                                    "complex128 per GPU, product-formula steps of the pulse trajectory (per_step=%d)" % (
                                        n, slice_bytes / 2 ** 30, a.per_step),
-                       "parallelism": "state split on its %d high-order qubits over %d GPUs; one all-to-all per step" % (g_bits, R_.world),
+                       "parallelism": "state split on its %d high-order qubits over %d GPUs; one exchange of (W-1)/W of the slice per "
+                                      "step: %s" % (g_bits, R_.world, "stores of the last local rotation pass into the peers' "
+                                                    "buffers (peer memory over NVLink) + one barrier" if st.peer_exchange else
+                                                    "NCCL all_to_all_single between two stream synchronisations"),
                        "l2": "slice (%.1f GiB) >> L2" % (slice_bytes / 2 ** 30)},
             "e2e": {"value": a.steps / t_tot, "unit": unit, "h2d_bytes_per_step": int(rows.shape[1] * 8), "d2h_bytes_per_step": 8,
                     "note": "the state lives on the devices by definition (64 GiB at n=32); per step the host sends one angle row; "
@@ -655,7 +662,9 @@ def run_distributed_state(a):
                          "exchange_GB_per_step_per_gpu": exch_bytes / 1e9,
                          "exchange_GBs_per_gpu": (exch_bytes / (exch_ms * 1e-3) / 1e9) if exch_ms else None,
                          "nvlink_peak_GBs": 900.0,
-                         "limiter": ("the all-to-all (%.1f GB per GPU per step over NVLink)" % (exch_bytes / 1e9)) if R_.world > 1 else
+                         "exchange_path": "peer-memory stores fused into the last local pass" if st.peer_exchange else
+                                          ("nccl all_to_all_single" if R_.world > 1 else "none"),
+                         "limiter": ("the exchange (%.1f GB per GPU per step over NVLink)" % (exch_bytes / 1e9)) if R_.world > 1 else
                                     "HBM passes (no exchange on one GPU)"},
             "parity": parity, "norm2_after": norm2, "clocks": sampler.window(*window),
             "cpu_baseline": {"value": None, "unit": unit, "cores": 0, "kind": "port",

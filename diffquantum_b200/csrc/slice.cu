@@ -6,6 +6,7 @@
 // bits [L-g, L) with the rank bits (done by the host through NCCL, diffquantum_b200/distributed.py).
 // Step semantics: the per-term product of diffqc.cc:155-164.
 #include <algorithm>
+#include <cuda.h>
 #include <stdlib.h>
 #include <string.h>
 #include <utility>
@@ -15,6 +16,7 @@ namespace {
 
 constexpr int kThreads = 256;
 constexpr int kMaxPairs = 256;
+constexpr int kMaxPeers = 16;
 
 struct PhaseArgs {
     int n_zz;
@@ -122,6 +124,11 @@ struct TileArgs {
     unsigned long long mask;        // OR of 1 << pos[i]
     double post;                    // scaled form: product of the cosines, applied once when the tile is stored
     int scaled;
+    // exchange fused into the stores of this pass (the last local pass before the global<->local qubit swap): element x of
+    // the slice goes to rank j = x >> (L - g) at peer[j][(rank << (L - g)) | (x & (2^(L-g) - 1))] -- the all-to-all of
+    // diffquantum_b200/distributed.py written straight into the peers' receive buffers over NVLink.  scatter_g = 0: in place.
+    int scatter_g, scatter_rank;
+    double2* peer[kMaxPeers];
 };
 
 // exp(-i theta X) on a pair.  SCALED: a' = a - i tan(theta) b (one FMA per real component, the cosines are applied once per
@@ -389,7 +396,13 @@ __global__ void __launch_bounds__(kThreads, 3) k_slice_rx_tile(double2* __restri
         {
             double2 v = tile[tslot(e)];
             if (SCALED) v = make_double2(v.x * A.post, v.y * A.post);
-            psi[base + (CONTIG ? (unsigned long long)e : ((e & lowmask) | hi_off[e >> lo]))] = v;
+            const unsigned long long x = base + (CONTIG ? (unsigned long long)e : ((e & lowmask) | hi_off[e >> lo]));
+            if (A.scatter_g) {
+                const int sh = L - A.scatter_g;
+                A.peer[x >> sh][((unsigned long long)A.scatter_rank << sh) | (x & ((1ull << sh) - 1ull))] = v;
+            } else {
+                psi[x] = v;
+            }
         }
         __syncthreads();
     }
@@ -594,8 +607,10 @@ int dq_slice_rx(dq_context* ctx, void* psi_dev, int L, int bit, double theta) {
 namespace {
 // All rotations of a step; d_phase != NULL: the step's diagonal phase is applied by the first pass if that pass is a
 // contiguous 12-bit tile pass (*phase_done says whether it was).
+struct Scatter { int g, rank; void* const* peer; };
+
 int rx_many_impl(dq_context* ctx, void* psi_dev, int L, int count, const int32_t* bits, const double* thetas,
-                 const PhaseArgs* d_phase, unsigned long long high_bits, bool* phase_done) {
+                 const PhaseArgs* d_phase, unsigned long long high_bits, bool* phase_done, const Scatter* scatter = nullptr) {
     if (phase_done) *phase_done = false;
     DQ_REQUIRE(ctx && psi_dev && (count == 0 || (bits && thetas)), "NULL argument");
     DQ_REQUIRE(L >= 1 && L <= 33 && count >= 0 && count <= L, "dq_slice_rx_many: L=%d count=%d", L, count);
@@ -669,6 +684,11 @@ int rx_many_impl(dq_context* ctx, void* psi_dev, int L, int count, const int32_t
             h.T = T;
         }
         for (int i = 0; i < h.T; ++i) h.mask |= 1ull << h.pos[i];
+        if (scatter && next >= tg.size()) {                 // the last pass of the step carries the exchange
+            h.scatter_g = scatter->g;
+            h.scatter_rank = scatter->rank;
+            for (int j = 0; j < (1 << scatter->g); ++j) h.peer[j] = (double2*)scatter->peer[j];
+        }
         // scaled form unless a rotation angle sits close to pi/2 (|tan| large: the cosine product would lose digits)
         h.scaled = 1;
         h.post = 1.0;
@@ -713,8 +733,63 @@ int dq_slice_rx_many(dq_context* ctx, void* psi_dev, int L, int count, const int
     return rx_many_impl(ctx, psi_dev, L, count, bits, thetas, nullptr, 0, nullptr);
 }
 
-int dq_slice_phase_rx_many(dq_context* ctx, void* psi_dev, int L, uint64_t high_bits, int n_total, int n_zz,
-                           const int32_t* pair_bits, const double* angles, int count, const int32_t* bits, const double* thetas) {
+int dq_slice_rx_many_scatter(dq_context* ctx, void* psi_dev, int L, int count, const int32_t* bits, const double* thetas,
+                             int g, int rank, void* const* peer_recv) {
+    DQ_REQUIRE(ctx && psi_dev && peer_recv, "NULL argument");
+    DQ_REQUIRE(g >= 1 && (1 << g) <= kMaxPeers && g <= L && rank >= 0 && rank < (1 << g), "dq_slice_rx_many_scatter: g=%d rank=%d L=%d", g, rank, L);
+    DQ_REQUIRE(count >= 1, "dq_slice_rx_many_scatter: needs at least one rotation to carry the exchange");
+    for (int j = 0; j < (1 << g); ++j) DQ_REQUIRE(peer_recv[j] != nullptr, "dq_slice_rx_many_scatter: NULL receive buffer of rank %d", j);
+    Scatter sc{g, rank, peer_recv};
+    return rx_many_impl(ctx, psi_dev, L, count, bits, thetas, nullptr, 0, nullptr, &sc);
+}
+
+int dq_ipc_export(dq_context* ctx, void* dev_ptr, void* handle64_out, uint64_t* offset_out) {
+    DQ_REQUIRE(ctx && dev_ptr && handle64_out && offset_out, "NULL argument");
+    DQ_TRY(ctx->set_device());
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    CUdeviceptr base = 0;
+    size_t size = 0;
+    // the handle names the whole allocation the pointer lives in (a caching allocator may hand out an interior pointer)
+    cudaPointerAttributes attr;
+    DQ_CUDA(cudaPointerGetAttributes(&attr, dev_ptr));
+    DQ_REQUIRE(attr.type == cudaMemoryTypeDevice, "dq_ipc_export: not a device pointer");
+    {
+        typedef CUresult (*RangeFn)(CUdeviceptr*, size_t*, CUdeviceptr);
+        void* f = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        DQ_CUDA(cudaGetDriverEntryPoint("cuMemGetAddressRange", &f, cudaEnableDefault, &q));
+        DQ_REQUIRE(q == cudaDriverEntryPointSuccess && f, "dq_ipc_export: cuMemGetAddressRange is not available");
+        if (reinterpret_cast<RangeFn>(f)(&base, &size, (CUdeviceptr)dev_ptr) != CUDA_SUCCESS) {
+            dq::set_error("dq_ipc_export: cuMemGetAddressRange failed");
+            return DQ_ERR_CUDA;
+        }
+    }
+    DQ_CUDA(cudaIpcGetMemHandle((cudaIpcMemHandle_t*)handle64_out, (void*)base));
+    *offset_out = (uint64_t)((CUdeviceptr)dev_ptr - base);
+    return DQ_OK;
+}
+
+int dq_ipc_open(dq_context* ctx, const void* handle64, uint64_t offset, void** ptr_out) {
+    DQ_REQUIRE(ctx && handle64 && ptr_out, "NULL argument");
+    DQ_TRY(ctx->set_device());
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, sizeof(h));
+    void* base = nullptr;
+    DQ_CUDA(cudaIpcOpenMemHandle(&base, h, cudaIpcMemLazyEnablePeerAccess));
+    *ptr_out = (char*)base + offset;
+    return DQ_OK;
+}
+
+int dq_ipc_close(dq_context* ctx, void* ptr, uint64_t offset) {
+    DQ_REQUIRE(ctx && ptr, "NULL argument");
+    DQ_TRY(ctx->set_device());
+    DQ_CUDA(cudaIpcCloseMemHandle((char*)ptr - offset));
+    return DQ_OK;
+}
+
+static int phase_rx_many(dq_context* ctx, void* psi_dev, int L, uint64_t high_bits, int n_total, int n_zz,
+                         const int32_t* pair_bits, const double* angles, int count, const int32_t* bits, const double* thetas,
+                         const Scatter* sc) {
     DQ_REQUIRE(ctx && psi_dev && angles, "NULL argument");
     DQ_REQUIRE(L >= 1 && L <= 33 && n_total >= L && n_total <= 40, "dq_slice_phase_rx_many: L=%d n=%d", L, n_total);
     DQ_REQUIRE((high_bits >> (n_total - L)) == 0, "dq_slice_phase_rx_many: high_bits do not fit %d global bits", n_total - L);
@@ -736,14 +811,30 @@ int dq_slice_phase_rx_many(dq_context* ctx, void* psi_dev, int L, uint64_t high_
     }
     if (!fusable) {
         DQ_TRY(dq_slice_phase(ctx, psi_dev, L, high_bits, n_total, n_zz, pair_bits, angles));
-        return rx_many_impl(ctx, psi_dev, L, count, bits, thetas, nullptr, 0, nullptr);
+        return rx_many_impl(ctx, psi_dev, L, count, bits, thetas, nullptr, 0, nullptr, sc);
     }
     PhaseArgs* d;
     DQ_TRY(upload_args(ctx, h, &d));
     bool done = false;
-    DQ_TRY(rx_many_impl(ctx, psi_dev, L, count, bits, thetas, d, high_bits, &done));
+    DQ_TRY(rx_many_impl(ctx, psi_dev, L, count, bits, thetas, d, high_bits, &done, sc));
     DQ_REQUIRE(done, "dq_slice_phase_rx_many: internal error: the phase was not applied");
     return DQ_OK;
+}
+
+int dq_slice_phase_rx_many(dq_context* ctx, void* psi_dev, int L, uint64_t high_bits, int n_total, int n_zz,
+                           const int32_t* pair_bits, const double* angles, int count, const int32_t* bits, const double* thetas) {
+    return phase_rx_many(ctx, psi_dev, L, high_bits, n_total, n_zz, pair_bits, angles, count, bits, thetas, nullptr);
+}
+
+int dq_slice_phase_rx_many_scatter(dq_context* ctx, void* psi_dev, int L, uint64_t high_bits, int n_total, int n_zz,
+                                   const int32_t* pair_bits, const double* angles, int count, const int32_t* bits,
+                                   const double* thetas, int g, int rank, void* const* peer_recv) {
+    DQ_REQUIRE(peer_recv, "NULL argument");
+    DQ_REQUIRE(g >= 1 && (1 << g) <= kMaxPeers && g <= L && rank >= 0 && rank < (1 << g), "dq_slice_phase_rx_many_scatter: g=%d rank=%d L=%d", g, rank, L);
+    DQ_REQUIRE(count >= 1, "dq_slice_phase_rx_many_scatter: needs at least one rotation to carry the exchange");
+    for (int j = 0; j < (1 << g); ++j) DQ_REQUIRE(peer_recv[j] != nullptr, "dq_slice_phase_rx_many_scatter: NULL receive buffer of rank %d", j);
+    Scatter sc{g, rank, peer_recv};
+    return phase_rx_many(ctx, psi_dev, L, high_bits, n_total, n_zz, pair_bits, angles, count, bits, thetas, &sc);
 }
 
 int dq_slice_energy(dq_context* ctx, const void* psi_dev, int L, uint64_t high_bits, int n_total, int n_zz,

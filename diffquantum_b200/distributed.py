@@ -66,6 +66,69 @@ class CudaSliceOps(object):
         _lib.check(self.lib.dq_slice_phase_rx_many(self.ctx.handle, self._p(psi), L, high, n, len(pair_bits), _lib.ptr(pair_bits),
                                                    _lib.ptr(angles), len(bits), _lib.ptr(bits), _lib.ptr(thetas)))
 
+    # -- exchange fused into the last local pass (peer memory) ------------------------------------------------
+    def enable_peer_exchange(self, buffers, rank, world):
+        """Map every rank's two slice buffers into this process (CUDA IPC; peer access over NVLink when the ranks own
+        different GPUs) so that the last local rotation pass of a step can store straight into the peers' receive buffers.
+        buffers: this rank's two tensors (they swap roles every step).  Returns False when the mapping is not possible
+        (the all-to-all path stays in use)."""
+        import torch.distributed as dist
+        mine = []
+        try:
+            for t in buffers:
+                handle = (ctypes.c_ubyte * 64)()
+                off = ctypes.c_uint64()
+                _lib.check(self.lib.dq_ipc_export(self.ctx.handle, self._p(t), handle, ctypes.byref(off)))
+                mine.append((bytes(handle), int(off.value)))
+        except Exception:
+            mine = None
+        everyone = [None] * world
+        dist.all_gather_object(everyone, mine)
+        if any(e is None for e in everyone):
+            return False
+        self._peer_tables, self._peer_opened = [], []
+        try:
+            for k in range(len(buffers)):
+                table = (ctypes.c_void_p * world)()
+                for j in range(world):
+                    if j == rank:
+                        table[j] = buffers[k].data_ptr()
+                    else:
+                        ptr = ctypes.c_void_p()
+                        h, off = everyone[j][k]
+                        _lib.check(self.lib.dq_ipc_open(self.ctx.handle, ctypes.c_char_p(h), off, ctypes.byref(ptr)))
+                        self._peer_opened.append((ptr.value, off))
+                        table[j] = ptr.value
+                self._peer_tables.append(table)
+            ok = True
+        except Exception:
+            ok = False
+        flags = [None] * world
+        dist.all_gather_object(flags, ok)
+        self._peer_ptrs = {buffers[k].data_ptr(): self._peer_tables[k] for k in range(len(buffers))} if all(flags) else None
+        self._rank, self._g = rank, world.bit_length() - 1
+        return self._peer_ptrs is not None
+
+    def phase_rx_many_scatter(self, psi, recv, L, high, n, pair_bits, angles, bits, thetas):
+        """Phase, the local rotations and the exchange of a step: the last pass writes into every rank's `recv` buffer."""
+        pair_bits = np.ascontiguousarray(pair_bits, dtype=np.int32)
+        angles = np.ascontiguousarray(angles, dtype=np.float64)
+        bits = np.ascontiguousarray(bits, dtype=np.int32)
+        thetas = np.ascontiguousarray(thetas, dtype=np.float64)
+        table = self._peer_ptrs[recv.data_ptr()]
+        _lib.check(self.lib.dq_slice_phase_rx_many_scatter(
+            self.ctx.handle, self._p(psi), L, high, n, len(pair_bits), _lib.ptr(pair_bits), _lib.ptr(angles), len(bits),
+            _lib.ptr(bits), _lib.ptr(thetas), self._g, self._rank, table))
+
+    def barrier(self):
+        """Every rank's stores into every receive buffer are complete (the pass has finished on every device)."""
+        import torch.distributed as dist
+        self.ctx.synchronize()
+        if dist.get_backend() == "nccl":
+            dist.barrier(device_ids=[self.device.index])
+        else:
+            dist.barrier()
+
     def energy(self, psi, L, high, n, pair_bits, m_zz, m_const):
         pair_bits = np.ascontiguousarray(pair_bits, dtype=np.int32)
         m_zz = np.ascontiguousarray(m_zz, dtype=np.float64)
@@ -99,7 +162,7 @@ class CudaSliceOps(object):
 class DistributedState(object):
     """The slice of one n-qubit state owned by this rank, plus the qubit -> physical-bit map."""
 
-    def __init__(self, problem, device=0, per_step=10, basis="BSpline", ops=None):
+    def __init__(self, problem, device=0, per_step=10, basis="BSpline", ops=None, peer_exchange=None):
         self.problem = problem
         self.per_step = per_step
         self.basis = basis
@@ -120,6 +183,9 @@ class DistributedState(object):
         self.exchanged_bytes = 0
         self.fused_rx = True               # False: one kernel per rotation (dq_slice_rx), kept for cross-checks
         self.fused_phase = True            # False: the diagonal phase as its own pass (dq_slice_phase)
+        # exchange fused into the stores of the last local pass (peer memory over NVLink) instead of an NCCL all-to-all
+        self.peer_exchange = bool(g) and hasattr(self.ops, "enable_peer_exchange") and peer_exchange is not False and \
+            self.ops.enable_peer_exchange([self.psi, self.recv], self.rank, self.world)
 
     # -- layout ------------------------------------------------------------------------------------
     def pair_bits(self):
@@ -133,6 +199,10 @@ class DistributedState(object):
         if self.g == 0:
             return
         self.ops.all_to_all(self.recv, self.psi)
+        self._swapped()
+
+    def _swapped(self):
+        """Bookkeeping after the amplitudes have moved: buffers change roles, index bits [L-g, L) <-> rank bits."""
         self.psi, self.recv = self.recv, self.psi
         L, g = self.L, self.g
         for q in range(self.n):
@@ -166,6 +236,14 @@ class DistributedState(object):
         x = row[1 + p.n_zz:]
         was_global = self.global_qubits()
         local = [q for q in range(self.n) if self.pos[q] < self.L]
+        if self.peer_exchange and was_global and local:
+            # one call: phase + every local rotation, the last pass storing into the peers' receive buffers; then a barrier
+            self.ops.phase_rx_many_scatter(self.psi, self.recv, self.L, self.rank, self.n, self.pair_bits(), row[:1 + p.n_zz],
+                                           [self.pos[q] for q in local], [x[q] for q in local])
+            self.ops.barrier()
+            self._swapped()
+            self._rotate(was_global, x)
+            return
         if self.fused_rx and self.fused_phase and hasattr(self.ops, "phase_rx_many") and local:
             self.ops.phase_rx_many(self.psi, self.L, self.rank, self.n, self.pair_bits(), row[:1 + p.n_zz],
                                    [self.pos[q] for q in local], [x[q] for q in local])

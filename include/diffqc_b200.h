@@ -248,6 +248,22 @@ int dq_slice_rx_many(dq_context* ctx, void* psi_dev, int L, int count, const int
  * less per product-formula step. */
 int dq_slice_phase_rx_many(dq_context* ctx, void* psi_dev, int L, uint64_t high_bits, int n_total, int n_zz,
                            const int32_t* pair_bits, const double* angles, int count, const int32_t* bits, const double* thetas);
+/* dq_slice_rx_many whose LAST pass also performs the global<->local qubit exchange: instead of writing the slice back in place
+ * it stores element x at peer_recv[x >> (L-g)][(rank << (L-g)) | (x & (2^(L-g) - 1))] -- exactly where an all_to_all_single of
+ * the 2^g contiguous chunks would put it -- through peer memory (NVLink P2P, or CUDA IPC mappings of the peers' receive
+ * buffers: dq_ipc_export / dq_ipc_open).  peer_recv[rank] is this rank's own receive buffer.  The caller synchronises the
+ * ranks (a barrier after the pass) before anybody reads its receive buffer. */
+int dq_slice_rx_many_scatter(dq_context* ctx, void* psi_dev, int L, int count, const int32_t* bits, const double* thetas,
+                             int g, int rank, void* const* peer_recv);
+/* The whole local part of a step -- phase, every local rotation, exchange -- in one call (dq_slice_phase_rx_many + scatter). */
+int dq_slice_phase_rx_many_scatter(dq_context* ctx, void* psi_dev, int L, uint64_t high_bits, int n_total, int n_zz,
+                                   const int32_t* pair_bits, const double* angles, int count, const int32_t* bits,
+                                   const double* thetas, int g, int rank, void* const* peer_recv);
+/* CUDA IPC plumbing for the above: a 64-byte handle + byte offset for a device pointer (the handle names the allocation the
+ * pointer lives in), and the mapping of such a handle in another process (same or peer device). */
+int dq_ipc_export(dq_context* ctx, void* dev_ptr, void* handle64_out, uint64_t* offset_out);
+int dq_ipc_open(dq_context* ctx, const void* handle64, uint64_t offset, void** ptr_out);
+int dq_ipc_close(dq_context* ctx, void* ptr, uint64_t offset);
 /* this rank's part of <psi| m_const + sum_e m_zz[e] Z_a Z_b |psi> (sim_plain.py:205,215,281) */
 int dq_slice_energy(dq_context* ctx, const void* psi_dev, int L, uint64_t high_bits, int n_total, int n_zz,
                     const int32_t* pair_bits, const double* m_zz, double m_const, double* partial_out);

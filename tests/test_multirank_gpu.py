@@ -4,7 +4,8 @@ When the box has >= W GPUs every rank takes its own device and the exchange is N
 diffquantum_b200/distributed.py: CudaSliceOps).  On a box with fewer GPUs the ranks SHARE devices: the CUDA slice /
 gradient kernels and the layout bookkeeping are exactly the same, only the all-to-all and the all-reduce are staged
 through the host over gloo (NCCL refuses two ranks on one device).  Either way:
-  (i)  DistributedState (one state split on its high qubits, one all-to-all per step) at n = 16, 18 against the oracle
+  (i)  DistributedState (one state split on its high qubits, one exchange per step: all-to-all, or fused into the last local
+       pass's stores through peer memory) at n = 16, 18 against the oracle
        (oracle/restate.py evolve_split_structured = diffqc.cc:155-164), amplitudes and energy to 1e-10;
   (ii) ShardedEstimator.per_sample_gradients with the real IsingSimulator: the W-rank result is BIT-equal to the
        same samples computed by one rank alone.
@@ -63,7 +64,7 @@ def _init(rank, world, port):
     return device, nccl
 
 
-def _state_worker(rank, world, port, n, out):
+def _state_worker(rank, world, port, n, peer, out):
     device, nccl = _init(rank, world, port)
     import torch.distributed as dist
     try:
@@ -75,7 +76,8 @@ def _state_worker(rank, world, port, n, out):
         ref = R.maxcut_structured(n, edges)
         coeff = np.random.RandomState(n).normal(0, 1, [len(prob.terms), 6])
         ops = None if nccl else _host_exchange_ops(device)
-        st = distributed.DistributedState(prob, device=device, per_step=2, ops=ops)
+        st = distributed.DistributedState(prob, device=device, per_step=2, ops=ops, peer_exchange=peer)
+        assert st.peer_exchange == bool(peer)                      # CUDA IPC mappings of every rank's buffers, or none
         st.fill_uniform()
         st.evolve(coeff, 0.2, 1.7)
         ns, dt, ts = R.step_grid(0.2, 1.7, 2)
@@ -138,9 +140,12 @@ def _spawn(target, world, *args):
     return got
 
 
+@pytest.mark.parametrize("peer", [False, True])
 @pytest.mark.parametrize("world,n", [(2, 16), (4, 18), (8, 18)])
-def test_distributed_state_cuda_vs_oracle(world, n):
-    _spawn(_state_worker, world, n)
+def test_distributed_state_cuda_vs_oracle(world, n, peer):
+    """peer=True: the exchange is fused into the stores of the last local rotation pass (peer memory through CUDA IPC, NVLink
+    when every rank has its own GPU) and a barrier; peer=False: NCCL (or host-staged) all-to-all."""
+    _spawn(_state_worker, world, n, peer)
 
 
 @pytest.mark.parametrize("world", [2, 4, 8])
