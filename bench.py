@@ -530,10 +530,13 @@ def run_dense_config(a):
                     "ms_per_step": 1e3 * t_e2e / a.steps,
                     "note": "public API with host buffers: host pulse tables + H2D + kernels + D2H + gradient assembly"},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "fp64", "kernel": "k_small (resident warp-per-trajectory engine)" if sim.stat("strategy") == 3 else "k_zgemm",
+            "roofline": {"bound": "fp64_tensor",
+                         "kernel": ("k_small_mma (resident engine: the shifted kets of a sample through the Horner recurrence on the FP64 "
+                                    "tensor cores, DMMA m8n8k4) + k_small (prefix kets, DFMA)") if sim.stat("strategy") == 3 else "k_zgemm (DMMA)",
                          "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": (ach / peak) if ach else None,
                          "peak_source": peak_src, "traffic": None,
-                         "flops_note": "degree x 2^squarings complex 16x16 mat-vecs per ket-step, 8 real flops per complex MAC"},
+                         "flops_note": "degree x 2^squarings complex 16x16 mat-vecs per ket-step, 8 real flops per complex MAC; peak = the "
+                                       "measured FP64 FMA rate of this device (dq_microbench), the DMMA pipe has the same nominal rate"},
             "parity": parity, "clocks": sampler.window(*window)}
     if a.config == 0:
         line["value_note"] = ("device time of the 202-epoch loop (CUDA events around the 1212 launches dq_dense_train enqueues); e2e = wall "
@@ -735,7 +738,7 @@ def run_b200_arm(a):
         sim.set_option("item_tiles_log2", a.item_tiles_log2)
     if sim.info("engine") != a.engine:
         raise RuntimeError("fused engine %d not available for n=%d" % (a.engine, a.n))
-    kernel_name = "k_fused_passes"
+    kernel_name = "k_fused_ws (warp-specialised loop-form pass kernel: every |x angle| <= 1; k_fused_passes otherwise)"
     n_H = len(prob.terms)
     stream = torch.cuda.ExternalStream(sim.ctx.stream, device=dev)
     flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
@@ -857,7 +860,9 @@ def run_b200_arm(a):
                 "avg_launch_ms": kern_ms / kern_launches if kern_launches else None,
                 "launches_timed": kern_launches, "kernel_share_of_step": kern_ms / sum(dev_ms) if dev_ms else None,
                 "note": "kets of a launch group stay in the 126 MB L2 between passes by design, so algorithmic GB/s can "
-                        "exceed DRAM GB/s; `traffic` is the ncu DRAM figure"}
+                        "exceed DRAM GB/s; `traffic` is the ncu DRAM figure.  The kernel is bound inside the SM (FP64 pipe 46 %, "
+                        "shared-memory wavefronts 53 %, their phases do not overlap: profiles/r02_o_fused_ws_ncu_summary.txt), not by HBM: "
+                        "`frac` is reported against the HBM peak because that is the contract's denominator"}
 
     line = {
         "metric": metric_of(a)[0], "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
