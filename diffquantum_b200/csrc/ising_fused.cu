@@ -65,6 +65,9 @@ constexpr int kMaxGroup = 128;             // kets per launch (their descriptors
 #ifndef DQ_CTAS_PER_SM
 #define DQ_CTAS_PER_SM 1
 #endif
+#ifndef DQ_WS_PIPE
+#define DQ_WS_PIPE 0           // experiment (negative: 79.3 vs 84.4 samples/s at n = 20): exchange stores interleaved with the last butterfly stage of the producing run -- issue is in order, so a store that finds the LSU queue full holds back the DFMAs behind it, and the hot code grows by 560 instructions
+#endif
 #ifndef DQ_WS_DIRECT_STORE
 #define DQ_WS_DIRECT_STORE 0   // experiment (negative: 81.1 vs 84.4 samples/s at n = 20; with a fence per consumer thread 76.7): finished tiles go from the registers straight to global memory instead of shared memory + bulk store -- the 16-byte global stores take the same LSU wavefronts as the shared-memory stores they replace, and the asynchronous bulk store is lost
 #endif
@@ -1157,6 +1160,158 @@ __device__ __forceinline__ void ws_tile(const LaunchArgs& A, WsShared& ws, const
     }
 
     c128 v[kRegs];
+#if DQ_WS_PIPE
+    // Software-pipelined form of the round loop.  Each round is  [head: amplitudes into registers, or the phase] [butterfly
+    // stages 0..3, one shared copy] [tail: stage 4, its stores issued pair by pair as the results appear].  The stores of an
+    // exchange ride on the last butterfly stage of the run that produced the data instead of following it: the LSU drains them
+    // while the FP64 pipe is still busy (with two consumer warps per scheduler nothing else would cover them).
+#define DQ_LIFT4_ST(ADDR)                                                                         \
+    _Pragma("unroll") for (int j = 0; j < 16; ++j) {                                              \
+        const int k = j | 16;                                                                     \
+        v[j].x = fma(rc4.x, v[k].y, v[j].x);                                                      \
+        v[j].y = fma(-rc4.x, v[k].x, v[j].y);                                                     \
+        v[k].x = fma(rc4.y, v[j].y, v[k].x);                                                      \
+        v[k].y = fma(-rc4.y, v[j].x, v[k].y);                                                     \
+        tile[ADDR(j)] = v[j];                                                                     \
+        tile[ADDR(k)] = v[k];                                                                     \
+    }
+#define DQ_A_K0(j) slot(sK, G0::regK(j))
+#define DQ_A_K1(j) slot(sK, G1::regK(j))
+#define DQ_A_J0(j) slot(sJ, G0::regJ(j))
+#define DQ_A_J1(j) slot(sJ, G1::regJ(j))
+#define DQ_A_LAND1(j) ((((j) & 1) ? b1 : b0) + G1::regK(j))
+    const int flags_all = P.flags;
+#pragma unroll 1
+    for (int r = 0; r < 4; ++r) {
+        asm volatile("" : "+r"(tid));
+        const int iK = type == 0 ? G0::baseK(tid) : G1::baseK(tid);
+        const int iJ = type == 0 ? G0::baseJ(tid) : G1::baseJ(tid);
+        const int sK = swz(iK), sJ = swz(iJ);
+        const int b0 = A.h_sw64 ? (iK ^ ((iK >> 3) & 3)) : sK;       // H landing layout: 64-byte swizzle at n = 20
+        const int b1 = A.h_sw64 ? b0 : (b0 ^ 4);
+        // ---- head ------------------------------------------------------------------------------------------------
+        if (r == 0) {
+            if (type == 0) {
+                DQ_FOR_REGS(v[j] = tile[DQ_A_K0(j)])
+            } else {
+                DQ_FOR_REGS(v[j] = tile[DQ_A_LAND1(j)])
+            }
+        } else if (r == 1) {
+            if (type == 0) {
+                DQ_FOR_REGS(v[j] = tile[DQ_A_J0(j)])
+            } else {
+                DQ_FOR_REGS(v[j] = tile[DQ_A_J1(j)])
+            }
+        } else if (r == 2) {
+            // ---- phase of the new step (the J1 rotations are done) ------------------------------------------
+            const int t_id = S.t_id;
+            const size_t tbase = ((size_t)(t_id & ((1 << T.tid_lo_bits) - 1)) << T.a) | ((size_t)(t_id >> T.tid_lo_bits) << T.high_end);
+            const size_t xJ = tbase + ((size_t)(iJ & T.lowmask) | ((size_t)(iJ >> T.a) << T.start));
+            const int kb = type == 0 ? G0::kbits(iJ) : G1::kbits(iJ);
+            c128 phi = cmul(S.tc[(iJ >> (type == 0 ? G0::spare_shift : G1::spare_shift)) & 3], P.tkk[kb]);
+#pragma unroll
+            for (int m = 0; m < 5; ++m) {
+                if (T.xk_msk[m][0]) {            // launch-uniform
+                    c128 w = P.xk[m][gather3(xJ, T.xk_pos[m], T.xk_msk[m])];
+                    if ((kb >> m) & 1) w.y = -w.y;
+                    phi = cmul(phi, w);
+                }
+            }
+            c128 F[5];
+#pragma unroll
+            for (int k = 0; k < 5; ++k) F[k] = P.fj[k][gather3(xJ, T.fj_pos[k], T.fj_msk[k])];
+            if (S.p == 0) {
+                const KetDesc* __restrict__ kd = skets + S.g;
+                if (kd->shift_kind == 0) {       // ZZ shift gate exp(i sigma alpha z0 z1); never both operands in J
+                    const int tb0 = tile_bit_of(kd->sb0), tb1 = tile_bit_of(kd->sb1);
+                    const double sigma = kd->sigma;
+                    const int j0b = type == 0 ? G0::jslot(tb0) : G1::jslot(tb0);
+                    const int j1b = type == 0 ? G0::jslot(tb1) : G1::jslot(tb1);
+                    const double z0 = ((xJ >> kd->sb0) & 1) ? -1.0 : 1.0;
+                    const double z1 = ((xJ >> kd->sb1) & 1) ? -1.0 : 1.0;
+                    // with the J operand at 0 (z = +1) the factor is exp(i sigma alpha z_other)
+                    phi = cmul(phi, make_double2(A.ca, sigma * A.sa * z0 * z1));
+                    const int jb = j0b >= 0 ? j0b : j1b;
+                    if (jb >= 0) {               // flipping that J bit multiplies by exp(-2 i sigma alpha z_other)
+                        const double zo = j0b >= 0 ? z1 : z0;
+                        const c128 f = make_double2(A.c2a, -sigma * A.s2a * zo);
+#pragma unroll
+                        for (int k = 0; k < 5; ++k)
+                            if (k == jb) F[k] = cmul(F[k], f);
+                    }
+                }
+            }
+#pragma unroll
+            for (int b4 = 0; b4 < 2; ++b4) {
+                const c128 p4 = b4 ? cmul(phi, F[4]) : phi;
+#pragma unroll
+                for (int b3 = 0; b3 < 2; ++b3) {
+                    const c128 p3 = b3 ? cmul(p4, F[3]) : p4;
+#pragma unroll
+                    for (int b2 = 0; b2 < 2; ++b2) {
+                        const c128 p2 = b2 ? cmul(p3, F[2]) : p3;
+#pragma unroll
+                        for (int b1 = 0; b1 < 2; ++b1) {
+                            const c128 p1 = b1 ? cmul(p2, F[1]) : p2;
+                            const int j = (b4 << 4) | (b3 << 3) | (b2 << 2) | (b1 << 1);
+                            v[j] = cmul(v[j], p1);
+                            v[j | 1] = cmul(v[j | 1], cmul(p1, F[0]));
+                        }
+                    }
+                }
+            }
+            if (AJ) {
+                DQ_FOR_REGS(v[j] = cmul(v[j], P.aj[j]))
+            }
+        } else {
+            if (type == 0) {
+                DQ_FOR_REGS(v[j] = tile[DQ_A_K0(j)])
+            } else {
+                DQ_FOR_REGS(v[j] = tile[DQ_A_K1(j)])
+            }
+        }
+        // ---- stages 0..3 -------------------------------------------------------------------------------------------
+        lift_bit<0>(v, P.rot[r][0]);
+        lift_bit<1>(v, P.rot[r][1]);
+        lift_bit<2>(v, P.rot[r][2]);
+        lift_bit<3>(v, P.rot[r][3]);
+        // ---- tail: stage 4 + the stores of the following exchange ----------------------------------------------------
+        const double2 rc4 = P.rot[r][4];
+        if (r == 0) {                                // K -> J exchange
+            if (type == 0) {
+                DQ_LIFT4_ST(DQ_A_K0)
+                __syncwarp();                        // L: the exchange never leaves the warp's 1024 amplitudes
+            } else {
+                __syncwarp();                        // from here on the tile lives in the 128-byte pattern
+                DQ_LIFT4_ST(DQ_A_K1)
+                team_sync(team);
+            }
+        } else if (r == 1) {
+            lift_bit<4>(v, rc4);
+        } else if (r == 2) {                         // J -> K exchange
+            if (type == 0) {
+                DQ_LIFT4_ST(DQ_A_J0)
+                __syncwarp();
+            } else {
+                DQ_LIFT4_ST(DQ_A_J1)
+                team_sync(team);
+            }
+        } else {
+            if (flags_all & F_STORE) {               // back into the landing layout of this buffer; one bulk store takes it from there
+                if (type == 0) {
+                    DQ_LIFT4_ST(DQ_A_K0)
+                } else {
+                    __syncwarp();                    // 64-byte pattern: these are not the slots this thread has just read
+                    DQ_LIFT4_ST(DQ_A_LAND1)
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            } else {
+                lift_bit<4>(v, rc4);
+            }
+        }
+    }
+#undef DQ_LIFT4_ST
+#else
 #pragma unroll 1
     for (int r = 0; r < 4; ++r) {
         // opaque per round: what a round derives from the thread index (slot addresses, gather indices, table addresses) is
@@ -1273,6 +1428,7 @@ __device__ __forceinline__ void ws_tile(const LaunchArgs& A, WsShared& ws, const
         if (r != 1) math_release(ws, tid >> 5);
 #endif
     }
+#endif
     {
         const int flags = P.flags;
         const int iK = type == 0 ? G0::baseK(tid) : G1::baseK(tid);
@@ -1298,6 +1454,8 @@ __device__ __forceinline__ void ws_tile(const LaunchArgs& A, WsShared& ws, const
             // the storer's gpu-scope fence (cumulative over everything it has observed), the ket counter.  No fence here: it
             // would hold this warp until its 32 stores are acknowledged by L2 (measured: 76.7 vs 84.4 samples/s).
         }
+#elif DQ_WS_PIPE
+        // the tile went back into the landing layout with the last butterfly stage (round 3 tail above)
 #else
         if (flags & F_STORE) {               // back into the landing layout of this buffer; one bulk store takes it from there
             const int sK = swz(iK);
