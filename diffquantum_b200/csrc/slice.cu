@@ -17,6 +17,7 @@ namespace {
 constexpr int kThreads = 256;
 constexpr int kMaxPairs = 256;
 constexpr int kMaxPeers = 16;
+constexpr int kTileBits12 = 12;                     // the TMA tile kernel: always 2^12 amplitudes (64 KiB)
 
 struct PhaseArgs {
     int n_zz;
@@ -149,95 +150,251 @@ __device__ __forceinline__ void rot_pair(double2& a, double2& b, double c, doubl
 // rounds (threads 32 / 64 / 128 bytes apart) stay bank-conflict free
 __device__ __forceinline__ int tslot(int e) { return e ^ ((e >> 3) & 7); }
 
+// The rotation rounds of one tile: every active bit, three (two, one) per shared-memory round trip.  `tid` < kThreads is the
+// thread's index in its team of kThreads threads, `bar` the named barrier the team synchronises on (0 = the whole CTA when the
+// CTA is one team).  pre != 1: the amplitudes are multiplied by `pre` as they are first read (scaled form: the product of the
+// cosines, for callers that cannot apply it on the way out).
+__device__ __forceinline__ void team_bar(int bar) { asm volatile("bar.sync %0, %1;" ::"r"(bar), "n"(kThreads) : "memory"); }
+
+template <bool SCALED>
+__device__ __forceinline__ void tile_rounds(double2* __restrict__ tile, const TileArgs& A, const int tid, const int bar, const double pre) {
+    const int n_el = 1 << A.T;
+    bool first = pre != 1.0;
+    int k = 0;
+    for (; k + 2 < A.n_active; k += 3) {                // three bits per round trip (A.active is ascending)
+        const int i0 = A.active[k], i1 = A.active[k + 1], i2 = A.active[k + 2];
+        const double c0 = A.c[k], s0 = A.s[k], c1 = A.c[k + 1], s1 = A.s[k + 1], c2 = A.c[k + 2], s2 = A.s[k + 2];
+        for (int q = tid; q < (n_el >> 3); q += kThreads) {
+            int e = ((q >> i0) << (i0 + 1)) | (q & ((1 << i0) - 1));
+            e = ((e >> i1) << (i1 + 1)) | (e & ((1 << i1) - 1));
+            e = ((e >> i2) << (i2 + 1)) | (e & ((1 << i2) - 1));
+            int sl[8];
+            double2 v[8];
+#pragma unroll
+            for (int b = 0; b < 8; ++b) {
+                sl[b] = tslot(e | ((b & 1) << i0) | (((b >> 1) & 1) << i1) | (((b >> 2) & 1) << i2));
+                v[b] = tile[sl[b]];
+            }
+            if (first) {
+#pragma unroll
+                for (int b = 0; b < 8; ++b) v[b] = make_double2(v[b].x * pre, v[b].y * pre);
+            }
+            rot_pair<SCALED>(v[0], v[1], c0, s0); rot_pair<SCALED>(v[2], v[3], c0, s0);
+            rot_pair<SCALED>(v[4], v[5], c0, s0); rot_pair<SCALED>(v[6], v[7], c0, s0);
+            rot_pair<SCALED>(v[0], v[2], c1, s1); rot_pair<SCALED>(v[1], v[3], c1, s1);
+            rot_pair<SCALED>(v[4], v[6], c1, s1); rot_pair<SCALED>(v[5], v[7], c1, s1);
+            rot_pair<SCALED>(v[0], v[4], c2, s2); rot_pair<SCALED>(v[1], v[5], c2, s2);
+            rot_pair<SCALED>(v[2], v[6], c2, s2); rot_pair<SCALED>(v[3], v[7], c2, s2);
+#pragma unroll
+            for (int b = 0; b < 8; ++b) tile[sl[b]] = v[b];
+        }
+        first = false;
+        team_bar(bar);
+    }
+    for (; k + 1 < A.n_active; k += 2) {                // two bits per round trip
+        const int i0 = min(A.active[k], A.active[k + 1]), i1 = max(A.active[k], A.active[k + 1]);
+        const double c0 = A.active[k] == i0 ? A.c[k] : A.c[k + 1], s0 = A.active[k] == i0 ? A.s[k] : A.s[k + 1];
+        const double c1 = A.active[k] == i0 ? A.c[k + 1] : A.c[k], s1 = A.active[k] == i0 ? A.s[k + 1] : A.s[k];
+        for (int q = tid; q < (n_el >> 2); q += kThreads) {
+            int e = ((q >> i0) << (i0 + 1)) | (q & ((1 << i0) - 1));            // zero at bit i0
+            e = ((e >> i1) << (i1 + 1)) | (e & ((1 << i1) - 1));                // zero at bit i1
+            const int s00 = tslot(e), s01 = tslot(e | (1 << i0)), s10 = tslot(e | (1 << i1)), s11 = tslot(e | (1 << i0) | (1 << i1));
+            double2 v00 = tile[s00], v01 = tile[s01], v10 = tile[s10], v11 = tile[s11];
+            if (first) {
+                v00 = make_double2(v00.x * pre, v00.y * pre); v01 = make_double2(v01.x * pre, v01.y * pre);
+                v10 = make_double2(v10.x * pre, v10.y * pre); v11 = make_double2(v11.x * pre, v11.y * pre);
+            }
+            rot_pair<SCALED>(v00, v01, c0, s0);
+            rot_pair<SCALED>(v10, v11, c0, s0);
+            rot_pair<SCALED>(v00, v10, c1, s1);
+            rot_pair<SCALED>(v01, v11, c1, s1);
+            tile[s00] = v00; tile[s01] = v01; tile[s10] = v10; tile[s11] = v11;
+        }
+        first = false;
+        team_bar(bar);
+    }
+    if (k < A.n_active) {
+        const int i0 = A.active[k];
+        const double c0 = A.c[k], s0 = A.s[k];
+        for (int q = tid; q < (n_el >> 1); q += kThreads) {
+            const int e = ((q >> i0) << (i0 + 1)) | (q & ((1 << i0) - 1));
+            const int sa = tslot(e), sb = tslot(e | (1 << i0));
+            double2 a = tile[sa], b = tile[sb];
+            if (first) { a = make_double2(a.x * pre, a.y * pre); b = make_double2(b.x * pre, b.y * pre); }
+            rot_pair<SCALED>(a, b, c0, s0);
+            tile[sa] = a; tile[sb] = b;
+        }
+        first = false;
+        team_bar(bar);
+    }
+}
+
 // PHASE (contiguous 12-bit tiles only): the diagonal phase of the SAME step rides on this pass -- applied to the tile in shared
 // memory right after it has landed, before the first rotation round -- so a product-formula step costs one pass over the
-// slice less.  Thread t owns tile bits 0..7 (= its index) and walks tile bits 8..11 in Gray-code order exactly like
-// k_slice_phase_gray: one full angle evaluation + sincos per 16 amplitudes, then per flipped bit the <= kGrayDeg pair factors
-// exp(+-2i w_e) of that bit.
+// slice less.  Thread t of a team owns tile bits 0..7 (= its index) and walks tile bits 8..11 in Gray-code order like
+// k_slice_phase_gray: one angle evaluation + sincos per 16 amplitudes, then ONE complex multiply per flipped bit.
 constexpr int kWalkBits = 4, kWalkLo = 8, kTileBits = 12, kMaxIn = 96;
+// Tables built once per CTA from the pair list (tile bit = physical bit k < 12 in a contiguous pass):
+//   out_*   per tile bit k: its pairs whose other end lies OUTSIDE the tile -> per tile a field h[k] on z_k
+//   in_*    pairs with both ends inside the tile
+//   oo_*    pairs with both ends outside the tile -> per tile a constant
+//   w_*     per walk bit j (tile bit 8 + j): exp(2i w) factors of its pairs with thread bits (w_in) and with outside bits (w_out,
+//           per tile folded into ONE factor f_out[j]; z_p = -1 takes its conjugate)
+//   ww      pairs among the walk bits themselves: the Gray sequence is fixed, so the state of the other walk bits at step kk is
+//           known -- one factor per step, the same for every thread and tile
+struct PhaseTabs {
+    int out_n[kTileBits], w_in_n[kWalkBits], w_out_n[kWalkBits], in_n, oo_n, has_ww;
+    unsigned char out_other[kTileBits][kGrayDeg], in_a[kMaxIn], in_b[kMaxIn], oo_a[kMaxPairs], oo_b[kMaxPairs];
+    unsigned char w_in_other[kWalkBits][kGrayDeg], w_out_other[kWalkBits][kGrayDeg];
+    double out_ang[kTileBits][kGrayDeg], in_ang[kMaxIn], oo_ang[kMaxPairs], c0;
+    double w_in_c2[kWalkBits][kGrayDeg], w_in_s2[kWalkBits][kGrayDeg], w_out_c2[kWalkBits][kGrayDeg], w_out_s2[kWalkBits][kGrayDeg];
+    double2 ww[1 << kWalkBits];
+};
+struct PhaseTile {                   // per tile (one per team): fields of the outside bits, the outside-outside constant, outside factors
+    double h_field[kTileBits], c_tile;
+    double2 f_out[kWalkBits];
+};
+
+// once per CTA; t = 0 .. (at least 48) distinct threads; a barrier must follow.  has_ww must be 0 on entry.
+__device__ __forceinline__ void phase_setup(PhaseTabs& P, const PhaseArgs* __restrict__ pa, const int t) {
+    const int n_zz = pa->n_zz;
+    if (t < kTileBits) {
+        const int k = t;
+        int d = 0;
+        for (int e = 0; e < n_zz; ++e) {
+            const int a = pa->a[e], b = pa->b[e];
+            if ((a != k && b != k) || (a < kTileBits && b < kTileBits)) continue;
+            P.out_other[k][d] = (unsigned char)(a == k ? b : a);
+            P.out_ang[k][d] = pa->ang[e];
+            ++d;
+        }
+        P.out_n[k] = d;
+    } else if (t == kTileBits) {
+        int d = 0, o = 0;
+        for (int e = 0; e < n_zz; ++e) {
+            const int a = pa->a[e], b = pa->b[e];
+            if (a < kTileBits && b < kTileBits) { P.in_a[d] = (unsigned char)a; P.in_b[d] = (unsigned char)b; P.in_ang[d] = pa->ang[e]; ++d; }
+            else if (a >= kTileBits && b >= kTileBits) { P.oo_a[o] = (unsigned char)a; P.oo_b[o] = (unsigned char)b; P.oo_ang[o] = pa->ang[e]; ++o; }
+        }
+        P.in_n = d;
+        P.oo_n = o;
+        P.c0 = pa->c0;
+    } else if (t < kTileBits + 1 + kWalkBits) {
+        const int j = t - kTileBits - 1, p = kWalkLo + j;
+        int di = 0, dout = 0;
+        for (int e = 0; e < n_zz; ++e) {
+            const int a = pa->a[e], b = pa->b[e];
+            if (a != p && b != p) continue;
+            const int o = a == p ? b : a;
+            if (o >= kWalkLo && o < kTileBits) continue;                 // walk-walk pair: ww[] below
+            double sn, cs;
+            sincos(2.0 * pa->ang[e], &sn, &cs);
+            if (o < kWalkLo) { P.w_in_other[j][di] = (unsigned char)o; P.w_in_c2[j][di] = cs; P.w_in_s2[j][di] = sn; ++di; }
+            else { P.w_out_other[j][dout] = (unsigned char)o; P.w_out_c2[j][dout] = cs; P.w_out_s2[j][dout] = sn; ++dout; }
+        }
+        P.w_in_n[j] = di;
+        P.w_out_n[j] = dout;
+    } else if (t >= 32 && t < 32 + (1 << kWalkBits)) {
+        const int kk = t - 32;
+        double2 f = make_double2(1.0, 0.0);
+        if (kk >= 1) {
+            const int j = __ffs(kk) - 1, p = kWalkLo + j;
+            const int before = (kk - 1) ^ ((kk - 1) >> 1);               // Gray code of the previous step = walk bits before this flip
+            const bool zp_neg = ((before >> j) & 1) != 0;
+            for (int e = 0; e < n_zz; ++e) {
+                const int a = pa->a[e], b = pa->b[e];
+                if (a != p && b != p) continue;
+                const int o = a == p ? b : a;
+                if (o < kWalkLo || o >= kTileBits) continue;
+                double sn, cs;
+                sincos(2.0 * pa->ang[e], &sn, &cs);
+                const bool differ = (((before >> (o - kWalkLo)) & 1) != 0) != zp_neg;
+                const double s2 = differ ? -sn : sn;
+                f = make_double2(f.x * cs - f.y * s2, f.x * s2 + f.y * cs);
+                P.has_ww = 1;
+            }
+        }
+        P.ww[kk] = f;
+    }
+}
+
+// per tile; t < kTileBits + 1 + kWalkBits threads do the work (fixed summation / product order); G = global index of the
+// tile's element 0.  A team barrier must follow.
+__device__ __forceinline__ void phase_tile_setup(const PhaseTabs& P, PhaseTile& Q, const unsigned long long G, const int t) {
+    if (t < kTileBits) {
+        const int k = t;
+        double hsum = 0.0;
+        for (int q = 0; q < P.out_n[k]; ++q) hsum += ((G >> P.out_other[k][q]) & 1ull) ? -P.out_ang[k][q] : P.out_ang[k][q];
+        Q.h_field[k] = hsum;
+    } else if (t == kTileBits) {
+        double c = P.c0;
+        for (int q = 0; q < P.oo_n; ++q) c += (((G >> P.oo_a[q]) ^ (G >> P.oo_b[q])) & 1ull) ? -P.oo_ang[q] : P.oo_ang[q];
+        Q.c_tile = c;
+    } else if (t < kTileBits + 1 + kWalkBits) {
+        const int j = t - kTileBits - 1;
+        double2 f = make_double2(1.0, 0.0);
+        for (int q = 0; q < P.w_out_n[j]; ++q) {
+            const double c2 = P.w_out_c2[j][q], s2 = ((G >> P.w_out_other[j][q]) & 1ull) ? -P.w_out_s2[j][q] : P.w_out_s2[j][q];
+            f = make_double2(f.x * c2 - f.y * s2, f.x * s2 + f.y * c2);
+        }
+        Q.f_out[j] = f;
+    }
+}
+
+// per tile, every thread of the team (t = 0..255 = tile bits 0..7); the tile must have landed, Q must be complete
+__device__ __forceinline__ void phase_apply(const PhaseTabs& P, const PhaseTile& Q, double2* __restrict__ tile, const int t) {
+    int e = t;                                                       // walk bits 8..11 start at 0
+    double a = Q.c_tile;
+#pragma unroll
+    for (int k = 0; k < kTileBits; ++k) a += ((e >> k) & 1) ? -Q.h_field[k] : Q.h_field[k];
+    for (int q = 0; q < P.in_n; ++q) a += (((e >> P.in_a[q]) ^ (e >> P.in_b[q])) & 1) ? -P.in_ang[q] : P.in_ang[q];
+    double sn, cs;
+    sincos(a, &sn, &cs);
+    double2 ph = make_double2(cs, -sn);                              // exp(-i a)
+    // flip factor of walk bit j for THIS thread and tile (z_p = +1 form): the outside pairs (f_out) times the pairs with
+    // this thread's own bits -- constant over the walk, so the walk itself is one multiply per flip
+    double2 F[kWalkBits];
+#pragma unroll
+    for (int j = 0; j < kWalkBits; ++j) {
+        double2 f = Q.f_out[j];
+        for (int q = 0; q < P.w_in_n[j]; ++q) {
+            const double c2 = P.w_in_c2[j][q], s2 = ((e >> P.w_in_other[j][q]) & 1) ? -P.w_in_s2[j][q] : P.w_in_s2[j][q];
+            f = make_double2(f.x * c2 - f.y * s2, f.x * s2 + f.y * c2);
+        }
+        F[j] = f;
+    }
+    const bool any_ww = P.has_ww != 0;
+    {
+        const double2 v = tile[tslot(e)];
+        tile[tslot(e)] = make_double2(v.x * ph.x - v.y * ph.y, v.x * ph.y + v.y * ph.x);
+    }
+#pragma unroll
+    for (int kk = 1; kk < (1 << kWalkBits); ++kk) {
+        const int j = (kk & 1) ? 0 : ((kk & 2) ? 1 : ((kk & 4) ? 2 : 3));       // lowest set bit of kk (compile time after unrolling)
+        const int before = (kk - 1) ^ ((kk - 1) >> 1);
+        const bool zp_neg = ((before >> j) & 1) != 0;                // z_p before the flip: known from the Gray sequence
+        const double fy = zp_neg ? -F[j].y : F[j].y;
+        ph = make_double2(ph.x * F[j].x - ph.y * fy, ph.x * fy + ph.y * F[j].x);
+        if (any_ww) {
+            const double2 w = P.ww[kk];
+            ph = make_double2(ph.x * w.x - ph.y * w.y, ph.x * w.y + ph.y * w.x);
+        }
+        e ^= 1 << (kWalkLo + j);
+        const double2 v = tile[tslot(e)];
+        tile[tslot(e)] = make_double2(v.x * ph.x - v.y * ph.y, v.x * ph.y + v.y * ph.x);
+    }
+}
+
 template <bool CONTIG, bool SCALED, bool PHASE>
 __global__ void __launch_bounds__(kThreads, 3) k_slice_rx_tile(double2* __restrict__ psi, int L, const TileArgs* __restrict__ ta,
                                                                const PhaseArgs* __restrict__ pa, unsigned long long high) {
     extern __shared__ __align__(16) double2 tile[];
     __shared__ TileArgs A;
-    // PHASE tables, built once per CTA from the pair list (tile bit = physical bit k < 12 in a contiguous pass):
-    //   out_*   per tile bit k: its pairs whose other end lies OUTSIDE the tile -> per tile a field h[k] on z_k
-    //   in_*    pairs with both ends inside the tile
-    //   oo_idx  pairs with both ends outside the tile -> per tile a constant
-    //   w_*     per walk bit j (tile bit 8 + j): exp(2i w) factors of its in-tile pairs, and of its outside pairs (per tile
-    //           folded into ONE factor f_out[j]; z_p = -1 takes its conjugate)
-    __shared__ int out_n[kTileBits], w_in_n[kWalkBits], w_out_n[kWalkBits], in_n, oo_n;
-    __shared__ unsigned char out_other[kTileBits][kGrayDeg], in_a[kMaxIn], in_b[kMaxIn], oo_idx[kMaxPairs];
-    __shared__ unsigned char w_in_other[kWalkBits][kGrayDeg], w_out_other[kWalkBits][kGrayDeg];
-    __shared__ double out_ang[kTileBits][kGrayDeg], in_ang[kMaxIn], oo_ang[PHASE ? kMaxPairs : 1];
-    __shared__ double w_in_c2[kWalkBits][kGrayDeg], w_in_s2[kWalkBits][kGrayDeg], w_out_c2[kWalkBits][kGrayDeg], w_out_s2[kWalkBits][kGrayDeg];
-    __shared__ double h_field[kTileBits], c_tile;
-    __shared__ double2 f_out[kWalkBits], ww[1 << kWalkBits];
-    __shared__ int has_ww;
-    if (threadIdx.x == 0) { A = *ta; has_ww = 0; }
+    __shared__ PhaseTabs PT[1];              // ~8 KB; unused (and removed by the compiler) without PHASE
+    __shared__ PhaseTile PQ;
+    if (threadIdx.x == 0) { A = *ta; PT[0].has_ww = 0; }
     __syncthreads();
-    if (PHASE) {
-        const int n_zz = pa->n_zz;
-        if (threadIdx.x < kTileBits) {
-            const int k = threadIdx.x;
-            int d = 0;
-            for (int e = 0; e < n_zz; ++e) {
-                const int a = pa->a[e], b = pa->b[e];
-                if ((a != k && b != k) || (a < kTileBits && b < kTileBits)) continue;
-                out_other[k][d] = (unsigned char)(a == k ? b : a);
-                out_ang[k][d] = pa->ang[e];
-                ++d;
-            }
-            out_n[k] = d;
-        } else if (threadIdx.x == kTileBits) {
-            int d = 0, o = 0;
-            for (int e = 0; e < n_zz; ++e) {
-                const int a = pa->a[e], b = pa->b[e];
-                if (a < kTileBits && b < kTileBits) { in_a[d] = (unsigned char)a; in_b[d] = (unsigned char)b; in_ang[d] = pa->ang[e]; ++d; }
-                else if (a >= kTileBits && b >= kTileBits) { oo_idx[o] = (unsigned char)e; oo_ang[o] = pa->ang[e]; ++o; }
-            }
-            in_n = d;
-            oo_n = o;
-        } else if (threadIdx.x < kTileBits + 1 + kWalkBits) {
-            const int j = threadIdx.x - kTileBits - 1, p = kWalkLo + j;
-            int di = 0, dout = 0;
-            for (int e = 0; e < n_zz; ++e) {
-                const int a = pa->a[e], b = pa->b[e];
-                if (a != p && b != p) continue;
-                const int o = a == p ? b : a;
-                if (o >= kWalkLo && o < kTileBits) continue;                 // walk-walk pair: ww[] below
-                double sn, cs;
-                sincos(2.0 * pa->ang[e], &sn, &cs);
-                if (o < kWalkLo) { w_in_other[j][di] = (unsigned char)o; w_in_c2[j][di] = cs; w_in_s2[j][di] = sn; ++di; }
-                else { w_out_other[j][dout] = (unsigned char)o; w_out_c2[j][dout] = cs; w_out_s2[j][dout] = sn; ++dout; }
-            }
-            w_in_n[j] = di;
-            w_out_n[j] = dout;
-        } else if (threadIdx.x >= 32 && threadIdx.x < 32 + (1 << kWalkBits)) {
-            // pairs among the walk bits themselves: the Gray sequence is fixed, so the state of the other walk bits at step kk
-            // is known -- one factor per step, the same for every thread and tile
-            const int kk = threadIdx.x - 32;
-            double2 f = make_double2(1.0, 0.0);
-            if (kk >= 1) {
-                const int j = __ffs(kk) - 1, p = kWalkLo + j;
-                const int before = (kk - 1) ^ ((kk - 1) >> 1);               // Gray code of the previous step = walk bits before this flip
-                const bool zp_neg = ((before >> j) & 1) != 0;
-                for (int e = 0; e < n_zz; ++e) {
-                    const int a = pa->a[e], b = pa->b[e];
-                    if (a != p && b != p) continue;
-                    const int o = a == p ? b : a;
-                    if (o < kWalkLo || o >= kTileBits) continue;
-                    double sn, cs;
-                    sincos(2.0 * pa->ang[e], &sn, &cs);
-                    const bool differ = (((before >> (o - kWalkLo)) & 1) != 0) != zp_neg;
-                    const double s2 = differ ? -sn : sn;
-                    f = make_double2(f.x * cs - f.y * s2, f.x * s2 + f.y * cs);
-                    has_ww = 1;
-                }
-            }
-            ww[kk] = f;
-        }
-    }
+    if (PHASE) phase_setup(PT[0], pa, threadIdx.x);
     __syncthreads();
     const int T = A.T, lo = A.lo, n_el = 1 << T;
     const unsigned lowmask = (1u << lo) - 1u;
@@ -266,132 +423,14 @@ __global__ void __launch_bounds__(kThreads, 3) k_slice_rx_tile(double2* __restri
             asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
-        if (PHASE) {
-            // per-tile constants while the tile is in flight: fields of the outside bits on every tile bit, the
-            // outside-outside constant, the outside factor of every walk bit (fixed summation / product order)
-            const unsigned long long G = (high << L) | base;                 // tile bits are zero in `base`
-            if (threadIdx.x < kTileBits) {
-                const int k = threadIdx.x;
-                double hsum = 0.0;
-                for (int q = 0; q < out_n[k]; ++q) hsum += ((G >> out_other[k][q]) & 1ull) ? -out_ang[k][q] : out_ang[k][q];
-                h_field[k] = hsum;
-            } else if (threadIdx.x == kTileBits) {
-                double c = pa->c0;
-                for (int q = 0; q < oo_n; ++q) {
-                    const int e = oo_idx[q];
-                    c += (((G >> pa->a[e]) ^ (G >> pa->b[e])) & 1ull) ? -oo_ang[q] : oo_ang[q];
-                }
-                c_tile = c;
-            } else if (threadIdx.x < kTileBits + 1 + kWalkBits) {
-                const int j = threadIdx.x - kTileBits - 1;
-                double2 f = make_double2(1.0, 0.0);
-                for (int q = 0; q < w_out_n[j]; ++q) {
-                    const double c2 = w_out_c2[j][q], s2 = ((G >> w_out_other[j][q]) & 1ull) ? -w_out_s2[j][q] : w_out_s2[j][q];
-                    f = make_double2(f.x * c2 - f.y * s2, f.x * s2 + f.y * c2);
-                }
-                f_out[j] = f;
-            }
-            asm volatile("cp.async.wait_group 0;" ::: "memory");
-            __syncthreads();
-            int e = threadIdx.x;                                             // tile bits 0..7; walk bits 8..11 start at 0
-            double a = c_tile;
-#pragma unroll
-            for (int k = 0; k < kTileBits; ++k) a += ((e >> k) & 1) ? -h_field[k] : h_field[k];
-            for (int q = 0; q < in_n; ++q) a += (((e >> in_a[q]) ^ (e >> in_b[q])) & 1) ? -in_ang[q] : in_ang[q];
-            double sn, cs;
-            sincos(a, &sn, &cs);
-            double2 ph = make_double2(cs, -sn);                              // exp(-i a)
-            // flip factor of walk bit j for THIS thread and tile (z_p = +1 form): the outside pairs (f_out) times the pairs
-            // with this thread's own bits -- constant over the walk, so the walk itself is one multiply per flip
-            double2 F[kWalkBits];
-#pragma unroll
-            for (int j = 0; j < kWalkBits; ++j) {
-                double2 f = f_out[j];
-                for (int q = 0; q < w_in_n[j]; ++q) {
-                    const double c2 = w_in_c2[j][q], s2 = ((e >> w_in_other[j][q]) & 1) ? -w_in_s2[j][q] : w_in_s2[j][q];
-                    f = make_double2(f.x * c2 - f.y * s2, f.x * s2 + f.y * c2);
-                }
-                F[j] = f;
-            }
-            const bool any_ww = has_ww != 0;
-            {
-                const double2 v = tile[tslot(e)];
-                tile[tslot(e)] = make_double2(v.x * ph.x - v.y * ph.y, v.x * ph.y + v.y * ph.x);
-            }
-#pragma unroll
-            for (int kk = 1; kk < (1 << kWalkBits); ++kk) {
-                const int j = (kk & 1) ? 0 : ((kk & 2) ? 1 : ((kk & 4) ? 2 : 3));       // lowest set bit of kk (compile time after unrolling)
-                const int before = (kk - 1) ^ ((kk - 1) >> 1);
-                const bool zp_neg = ((before >> j) & 1) != 0;                // z_p before the flip: known from the Gray sequence
-                const double fy = zp_neg ? -F[j].y : F[j].y;
-                ph = make_double2(ph.x * F[j].x - ph.y * fy, ph.x * fy + ph.y * F[j].x);
-                if (any_ww) {
-                    const double2 w = ww[kk];
-                    ph = make_double2(ph.x * w.x - ph.y * w.y, ph.x * w.y + ph.y * w.x);
-                }
-                e ^= 1 << (kWalkLo + j);
-                const double2 v = tile[tslot(e)];
-                tile[tslot(e)] = make_double2(v.x * ph.x - v.y * ph.y, v.x * ph.y + v.y * ph.x);
-            }
-        } else {
-            asm volatile("cp.async.wait_group 0;" ::: "memory");
-        }
+        if (PHASE) phase_tile_setup(PT[0], PQ, (high << L) | base, threadIdx.x);     // while the tile is in flight
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
         __syncthreads();
-        int k = 0;
-        for (; k + 2 < A.n_active; k += 3) {                // three bits per round trip (A.active is ascending)
-            const int i0 = A.active[k], i1 = A.active[k + 1], i2 = A.active[k + 2];
-            const double c0 = A.c[k], s0 = A.s[k], c1 = A.c[k + 1], s1 = A.s[k + 1], c2 = A.c[k + 2], s2 = A.s[k + 2];
-            for (int q = threadIdx.x; q < (n_el >> 3); q += kThreads) {
-                int e = ((q >> i0) << (i0 + 1)) | (q & ((1 << i0) - 1));
-                e = ((e >> i1) << (i1 + 1)) | (e & ((1 << i1) - 1));
-                e = ((e >> i2) << (i2 + 1)) | (e & ((1 << i2) - 1));
-                int sl[8];
-                double2 v[8];
-#pragma unroll
-                for (int b = 0; b < 8; ++b) {
-                    sl[b] = tslot(e | ((b & 1) << i0) | (((b >> 1) & 1) << i1) | (((b >> 2) & 1) << i2));
-                    v[b] = tile[sl[b]];
-                }
-                rot_pair<SCALED>(v[0], v[1], c0, s0); rot_pair<SCALED>(v[2], v[3], c0, s0);
-                rot_pair<SCALED>(v[4], v[5], c0, s0); rot_pair<SCALED>(v[6], v[7], c0, s0);
-                rot_pair<SCALED>(v[0], v[2], c1, s1); rot_pair<SCALED>(v[1], v[3], c1, s1);
-                rot_pair<SCALED>(v[4], v[6], c1, s1); rot_pair<SCALED>(v[5], v[7], c1, s1);
-                rot_pair<SCALED>(v[0], v[4], c2, s2); rot_pair<SCALED>(v[1], v[5], c2, s2);
-                rot_pair<SCALED>(v[2], v[6], c2, s2); rot_pair<SCALED>(v[3], v[7], c2, s2);
-#pragma unroll
-                for (int b = 0; b < 8; ++b) tile[sl[b]] = v[b];
-            }
+        if (PHASE) {
+            phase_apply(PT[0], PQ, tile, threadIdx.x);
             __syncthreads();
         }
-        for (; k + 1 < A.n_active; k += 2) {                // two bits per round trip
-            const int i0 = min(A.active[k], A.active[k + 1]), i1 = max(A.active[k], A.active[k + 1]);
-            const double c0 = A.active[k] == i0 ? A.c[k] : A.c[k + 1], s0 = A.active[k] == i0 ? A.s[k] : A.s[k + 1];
-            const double c1 = A.active[k] == i0 ? A.c[k + 1] : A.c[k], s1 = A.active[k] == i0 ? A.s[k + 1] : A.s[k];
-            for (int q = threadIdx.x; q < (n_el >> 2); q += kThreads) {
-                int e = ((q >> i0) << (i0 + 1)) | (q & ((1 << i0) - 1));            // zero at bit i0
-                e = ((e >> i1) << (i1 + 1)) | (e & ((1 << i1) - 1));                // zero at bit i1
-                const int s00 = tslot(e), s01 = tslot(e | (1 << i0)), s10 = tslot(e | (1 << i1)), s11 = tslot(e | (1 << i0) | (1 << i1));
-                double2 v00 = tile[s00], v01 = tile[s01], v10 = tile[s10], v11 = tile[s11];
-                rot_pair<SCALED>(v00, v01, c0, s0);
-                rot_pair<SCALED>(v10, v11, c0, s0);
-                rot_pair<SCALED>(v00, v10, c1, s1);
-                rot_pair<SCALED>(v01, v11, c1, s1);
-                tile[s00] = v00; tile[s01] = v01; tile[s10] = v10; tile[s11] = v11;
-            }
-            __syncthreads();
-        }
-        if (k < A.n_active) {
-            const int i0 = A.active[k];
-            const double c0 = A.c[k], s0 = A.s[k];
-            for (int q = threadIdx.x; q < (n_el >> 1); q += kThreads) {
-                const int e = ((q >> i0) << (i0 + 1)) | (q & ((1 << i0) - 1));
-                const int sa = tslot(e), sb = tslot(e | (1 << i0));
-                double2 a = tile[sa], b = tile[sb];
-                rot_pair<SCALED>(a, b, c0, s0);
-                tile[sa] = a; tile[sb] = b;
-            }
-            __syncthreads();
-        }
+        tile_rounds<SCALED>(tile, A, threadIdx.x, 0, 1.0);
         for (int e = threadIdx.x; e < n_el; e += kThreads)
         {
             double2 v = tile[tslot(e)];
@@ -405,6 +444,136 @@ __global__ void __launch_bounds__(kThreads, 3) k_slice_rx_tile(double2* __restri
             }
         }
         __syncthreads();
+    }
+}
+
+// ---- the same pass with TMA tiles, three buffers per SM --------------------------------------------------------------
+// One persistent CTA per SM: two consumer teams of kThreads threads, a loader warp and a storer warp (the structure of
+// k_fused_ws, without dependencies between tiles).  The tile arrives by ONE tensor load (cp.async.bulk.tensor, hardware
+// 128-byte swizzle = tslot, mbarrier completion) and leaves by ONE tensor store; while a team rotates tile k the loader already
+// has tile k + 1 (the other team's) and k + 2 in flight and the storer drains tile k - 1, so neither the load latency nor
+// the write-back sits on a team's critical path (k_slice_rx_tile: load, rotate and store of a tile are serial in its CTA, and
+// the three resident CTAs only partly cover for one another).  The tile is described by a tensor of rank <= 5 over the slice:
+// dimension 0 = 8 amplitudes (128 bytes), every further dimension one run of consecutive tile bits, spanning up to the next
+// run so that its coordinate also carries the tile-index bits lying in between (box = the run).  Passes whose tile bits form
+// more than four runs, scatter passes and slices below 2^12 stay on k_slice_rx_tile.
+constexpr int kTmaBufs = 3, kTmaTeams = 2, kTmaThreads = kTmaTeams * kThreads + 64;
+struct TmaGeom {
+    int rank;                        // 2..5
+    int start[5], nbits[5];          // coordinate of dimension d >= 1: (base >> start[d]) & (2^nbits[d] - 1); dimension 0: 0
+};
+struct TmaShared {
+    unsigned long long full[kTmaBufs], done[kTmaBufs], empty[kTmaBufs];
+    // which tile of this CTA the buffer holds (written by the loader before it arms `full`).  A parity wait cannot tell
+    // "phase n + 1 is complete" from "phase n is not complete yet"; tiles k and k + 3 share a buffer but belong to different
+    // teams, so a team that gets to tile k + 3 while the load of tile k is still in flight would fall through its wait.
+    volatile unsigned long long seq[kTmaBufs];
+    TileArgs A;
+};
+
+__device__ __forceinline__ unsigned s_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void s_mbar_wait(unsigned long long* bar, unsigned parity) {
+    const unsigned addr = s_u32(bar);
+    unsigned ok;
+    do {
+        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void tma_coords(const TmaGeom& g, unsigned long long base, int (&c)[5]) {
+    c[0] = 0;
+#pragma unroll
+    for (int d = 1; d < 5; ++d) c[d] = d < g.rank ? (int)((base >> g.start[d]) & ((1ull << g.nbits[d]) - 1ull)) : 0;
+}
+
+template <bool SCALED>
+__global__ void __launch_bounds__(kTmaThreads, 1) k_slice_rx_tma(const __grid_constant__ CUtensorMap map, int L,
+                                                                 const TileArgs* __restrict__ ta, const TmaGeom geom) {
+    extern __shared__ __align__(16) unsigned char smem_dyn[];
+    unsigned char* smem_raw = smem_dyn + ((1024u - (s_u32(smem_dyn) & 1023u)) & 1023u);      // swizzled TMA boxes: 1 KiB aligned
+    double2* tiles = reinterpret_cast<double2*>(smem_raw);
+    __shared__ __align__(16) TmaShared sh;
+    constexpr unsigned kTileBytes = (unsigned)(sizeof(double2) << kTileBits12);
+    if (threadIdx.x == 0) {
+        sh.A = *ta;
+        for (int b = 0; b < kTmaBufs; ++b) {
+            sh.seq[b] = ~0ull;
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(s_u32(&sh.full[b])), "r"(1) : "memory");
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(s_u32(&sh.done[b])), "r"(kThreads) : "memory");
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(s_u32(&sh.empty[b])), "r"(1) : "memory");
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const unsigned long long n_tiles = 1ull << (L - kTileBits12);
+    const unsigned long long mine = blockIdx.x < n_tiles ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;   // tiles of this CTA
+    const int wg = threadIdx.x / kThreads;
+    if (wg < kTmaTeams) {
+        // ------------------------------ consumer team ----------------------------------------------------------
+        const int tid = threadIdx.x - wg * kThreads;
+        const double pre = SCALED ? sh.A.post : 1.0;
+        for (unsigned long long k = (unsigned long long)wg; k < mine; k += kTmaTeams) {
+            const int b = (int)(k % kTmaBufs);
+            do {
+                s_mbar_wait(&sh.full[b], (unsigned)((k / kTmaBufs) & 1ull));
+            } while (sh.seq[b] != k);
+            tile_rounds<SCALED>(tiles + ((size_t)b << kTileBits12), sh.A, tid, 1 + wg, pre);
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // this thread's tile writes -> the bulk store
+            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(s_u32(&sh.done[b])) : "memory");
+        }
+    } else if (threadIdx.x == kTmaTeams * kThreads) {
+        // ------------------------------ loader -------------------------------------------------------------------
+        const unsigned long long mask = sh.A.mask;
+        for (unsigned long long k = 0; k < mine; ++k) {
+            const int b = (int)(k % kTmaBufs);
+            unsigned long long base = 0, rest = blockIdx.x + k * gridDim.x;
+            for (int p = 0; p < L; ++p)
+                if (!((mask >> p) & 1ull)) { base |= (rest & 1ull) << p; rest >>= 1; }
+            int c[5];
+            tma_coords(geom, base, c);
+            if (k >= kTmaBufs) s_mbar_wait(&sh.empty[b], (unsigned)(((k / kTmaBufs) - 1ull) & 1ull));   // the store of tile k - 3 has read it
+            sh.seq[b] = k;
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(s_u32(&sh.full[b])), "r"(kTileBytes) : "memory");
+            const unsigned dst = s_u32(tiles + ((size_t)b << kTileBits12)), bar = s_u32(&sh.full[b]);
+            switch (geom.rank) {
+                case 2: asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                                     ::"r"(dst), "l"(&map), "r"(bar), "r"(c[0]), "r"(c[1]) : "memory"); break;
+                case 3: asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                                     ::"r"(dst), "l"(&map), "r"(bar), "r"(c[0]), "r"(c[1]), "r"(c[2]) : "memory"); break;
+                case 4: asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+                                     ::"r"(dst), "l"(&map), "r"(bar), "r"(c[0]), "r"(c[1]), "r"(c[2]), "r"(c[3]) : "memory"); break;
+                default: asm volatile("cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+                                      ::"r"(dst), "l"(&map), "r"(bar), "r"(c[0]), "r"(c[1]), "r"(c[2]), "r"(c[3]), "r"(c[4]) : "memory"); break;
+            }
+        }
+    } else if (threadIdx.x == kTmaTeams * kThreads + 32) {
+        // ------------------------------ storer -------------------------------------------------------------------
+        const unsigned long long mask = sh.A.mask;
+        for (unsigned long long k = 0; k < mine; ++k) {
+            const int b = (int)(k % kTmaBufs);
+            unsigned long long base = 0, rest = blockIdx.x + k * gridDim.x;
+            for (int p = 0; p < L; ++p)
+                if (!((mask >> p) & 1ull)) { base |= (rest & 1ull) << p; rest >>= 1; }
+            int c[5];
+            tma_coords(geom, base, c);
+            s_mbar_wait(&sh.done[b], (unsigned)((k / kTmaBufs) & 1ull));
+            const unsigned src = s_u32(tiles + ((size_t)b << kTileBits12));
+            switch (geom.rank) {
+                case 2: asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%2, %3}], [%1];"
+                                     ::"l"(&map), "r"(src), "r"(c[0]), "r"(c[1]) : "memory"); break;
+                case 3: asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4}], [%1];"
+                                     ::"l"(&map), "r"(src), "r"(c[0]), "r"(c[1]), "r"(c[2]) : "memory"); break;
+                case 4: asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+                                     ::"l"(&map), "r"(src), "r"(c[0]), "r"(c[1]), "r"(c[2]), "r"(c[3]) : "memory"); break;
+                default: asm volatile("cp.async.bulk.tensor.5d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];"
+                                      ::"l"(&map), "r"(src), "r"(c[0]), "r"(c[1]), "r"(c[2]), "r"(c[3]), "r"(c[4]) : "memory"); break;
+            }
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");     // the store has read the buffer: the loader may refill it
+            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(s_u32(&sh.empty[b])) : "memory");
+        }
+        asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");              // every store is complete before the kernel ends
     }
 }
 
@@ -607,6 +776,59 @@ int dq_slice_rx(dq_context* ctx, void* psi_dev, int L, int bit, double theta) {
 namespace {
 // All rotations of a step; d_phase != NULL: the step's diagonal phase is applied by the first pass if that pass is a
 // contiguous 12-bit tile pass (*phase_done says whether it was).
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn slice_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* f = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(f);
+        cudaGetLastError();
+    }
+    return fn;
+}
+
+// Tensor view of a pass's tiles over the slice (see k_slice_rx_tma); false: not expressible with rank <= 5.
+bool make_tile_map(const TileArgs& h, int L, void* psi, CUtensorMap* map, TmaGeom* g) {
+    EncodeTiledFn enc = slice_encode_fn();
+    if (!enc || h.T != kTileBits12 || L < kTileBits12 || h.lo < 3) return false;
+    // runs of consecutive tile bits above bit 2 (bits 0..2 are dimension 0), at most 8 bits each (box extent <= 256)
+    int run_start[8], run_len[8], n_runs = 0;
+    for (int i = 3; i < h.T;) {
+        int len = 1;
+        while (i + len < h.T && h.pos[i + len] == h.pos[i] + len && len < 8) ++len;
+        if (n_runs == 4) return false;
+        run_start[n_runs] = h.pos[i];
+        run_len[n_runs] = len;
+        ++n_runs;
+        i += len;
+    }
+    if (n_runs == 0) return false;
+    cuuint64_t dims[5], strides[4];
+    cuuint32_t box[5], ones[5] = {1, 1, 1, 1, 1};
+    dims[0] = 16;                                                        // 8 amplitudes = 16 doubles = 128 bytes
+    box[0] = 16;
+    g->rank = 1 + n_runs;
+    g->start[0] = 0;
+    g->nbits[0] = 0;
+    for (int r = 0; r < n_runs; ++r) {
+        const int end = r + 1 < n_runs ? run_start[r + 1] : L;          // the dimension spans up to the next run
+        dims[1 + r] = (cuuint64_t)1 << (end - run_start[r]);
+        strides[r] = (cuuint64_t)16 << run_start[r];
+        box[1 + r] = (cuuint32_t)1 << run_len[r];
+        g->start[1 + r] = run_start[r];
+        g->nbits[1 + r] = end - run_start[r];
+    }
+    for (int d = g->rank; d < 5; ++d) { g->start[d] = 0; g->nbits[d] = 0; }
+    return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, (cuuint32_t)g->rank, psi, dims, strides, box, ones, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 struct Scatter { int g, rank; void* const* peer; };
 
 int rx_many_impl(dq_context* ctx, void* psi_dev, int L, int count, const int32_t* bits, const double* thetas,
@@ -711,6 +933,27 @@ int rx_many_impl(dq_context* ctx, void* psi_dev, int L, int count, const int32_t
         const unsigned grid = (unsigned)std::min<unsigned long long>(n_tiles, (unsigned long long)ctx->prop.multiProcessorCount * per_sm);
         double2* psi = (double2*)psi_dev;
         const bool with_phase = d_phase && phase_done && !*phase_done && h.lo == h.T && h.T == kWalkLo + kWalkBits;
+        if (!with_phase && !h.scatter_g && !getenv("DQ_SLICE_NO_TMA")) {
+            // TMA tiles, three buffers per SM (k_slice_rx_tma); the map is a kernel parameter, nothing to keep alive
+            CUtensorMap map;
+            TmaGeom geom;
+            if (make_tile_map(h, L, psi_dev, &map, &geom)) {
+                static bool attr_done[64] = {false};
+                const size_t tsmem = (size_t)kTmaBufs * (sizeof(double2) << kTileBits12) + 1024;
+                const int dev = ctx->device;
+                if (dev < 0 || dev >= 64 || !attr_done[dev]) {
+                    DQ_CUDA(cudaFuncSetAttribute(k_slice_rx_tma<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsmem));
+                    DQ_CUDA(cudaFuncSetAttribute(k_slice_rx_tma<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsmem));
+                    if (dev >= 0 && dev < 64) attr_done[dev] = true;
+                }
+                const unsigned tgrid = (unsigned)std::min<unsigned long long>(n_tiles, (unsigned long long)ctx->prop.multiProcessorCount);
+                if (h.scaled) k_slice_rx_tma<true><<<tgrid, kTmaThreads, tsmem, ctx->stream>>>(map, L, d, geom);
+                else k_slice_rx_tma<false><<<tgrid, kTmaThreads, tsmem, ctx->stream>>>(map, L, d, geom);
+                ctx->launches++;
+                DQ_CUDA(cudaGetLastError());
+                continue;
+            }
+        }
         if (with_phase) {
             if (h.scaled) k_slice_rx_tile<true, true, true><<<grid, kThreads, smem, ctx->stream>>>(psi, L, d, d_phase, high_bits);
             else k_slice_rx_tile<true, false, true><<<grid, kThreads, smem, ctx->stream>>>(psi, L, d, d_phase, high_bits);
