@@ -614,7 +614,21 @@ def run_distributed_state(a):
     t_start = time.time()
     l0 = st.ops.ctx.launch_count
     x0, b0 = st.exchanges, st.exchanged_bytes
-    for i in range(a.warmup + a.steps):
+    if R_.world == 1:
+        # nothing to exchange: the public call is evolve_rows, which chains the passes over the step boundaries
+        # (dq_slice_evolve_steps); warm-up and the timed steps are one call each
+        take = lambda k0, cnt: np.stack([rows[(k0 + j) % len(rows)] for j in range(cnt)])
+        st.evolve_rows(take(0, a.warmup))
+        st.ops.ctx.synchronize()
+        torch.cuda.synchronize(R_.dev)
+        t_start = time.time()
+        l0 = st.ops.ctx.launch_count
+        t0 = time.perf_counter()
+        st.evolve_rows(take(a.warmup, a.steps))
+        st.ops.ctx.synchronize()
+        torch.cuda.synchronize(R_.dev)
+        times.append(time.perf_counter() - t0)
+    for i in range(a.warmup + a.steps if R_.world > 1 else 0):
         if i == a.warmup:
             t_start = time.time()
             l0 = st.ops.ctx.launch_count
@@ -623,6 +637,10 @@ def run_distributed_state(a):
         R_.barrier()
         t0 = time.perf_counter()
         st.step(rows[k % len(rows)])
+        # the rotations a step leaves owed to the next step's first pass: every timed step but the last carries the ones of
+        # its predecessor, the last one also runs its own, so the K timed steps contain exactly the work of K steps
+        if i == a.warmup - 1 or i == a.warmup + a.steps - 1:
+            st.flush()
         st.ops.ctx.synchronize()
         torch.cuda.synchronize(R_.dev)
         dt = time.perf_counter() - t0
@@ -653,14 +671,16 @@ def run_distributed_state(a):
                        "l2": "slice (%.1f GiB) >> L2" % (slice_bytes / 2 ** 30)},
             "e2e": {"value": a.steps / t_tot, "unit": unit, "h2d_bytes_per_step": int(rows.shape[1] * 8), "d2h_bytes_per_step": 8,
                     "note": "the state lives on the devices by definition (64 GiB at n=32); per step the host sends one angle row; "
-                            "`value` and `e2e` are the same wall-clock measurement through DistributedState.step"},
+                            "`value` and `e2e` are the same wall-clock measurement through DistributedState.step (N > 1) / "
+                            "DistributedState.evolve_rows (N = 1)"},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "kernel": "k_slice_rx_tile / k_slice_phase_gray (whole step, exchange included)",
+            "roofline": {"bound": "hbm", "kernel": "k_slice_rx_tma (TMA tile passes: rotations, phase and the previous step's owed rotations on "
+                                                    "one tile; the pass that carries the exchange: k_slice_rx_tile) -- whole step, exchange included",
                          "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "peak_source": peak_src, "traffic": None,
                          "alg_bytes_per_step_per_gpu": 2 * slice_bytes,
                          "passes_per_step": passes, "launches_per_step": launches / max(1, a.steps),
                          "per_pass_GBs": (launches / max(1, a.steps)) * ach,
-                         "per_pass_note": "every launch of a step is one read + write of the slice (phase pass, rotation passes): "
+                         "per_pass_note": "every launch of a step is one read + write of the slice: "
                                           "per-pass rate = launches per step x the per-step figure; an exchange lowers it",
                          "exchange_GB_per_step_per_gpu": exch_bytes / 1e9,
                          "exchange_GBs_per_gpu": (exch_bytes / (exch_ms * 1e-3) / 1e9) if exch_ms else None,

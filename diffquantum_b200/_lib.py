@@ -73,6 +73,12 @@ SIGNATURES = {
     "dq_slice_rx_many_scatter": (ctypes.c_int, [_VP, _VP, ctypes.c_int, ctypes.c_int, _VP, _VP, ctypes.c_int, ctypes.c_int, _VP]),
     "dq_slice_phase_rx_many_scatter": (ctypes.c_int, [_VP, _VP, ctypes.c_int, ctypes.c_uint64, ctypes.c_int, ctypes.c_int, _VP, _VP,
                                                       ctypes.c_int, _VP, _VP, ctypes.c_int, ctypes.c_int, _VP]),
+    "dq_slice_step": (ctypes.c_int, [_VP, _VP, ctypes.c_int, ctypes.c_uint64, ctypes.c_int, ctypes.c_int, _VP, _VP,
+                                     ctypes.c_int, _VP, _VP, ctypes.c_int, _VP, _VP]),
+    "dq_slice_step_scatter": (ctypes.c_int, [_VP, _VP, ctypes.c_int, ctypes.c_uint64, ctypes.c_int, ctypes.c_int, _VP, _VP,
+                                             ctypes.c_int, _VP, _VP, ctypes.c_int, _VP, _VP, ctypes.c_int, ctypes.c_int, _VP]),
+    "dq_slice_evolve_steps": (ctypes.c_int, [_VP, _VP, ctypes.c_int, ctypes.c_uint64, ctypes.c_int, ctypes.c_int, _VP,
+                                             ctypes.c_int, _VP, ctypes.c_int, _VP, ctypes.c_int64, _VP, ctypes.c_int64]),
     "dq_ipc_export": (ctypes.c_int, [_VP, _VP, _VP, ctypes.POINTER(ctypes.c_uint64)]),
     "dq_ipc_open": (ctypes.c_int, [_VP, _VP, ctypes.c_uint64, ctypes.POINTER(_VP)]),
     "dq_ipc_close": (ctypes.c_int, [_VP, _VP, ctypes.c_uint64]),

@@ -78,6 +78,7 @@ struct dq_context {
     int dense_small_mma = 1;               // dense resident engine: shifted kets of a sample on the FP64 tensor cores (k_small_mma)
     void* slice_partials = nullptr;        // slice.cu: per-block energy partials (1024 doubles)
     unsigned slice_cursor = 0;
+    bool slice_tma_attr = false;           // slice.cu: dynamic shared-memory attribute of the TMA tile kernels set on this device
     int device = 0;
     cudaStream_t stream = nullptr;
     cudaDeviceProp prop;

@@ -18,8 +18,8 @@ int check_rows(const dq_ising* p, const double* rows, int64_t n_rows, const char
 // the fused engines implement the product-formula step only; the exact step runs on the generic engine
 bool use_fused(const dq_ising* p) { return p->step_mode == 0 && p->engine >= 1 && !p->want_pairs && dq::fused_supported(p); }
 
-// n > 20 (the persistent pass engine plans 12 <= n <= 20): the product step runs on the fused slice kernels of slice.cu --
-// one Gray-code phase pass and ceil-ish(n / 12) rotation passes per step instead of n + 1 per-term kernels.
+// n > 20 (the persistent pass engine plans 12 <= n <= 20): the product step runs on the TMA tile passes of slice.cu, chained
+// over the step boundaries -- one pass per step at n = 21, two at n <= 30 -- instead of n + 1 per-term kernels.
 bool use_slice_passes(const dq_ising* p) { return p->step_mode == 0 && p->engine >= 1 && !p->want_pairs && p->n > 20; }
 
 // One product-formula step sequence on ONE state of n qubits held whole on this device (L = n, no high bits).
@@ -27,12 +27,9 @@ int slice_evolve(dq_ising* p, c128* psi, const double* h_rows, int n_steps) {
     std::vector<int32_t> pair_bits(2 * (size_t)std::max(1, p->n_zz)), xbits(p->n);
     for (int e = 0; e < p->n_zz; ++e) { pair_bits[2 * e] = p->pa[e]; pair_bits[2 * e + 1] = p->pb[e]; }
     for (int q = 0; q < p->n; ++q) xbits[q] = p->bitpos[q];
-    for (int k = 0; k < n_steps; ++k) {
-        const double* row = h_rows + (size_t)k * p->row_len;
-        DQ_TRY(dq_slice_phase_rx_many(p->ctx, psi, p->n, 0, p->n, p->n_zz, pair_bits.data(), row, p->n, xbits.data(),
-                                      row + 1 + p->n_zz));
-    }
-    return DQ_OK;
+    // chained passes: (tile sets - 1) read + writes of the state per step (dq_slice_evolve_steps)
+    return dq_slice_evolve_steps(p->ctx, psi, p->n, 0, p->n, p->n_zz, pair_bits.data(), p->n, xbits.data(), n_steps, h_rows,
+                                 p->row_len, h_rows + 1 + p->n_zz, p->row_len);
 }
 
 // Batched gradient samples for n > 20: per sample the prefix state, then the 2 n_shift shifted kets in chunks that fit the

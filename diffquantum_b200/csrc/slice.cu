@@ -18,6 +18,7 @@ constexpr int kThreads = 256;
 constexpr int kMaxPairs = 256;
 constexpr int kMaxPeers = 16;
 constexpr int kTileBits12 = 12;                     // the TMA tile kernel: always 2^12 amplitudes (64 KiB)
+constexpr unsigned kRingSlots = 256;                // device argument tables in flight (ctx->slice_ring)
 
 struct PhaseArgs {
     int n_zz;
@@ -130,6 +131,12 @@ struct TileArgs {
     // diffquantum_b200/distributed.py written straight into the peers' receive buffers over NVLink.  scatter_g = 0: in place.
     int scatter_g, scatter_rank;
     double2* peer[kMaxPeers];
+    // rotations applied BEFORE the phase (k_slice_rx_tma with PHASE only): the rotations of the PREVIOUS step on this tile's
+    // bits, so that a pass reads  [rotations of step p] [phase of step p+1] [rotations of step p+1]  and a step costs one
+    // pass less; scaled form: their cosines are part of `post`
+    int n_pre;
+    unsigned char pre_active[12];
+    double pre_c[12], pre_s[12];
 };
 
 // exp(-i theta X) on a pair.  SCALED: a' = a - i tan(theta) b (one FMA per real component, the cosines are applied once per
@@ -157,13 +164,14 @@ __device__ __forceinline__ int tslot(int e) { return e ^ ((e >> 3) & 7); }
 __device__ __forceinline__ void team_bar(int bar) { asm volatile("bar.sync %0, %1;" ::"r"(bar), "n"(kThreads) : "memory"); }
 
 template <bool SCALED>
-__device__ __forceinline__ void tile_rounds(double2* __restrict__ tile, const TileArgs& A, const int tid, const int bar, const double pre) {
-    const int n_el = 1 << A.T;
+__device__ __forceinline__ void tile_rounds(double2* __restrict__ tile, const int T, const int n_active, const unsigned char* active,
+                                            const double* rc, const double* rs, const int tid, const int bar, const double pre) {
+    const int n_el = 1 << T;
     bool first = pre != 1.0;
     int k = 0;
-    for (; k + 2 < A.n_active; k += 3) {                // three bits per round trip (A.active is ascending)
-        const int i0 = A.active[k], i1 = A.active[k + 1], i2 = A.active[k + 2];
-        const double c0 = A.c[k], s0 = A.s[k], c1 = A.c[k + 1], s1 = A.s[k + 1], c2 = A.c[k + 2], s2 = A.s[k + 2];
+    for (; k + 2 < n_active; k += 3) {                  // three bits per round trip (`active` is ascending)
+        const int i0 = active[k], i1 = active[k + 1], i2 = active[k + 2];
+        const double c0 = rc[k], s0 = rs[k], c1 = rc[k + 1], s1 = rs[k + 1], c2 = rc[k + 2], s2 = rs[k + 2];
         for (int q = tid; q < (n_el >> 3); q += kThreads) {
             int e = ((q >> i0) << (i0 + 1)) | (q & ((1 << i0) - 1));
             e = ((e >> i1) << (i1 + 1)) | (e & ((1 << i1) - 1));
@@ -191,10 +199,10 @@ __device__ __forceinline__ void tile_rounds(double2* __restrict__ tile, const Ti
         first = false;
         team_bar(bar);
     }
-    for (; k + 1 < A.n_active; k += 2) {                // two bits per round trip
-        const int i0 = min(A.active[k], A.active[k + 1]), i1 = max(A.active[k], A.active[k + 1]);
-        const double c0 = A.active[k] == i0 ? A.c[k] : A.c[k + 1], s0 = A.active[k] == i0 ? A.s[k] : A.s[k + 1];
-        const double c1 = A.active[k] == i0 ? A.c[k + 1] : A.c[k], s1 = A.active[k] == i0 ? A.s[k + 1] : A.s[k];
+    for (; k + 1 < n_active; k += 2) {                  // two bits per round trip
+        const int i0 = min(active[k], active[k + 1]), i1 = max(active[k], active[k + 1]);
+        const double c0 = active[k] == i0 ? rc[k] : rc[k + 1], s0 = active[k] == i0 ? rs[k] : rs[k + 1];
+        const double c1 = active[k] == i0 ? rc[k + 1] : rc[k], s1 = active[k] == i0 ? rs[k + 1] : rs[k];
         for (int q = tid; q < (n_el >> 2); q += kThreads) {
             int e = ((q >> i0) << (i0 + 1)) | (q & ((1 << i0) - 1));            // zero at bit i0
             e = ((e >> i1) << (i1 + 1)) | (e & ((1 << i1) - 1));                // zero at bit i1
@@ -213,9 +221,9 @@ __device__ __forceinline__ void tile_rounds(double2* __restrict__ tile, const Ti
         first = false;
         team_bar(bar);
     }
-    if (k < A.n_active) {
-        const int i0 = A.active[k];
-        const double c0 = A.c[k], s0 = A.s[k];
+    if (k < n_active) {
+        const int i0 = active[k];
+        const double c0 = rc[k], s0 = rs[k];
         for (int q = tid; q < (n_el >> 1); q += kThreads) {
             const int e = ((q >> i0) << (i0 + 1)) | (q & ((1 << i0) - 1));
             const int sa = tslot(e), sb = tslot(e | (1 << i0));
@@ -255,16 +263,27 @@ struct PhaseTile {                   // per tile (one per team): fields of the o
     double2 f_out[kWalkBits];
 };
 
-// once per CTA; t = 0 .. (at least 48) distinct threads; a barrier must follow.  has_ww must be 0 on entry.
-__device__ __forceinline__ void phase_setup(PhaseTabs& P, const PhaseArgs* __restrict__ pa, const int t) {
+// tile bit of physical bit `phys` (-1: the tile does not span it)
+__device__ __forceinline__ int tile_bit_of(const TileArgs& A, const int phys) {
+    int r = -1;
+    for (int i = 0; i < A.T; ++i) r = A.pos[i] == phys ? i : r;
+    return r;
+}
+
+// once per CTA; t = 0 .. (at least 48) distinct threads; a barrier must follow.  has_ww must be 0 on entry.  The tile (A.T = 12)
+// may span any physical bits: pair ends are classified by tile membership, in-tile ends are stored as TILE bits, outside ends
+// as PHYSICAL bits (they are read from the global index of the tile's element 0).
+__device__ __forceinline__ void phase_setup(PhaseTabs& P, const PhaseArgs* __restrict__ pa, const TileArgs& A, const int t) {
     const int n_zz = pa->n_zz;
     if (t < kTileBits) {
-        const int k = t;
+        const int k = t, pk = A.pos[k];
         int d = 0;
         for (int e = 0; e < n_zz; ++e) {
             const int a = pa->a[e], b = pa->b[e];
-            if ((a != k && b != k) || (a < kTileBits && b < kTileBits)) continue;
-            P.out_other[k][d] = (unsigned char)(a == k ? b : a);
+            if (a != pk && b != pk) continue;
+            const int o = a == pk ? b : a;
+            if (tile_bit_of(A, o) >= 0) continue;
+            P.out_other[k][d] = (unsigned char)o;
             P.out_ang[k][d] = pa->ang[e];
             ++d;
         }
@@ -273,23 +292,24 @@ __device__ __forceinline__ void phase_setup(PhaseTabs& P, const PhaseArgs* __res
         int d = 0, o = 0;
         for (int e = 0; e < n_zz; ++e) {
             const int a = pa->a[e], b = pa->b[e];
-            if (a < kTileBits && b < kTileBits) { P.in_a[d] = (unsigned char)a; P.in_b[d] = (unsigned char)b; P.in_ang[d] = pa->ang[e]; ++d; }
-            else if (a >= kTileBits && b >= kTileBits) { P.oo_a[o] = (unsigned char)a; P.oo_b[o] = (unsigned char)b; P.oo_ang[o] = pa->ang[e]; ++o; }
+            const int ta = tile_bit_of(A, a), tb = tile_bit_of(A, b);
+            if (ta >= 0 && tb >= 0) { P.in_a[d] = (unsigned char)ta; P.in_b[d] = (unsigned char)tb; P.in_ang[d] = pa->ang[e]; ++d; }
+            else if (ta < 0 && tb < 0) { P.oo_a[o] = (unsigned char)a; P.oo_b[o] = (unsigned char)b; P.oo_ang[o] = pa->ang[e]; ++o; }
         }
         P.in_n = d;
         P.oo_n = o;
         P.c0 = pa->c0;
     } else if (t < kTileBits + 1 + kWalkBits) {
-        const int j = t - kTileBits - 1, p = kWalkLo + j;
+        const int j = t - kTileBits - 1, p = A.pos[kWalkLo + j];
         int di = 0, dout = 0;
         for (int e = 0; e < n_zz; ++e) {
             const int a = pa->a[e], b = pa->b[e];
             if (a != p && b != p) continue;
-            const int o = a == p ? b : a;
-            if (o >= kWalkLo && o < kTileBits) continue;                 // walk-walk pair: ww[] below
+            const int o = a == p ? b : a, to = tile_bit_of(A, o);
+            if (to >= kWalkLo) continue;                                 // walk-walk pair: ww[] below
             double sn, cs;
             sincos(2.0 * pa->ang[e], &sn, &cs);
-            if (o < kWalkLo) { P.w_in_other[j][di] = (unsigned char)o; P.w_in_c2[j][di] = cs; P.w_in_s2[j][di] = sn; ++di; }
+            if (to >= 0) { P.w_in_other[j][di] = (unsigned char)to; P.w_in_c2[j][di] = cs; P.w_in_s2[j][di] = sn; ++di; }
             else { P.w_out_other[j][dout] = (unsigned char)o; P.w_out_c2[j][dout] = cs; P.w_out_s2[j][dout] = sn; ++dout; }
         }
         P.w_in_n[j] = di;
@@ -298,17 +318,17 @@ __device__ __forceinline__ void phase_setup(PhaseTabs& P, const PhaseArgs* __res
         const int kk = t - 32;
         double2 f = make_double2(1.0, 0.0);
         if (kk >= 1) {
-            const int j = __ffs(kk) - 1, p = kWalkLo + j;
+            const int j = __ffs(kk) - 1, p = A.pos[kWalkLo + j];
             const int before = (kk - 1) ^ ((kk - 1) >> 1);               // Gray code of the previous step = walk bits before this flip
             const bool zp_neg = ((before >> j) & 1) != 0;
             for (int e = 0; e < n_zz; ++e) {
                 const int a = pa->a[e], b = pa->b[e];
                 if (a != p && b != p) continue;
-                const int o = a == p ? b : a;
-                if (o < kWalkLo || o >= kTileBits) continue;
+                const int to = tile_bit_of(A, a == p ? b : a);
+                if (to < kWalkLo) continue;
                 double sn, cs;
                 sincos(2.0 * pa->ang[e], &sn, &cs);
-                const bool differ = (((before >> (o - kWalkLo)) & 1) != 0) != zp_neg;
+                const bool differ = (((before >> (to - kWalkLo)) & 1) != 0) != zp_neg;
                 const double s2 = differ ? -sn : sn;
                 f = make_double2(f.x * cs - f.y * s2, f.x * s2 + f.y * cs);
                 P.has_ww = 1;
@@ -342,7 +362,8 @@ __device__ __forceinline__ void phase_tile_setup(const PhaseTabs& P, PhaseTile& 
 }
 
 // per tile, every thread of the team (t = 0..255 = tile bits 0..7); the tile must have landed, Q must be complete
-__device__ __forceinline__ void phase_apply(const PhaseTabs& P, const PhaseTile& Q, double2* __restrict__ tile, const int t) {
+__device__ __forceinline__ void phase_apply(const PhaseTabs& P, const PhaseTile& Q, double2* __restrict__ tile, const int t,
+                                            const double scale = 1.0) {
     int e = t;                                                       // walk bits 8..11 start at 0
     double a = Q.c_tile;
 #pragma unroll
@@ -350,7 +371,7 @@ __device__ __forceinline__ void phase_apply(const PhaseTabs& P, const PhaseTile&
     for (int q = 0; q < P.in_n; ++q) a += (((e >> P.in_a[q]) ^ (e >> P.in_b[q])) & 1) ? -P.in_ang[q] : P.in_ang[q];
     double sn, cs;
     sincos(a, &sn, &cs);
-    double2 ph = make_double2(cs, -sn);                              // exp(-i a)
+    double2 ph = make_double2(cs * scale, -sn * scale);              // scale * exp(-i a)
     // flip factor of walk bit j for THIS thread and tile (z_p = +1 form): the outside pairs (f_out) times the pairs with
     // this thread's own bits -- constant over the walk, so the walk itself is one multiply per flip
     double2 F[kWalkBits];
@@ -394,13 +415,13 @@ __global__ void __launch_bounds__(kThreads, 3) k_slice_rx_tile(double2* __restri
     __shared__ PhaseTile PQ;
     if (threadIdx.x == 0) { A = *ta; PT[0].has_ww = 0; }
     __syncthreads();
-    if (PHASE) phase_setup(PT[0], pa, threadIdx.x);
+    if (PHASE) phase_setup(PT[0], pa, A, threadIdx.x);
     __syncthreads();
     const int T = A.T, lo = A.lo, n_el = 1 << T;
     const unsigned lowmask = (1u << lo) - 1u;
     const unsigned long long n_tiles = 1ull << (L - T);
-    // physical offset of the non-contiguous tile bits, tabulated once per CTA (at most 2^8 entries: lo >= 4 when T = 12)
-    __shared__ unsigned long long hi_off[256];
+    // physical offset of the non-contiguous tile bits, tabulated once per CTA (at most 2^9 entries: lo >= 3 when T = 12)
+    __shared__ unsigned long long hi_off[512];
     for (int v = threadIdx.x; v < (1 << (T - lo)); v += kThreads) {
         unsigned long long off = 0;
         for (int i = lo; i < T; ++i) off |= (unsigned long long)((v >> (i - lo)) & 1) << A.pos[i];
@@ -430,7 +451,7 @@ __global__ void __launch_bounds__(kThreads, 3) k_slice_rx_tile(double2* __restri
             phase_apply(PT[0], PQ, tile, threadIdx.x);
             __syncthreads();
         }
-        tile_rounds<SCALED>(tile, A, threadIdx.x, 0, 1.0);
+        tile_rounds<SCALED>(tile, A.T, A.n_active, A.active, A.c, A.s, threadIdx.x, 0, 1.0);
         for (int e = threadIdx.x; e < n_el; e += kThreads)
         {
             double2 v = tile[tslot(e)];
@@ -460,7 +481,7 @@ __global__ void __launch_bounds__(kThreads, 3) k_slice_rx_tile(double2* __restri
 constexpr int kTmaBufs = 3, kTmaTeams = 2, kTmaThreads = kTmaTeams * kThreads + 64;
 struct TmaGeom {
     int rank;                        // 2..5
-    int start[5], nbits[5];          // coordinate of dimension d >= 1: (base >> start[d]) & (2^nbits[d] - 1); dimension 0: 0
+    int start[5], nbits[5];          // coordinate of dimension d: (base >> start[d]) & (2^nbits[d] - 1) (dimension 0: x 16 doubles)
 };
 struct TmaShared {
     unsigned long long full[kTmaBufs], done[kTmaBufs], empty[kTmaBufs];
@@ -481,21 +502,26 @@ __device__ __forceinline__ void s_mbar_wait(unsigned long long* bar, unsigned pa
     } while (!ok);
 }
 __device__ __forceinline__ void tma_coords(const TmaGeom& g, unsigned long long base, int (&c)[5]) {
-    c[0] = 0;
+    // dimension 0: 128-byte rows (16 doubles); its coordinate carries the tile-index bits between bit 3 and the first run
+    c[0] = (int)(((base >> g.start[0]) & ((1ull << g.nbits[0]) - 1ull)) << 4);
 #pragma unroll
     for (int d = 1; d < 5; ++d) c[d] = d < g.rank ? (int)((base >> g.start[d]) & ((1ull << g.nbits[d]) - 1ull)) : 0;
 }
 
-template <bool SCALED>
+template <bool SCALED, bool PHASE>
 __global__ void __launch_bounds__(kTmaThreads, 1) k_slice_rx_tma(const __grid_constant__ CUtensorMap map, int L,
-                                                                 const TileArgs* __restrict__ ta, const TmaGeom geom) {
+                                                                 const TileArgs* __restrict__ ta, const TmaGeom geom,
+                                                                 const PhaseArgs* __restrict__ pa, unsigned long long high) {
     extern __shared__ __align__(16) unsigned char smem_dyn[];
     unsigned char* smem_raw = smem_dyn + ((1024u - (s_u32(smem_dyn) & 1023u)) & 1023u);      // swizzled TMA boxes: 1 KiB aligned
     double2* tiles = reinterpret_cast<double2*>(smem_raw);
     __shared__ __align__(16) TmaShared sh;
+    __shared__ PhaseTabs PT[1];                           // PHASE (contiguous tiles only): see k_slice_rx_tile
+    __shared__ PhaseTile PQ[kTmaTeams];
     constexpr unsigned kTileBytes = (unsigned)(sizeof(double2) << kTileBits12);
     if (threadIdx.x == 0) {
         sh.A = *ta;
+        if (PHASE) PT[0].has_ww = 0;
         for (int b = 0; b < kTmaBufs; ++b) {
             sh.seq[b] = ~0ull;
             asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(s_u32(&sh.full[b])), "r"(1) : "memory");
@@ -505,6 +531,10 @@ __global__ void __launch_bounds__(kTmaThreads, 1) k_slice_rx_tma(const __grid_co
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
+    if (PHASE) {
+        phase_setup(PT[0], pa, sh.A, threadIdx.x);
+        __syncthreads();
+    }
     const unsigned long long n_tiles = 1ull << (L - kTileBits12);
     const unsigned long long mine = blockIdx.x < n_tiles ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;   // tiles of this CTA
     const int wg = threadIdx.x / kThreads;
@@ -514,10 +544,27 @@ __global__ void __launch_bounds__(kTmaThreads, 1) k_slice_rx_tma(const __grid_co
         const double pre = SCALED ? sh.A.post : 1.0;
         for (unsigned long long k = (unsigned long long)wg; k < mine; k += kTmaTeams) {
             const int b = (int)(k % kTmaBufs);
+            double2* tile = tiles + ((size_t)b << kTileBits12);
+            if (PHASE) {
+                // per-tile constants while the tile is in flight: the tile's index deposited into the bits it does not span
+                unsigned long long base = 0, rest = blockIdx.x + k * gridDim.x;
+                const unsigned long long mask = sh.A.mask;
+                for (int p = 0; p < L; ++p)
+                    if (!((mask >> p) & 1ull)) { base |= (rest & 1ull) << p; rest >>= 1; }
+                phase_tile_setup(PT[0], PQ[wg], (high << L) | base, tid);
+                team_bar(1 + wg);
+            }
             do {
                 s_mbar_wait(&sh.full[b], (unsigned)((k / kTmaBufs) & 1ull));
             } while (sh.seq[b] != k);
-            tile_rounds<SCALED>(tiles + ((size_t)b << kTileBits12), sh.A, tid, 1 + wg, pre);
+            if (PHASE) {
+                // [rotations left over from the previous step] [phase] [this step's rotations]; the cosine product of both
+                // rotation sets rides on the phase
+                if (sh.A.n_pre) tile_rounds<SCALED>(tile, kTileBits12, sh.A.n_pre, sh.A.pre_active, sh.A.pre_c, sh.A.pre_s, tid, 1 + wg, 1.0);
+                phase_apply(PT[0], PQ[wg], tile, tid, pre);
+                team_bar(1 + wg);
+            }
+            tile_rounds<SCALED>(tile, kTileBits12, sh.A.n_active, sh.A.active, sh.A.c, sh.A.s, tid, 1 + wg, PHASE ? 1.0 : pre);
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // this thread's tile writes -> the bulk store
             asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(s_u32(&sh.done[b])) : "memory");
         }
@@ -684,9 +731,9 @@ int fill_args(PhaseArgs& h, int n_total, int n_zz, const int32_t* pair_bits, con
 
 int upload_args(dq_context* ctx, const PhaseArgs& h, PhaseArgs** d_out) {
     // a small ring so that consecutive asynchronous launches never share a table
-    if (!ctx->slice_ring) DQ_CUDA(cudaMalloc(&ctx->slice_ring, sizeof(PhaseArgs) * 64));
-    PhaseArgs* d = reinterpret_cast<PhaseArgs*>(ctx->slice_ring) + (ctx->slice_cursor++ & 63);
-    if ((ctx->slice_cursor & 63) == 0) DQ_CUDA(cudaStreamSynchronize(ctx->stream));      // ring wrapped: drain
+    if (!ctx->slice_ring) DQ_CUDA(cudaMalloc(&ctx->slice_ring, sizeof(PhaseArgs) * kRingSlots));
+    PhaseArgs* d = reinterpret_cast<PhaseArgs*>(ctx->slice_ring) + (ctx->slice_cursor++ % kRingSlots);
+    if ((ctx->slice_cursor % kRingSlots) == 0) DQ_CUDA(cudaStreamSynchronize(ctx->stream));      // ring wrapped: drain
     DQ_CUDA(cudaMemcpyAsync(d, &h, sizeof(PhaseArgs), cudaMemcpyHostToDevice, ctx->stream));
     *d_out = d;
     return DQ_OK;
@@ -713,8 +760,8 @@ bool build_gray(const PhaseArgs& h, int L, bool energy, GrayArgs& gh) {
 
 int upload_gray(dq_context* ctx, const GrayArgs& gh, GrayArgs** d_out) {
     static_assert(sizeof(GrayArgs) <= sizeof(PhaseArgs), "ring slot too small");
-    GrayArgs* dg = reinterpret_cast<GrayArgs*>(reinterpret_cast<PhaseArgs*>(ctx->slice_ring) + (ctx->slice_cursor++ & 63));
-    if ((ctx->slice_cursor & 63) == 0) DQ_CUDA(cudaStreamSynchronize(ctx->stream));
+    GrayArgs* dg = reinterpret_cast<GrayArgs*>(reinterpret_cast<PhaseArgs*>(ctx->slice_ring) + (ctx->slice_cursor++ % kRingSlots));
+    if ((ctx->slice_cursor % kRingSlots) == 0) DQ_CUDA(cudaStreamSynchronize(ctx->stream));
     DQ_CUDA(cudaMemcpyAsync(dg, &gh, sizeof(GrayArgs), cudaMemcpyHostToDevice, ctx->stream));
     *d_out = dg;
     return DQ_OK;
@@ -793,29 +840,102 @@ EncodeTiledFn slice_encode_fn() {
     return fn;
 }
 
-// Tensor view of a pass's tiles over the slice (see k_slice_rx_tma); false: not expressible with rank <= 5.
-bool make_tile_map(const TileArgs& h, int L, void* psi, CUtensorMap* map, TmaGeom* g) {
-    EncodeTiledFn enc = slice_encode_fn();
-    if (!enc || h.T != kTileBits12 || L < kTileBits12 || h.lo < 3) return false;
+struct Scatter { int g, rank; void* const* peer; };
+struct Rot { int bit; double theta; };
+
+// One tile geometry and the rotation targets it carries.  A tile is 2^T amplitudes spanned by T physical bits pos[0] < pos[1] < ...:
+// the `lo` lowest are bits 0 .. lo-1 (contiguous 16 * 2^lo byte runs in global memory), the others are targets.
+struct TileSet {
+    int T, lo;
+    unsigned char pos[12];
+    unsigned long long mask;
+    int n_targets;
+    int target[12];                 // physical bits, ascending; every one is a pos[]
+    bool contiguous() const { return lo == T; }
+    bool has(int bit) const {
+        for (int i = 0; i < n_targets; ++i)
+            if (target[i] == bit) return true;
+        return false;
+    }
+};
+
+int tile_bits_max() {               // 2^12 amplitudes (64 KiB) unless DQ_SLICE_TILE_BITS says otherwise (8..12; experiments)
+    static int tile_bits = 0;
+    if (!tile_bits) {
+        const char* env = getenv("DQ_SLICE_TILE_BITS");
+        const int v = env ? atoi(env) : 12;
+        tile_bits = (v >= 8 && v <= 12) ? v : 12;
+    }
+    return tile_bits;
+}
+
+// The tiles that cover the (ascending) target bits.  Every target below bit Tmax goes into ONE contiguous tile (bits 0 .. Tmax-1).
+// High targets: the tile is 2^Tmax amplitudes - `lo` contiguous low bits + the targets of the pass; the targets are split evenly
+// over the fewest passes that leave lo >= 3 (128-byte runs: one row of the TMA tile), so a pass with few targets gets long
+// contiguous runs instead of a small tile.
+std::vector<TileSet> plan_sets(int L, const std::vector<int>& bits) {
+    std::vector<TileSet> sets;
+    const int Tmax = std::min(tile_bits_max(), L);
+    static int min_lo = 0;
+    if (!min_lo) {
+        const char* env = getenv("DQ_SLICE_MIN_LO");
+        const int v = env ? atoi(env) : 3;
+        min_lo = (v >= 1 && v <= 8) ? v : 3;
+    }
+    size_t next = 0;
+    if (next < bits.size() && bits[next] < Tmax) {
+        TileSet S;
+        memset(&S, 0, sizeof(S));
+        S.T = S.lo = Tmax;
+        for (int i = 0; i < Tmax; ++i) S.pos[i] = (unsigned char)i;
+        while (next < bits.size() && bits[next] < Tmax) S.target[S.n_targets++] = bits[next++];
+        sets.push_back(S);
+    }
+    const int rest = (int)(bits.size() - next);
+    if (rest > 0) {
+        const int cap = std::max(1, Tmax - std::min(min_lo, Tmax - 1));
+        const int passes = (rest + cap - 1) / cap;
+        for (int k = 0; k < passes; ++k) {
+            const int cnt = rest / passes + (k < rest % passes ? 1 : 0);
+            TileSet S;
+            memset(&S, 0, sizeof(S));
+            S.lo = Tmax - cnt;
+            for (int i = 0; i < S.lo; ++i) S.pos[i] = (unsigned char)i;
+            S.T = S.lo;
+            for (int i = 0; i < cnt; ++i) {
+                S.pos[S.T++] = (unsigned char)bits[next];
+                S.target[S.n_targets++] = bits[next++];
+            }
+            sets.push_back(S);
+        }
+    }
+    for (auto& S : sets)
+        for (int i = 0; i < S.T; ++i) S.mask |= 1ull << S.pos[i];
+    return sets;
+}
+
+// Tensor view of a tile set over the slice (see k_slice_rx_tma); false: not expressible with rank <= 5 (or no driver entry).
+bool tile_geom(const TileSet& S, int L, TmaGeom* g, cuuint64_t* dims, cuuint64_t* strides, cuuint32_t* box) {
+    if (S.T != kTileBits12 || L < kTileBits12 || S.lo < 3) return false;
     // runs of consecutive tile bits above bit 2 (bits 0..2 are dimension 0), at most 8 bits each (box extent <= 256)
     int run_start[8], run_len[8], n_runs = 0;
-    for (int i = 3; i < h.T;) {
+    for (int i = 3; i < S.T;) {
         int len = 1;
-        while (i + len < h.T && h.pos[i + len] == h.pos[i] + len && len < 8) ++len;
+        while (i + len < S.T && S.pos[i + len] == S.pos[i] + len && len < 8) ++len;
         if (n_runs == 4) return false;
-        run_start[n_runs] = h.pos[i];
+        run_start[n_runs] = S.pos[i];
         run_len[n_runs] = len;
         ++n_runs;
         i += len;
     }
     if (n_runs == 0) return false;
-    cuuint64_t dims[5], strides[4];
-    cuuint32_t box[5], ones[5] = {1, 1, 1, 1, 1};
-    dims[0] = 16;                                                        // 8 amplitudes = 16 doubles = 128 bytes
+    // dimension 0: rows of 8 amplitudes = 16 doubles = 128 bytes (tile bits 0..2), spanning up to the first run: with lo = 3 the
+    // first run starts above bit 3 and the tile-index bits in between select the row
+    dims[0] = (cuuint64_t)16 << (run_start[0] - 3);
     box[0] = 16;
     g->rank = 1 + n_runs;
-    g->start[0] = 0;
-    g->nbits[0] = 0;
+    g->start[0] = 3;
+    g->nbits[0] = run_start[0] - 3;
     for (int r = 0; r < n_runs; ++r) {
         const int end = r + 1 < n_runs ? run_start[r + 1] : L;          // the dimension spans up to the next run
         dims[1 + r] = (cuuint64_t)1 << (end - run_start[r]);
@@ -825,36 +945,143 @@ bool make_tile_map(const TileArgs& h, int L, void* psi, CUtensorMap* map, TmaGeo
         g->nbits[1 + r] = end - run_start[r];
     }
     for (int d = g->rank; d < 5; ++d) { g->start[d] = 0; g->nbits[d] = 0; }
+    return true;
+}
+
+bool tma_usable(const TileSet& S, int L) {
+    TmaGeom g;
+    cuuint64_t dims[5], strides[4];
+    cuuint32_t box[5];
+    return !getenv("DQ_SLICE_NO_TMA") && slice_encode_fn() && tile_geom(S, L, &g, dims, strides, box);
+}
+
+bool make_tile_map(const TileSet& S, int L, void* psi, CUtensorMap* map, TmaGeom* g) {
+    EncodeTiledFn enc = slice_encode_fn();
+    cuuint64_t dims[5], strides[4];
+    cuuint32_t box[5], ones[5] = {1, 1, 1, 1, 1};
+    if (!enc || !tile_geom(S, L, g, dims, strides, box)) return false;
     return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, (cuuint32_t)g->rank, psi, dims, strides, box, ones, CU_TENSOR_MAP_INTERLEAVE_NONE,
                CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-struct Scatter { int g, rank; void* const* peer; };
+// Do the kernels' phase tables hold this pair list for this tile?  (12-bit tiles only; every tile bit at most kGrayDeg pairs,
+// at most kMaxIn pairs inside the tile.)
+bool phase_fits(const PhaseArgs& h, const TileSet& S) {
+    if (S.T != kTileBits) return false;
+    int n_in = 0, deg[kTileBits] = {0};
+    for (int e = 0; e < h.n_zz; ++e) {
+        int ta = -1, tb = -1;
+        for (int i = 0; i < S.T; ++i) {
+            if (S.pos[i] == h.a[e]) ta = i;
+            if (S.pos[i] == h.b[e]) tb = i;
+        }
+        if (ta >= 0) ++deg[ta];
+        if (tb >= 0) ++deg[tb];
+        n_in += (ta >= 0 && tb >= 0) ? 1 : 0;
+    }
+    for (int k = 0; k < kTileBits; ++k)
+        if (deg[k] > kGrayDeg) return false;
+    return n_in <= kMaxIn;
+}
 
-int rx_many_impl(dq_context* ctx, void* psi_dev, int L, int count, const int32_t* bits, const double* thetas,
-                 const PhaseArgs* d_phase, unsigned long long high_bits, bool* phase_done, const Scatter* scatter = nullptr) {
-    if (phase_done) *phase_done = false;
-    DQ_REQUIRE(ctx && psi_dev && (count == 0 || (bits && thetas)), "NULL argument");
-    DQ_REQUIRE(L >= 1 && L <= 33 && count >= 0 && count <= L, "dq_slice_rx_many: L=%d count=%d", L, count);
-    DQ_TRY(ctx->set_device());
-    std::vector<std::pair<int, double>> tg(count);
-    unsigned long long seen = 0;
-    for (int i = 0; i < count; ++i) {
-        DQ_REQUIRE(bits[i] >= 0 && bits[i] < L, "dq_slice_rx_many: bit %d is not local (L=%d)", bits[i], L);
-        DQ_REQUIRE(!((seen >> bits[i]) & 1ull), "dq_slice_rx_many: bit %d listed twice", bits[i]);
-        DQ_REQUIRE(isfinite(thetas[i]), "dq_slice_rx_many: non-finite angle");
-        seen |= 1ull << bits[i];
-        tg[i] = {bits[i], thetas[i]};
+// Can launch_pass carry the phase (and, with `pre`, the previous step's rotations) on this set?  A scatter pass runs on the
+// cp.async kernel, which knows the phase for the contiguous tile only and no pre-rotations.
+bool can_carry_phase(const PhaseArgs& h, const TileSet& S, int L, bool pre, bool scatter) {
+    if (!phase_fits(h, S)) return false;
+    if (!scatter && tma_usable(S, L)) return true;
+    return !pre && S.contiguous() && !getenv("DQ_SLICE_NO_PHASE_FUSION");
+}
+
+// ONE pass over the slice: [pre: rotations left over from the previous step] [the diagonal phase, d_phase != NULL] [rot], all
+// on the bits of tile set S (rot / pre ascending in their bit, every bit a target of S); sc: the stores of this pass are the
+// exchange.  Callers make sure the combination is supported (can_carry_phase).
+int launch_pass(dq_context* ctx, void* psi_dev, int L, const TileSet& S, const std::vector<Rot>& rot, const std::vector<Rot>& pre,
+                const PhaseArgs* d_phase, unsigned long long high_bits, const Scatter* sc) {
+    TileArgs h;
+    memset(&h, 0, sizeof(h));
+    h.T = S.T;
+    h.lo = S.lo;
+    h.mask = S.mask;
+    memcpy(h.pos, S.pos, sizeof(h.pos));
+    auto tile_bit = [&](int bit) {
+        for (int i = 0; i < S.T; ++i)
+            if (S.pos[i] == bit) return i;
+        return -1;
+    };
+    for (const Rot& r : rot) {
+        const int tb = tile_bit(r.bit);
+        DQ_REQUIRE(tb >= 0 && h.n_active < 12, "slice pass: internal error: bit %d is not in the tile", r.bit);
+        h.active[h.n_active] = (unsigned char)tb;
+        h.c[h.n_active] = cos(r.theta);
+        h.s[h.n_active] = sin(r.theta);
+        ++h.n_active;
     }
-    std::sort(tg.begin(), tg.end());
-    // tile size: 2^12 amplitudes (64 KiB, 3 CTAs per SM) unless DQ_SLICE_TILE_BITS says otherwise (8..12; experiments)
-    static int tile_bits = 0;
-    if (!tile_bits) {
-        const char* env = getenv("DQ_SLICE_TILE_BITS");
-        const int v = env ? atoi(env) : 12;
-        tile_bits = (v >= 8 && v <= 12) ? v : 12;
+    for (const Rot& r : pre) {
+        const int tb = tile_bit(r.bit);
+        DQ_REQUIRE(tb >= 0 && h.n_pre < 12, "slice pass: internal error: bit %d is not in the tile", r.bit);
+        h.pre_active[h.n_pre] = (unsigned char)tb;
+        h.pre_c[h.n_pre] = cos(r.theta);
+        h.pre_s[h.n_pre] = sin(r.theta);
+        ++h.n_pre;
     }
-    const int Tmax = std::min(tile_bits, L);
+    if (sc) {
+        h.scatter_g = sc->g;
+        h.scatter_rank = sc->rank;
+        for (int j = 0; j < (1 << sc->g); ++j) h.peer[j] = (double2*)sc->peer[j];
+    }
+    // scaled form unless a rotation angle sits close to pi/2 (|tan| large: the cosine product would lose digits)
+    h.scaled = 1;
+    h.post = 1.0;
+    for (int k = 0; k < h.n_active; ++k)
+        if (fabs(h.c[k]) < 0.05) h.scaled = 0;
+    for (int k = 0; k < h.n_pre; ++k)
+        if (fabs(h.pre_c[k]) < 0.05) h.scaled = 0;
+    if (h.scaled) {
+        for (int k = 0; k < h.n_active; ++k) {
+            h.post *= h.c[k];
+            h.s[k] = h.s[k] / h.c[k];
+            h.c[k] = 1.0;
+        }
+        for (int k = 0; k < h.n_pre; ++k) {
+            h.post *= h.pre_c[k];
+            h.pre_s[k] = h.pre_s[k] / h.pre_c[k];
+            h.pre_c[k] = 1.0;
+        }
+    }
+    if (!ctx->slice_ring) DQ_CUDA(cudaMalloc(&ctx->slice_ring, sizeof(PhaseArgs) * kRingSlots));
+    static_assert(sizeof(TileArgs) <= sizeof(PhaseArgs), "ring slot too small");
+    TileArgs* d = reinterpret_cast<TileArgs*>(reinterpret_cast<PhaseArgs*>(ctx->slice_ring) + (ctx->slice_cursor++ % kRingSlots));
+    if ((ctx->slice_cursor % kRingSlots) == 0) DQ_CUDA(cudaStreamSynchronize(ctx->stream));
+    DQ_CUDA(cudaMemcpyAsync(d, &h, sizeof(TileArgs), cudaMemcpyHostToDevice, ctx->stream));
+    const unsigned long long n_tiles = 1ull << (L - h.T);
+    double2* psi = (double2*)psi_dev;
+    if (!sc && !getenv("DQ_SLICE_NO_TMA")) {
+        // TMA tiles, three buffers per SM (k_slice_rx_tma); the map is a kernel parameter, nothing to keep alive
+        CUtensorMap map;
+        TmaGeom geom;
+        if (make_tile_map(S, L, psi_dev, &map, &geom)) {
+            const size_t tsmem = (size_t)kTmaBufs * (sizeof(double2) << kTileBits12) + 1024;
+            if (!ctx->slice_tma_attr) {         // per device (a context is one device)
+                DQ_CUDA(cudaFuncSetAttribute(k_slice_rx_tma<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsmem));
+                DQ_CUDA(cudaFuncSetAttribute(k_slice_rx_tma<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsmem));
+                DQ_CUDA(cudaFuncSetAttribute(k_slice_rx_tma<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsmem));
+                DQ_CUDA(cudaFuncSetAttribute(k_slice_rx_tma<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsmem));
+                ctx->slice_tma_attr = true;
+            }
+            const unsigned tgrid = (unsigned)std::min<unsigned long long>(n_tiles, (unsigned long long)ctx->prop.multiProcessorCount);
+            if (d_phase) {
+                if (h.scaled) k_slice_rx_tma<true, true><<<tgrid, kTmaThreads, tsmem, ctx->stream>>>(map, L, d, geom, d_phase, high_bits);
+                else k_slice_rx_tma<false, true><<<tgrid, kTmaThreads, tsmem, ctx->stream>>>(map, L, d, geom, d_phase, high_bits);
+            }
+            else if (h.scaled) k_slice_rx_tma<true, false><<<tgrid, kTmaThreads, tsmem, ctx->stream>>>(map, L, d, geom, nullptr, 0);
+            else k_slice_rx_tma<false, false><<<tgrid, kTmaThreads, tsmem, ctx->stream>>>(map, L, d, geom, nullptr, 0);
+            ctx->launches++;
+            DQ_CUDA(cudaGetLastError());
+            return DQ_OK;
+        }
+    }
+    DQ_REQUIRE(pre.empty() && (!d_phase || (S.contiguous() && S.T == kTileBits)),
+               "slice pass: internal error: this pass needs the TMA tile kernel (T=%d lo=%d)", S.T, S.lo);
     {   // the attribute is per device and cheap to set: no process-wide "done" flag (two contexts, two devices)
         const int max_smem = (int)(sizeof(double2) << 12);
         DQ_CUDA(cudaFuncSetAttribute(k_slice_rx_tile<true, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
@@ -864,108 +1091,105 @@ int rx_many_impl(dq_context* ctx, void* psi_dev, int L, int count, const int32_t
         DQ_CUDA(cudaFuncSetAttribute(k_slice_rx_tile<true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
         DQ_CUDA(cudaFuncSetAttribute(k_slice_rx_tile<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
     }
-    // The contiguous pass takes every target below bit 12 whether or not it carries the phase.  (Measured at n = 24: the phase
-    // adds ~70 us to it -- 181 us against 109 us alone and 88 us for the phase as its own pass, the tile kernel being bound by
-    // instruction issue and shared-memory latency rather than HBM -- and moving targets 8..11 to the high-bit passes to
-    // balance the three passes made the step slower, 386 us against 371 us: every tile pass pays a fixed load/store latency.)
-    const int contig_take = Tmax;
-    size_t next = 0;
-    while (next < tg.size()) {
-        TileArgs h;
-        memset(&h, 0, sizeof(h));
-        if (tg[next].first < contig_take) {                 // pass over the contiguous tile bits [0, Tmax)
-            h.T = Tmax;
-            h.lo = Tmax;
-            for (int i = 0; i < Tmax; ++i) h.pos[i] = (unsigned char)i;
-            while (next < tg.size() && tg[next].first < contig_take) {
-                h.active[h.n_active] = (unsigned char)tg[next].first;
-                h.c[h.n_active] = cos(tg[next].second);
-                h.s[h.n_active] = sin(tg[next].second);
-                ++h.n_active;
-                ++next;
-            }
-        } else {
-            // High targets: the tile is always 2^Tmax amplitudes - `lo` contiguous low bits (16 * 2^lo byte runs in global
-            // memory) + the targets of this pass; the remaining targets are split evenly over the fewest passes that
-            // leave lo >= 4, so a pass with few targets gets long contiguous runs instead of a small tile.
-            const int rest = (int)(tg.size() - next), cap = std::max(1, Tmax - std::min(4, Tmax - 1));
-            const int passes = (rest + cap - 1) / cap, cnt = (rest + passes - 1) / passes;
-            const int lo = Tmax - cnt;
-            h.lo = lo;
-            for (int i = 0; i < lo; ++i) h.pos[i] = (unsigned char)i;
-            int T = lo;
-            for (int k = 0; k < cnt && next < tg.size(); ++k) {
-                h.pos[T] = (unsigned char)tg[next].first;
-                h.active[h.n_active] = (unsigned char)T;
-                h.c[h.n_active] = cos(tg[next].second);
-                h.s[h.n_active] = sin(tg[next].second);
-                ++h.n_active;
-                ++T;
-                ++next;
-            }
-            h.T = T;
-        }
-        for (int i = 0; i < h.T; ++i) h.mask |= 1ull << h.pos[i];
-        if (scatter && next >= tg.size()) {                 // the last pass of the step carries the exchange
-            h.scatter_g = scatter->g;
-            h.scatter_rank = scatter->rank;
-            for (int j = 0; j < (1 << scatter->g); ++j) h.peer[j] = (double2*)scatter->peer[j];
-        }
-        // scaled form unless a rotation angle sits close to pi/2 (|tan| large: the cosine product would lose digits)
-        h.scaled = 1;
-        h.post = 1.0;
-        for (int k = 0; k < h.n_active; ++k)
-            if (fabs(h.c[k]) < 0.05) h.scaled = 0;
-        if (h.scaled)
-            for (int k = 0; k < h.n_active; ++k) {
-                h.post *= h.c[k];
-                h.s[k] = h.s[k] / h.c[k];
-                h.c[k] = 1.0;
-            }
-        if (!ctx->slice_ring) DQ_CUDA(cudaMalloc(&ctx->slice_ring, sizeof(PhaseArgs) * 64));
-        static_assert(sizeof(TileArgs) <= sizeof(PhaseArgs), "ring slot too small");
-        TileArgs* d = reinterpret_cast<TileArgs*>(reinterpret_cast<PhaseArgs*>(ctx->slice_ring) + (ctx->slice_cursor++ & 63));
-        if ((ctx->slice_cursor & 63) == 0) DQ_CUDA(cudaStreamSynchronize(ctx->stream));
-        DQ_CUDA(cudaMemcpyAsync(d, &h, sizeof(TileArgs), cudaMemcpyHostToDevice, ctx->stream));
-        const unsigned long long n_tiles = 1ull << (L - h.T);
-        const size_t smem = sizeof(double2) << h.T;
-        const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, ((size_t)200 << 10) / std::max<size_t>(smem, 1)));
-        const unsigned grid = (unsigned)std::min<unsigned long long>(n_tiles, (unsigned long long)ctx->prop.multiProcessorCount * per_sm);
-        double2* psi = (double2*)psi_dev;
-        const bool with_phase = d_phase && phase_done && !*phase_done && h.lo == h.T && h.T == kWalkLo + kWalkBits;
-        if (!with_phase && !h.scatter_g && !getenv("DQ_SLICE_NO_TMA")) {
-            // TMA tiles, three buffers per SM (k_slice_rx_tma); the map is a kernel parameter, nothing to keep alive
-            CUtensorMap map;
-            TmaGeom geom;
-            if (make_tile_map(h, L, psi_dev, &map, &geom)) {
-                static bool attr_done[64] = {false};
-                const size_t tsmem = (size_t)kTmaBufs * (sizeof(double2) << kTileBits12) + 1024;
-                const int dev = ctx->device;
-                if (dev < 0 || dev >= 64 || !attr_done[dev]) {
-                    DQ_CUDA(cudaFuncSetAttribute(k_slice_rx_tma<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsmem));
-                    DQ_CUDA(cudaFuncSetAttribute(k_slice_rx_tma<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsmem));
-                    if (dev >= 0 && dev < 64) attr_done[dev] = true;
-                }
-                const unsigned tgrid = (unsigned)std::min<unsigned long long>(n_tiles, (unsigned long long)ctx->prop.multiProcessorCount);
-                if (h.scaled) k_slice_rx_tma<true><<<tgrid, kTmaThreads, tsmem, ctx->stream>>>(map, L, d, geom);
-                else k_slice_rx_tma<false><<<tgrid, kTmaThreads, tsmem, ctx->stream>>>(map, L, d, geom);
-                ctx->launches++;
-                DQ_CUDA(cudaGetLastError());
-                continue;
-            }
-        }
-        if (with_phase) {
-            if (h.scaled) k_slice_rx_tile<true, true, true><<<grid, kThreads, smem, ctx->stream>>>(psi, L, d, d_phase, high_bits);
-            else k_slice_rx_tile<true, false, true><<<grid, kThreads, smem, ctx->stream>>>(psi, L, d, d_phase, high_bits);
-            *phase_done = true;
-        }
-        else if (h.lo == h.T && h.scaled) k_slice_rx_tile<true, true, false><<<grid, kThreads, smem, ctx->stream>>>(psi, L, d, nullptr, 0);
-        else if (h.lo == h.T) k_slice_rx_tile<true, false, false><<<grid, kThreads, smem, ctx->stream>>>(psi, L, d, nullptr, 0);
-        else if (h.scaled) k_slice_rx_tile<false, true, false><<<grid, kThreads, smem, ctx->stream>>>(psi, L, d, nullptr, 0);
-        else k_slice_rx_tile<false, false, false><<<grid, kThreads, smem, ctx->stream>>>(psi, L, d, nullptr, 0);
-        ctx->launches++;
-        DQ_CUDA(cudaGetLastError());
+    const size_t smem = sizeof(double2) << h.T;
+    const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, ((size_t)200 << 10) / std::max<size_t>(smem, 1)));
+    const unsigned grid = (unsigned)std::min<unsigned long long>(n_tiles, (unsigned long long)ctx->prop.multiProcessorCount * per_sm);
+    if (d_phase) {
+        if (h.scaled) k_slice_rx_tile<true, true, true><<<grid, kThreads, smem, ctx->stream>>>(psi, L, d, d_phase, high_bits);
+        else k_slice_rx_tile<true, false, true><<<grid, kThreads, smem, ctx->stream>>>(psi, L, d, d_phase, high_bits);
     }
+    else if (S.contiguous() && h.scaled) k_slice_rx_tile<true, true, false><<<grid, kThreads, smem, ctx->stream>>>(psi, L, d, nullptr, 0);
+    else if (S.contiguous()) k_slice_rx_tile<true, false, false><<<grid, kThreads, smem, ctx->stream>>>(psi, L, d, nullptr, 0);
+    else if (h.scaled) k_slice_rx_tile<false, true, false><<<grid, kThreads, smem, ctx->stream>>>(psi, L, d, nullptr, 0);
+    else k_slice_rx_tile<false, false, false><<<grid, kThreads, smem, ctx->stream>>>(psi, L, d, nullptr, 0);
+    ctx->launches++;
+    DQ_CUDA(cudaGetLastError());
+    return DQ_OK;
+}
+
+// (bit, theta) lists: validated, ascending in the bit
+int sorted_rots(const char* what, int L, int count, const int32_t* bits, const double* thetas, std::vector<Rot>& out) {
+    DQ_REQUIRE(count == 0 || (bits && thetas), "%s: NULL argument", what);
+    DQ_REQUIRE(count >= 0 && count <= L, "%s: L=%d count=%d", what, L, count);
+    out.resize(count);
+    unsigned long long seen = 0;
+    for (int i = 0; i < count; ++i) {
+        DQ_REQUIRE(bits[i] >= 0 && bits[i] < L, "%s: bit %d is not local (L=%d)", what, bits[i], L);
+        DQ_REQUIRE(!((seen >> bits[i]) & 1ull), "%s: bit %d listed twice", what, bits[i]);
+        DQ_REQUIRE(isfinite(thetas[i]), "%s: non-finite angle", what);
+        seen |= 1ull << bits[i];
+        out[i] = Rot{bits[i], thetas[i]};
+    }
+    std::sort(out.begin(), out.end(), [](const Rot& a, const Rot& b) { return a.bit < b.bit; });
+    return DQ_OK;
+}
+
+std::vector<Rot> rots_of(const TileSet& S, const std::vector<Rot>& all) {
+    std::vector<Rot> r;
+    for (const Rot& x : all)
+        if (S.has(x.bit)) r.push_back(x);
+    return r;
+}
+
+// All rotations of a step, every tile set one pass; sc: the last pass carries the exchange.
+int rx_many_impl(dq_context* ctx, void* psi_dev, int L, int count, const int32_t* bits, const double* thetas, const Scatter* sc = nullptr) {
+    DQ_REQUIRE(ctx && psi_dev, "NULL argument");
+    DQ_REQUIRE(L >= 1 && L <= 33, "dq_slice_rx_many: L=%d", L);
+    DQ_TRY(ctx->set_device());
+    std::vector<Rot> rot;
+    DQ_TRY(sorted_rots("dq_slice_rx_many", L, count, bits, thetas, rot));
+    std::vector<int> tb(rot.size());
+    for (size_t i = 0; i < rot.size(); ++i) tb[i] = rot[i].bit;
+    const std::vector<TileSet> sets = plan_sets(L, tb);
+    const std::vector<Rot> none;
+    for (size_t k = 0; k < sets.size(); ++k)
+        DQ_TRY(launch_pass(ctx, psi_dev, L, sets[k], rots_of(sets[k], rot), none, nullptr, 0, (sc && k + 1 == sets.size()) ? sc : nullptr));
+    return DQ_OK;
+}
+
+// One product-formula step on a slice:  [pre: rotations still owed to the previous step] [phase, angles != NULL] [rot] (+ the
+// exchange on the last pass).  `skip` >= 0: the rotations of tile set `skip` are NOT applied (the caller passes them as `pre`
+// of the next step); `first` >= 0: the tile set that must carry pre + phase (the caller has checked can_carry_phase).
+// Without `first` the function picks the set itself; when no set can carry the work the pieces run as separate passes.
+int step_impl(dq_context* ctx, void* psi_dev, int L, unsigned long long high_bits, const PhaseArgs* h_phase, const std::vector<Rot>& pre,
+              const std::vector<Rot>& rot, const std::vector<TileSet>& sets, int first, int skip, const Scatter* sc,
+              int n_total, int n_zz, const int32_t* pair_bits, const double* angles) {
+    const std::vector<Rot> none;
+    const bool only_set_scatters = sc && sets.size() == 1;
+    bool pre_fused = !pre.empty();
+    if (first < 0 && h_phase && !pre.empty()) {                   // the set that holds every pre bit among its targets
+        for (size_t k = 0; k < sets.size() && first < 0; ++k) {
+            bool all = true;
+            for (const Rot& r : pre) all = all && sets[k].has(r.bit);
+            if (all && (int)k != skip && can_carry_phase(*h_phase, sets[k], L, true, only_set_scatters)) first = (int)k;
+        }
+    }
+    if (first < 0 && !pre.empty()) {                              // no such set: the owed rotations as passes of their own
+        std::vector<int32_t> pb(pre.size());
+        std::vector<double> pt(pre.size());
+        for (size_t i = 0; i < pre.size(); ++i) { pb[i] = pre[i].bit; pt[i] = pre[i].theta; }
+        DQ_TRY(rx_many_impl(ctx, psi_dev, L, (int)pre.size(), pb.data(), pt.data()));
+        pre_fused = false;
+    }
+    if (first < 0 && h_phase) {
+        for (size_t k = 0; k < sets.size() && first < 0; ++k)
+            if ((int)k != skip && can_carry_phase(*h_phase, sets[k], L, false, only_set_scatters)) first = (int)k;
+    }
+    if (first < 0 && h_phase) DQ_TRY(dq_slice_phase(ctx, psi_dev, L, high_bits, n_total, n_zz, pair_bits, angles));
+    PhaseArgs* d_phase = nullptr;
+    if (first >= 0 && h_phase) DQ_TRY(upload_args(ctx, *h_phase, &d_phase));
+    // launch order: `first`, then the others; the last one launched carries the exchange
+    std::vector<int> order;
+    if (first >= 0) order.push_back(first);
+    for (size_t k = 0; k < sets.size(); ++k)
+        if ((int)k != first && (int)k != skip) order.push_back((int)k);
+    for (size_t i = 0; i < order.size(); ++i) {
+        const int k = order[i];
+        const bool lead = k == first;
+        DQ_TRY(launch_pass(ctx, psi_dev, L, sets[k], rots_of(sets[k], rot), (lead && pre_fused) ? pre : none, lead ? d_phase : nullptr, high_bits,
+                           (sc && i + 1 == order.size()) ? sc : nullptr));
+    }
+    DQ_REQUIRE(!sc || !order.empty(), "slice step: needs at least one rotation to carry the exchange");
     return DQ_OK;
 }
 }  // namespace
@@ -973,7 +1197,7 @@ int rx_many_impl(dq_context* ctx, void* psi_dev, int L, int count, const int32_t
 extern "C" {
 
 int dq_slice_rx_many(dq_context* ctx, void* psi_dev, int L, int count, const int32_t* bits, const double* thetas) {
-    return rx_many_impl(ctx, psi_dev, L, count, bits, thetas, nullptr, 0, nullptr);
+    return rx_many_impl(ctx, psi_dev, L, count, bits, thetas);
 }
 
 int dq_slice_rx_many_scatter(dq_context* ctx, void* psi_dev, int L, int count, const int32_t* bits, const double* thetas,
@@ -983,7 +1207,7 @@ int dq_slice_rx_many_scatter(dq_context* ctx, void* psi_dev, int L, int count, c
     DQ_REQUIRE(count >= 1, "dq_slice_rx_many_scatter: needs at least one rotation to carry the exchange");
     for (int j = 0; j < (1 << g); ++j) DQ_REQUIRE(peer_recv[j] != nullptr, "dq_slice_rx_many_scatter: NULL receive buffer of rank %d", j);
     Scatter sc{g, rank, peer_recv};
-    return rx_many_impl(ctx, psi_dev, L, count, bits, thetas, nullptr, 0, nullptr, &sc);
+    return rx_many_impl(ctx, psi_dev, L, count, bits, thetas, &sc);
 }
 
 int dq_ipc_export(dq_context* ctx, void* dev_ptr, void* handle64_out, uint64_t* offset_out) {
@@ -1030,54 +1254,108 @@ int dq_ipc_close(dq_context* ctx, void* ptr, uint64_t offset) {
     return DQ_OK;
 }
 
-static int phase_rx_many(dq_context* ctx, void* psi_dev, int L, uint64_t high_bits, int n_total, int n_zz,
-                         const int32_t* pair_bits, const double* angles, int count, const int32_t* bits, const double* thetas,
-                         const Scatter* sc) {
+// pre-rotations (may be none), phase, rotations, exchange (may be none): see step_impl
+static int slice_step(const char* what, dq_context* ctx, void* psi_dev, int L, uint64_t high_bits, int n_total, int n_zz,
+                      const int32_t* pair_bits, const double* angles, int n_pre, const int32_t* pre_bits, const double* pre_thetas,
+                      int count, const int32_t* bits, const double* thetas, const Scatter* sc) {
     DQ_REQUIRE(ctx && psi_dev && angles, "NULL argument");
-    DQ_REQUIRE(L >= 1 && L <= 33 && n_total >= L && n_total <= 40, "dq_slice_phase_rx_many: L=%d n=%d", L, n_total);
-    DQ_REQUIRE((high_bits >> (n_total - L)) == 0, "dq_slice_phase_rx_many: high_bits do not fit %d global bits", n_total - L);
+    DQ_REQUIRE(L >= 1 && L <= 33 && n_total >= L && n_total <= 40, "%s: L=%d n=%d", what, L, n_total);
+    DQ_REQUIRE((high_bits >> (n_total - L)) == 0, "%s: high_bits do not fit %d global bits", what, n_total - L);
     DQ_TRY(ctx->set_device());
-    // fusable when the rotations start with a contiguous 12-bit tile pass (some target below bit 12, L >= 12) and no walk
-    // bit (8..11) carries more than kGrayDeg pairs; otherwise the phase runs as its own pass first
-    bool low_target = false;
-    for (int i = 0; i < count; ++i) low_target = low_target || (bits && bits[i] >= 0 && bits[i] < kWalkLo + kWalkBits);
+    std::vector<Rot> pre, rot;
+    DQ_TRY(sorted_rots(what, L, n_pre, pre_bits, pre_thetas, pre));
+    DQ_TRY(sorted_rots(what, L, count, bits, thetas, rot));
     PhaseArgs h;
     DQ_TRY(fill_args(h, n_total, n_zz, pair_bits, angles + 1, angles[0]));
-    bool fusable = low_target && L >= kTileBits && !getenv("DQ_SLICE_NO_PHASE_FUSION");
-    int n_in = 0;
-    for (int e = 0; e < h.n_zz; ++e) n_in += (h.a[e] < kTileBits && h.b[e] < kTileBits) ? 1 : 0;
-    fusable = fusable && n_in <= kMaxIn;
-    for (int k = 0; k < kTileBits && fusable; ++k) {      // every tile bit's pair list must fit the kernel's tables
-        int d = 0;
-        for (int e = 0; e < h.n_zz; ++e) d += (h.a[e] == k || h.b[e] == k) ? 1 : 0;
-        fusable = d <= kGrayDeg;
-    }
-    if (!fusable) {
-        DQ_TRY(dq_slice_phase(ctx, psi_dev, L, high_bits, n_total, n_zz, pair_bits, angles));
-        return rx_many_impl(ctx, psi_dev, L, count, bits, thetas, nullptr, 0, nullptr, sc);
-    }
-    PhaseArgs* d;
-    DQ_TRY(upload_args(ctx, h, &d));
-    bool done = false;
-    DQ_TRY(rx_many_impl(ctx, psi_dev, L, count, bits, thetas, d, high_bits, &done, sc));
-    DQ_REQUIRE(done, "dq_slice_phase_rx_many: internal error: the phase was not applied");
+    std::vector<int> tb(rot.size());
+    for (size_t i = 0; i < rot.size(); ++i) tb[i] = rot[i].bit;
+    const std::vector<TileSet> sets = plan_sets(L, tb);
+    return step_impl(ctx, psi_dev, L, high_bits, &h, pre, rot, sets, -1, -1, sc, n_total, n_zz, pair_bits, angles);
+}
+
+static int check_scatter(const char* what, int L, int count, int g, int rank, void* const* peer_recv) {
+    DQ_REQUIRE(peer_recv, "NULL argument");
+    DQ_REQUIRE(g >= 1 && (1 << g) <= kMaxPeers && g <= L && rank >= 0 && rank < (1 << g), "%s: g=%d rank=%d L=%d", what, g, rank, L);
+    DQ_REQUIRE(count >= 1, "%s: needs at least one rotation to carry the exchange", what);
+    for (int j = 0; j < (1 << g); ++j) DQ_REQUIRE(peer_recv[j] != nullptr, "%s: NULL receive buffer of rank %d", what, j);
     return DQ_OK;
 }
 
 int dq_slice_phase_rx_many(dq_context* ctx, void* psi_dev, int L, uint64_t high_bits, int n_total, int n_zz,
                            const int32_t* pair_bits, const double* angles, int count, const int32_t* bits, const double* thetas) {
-    return phase_rx_many(ctx, psi_dev, L, high_bits, n_total, n_zz, pair_bits, angles, count, bits, thetas, nullptr);
+    return slice_step("dq_slice_phase_rx_many", ctx, psi_dev, L, high_bits, n_total, n_zz, pair_bits, angles, 0, nullptr, nullptr,
+                      count, bits, thetas, nullptr);
 }
 
 int dq_slice_phase_rx_many_scatter(dq_context* ctx, void* psi_dev, int L, uint64_t high_bits, int n_total, int n_zz,
                                    const int32_t* pair_bits, const double* angles, int count, const int32_t* bits,
                                    const double* thetas, int g, int rank, void* const* peer_recv) {
-    DQ_REQUIRE(peer_recv, "NULL argument");
-    DQ_REQUIRE(g >= 1 && (1 << g) <= kMaxPeers && g <= L && rank >= 0 && rank < (1 << g), "dq_slice_phase_rx_many_scatter: g=%d rank=%d L=%d", g, rank, L);
-    DQ_REQUIRE(count >= 1, "dq_slice_phase_rx_many_scatter: needs at least one rotation to carry the exchange");
-    for (int j = 0; j < (1 << g); ++j) DQ_REQUIRE(peer_recv[j] != nullptr, "dq_slice_phase_rx_many_scatter: NULL receive buffer of rank %d", j);
+    DQ_TRY(check_scatter("dq_slice_phase_rx_many_scatter", L, count, g, rank, peer_recv));
     Scatter sc{g, rank, peer_recv};
-    return phase_rx_many(ctx, psi_dev, L, high_bits, n_total, n_zz, pair_bits, angles, count, bits, thetas, &sc);
+    return slice_step("dq_slice_phase_rx_many_scatter", ctx, psi_dev, L, high_bits, n_total, n_zz, pair_bits, angles, 0, nullptr,
+                      nullptr, count, bits, thetas, &sc);
+}
+
+int dq_slice_step(dq_context* ctx, void* psi_dev, int L, uint64_t high_bits, int n_total, int n_zz, const int32_t* pair_bits,
+                  const double* angles, int n_pre, const int32_t* pre_bits, const double* pre_thetas, int count,
+                  const int32_t* bits, const double* thetas) {
+    return slice_step("dq_slice_step", ctx, psi_dev, L, high_bits, n_total, n_zz, pair_bits, angles, n_pre, pre_bits, pre_thetas,
+                      count, bits, thetas, nullptr);
+}
+
+int dq_slice_step_scatter(dq_context* ctx, void* psi_dev, int L, uint64_t high_bits, int n_total, int n_zz,
+                          const int32_t* pair_bits, const double* angles, int n_pre, const int32_t* pre_bits,
+                          const double* pre_thetas, int count, const int32_t* bits, const double* thetas, int g, int rank,
+                          void* const* peer_recv) {
+    DQ_TRY(check_scatter("dq_slice_step_scatter", L, count, g, rank, peer_recv));
+    Scatter sc{g, rank, peer_recv};
+    return slice_step("dq_slice_step_scatter", ctx, psi_dev, L, high_bits, n_total, n_zz, pair_bits, angles, n_pre, pre_bits,
+                      pre_thetas, count, bits, thetas, &sc);
+}
+
+int dq_slice_evolve_steps(dq_context* ctx, void* psi_dev, int L, uint64_t high_bits, int n_total, int n_zz,
+                          const int32_t* pair_bits, int count, const int32_t* bits, int n_steps, const double* angles,
+                          int64_t ld_angles, const double* thetas, int64_t ld_thetas) {
+    const char* what = "dq_slice_evolve_steps";
+    DQ_REQUIRE(ctx && psi_dev && (n_steps == 0 || (angles && (count == 0 || thetas))), "NULL argument");
+    DQ_REQUIRE(L >= 1 && L <= 33 && n_total >= L && n_total <= 40 && n_steps >= 0, "%s: L=%d n=%d steps=%d", what, L, n_total, n_steps);
+    DQ_REQUIRE((high_bits >> (n_total - L)) == 0, "%s: high_bits do not fit %d global bits", what, n_total - L);
+    DQ_REQUIRE(ld_angles >= 1 + n_zz && ld_thetas >= count, "%s: row strides %lld, %lld", what, (long long)ld_angles, (long long)ld_thetas);
+    if (n_steps == 0) return DQ_OK;
+    DQ_TRY(ctx->set_device());
+    std::vector<std::vector<Rot>> rot(n_steps);
+    for (int k = 0; k < n_steps; ++k) DQ_TRY(sorted_rots(what, L, count, bits, thetas + (size_t)k * ld_thetas, rot[k]));
+    std::vector<int> tb(rot[0].size());
+    for (size_t i = 0; i < rot[0].size(); ++i) tb[i] = rot[0][i].bit;
+    const std::vector<TileSet> sets = plan_sets(L, tb);
+    PhaseArgs h;
+    DQ_TRY(fill_args(h, n_total, n_zz, pair_bits, angles + 1, angles[0]));
+    // Chained form: step p leaves the rotations of ONE tile set (d_p) undone; the first pass of step p + 1 runs on that set and
+    // applies [d_p's rotations of step p] [phase of step p + 1] [d_p's rotations of step p + 1] -- a step costs one pass less
+    // (two tile sets: ONE pass per step).  Two sets that can carry the phase take turns as d_p.
+    // (the two with the fewest targets: the boundary pass rotates its targets twice)
+    int b0 = -1, b1 = -1;
+    for (size_t k = 0; k < sets.size(); ++k)
+        if (can_carry_phase(h, sets[k], L, true, false)) {
+            if (b0 < 0 || sets[k].n_targets < sets[b0].n_targets) { b1 = b0; b0 = (int)k; }
+            else if (b1 < 0 || sets[k].n_targets < sets[b1].n_targets) b1 = (int)k;
+        }
+    const bool chain = b1 >= 0 && n_steps >= 2 && !getenv("DQ_SLICE_NO_CHAIN");
+    const std::vector<Rot> none;
+    int owed = -1;                                                    // tile set whose rotations of the previous step are still owed
+    for (int k = 0; k < n_steps; ++k) {
+        const double* row = angles + (size_t)k * ld_angles;
+        DQ_TRY(fill_args(h, n_total, n_zz, pair_bits, row + 1, row[0]));
+        int first = -1, skip = -1;
+        if (chain) {
+            first = owed >= 0 ? owed : b0;
+            skip = k + 1 < n_steps ? (first == b0 ? b1 : b0) : -1;
+        }
+        DQ_TRY(step_impl(ctx, psi_dev, L, high_bits, &h, owed >= 0 ? rots_of(sets[owed], rot[k - 1]) : none, rot[k], sets, first, skip,
+                         nullptr, n_total, n_zz, pair_bits, row));
+        owed = skip;
+    }
+    return DQ_OK;
 }
 
 int dq_slice_energy(dq_context* ctx, const void* psi_dev, int L, uint64_t high_bits, int n_total, int n_zz,

@@ -66,6 +66,30 @@ class CudaSliceOps(object):
         _lib.check(self.lib.dq_slice_phase_rx_many(self.ctx.handle, self._p(psi), L, high, n, len(pair_bits), _lib.ptr(pair_bits),
                                                    _lib.ptr(angles), len(bits), _lib.ptr(bits), _lib.ptr(thetas)))
 
+    def step(self, psi, L, high, n, pair_bits, angles, pre_bits, pre_thetas, bits, thetas):
+        """[rotations still owed to the previous step] [phase] [rotations]: when one tile of the pass plan holds the owed bits,
+        all three ride on one pass over the slice (dq_slice_step)."""
+        pair_bits = np.ascontiguousarray(pair_bits, dtype=np.int32)
+        angles = np.ascontiguousarray(angles, dtype=np.float64)
+        pre_bits = np.ascontiguousarray(pre_bits, dtype=np.int32)
+        pre_thetas = np.ascontiguousarray(pre_thetas, dtype=np.float64)
+        bits = np.ascontiguousarray(bits, dtype=np.int32)
+        thetas = np.ascontiguousarray(thetas, dtype=np.float64)
+        _lib.check(self.lib.dq_slice_step(self.ctx.handle, self._p(psi), L, high, n, len(pair_bits), _lib.ptr(pair_bits),
+                                          _lib.ptr(angles), len(pre_bits), _lib.ptr(pre_bits), _lib.ptr(pre_thetas), len(bits),
+                                          _lib.ptr(bits), _lib.ptr(thetas)))
+
+    def evolve_steps(self, psi, L, high, n, pair_bits, bits, angle_rows, theta_rows):
+        """Steps of a slice that needs no exchange, chained over the step boundaries (dq_slice_evolve_steps)."""
+        pair_bits = np.ascontiguousarray(pair_bits, dtype=np.int32)
+        bits = np.ascontiguousarray(bits, dtype=np.int32)
+        angle_rows = np.ascontiguousarray(angle_rows, dtype=np.float64)
+        theta_rows = np.ascontiguousarray(theta_rows, dtype=np.float64)
+        assert angle_rows.shape == (len(theta_rows), 1 + len(pair_bits)) and theta_rows.shape[1] == len(bits)
+        _lib.check(self.lib.dq_slice_evolve_steps(self.ctx.handle, self._p(psi), L, high, n, len(pair_bits), _lib.ptr(pair_bits),
+                                                  len(bits), _lib.ptr(bits), len(theta_rows), _lib.ptr(angle_rows),
+                                                  angle_rows.shape[1], _lib.ptr(theta_rows), theta_rows.shape[1]))
+
     # -- exchange fused into the last local pass (peer memory) ------------------------------------------------
     def enable_peer_exchange(self, buffers, rank, world):
         """Map every rank's two slice buffers into this process (CUDA IPC; peer access over NVLink when the ranks own
@@ -119,6 +143,19 @@ class CudaSliceOps(object):
         _lib.check(self.lib.dq_slice_phase_rx_many_scatter(
             self.ctx.handle, self._p(psi), L, high, n, len(pair_bits), _lib.ptr(pair_bits), _lib.ptr(angles), len(bits),
             _lib.ptr(bits), _lib.ptr(thetas), self._g, self._rank, table))
+
+    def step_scatter(self, psi, recv, L, high, n, pair_bits, angles, pre_bits, pre_thetas, bits, thetas):
+        """dq_slice_step whose last pass writes into every rank's `recv` buffer."""
+        pair_bits = np.ascontiguousarray(pair_bits, dtype=np.int32)
+        angles = np.ascontiguousarray(angles, dtype=np.float64)
+        pre_bits = np.ascontiguousarray(pre_bits, dtype=np.int32)
+        pre_thetas = np.ascontiguousarray(pre_thetas, dtype=np.float64)
+        bits = np.ascontiguousarray(bits, dtype=np.int32)
+        thetas = np.ascontiguousarray(thetas, dtype=np.float64)
+        table = self._peer_ptrs[recv.data_ptr()]
+        _lib.check(self.lib.dq_slice_step_scatter(
+            self.ctx.handle, self._p(psi), L, high, n, len(pair_bits), _lib.ptr(pair_bits), _lib.ptr(angles), len(pre_bits),
+            _lib.ptr(pre_bits), _lib.ptr(pre_thetas), len(bits), _lib.ptr(bits), _lib.ptr(thetas), self._g, self._rank, table))
 
     def barrier(self):
         """Every rank's stores into every receive buffer are complete (the pass has finished on every device)."""
@@ -183,6 +220,11 @@ class DistributedState(object):
         self.exchanged_bytes = 0
         self.fused_rx = True               # False: one kernel per rotation (dq_slice_rx), kept for cross-checks
         self.fused_phase = True            # False: the diagonal phase as its own pass (dq_slice_phase)
+        # The rotations of the qubits that became local in a step's exchange are not run as a pass of their own: they stay OWED
+        # and ride, with the next step's phase, on the first pass of the next step (dq_slice_step) -- one pass over the slice
+        # less per step.  flush() runs what is owed (before anything reads the state).
+        self.defer_post = hasattr(self.ops, "step")
+        self.owed = None                   # (qubits, angles)
         # exchange fused into the stores of the last local pass (peer memory over NVLink) instead of an NCCL all-to-all
         self.peer_exchange = bool(g) and hasattr(self.ops, "enable_peer_exchange") and peer_exchange is not False and \
             self.ops.enable_peer_exchange([self.psi, self.recv], self.rank, self.world)
@@ -194,10 +236,18 @@ class DistributedState(object):
     def global_qubits(self):
         return [q for q in range(self.n) if self.pos[q] >= self.L]
 
+    def flush(self):
+        """Run the rotations still owed to the last step (see defer_post)."""
+        if self.owed is not None:
+            qubits, angles = self.owed
+            self.owed = None
+            self._rotate_angles(qubits, angles)
+
     def swap_global_local(self):
         """All-to-all that exchanges index bits [L-g, L) with the rank bits [L, n)."""
         if self.g == 0:
             return
+        self.flush()
         self.ops.all_to_all(self.recv, self.psi)
         self._swapped()
 
@@ -214,6 +264,7 @@ class DistributedState(object):
         self.exchanged_bytes += 16 * (1 << L) * (self.world - 1) // self.world
 
     def restore_layout(self):
+        self.flush()
         if self.pos != [self.n - 1 - q for q in range(self.n)]:
             self.swap_global_local()
 
@@ -236,23 +287,48 @@ class DistributedState(object):
         x = row[1 + p.n_zz:]
         was_global = self.global_qubits()
         local = [q for q in range(self.n) if self.pos[q] < self.L]
+        fused = self.fused_rx and self.fused_phase and bool(local)
+        if self.owed is not None and not (fused and self.defer_post):
+            self.flush()
+        pre_bits, pre_thetas = [], []
+        if self.owed is not None:
+            pre_bits, pre_thetas = [self.pos[q] for q in self.owed[0]], list(self.owed[1])
+            self.owed = None
+        bits, thetas = [self.pos[q] for q in local], [x[q] for q in local]
         if self.peer_exchange and was_global and local:
-            # one call: phase + every local rotation, the last pass storing into the peers' receive buffers; then a barrier
-            self.ops.phase_rx_many_scatter(self.psi, self.recv, self.L, self.rank, self.n, self.pair_bits(), row[:1 + p.n_zz],
-                                           [self.pos[q] for q in local], [x[q] for q in local])
+            # one call: (owed rotations +) phase + every local rotation, the last pass storing into the peers' receive buffers;
+            # then a barrier
+            if pre_bits or (self.defer_post and hasattr(self.ops, "step_scatter")):
+                self.ops.step_scatter(self.psi, self.recv, self.L, self.rank, self.n, self.pair_bits(), row[:1 + p.n_zz],
+                                      pre_bits, pre_thetas, bits, thetas)
+            else:
+                self.ops.phase_rx_many_scatter(self.psi, self.recv, self.L, self.rank, self.n, self.pair_bits(), row[:1 + p.n_zz],
+                                               bits, thetas)
             self.ops.barrier()
             self._swapped()
-            self._rotate(was_global, x)
+            self._post(was_global, x)
             return
-        if self.fused_rx and self.fused_phase and hasattr(self.ops, "phase_rx_many") and local:
-            self.ops.phase_rx_many(self.psi, self.L, self.rank, self.n, self.pair_bits(), row[:1 + p.n_zz],
-                                   [self.pos[q] for q in local], [x[q] for q in local])
+        if fused and self.defer_post:
+            self.ops.step(self.psi, self.L, self.rank, self.n, self.pair_bits(), row[:1 + p.n_zz], pre_bits, pre_thetas, bits, thetas)
+        elif fused and hasattr(self.ops, "phase_rx_many"):
+            self.ops.phase_rx_many(self.psi, self.L, self.rank, self.n, self.pair_bits(), row[:1 + p.n_zz], bits, thetas)
         else:
             self.ops.phase(self.psi, self.L, self.rank, self.n, self.pair_bits(), row[:1 + p.n_zz])
             self._rotate(local, x)
         if was_global:
             self.swap_global_local()
-            self._rotate(was_global, x)
+            self._post(was_global, x)
+
+    def _post(self, qubits, x):
+        """The step's rotations on the qubits that have just become local: owed to the next step's first pass, or run now."""
+        if self.defer_post and self.fused_rx and self.fused_phase:
+            self.owed = (list(qubits), [x[q] for q in qubits])
+        else:
+            self._rotate(qubits, x)
+
+    def _rotate_angles(self, qubits, angles):
+        x = {q: a for q, a in zip(qubits, angles)}
+        self._rotate(qubits, x)
 
     def _rotate(self, qubits, x):
         """X rotations of one step on local qubits: they commute, so the fused pass kernel takes them all at once."""
@@ -265,8 +341,16 @@ class DistributedState(object):
                 self.ops.rx(self.psi, self.L, self.pos[q], x[q])
 
     def evolve_rows(self, rows):
-        for row in np.asarray(rows, dtype=np.float64).reshape(-1, self.problem.row_len):
+        rows = np.asarray(rows, dtype=np.float64).reshape(-1, self.problem.row_len)
+        if self.g == 0 and self.fused_rx and self.fused_phase and hasattr(self.ops, "evolve_steps") and len(rows):
+            # nothing to exchange: the whole sequence in one call, chained over the step boundaries
+            p = self.problem
+            self.ops.evolve_steps(self.psi, self.L, self.rank, self.n, self.pair_bits(), [self.pos[q] for q in range(self.n)],
+                                  rows[:, :1 + p.n_zz], rows[:, 1 + p.n_zz:])
+            return
+        for row in rows:
             self.step(row)
+        self.flush()
 
     def evolve(self, coeff, T0, T1):
         """SimulatorPlain.trotter's step grid (sim_plain.py:123-150) with the product-formula step."""
@@ -275,12 +359,14 @@ class DistributedState(object):
     def energy(self):
         """<psi|M|psi> for the problem's diagonal observable, summed over ranks."""
         p = self.problem
+        self.flush()
         if p.m_diag is not None:
             raise NotImplementedError("distributed energies need the observable in ZZ form (m_zz, m_const)")
         part = self.ops.energy(self.psi, self.L, self.rank, self.n, self.pair_bits(), p.m_zz, p.m_const)
         return self.ops.all_reduce_scalar(part) if self.world > 1 else part
 
     def norm2(self):
+        self.flush()
         zero = np.zeros(self.problem.n_zz)
         part = self.ops.energy(self.psi, self.L, self.rank, self.n, self.pair_bits(), zero, 1.0)
         return self.ops.all_reduce_scalar(part) if self.world > 1 else part

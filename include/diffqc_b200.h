@@ -259,6 +259,28 @@ int dq_slice_rx_many_scatter(dq_context* ctx, void* psi_dev, int L, int count, c
 int dq_slice_phase_rx_many_scatter(dq_context* ctx, void* psi_dev, int L, uint64_t high_bits, int n_total, int n_zz,
                                    const int32_t* pair_bits, const double* angles, int count, const int32_t* bits,
                                    const double* thetas, int g, int rank, void* const* peer_recv);
+/* One product-formula step of a slice with rotations still owed to the PREVIOUS step (diffqc.cc:155-164 over a step boundary):
+ *   [exp(-i pre_thetas[k] X) on pre_bits]  [phase of this step]  [exp(-i thetas[k] X) on bits]
+ * When one tile of the pass plan holds every pre bit, all three ride on ONE pass over the slice (TMA tile kernel: rotation
+ * rounds, phase and rotation rounds on the tile in shared memory).  A distributed step uses it to fold the rotations of the
+ * qubits that became local in the last exchange into the first pass of the next step (5 -> 3 launches per step at n = 32 on
+ * 8 GPUs); n_pre = 0 is dq_slice_phase_rx_many.  The _scatter form ends with the exchange (see dq_slice_rx_many_scatter). */
+int dq_slice_step(dq_context* ctx, void* psi_dev, int L, uint64_t high_bits, int n_total, int n_zz, const int32_t* pair_bits,
+                  const double* angles, int n_pre, const int32_t* pre_bits, const double* pre_thetas, int count,
+                  const int32_t* bits, const double* thetas);
+int dq_slice_step_scatter(dq_context* ctx, void* psi_dev, int L, uint64_t high_bits, int n_total, int n_zz,
+                          const int32_t* pair_bits, const double* angles, int n_pre, const int32_t* pre_bits,
+                          const double* pre_thetas, int count, const int32_t* bits, const double* thetas, int g, int rank,
+                          void* const* peer_recv);
+/* n_steps product-formula steps of a slice that needs no exchange (every rotated bit local), chained: step p leaves the
+ * rotations of one tile set undone and the first pass of step p + 1 applies them, the phase of step p + 1 and that set's
+ * rotations of step p + 1 -- (tile sets - 1) passes per step instead of (tile sets), i.e. ONE read + write of the state per
+ * step for n <= 21 and two for n <= 30.  angles: row k at angles + k * ld_angles = [c | n_zz pair angles]; thetas: row k at
+ * thetas + k * ld_thetas = one angle per entry of bits.  The loop of sim_plain.py:135-150 in the product form of
+ * diffqc.cc:155-164. */
+int dq_slice_evolve_steps(dq_context* ctx, void* psi_dev, int L, uint64_t high_bits, int n_total, int n_zz,
+                          const int32_t* pair_bits, int count, const int32_t* bits, int n_steps, const double* angles,
+                          int64_t ld_angles, const double* thetas, int64_t ld_thetas);
 /* CUDA IPC plumbing for the above: a 64-byte handle + byte offset for a device pointer (the handle names the allocation the
  * pointer lives in), and the mapping of such a handle in another process (same or peer device). */
 int dq_ipc_export(dq_context* ctx, void* dev_ptr, void* handle64_out, uint64_t* offset_out);

@@ -78,6 +78,20 @@ class NumpySliceOps(object):
         psi.numpy()[:] = array
 
 
+class NumpySliceOpsStep(NumpySliceOps):
+    """The stand-in with dq_slice_step: rotations owed to the previous step, phase, rotations in one call."""
+
+    def step(self, psi, L, high, n, pair_bits, angles, pre_bits, pre_thetas, bits, thetas):
+        assert len(set(pre_bits)) == len(pre_bits) and all(0 <= b < L for b in pre_bits)
+        self.step_calls = getattr(self, "step_calls", 0) + 1
+        self.step_pre = getattr(self, "step_pre", 0) + (1 if len(pre_bits) else 0)
+        for b, th in zip(pre_bits, pre_thetas):
+            self.rx(psi, L, b, th)
+        self.phase(psi, L, high, n, pair_bits, angles)
+        for b, th in zip(bits, thetas):
+            self.rx(psi, L, b, th)
+
+
 def _check(n, rank, world, ops, device=0, steps_per=3):
     edges = R.random_regular_edges(n, seed=n)
     prob = IsingProblem.maxcut(n, edges)
@@ -89,7 +103,10 @@ def _check(n, rank, world, ops, device=0, steps_per=3):
     ns, dt, ts = R.step_grid(0.2, 1.7, steps_per)
     want = R.evolve_split_structured(ref, R.coef_table_plain(coeff, ref["omegas"], ref["T"], ts), dt, ref["psi0"])
     assert st.exchanges == (ns if world > 1 else 0)                     # one all-to-all per step, no more
-    if hasattr(st.ops, "rx_many_calls"):                                # fused rotations: local set, then the swapped-in qubits
+    if hasattr(st.ops, "step_calls"):                                   # owed rotations ride on the next step's first call
+        assert st.ops.step_calls == ns and st.ops.step_pre == (ns - 1 if world > 1 else 0)
+        assert getattr(st.ops, "rx_many_calls", 0) == (1 if world > 1 else 0)      # the flush after the last step
+    elif hasattr(st.ops, "rx_many_calls"):                              # fused rotations: local set, then the swapped-in qubits
         assert st.ops.rx_many_calls == ns * (2 if world > 1 else 1)
     e = st.energy()                                                     # layout-agnostic: no restore needed
     assert abs(e - R.energy_diag(ref["m_diag"], want)) < 1e-10
@@ -119,6 +136,7 @@ def _cpu_worker(rank, world, port, n):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         _check(n, rank, world, NumpySliceOps())
+        _check(n, rank, world, NumpySliceOpsStep())
     finally:
         dist.destroy_process_group()
 
@@ -144,6 +162,7 @@ def test_layout_bookkeeping_over_gloo(world, n):
 
 def test_single_rank_bookkeeping_numpy():
     _check(6, 0, 1, NumpySliceOps())
+    _check(6, 0, 1, NumpySliceOpsStep())
 
 
 def test_bad_world_sizes_are_rejected():
@@ -197,8 +216,8 @@ def test_fused_rotation_pass_equals_one_kernel_per_rotation(L, bits):
 @pytest.mark.gpu
 @pytest.mark.parametrize("L,n,high", [(12, 12, 0), (16, 16, 0), (18, 20, 3), (21, 21, 0)])
 def test_phase_fused_into_the_first_rotation_pass(L, n, high):
-    """dq_slice_phase_rx_many (the step's diagonal phase applied inside the contiguous 12-bit rotation pass) against
-    dq_slice_phase followed by dq_slice_rx_many; high rank bits included, and a bit list without low targets (no fusion)."""
+    """dq_slice_phase_rx_many (the step's diagonal phase applied to the tile of the first rotation pass) against dq_slice_phase
+    followed by dq_slice_rx_many; high rank bits included, and a bit list without low targets (the phase rides on a high-bit tile)."""
     from oracle import restate as R
     ops = distributed.CudaSliceOps(0)
     rng = np.random.RandomState(100 + L)
@@ -225,8 +244,91 @@ def test_phase_fused_into_the_first_rotation_pass(L, n, high):
         got, want = ops.to_host(a), ops.to_host(b)
         assert np.abs(got - want).max() < 1e-13
         assert abs(np.linalg.norm(got) - 1.0) < 1e-12
-        low_target = any(bit < 12 for bit in bits)
-        assert fused_launches == split_launches - (1 if low_target else 0)
+        assert fused_launches == split_launches - 1          # any 12-bit tile of the plan can carry the phase (TMA tile kernel)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("L,n,high,pre_bits", [(13, 16, 5, [10, 11, 12]), (15, 18, 2, [12, 13, 14]), (16, 16, 0, [15]),
+                                               (20, 21, 1, [17, 18, 19]), (21, 21, 0, [3, 7])])
+def test_step_with_owed_rotations(L, n, high, pre_bits):
+    """dq_slice_step: [rotations owed to the previous step] [phase] [rotations] against the three pieces as separate calls.
+    When one tile of the plan holds every owed bit the three ride on ONE pass (launch count checked); (13, ...) has the owed
+    bits spread over two tiles and must fall back to a pass of their own."""
+    from oracle import restate as R
+    ops = distributed.CudaSliceOps(0)
+    rng = np.random.RandomState(300 + L)
+    edges = R.random_regular_edges(n, seed=L) if n % 2 == 0 else [(i, (i + 1) % n) for i in range(n)] + [(i, (i + 5) % n) for i in range(0, n, 3)]
+    pair_bits = np.array([[n - 1 - a, n - 1 - b] for a, b in edges], dtype=np.int32)
+    angles = rng.normal(size=1 + len(edges))
+    host = rng.normal(size=1 << L) + 1j * rng.normal(size=1 << L)
+    host /= np.linalg.norm(host)
+    bits = list(range(L))
+    for trial in range(2):
+        thetas = rng.uniform(-1.2, 1.2, size=L)
+        pre_thetas = rng.uniform(-1.2, 1.2, size=len(pre_bits))
+        if trial == 1:
+            pre_thetas[0] = np.pi / 2               # cos = 0: the unscaled form of the pass
+        a, b = ops.alloc(1 << L), ops.alloc(1 << L)
+        ops.from_host(a, host)
+        ops.from_host(b, host)
+        l0 = ops.ctx.launch_count
+        ops.step(a, L, high, n, pair_bits, angles, pre_bits, pre_thetas, bits, thetas)
+        fused_launches = ops.ctx.launch_count - l0
+        l0 = ops.ctx.launch_count
+        ops.rx_many(b, L, pre_bits, pre_thetas)
+        ops.phase(b, L, high, n, pair_bits, angles)
+        ops.rx_many(b, L, bits, thetas)
+        split_launches = ops.ctx.launch_count - l0
+        ops.ctx.synchronize()
+        got, want = ops.to_host(a), ops.to_host(b)
+        assert np.abs(got - want).max() < 1e-13
+        assert abs(np.linalg.norm(got) - 1.0) < 1e-12
+        one_tile = L != 13
+        assert fused_launches == split_launches - (2 if one_tile else 1)
+    with pytest.raises(ValueError):
+        ops.step(a, L, high, n, pair_bits, angles, [L], [0.1], bits, thetas)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n,steps", [(11, 3), (14, 4), (18, 5), (21, 3), (22, 4)])
+def test_chained_steps_equal_step_by_step(n, steps, monkeypatch):
+    """dq_slice_evolve_steps (the rotations of one tile set owed across every step boundary: tile sets - 1 passes per step)
+    against one dq_slice_phase + dq_slice_rx_many per step, and against the same call with chaining switched off."""
+    from oracle import restate as R
+    ops = distributed.CudaSliceOps(0)
+    rng = np.random.RandomState(400 + n)
+    edges = R.random_regular_edges(n, seed=n) if n % 2 == 0 else [(i, (i + 1) % n) for i in range(n)] + [(i, (i + 5) % n) for i in range(0, n, 3)]
+    pair_bits = np.array([[n - 1 - a, n - 1 - b] for a, b in edges], dtype=np.int32)
+    angle_rows = rng.normal(size=(steps, 1 + len(edges))) * 0.4
+    bits = list(rng.permutation(n))
+    theta_rows = rng.uniform(-1.0, 1.0, size=(steps, n))
+    host = rng.normal(size=1 << n) + 1j * rng.normal(size=1 << n)
+    host /= np.linalg.norm(host)
+    a, b, c = ops.alloc(1 << n), ops.alloc(1 << n), ops.alloc(1 << n)
+    for t in (a, b, c):
+        ops.from_host(t, host)
+    l0 = ops.ctx.launch_count
+    ops.evolve_steps(a, n, 0, n, pair_bits, bits, angle_rows, theta_rows)
+    chained = ops.ctx.launch_count - l0
+    for k in range(steps):
+        ops.phase(b, n, 0, n, pair_bits, angle_rows[k])
+        ops.rx_many(b, n, bits, theta_rows[k])
+    monkeypatch.setenv("DQ_SLICE_NO_CHAIN", "1")
+    l0 = ops.ctx.launch_count
+    ops.evolve_steps(c, n, 0, n, pair_bits, bits, angle_rows, theta_rows)
+    unchained = ops.ctx.launch_count - l0
+    monkeypatch.delenv("DQ_SLICE_NO_CHAIN")
+    ops.ctx.synchronize()
+    got, want, got2 = ops.to_host(a), ops.to_host(b), ops.to_host(c)
+    assert np.abs(got - want).max() < 1e-13
+    assert np.abs(got2 - want).max() < 1e-13
+    assert abs(np.linalg.norm(got) - 1.0) < 1e-12
+    if n < 12:                                      # no 12-bit tile: phase pass + rotation pass per step
+        assert unchained == chained == 2 * steps
+    else:
+        sets = 1 if n == 12 else (2 if n <= 21 else 3)
+        assert unchained == steps * sets
+        assert chained == (steps * (sets - 1) + 1 if sets > 1 else steps)
 
 
 def _gpu_worker(rank, world, port, n):

@@ -63,5 +63,38 @@ for bits in groups:
     rec["norm"] = float(res["tma"].norm())
     print(json.dumps(rec), flush=True)
     out.append(rec)
+# the contiguous pass carrying the step's phase (3-regular graph on L qubits) vs the separate Gray-code phase pass + rotation pass
+from oracle import restate as R
+edges = R.random_regular_edges(L, seed=0)
+pair_bits = np.array([[L - 1 - a, L - 1 - b] for a, b in edges], dtype=np.int32)
+angles = rng.uniform(-0.3, 0.3, size=1 + len(edges))       # [c | one angle per pair]
+bits = list(range(min(12, L)))
+thetas = rng.uniform(-0.9, 0.9, size=len(bits))
+rec = {"L": L, "bits": "phase + 0..11"}
+res = {}
+for tag, env, fused in (("separate_tma", None, False), ("fused_cp_async", "1", True), ("fused_tma", None, True)):
+    if env:
+        os.environ["DQ_SLICE_NO_TMA"] = env
+    else:
+        os.environ.pop("DQ_SLICE_NO_TMA", None)
+    times = []
+    for r in range(reps + 1):
+        b.copy_(a)
+        ops.ctx.synchronize()
+        torch.cuda.synchronize()
+        l0 = ops.ctx.launch_count
+        if fused:
+            t = timed(lambda: ops.phase_rx_many(b, L, 0, L, pair_bits, angles, bits, thetas))
+        else:
+            t = timed(lambda: (ops.phase(b, L, 0, L, pair_bits, angles), ops.rx_many(b, L, bits, thetas)))
+        if r:
+            times.append(t)
+        rec[tag + "_launches"] = ops.ctx.launch_count - l0
+    res[tag] = b.clone()
+    rec[tag + "_ms"] = float(np.median(times))
+rec["max_diff_fused_tma_vs_separate"] = float((res["fused_tma"] - res["separate_tma"]).abs().max())
+rec["max_diff_fused_tma_vs_fused_cp_async"] = float((res["fused_tma"] - res["fused_cp_async"]).abs().max())
+print(json.dumps(rec), flush=True)
+out.append(rec)
 os.makedirs("gpurun_out", exist_ok=True)
 json.dump(out, open("gpurun_out/slice_pass_bench_L%d.json" % L, "w"), indent=1)
