@@ -15,14 +15,27 @@ __device__ __forceinline__ void dmma(double& c0, double& c1, const double a, con
 
 // CTA tile BM x BN, WM x WN warps, each warp (BM/WM) x (BN/WN) as 8x8 DMMA tiles.
 // Fragment ownership of m8n8k4 (lane = 4*g + t):  A[g][t], B[t][g], C[g][2t], C[g][2t+1].
-// Shared tiles are padded (+4 doubles per row) so both fragment loads are bank-conflict free.
+// Shared tiles are padded (+4 doubles per row) so both fragment loads are bank-conflict free.  Two stages: the k-slab k+1 is
+// on its way (cp.async, 16-byte pieces, zero fill outside the matrices) while the DMMAs run on slab k.
+template <int BM, int BN>
+struct ZgemmSmem {
+    static constexpr int SA = BK + 4, SB = BN + 4;
+    double As[2][2][BM][SA];           // [stage][plane][row][k]
+    double Bs[2][2][BK][SB];           // [stage][plane][k][col]
+};
+
+__device__ __forceinline__ void cp_async16_zfill(void* smem, const void* gmem, bool valid) {
+    const unsigned dst = (unsigned)__cvta_generic_to_shared(smem);
+    const int bytes = valid ? 16 : 0;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(gmem), "r"(bytes) : "memory");
+}
+
 template <int BM, int BN, int WM, int WN>
 __global__ void __launch_bounds__(WM * WN * 32) k_zgemm(const Gemm g) {
     constexpr int NT = WM * WN * 32;
     constexpr int TM = BM / WM / 8, TN = BN / WN / 8;
-    constexpr int SA = BK + 4, SB = BN + 4;
-    __shared__ __align__(16) double As[2][BM][SA];
-    __shared__ __align__(16) double Bs[2][BK][SB];
+    extern __shared__ __align__(16) unsigned char zgemm_smem[];
+    ZgemmSmem<BM, BN>& S = *reinterpret_cast<ZgemmSmem<BM, BN>*>(zgemm_smem);
 
     const int z = blockIdx.z;
     const double* __restrict__ A = g.A + (long long)z * g.strideA;
@@ -40,23 +53,32 @@ __global__ void __launch_bounds__(WM * WN * 32) k_zgemm(const Gemm g) {
 #pragma unroll
         for (int j = 0; j < TN; ++j) cr[i][j][0] = cr[i][j][1] = ci[i][j][0] = ci[i][j][1] = 0.0;
 
-    for (int k0 = 0; k0 < g.K; k0 += BK) {
-        // stage A[m0:m0+BM, k0:k0+BK] and B[k0:k0+BK, n0:n0+BN], both planes, 16-byte vectors, zero fill
+    // stage A[m0:m0+BM, k0:k0+BK] and B[k0:k0+BK, n0:n0+BN], both planes
+    auto issue = [&](int st, int k0) {
         for (int v = tid; v < BM * (BK / 2) * 2; v += NT) {
             const int pl = v / (BM * (BK / 2)), w = v % (BM * (BK / 2));
             const int r = w / (BK / 2), c = (w % (BK / 2)) * 2;
-            double2 val = make_double2(0.0, 0.0);
-            if (m0 + r < g.M && k0 + c < g.K)
-                val = *reinterpret_cast<const double2*>(A + pl * g.planeA + (long long)(m0 + r) * g.lda + k0 + c);
-            *reinterpret_cast<double2*>(&As[pl][r][c]) = val;
+            const bool ok = m0 + r < g.M && k0 + c < g.K;
+            cp_async16_zfill(&S.As[st][pl][r][c], ok ? A + pl * g.planeA + (long long)(m0 + r) * g.lda + k0 + c : A, ok);
         }
         for (int v = tid; v < BK * (BN / 2) * 2; v += NT) {
             const int pl = v / (BK * (BN / 2)), w = v % (BK * (BN / 2));
             const int r = w / (BN / 2), c = (w % (BN / 2)) * 2;
-            double2 val = make_double2(0.0, 0.0);
-            if (k0 + r < g.K && n0 + c < g.N)
-                val = *reinterpret_cast<const double2*>(B + pl * g.planeB + (long long)(k0 + r) * g.ldb + n0 + c);
-            *reinterpret_cast<double2*>(&Bs[pl][r][c]) = val;
+            const bool ok = k0 + r < g.K && n0 + c < g.N;
+            cp_async16_zfill(&S.Bs[st][pl][r][c], ok ? B + pl * g.planeB + (long long)(k0 + r) * g.ldb + n0 + c : B, ok);
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+
+    const int nk = (g.K + BK - 1) / BK;
+    issue(0, 0);
+    for (int kt = 0; kt < nk; ++kt) {
+        const int st = kt & 1;
+        if (kt + 1 < nk) {
+            issue(st ^ 1, (kt + 1) * BK);
+            asm volatile("cp.async.wait_group 1;" ::: "memory");
+        } else {
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
         }
         __syncthreads();
 #pragma unroll
@@ -64,14 +86,14 @@ __global__ void __launch_bounds__(WM * WN * 32) k_zgemm(const Gemm g) {
             double ar[TM], ai[TM], nai[TM], br[TN], bi[TN];
 #pragma unroll
             for (int i = 0; i < TM; ++i) {
-                ar[i] = As[0][wm0 + i * 8 + gq][kk + tq];
-                ai[i] = As[1][wm0 + i * 8 + gq][kk + tq];
+                ar[i] = S.As[st][0][wm0 + i * 8 + gq][kk + tq];
+                ai[i] = S.As[st][1][wm0 + i * 8 + gq][kk + tq];
                 nai[i] = -ai[i];
             }
 #pragma unroll
             for (int j = 0; j < TN; ++j) {
-                br[j] = Bs[0][kk + tq][wn0 + j * 8 + gq];
-                bi[j] = Bs[1][kk + tq][wn0 + j * 8 + gq];
+                br[j] = S.Bs[st][0][kk + tq][wn0 + j * 8 + gq];
+                bi[j] = S.Bs[st][1][kk + tq][wn0 + j * 8 + gq];
             }
 #pragma unroll
             for (int i = 0; i < TM; ++i)
@@ -83,7 +105,7 @@ __global__ void __launch_bounds__(WM * WN * 32) k_zgemm(const Gemm g) {
                     dmma(ci[i][j][0], ci[i][j][1], ai[i], br[j]);
                 }
         }
-        __syncthreads();
+        __syncthreads();               // everybody is done with stage st before the next iteration refills it
     }
     // epilogue: C = alpha * acc (+ Add) (+ I)
 #pragma unroll
@@ -161,7 +183,10 @@ __global__ void __launch_bounds__(256) k_zgemm_skinny(const Gemm g) {
 template <int BM, int BN, int WM, int WN>
 int launch_zgemm(dq_context* ctx, const Gemm& g) {
     dim3 grid((g.N + BN - 1) / BN, (g.M + BM - 1) / BM, g.batch);
-    k_zgemm<BM, BN, WM, WN><<<grid, WM * WN * 32, 0, ctx->stream>>>(g);
+    const size_t smem = sizeof(ZgemmSmem<BM, BN>);
+    if (smem > (48u << 10))            // per device and cheap to set
+        DQ_CUDA(cudaFuncSetAttribute(k_zgemm<BM, BN, WM, WN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_zgemm<BM, BN, WM, WN><<<grid, WM * WN * 32, smem, ctx->stream>>>(g);
     ctx->launches++;
     DQ_CUDA(cudaGetLastError());
     return DQ_OK;

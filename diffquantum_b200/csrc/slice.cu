@@ -429,11 +429,23 @@ __global__ void __launch_bounds__(kThreads, 3) k_slice_rx_tile(double2* __restri
     }
     __syncthreads();
     for (unsigned long long t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-        // deposit the bits of t into the physical positions the tile does not span
+        // deposit the bits of t into the physical positions the tile does not span.  A scatter pass fills the peer-selecting
+        // positions [L - g, L) FIRST and starts at its own rank: consecutive tiles (= the CTAs running at any moment) go to
+        // different peers and no two ranks aim at the same peer with the same tile index -- with the plain order every CTA of
+        // every rank wrote to peer 0 first, then all to peer 1, ... and each receiver's NVLink ingress took the traffic of all
+        // senders in turn (measured at n = 32 on 8 GPUs: 36 ms per step instead of 21)
         unsigned long long base = 0;
         {
             unsigned long long rest = t;
-            for (int p = 0; p < L; ++p)
+            const int p_split = A.scatter_g ? L - A.scatter_g : L;
+            if (A.scatter_g) {
+                int free_top = 0;
+                for (int p = p_split; p < L; ++p) free_top += ((A.mask >> p) & 1ull) ? 0 : 1;
+                rest = (rest & ~((1ull << free_top) - 1ull)) | ((rest + (unsigned long long)A.scatter_rank) & ((1ull << free_top) - 1ull));
+                for (int p = p_split; p < L; ++p)
+                    if (!((A.mask >> p) & 1ull)) { base |= (rest & 1ull) << p; rest >>= 1; }
+            }
+            for (int p = 0; p < p_split; ++p)
                 if (!((A.mask >> p) & 1ull)) { base |= (rest & 1ull) << p; rest >>= 1; }
         }
         // asynchronous global -> shared copies (LDGSTS): all of a thread's 16-byte pieces are in flight at once and never
@@ -1183,6 +1195,14 @@ int step_impl(dq_context* ctx, void* psi_dev, int L, unsigned long long high_bit
     if (first >= 0) order.push_back(first);
     for (size_t k = 0; k < sets.size(); ++k)
         if ((int)k != first && (int)k != skip) order.push_back((int)k);
+    if (sc && order.size() > 2 - (first < 0 ? 1 : 0)) {
+        // the exchange rides on the pass with the longest contiguous runs (the contiguous tile: 64 KiB per remote write burst)
+        const size_t from = first >= 0 ? 1 : 0;
+        size_t best = from;
+        for (size_t i = from; i < order.size(); ++i)
+            if (sets[order[i]].lo > sets[order[best]].lo) best = i;
+        std::swap(order[best], order.back());
+    }
     for (size_t i = 0; i < order.size(); ++i) {
         const int k = order[i];
         const bool lead = k == first;
