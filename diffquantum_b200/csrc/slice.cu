@@ -338,51 +338,71 @@ __device__ __forceinline__ void phase_setup(PhaseTabs& P, const PhaseArgs* __res
     }
 }
 
-// per tile; t < kTileBits + 1 + kWalkBits threads do the work (fixed summation / product order); G = global index of the
-// tile's element 0.  A team barrier must follow.
+// per tile; threads t < 16 and 32 <= t < 64 of the team do the work (fixed summation / product order); G = global index of the
+// tile's element 0.  A team barrier must follow.  The constant over the outside-outside pairs is a warp-wide sum (lane q takes
+// pairs q, q + 32, ...; a serial loop over ~20 pairs was ~2000 cycles of dependent latency per tile with the team waiting).
 __device__ __forceinline__ void phase_tile_setup(const PhaseTabs& P, PhaseTile& Q, const unsigned long long G, const int t) {
     if (t < kTileBits) {
         const int k = t;
         double hsum = 0.0;
         for (int q = 0; q < P.out_n[k]; ++q) hsum += ((G >> P.out_other[k][q]) & 1ull) ? -P.out_ang[k][q] : P.out_ang[k][q];
         Q.h_field[k] = hsum;
-    } else if (t == kTileBits) {
-        double c = P.c0;
-        for (int q = 0; q < P.oo_n; ++q) c += (((G >> P.oo_a[q]) ^ (G >> P.oo_b[q])) & 1ull) ? -P.oo_ang[q] : P.oo_ang[q];
-        Q.c_tile = c;
-    } else if (t < kTileBits + 1 + kWalkBits) {
-        const int j = t - kTileBits - 1;
+    } else if (t < kTileBits + kWalkBits) {
+        const int j = t - kTileBits;
         double2 f = make_double2(1.0, 0.0);
         for (int q = 0; q < P.w_out_n[j]; ++q) {
             const double c2 = P.w_out_c2[j][q], s2 = ((G >> P.w_out_other[j][q]) & 1ull) ? -P.w_out_s2[j][q] : P.w_out_s2[j][q];
             f = make_double2(f.x * c2 - f.y * s2, f.x * s2 + f.y * c2);
         }
         Q.f_out[j] = f;
+    } else if (t >= 32 && t < 64) {                                  // one whole warp
+        const int lane = t - 32;
+        double c = 0.0;
+        for (int q = lane; q < P.oo_n; q += 32) c += (((G >> P.oo_a[q]) ^ (G >> P.oo_b[q])) & 1ull) ? -P.oo_ang[q] : P.oo_ang[q];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+        if (lane == 0) Q.c_tile = P.c0 + c;
+    }
+}
+
+// what a thread's part of the phase does not owe to the tile: the angle of the pairs inside the tile at walk bits 0 and the
+// flip factors of the walk bits from their pairs with the thread's own bits -- once per launch, not once per tile
+struct PhaseThread {
+    double a_in;
+    double2 f_in[kWalkBits];
+};
+__device__ __forceinline__ void phase_thread_init(const PhaseTabs& P, PhaseThread& H, const int t) {
+    double a = 0.0;
+    for (int q = 0; q < P.in_n; ++q) a += (((t >> P.in_a[q]) ^ (t >> P.in_b[q])) & 1) ? -P.in_ang[q] : P.in_ang[q];
+    H.a_in = a;
+#pragma unroll
+    for (int j = 0; j < kWalkBits; ++j) {
+        double2 f = make_double2(1.0, 0.0);
+        for (int q = 0; q < P.w_in_n[j]; ++q) {
+            const double c2 = P.w_in_c2[j][q], s2 = ((t >> P.w_in_other[j][q]) & 1) ? -P.w_in_s2[j][q] : P.w_in_s2[j][q];
+            f = make_double2(f.x * c2 - f.y * s2, f.x * s2 + f.y * c2);
+        }
+        H.f_in[j] = f;
     }
 }
 
 // per tile, every thread of the team (t = 0..255 = tile bits 0..7); the tile must have landed, Q must be complete
-__device__ __forceinline__ void phase_apply(const PhaseTabs& P, const PhaseTile& Q, double2* __restrict__ tile, const int t,
-                                            const double scale = 1.0) {
+__device__ __forceinline__ void phase_apply(const PhaseTabs& P, const PhaseTile& Q, const PhaseThread& H, double2* __restrict__ tile,
+                                            const int t, const double scale = 1.0) {
     int e = t;                                                       // walk bits 8..11 start at 0
-    double a = Q.c_tile;
+    double a = Q.c_tile + H.a_in;
 #pragma unroll
     for (int k = 0; k < kTileBits; ++k) a += ((e >> k) & 1) ? -Q.h_field[k] : Q.h_field[k];
-    for (int q = 0; q < P.in_n; ++q) a += (((e >> P.in_a[q]) ^ (e >> P.in_b[q])) & 1) ? -P.in_ang[q] : P.in_ang[q];
     double sn, cs;
     sincos(a, &sn, &cs);
     double2 ph = make_double2(cs * scale, -sn * scale);              // scale * exp(-i a)
-    // flip factor of walk bit j for THIS thread and tile (z_p = +1 form): the outside pairs (f_out) times the pairs with
-    // this thread's own bits -- constant over the walk, so the walk itself is one multiply per flip
+    // flip factor of walk bit j for THIS thread and tile (z_p = +1 form): the outside pairs (f_out, per tile) times the pairs
+    // with this thread's own bits (f_in, per launch) -- constant over the walk, so the walk itself is one multiply per flip
     double2 F[kWalkBits];
 #pragma unroll
     for (int j = 0; j < kWalkBits; ++j) {
-        double2 f = Q.f_out[j];
-        for (int q = 0; q < P.w_in_n[j]; ++q) {
-            const double c2 = P.w_in_c2[j][q], s2 = ((e >> P.w_in_other[j][q]) & 1) ? -P.w_in_s2[j][q] : P.w_in_s2[j][q];
-            f = make_double2(f.x * c2 - f.y * s2, f.x * s2 + f.y * c2);
-        }
-        F[j] = f;
+        const double2 fo = Q.f_out[j], fi = H.f_in[j];
+        F[j] = make_double2(fo.x * fi.x - fo.y * fi.y, fo.x * fi.y + fo.y * fi.x);
     }
     const bool any_ww = P.has_ww != 0;
     {
@@ -417,6 +437,8 @@ __global__ void __launch_bounds__(kThreads, 3) k_slice_rx_tile(double2* __restri
     __syncthreads();
     if (PHASE) phase_setup(PT[0], pa, A, threadIdx.x);
     __syncthreads();
+    PhaseThread PH;
+    if (PHASE) phase_thread_init(PT[0], PH, threadIdx.x);
     const int T = A.T, lo = A.lo, n_el = 1 << T;
     const unsigned lowmask = (1u << lo) - 1u;
     const unsigned long long n_tiles = 1ull << (L - T);
@@ -460,7 +482,7 @@ __global__ void __launch_bounds__(kThreads, 3) k_slice_rx_tile(double2* __restri
         asm volatile("cp.async.wait_group 0;" ::: "memory");
         __syncthreads();
         if (PHASE) {
-            phase_apply(PT[0], PQ, tile, threadIdx.x);
+            phase_apply(PT[0], PQ, PH, tile, threadIdx.x);
             __syncthreads();
         }
         tile_rounds<SCALED>(tile, A.T, A.n_active, A.active, A.c, A.s, threadIdx.x, 0, 1.0);
@@ -554,6 +576,8 @@ __global__ void __launch_bounds__(kTmaThreads, 1) k_slice_rx_tma(const __grid_co
         // ------------------------------ consumer team ----------------------------------------------------------
         const int tid = threadIdx.x - wg * kThreads;
         const double pre = SCALED ? sh.A.post : 1.0;
+        PhaseThread PH;
+        if (PHASE) phase_thread_init(PT[0], PH, tid);
         for (unsigned long long k = (unsigned long long)wg; k < mine; k += kTmaTeams) {
             const int b = (int)(k % kTmaBufs);
             double2* tile = tiles + ((size_t)b << kTileBits12);
@@ -573,7 +597,7 @@ __global__ void __launch_bounds__(kTmaThreads, 1) k_slice_rx_tma(const __grid_co
                 // [rotations left over from the previous step] [phase] [this step's rotations]; the cosine product of both
                 // rotation sets rides on the phase
                 if (sh.A.n_pre) tile_rounds<SCALED>(tile, kTileBits12, sh.A.n_pre, sh.A.pre_active, sh.A.pre_c, sh.A.pre_s, tid, 1 + wg, 1.0);
-                phase_apply(PT[0], PQ[wg], tile, tid, pre);
+                phase_apply(PT[0], PQ[wg], PH, tile, tid, pre);
                 team_bar(1 + wg);
             }
             tile_rounds<SCALED>(tile, kTileBits12, sh.A.n_active, sh.A.active, sh.A.c, sh.A.s, tid, 1 + wg, PHASE ? 1.0 : pre);
