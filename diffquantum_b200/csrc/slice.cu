@@ -879,6 +879,14 @@ EncodeTiledFn slice_encode_fn() {
 struct Scatter { int g, rank; void* const* peer; };
 struct Rot { int bit; double theta; };
 
+// dq_slice_plan: the planner runs for real, the launches are written down instead of made (no device needed)
+struct PlanRec {
+    std::vector<int32_t> rows;      // per launch: step, T, lo, n_pre, phase, n_rot, scatter, mask low 32, mask high 32
+    bool assume_tma;
+    int step;
+};
+thread_local PlanRec* g_rec = nullptr;
+
 // One tile geometry and the rotation targets it carries.  A tile is 2^T amplitudes spanned by T physical bits pos[0] < pos[1] < ...:
 // the `lo` lowest are bits 0 .. lo-1 (contiguous 16 * 2^lo byte runs in global memory), the others are targets.
 struct TileSet {
@@ -988,6 +996,7 @@ bool tma_usable(const TileSet& S, int L) {
     TmaGeom g;
     cuuint64_t dims[5], strides[4];
     cuuint32_t box[5];
+    if (g_rec) return g_rec->assume_tma && tile_geom(S, L, &g, dims, strides, box);
     return !getenv("DQ_SLICE_NO_TMA") && slice_encode_fn() && tile_geom(S, L, &g, dims, strides, box);
 }
 
@@ -1033,6 +1042,12 @@ bool can_carry_phase(const PhaseArgs& h, const TileSet& S, int L, bool pre, bool
 // exchange.  Callers make sure the combination is supported (can_carry_phase).
 int launch_pass(dq_context* ctx, void* psi_dev, int L, const TileSet& S, const std::vector<Rot>& rot, const std::vector<Rot>& pre,
                 const PhaseArgs* d_phase, unsigned long long high_bits, const Scatter* sc) {
+    if (g_rec) {
+        const int32_t row[9] = {g_rec->step, S.T, S.lo, (int32_t)pre.size(), d_phase ? 1 : 0, (int32_t)rot.size(), sc ? 1 : 0,
+                                (int32_t)(S.mask & 0xffffffffull), (int32_t)(S.mask >> 32)};
+        g_rec->rows.insert(g_rec->rows.end(), row, row + 9);
+        return DQ_OK;
+    }
     TileArgs h;
     memset(&h, 0, sizeof(h));
     h.T = S.T;
@@ -1169,9 +1184,9 @@ std::vector<Rot> rots_of(const TileSet& S, const std::vector<Rot>& all) {
 
 // All rotations of a step, every tile set one pass; sc: the last pass carries the exchange.
 int rx_many_impl(dq_context* ctx, void* psi_dev, int L, int count, const int32_t* bits, const double* thetas, const Scatter* sc = nullptr) {
-    DQ_REQUIRE(ctx && psi_dev, "NULL argument");
+    DQ_REQUIRE(g_rec || (ctx && psi_dev), "NULL argument");
     DQ_REQUIRE(L >= 1 && L <= 33, "dq_slice_rx_many: L=%d", L);
-    DQ_TRY(ctx->set_device());
+    if (!g_rec) DQ_TRY(ctx->set_device());
     std::vector<Rot> rot;
     DQ_TRY(sorted_rots("dq_slice_rx_many", L, count, bits, thetas, rot));
     std::vector<int> tb(rot.size());
@@ -1211,9 +1226,19 @@ int step_impl(dq_context* ctx, void* psi_dev, int L, unsigned long long high_bit
         for (size_t k = 0; k < sets.size() && first < 0; ++k)
             if ((int)k != skip && can_carry_phase(*h_phase, sets[k], L, false, only_set_scatters)) first = (int)k;
     }
-    if (first < 0 && h_phase) DQ_TRY(dq_slice_phase(ctx, psi_dev, L, high_bits, n_total, n_zz, pair_bits, angles));
+    if (first < 0 && h_phase) {
+        if (g_rec) {                                              // the stand-alone phase pass
+            const int32_t row[9] = {g_rec->step, 0, 0, 0, 1, 0, 0, 0, 0};
+            g_rec->rows.insert(g_rec->rows.end(), row, row + 9);
+        } else {
+            DQ_TRY(dq_slice_phase(ctx, psi_dev, L, high_bits, n_total, n_zz, pair_bits, angles));
+        }
+    }
     PhaseArgs* d_phase = nullptr;
-    if (first >= 0 && h_phase) DQ_TRY(upload_args(ctx, *h_phase, &d_phase));
+    if (first >= 0 && h_phase) {
+        if (g_rec) d_phase = reinterpret_cast<PhaseArgs*>(sizeof(PhaseArgs));      // never dereferenced
+        else DQ_TRY(upload_args(ctx, *h_phase, &d_phase));
+    }
     // launch order: `first`, then the others; the last one launched carries the exchange
     std::vector<int> order;
     if (first >= 0) order.push_back(first);
@@ -1361,12 +1386,12 @@ int dq_slice_evolve_steps(dq_context* ctx, void* psi_dev, int L, uint64_t high_b
                           const int32_t* pair_bits, int count, const int32_t* bits, int n_steps, const double* angles,
                           int64_t ld_angles, const double* thetas, int64_t ld_thetas) {
     const char* what = "dq_slice_evolve_steps";
-    DQ_REQUIRE(ctx && psi_dev && (n_steps == 0 || (angles && (count == 0 || thetas))), "NULL argument");
+    DQ_REQUIRE((g_rec || (ctx && psi_dev)) && (n_steps == 0 || (angles && (count == 0 || thetas))), "NULL argument");
     DQ_REQUIRE(L >= 1 && L <= 33 && n_total >= L && n_total <= 40 && n_steps >= 0, "%s: L=%d n=%d steps=%d", what, L, n_total, n_steps);
     DQ_REQUIRE((high_bits >> (n_total - L)) == 0, "%s: high_bits do not fit %d global bits", what, n_total - L);
     DQ_REQUIRE(ld_angles >= 1 + n_zz && ld_thetas >= count, "%s: row strides %lld, %lld", what, (long long)ld_angles, (long long)ld_thetas);
     if (n_steps == 0) return DQ_OK;
-    DQ_TRY(ctx->set_device());
+    if (!g_rec) DQ_TRY(ctx->set_device());
     std::vector<std::vector<Rot>> rot(n_steps);
     for (int k = 0; k < n_steps; ++k) DQ_TRY(sorted_rots(what, L, count, bits, thetas + (size_t)k * ld_thetas, rot[k]));
     std::vector<int> tb(rot[0].size());
@@ -1391,6 +1416,7 @@ int dq_slice_evolve_steps(dq_context* ctx, void* psi_dev, int L, uint64_t high_b
         const double* row = angles + (size_t)k * ld_angles;
         DQ_TRY(fill_args(h, n_total, n_zz, pair_bits, row + 1, row[0]));
         int first = -1, skip = -1;
+        if (g_rec) g_rec->step = k;
         if (chain) {
             first = owed >= 0 ? owed : b0;
             skip = k + 1 < n_steps ? (first == b0 ? b1 : b0) : -1;
@@ -1399,6 +1425,25 @@ int dq_slice_evolve_steps(dq_context* ctx, void* psi_dev, int L, uint64_t high_b
                          nullptr, n_total, n_zz, pair_bits, row));
         owed = skip;
     }
+    return DQ_OK;
+}
+
+int dq_slice_plan(int L, int n_total, int n_zz, const int32_t* pair_bits, int count, const int32_t* bits, int n_steps,
+                  int assume_tma, int32_t* rows_out, int64_t rows_cap, int64_t* n_rows_out) {
+    DQ_REQUIRE(n_rows_out && (rows_cap == 0 || rows_out), "NULL argument");
+    DQ_REQUIRE(n_steps >= 0 && n_steps <= 4096 && count >= 0 && count <= 64 && n_zz >= 0 && n_zz <= kMaxPairs, "dq_slice_plan: steps=%d count=%d n_zz=%d", n_steps, count, n_zz);
+    std::vector<double> angles((size_t)std::max(1, n_steps) * (1 + n_zz), 0.01), thetas((size_t)std::max(1, n_steps) * std::max(1, count), 0.1);
+    PlanRec rec;
+    rec.assume_tma = assume_tma != 0;
+    rec.step = 0;
+    g_rec = &rec;
+    const int st = dq_slice_evolve_steps(nullptr, nullptr, L, 0, n_total, n_zz, pair_bits, count, bits, n_steps, angles.data(), 1 + n_zz,
+                                         thetas.data(), std::max(1, count));
+    g_rec = nullptr;
+    if (st != DQ_OK) return st;
+    const int64_t n_rows = (int64_t)rec.rows.size() / 9;
+    *n_rows_out = n_rows;
+    for (int64_t i = 0; i < std::min(n_rows, rows_cap) * 9; ++i) rows_out[i] = rec.rows[(size_t)i];
     return DQ_OK;
 }
 

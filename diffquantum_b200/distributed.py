@@ -24,6 +24,27 @@ from . import _lib
 from .sharding import dist_info
 
 
+def slice_plan(L, n_total, pair_bits, bits, n_steps, assume_tma=True):
+    """The launches dq_slice_evolve_steps would make (dq_slice_plan; host only, no device needed): one row per launch with the
+    fields step, T, lo, n_pre, phase, n_rot, scatter, mask (the tile's physical bits as a Python int)."""
+    pair_bits = np.ascontiguousarray(pair_bits, dtype=np.int32).reshape(-1, 2)
+    bits = np.ascontiguousarray(bits, dtype=np.int32)
+    lib = _lib.load()
+    n_rows = ctypes.c_int64()
+    cap = 4 * (n_steps + 1) * 8 + 16
+    rows = np.zeros((cap, 9), dtype=np.int32)
+    _lib.check(lib.dq_slice_plan(int(L), int(n_total), len(pair_bits), _lib.ptr(pair_bits), len(bits), _lib.ptr(bits), int(n_steps),
+                                 1 if assume_tma else 0, _lib.ptr(rows), cap, ctypes.byref(n_rows)))
+    assert n_rows.value <= cap
+    keys = ("step", "T", "lo", "n_pre", "phase", "n_rot", "scatter")
+    out = []
+    for r in rows[:n_rows.value]:
+        d = {k: int(v) for k, v in zip(keys, r[:7])}
+        d["mask"] = (int(r[7]) & 0xffffffff) | ((int(r[8]) & 0xffffffff) << 32)
+        out.append(d)
+    return out
+
+
 class CudaSliceOps(object):
     """Slice kernels through the C ABI; buffers are torch CUDA tensors (device memory + NCCL only)."""
 

@@ -281,6 +281,13 @@ int dq_slice_step_scatter(dq_context* ctx, void* psi_dev, int L, uint64_t high_b
 int dq_slice_evolve_steps(dq_context* ctx, void* psi_dev, int L, uint64_t high_bits, int n_total, int n_zz,
                           const int32_t* pair_bits, int count, const int32_t* bits, int n_steps, const double* angles,
                           int64_t ld_angles, const double* thetas, int64_t ld_thetas);
+/* The launches dq_slice_evolve_steps would make for n_steps steps on these bits and pairs, written down instead of made (host
+ * only, no device: planning introspection for callers and tests).  9 int32 per launch: step, tile bits T, contiguous low bits lo,
+ * rotations owed to the previous step, 1 if the pass carries the phase, rotations of this step, 1 if it carries an exchange,
+ * the tile's physical-bit mask (low, high word); T = 0: a stand-alone phase pass.  assume_tma: plan as on a device where the
+ * TMA tile kernel is available.  At most rows_cap launches are written, *n_rows_out is the full count. */
+int dq_slice_plan(int L, int n_total, int n_zz, const int32_t* pair_bits, int count, const int32_t* bits, int n_steps,
+                  int assume_tma, int32_t* rows_out, int64_t rows_cap, int64_t* n_rows_out);
 /* CUDA IPC plumbing for the above: a 64-byte handle + byte offset for a device pointer (the handle names the allocation the
  * pointer lives in), and the mapping of such a handle in another process (same or peer device). */
 int dq_ipc_export(dq_context* ctx, void* dev_ptr, void* handle64_out, uint64_t* offset_out);

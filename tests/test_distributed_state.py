@@ -165,6 +165,50 @@ def test_single_rank_bookkeeping_numpy():
     _check(6, 0, 1, NumpySliceOpsStep())
 
 
+def _ring_pairs(n):
+    """ring + chords: degree <= 4, any n"""
+    edges = [(i, (i + 1) % n) for i in range(n)] + [(i, (i + 5) % n) for i in range(0, n, 3)]
+    return np.array([[n - 1 - a, n - 1 - b] for a, b in edges], dtype=np.int32)
+
+
+@pytest.mark.parametrize("n,steps,sets", [(12, 4, 1), (14, 5, 2), (21, 6, 2), (22, 3, 3), (29, 6, 3), (30, 2, 3), (33, 2, 4)])
+def test_chained_pass_plan(n, steps, sets):
+    """The pass planner of dq_slice_evolve_steps (host logic, no device: dq_slice_plan): with the TMA tile kernel every step costs
+    (tile sets - 1) passes, every bit is rotated exactly once per step -- by the step's own passes or, owed, by the first pass
+    of the next step --, every step has exactly one phase and it comes before the step's rotations on the same tile."""
+    plan = distributed.slice_plan(n, n, _ring_pairs(n), list(range(n)), steps)
+    assert len(plan) == (steps * (sets - 1) + 1 if sets > 1 else steps)
+    for k in range(steps):
+        mine = [r for r in plan if r["step"] == k]
+        assert sum(r["phase"] for r in mine) == 1 and mine[0]["phase"] == 1           # the step opens with its phase
+        owed_to_next = sum(r["n_pre"] for r in plan if r["step"] == k + 1)
+        assert sum(r["n_rot"] for r in mine) + owed_to_next == n
+        assert mine[0]["n_pre"] == (0 if k == 0 else n - sum(r["n_rot"] for r in plan if r["step"] == k - 1))
+        assert all(r["n_pre"] == 0 for r in mine[1:])
+    for r in plan:
+        assert r["T"] == 12 and r["lo"] >= 3 and bin(r["mask"]).count("1") == 12 and r["scatter"] == 0
+        assert r["mask"] & ((1 << r["lo"]) - 1) == (1 << r["lo"]) - 1                 # the lo low bits are in the tile
+        assert r["n_rot"] <= 12 - (0 if r["lo"] == 12 else r["lo"])
+    # without the TMA kernel only the contiguous tile can carry the phase and nothing is chained
+    plain = distributed.slice_plan(n, n, _ring_pairs(n), list(range(n)), steps, assume_tma=False)
+    assert len(plain) == steps * sets and all(r["n_pre"] == 0 for r in plain)
+    assert sum(r["phase"] for r in plain) == steps
+
+
+def test_pass_plan_small_and_dense_cases():
+    # below 12 bits no tile can carry the phase: phase pass + one rotation pass per step
+    plan = distributed.slice_plan(10, 10, _ring_pairs(10), list(range(10)), 3)
+    assert [(r["T"], r["phase"], r["n_rot"]) for r in plan] == [(0, 1, 0), (10, 0, 10)] * 3
+    # a qubit with more pairs than the kernel's tables hold (17 > 16): the phase runs as its own pass, no chaining
+    n = 20
+    star = np.array([[0, b] for b in range(1, 18)], dtype=np.int32)
+    plan = distributed.slice_plan(n, n, star, list(range(n)), 2)
+    assert sum(r["phase"] for r in plan) == 2 and all(r["T"] == 0 for r in plan if r["phase"]) and all(r["n_pre"] == 0 for r in plan)
+    # rotations on a subset of the bits: only the tiles that hold targets are launched
+    plan = distributed.slice_plan(24, 24, _ring_pairs(24), [0, 5, 23], 2)
+    assert sum(r["n_rot"] + r["n_pre"] for r in plan) == 6 and len(plan) == 3
+
+
 def test_bad_world_sizes_are_rejected():
     prob = IsingProblem.maxcut(4, [[0, 1], [0, 3], [1, 2], [2, 3]])
     st = distributed.DistributedState(prob, ops=NumpySliceOps())
