@@ -248,8 +248,7 @@ constexpr int kWalkBits = 4, kWalkLo = 8, kTileBits = 12, kMaxIn = 96;
 //   oo_*    pairs with both ends outside the tile -> per tile a constant
 //   w_*     per walk bit j (tile bit 8 + j): exp(2i w) factors of its pairs with thread bits (w_in) and with outside bits (w_out,
 //           per tile folded into ONE factor f_out[j]; z_p = -1 takes its conjugate)
-//   ww      pairs among the walk bits themselves: the Gray sequence is fixed, so the state of the other walk bits at step kk is
-//           known -- one factor per step, the same for every thread and tile
+//   ww      pairs among the walk bits themselves: one factor per value of the walk bits, the same for every thread and tile
 struct PhaseTabs {
     int out_n[kTileBits], w_in_n[kWalkBits], w_out_n[kWalkBits], in_n, oo_n, has_ww;
     unsigned char out_other[kTileBits][kGrayDeg], in_a[kMaxIn], in_b[kMaxIn], oo_a[kMaxPairs], oo_b[kMaxPairs];
@@ -315,26 +314,19 @@ __device__ __forceinline__ void phase_setup(PhaseTabs& P, const PhaseArgs* __res
         P.w_in_n[j] = di;
         P.w_out_n[j] = dout;
     } else if (t >= 32 && t < 32 + (1 << kWalkBits)) {
-        const int kk = t - 32;
+        // pairs among the walk bits themselves: relative to walk value 0 a pair whose two bits differ contributes exp(+2i w)
+        const int w = t - 32;
         double2 f = make_double2(1.0, 0.0);
-        if (kk >= 1) {
-            const int j = __ffs(kk) - 1, p = A.pos[kWalkLo + j];
-            const int before = (kk - 1) ^ ((kk - 1) >> 1);               // Gray code of the previous step = walk bits before this flip
-            const bool zp_neg = ((before >> j) & 1) != 0;
-            for (int e = 0; e < n_zz; ++e) {
-                const int a = pa->a[e], b = pa->b[e];
-                if (a != p && b != p) continue;
-                const int to = tile_bit_of(A, a == p ? b : a);
-                if (to < kWalkLo) continue;
-                double sn, cs;
-                sincos(2.0 * pa->ang[e], &sn, &cs);
-                const bool differ = (((before >> (to - kWalkLo)) & 1) != 0) != zp_neg;
-                const double s2 = differ ? -sn : sn;
-                f = make_double2(f.x * cs - f.y * s2, f.x * s2 + f.y * cs);
-                P.has_ww = 1;
-            }
+        for (int e = 0; e < n_zz; ++e) {
+            const int ta = tile_bit_of(A, pa->a[e]), tb = tile_bit_of(A, pa->b[e]);
+            if (ta < kWalkLo || tb < kWalkLo) continue;
+            P.has_ww = 1;
+            if ((((w >> (ta - kWalkLo)) ^ (w >> (tb - kWalkLo))) & 1) == 0) continue;
+            double sn, cs;
+            sincos(2.0 * pa->ang[e], &sn, &cs);
+            f = make_double2(f.x * cs - f.y * sn, f.x * sn + f.y * cs);
         }
-        P.ww[kk] = f;
+        P.ww[w] = f;
     }
 }
 
@@ -386,43 +378,47 @@ __device__ __forceinline__ void phase_thread_init(const PhaseTabs& P, PhaseThrea
     }
 }
 
-// per tile, every thread of the team (t = 0..255 = tile bits 0..7); the tile must have landed, Q must be complete
+// per tile, every thread of the team (t = 0..255 = tile bits 0..7); the tile must have landed, Q must be complete.
+// The 16 phases of a thread (walk bits 8..11) are a doubling product ph(w) = ph(0) * prod_{j in w} F[j] * ww[w], evaluated depth
+// first (four live partial products): dependency depth 4 instead of the 15-step chain of a Gray-code walk, which left the FP64
+// pipe waiting on its own latency (the phase cost as much as five rotation rounds).
+__device__ __forceinline__ double2 cmul2(const double2 a, const double2 b) {
+    return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
 __device__ __forceinline__ void phase_apply(const PhaseTabs& P, const PhaseTile& Q, const PhaseThread& H, double2* __restrict__ tile,
                                             const int t, const double scale = 1.0) {
-    int e = t;                                                       // walk bits 8..11 start at 0
-    double a = Q.c_tile + H.a_in;
+    double hs[kTileBits];
 #pragma unroll
-    for (int k = 0; k < kTileBits; ++k) a += ((e >> k) & 1) ? -Q.h_field[k] : Q.h_field[k];
+    for (int k = 0; k < kTileBits; ++k) hs[k] = ((t >> k) & 1) ? -Q.h_field[k] : Q.h_field[k];     // walk bits are 0 in t
+    const double a = ((Q.c_tile + H.a_in) + ((hs[0] + hs[1]) + (hs[2] + hs[3]))) + (((hs[4] + hs[5]) + (hs[6] + hs[7])) + ((hs[8] + hs[9]) + (hs[10] + hs[11])));
     double sn, cs;
     sincos(a, &sn, &cs);
-    double2 ph = make_double2(cs * scale, -sn * scale);              // scale * exp(-i a)
-    // flip factor of walk bit j for THIS thread and tile (z_p = +1 form): the outside pairs (f_out, per tile) times the pairs
-    // with this thread's own bits (f_in, per launch) -- constant over the walk, so the walk itself is one multiply per flip
+    const double2 ph = make_double2(cs * scale, -sn * scale);        // scale * exp(-i a)
+    // flip factor of walk bit j for THIS thread and tile (z_j: +1 -> -1, the other walk bits at +1): the outside pairs (f_out,
+    // per tile) times the pairs with this thread's own bits (f_in, per launch)
     double2 F[kWalkBits];
 #pragma unroll
-    for (int j = 0; j < kWalkBits; ++j) {
-        const double2 fo = Q.f_out[j], fi = H.f_in[j];
-        F[j] = make_double2(fo.x * fi.x - fo.y * fi.y, fo.x * fi.y + fo.y * fi.x);
-    }
+    for (int j = 0; j < kWalkBits; ++j) F[j] = cmul2(Q.f_out[j], H.f_in[j]);
     const bool any_ww = P.has_ww != 0;
-    {
-        const double2 v = tile[tslot(e)];
-        tile[tslot(e)] = make_double2(v.x * ph.x - v.y * ph.y, v.x * ph.y + v.y * ph.x);
-    }
 #pragma unroll
-    for (int kk = 1; kk < (1 << kWalkBits); ++kk) {
-        const int j = (kk & 1) ? 0 : ((kk & 2) ? 1 : ((kk & 4) ? 2 : 3));       // lowest set bit of kk (compile time after unrolling)
-        const int before = (kk - 1) ^ ((kk - 1) >> 1);
-        const bool zp_neg = ((before >> j) & 1) != 0;                // z_p before the flip: known from the Gray sequence
-        const double fy = zp_neg ? -F[j].y : F[j].y;
-        ph = make_double2(ph.x * F[j].x - ph.y * fy, ph.x * fy + ph.y * F[j].x);
-        if (any_ww) {
-            const double2 w = P.ww[kk];
-            ph = make_double2(ph.x * w.x - ph.y * w.y, ph.x * w.y + ph.y * w.x);
+    for (int b3 = 0; b3 < 2; ++b3) {
+        const double2 p3 = b3 ? cmul2(ph, F[3]) : ph;
+#pragma unroll
+        for (int b2 = 0; b2 < 2; ++b2) {
+            const double2 p2 = b2 ? cmul2(p3, F[2]) : p3;
+#pragma unroll
+            for (int b1 = 0; b1 < 2; ++b1) {
+                const double2 p1 = b1 ? cmul2(p2, F[1]) : p2;
+#pragma unroll
+                for (int b0 = 0; b0 < 2; ++b0) {
+                    const int w = (b3 << 3) | (b2 << 2) | (b1 << 1) | b0;
+                    double2 q = b0 ? cmul2(p1, F[0]) : p1;
+                    if (any_ww) q = cmul2(q, P.ww[w]);
+                    const int sl = tslot(t | (w << kWalkLo));
+                    tile[sl] = cmul2(tile[sl], q);
+                }
+            }
         }
-        e ^= 1 << (kWalkLo + j);
-        const double2 v = tile[tslot(e)];
-        tile[tslot(e)] = make_double2(v.x * ph.x - v.y * ph.y, v.x * ph.y + v.y * ph.x);
     }
 }
 
@@ -524,7 +520,31 @@ struct TmaShared {
     // teams, so a team that gets to tile k + 3 while the load of tile k is still in flight would fall through its wait.
     volatile unsigned long long seq[kTmaBufs];
     TileArgs A;
+    // the bits a tile does NOT span, as runs of consecutive positions: tile index -> index of the tile's element 0 in a few
+    // shifts (a bit-by-bit deposit over L positions, per thread and tile, was 10 % of the phase pass's stall samples)
+    int n_runs;
+    unsigned char run_in[12], run_w[12], run_out[12];
 };
+__device__ __forceinline__ void deposit_runs(TmaShared& sh, const int L) {       // one thread, once per CTA
+    int n = 0, in = 0;
+    for (int p = 0; p < L;) {
+        if ((sh.A.mask >> p) & 1ull) { ++p; continue; }
+        int w = 0;
+        while (p + w < L && !((sh.A.mask >> (p + w)) & 1ull)) ++w;
+        sh.run_in[n] = (unsigned char)in;
+        sh.run_w[n] = (unsigned char)w;
+        sh.run_out[n] = (unsigned char)p;
+        ++n;
+        in += w;
+        p += w;
+    }
+    sh.n_runs = n;
+}
+__device__ __forceinline__ unsigned long long deposit(const TmaShared& sh, const unsigned long long t) {
+    unsigned long long base = 0;
+    for (int r = 0; r < sh.n_runs; ++r) base |= ((t >> sh.run_in[r]) & ((1ull << sh.run_w[r]) - 1ull)) << sh.run_out[r];
+    return base;
+}
 
 __device__ __forceinline__ unsigned s_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void s_mbar_wait(unsigned long long* bar, unsigned parity) {
@@ -551,10 +571,11 @@ __global__ void __launch_bounds__(kTmaThreads, 1) k_slice_rx_tma(const __grid_co
     double2* tiles = reinterpret_cast<double2*>(smem_raw);
     __shared__ __align__(16) TmaShared sh;
     __shared__ PhaseTabs PT[1];                           // PHASE (contiguous tiles only): see k_slice_rx_tile
-    __shared__ PhaseTile PQ[kTmaTeams];
+    __shared__ PhaseTile PQ[kTmaTeams][2];
     constexpr unsigned kTileBytes = (unsigned)(sizeof(double2) << kTileBits12);
     if (threadIdx.x == 0) {
         sh.A = *ta;
+        deposit_runs(sh, L);
         if (PHASE) PT[0].has_ww = 0;
         for (int b = 0; b < kTmaBufs; ++b) {
             sh.seq[b] = ~0ull;
@@ -577,19 +598,17 @@ __global__ void __launch_bounds__(kTmaThreads, 1) k_slice_rx_tma(const __grid_co
         const int tid = threadIdx.x - wg * kThreads;
         const double pre = SCALED ? sh.A.post : 1.0;
         PhaseThread PH;
-        if (PHASE) phase_thread_init(PT[0], PH, tid);
+        int par = 0;                                                  // which PhaseTile of the team the current tile uses
+        if (PHASE) {
+            phase_thread_init(PT[0], PH, tid);
+            if ((unsigned long long)wg < mine) {
+                if (tid < 64) phase_tile_setup(PT[0], PQ[wg][0], (high << L) | deposit(sh, blockIdx.x + wg * gridDim.x), tid);
+                team_bar(1 + wg);
+            }
+        }
         for (unsigned long long k = (unsigned long long)wg; k < mine; k += kTmaTeams) {
             const int b = (int)(k % kTmaBufs);
             double2* tile = tiles + ((size_t)b << kTileBits12);
-            if (PHASE) {
-                // per-tile constants while the tile is in flight: the tile's index deposited into the bits it does not span
-                unsigned long long base = 0, rest = blockIdx.x + k * gridDim.x;
-                const unsigned long long mask = sh.A.mask;
-                for (int p = 0; p < L; ++p)
-                    if (!((mask >> p) & 1ull)) { base |= (rest & 1ull) << p; rest >>= 1; }
-                phase_tile_setup(PT[0], PQ[wg], (high << L) | base, tid);
-                team_bar(1 + wg);
-            }
             do {
                 s_mbar_wait(&sh.full[b], (unsigned)((k / kTmaBufs) & 1ull));
             } while (sh.seq[b] != k);
@@ -597,8 +616,14 @@ __global__ void __launch_bounds__(kTmaThreads, 1) k_slice_rx_tma(const __grid_co
                 // [rotations left over from the previous step] [phase] [this step's rotations]; the cosine product of both
                 // rotation sets rides on the phase
                 if (sh.A.n_pre) tile_rounds<SCALED>(tile, kTileBits12, sh.A.n_pre, sh.A.pre_active, sh.A.pre_c, sh.A.pre_s, tid, 1 + wg, 1.0);
-                phase_apply(PT[0], PQ[wg], PH, tile, tid, pre);
+                phase_apply(PT[0], PQ[wg][par], PH, tile, tid, pre);
                 team_bar(1 + wg);
+                // the per-tile constants of the team's NEXT tile (its index deposited into the bits the tile does not span),
+                // published by the barriers of the rotation rounds below
+                if (k + kTmaTeams < mine && tid < 64)
+                    phase_tile_setup(PT[0], PQ[wg][par ^ 1], (high << L) | deposit(sh, blockIdx.x + (k + kTmaTeams) * gridDim.x), tid);
+                if (sh.A.n_active == 0) team_bar(1 + wg);
+                par ^= 1;
             }
             tile_rounds<SCALED>(tile, kTileBits12, sh.A.n_active, sh.A.active, sh.A.c, sh.A.s, tid, 1 + wg, PHASE ? 1.0 : pre);
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // this thread's tile writes -> the bulk store
@@ -606,12 +631,9 @@ __global__ void __launch_bounds__(kTmaThreads, 1) k_slice_rx_tma(const __grid_co
         }
     } else if (threadIdx.x == kTmaTeams * kThreads) {
         // ------------------------------ loader -------------------------------------------------------------------
-        const unsigned long long mask = sh.A.mask;
         for (unsigned long long k = 0; k < mine; ++k) {
             const int b = (int)(k % kTmaBufs);
-            unsigned long long base = 0, rest = blockIdx.x + k * gridDim.x;
-            for (int p = 0; p < L; ++p)
-                if (!((mask >> p) & 1ull)) { base |= (rest & 1ull) << p; rest >>= 1; }
+            const unsigned long long base = deposit(sh, blockIdx.x + k * gridDim.x);
             int c[5];
             tma_coords(geom, base, c);
             if (k >= kTmaBufs) s_mbar_wait(&sh.empty[b], (unsigned)(((k / kTmaBufs) - 1ull) & 1ull));   // the store of tile k - 3 has read it
@@ -632,12 +654,9 @@ __global__ void __launch_bounds__(kTmaThreads, 1) k_slice_rx_tma(const __grid_co
         }
     } else if (threadIdx.x == kTmaTeams * kThreads + 32) {
         // ------------------------------ storer -------------------------------------------------------------------
-        const unsigned long long mask = sh.A.mask;
         for (unsigned long long k = 0; k < mine; ++k) {
             const int b = (int)(k % kTmaBufs);
-            unsigned long long base = 0, rest = blockIdx.x + k * gridDim.x;
-            for (int p = 0; p < L; ++p)
-                if (!((mask >> p) & 1ull)) { base |= (rest & 1ull) << p; rest >>= 1; }
+            const unsigned long long base = deposit(sh, blockIdx.x + k * gridDim.x);
             int c[5];
             tma_coords(geom, base, c);
             s_mbar_wait(&sh.done[b], (unsigned)((k / kTmaBufs) & 1ull));
