@@ -375,6 +375,40 @@ def test_chained_steps_equal_step_by_step(n, steps, monkeypatch):
         assert chained == (steps * (sets - 1) + 1 if sets > 1 else steps)
 
 
+@pytest.mark.gpu
+def test_cp_async_fallback_path_agrees_with_the_tma_path(monkeypatch):
+    """DQ_SLICE_NO_TMA=1 routes every pass through k_slice_rx_tile (the kernel that carries exchanges and tile shapes a tensor map
+    cannot express): same results as the TMA tile kernel for rotations, a step with owed rotations and a chained sequence."""
+    from oracle import restate as R
+    n = 18
+    ops = distributed.CudaSliceOps(0)
+    rng = np.random.RandomState(77)
+    edges = R.random_regular_edges(n, seed=n)
+    pair_bits = np.array([[n - 1 - a, n - 1 - b] for a, b in edges], dtype=np.int32)
+    angle_rows = rng.normal(size=(3, 1 + len(edges))) * 0.4
+    theta_rows = rng.uniform(-1.0, 1.0, size=(3, n))
+    bits = list(range(n))
+    host = rng.normal(size=1 << n) + 1j * rng.normal(size=1 << n)
+    host /= np.linalg.norm(host)
+    results = []
+    for no_tma in (False, True):
+        if no_tma:
+            monkeypatch.setenv("DQ_SLICE_NO_TMA", "1")
+        a = ops.alloc(1 << n)
+        ops.from_host(a, host)
+        l0 = ops.ctx.launch_count
+        ops.rx_many(a, n, bits, theta_rows[0])
+        ops.step(a, n, 0, n, pair_bits, angle_rows[0], [15, 16, 17], [0.3, -0.2, 0.9], bits, theta_rows[1])
+        ops.evolve_steps(a, n, 0, n, pair_bits, bits, angle_rows, theta_rows)
+        ops.ctx.synchronize()
+        results.append((ops.to_host(a), ops.ctx.launch_count - l0))
+    monkeypatch.delenv("DQ_SLICE_NO_TMA")
+    (tma, l_tma), (plain, l_plain) = results
+    assert np.abs(tma - plain).max() < 1e-13
+    assert abs(np.linalg.norm(tma) - 1.0) < 1e-12
+    assert l_tma == 2 + 2 + 4 and l_plain == 2 + 3 + 6           # chaining and owed rotations need the TMA tile kernel
+
+
 def _gpu_worker(rank, world, port, n):
     sys.path.insert(0, ROOT)
     import torch
