@@ -883,6 +883,18 @@ def run_b200_arm(a):
                         "exceed DRAM GB/s; `traffic` is the ncu DRAM figure.  The kernel is bound inside the SM (FP64 pipe 46 %, "
                         "shared-memory wavefronts 53 %, their phases do not overlap: profiles/r02_o_fused_ws_ncu_summary.txt), not by HBM: "
                         "`frac` is reported against the HBM peak because that is the contract's denominator"}
+    if achieved and a.config == 3 and (a.n in (None, 20)):
+        # the limits that do apply at n = 20: per 64 KiB tile (128 KiB algorithmic) 3 545 cycles of FP64 pipe
+        # (52 DFMA per amplitude and step at one warp-wide DFMA per 2.24 cycles and sub-partition) and 4 570 cycles of
+        # shared-memory pipe (three register<->shared exchanges, the TMA load and store, 10 % bank conflicts), 148 SMs at the
+        # SM clock sampled during the run
+        mhz = (clk or {}).get("sm_mhz") or 1965.0
+        per_tile = 148 * 131072.0 * mhz * 1e6 / 1e9
+        roofline["sm_co_limits"] = {
+            "fp64_pipe_GBs": per_tile / 3545.0, "shared_memory_pipe_GBs": per_tile / 4570.0,
+            "frac_of_fp64_pipe": achieved / (per_tile / 3545.0), "frac_of_shared_memory_pipe": achieved / (per_tile / 4570.0),
+            "source": "profiles/r02_o_fused_ws_ncu_summary.txt (instruction and wavefront counts per tile), "
+                      "profiles/r02_al_fp64_lsu_overlap_microbench.txt (the two pipes overlap across warps: 88 % of the slower one)"}
 
     line = {
         "metric": metric_of(a)[0], "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
