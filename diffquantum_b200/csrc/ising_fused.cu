@@ -1067,7 +1067,8 @@ struct WsSlot {                     // one per tile buffer; written by the loade
     int p, g, t_id, grp;
     int stop;                       // 1: no more tiles for the team that receives this buffer
     unsigned item;                  // raw work-item index (DQ_TRACE builds index the trace with it)
-    int pad_[2];
+    unsigned tile_idx;              // the tile's part of the ten phase-table indices (see ws_pack_idx), formed by the loader
+    int pad_;
     double2 tc[4];                  // base-phase column entries of this tile (bulk-copied from the column table)
 };
 struct WsShared {
@@ -1076,7 +1077,24 @@ struct WsShared {
     double red[kBufs][kTeamThreads / 32];
     double red2[kBufs][kTeamThreads / 32];
     unsigned math_lock[kTeamThreads / 32];      // see math_acquire
+    unsigned thread_idx[2][kTeamThreads];       // per pass type: a team thread's part of the ten phase-table indices
 };
+
+// The phase of a step looks up ten small tables (fj[5], xk[5]) with 3-bit indices gathered from up to three physical bits of the
+// amplitude index xJ = tile part | thread part.  Bit gathering is linear over OR and the two parts share no bit, so each part is
+// gathered once -- the thread part per launch (ws.thread_idx), the tile part per tile by the loader (WsSlot::tile_idx) -- and
+// packed 3 bits per table: fj[k] at bit 3k, xk[m] at bit 15 + 3m.  The consumers then form an index with one shift and one
+// AND instead of ~20 instructions and six constant-bank loads (the ten gathers were 4 % of the kernel's instructions, all of
+// them on the latency chain at the head of the phase section).
+__device__ __forceinline__ unsigned ws_pack_idx(const TypeGeom& T, const size_t x) {
+    unsigned packed = 0;
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+        packed |= (unsigned)gather3(x, T.fj_pos[k], T.fj_msk[k]) << (3 * k);
+        packed |= (unsigned)gather3(x, T.xk_pos[k], T.xk_msk[k]) << (15 + 3 * k);
+    }
+    return packed;
+}
 constexpr int kWsThreads = 384;
 constexpr int kWsConsumerRegs = 232, kWsProducerRegs = 40;     // 2 x 128 x 232 + 128 x 40 = 64512 <= 65536
 
@@ -1204,25 +1222,26 @@ __device__ __forceinline__ void ws_tile(const LaunchArgs& A, WsShared& ws, const
             }
         } else if (r == 2) {
             // ---- phase of the new step (the J1 rotations are done) ------------------------------------------
-            const int t_id = S.t_id;
-            const size_t tbase = ((size_t)(t_id & ((1 << T.tid_lo_bits) - 1)) << T.a) | ((size_t)(t_id >> T.tid_lo_bits) << T.high_end);
-            const size_t xJ = tbase + ((size_t)(iJ & T.lowmask) | ((size_t)(iJ >> T.a) << T.start));
+            const unsigned idx = ws.thread_idx[type][tid] | S.tile_idx;          // ten 3-bit table indices (ws_pack_idx)
             const int kb = type == 0 ? G0::kbits(iJ) : G1::kbits(iJ);
             c128 phi = cmul(S.tc[(iJ >> (type == 0 ? G0::spare_shift : G1::spare_shift)) & 3], P.tkk[kb]);
 #pragma unroll
             for (int m = 0; m < 5; ++m) {
                 if (T.xk_msk[m][0]) {            // launch-uniform
-                    c128 w = P.xk[m][gather3(xJ, T.xk_pos[m], T.xk_msk[m])];
+                    c128 w = P.xk[m][(idx >> (15 + 3 * m)) & 7u];
                     if ((kb >> m) & 1) w.y = -w.y;
                     phi = cmul(phi, w);
                 }
             }
             c128 F[5];
 #pragma unroll
-            for (int k = 0; k < 5; ++k) F[k] = P.fj[k][gather3(xJ, T.fj_pos[k], T.fj_msk[k])];
+            for (int k = 0; k < 5; ++k) F[k] = P.fj[k][(idx >> (3 * k)) & 7u];
             if (S.p == 0) {
                 const KetDesc* __restrict__ kd = skets + S.g;
                 if (kd->shift_kind == 0) {       // ZZ shift gate exp(i sigma alpha z0 z1); never both operands in J
+                    const int t_id = S.t_id;
+                    const size_t tbase = ((size_t)(t_id & ((1 << T.tid_lo_bits) - 1)) << T.a) | ((size_t)(t_id >> T.tid_lo_bits) << T.high_end);
+                    const size_t xJ = tbase + ((size_t)(iJ & T.lowmask) | ((size_t)(iJ >> T.a) << T.start));
                     const int tb0 = tile_bit_of(kd->sb0), tb1 = tile_bit_of(kd->sb1);
                     const double sigma = kd->sigma;
                     const int j0b = type == 0 ? G0::jslot(tb0) : G1::jslot(tb0);
@@ -1344,25 +1363,26 @@ __device__ __forceinline__ void ws_tile(const LaunchArgs& A, WsShared& ws, const
             }
         } else if (r == 2) {
             // ---- phase of the new step (the J1 rotations are done) ------------------------------------------
-            const int t_id = S.t_id;
-            const size_t tbase = ((size_t)(t_id & ((1 << T.tid_lo_bits) - 1)) << T.a) | ((size_t)(t_id >> T.tid_lo_bits) << T.high_end);
-            const size_t xJ = tbase + ((size_t)(iJ & T.lowmask) | ((size_t)(iJ >> T.a) << T.start));
+            const unsigned idx = ws.thread_idx[type][tid] | S.tile_idx;          // ten 3-bit table indices (ws_pack_idx)
             const int kb = type == 0 ? G0::kbits(iJ) : G1::kbits(iJ);
             c128 phi = cmul(S.tc[(iJ >> (type == 0 ? G0::spare_shift : G1::spare_shift)) & 3], P.tkk[kb]);
 #pragma unroll
             for (int m = 0; m < 5; ++m) {
                 if (T.xk_msk[m][0]) {            // launch-uniform
-                    c128 w = P.xk[m][gather3(xJ, T.xk_pos[m], T.xk_msk[m])];
+                    c128 w = P.xk[m][(idx >> (15 + 3 * m)) & 7u];
                     if ((kb >> m) & 1) w.y = -w.y;
                     phi = cmul(phi, w);
                 }
             }
             c128 F[5];
 #pragma unroll
-            for (int k = 0; k < 5; ++k) F[k] = P.fj[k][gather3(xJ, T.fj_pos[k], T.fj_msk[k])];
+            for (int k = 0; k < 5; ++k) F[k] = P.fj[k][(idx >> (3 * k)) & 7u];
             if (S.p == 0) {
                 const KetDesc* __restrict__ kd = skets + S.g;
                 if (kd->shift_kind == 0) {       // ZZ shift gate exp(i sigma alpha z0 z1); never both operands in J
+                    const int t_id = S.t_id;
+                    const size_t tbase = ((size_t)(t_id & ((1 << T.tid_lo_bits) - 1)) << T.a) | ((size_t)(t_id >> T.tid_lo_bits) << T.high_end);
+                    const size_t xJ = tbase + ((size_t)(iJ & T.lowmask) | ((size_t)(iJ >> T.a) << T.start));
                     const int tb0 = tile_bit_of(kd->sb0), tb1 = tile_bit_of(kd->sb1);
                     const double sigma = kd->sigma;
                     const int j0b = type == 0 ? G0::jslot(tb0) : G1::jslot(tb0);
@@ -1522,6 +1542,15 @@ __global__ void __launch_bounds__(kWsThreads, 1) k_fused_ws(const __grid_constan
         int4* dst = reinterpret_cast<int4*>(skets);
         for (int i = threadIdx.x; i < A.n_kets * (int)(sizeof(KetDesc) / 16); i += kWsThreads) dst[i] = __ldg(src + i);
     }
+    if (threadIdx.x < kTeamThreads) {             // the same for both teams
+        const int tid = threadIdx.x;
+#pragma unroll
+        for (int type = 0; type < 2; ++type) {
+            const TypeGeom& T = A.geom[type];
+            const int iJ = type == 0 ? Geo<0>::baseJ(tid) : Geo<1>::baseJ(tid);
+            ws.thread_idx[type][tid] = ws_pack_idx(T, (size_t)(iJ & T.lowmask) | ((size_t)(iJ >> T.a) << T.start));
+        }
+    }
     __syncthreads();                              // the last CTA-wide barrier: the roles part ways here
     const unsigned total = ((unsigned)A.max_pass * (unsigned)A.group * (unsigned)A.n_groups) << A.ipp_log2;
     const int wg = threadIdx.x / kTeamThreads;
@@ -1600,6 +1629,10 @@ __global__ void __launch_bounds__(kWsThreads, 1) k_fused_ws(const __grid_constan
                 S.item = I.item;
                 S.stop = 0;
                 const int type = (I.p + kd->cls) & 1;
+                {
+                    const TypeGeom& T = A.geom[type];
+                    S.tile_idx = ws_pack_idx(T, ((size_t)(I.t_id & ((1 << T.tid_lo_bits) - 1)) << T.a) | ((size_t)(I.t_id >> T.tid_lo_bits) << T.high_end));
+                }
                 const CUtensorMap* map = A.maps + 2 * (I.p == 0 ? kd->map_src : kd->map_buf) + type;
                 c128* tile = tiles + (size_t)b * kTile;
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
