@@ -81,6 +81,8 @@ SIGNATURES = {
                                              ctypes.c_int, _VP, ctypes.c_int, _VP, ctypes.c_int64, _VP, ctypes.c_int64]),
     "dq_slice_plan": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_int, _VP, ctypes.c_int, _VP, ctypes.c_int, ctypes.c_int,
                                      _VP, ctypes.c_int64, ctypes.POINTER(ctypes.c_int64)]),
+    "dq_slice_plan_step": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_int, _VP, ctypes.c_int, _VP, ctypes.c_int, _VP,
+                                          ctypes.c_int, ctypes.c_int, _VP, ctypes.c_int64, ctypes.POINTER(ctypes.c_int64)]),
     "dq_ipc_export": (ctypes.c_int, [_VP, _VP, _VP, ctypes.POINTER(ctypes.c_uint64)]),
     "dq_ipc_open": (ctypes.c_int, [_VP, _VP, ctypes.c_uint64, ctypes.POINTER(_VP)]),
     "dq_ipc_close": (ctypes.c_int, [_VP, _VP, ctypes.c_uint64]),

@@ -1346,10 +1346,10 @@ int dq_ipc_close(dq_context* ctx, void* ptr, uint64_t offset) {
 static int slice_step(const char* what, dq_context* ctx, void* psi_dev, int L, uint64_t high_bits, int n_total, int n_zz,
                       const int32_t* pair_bits, const double* angles, int n_pre, const int32_t* pre_bits, const double* pre_thetas,
                       int count, const int32_t* bits, const double* thetas, const Scatter* sc) {
-    DQ_REQUIRE(ctx && psi_dev && angles, "NULL argument");
+    DQ_REQUIRE((g_rec || (ctx && psi_dev)) && angles, "NULL argument");
     DQ_REQUIRE(L >= 1 && L <= 33 && n_total >= L && n_total <= 40, "%s: L=%d n=%d", what, L, n_total);
     DQ_REQUIRE((high_bits >> (n_total - L)) == 0, "%s: high_bits do not fit %d global bits", what, n_total - L);
-    DQ_TRY(ctx->set_device());
+    if (!g_rec) DQ_TRY(ctx->set_device());
     std::vector<Rot> pre, rot;
     DQ_TRY(sorted_rots(what, L, n_pre, pre_bits, pre_thetas, pre));
     DQ_TRY(sorted_rots(what, L, count, bits, thetas, rot));
@@ -1458,6 +1458,29 @@ int dq_slice_plan(int L, int n_total, int n_zz, const int32_t* pair_bits, int co
     g_rec = &rec;
     const int st = dq_slice_evolve_steps(nullptr, nullptr, L, 0, n_total, n_zz, pair_bits, count, bits, n_steps, angles.data(), 1 + n_zz,
                                          thetas.data(), std::max(1, count));
+    g_rec = nullptr;
+    if (st != DQ_OK) return st;
+    const int64_t n_rows = (int64_t)rec.rows.size() / 9;
+    *n_rows_out = n_rows;
+    for (int64_t i = 0; i < std::min(n_rows, rows_cap) * 9; ++i) rows_out[i] = rec.rows[(size_t)i];
+    return DQ_OK;
+}
+
+int dq_slice_plan_step(int L, int n_total, int n_zz, const int32_t* pair_bits, int n_pre, const int32_t* pre_bits, int count,
+                       const int32_t* bits, int scatter_g, int assume_tma, int32_t* rows_out, int64_t rows_cap, int64_t* n_rows_out) {
+    DQ_REQUIRE(n_rows_out && (rows_cap == 0 || rows_out), "NULL argument");
+    DQ_REQUIRE(n_pre >= 0 && n_pre <= 64 && count >= 0 && count <= 64 && n_zz >= 0 && n_zz <= kMaxPairs && scatter_g >= 0 &&
+               (1 << scatter_g) <= kMaxPeers, "dq_slice_plan_step: n_pre=%d count=%d n_zz=%d g=%d", n_pre, count, n_zz, scatter_g);
+    std::vector<double> angles((size_t)1 + n_zz, 0.01), thetas((size_t)std::max(1, count), 0.1), pre_thetas((size_t)std::max(1, n_pre), 0.2);
+    void* peers[kMaxPeers];
+    for (int j = 0; j < kMaxPeers; ++j) peers[j] = &peers[0];          // never dereferenced
+    Scatter sc{scatter_g, 0, peers};
+    PlanRec rec;
+    rec.assume_tma = assume_tma != 0;
+    rec.step = 0;
+    g_rec = &rec;
+    const int st = slice_step("dq_slice_plan_step", nullptr, nullptr, L, 0, n_total, n_zz, pair_bits, angles.data(), n_pre, pre_bits,
+                              pre_thetas.data(), count, bits, thetas.data(), scatter_g > 0 ? &sc : nullptr);
     g_rec = nullptr;
     if (st != DQ_OK) return st;
     const int64_t n_rows = (int64_t)rec.rows.size() / 9;

@@ -45,6 +45,25 @@ def slice_plan(L, n_total, pair_bits, bits, n_steps, assume_tma=True):
     return out
 
 
+def slice_plan_step(L, n_total, pair_bits, pre_bits, bits, scatter_g=0, assume_tma=True):
+    """The launches of ONE step of a distributed slice (dq_slice_plan_step; host only): rows as in slice_plan."""
+    pair_bits = np.ascontiguousarray(pair_bits, dtype=np.int32).reshape(-1, 2)
+    pre_bits = np.ascontiguousarray(pre_bits, dtype=np.int32)
+    bits = np.ascontiguousarray(bits, dtype=np.int32)
+    n_rows = ctypes.c_int64()
+    rows = np.zeros((64, 9), dtype=np.int32)
+    _lib.check(_lib.load().dq_slice_plan_step(int(L), int(n_total), len(pair_bits), _lib.ptr(pair_bits), len(pre_bits),
+                                              _lib.ptr(pre_bits), len(bits), _lib.ptr(bits), int(scatter_g), 1 if assume_tma else 0,
+                                              _lib.ptr(rows), len(rows), ctypes.byref(n_rows)))
+    keys = ("step", "T", "lo", "n_pre", "phase", "n_rot", "scatter")
+    out = []
+    for r in rows[:n_rows.value]:
+        d = {k: int(v) for k, v in zip(keys, r[:7])}
+        d["mask"] = (int(r[7]) & 0xffffffff) | ((int(r[8]) & 0xffffffff) << 32)
+        out.append(d)
+    return out
+
+
 class CudaSliceOps(object):
     """Slice kernels through the C ABI; buffers are torch CUDA tensors (device memory + NCCL only)."""
 

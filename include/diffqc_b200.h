@@ -288,6 +288,10 @@ int dq_slice_evolve_steps(dq_context* ctx, void* psi_dev, int L, uint64_t high_b
  * TMA tile kernel is available.  At most rows_cap launches are written, *n_rows_out is the full count. */
 int dq_slice_plan(int L, int n_total, int n_zz, const int32_t* pair_bits, int count, const int32_t* bits, int n_steps,
                   int assume_tma, int32_t* rows_out, int64_t rows_cap, int64_t* n_rows_out);
+/* The same for ONE step of a distributed slice (dq_slice_step / dq_slice_step_scatter): rotations owed on pre_bits, the phase,
+ * rotations on bits, and -- scatter_g > 0 -- the exchange with 2^scatter_g ranks on the last launch. */
+int dq_slice_plan_step(int L, int n_total, int n_zz, const int32_t* pair_bits, int n_pre, const int32_t* pre_bits, int count,
+                       const int32_t* bits, int scatter_g, int assume_tma, int32_t* rows_out, int64_t rows_cap, int64_t* n_rows_out);
 /* CUDA IPC plumbing for the above: a 64-byte handle + byte offset for a device pointer (the handle names the allocation the
  * pointer lives in), and the mapping of such a handle in another process (same or peer device). */
 int dq_ipc_export(dq_context* ctx, void* dev_ptr, void* handle64_out, uint64_t* offset_out);

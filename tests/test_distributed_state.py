@@ -209,6 +209,27 @@ def test_pass_plan_small_and_dense_cases():
     assert sum(r["n_rot"] + r["n_pre"] for r in plan) == 6 and len(plan) == 3
 
 
+def test_distributed_step_plan():
+    """One step of the n = 32 state on 8 ranks (L = 29, the three qubits swapped in by the last exchange owed): three launches --
+    the owed rotations, the phase and 8 rotations on the tile that holds the top bits; 9 rotations; the contiguous tile carrying
+    the exchange.  Without owed rotations and without the TMA kernel the step degrades gracefully."""
+    n, L, g = 32, 29, 3
+    pairs = _ring_pairs(n)
+    plan = distributed.slice_plan_step(L, n, pairs, [26, 27, 28], list(range(L)), scatter_g=g)
+    assert [(r["n_pre"], r["phase"], r["n_rot"], r["scatter"]) for r in plan] == [(3, 1, 8, 0), (0, 0, 9, 0), (0, 0, 12, 1)]
+    assert plan[0]["mask"] >> 21 == 0xff and plan[2]["lo"] == 12 and plan[2]["mask"] == 0xfff
+    first = distributed.slice_plan_step(L, n, pairs, [], list(range(L)), scatter_g=g)           # the very first step: nothing owed
+    assert len(first) == 3 and first[0]["phase"] == 1 and first[-1]["scatter"] == 1 and sum(r["n_rot"] for r in first) == L
+    plain = distributed.slice_plan_step(L, n, pairs, [26, 27, 28], list(range(L)), scatter_g=g, assume_tma=False)
+    # cp.async kernels only: the owed rotations as a pass of their own, the phase on the contiguous tile, the exchange last
+    assert [(r["n_pre"], r["phase"], r["scatter"]) for r in plain] == [(0, 0, 0), (0, 1, 0), (0, 0, 0), (0, 0, 1)]
+    assert plain[0]["n_rot"] == 3 and sum(r["n_rot"] for r in plain[1:]) == L
+    # owed bits spread over two tiles (L = 13: bits 10, 11 in the contiguous tile, bit 12 alone): a pass of their own each
+    spread = distributed.slice_plan_step(13, 16, _ring_pairs(16), [10, 11, 12], list(range(13)), scatter_g=3)
+    assert sum(r["n_pre"] for r in spread) == 0 and sum(r["phase"] for r in spread) == 1 and spread[-1]["scatter"] == 1
+    assert sum(r["n_rot"] for r in spread) == 3 + 13
+
+
 def test_bad_world_sizes_are_rejected():
     prob = IsingProblem.maxcut(4, [[0, 1], [0, 3], [1, 2], [2, 3]])
     st = distributed.DistributedState(prob, ops=NumpySliceOps())
