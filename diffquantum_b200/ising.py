@@ -125,9 +125,12 @@ class IsingProblem(object):
         rows = np.zeros((K, self.row_len))
         rows[:, 0] = self.h0_const
         rows[:, 1:1 + self.n_zz] = self.h0_zz[None, :]
-        for i in range(len(self.terms)):
-            col = (1 + self.term_index[i]) if self.term_kind[i] == 0 else (1 + self.n_zz + self.term_index[i])
-            rows[:, col] += u[:, i]
+        cols = np.where(self.term_kind == 0, 1 + self.term_index, 1 + self.n_zz + self.term_index)
+        if len(np.unique(cols)) == len(cols):
+            rows[:, cols] += u                     # every column takes one pulse: one indexed add, the same additions
+        else:
+            for i in range(len(self.terms)):       # several controls on one pair / qubit: summed in list order
+                rows[:, cols[i]] += u[:, i]
         return rows * dt
 
     def trajectory_rows(self, coeff, T0, T1, per_step, basis='BSpline'):

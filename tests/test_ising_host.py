@@ -167,3 +167,27 @@ def test_interleaved_commuting_order_matches_oracle_semantics():
             v = psi.reshape(1 << q, 2, -1)
             psi = np.stack([np.cos(th) * v[:, 0] - 1j * np.sin(th) * v[:, 1], np.cos(th) * v[:, 1] - 1j * np.sin(th) * v[:, 0]], axis=1).reshape(-1)
     np.testing.assert_allclose(psi, want, atol=1e-14)
+
+
+def test_angle_rows_indexed_add_equals_the_term_loop():
+    """IsingProblem.angle_rows adds every pulse column with one indexed add when no two controls share a pair / qubit; same bits
+    as the term-by-term loop, which stays for repeated controls."""
+    import numpy as np
+    from diffquantum_b200.ising import IsingProblem
+    from oracle import restate as R
+
+    def loop(p, u, dt):
+        rows = np.zeros((u.shape[0], p.row_len))
+        rows[:, 0] = p.h0_const
+        rows[:, 1:1 + p.n_zz] = p.h0_zz[None, :]
+        for i in range(len(p.terms)):
+            col = (1 + p.term_index[i]) if p.term_kind[i] == 0 else (1 + p.n_zz + p.term_index[i])
+            rows[:, col] += u[:, i]
+        return rows * dt
+
+    prob = IsingProblem.maxcut(12, R.random_regular_edges(12, seed=3))
+    u = np.random.default_rng(1).normal(size=(37, len(prob.terms)))
+    assert np.array_equal(loop(prob, u, 0.013), prob.angle_rows(u, 0.013))
+    rep = IsingProblem(4, [('zz', 0, 1), ('x', 0), ('x', 0), ('x', 1)], [1.0, 0.5, 0.25, 2.0], 1.0)
+    u = np.random.default_rng(2).normal(size=(5, 4))
+    assert np.array_equal(loop(rep, u, 0.1), rep.angle_rows(u, 0.1))
